@@ -1,0 +1,87 @@
+"""ctypes loader for libopadpo_b200.so (the C ABI declared in include/opadpo_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the CUDA library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libopadpo_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_lib = None
+
+
+class OpadpoError(RuntimeError):
+    pass
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libopadpo_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(max(1, (os.cpu_count() or 2)))]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise OpadpoError("building libopadpo_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K1", ctypes.c_int32), ("K2", ctypes.c_int32),
+        ("a_mn_major", ctypes.c_int32), ("b_mn_major", ctypes.c_int32),
+        ("A1", ctypes.c_void_p), ("lda1", ctypes.c_int64),
+        ("B1", ctypes.c_void_p), ("ldb1", ctypes.c_int64),
+        ("A2", ctypes.c_void_p), ("lda2", ctypes.c_int64),
+        ("B2", ctypes.c_void_p), ("ldb2", ctypes.c_int64),
+        ("a2_group_n", ctypes.c_int32), ("a2_group_stride", ctypes.c_int32),
+        ("splits", ctypes.c_int32), ("epilogue", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
+        ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+        ("bias", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64),
+        ("act", ctypes.c_int32),
+        ("labels", ctypes.c_void_p),
+        ("lse_partials", ctypes.c_void_p),
+        ("label_logit", ctypes.c_void_p),
+        ("lse", ctypes.c_void_p),
+        ("dlp", ctypes.c_void_p),
+        ("max_ctas", ctypes.c_int32),
+    ]
+
+
+def _declare(lib):
+    lib.opadpo_last_error.restype = ctypes.c_char_p
+    lib.opadpo_abi_version.restype = ctypes.c_int
+    lib.opadpo_gemm_n_tiles.argtypes = [ctypes.c_int32]
+    lib.opadpo_gemm_n_tiles.restype = ctypes.c_int
+    lib.opadpo_op_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
+    lib.opadpo_op_gemm.restype = ctypes.c_int
+
+
+def load(build_if_missing: bool = False):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            build_library()
+        else:
+            raise OpadpoError(
+                f"{LIB_PATH} is missing: the CUDA extension is the only implementation of the hot path "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().opadpo_last_error()
+        raise OpadpoError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

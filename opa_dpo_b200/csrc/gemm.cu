@@ -1,0 +1,538 @@
+// Persistent, warp-specialised tcgen05 GEMM (sm_100a). See gemm.h for the math and DESIGN.md for the layout.
+//
+//   warp 0 : TMA producer (one elected lane)          global -> 128B-swizzled smem ring (4 stages x 48 KB)
+//   warp 1 : MMA issuer   (one elected lane)          tcgen05.mma 128x256x16, fp32 accumulators in TMEM
+//   warp 2 : TMEM allocator (512 columns = 2 accumulator buffers, so epilogue(i) overlaps mainloop(i+1))
+//   warps 4-7 : epilogue, one thread per accumulator row (TMEM lane), tcgen05.ld 32 columns at a time
+#include "gemm.h"
+
+#include <cstdio>
+
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace opadpo {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int GROUP_M = 16;  // tile rasterisation: 16 m-blocks share each B panel while it is L2-hot
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct KParams {
+  int M, N;
+  int kb1, kb2;
+  int a2_group_n, a2_group_stride;
+  int splits, kb_per_split;
+  int num_m, num_n, num_tiles;
+  float alpha;
+  void* C;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+  int act;
+  const int32_t* labels;
+  float4* lse_partials;
+  float* label_logit;
+  const float* lse;
+  const float* dlp;
+};
+
+struct Tile {
+  int m_blk, n_blk, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ Tile decode_tile(const KParams& p, int tile) {
+  const int tiles_mn = p.num_m * p.num_n;
+  const int split = tile / tiles_mn;
+  const int t = tile - split * tiles_mn;
+  const int per_group = GROUP_M * p.num_n;
+  const int group = t / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(GROUP_M, p.num_m - first_m);
+  const int r = t - group * per_group;
+  Tile o;
+  o.m_blk = first_m + r % gsize;
+  o.n_blk = r / gsize;
+  if (p.splits == 1) {
+    o.kb_begin = 0;
+    o.kb_end = p.kb1 + p.kb2;
+  } else {
+    o.kb_begin = split * p.kb_per_split;
+    o.kb_end = min(p.kb1, o.kb_begin + p.kb_per_split);
+  }
+  return o;
+}
+
+__device__ __forceinline__ float act_fn(float x, int act) {
+  if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (act == ACT_QUICK_GELU) return x / (1.f + __expf(-1.702f * x));
+  return x;
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmA1);
+      ptx::prefetch_tmap(&tmB1);
+      ptx::prefetch_tmap(&tmA2);
+      ptx::prefetch_tmap(&tmB2);
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        ptx::mbar_init(&full_bar[i], 1);
+        ptx::mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&tfull_bar[i], 1);
+        ptx::mbar_init(&tempty_bar[i], 4);
+      }
+      ptx::fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const Tile t = decode_tile(p, tile);
+        const int m0 = t.m_blk * BM, n0 = t.n_blk * BN;
+        const int a2off = p.a2_group_n > 0 ? (n0 / p.a2_group_n) * p.a2_group_stride : 0;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const bool seg2 = kb >= p.kb1;
+          const CUtensorMap* ma = seg2 ? &tmA2 : &tmA1;
+          const CUtensorMap* mb = seg2 ? &tmB2 : &tmB1;
+          const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          if (!A_MN) {
+            ptx::tma_load_2d(sA, ma, &full_bar[stage], k0 + (seg2 ? a2off : 0), m0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) ptx::tma_load_2d(sA + g * 8192, ma, &full_bar[stage], m0 + g * 64, k0);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sB + g * 8192, mb, &full_bar[stage], n0 + g * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const Tile t = decode_tile(p, tile);
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                        : ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                        : ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+            ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+          ptx::mma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::mma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (thread == accumulator row)
+    const int quad = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const Tile t = decode_tile(p, tile);
+      const int m0 = t.m_blk * BM, n0 = t.n_blk * BN;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
+      if constexpr (EPI == EPI_BF16) {
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+        const __nv_bfloat16* rrow = p.residual ? p.residual + static_cast<int64_t>(row) * p.ldr : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (col0 + 32 <= p.N) {
+            if (p.bias) {
+              const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = __ldg(b4 + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] += f.x;
+                  v[q * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fn(v[j], p.act);
+            }
+            if (rrow) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(rrow + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = __ldg(r4 + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  v[q * 8 + e * 2] += f.x;
+                  v[q * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < p.N) {
+                float x = v[j];
+                if (p.bias) x += __bfloat162float(p.bias[col]);
+                x = act_fn(x, p.act);
+                if (rrow) x += __bfloat162float(rrow[col]);
+                crow[col] = __float2bfloat16(x);
+              }
+            }
+          }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_F32_ATOMIC) {
+        float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < p.N) {
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(crow + col0 + j, __uint_as_float(r[j]) * p.alpha, __uint_as_float(r[j + 1]) * p.alpha,
+                         __uint_as_float(r[j + 2]) * p.alpha, __uint_as_float(r[j + 3]) * p.alpha);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]) * p.alpha);
+          }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_LSE) {
+        // Online log-sum-exp over this tile's columns, in base 2 (z2 = z*log2e).
+        const int label = row_ok ? p.labels[row] : -1;
+        float mx = -INFINITY, s = 0.f, zs = 0.f;
+        const float a2 = p.alpha * LOG2E;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (col0 < p.N) {
+          const int nvalid = min(32, p.N - col0);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]) * a2);
+          const float nm = fmaxf(mx, cm);
+          const float sc = exp2f(mx - nm);  // mx=-inf -> 0
+          s *= sc;
+          zs *= sc;
+          mx = nm;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              const float z2 = __uint_as_float(r[j]) * a2;
+              const float e = exp2f(z2 - mx);
+              s += e;
+              zs += z2 * e;
+              if (col0 + j == label) p.label_logit[row] = __uint_as_float(r[j]) * p.alpha;
+            }
+          }
+          }
+          __syncwarp();
+        }
+        if (row_ok) p.lse_partials[static_cast<int64_t>(row) * p.num_n + t.n_blk] = make_float4(mx, s, zs, 0.f);
+      } else if constexpr (EPI == EPI_CEGRAD) {
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+        const int label = row_ok ? p.labels[row] : -1;
+        const float g = row_ok ? p.dlp[row] * p.alpha : 0.f;
+        const float lse2 = row_ok ? p.lse[row] * LOG2E : 0.f;
+        const float a2 = p.alpha * LOG2E;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = (g != 0.f) ? exp2f(__uint_as_float(r[j]) * a2 - lse2) : 0.f;
+            v[j] = g * ((col0 + j == label ? 1.f : 0.f) - pr);
+          }
+          if (col0 + 32 <= p.N) {
+            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = __float2bfloat16(v[j]);
+          }
+          }
+          __syncwarp();
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+thread_local char g_err[512] = {0};
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e));
+      return -10;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "gemm launch: %s", cudaGetErrorString(e));
+    return -11;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+const char* gemm_last_error() { return g_err; }
+int gemm_num_n_tiles(int N) { return (N + BN - 1) / BN; }
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K1 <= 0) {
+    snprintf(g_err, sizeof(g_err), "gemm: bad dims M=%d N=%d K1=%d", a.M, a.N, a.K1);
+    return -1;
+  }
+  if (a.a_mn_major && !a.b_mn_major) {
+    snprintf(g_err, sizeof(g_err), "gemm: (A MN-major, B K-major) is not instantiated");
+    return -2;
+  }
+  if (a.splits > 1 && (a.epilogue != EPI_F32_ATOMIC || a.K2 > 0)) {
+    snprintf(g_err, sizeof(g_err), "gemm: split-K needs EPI_F32_ATOMIC and a single K segment");
+    return -3;
+  }
+  if (a.a2_group_n > 0 && (a.a2_group_n % BN != 0 || a.a_mn_major)) {
+    snprintf(g_err, sizeof(g_err), "gemm: a2_group_n must be a multiple of %d with K-major A", BN);
+    return -4;
+  }
+  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD) && (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+    snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
+    return -5;
+  }
+  if (a.epilogue == EPI_F32_ATOMIC && (a.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+    snprintf(g_err, sizeof(g_err), "gemm: f32 output needs ldc %% 4 == 0 and 16B-aligned C");
+    return -5;
+  }
+
+  CUtensorMap maps[4];
+  auto mk = [&](CUtensorMap* m, const GemmOperand& op, bool mn_major, int rows_out, int K, int box_rows_kmajor,
+                int extra_cols) -> int {
+    if (!mn_major) return make_tmap_bf16_2d(m, op.ptr, rows_out, (uint64_t)K + extra_cols, op.ld, box_rows_kmajor, 64);
+    return make_tmap_bf16_2d(m, op.ptr, K, rows_out, op.ld, 64, 64);
+  };
+  int groups = a.a2_group_n > 0 ? (a.N + a.a2_group_n - 1) / a.a2_group_n : 1;
+  int rc = 0;
+  rc |= mk(&maps[0], a.A1, a.a_mn_major, a.M, a.K1, BM, 0);
+  rc |= mk(&maps[1], a.B1, a.b_mn_major, a.N, a.K1, BN, 0);
+  if (a.K2 > 0) {
+    rc |= mk(&maps[2], a.A2, a.a_mn_major, a.M, a.K2, BM, (groups - 1) * a.a2_group_stride);
+    rc |= mk(&maps[3], a.B2, a.b_mn_major, a.N, a.K2, BN, 0);
+  } else {
+    maps[2] = maps[0];
+    maps[3] = maps[1];
+  }
+  if (rc != 0) {
+    snprintf(g_err, sizeof(g_err), "gemm: tensor map: %s", tmap_last_error());
+    return -6;
+  }
+
+  KParams kp{};
+  kp.M = a.M;
+  kp.N = a.N;
+  kp.kb1 = (a.K1 + BK - 1) / BK;
+  kp.kb2 = (a.K2 + BK - 1) / BK;
+  kp.a2_group_n = a.a2_group_n;
+  kp.a2_group_stride = a.a2_group_stride;
+  int splits = a.splits < 1 ? 1 : a.splits;
+  if (splits > kp.kb1) splits = kp.kb1;
+  kp.kb_per_split = (kp.kb1 + splits - 1) / splits;
+  kp.splits = (kp.kb1 + kp.kb_per_split - 1) / kp.kb_per_split;
+  kp.num_m = (a.M + BM - 1) / BM;
+  kp.num_n = (a.N + BN - 1) / BN;
+  kp.num_tiles = kp.num_m * kp.num_n * kp.splits;
+  kp.alpha = a.alpha;
+  kp.C = a.C;
+  kp.ldc = a.ldc;
+  kp.bias = a.bias;
+  kp.residual = a.residual;
+  kp.ldr = a.ldr;
+  kp.act = a.act;
+  kp.labels = a.labels;
+  kp.lse_partials = a.lse_partials;
+  kp.label_logit = a.label_logit;
+  kp.lse = a.lse;
+  kp.dlp = a.dlp;
+
+  int grid = num_sms();
+  if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
+  if (grid > kp.num_tiles) grid = kp.num_tiles;
+
+#define OPADPO_DISPATCH(AMN, BMN)                                                            \
+  switch (a.epilogue) {                                                                      \
+    case EPI_BF16: return launch_impl<AMN, BMN, EPI_BF16>(maps, kp, grid, stream);           \
+    case EPI_F32_ATOMIC: return launch_impl<AMN, BMN, EPI_F32_ATOMIC>(maps, kp, grid, stream); \
+    case EPI_LSE: return launch_impl<AMN, BMN, EPI_LSE>(maps, kp, grid, stream);             \
+    case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD>(maps, kp, grid, stream);       \
+    default: break;                                                                          \
+  }
+  if (!a.a_mn_major && !a.b_mn_major) {
+    OPADPO_DISPATCH(false, false)
+  } else if (!a.a_mn_major && a.b_mn_major) {
+    OPADPO_DISPATCH(false, true)
+  } else {
+    OPADPO_DISPATCH(true, true)
+  }
+#undef OPADPO_DISPATCH
+  snprintf(g_err, sizeof(g_err), "gemm: unknown epilogue %d", a.epilogue);
+  return -7;
+}
+
+}  // namespace opadpo

@@ -1,0 +1,63 @@
+// tcgen05 GEMM for the OPA-DPO hot path (all linears of LLaMA / CLIP / projector / lm_head, LoRA included).
+//
+//   C[M,N] = epilogue( alpha * ( A1 (M x K1) * B1 (N x K1)^T  +  A2 (M x K2) * B2 (N x K2)^T ) )
+//
+// The second K-segment is how LoRA is fused into the base-weight GEMM: the LoRA-A product t = s*x*A^T is a
+// skinny pre-GEMM and [x | t] * [W^T ; B^T] accumulates into the SAME TMEM accumulator (peft lora.Linear:
+// W x + s*B(A x); reference call site opadpo/dpo_models/qlora_model.py:211-216).
+//
+// Operand "major": K-major means the contraction index is contiguous in memory (row-major [rows, K]);
+// MN-major means the output index is contiguous (row-major [K, rows]) — used for dgrad (B = W as stored)
+// and for LoRA wgrad (both operands contract over tokens), so no transposed copies are ever made.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace opadpo {
+
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,      // C bf16 = act(alpha*acc + bias) + residual
+  EPI_F32_ATOMIC = 1,  // C f32 += alpha*acc  (red.global.add; split-K capable)  -- LoRA wgrad into the grad bucket
+  EPI_LSE = 2,       // fused lm_head log-sum-exp partials + label-logit gather (never materialises logits)
+  EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - exp(alpha*acc - lse[m]))  (CE backward tile)
+};
+
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICK_GELU = 2 };
+
+struct GemmOperand {
+  const __nv_bfloat16* ptr = nullptr;
+  int64_t ld = 0;  // leading dimension in elements
+};
+
+struct GemmArgs {
+  int M = 0, N = 0;
+  int K1 = 0, K2 = 0;
+  bool a_mn_major = false, b_mn_major = false;
+  GemmOperand A1, B1, A2, B2;
+  // Segment-2 A column offset for fused groups (q|k|v, gate|up): off = (n0 / a2_group_n) * a2_group_stride.
+  int a2_group_n = 0, a2_group_stride = 0;
+  int splits = 1;  // split-K over segment 1 (EPI_F32_ATOMIC only)
+  int epilogue = EPI_BF16;
+  float alpha = 1.f;
+  void* C = nullptr;
+  int64_t ldc = 0;
+  const __nv_bfloat16* bias = nullptr;      // [N]
+  const __nv_bfloat16* residual = nullptr;  // [M, ldr]
+  int64_t ldr = 0;
+  int act = ACT_NONE;
+  // EPI_LSE / EPI_CEGRAD
+  const int32_t* labels = nullptr;  // [M]; <0 = ignore
+  float4* lse_partials = nullptr;   // [M, ceil(N/256)] (max, sumexp, sum z*exp, -)
+  float* label_logit = nullptr;     // [M]
+  const float* lse = nullptr;       // [M]
+  const float* dlp = nullptr;       // [M]
+  int max_ctas = 0;                 // 0 = all SMs
+};
+
+// Returns 0 on success, negative on error (message via gemm_last_error()).
+int gemm_launch(const GemmArgs& args, cudaStream_t stream);
+const char* gemm_last_error();
+int gemm_num_n_tiles(int N);
+
+}  // namespace opadpo

@@ -1,0 +1,79 @@
+"""Operator-level bindings: torch tensors in, C ABI calls out (device pointers + sizes only cross the boundary).
+
+These wrap `opadpo_op_*` one-to-one; they are what tests/ uses for kernel parity and what the host-side mirror of
+the reference interface composes. No function here computes anything in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc
+
+EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk2d(t: torch.Tensor, dtype=torch.bfloat16):
+    assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1 and t.dtype == dtype, (t.shape, t.stride(), t.dtype)
+
+
+def gemm_n_tiles(n: int) -> int:
+    return _lib.load().opadpo_gemm_n_tiles(n)
+
+
+def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=None, a_mn=False, b_mn=False,
+         alpha: float = 1.0, epilogue: int = EPI_BF16, bias=None, residual=None, act: int = ACT_NONE,
+         a2_group_n: int = 0, a2_group_stride: int = 0, splits: int = 1, labels=None, lse_partials=None,
+         label_logit=None, lse=None, dlp=None, M=None, N=None, K1=None, K2=None, max_ctas: int = 0):
+    """out[M,N] = epilogue(alpha*(A1 B1^T + A2 B2^T)). Operand shapes follow their 'major':
+    K-major A is [M,K], MN-major A is [K,M]; K-major B is [N,K], MN-major B is [K,N]."""
+    lib = _lib.load()
+    _chk2d(a1), _chk2d(b1)
+    if M is None:
+        M = a1.shape[1] if a_mn else a1.shape[0]
+    if K1 is None:
+        K1 = a1.shape[0] if a_mn else a1.shape[1]
+    if N is None:
+        N = b1.shape[1] if b_mn else b1.shape[0]
+    d = GemmDesc()
+    d.M, d.N, d.K1 = M, N, K1
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
+    d.A1, d.lda1 = a1.data_ptr(), a1.stride(0)
+    d.B1, d.ldb1 = b1.data_ptr(), b1.stride(0)
+    if a2 is not None:
+        _chk2d(a2), _chk2d(b2)
+        if K2 is None:
+            K2 = b2.shape[0] if b_mn else b2.shape[1]
+        d.K2 = K2
+        d.A2, d.lda2 = a2.data_ptr(), a2.stride(0)
+        d.B2, d.ldb2 = b2.data_ptr(), b2.stride(0)
+    else:
+        d.K2 = 0
+    d.a2_group_n, d.a2_group_stride = a2_group_n, a2_group_stride
+    d.splits, d.epilogue, d.alpha = splits, epilogue, alpha
+    if epilogue != EPI_LSE:
+        d.C, d.ldc = out.data_ptr(), out.stride(0)
+    d.bias = _ptr(bias)
+    if residual is not None:
+        d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
+    d.act = act
+    d.labels = _ptr(labels)
+    d.lse_partials = _ptr(lse_partials)
+    d.label_logit = _ptr(label_logit)
+    d.lse = _ptr(lse)
+    d.dlp = _ptr(dlp)
+    d.max_ctas = max_ctas
+    _lib.check(lib.opadpo_op_gemm(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_gemm")
+    return out

@@ -1,0 +1,145 @@
+"""Kernel parity: tcgen05 GEMM (through the C ABI) vs a plain PyTorch fp32 matmul of the same bf16 operands.
+
+Tolerance: bf16 output rounding (rel 2^-8) on top of fp32 accumulation; stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * scale).to(torch.bfloat16)
+
+
+def _close(out, ref, rtol=1e-2, atol=None, what=""):
+    ref = ref.float()
+    out = out.float()
+    if atol is None:
+        atol = 1e-2 * ref.abs().max().item() + 1e-6
+    err = (out - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} mismatches, max err {err.max().item():.4g}, " \
+                          f"ref max {ref.abs().max().item():.4g}, first bad idx {bad.nonzero()[0].tolist()}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 128), (200, 264, 136),
+                                   (1215, 768, 320), (4096, 4096, 4096)])
+def test_gemm_kk(M, N, K):
+    from opa_dpo_b200 import ops
+    a, b = _mk((M, K), 1), _mk((N, K), 2)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().t(), what=f"kk {M}x{N}x{K}")
+
+
+def test_gemm_kk_strided_views():
+    from opa_dpo_b200 import ops
+    M, N, K = 300, 512, 192
+    abuf, bbuf = _mk((M, K + 64), 3), _mk((N, K + 8), 4)
+    a, b = abuf[:, 64:], bbuf[:, :K]
+    cbuf = torch.zeros((M, N + 256), device="cuda", dtype=torch.bfloat16)
+    out = cbuf[:, 256:]
+    ops.gemm(a, b, out)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().t(), what="strided")
+    assert cbuf[:, :256].abs().max().item() == 0
+
+
+def test_gemm_epilogue_bias_act_residual():
+    from opa_dpo_b200 import ops
+    M, N, K = 333, 512, 256
+    a, b = _mk((M, K), 5), _mk((N, K), 6, 0.1)
+    bias, res = _mk((N,), 7), _mk((M, N), 8)
+    for act, fn in [(ops.ACT_NONE, lambda x: x), (ops.ACT_GELU, torch.nn.functional.gelu),
+                    (ops.ACT_QUICK_GELU, lambda x: x * torch.sigmoid(1.702 * x))]:
+        out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, out, bias=bias, residual=res, act=act, alpha=0.5)
+        torch.cuda.synchronize()
+        ref = fn(0.5 * (a.float() @ b.float().t()) + bias.float()) + res.float()
+        _close(out, ref, what=f"epilogue act={act}")
+
+
+def test_gemm_lora_second_segment_and_groups():
+    """[x | t] [W^T ; B^T] with per-group t columns (fused q|k|v): y_g = x W_g^T + t_g B_g^T."""
+    from opa_dpo_b200 import ops
+    M, K, r, G, Ng = 500, 320, 64, 3, 256
+    x, W = _mk((M, K), 9), _mk((G * Ng, K), 10, 0.05)
+    t, B = _mk((M, G * r), 11), _mk((G * Ng, r), 12, 0.05)
+    out = torch.empty((M, G * Ng), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, W, out, a2=t, b2=B, a2_group_n=Ng, a2_group_stride=r, K2=r)
+    torch.cuda.synchronize()
+    ref = x.float() @ W.float().t()
+    for g in range(G):
+        ref[:, g * Ng:(g + 1) * Ng] += t[:, g * r:(g + 1) * r].float() @ B[g * Ng:(g + 1) * Ng].float().t()
+    _close(out, ref, what="lora groups")
+    # ungrouped, tiny rank (K2 = 8 -> zero-filled k tail)
+    t8, B8 = _mk((M, 8), 13), _mk((G * Ng, 8), 14)
+    ops.gemm(x, W, out, a2=t8, b2=B8)
+    torch.cuda.synchronize()
+    _close(out, x.float() @ W.float().t() + t8.float() @ B8.float().t(), what="lora r=8")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 520, 200), (2048, 4096, 1024)])
+def test_gemm_b_mn_major(M, N, K):
+    """dgrad form: dx = dy W with W stored [K(contraction), N(output)] row-major."""
+    from opa_dpo_b200 import ops
+    a, b = _mk((M, K), 15), _mk((K, N), 16)
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, b_mn=True)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float(), what=f"k-mn {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 256, 64, 1), (256, 520, 1000, 1), (256, 4096, 5000, 7), (40, 264, 700, 3)])
+def test_gemm_wgrad_mn_mn_atomic(M, N, K, splits):
+    """LoRA wgrad form: dW[M,N] += alpha * A^T B with A [K,M], B [K,N] (contraction over tokens), fp32 atomics."""
+    from opa_dpo_b200 import ops
+    a, b = _mk((K, M), 17), _mk((K, N), 18)
+    init = torch.randn((M, N), device="cuda", dtype=torch.float32)
+    out = init.clone()
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC, splits=splits, alpha=2.0)
+    torch.cuda.synchronize()
+    ref = init + 2.0 * (a.float().t() @ b.float())
+    _close(out, ref, rtol=1e-4, atol=1e-3 * ref.abs().max().item(), what="wgrad")
+
+
+def test_gemm_lse_and_cegrad():
+    """Fused lm_head epilogues vs torch log_softmax / autograd."""
+    from opa_dpo_b200 import ops
+    M, V, K, T = 700, 1000, 256, 0.7
+    h, W = _mk((M, K), 19), _mk((V, K), 20, 0.2)
+    labels = torch.randint(0, V, (M,), device="cuda", dtype=torch.int32)
+    labels[::7] = -1
+    nt = ops.gemm_n_tiles(V)
+    part = torch.zeros((M, nt, 4), device="cuda", dtype=torch.float32)
+    lab = torch.zeros((M,), device="cuda", dtype=torch.float32)
+    ops.gemm(h, W, None, epilogue=ops.EPI_LSE, alpha=1.0 / T, labels=labels, lse_partials=part, label_logit=lab)
+    torch.cuda.synchronize()
+    z = (h.float() @ W.float().t()) / T
+    # combine partials (base-2 domain)
+    mx = part[..., 0].max(dim=1).values
+    s = (part[..., 1] * torch.exp2(part[..., 0] - mx[:, None])).sum(1)
+    zs = (part[..., 2] * torch.exp2(part[..., 0] - mx[:, None])).sum(1)
+    lse = (mx + torch.log2(s)) * math.log(2.0)
+    ref_lse = torch.logsumexp(z, dim=-1)
+    assert (lse - ref_lse).abs().max().item() < 2e-4 * max(1.0, ref_lse.abs().max().item())
+    valid = labels >= 0
+    ref_lab = z.gather(1, labels.clamp(min=0).long()[:, None])[:, 0]
+    assert (lab - ref_lab)[valid].abs().max().item() < 1e-4 * max(1.0, ref_lab.abs().max().item())
+    ent = lse - (zs / s) * math.log(2.0)
+    lsm = torch.log_softmax(z, -1)
+    ref_ent = -(lsm.exp() * lsm).sum(-1)
+    assert (ent - ref_ent).abs().max().item() < 1e-3
+    # CE backward tile
+    dlp = torch.randn((M,), device="cuda", dtype=torch.float32) * valid
+    G = torch.empty((M, V), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(h, W, G, epilogue=ops.EPI_CEGRAD, alpha=1.0 / T, labels=labels, lse=lse.contiguous(), dlp=dlp)
+    torch.cuda.synchronize()
+    onehot = torch.zeros_like(z)
+    onehot[valid, labels[valid].long()] = 1.0
+    refG = dlp[:, None] * (onehot - lsm.exp()) / T
+    _close(G, refG, what="cegrad")
