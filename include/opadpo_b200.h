@@ -66,6 +66,30 @@ typedef struct opadpo_gemm_desc {
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);
 int opadpo_gemm_n_tiles(int32_t N);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator level: tcgen05 flash attention. q/k/v/o/dO/dq/dk/dv are bf16 row-major [N*S, H*HD] views with the
+ * given leading dimensions (head h at columns [h*HD,(h+1)*HD)); lse/delta are f32 [N*S, H]; kbits is the packed
+ * key-validity mask u64 [N, ceil(S/64)] (NULL = all valid) made by opadpo_op_pack_mask.
+ * Replaces HF LlamaFlashAttention2 / flash_attn_varlen_func and CLIPAttention [UPSTREAM]; call site
+ * opadpo/dpo_models/qlora_model.py:133-143 (use_flash_attention_2) and rl_models.py:120.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct opadpo_attn_desc {
+  int32_t N, S, H, HD;
+  int32_t causal;
+  float scale;
+  const void *q, *k, *v; int64_t ld_qkv;
+  void* o; int64_t ld_o;
+  float* lse;
+  const uint64_t* kbits;
+  const void* dO; int64_t ld_do;   /* backward only from here */
+  float* delta;
+  void *dq, *dk, *dv; int64_t ld_dqkv;
+} opadpo_attn_desc;
+
+int opadpo_op_attn_fwd(const opadpo_attn_desc* d, void* stream);
+int opadpo_op_attn_bwd(const opadpo_attn_desc* d, void* stream);
+int opadpo_op_pack_mask(const uint8_t* mask, uint64_t* bits, int32_t N, int32_t S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,19 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class AttnDesc(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int32), ("S", ctypes.c_int32), ("H", ctypes.c_int32), ("HD", ctypes.c_int32),
+        ("causal", ctypes.c_int32), ("scale", ctypes.c_float),
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p), ("ld_qkv", ctypes.c_int64),
+        ("o", ctypes.c_void_p), ("ld_o", ctypes.c_int64),
+        ("lse", ctypes.c_void_p), ("kbits", ctypes.c_void_p),
+        ("dO", ctypes.c_void_p), ("ld_do", ctypes.c_int64),
+        ("delta", ctypes.c_void_p),
+        ("dq", ctypes.c_void_p), ("dk", ctypes.c_void_p), ("dv", ctypes.c_void_p), ("ld_dqkv", ctypes.c_int64),
+    ]
+
+
 def _declare(lib):
     lib.opadpo_last_error.restype = ctypes.c_char_p
     lib.opadpo_abi_version.restype = ctypes.c_int
@@ -62,6 +75,12 @@ def _declare(lib):
     lib.opadpo_gemm_n_tiles.restype = ctypes.c_int
     lib.opadpo_op_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
     lib.opadpo_op_gemm.restype = ctypes.c_int
+    for name in ("opadpo_op_attn_fwd", "opadpo_op_attn_bwd"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.POINTER(AttnDesc), ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.opadpo_op_pack_mask.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    lib.opadpo_op_pack_mask.restype = ctypes.c_int
 
 
 def load(build_if_missing: bool = False):

@@ -4,6 +4,7 @@
 
 #include "../../include/opadpo_b200.h"
 #include "common.h"
+#include "attention.h"
 #include "gemm.h"
 
 namespace opadpo {
@@ -63,6 +64,50 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
     set_error("%s", gemm_last_error());
     return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL;
   }
+  return OPADPO_OK;
+}
+
+
+static AttnArgs to_attn(const opadpo_attn_desc* d) {
+  AttnArgs a;
+  a.N = d->N; a.S = d->S; a.H = d->H; a.HD = d->HD;
+  a.causal = d->causal != 0;
+  a.scale = d->scale;
+  a.q = static_cast<const __nv_bfloat16*>(d->q);
+  a.k = static_cast<const __nv_bfloat16*>(d->k);
+  a.v = static_cast<const __nv_bfloat16*>(d->v);
+  a.ld_qkv = d->ld_qkv;
+  a.o = static_cast<__nv_bfloat16*>(d->o);
+  a.ld_o = d->ld_o;
+  a.lse = d->lse;
+  a.kbits = d->kbits;
+  a.dO = static_cast<const __nv_bfloat16*>(d->dO);
+  a.ld_do = d->ld_do;
+  a.delta = d->delta;
+  a.dq = static_cast<__nv_bfloat16*>(d->dq);
+  a.dk = static_cast<__nv_bfloat16*>(d->dk);
+  a.dv = static_cast<__nv_bfloat16*>(d->dv);
+  a.ld_dqkv = d->ld_dqkv;
+  return a;
+}
+
+int opadpo_op_attn_fwd(const opadpo_attn_desc* d, void* stream) {
+  if (!d) { set_error("opadpo_op_attn_fwd: null descriptor"); return OPADPO_EINVAL; }
+  int rc = attn_forward(to_attn(d), static_cast<cudaStream_t>(stream));
+  if (rc != 0) { set_error("%s", attn_last_error()); return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL; }
+  return OPADPO_OK;
+}
+
+int opadpo_op_attn_bwd(const opadpo_attn_desc* d, void* stream) {
+  if (!d) { set_error("opadpo_op_attn_bwd: null descriptor"); return OPADPO_EINVAL; }
+  int rc = attn_backward(to_attn(d), static_cast<cudaStream_t>(stream));
+  if (rc != 0) { set_error("%s", attn_last_error()); return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL; }
+  return OPADPO_OK;
+}
+
+int opadpo_op_pack_mask(const uint8_t* mask, uint64_t* bits, int32_t N, int32_t S, void* stream) {
+  int rc = attn_pack_mask(mask, bits, N, S, static_cast<cudaStream_t>(stream));
+  if (rc != 0) { set_error("pack_mask launch failed"); return OPADPO_ECUDA; }
   return OPADPO_OK;
 }
 

@@ -1,0 +1,808 @@
+// tcgen05 flash attention for sm_100a. One CTA = (sequence n, head h, tile); 6 warps:
+//   warps 0-3 : softmax / epilogue, ONE THREAD PER TMEM LANE (= query row, or head-dim row for dK^T/dV^T)
+//   warp 4    : TMA producer (one elected lane) + TMEM allocation
+//   warp 5    : MMA issuer (one elected lane)
+// Score tiles live in TMEM; P / dS are written by the softmax threads into 128B-swizzled smem and consumed by the
+// next MMA either as a K-major A operand (P V, dS K) or, unchanged, as an MN-major B operand (dO^T P, Q^T dS).
+#include "attention.h"
+
+#include <cstdio>
+
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace opadpo {
+namespace {
+
+constexpr int BQ = 128;   // query rows per tile
+constexpr int BKV = 64;   // keys per tile
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int NTHREADS = 192;
+
+struct AttnParams {
+  int N, S, H;
+  int nwords;
+  float scale, scale_log2;
+  const uint64_t* kbits;
+  __nv_bfloat16* o;
+  int64_t ld_o;
+  float* lse;
+  const float* delta;
+  __nv_bfloat16 *dq, *dk, *dv;
+  int64_t ld_dqkv;
+};
+
+// K-major tile of `rows` rows x (nblk*64) columns -> smem [blk][rows][128 B]
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int col0, int row0,
+                                          int rows, int nblk) {
+  for (int b = 0; b < nblk; ++b) ptx::tma_load_2d(dst + b * rows * 128, m, bar, col0 + 64 * b, row0);
+}
+
+// Write 32 consecutive bf16 values (columns [half*32, half*32+32) of a 64-wide, 128 B row) into a swizzled tile.
+__device__ __forceinline__ void store_half_row_sw128(uint8_t* tile, int r, int half, const float (&v)[32]) {
+  uint8_t* rowp = tile + r * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    const int chunk = (half * 4 + q) ^ (r & 7);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+  }
+}
+
+__device__ __forceinline__ uint64_t key_bits(const AttnParams& p, int n, int j, int i, bool causal, bool row_valid) {
+  uint64_t bits = p.kbits ? p.kbits[static_cast<int64_t>(n) * p.nwords + j] : ~0ull;
+  const int rem = p.S - j * BKV;  // keys beyond the sequence end
+  if (rem < 64) bits &= (rem <= 0) ? 0ull : ((1ull << rem) - 1ull);
+  if (causal) {
+    const int lim = i - j * BKV;  // keys c <= lim visible
+    if (lim < 63) bits &= (lim < 0) ? 0ull : ((2ull << lim) - 1ull);
+  }
+  return row_valid ? bits : 0ull;
+}
+
+// =====================================================================================================
+// Forward
+// =====================================================================================================
+template <int HD>
+struct FwdSmem {
+  static constexpr int NB = HD / 64;
+  static constexpr int Q_BYTES = NB * BQ * 128;
+  static constexpr int KV_BYTES = NB * BKV * 128;
+  static constexpr int P_BYTES = BQ * 128;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 128;
+  static constexpr int TMEM_COLS = (64 + HD) <= 128 ? 128 : 256;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(NTHREADS, 2)
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = FwdSmem<HD>;
+  constexpr int NB = L::NB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int row0 = n * p.S + q0;
+  const int col0 = h * HD;
+  int num_kv = (p.S + BKV - 1) / BKV;
+  if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK);
+      ptx::prefetch_tmap(&tmV);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
+    ptx::tmem_relinquish();
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+      ptx::mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&kv_full[i], 1);
+        ptx::mbar_init(&kv_empty[i], 1);
+      }
+      ptx::mbar_init(s_full, 1);
+      ptx::mbar_init(p_full, 128);
+      ptx::mbar_init(o_full, 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_o = tmem + 64;
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
+      for (int j = 0; j < num_kv; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
+        load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+      }
+    }
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, false, false);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, false, true);
+      const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
+      const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j < num_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
+        const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
+        ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_qk, kk > 0);
+        }
+        ptx::mma_commit(s_full);
+        ptx::mbar_wait(p_full, j & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          ptx::mma_bf16_ss(t_o, ptx::make_smem_desc(aP + kk * 32, 16, 1024),
+                           ptx::make_smem_desc(aV + kk * 2048, BKV * 128, 1024), idesc_pv, (j > 0 || kk > 0));
+        }
+        ptx::mma_commit(&kv_empty[st]);
+        if (j == num_kv - 1) ptx::mma_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: thread == query row
+    const int tid = threadIdx.x;
+    const int i = q0 + tid;
+    const bool row_valid = i < p.S;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < num_kv; ++j) {
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(t_s + lane_off, r0);
+      ptx::tmem_ld32(t_s + lane_off + 32, r1);
+      ptx::tmem_ld_wait();
+      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
+      float cm = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float x = ((bits >> c) & 1ull) ? __uint_as_float(r0[c]) * p.scale_log2 : -INFINITY;
+        float y = ((bits >> (32 + c)) & 1ull) ? __uint_as_float(r1[c]) * p.scale_log2 : -INFINITY;
+        r0[c] = __float_as_uint(x);
+        r1[c] = __float_as_uint(y);
+        cm = fmaxf(cm, fmaxf(x, y));
+      }
+      // Lazy rescale: only move the reference max when it grows by more than 2^8 (exact result either way).
+      const bool need = cm > m_ref + 8.f;
+      float alpha = 1.f;
+      if (need) {
+        alpha = exp2f(m_ref - cm);
+        m_ref = cm;
+        l *= alpha;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t t[32];
+          ptx::tmem_ld32(t_o + lane_off + c * 32, t);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
+          ptx::tmem_st32(t_o + lane_off + c * 32, t);
+        }
+        ptx::tmem_st_wait();
+      }
+      const float mu = (m_ref == -INFINITY) ? 0.f : m_ref;
+      float sum = 0.f;
+      float pv[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        pv[c] = exp2f(__uint_as_float(r0[c]) - mu);
+        sum += pv[c];
+      }
+      store_half_row_sw128(smem + L::OFF_P, tid, 0, pv);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        pv[c] = exp2f(__uint_as_float(r1[c]) - mu);
+        sum += pv[c];
+      }
+      store_half_row_sw128(smem + L::OFF_P, tid, 1, pv);
+      l += sum;
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row0 + tid) * p.ld_o + col0;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t t[32];
+      ptx::tmem_ld32(t_o + lane_off + c * 32, t);
+      ptx::tmem_ld_wait();
+      if (row_valid) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]) * inv, __uint_as_float(t[q * 8 + 1]) * inv);
+          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]) * inv, __uint_as_float(t[q * 8 + 3]) * inv);
+          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]) * inv, __uint_as_float(t[q * 8 + 5]) * inv);
+          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]) * inv, __uint_as_float(t[q * 8 + 7]) * inv);
+          dst[q] = u;
+        }
+      }
+      __syncwarp();
+    }
+    if (row_valid && p.lse)
+      p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] = l > 0.f ? (m_ref + log2f(l)) * LN2 : INFINITY;
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, L::TMEM_COLS);
+  }
+}
+
+// =====================================================================================================
+// Backward, shared score recomputation: p = exp2(s*scale_log2 - lse2), ds = p*(dp - delta)*scale
+// =====================================================================================================
+__device__ __forceinline__ void recompute_half(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint64_t bits, int half,
+                                               float scale_log2, float scale, float lse2, float delta, float (&pv)[32],
+                                               float (&dsv)[32]) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const bool ok = (bits >> (half * 32 + c)) & 1ull;
+    const float pr = ok ? exp2f(__uint_as_float(s[c]) * scale_log2 - lse2) : 0.f;
+    pv[c] = pr;
+    dsv[c] = pr * (__uint_as_float(dp[c]) - delta) * scale;
+  }
+}
+
+// ---------------------------------------------------------------- dQ: one CTA per query tile, loops over key tiles
+template <int HD>
+struct DqSmem {
+  static constexpr int NB = HD / 64;
+  static constexpr int Q_BYTES = NB * BQ * 128;
+  static constexpr int KV_BYTES = NB * BKV * 128;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DO = OFF_Q + Q_BYTES;
+  static constexpr int OFF_K = OFF_DO + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
+  static constexpr int OFF_DS = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_DS + BQ * 128;
+  static constexpr int TOTAL = OFF_BAR + 128;
+  static constexpr int TMEM_COLS = 256;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const AttnParams p) {
+  using L = DqSmem<HD>;
+  constexpr int NB = L::NB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = bars + 3;
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int row0 = n * p.S + q0;
+  const int col0 = h * HD;
+  int num_kv = (p.S + BKV - 1) / BKV;
+  if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
+
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
+    ptx::tmem_relinquish();
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+      ptx::mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&kv_full[i], 1);
+        ptx::mbar_init(&kv_empty[i], 1);
+      }
+      ptx::mbar_init(sdp_full, 1);
+      ptx::mbar_init(ds_full, 128);
+      ptx::mbar_init(dq_done, 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(q_full, 2 * L::Q_BYTES);
+      load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
+      load_tile(smem + L::OFF_DO, &tmdO, q_full, col0, row0, BQ, NB);
+      for (int j = 0; j < num_kv; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
+        load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+      }
+    }
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, false, false);
+      constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(BQ, HD, false, true);
+      const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
+      const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO);
+      const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j < num_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
+        const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
+        ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(adO + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+        }
+        ptx::mma_commit(sdp_full);
+        ptx::mbar_wait(ds_full, j & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          ptx::mma_bf16_ss(t_dq, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
+                           ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024), idesc_dq, (j > 0 || kk > 0));
+        }
+        ptx::mma_commit(&kv_empty[st]);
+        if (j == num_kv - 1) ptx::mma_commit(dq_done);
+      }
+    }
+  } else {
+    const int tid = threadIdx.x;
+    const int i = q0 + tid;
+    const bool row_valid = i < p.S;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
+    const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
+    for (int j = 0; j < num_kv; ++j) {
+      ptx::mbar_wait(sdp_full, j & 1);
+      ptx::tc_fence_after();
+      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32];
+        ptx::tmem_ld32(t_s + lane_off + half * 32, s);
+        ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
+        ptx::tmem_ld_wait();
+        float pv[32], dsv[32];
+        recompute_half(s, dp, bits, half, p.scale_log2, p.scale, lse2, delta, pv, dsv);
+        store_half_row_sw128(smem + L::OFF_DS, tid, half, dsv);
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ds_full);
+    }
+    ptx::mbar_wait(dq_done, 0);
+    ptx::tc_fence_after();
+    __nv_bfloat16* drow = p.dq + static_cast<int64_t>(row0 + tid) * p.ld_dqkv + col0;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t t[32];
+      ptx::tmem_ld32(t_dq + lane_off + c * 32, t);
+      ptx::tmem_ld_wait();
+      if (row_valid) {
+        uint4* dst = reinterpret_cast<uint4*>(drow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]), __uint_as_float(t[q * 8 + 1]));
+          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]), __uint_as_float(t[q * 8 + 3]));
+          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]), __uint_as_float(t[q * 8 + 5]));
+          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]), __uint_as_float(t[q * 8 + 7]));
+          dst[q] = u;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, L::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- dK, dV: one CTA per key tile, loops over query tiles
+template <int HD>
+struct DkvSmem {
+  static constexpr int NB = HD / 64;
+  static constexpr int Q_BYTES = NB * BQ * 128;
+  static constexpr int KV_BYTES = NB * BKV * 128;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [2]
+  static constexpr int OFF_DO = OFF_Q + 2 * Q_BYTES;   // [2]
+  static constexpr int OFF_P = OFF_DO + 2 * Q_BYTES;
+  static constexpr int OFF_DS = OFF_P + BQ * 128;
+  static constexpr int OFF_BAR = OFF_DS + BQ * 128;
+  static constexpr int TOTAL = OFF_BAR + 128;
+  static constexpr int TMEM_COLS = 256;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                         const AttnParams p) {
+  static_assert(HD == 128, "dK^T/dV^T accumulate with M = HD = 128 TMEM lanes");
+  using L = DkvSmem<HD>;
+  constexpr int NB = L::NB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int j = blockIdx.x;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int k0 = j * BKV;
+  const int col0 = h * HD;
+  const int nq = (p.S + BQ - 1) / BQ;
+  const int i0 = CAUSAL ? (k0 / BQ) : 0;
+  const int niter = nq - i0;
+
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
+    ptx::tmem_relinquish();
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+      ptx::mbar_init(kv_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&qdo_full[i], 1);
+        ptx::mbar_init(&qdo_empty[i], 1);
+      }
+      ptx::mbar_init(sdp_full, 1);
+      ptx::mbar_init(pds_full, 128);
+      ptx::mbar_init(done, 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dv = tmem + 128, t_dk = tmem + 192;
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * L::KV_BYTES);
+      load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKV, NB);
+      load_tile(smem + L::OFF_V, &tmV, kv_full, col0, n * p.S + k0, BKV, NB);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1;
+        ptx::mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&qdo_full[st], 2 * L::Q_BYTES);
+        const int r0 = n * p.S + (i0 + it) * BQ;
+        load_tile(smem + L::OFF_Q + st * L::Q_BYTES, &tmQ, &qdo_full[st], col0, r0, BQ, NB);
+        load_tile(smem + L::OFF_DO + st * L::Q_BYTES, &tmdO, &qdo_full[st], col0, r0, BQ, NB);
+      }
+    }
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, false, false);
+      constexpr uint32_t idesc_t = ptx::make_idesc_bf16(HD, BKV, true, true);
+      const uint32_t aK = ptx::smem_u32(smem + L::OFF_K);
+      const uint32_t aV = ptx::smem_u32(smem + L::OFF_V);
+      const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
+      const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
+      ptx::mbar_wait(kv_full, 0);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1;
+        const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
+        const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
+        ptx::mbar_wait(&qdo_full[st], (it >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(adO + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+        }
+        ptx::mma_commit(sdp_full);
+        ptx::mbar_wait(pds_full, it & 1);
+        ptx::tc_fence_after();
+        // dV^T[hd, keys] += dO^T P ; dK^T[hd, keys] += Q^T dS   (contraction over the 128 query rows)
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk) {
+          ptx::mma_bf16_ss(t_dv, ptx::make_smem_desc(adO + kk * 2048, BQ * 128, 1024),
+                           ptx::make_smem_desc(aP + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
+        }
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk) {
+          ptx::mma_bf16_ss(t_dk, ptx::make_smem_desc(aQ + kk * 2048, BQ * 128, 1024),
+                           ptx::make_smem_desc(adS + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
+        }
+        ptx::mma_commit(&qdo_empty[st]);
+        if (it == niter - 1) ptx::mma_commit(done);
+      }
+    }
+  } else {
+    const int tid = threadIdx.x;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    for (int it = 0; it < niter; ++it) {
+      const int q0 = (i0 + it) * BQ;
+      const int i = q0 + tid;
+      const bool row_valid = i < p.S;
+      const int64_t grow = static_cast<int64_t>(n) * p.S + i;
+      const float lse2 = row_valid ? p.lse[grow * p.H + h] * LOG2E : INFINITY;
+      const float delta = row_valid ? p.delta[grow * p.H + h] : 0.f;
+      ptx::mbar_wait(sdp_full, it & 1);
+      ptx::tc_fence_after();
+      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32];
+        ptx::tmem_ld32(t_s + lane_off + half * 32, s);
+        ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
+        ptx::tmem_ld_wait();
+        float pv[32], dsv[32];
+        recompute_half(s, dp, bits, half, p.scale_log2, p.scale, lse2, delta, pv, dsv);
+        store_half_row_sw128(smem + L::OFF_P, tid, half, pv);
+        store_half_row_sw128(smem + L::OFF_DS, tid, half, dsv);
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(pds_full);
+    }
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after();
+    // thread == head-dim index; columns == keys
+    const int nkeys = min(BKV, p.S - k0);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t tv[32], tk[32];
+      ptx::tmem_ld32(t_dv + lane_off + half * 32, tv);
+      ptx::tmem_ld32(t_dk + lane_off + half * 32, tk);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int key = half * 32 + c;
+        if (key < nkeys) {
+          const int64_t off = (static_cast<int64_t>(n) * p.S + k0 + key) * p.ld_dqkv + col0 + tid;
+          p.dv[off] = __float2bfloat16(__uint_as_float(tv[c]));
+          p.dk[off] = __float2bfloat16(__uint_as_float(tk[c]));
+        }
+      }
+      __syncwarp();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, L::TMEM_COLS);
+  }
+}
+
+// delta[t, h] = sum_c dO[t, h*HD + c] * O[t, h*HD + c]   (one warp per (t, h))
+template <int HD>
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int64_t ld_do, const __nv_bfloat16* __restrict__ O,
+                                  int64_t ld_o, float* __restrict__ delta, int64_t T, int H) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= T * H) return;
+  const int64_t t = w / H;
+  const int h = static_cast<int>(w % H);
+  const __nv_bfloat16* a = dO + t * ld_do + h * HD;
+  const __nv_bfloat16* b = O + t * ld_o + h * HD;
+  float s = 0.f;
+  for (int c = lane * 2; c < HD; c += 64) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + c));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + c));
+    s += x.x * y.x + x.y * y.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) delta[w] = s;
+}
+
+__global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __restrict__ bits, int N, int S, int nwords) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nwords) return;
+  const int n = idx / nwords, w = idx % nwords;
+  uint64_t b = 0;
+  for (int c = 0; c < 64; ++c) {
+    const int k = w * 64 + c;
+    if (k < S && mask[static_cast<int64_t>(n) * S + k]) b |= (1ull << c);
+  }
+  bits[idx] = b;
+}
+
+thread_local char g_err[512] = {0};
+
+int make_maps(const AttnArgs& a, const __nv_bfloat16* base, int64_t ld, int box_rows, CUtensorMap* m) {
+  const uint64_t T = static_cast<uint64_t>(a.N) * a.S;
+  int rc = make_tmap_bf16_2d(m, base, T, static_cast<uint64_t>(a.H) * a.HD, ld, box_rows, 64);
+  if (rc != 0) snprintf(g_err, sizeof(g_err), "attention tensor map: %s", tmap_last_error());
+  return rc;
+}
+
+AttnParams make_params(const AttnArgs& a) {
+  AttnParams p{};
+  p.N = a.N;
+  p.S = a.S;
+  p.H = a.H;
+  p.nwords = (a.S + 63) / 64;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * LOG2E;
+  p.kbits = a.kbits;
+  p.o = a.o;
+  p.ld_o = a.ld_o;
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.dq = a.dq;
+  p.dk = a.dk;
+  p.dv = a.dv;
+  p.ld_dqkv = a.ld_dqkv;
+  return p;
+}
+
+template <typename K>
+int set_smem(K kern, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(%d): %s", bytes, cudaGetErrorString(e));
+    return -10;
+  }
+  return 0;
+}
+
+template <int HD, bool CAUSAL>
+int launch_fwd(const AttnArgs& a, cudaStream_t stream) {
+  CUtensorMap mq, mk, mv;
+  if (make_maps(a, a.q, a.ld_qkv, BQ, &mq) || make_maps(a, a.k, a.ld_qkv, BKV, &mk) || make_maps(a, a.v, a.ld_qkv, BKV, &mv))
+    return -6;
+  auto kern = attn_fwd_kernel<HD, CAUSAL>;
+  static bool once = false;
+  if (!once) {
+    if (int rc = set_smem(kern, FwdSmem<HD>::TOTAL)) return rc;
+    once = true;
+  }
+  dim3 grid((a.S + BQ - 1) / BQ, a.H, a.N);
+  kern<<<grid, NTHREADS, FwdSmem<HD>::TOTAL, stream>>>(mq, mk, mv, make_params(a));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "attn fwd launch: %s", cudaGetErrorString(e));
+    return -11;
+  }
+  return 0;
+}
+
+template <bool CAUSAL>
+int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
+  constexpr int HD = 128;
+  CUtensorMap mq, mdo, mk, mv;
+  if (make_maps(a, a.q, a.ld_qkv, BQ, &mq) || make_maps(a, a.dO, a.ld_do, BQ, &mdo) ||
+      make_maps(a, a.k, a.ld_qkv, BKV, &mk) || make_maps(a, a.v, a.ld_qkv, BKV, &mv))
+    return -6;
+  const int64_t T = static_cast<int64_t>(a.N) * a.S;
+  {
+    const int64_t warps = T * a.H;
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    attn_delta_kernel<HD><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(a.dO, a.ld_do, a.o, a.ld_o, a.delta, T, a.H);
+  }
+  AttnParams p = make_params(a);
+  auto kdq = attn_bwd_dq_kernel<HD, CAUSAL>;
+  auto kdkv = attn_bwd_dkdv_kernel<HD, CAUSAL>;
+  static bool once = false;
+  if (!once) {
+    if (int rc = set_smem(kdq, DqSmem<HD>::TOTAL)) return rc;
+    if (int rc = set_smem(kdkv, DkvSmem<HD>::TOTAL)) return rc;
+    once = true;
+  }
+  dim3 gq((a.S + BQ - 1) / BQ, a.H, a.N);
+  kdq<<<gq, NTHREADS, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  dim3 gk((a.S + BKV - 1) / BKV, a.H, a.N);
+  kdkv<<<gk, NTHREADS, DkvSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "attn bwd launch: %s", cudaGetErrorString(e));
+    return -11;
+  }
+  return 0;
+}
+
+}  // namespace
+
+const char* attn_last_error() { return g_err; }
+
+int attn_forward(const AttnArgs& a, cudaStream_t stream) {
+  if (a.HD == 128) return a.causal ? launch_fwd<128, true>(a, stream) : launch_fwd<128, false>(a, stream);
+  if (a.HD == 64) return a.causal ? launch_fwd<64, true>(a, stream) : launch_fwd<64, false>(a, stream);
+  snprintf(g_err, sizeof(g_err), "attention: head_dim %d not supported (64 or 128)", a.HD);
+  return -1;
+}
+
+int attn_backward(const AttnArgs& a, cudaStream_t stream) {
+  if (a.HD != 128) {
+    snprintf(g_err, sizeof(g_err), "attention backward: head_dim %d not supported (128)", a.HD);
+    return -1;
+  }
+  return a.causal ? launch_bwd<true>(a, stream) : launch_bwd<false>(a, stream);
+}
+
+int attn_pack_mask(const uint8_t* mask, uint64_t* bits, int N, int S, cudaStream_t stream) {
+  const int nwords = (S + 63) / 64;
+  const int total = N * nwords;
+  pack_mask_kernel<<<(total + 127) / 128, 128, 0, stream>>>(mask, bits, N, S, nwords);
+  return cudaGetLastError() == cudaSuccess ? 0 : -11;
+}
+
+}  // namespace opadpo

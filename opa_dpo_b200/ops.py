@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import GemmDesc
+from ._lib import AttnDesc, GemmDesc
 
 EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2
@@ -77,3 +77,42 @@ def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=N
     d.max_ctas = max_ctas
     _lib.check(lib.opadpo_op_gemm(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_gemm")
     return out
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """[N, S] bool/uint8 key-validity mask -> packed u64 bit words [N, ceil(S/64)] (int64 storage)."""
+    lib = _lib.load()
+    m = mask.to(torch.uint8).contiguous()
+    N, S = m.shape
+    bits = torch.empty((N, (S + 63) // 64), device=m.device, dtype=torch.int64)
+    _lib.check(lib.opadpo_op_pack_mask(m.data_ptr(), bits.data_ptr(), N, S, ctypes.c_void_p(_stream())), "pack_mask")
+    return bits
+
+
+def _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits):
+    d = AttnDesc()
+    d.N, d.S, d.H, d.HD, d.causal, d.scale = N, S, H, HD, int(causal), scale
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    d.q, d.k, d.v, d.ld_qkv = q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0)
+    d.o, d.ld_o = o.data_ptr(), o.stride(0)
+    d.lse = _ptr(lse)
+    d.kbits = _ptr(kbits)
+    return d
+
+
+def attn_fwd(q, k, v, o, lse, *, N, S, H, HD, causal, scale, kbits=None):
+    """q,k,v,o: [N*S, H*HD] bf16 views; lse: [N*S, H] f32 (or None)."""
+    lib = _lib.load()
+    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits)
+    _lib.check(lib.opadpo_op_attn_fwd(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_attn_fwd")
+    return o
+
+
+def attn_bwd(q, k, v, o, lse, dO, dq, dk, dv, delta, *, N, S, H, HD, causal, scale, kbits=None):
+    lib = _lib.load()
+    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits)
+    d.dO, d.ld_do = dO.data_ptr(), dO.stride(0)
+    d.delta = delta.data_ptr()
+    assert dq.stride(0) == dk.stride(0) == dv.stride(0)
+    d.dq, d.dk, d.dv, d.ld_dqkv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dq.stride(0)
+    _lib.check(lib.opadpo_op_attn_bwd(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_attn_bwd")
