@@ -90,6 +90,102 @@ int opadpo_op_attn_fwd(const opadpo_attn_desc* d, void* stream);
 int opadpo_op_attn_bwd(const opadpo_attn_desc* d, void* stream);
 int opadpo_op_pack_mask(const uint8_t* mask, uint64_t* bits, int32_t N, int32_t S, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator level: one DPO preference pair — per-token sigmoid log-ratio loss, its gradient w.r.t. the policy
+ * log-probs, the AncPO anchor term and the masked-mean reward statistics, in one single-CTA warp-reduce kernel.
+ * Replaces DPOTrainer.dpo_loss (opadpo/dpo_models/dpo_trainer.py:429-473), the `.mean()` reductions of
+ * compute_policy_loss (:631,693), the anchor (:702-712) and the reward stats (:785-796).
+ * All pointers are device f32 [n] (n = b*R); s_c/s_r/d_c/d_r may be NULL. d_c/d_r are accumulated (+=).
+ * out[8] = {mean loss, mean anchor, masked-mean chosen reward, masked-mean rejected reward, #chosen mask,
+ *          #rejected mask, 0, 0} where reward = beta*(pi - ref) and mask = (ref != 0).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct opadpo_dpo_pair_desc {
+  const float *pi_c, *pi_r, *ref_c, *ref_r;
+  const float *s_c, *s_r;
+  float *d_c, *d_r;
+  float* out;
+  int64_t n;
+  float beta, label_smoothing;
+  int32_t reference_free;
+  int32_t divergence;      /* 0 reverse_kl, 1 js_divergence, 2 alpha_divergence */
+  float alpha_div;
+  float loss_coef;         /* weight of mean(loss) in the total loss */
+  int32_t anchor_mode;     /* 0 none, 1 mDPO: -logsigmoid(sign*(cr - a)), 2: (cr - a)^2 */
+  float anchor_sign, anchor_value, anchor_coef;
+  float grad_scale;        /* multiplies every gradient (1/gradient_accumulation_steps) */
+} opadpo_dpo_pair_desc;
+int opadpo_op_dpo_pair(const opadpo_dpo_pair_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine level. One engine per process per GPU (current CUDA device at create time). The engine owns the base
+ * weights (bf16), two LoRA adapter sets (0 = lora_policy, 1 = lora_ref_policy; qlora_model.py:21,66-93), the
+ * trainable adapter's fp32 masters / gradients / Adam moments as ONE flat bucket, and all activations.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct opadpo_engine opadpo_engine;
+
+typedef struct opadpo_config {
+  /* LLaMA decoder [UPSTREAM LlamaConfig] */
+  int32_t d_model, n_layers, n_heads, d_ffn, vocab;
+  float rms_eps, rope_theta;
+  int32_t max_positions;
+  /* CLIP vision tower [UPSTREAM CLIPVisionConfig]; v_layers = number of encoder layers EXECUTED
+   * (mm_vision_select_layer = -2 on a 24-layer tower -> 23; llava_modifications.patch:15185-15217) */
+  int32_t v_d, v_layers, v_heads, v_ffn, v_image, v_patch;
+  float v_eps;
+  /* LoRA (opa_train.py:466-484): r, alpha; targets = every Linear but lm_head */
+  int32_t lora_r;
+  float lora_alpha;
+  int32_t pad_id, eos_id, image_token;   /* 0, 2, -200 (utils/constants.py:20-33) */
+} opadpo_config;
+
+enum { OPADPO_DT_BF16 = 0, OPADPO_DT_F32 = 1 };
+
+int opadpo_engine_create(const opadpo_config* cfg, opadpo_engine** out);
+int opadpo_engine_destroy(opadpo_engine* e);
+/* Copy one base tensor (HF state-dict name, e.g. "model.layers.3.self_attn.q_proj.weight") from device memory. */
+int opadpo_engine_load_tensor(opadpo_engine* e, const char* name, const void* dev_ptr, int32_t dtype, int64_t rows,
+                              int64_t cols, void* stream);
+/* Copy one LoRA pair for module path `module` (e.g. "model.layers.3.self_attn.q_proj"): A [r, in], B [out, r]. */
+int opadpo_engine_load_lora(opadpo_engine* e, int32_t adapter, const char* module, const void* A, const void* B,
+                            int32_t dtype, void* stream);
+int opadpo_engine_export_lora(opadpo_engine* e, int32_t adapter, const char* module, float* A_out, float* B_out,
+                              void* stream);
+/* Shape of a LoRA target: in/out features; returns OPADPO_EINVAL if `module` is not a LoRA target. */
+int opadpo_engine_lora_shape(opadpo_engine* e, const char* module, int64_t* in_features, int64_t* out_features);
+/* Make `adapter` trainable: allocates fp32 masters (from the current values), gradient bucket and Adam moments. */
+int opadpo_engine_set_trainable(opadpo_engine* e, int32_t adapter);
+/* Flat buffers of the trainable adapter (device pointers; n_train leading elements receive gradients). */
+int opadpo_engine_buffers(opadpo_engine* e, float** master, float** grad, float** exp_avg, float** exp_avg_sq,
+                          int64_t* n_total, int64_t* n_train);
+/* Where module's A [groups*r... see DESIGN.md] and B live inside the flat bucket (element offsets). */
+int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* offA, int64_t* offB);
+/* After the caller modified the fp32 masters directly (e.g. optimizer state restore): refresh the bf16 shadows. */
+int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream);
+
+/* AutoregressivePolicy.forward (opadpo/dpo_models/rl_models.py:75-144): K responses per query, stacked [K*b] rows.
+ *   images [b,3,v_image,v_image] f32; queries int64 [b,Q] (left-padded, one image_token); qmask u8 [b,Q];
+ *   img_mask u8 [b,P] or NULL (CoPO 'attention' holes, rl_models.py:103-105); responses: K device pointers to
+ *   int64 [b,R] (right-padded). out_logprobs / out_entropies (nullable): f32 [K,b,R].
+ *   save_slot: -1 = inference; 0/1 = keep activations for opadpo_backward(slot). */
+int opadpo_forward_logprobs(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
+                            const uint8_t* qmask, const uint8_t* img_mask, int32_t Q, int32_t K,
+                            const int64_t* const* responses, int32_t R, float temperature, float* out_logprobs,
+                            float* out_entropies, int32_t save_slot, void* stream);
+/* d(loss)/d(logprobs) [K,b,R] f32 -> accumulates LoRA gradients into the flat bucket (autograd of rl_models.py:120
+ * through the trainable adapter; rl_trainer.py:162). Releases the slot. */
+int opadpo_backward(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, void* stream);
+int opadpo_zero_grad(opadpo_engine* e, void* stream);
+/* clip_grad_norm_ (rl_trainer.py:165-168) + AdamW (utils/trainer_utils.py:9-38) over the flat bucket.
+ * grad_scale multiplies the bucket first (1/world_size after a sum all-reduce). grad_norm_out: device f32 or NULL. */
+int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          float max_grad_norm, float grad_scale, float* grad_norm_out, void* stream);
+/* Greedy rollout (online_generator.py:292-309 with do_sample=False; rl_models.py:166-188): writes
+ * out_ids int64 [b, Q + max_new] = queries | generated (pad after EOS). adapter = -1 runs the bare base model. */
+int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
+                    const uint8_t* qmask, int32_t Q, int32_t max_new, int64_t* out_ids, void* stream);
+/* Number of kernels this library has launched so far in this process. */
+int64_t opadpo_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

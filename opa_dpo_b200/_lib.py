@@ -68,7 +68,77 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class DpoPairDesc(ctypes.Structure):
+    _fields_ = [
+        ("pi_c", ctypes.c_void_p), ("pi_r", ctypes.c_void_p), ("ref_c", ctypes.c_void_p), ("ref_r", ctypes.c_void_p),
+        ("s_c", ctypes.c_void_p), ("s_r", ctypes.c_void_p),
+        ("d_c", ctypes.c_void_p), ("d_r", ctypes.c_void_p),
+        ("out", ctypes.c_void_p),
+        ("n", ctypes.c_int64),
+        ("beta", ctypes.c_float), ("label_smoothing", ctypes.c_float),
+        ("reference_free", ctypes.c_int32), ("divergence", ctypes.c_int32),
+        ("alpha_div", ctypes.c_float), ("loss_coef", ctypes.c_float),
+        ("anchor_mode", ctypes.c_int32),
+        ("anchor_sign", ctypes.c_float), ("anchor_value", ctypes.c_float), ("anchor_coef", ctypes.c_float),
+        ("grad_scale", ctypes.c_float),
+    ]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32),
+        ("d_ffn", ctypes.c_int32), ("vocab", ctypes.c_int32),
+        ("rms_eps", ctypes.c_float), ("rope_theta", ctypes.c_float),
+        ("max_positions", ctypes.c_int32),
+        ("v_d", ctypes.c_int32), ("v_layers", ctypes.c_int32), ("v_heads", ctypes.c_int32),
+        ("v_ffn", ctypes.c_int32), ("v_image", ctypes.c_int32), ("v_patch", ctypes.c_int32),
+        ("v_eps", ctypes.c_float),
+        ("lora_r", ctypes.c_int32), ("lora_alpha", ctypes.c_float),
+        ("pad_id", ctypes.c_int32), ("eos_id", ctypes.c_int32), ("image_token", ctypes.c_int32),
+    ]
+
+
+# every symbol include/opadpo_b200.h declares (tests check the built library exports all of them)
+EXPORTED_SYMBOLS = [
+    "opadpo_last_error", "opadpo_abi_version", "opadpo_op_gemm", "opadpo_gemm_n_tiles", "opadpo_op_attn_fwd",
+    "opadpo_op_attn_bwd", "opadpo_op_pack_mask", "opadpo_op_dpo_pair", "opadpo_engine_create", "opadpo_engine_destroy",
+    "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
+    "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
+    "opadpo_forward_logprobs", "opadpo_backward", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
+    "opadpo_launch_count",
+]
+
+
+def _declare_engine(lib):
+    c = ctypes
+    vp, i32, i64, f32 = c.c_void_p, c.c_int32, c.c_int64, c.c_float
+    lib.opadpo_op_dpo_pair.argtypes = [c.POINTER(DpoPairDesc), vp]
+    lib.opadpo_engine_create.argtypes = [c.POINTER(Config), c.POINTER(vp)]
+    lib.opadpo_engine_destroy.argtypes = [vp]
+    lib.opadpo_engine_load_tensor.argtypes = [vp, c.c_char_p, vp, i32, i64, i64, vp]
+    lib.opadpo_engine_load_lora.argtypes = [vp, i32, c.c_char_p, vp, vp, i32, vp]
+    lib.opadpo_engine_export_lora.argtypes = [vp, i32, c.c_char_p, vp, vp, vp]
+    lib.opadpo_engine_lora_shape.argtypes = [vp, c.c_char_p, c.POINTER(i64), c.POINTER(i64)]
+    lib.opadpo_engine_set_trainable.argtypes = [vp, i32]
+    lib.opadpo_engine_buffers.argtypes = [vp, c.POINTER(vp), c.POINTER(vp), c.POINTER(vp), c.POINTER(vp),
+                                          c.POINTER(i64), c.POINTER(i64)]
+    lib.opadpo_engine_lora_offsets.argtypes = [vp, c.c_char_p, c.POINTER(i64), c.POINTER(i64)]
+    lib.opadpo_engine_sync_shadow.argtypes = [vp, vp]
+    lib.opadpo_forward_logprobs.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, c.POINTER(vp), i32, f32, vp, vp,
+                                            i32, vp]
+    lib.opadpo_backward.argtypes = [vp, i32, vp, vp]
+    lib.opadpo_zero_grad.argtypes = [vp, vp]
+    lib.opadpo_optimizer_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]
+    lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp]
+    lib.opadpo_launch_count.argtypes = []
+    lib.opadpo_launch_count.restype = c.c_int64
+    for name in EXPORTED_SYMBOLS:
+        if name not in ("opadpo_last_error", "opadpo_launch_count"):
+            getattr(lib, name).restype = c.c_int
+
+
 def _declare(lib):
+    _declare_engine(lib)
     lib.opadpo_last_error.restype = ctypes.c_char_p
     lib.opadpo_abi_version.restype = ctypes.c_int
     lib.opadpo_gemm_n_tiles.argtypes = [ctypes.c_int32]

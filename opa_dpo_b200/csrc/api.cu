@@ -6,9 +6,12 @@
 #include "common.h"
 #include "attention.h"
 #include "gemm.h"
+#include "elementwise.h"
+#include "engine.h"
 
 namespace opadpo {
 thread_local char g_last_error[1024] = {0};
+std::atomic<int64_t> g_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -22,7 +25,8 @@ using namespace opadpo;
 extern "C" {
 
 const char* opadpo_last_error(void) { return g_last_error; }
-int opadpo_abi_version(void) { return 1; }
+int opadpo_abi_version(void) { return 2; }
+int64_t opadpo_launch_count(void) { return g_launches.load(); }
 
 int opadpo_gemm_n_tiles(int32_t N) { return gemm_num_n_tiles(N); }
 
@@ -109,6 +113,127 @@ int opadpo_op_pack_mask(const uint8_t* mask, uint64_t* bits, int32_t N, int32_t 
   int rc = attn_pack_mask(mask, bits, N, S, static_cast<cudaStream_t>(stream));
   if (rc != 0) { set_error("pack_mask launch failed"); return OPADPO_ECUDA; }
   return OPADPO_OK;
+}
+
+int opadpo_op_dpo_pair(const opadpo_dpo_pair_desc* d, void* stream) {
+  g_last_error[0] = 0;
+  if (!d || !d->pi_c || !d->pi_r || !d->ref_c || !d->ref_r || !d->out || d->n <= 0) {
+    set_error("opadpo_op_dpo_pair: null pointer or n <= 0");
+    return OPADPO_EINVAL;
+  }
+  DpoPairArgs a;
+  a.pi_c = d->pi_c; a.pi_r = d->pi_r; a.ref_c = d->ref_c; a.ref_r = d->ref_r;
+  a.s_c = d->s_c; a.s_r = d->s_r; a.d_c = d->d_c; a.d_r = d->d_r; a.out = d->out; a.n = d->n;
+  a.beta = d->beta; a.label_smoothing = d->label_smoothing; a.reference_free = d->reference_free;
+  a.divergence = d->divergence; a.alpha_div = d->alpha_div; a.loss_coef = d->loss_coef;
+  a.anchor_mode = d->anchor_mode; a.anchor_sign = d->anchor_sign; a.anchor_value = d->anchor_value;
+  a.anchor_coef = d->anchor_coef; a.grad_scale = d->grad_scale;
+  int rc = dpo_pair_loss(a, static_cast<cudaStream_t>(stream));
+  if (rc != 0) { set_error("dpo_pair_loss launch failed"); return OPADPO_ECUDA; }
+  return OPADPO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- engine level
+struct opadpo_engine {
+  Engine* impl;
+};
+
+#define ENGINE_GUARD(e)                                   \
+  g_last_error[0] = 0;                                    \
+  if (!(e) || !(e)->impl) {                               \
+    set_error("%s: null engine", __func__);               \
+    return OPADPO_EINVAL;                                 \
+  }
+
+int opadpo_engine_create(const opadpo_config* cfg, opadpo_engine** out) {
+  g_last_error[0] = 0;
+  if (!cfg || !out) { set_error("opadpo_engine_create: null argument"); return OPADPO_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("opadpo_engine_create: no CUDA device (the engine has no CPU path)");
+    return OPADPO_ECUDA;
+  }
+  Engine* impl = new Engine(*cfg);
+  int rc = impl->init();
+  if (rc != 0) { delete impl; return rc; }
+  *out = new opadpo_engine{impl};
+  return OPADPO_OK;
+}
+int opadpo_engine_destroy(opadpo_engine* e) {
+  if (!e) return OPADPO_OK;
+  delete e->impl;
+  delete e;
+  return OPADPO_OK;
+}
+int opadpo_engine_load_tensor(opadpo_engine* e, const char* name, const void* dev_ptr, int32_t dtype, int64_t rows,
+                              int64_t cols, void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->load_tensor(name, dev_ptr, dtype, rows, cols, static_cast<cudaStream_t>(stream));
+}
+int opadpo_engine_load_lora(opadpo_engine* e, int32_t adapter, const char* module, const void* A, const void* B,
+                            int32_t dtype, void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->load_lora(adapter, module, A, B, dtype, static_cast<cudaStream_t>(stream));
+}
+int opadpo_engine_export_lora(opadpo_engine* e, int32_t adapter, const char* module, float* A_out, float* B_out,
+                              void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->export_lora(adapter, module, A_out, B_out, static_cast<cudaStream_t>(stream));
+}
+int opadpo_engine_lora_shape(opadpo_engine* e, const char* module, int64_t* in_features, int64_t* out_features) {
+  ENGINE_GUARD(e);
+  return e->impl->lora_shape(module, in_features, out_features);
+}
+int opadpo_engine_set_trainable(opadpo_engine* e, int32_t adapter) {
+  ENGINE_GUARD(e);
+  return e->impl->set_trainable(adapter);
+}
+int opadpo_engine_buffers(opadpo_engine* e, float** master, float** grad, float** exp_avg, float** exp_avg_sq,
+                          int64_t* n_total, int64_t* n_train) {
+  ENGINE_GUARD(e);
+  return e->impl->buffers(master, grad, exp_avg, exp_avg_sq, n_total, n_train);
+}
+int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* offA, int64_t* offB) {
+  ENGINE_GUARD(e);
+  return e->impl->lora_offsets(module, offA, offB);
+}
+int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->sync_shadow(static_cast<cudaStream_t>(stream));
+}
+int opadpo_forward_logprobs(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
+                            const uint8_t* qmask, const uint8_t* img_mask, int32_t Q, int32_t K,
+                            const int64_t* const* responses, int32_t R, float temperature, float* out_logprobs,
+                            float* out_entropies, int32_t save_slot, void* stream) {
+  ENGINE_GUARD(e);
+  if (!images || !queries || !qmask || !responses || !out_logprobs) {
+    set_error("opadpo_forward_logprobs: null pointer");
+    return OPADPO_EINVAL;
+  }
+  return e->impl->forward_logprobs(adapter, images, b, queries, qmask, img_mask, Q, K, responses, R, temperature,
+                                   out_logprobs, out_entropies, save_slot, static_cast<cudaStream_t>(stream));
+}
+int opadpo_backward(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, void* stream) {
+  ENGINE_GUARD(e);
+  if (!dlogprobs) { set_error("opadpo_backward: null dlogprobs"); return OPADPO_EINVAL; }
+  return e->impl->backward(save_slot, dlogprobs, static_cast<cudaStream_t>(stream));
+}
+int opadpo_zero_grad(opadpo_engine* e, void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->zero_grad(static_cast<cudaStream_t>(stream));
+}
+int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          float max_grad_norm, float grad_scale, float* grad_norm_out, void* stream) {
+  ENGINE_GUARD(e);
+  return e->impl->optimizer_step(lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, grad_norm_out,
+                                 static_cast<cudaStream_t>(stream));
+}
+int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
+                    const uint8_t* qmask, int32_t Q, int32_t max_new, int64_t* out_ids, void* stream) {
+  ENGINE_GUARD(e);
+  if (!images || !queries || !qmask || !out_ids) { set_error("opadpo_generate: null pointer"); return OPADPO_EINVAL; }
+  return e->impl->generate(adapter, images, b, queries, qmask, Q, max_new, out_ids, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

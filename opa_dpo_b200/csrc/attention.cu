@@ -8,6 +8,7 @@
 
 #include <cstdio>
 
+#include "common.h"
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -736,6 +737,7 @@ int launch_fwd(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 grid((a.S + BQ - 1) / BQ, a.H, a.N);
   kern<<<grid, NTHREADS, FwdSmem<HD>::TOTAL, stream>>>(mq, mk, mv, make_params(a));
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "attn fwd launch: %s", cudaGetErrorString(e));
@@ -771,6 +773,7 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
   kdq<<<gq, NTHREADS, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
   dim3 gk((a.S + BKV - 1) / BKV, a.H, a.N);
   kdkv<<<gk, NTHREADS, DkvSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  count_launch(3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "attn bwd launch: %s", cudaGetErrorString(e));
@@ -802,6 +805,7 @@ int attn_pack_mask(const uint8_t* mask, uint64_t* bits, int N, int S, cudaStream
   const int nwords = (S + 63) / 64;
   const int total = N * nwords;
   pack_mask_kernel<<<(total + 127) / 128, 128, 0, stream>>>(mask, bits, N, S, nwords);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 

@@ -1,0 +1,936 @@
+// HBM-bound kernels of the OPA-DPO hot path (see elementwise.h). sm_100a; 16-byte vector accesses, fp32 math.
+#include "elementwise.h"
+
+#include <cmath>
+#include <cstdio>
+
+#include "common.h"
+
+namespace opadpo {
+namespace {
+
+constexpr int kIgnore = -1;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum over the block (all threads get the result). red must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__device__ __forceinline__ int64_t map_row(int64_t r, const RowMap& m) {
+  if (m.rows_per_seq == 0) return r;
+  return (r / m.rows_per_seq) * m.seq_stride + m.seq_off + (r % m.rows_per_seq);
+}
+
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_MAXV = 4;  // up to 8192 columns held in registers
+
+// ---------------------------------------------------------------------------------------------- RMSNorm
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                    bf16* __restrict__ y, int d, float eps, RowMap map) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + map_row(r, map) * d);
+  const int nv = d >> 3;
+  uint4 xv[NORM_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      xv[i] = xr[v];
+      float f[8];
+      unpack8(xv[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / d + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + r * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      float f[8], g[8];
+      unpack8(xv[i], f);
+      unpack8(__ldg(wr + v), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = g[e] * bf16_round(f[e] * rstd);
+      yr[v] = pack8(f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NORM_THREADS)
+    rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                       const bf16* dres, bf16* dx, int d, float eps, RowMap map) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const int64_t fr = map_row(r, map);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + fr * d);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const int nv = d >> 3;
+  uint4 xv[NORM_MAXV], gv[NORM_MAXV];  // gv = w*dy packed as bf16 is lossy; keep dy and re-multiply
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      xv[i] = xr[v];
+      gv[i] = dyr[v];
+      float f[8], g[8], ww[8];
+      unpack8(xv[i], f);
+      unpack8(gv[i], g);
+      unpack8(__ldg(wr + v), ww);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ss += f[e] * f[e];
+        dot += ww[e] * g[e] * f[e];
+      }
+    }
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float rstd = rsqrtf(ss / d + eps);
+  const float c = dot / d * rstd * rstd * rstd;
+  uint4* dxr = reinterpret_cast<uint4*>(dx + fr * d);
+  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + fr * d) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      float f[8], g[8], ww[8], o[8];
+      unpack8(xv[i], f);
+      unpack8(gv[i], g);
+      unpack8(__ldg(wr + v), ww);
+      if (drr) {
+        unpack8(drr[v], o);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += rstd * ww[e] * g[e] - f[e] * c;
+      dxr[v] = pack8(o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NORM_THREADS)
+    layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                         bf16* __restrict__ y, int d, float eps) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + r * d);
+  const int nv = d >> 3;
+  uint4 xv[NORM_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      xv[i] = xr[v];
+      float f[8];
+      unpack8(xv[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[e];
+    }
+  }
+  const float mean = block_sum(s, red) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      float f[8];
+      unpack8(xv[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += (f[e] - mean) * (f[e] - mean);
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / d + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + r * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const uint4* br = reinterpret_cast<const uint4*>(b);
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
+      float f[8], g[8], h[8];
+      unpack8(xv[i], f);
+      unpack8(__ldg(wr + v), g);
+      unpack8(__ldg(br + v), h);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + h[e];
+      yr[v] = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- RoPE
+__global__ void rope_kernel(bf16* x, int64_t ld, int64_t T, int S, const int32_t* __restrict__ pos, int pos_offset,
+                            int nheads, int hd, const float2* __restrict__ cs, int inverse) {
+  const int vec_per_head = hd >> 4;  // uint4 vectors in half a head
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = T * nheads * vec_per_head;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % vec_per_head);
+  const int h = static_cast<int>((idx / vec_per_head) % nheads);
+  const int64_t t = idx / (static_cast<int64_t>(vec_per_head) * nheads);
+  const int p = (pos ? pos[t] : static_cast<int>(t % S)) + pos_offset;
+  bf16* base = x + t * ld + h * hd + v * 8;
+  uint4 lo = *reinterpret_cast<uint4*>(base);
+  uint4 hi = *reinterpret_cast<uint4*>(base + (hd >> 1));
+  float a[8], b[8];
+  unpack8(lo, a);
+  unpack8(hi, b);
+  const float2* c = cs + static_cast<int64_t>(p) * (hd >> 1) + v * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 k = __ldg(c + e);
+    const float sn = inverse ? -k.y : k.y;
+    const float na = a[e] * k.x - b[e] * sn;
+    const float nb = b[e] * k.x + a[e] * sn;
+    a[e] = na;
+    b[e] = nb;
+  }
+  *reinterpret_cast<uint4*>(base) = pack8(a);
+  *reinterpret_cast<uint4*>(base + (hd >> 1)) = pack8(b);
+}
+
+__global__ void rope_table_kernel(float2* cs, int max_pos, int half, float theta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= max_pos * half) return;
+  const int p = idx / half, j = idx % half;
+  // inv_freq = theta^(-2j/hd) in fp32, angle = p * inv_freq in fp32 (HF LlamaRotaryEmbedding arithmetic)
+  const float inv = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(2 * half));
+  const float ang = static_cast<float>(p) * inv;
+  cs[idx] = make_float2(cosf(ang), sinf(ang));
+}
+
+// ---------------------------------------------------------------------------------------------- SwiGLU / GELU
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int64_t T, int F) {
+  const int fv = F >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= T * fv) return;
+  const int64_t t = idx / fv;
+  const int v = static_cast<int>(idx % fv);
+  const uint4* row = reinterpret_cast<const uint4*>(gu + t * 2 * F);
+  float g[8], u[8];
+  unpack8(row[v], g);
+  unpack8(row[fv + v], u);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) g[e] = bf16_round(g[e] / (1.f + __expf(-g[e]))) * u[e];
+  reinterpret_cast<uint4*>(act + t * F)[v] = pack8(g);
+}
+
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
+                                  int64_t T, int F) {
+  const int fv = F >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= T * fv) return;
+  const int64_t t = idx / fv;
+  const int v = static_cast<int>(idx % fv);
+  const uint4* row = reinterpret_cast<const uint4*>(gu + t * 2 * F);
+  float g[8], u[8], da[8], dg[8], du[8];
+  unpack8(row[v], g);
+  unpack8(row[fv + v], u);
+  unpack8(reinterpret_cast<const uint4*>(dact + t * F)[v], da);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float sg = 1.f / (1.f + __expf(-g[e]));
+    const float silu = g[e] * sg;
+    du[e] = da[e] * silu;
+    dg[e] = da[e] * u[e] * sg * (1.f + g[e] * (1.f - sg));
+  }
+  uint4* orow = reinterpret_cast<uint4*>(dgu + t * 2 * F);
+  orow[v] = pack8(dg);
+  orow[fv + v] = pack8(du);
+}
+
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nv) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  float f[8];
+  unpack8(reinterpret_cast<const uint4*>(x)[idx], f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752f));
+  reinterpret_cast<uint4*>(y)[idx] = pack8(f);
+}
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nv) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  float f[8], g[8];
+  unpack8(reinterpret_cast<const uint4*>(x)[idx], f);
+  unpack8(reinterpret_cast<const uint4*>(dy)[idx], g);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float cdf = 0.5f * (1.f + erff(f[e] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * f[e] * f[e]);
+    g[e] *= cdf + f[e] * pdf;
+  }
+  reinterpret_cast<uint4*>(dx)[idx] = pack8(g);
+}
+
+// ---------------------------------------------------------------------------------------------- embedding splice
+__global__ void find_image_pos_kernel(const int32_t* __restrict__ ids, int32_t* __restrict__ img_pos, int N, int L,
+                                      int image_token) {
+  const int n = blockIdx.x;
+  if (n >= N) return;
+  int found = L;  // no image token: slot placed past the end (all rows are text)
+  for (int i = threadIdx.x; i < L; i += blockDim.x)
+    if (ids[static_cast<int64_t>(n) * L + i] == image_token) found = min(found, i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+  if (threadIdx.x == 0) img_pos[n] = found;
+}
+
+__global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const uint8_t* __restrict__ tok_mask,
+                                    const uint8_t* __restrict__ img_mask, const int32_t* __restrict__ img_of_row,
+                                    const bf16* __restrict__ table, const bf16* __restrict__ feats, bf16* __restrict__ out,
+                                    uint8_t* __restrict__ out_mask, const int32_t* __restrict__ img_pos, int L, int P,
+                                    int d, int vocab) {
+  const int S = L - 1 + P;
+  const int64_t row = blockIdx.x;  // n * S + s
+  const int n = static_cast<int>(row / S);
+  const int s = static_cast<int>(row % S);
+  const int p0 = img_pos[n];
+  const uint4* src;
+  uint8_t m;
+  if (s >= p0 && s < p0 + P) {
+    src = reinterpret_cast<const uint4*>(feats + (static_cast<int64_t>(img_of_row[n]) * P + (s - p0)) * d);
+    m = img_mask ? img_mask[static_cast<int64_t>(img_of_row[n]) * P + (s - p0)] : 1;
+  } else {
+    const int l = s < p0 ? s : s - P + 1;
+    int id = ids[static_cast<int64_t>(n) * L + l];
+    id = min(max(id, 0), vocab - 1);
+    src = reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d);
+    m = tok_mask[static_cast<int64_t>(n) * L + l];
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + row * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) dst[v] = __ldg(src + v);
+  if (threadIdx.x == 0 && out_mask) out_mask[row] = m;
+}
+
+__global__ void embed_splice_bwd_kernel(const bf16* __restrict__ dX, const int32_t* __restrict__ img_of_row,
+                                        const int32_t* __restrict__ img_pos, bf16* __restrict__ dfeats, int N, int S,
+                                        int P, int d) {
+  const int64_t fr = blockIdx.x;  // img * P + p
+  const int img = static_cast<int>(fr / P), p = static_cast<int>(fr % P);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int n = 0; n < N; ++n) {
+      if (img_of_row[n] != img) continue;
+      float f[8];
+      unpack8(reinterpret_cast<const uint4*>(dX + (static_cast<int64_t>(n) * S + img_pos[n] + p) * d)[v], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    reinterpret_cast<uint4*>(dfeats + fr * d)[v] = pack8(acc);
+  }
+}
+
+__global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table, bf16* __restrict__ out,
+                                  int d, int vocab) {
+  const int r = blockIdx.x;
+  const int id = min(max(ids[r], 0), vocab - 1);
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) dst[v] = __ldg(src + v);
+}
+
+// ---------------------------------------------------------------------------------------------- CLIP front end
+__global__ void clip_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int n, int R, int ps, int Kp) {
+  const int g = R / ps;
+  const int P = g * g;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(n) * P * Kp;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx % Kp);
+  const int64_t pr = idx / Kp;
+  const int p = static_cast<int>(pr % P);
+  const int im = static_cast<int>(pr / P);
+  float v = 0.f;
+  if (k < 3 * ps * ps) {
+    const int c = k / (ps * ps), rem = k % (ps * ps);
+    const int ky = rem / ps, kx = rem % ps;
+    const int py = p / g, px = p % g;
+    v = img[((static_cast<int64_t>(im) * 3 + c) * R + (py * ps + ky)) * R + (px * ps + kx)];
+  }
+  patches[idx] = __float2bfloat16(v);
+}
+
+__global__ void clip_assemble_kernel(const bf16* __restrict__ pe, const bf16* __restrict__ cls, const bf16* __restrict__ pos,
+                                     bf16* __restrict__ out, int P, int d) {
+  const int64_t row = blockIdx.x;  // n * (P+1) + t
+  const int t = static_cast<int>(row % (P + 1));
+  const int n = static_cast<int>(row / (P + 1));
+  const uint4* a = t == 0 ? reinterpret_cast<const uint4*>(cls)
+                          : reinterpret_cast<const uint4*>(pe + (static_cast<int64_t>(n) * P + (t - 1)) * d);
+  const uint4* b = reinterpret_cast<const uint4*>(pos + static_cast<int64_t>(t) * d);
+  uint4* o = reinterpret_cast<uint4*>(out + row * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
+    float f[8], g[8];
+    unpack8(a[v], f);
+    unpack8(b[v], g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] += g[e];
+    o[v] = pack8(f);
+  }
+}
+
+__global__ void clip_drop_cls_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int P, int d) {
+  const int64_t row = blockIdx.x;  // n * P + p
+  const int p = static_cast<int>(row % P);
+  const int n = static_cast<int>(row / P);
+  const uint4* a = reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(n) * (P + 1) + 1 + p) * d);
+  uint4* o = reinterpret_cast<uint4*>(out + row * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) o[v] = a[v];
+}
+
+// ---------------------------------------------------------------------------------------------- log-prob finalise
+__global__ void logprob_finalize_kernel(const float4* __restrict__ partials, int ntiles, const float* __restrict__ label_logit,
+                                        const int32_t* __restrict__ labels, float* __restrict__ logprob,
+                                        float* __restrict__ entropy, float* __restrict__ lse_out, int64_t M) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  constexpr float LN2 = 0.6931471805599453f;
+  float m = -INFINITY;
+  for (int i = 0; i < ntiles; ++i) m = fmaxf(m, partials[r * ntiles + i].x);
+  float s = 0.f, zs = 0.f;
+  for (int i = 0; i < ntiles; ++i) {
+    const float4 p = partials[r * ntiles + i];
+    const float sc = exp2f(p.x - m);
+    s += p.y * sc;
+    zs += p.z * sc;
+  }
+  const float lse2 = m + log2f(s);
+  const float lse = lse2 * LN2;
+  const int label = labels[r];
+  const bool ok = label >= 0;
+  logprob[r] = ok ? (label_logit[r] - lse) : 0.f;
+  if (entropy) entropy[r] = ok ? (lse - (zs / s) * LN2) : 0.f;
+  if (lse_out) lse_out[r] = lse;
+}
+
+// ---------------------------------------------------------------------------------------------- DPO loss
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
+__device__ __forceinline__ float logsigmoid_f(float x) { return fminf(x, 0.f) - log1pf(__expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(1024) dpo_pair_kernel(DpoPairArgs a) {
+  __shared__ float red[32];
+  constexpr float EXP_CAP = 88.7228f;  // floor(log(FLT_MAX)*1e4)/1e4  (dpo_trainer.py:74-81, fp32)
+  float sl = 0.f, sa = 0.f, scr = 0.f, smc = 0.f, srr = 0.f, smr = 0.f;
+  const float inv_n = 1.f / static_cast<float>(a.n);
+  for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const float rc = a.ref_c[i], rr = a.ref_r[i];
+    const float sc = a.s_c ? a.s_c[i] : 1.f, sr = a.s_r ? a.s_r[i] : 1.f;
+    const float dc = a.pi_c[i] - (a.reference_free ? 0.f : rc);
+    const float dr = a.pi_r[i] - (a.reference_free ? 0.f : rr);
+    float u, du_dc, du_dr;
+    if (a.divergence == 2) {
+      const float al = a.alpha_div;
+      const float xr = -al * dr, xc = -al * dc;
+      const float er = __expf(fminf(xr, EXP_CAP)), ec = __expf(fminf(xc, EXP_CAP));
+      u = (er - ec) / al;
+      du_dc = xc <= EXP_CAP ? ec : 0.f;
+      du_dr = xr <= EXP_CAP ? -er : 0.f;
+    } else {
+      u = sc * dc - sr * dr;
+      du_dc = sc;
+      du_dr = -sr;
+      if (a.divergence == 1) {
+        u -= softplus_f(dc) - softplus_f(dr);
+        du_dc -= sigmoid_f(dc);
+        du_dr += sigmoid_f(dr);
+      }
+    }
+    const float bu = a.beta * u;
+    const float loss = -logsigmoid_f(bu) * (1.f - a.label_smoothing) - logsigmoid_f(-bu) * a.label_smoothing;
+    const float dl_du = a.beta * (-(1.f - a.label_smoothing) * sigmoid_f(-bu) + a.label_smoothing * sigmoid_f(bu));
+    sl += loss;
+    float gc = a.loss_coef * inv_n * dl_du * du_dc;
+    float gr = a.loss_coef * inv_n * dl_du * du_dr;
+    const float cr = a.beta * dc, rrw = a.beta * dr;
+    if (a.anchor_mode == 1) {
+      const float z = a.anchor_sign * (cr - a.anchor_value);
+      sa += -logsigmoid_f(z);
+      gc += a.anchor_coef * inv_n * (-sigmoid_f(-z)) * a.anchor_sign * a.beta;
+    } else if (a.anchor_mode == 2) {
+      const float z = cr - a.anchor_value;
+      sa += z * z;
+      gc += a.anchor_coef * inv_n * 2.f * z * a.beta;
+    }
+    if (a.d_c) a.d_c[i] += gc * a.grad_scale;
+    if (a.d_r) a.d_r[i] += gr * a.grad_scale;
+    const float mc = rc != 0.f ? 1.f : 0.f, mr = rr != 0.f ? 1.f : 0.f;
+    scr += cr * mc;
+    smc += mc;
+    srr += rrw * mr;
+    smr += mr;
+  }
+  sl = block_sum(sl, red);
+  sa = block_sum(sa, red);
+  scr = block_sum(scr, red);
+  smc = block_sum(smc, red);
+  srr = block_sum(srr, red);
+  smr = block_sum(smr, red);
+  if (threadIdx.x == 0) {
+    a.out[0] = sl * inv_n;
+    a.out[1] = sa * inv_n;
+    a.out[2] = scr / smc;
+    a.out[3] = srr / smr;
+    a.out[4] = smc;
+    a.out[5] = smr;
+    a.out[6] = 0.f;
+    a.out[7] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- optimiser
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += g[i] * g[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void adamw_kernel(float* __restrict__ master, const float* __restrict__ grad, float* __restrict__ m,
+                             float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr, float b1, float b2,
+                             float eps, float wd, float bc1, float bc2, float gscale, const float* sumsq, float max_norm) {
+  float gs = gscale;
+  if (sumsq && max_norm > 0.f) {
+    const float norm = sqrtf(*sumsq) * gscale;
+    gs *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float g = grad[i] * gs;
+    float p = master[i];
+    p *= 1.f - lr * wd;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p -= (lr / bc1) * (mi / denom);
+    master[i] = p;
+    shadow[i] = __float2bfloat16(p);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+__global__ void norm_from_sumsq_kernel(const float* sumsq, float gscale, float* out) { *out = sqrtf(*sumsq) * gscale; }
+__global__ void fill_mod_kernel(int32_t* out, int n, int mod) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i % mod;
+}
+__global__ void queries_to_i32_kernel(const int64_t* __restrict__ q, const uint8_t* __restrict__ qm, int32_t* ids,
+                                      uint8_t* mask, int64_t* out, int64_t out_ld, int N, int Q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Q) return;
+  const int n = i / Q, l = i % Q;
+  ids[i] = static_cast<int32_t>(q[i]);
+  mask[i] = qm[i];
+  out[static_cast<int64_t>(n) * out_ld + l] = q[i];
+}
+
+// ---------------------------------------------------------------------------------------------- input stacking
+struct RespPtrs {
+  const int64_t* p[8];
+};
+__global__ void stack_inputs_kernel(const int64_t* __restrict__ queries, const uint8_t* __restrict__ qmask, RespPtrs resp,
+                                    int K, int b, int Q, int R, int pad_id, int32_t* __restrict__ ids,
+                                    uint8_t* __restrict__ mask, int32_t* __restrict__ labels) {
+  const int L = Q + R;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(K) * b * L) return;
+  const int l = static_cast<int>(idx % L);
+  const int row = static_cast<int>(idx / L);
+  const int k = row / b, i = row % b;
+  if (l < Q) {
+    ids[idx] = static_cast<int32_t>(queries[static_cast<int64_t>(i) * Q + l]);
+    mask[idx] = qmask[static_cast<int64_t>(i) * Q + l];
+  } else {
+    const int32_t id = static_cast<int32_t>(resp.p[k][static_cast<int64_t>(i) * R + (l - Q)]);
+    ids[idx] = id;
+    mask[idx] = id != pad_id;
+    labels[static_cast<int64_t>(row) * R + (l - Q)] = id != pad_id ? id : kIgnore;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- decode
+__global__ void kv_store_prefill_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, int S,
+                                        int S_max, int d) {
+  const int64_t row = blockIdx.x;  // n * S + s
+  const int n = static_cast<int>(row / S), s = static_cast<int>(row % S);
+  const uint4* k = reinterpret_cast<const uint4*>(qkv + row * 3 * d + d);
+  const uint4* v = reinterpret_cast<const uint4*>(qkv + row * 3 * d + 2 * d);
+  uint4* ko = reinterpret_cast<uint4*>(kc + (static_cast<int64_t>(n) * S_max + s) * d);
+  uint4* vo = reinterpret_cast<uint4*>(vc + (static_cast<int64_t>(n) * S_max + s) * d);
+  for (int i = threadIdx.x; i < (d >> 3); i += blockDim.x) {
+    ko[i] = k[i];
+    vo[i] = v[i];
+  }
+}
+
+// One CTA per (sequence, head): 128 threads; each warp strides over keys, lanes split the head dimension.
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
+                                                               bf16* __restrict__ vc, const uint8_t* __restrict__ kmask,
+                                                               bf16* __restrict__ o, int H, int len, int S_max, float scale) {
+  constexpr int EPL = HD / 32;  // elements per lane
+  const int n = blockIdx.y, h = blockIdx.x;
+  const int d = H * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* qrow = qkv + static_cast<int64_t>(n) * 3 * d + h * HD;
+  bf16* kbase = kc + static_cast<int64_t>(n) * S_max * d + h * HD;
+  bf16* vbase = vc + static_cast<int64_t>(n) * S_max * d + h * HD;
+  // append the new key/value at position len
+  if (warp == 0) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      kbase[static_cast<int64_t>(len) * d + lane * EPL + e] = qrow[d + lane * EPL + e];
+      vbase[static_cast<int64_t>(len) * d + lane * EPL + e] = qrow[2 * d + lane * EPL + e];
+    }
+  }
+  __syncthreads();
+  float q[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) q[e] = __bfloat162float(qrow[lane * EPL + e]) * scale;
+  float m = -INFINITY, l = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  const uint8_t* km = kmask + static_cast<int64_t>(n) * S_max;
+  for (int j = warp; j <= len; j += 4) {
+    if (!km[j]) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) s += q[e] * __bfloat162float(kbase[static_cast<int64_t>(j) * d + lane * EPL + e]);
+    s = warp_sum(s);
+    const float nm = fmaxf(m, s);
+    const float sc = __expf(m - nm);
+    const float p = __expf(s - nm);
+    l = l * sc + p;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e)
+      acc[e] = acc[e] * sc + p * __bfloat162float(vbase[static_cast<int64_t>(j) * d + lane * EPL + e]);
+    m = nm;
+  }
+  __shared__ float sm[4], sl[4], sacc[4][HD];
+  if (lane == 0) {
+    sm[warp] = m;
+    sl[warp] = l;
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) sacc[warp][lane * EPL + e] = acc[e];
+  __syncthreads();
+  if (warp == 0) {
+    float gm = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+    float tot = 0.f;
+    float out[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) out[e] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float sc = sm[w] == -INFINITY ? 0.f : __expf(sm[w] - gm);
+      tot += sl[w] * sc;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) out[e] += sacc[w][lane * EPL + e] * sc;
+    }
+    const float inv = tot > 0.f ? 1.f / tot : 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[static_cast<int64_t>(n) * d + h * HD + lane * EPL + e] = __float2bfloat16(out[e] * inv);
+  }
+}
+
+__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ logits, int V, int eos_id, int pad_id,
+                                                           uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld,
+                                                           int step) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  const int n = blockIdx.x;
+  const float* row = logits + static_cast<int64_t>(n) * V;
+  float best = -INFINITY;
+  int besti = V;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float x = row[i];
+    if (x > best || (x == best && i < besti)) {
+      best = x;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) {
+      best = ob;
+      besti = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    bv[warp] = best;
+    bi[warp] = besti;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < (blockDim.x >> 5) ? bv[lane] : -INFINITY;
+    besti = lane < (blockDim.x >> 5) ? bi[lane] : V;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
+    }
+    if (lane == 0) {
+      int id = besti;
+      if (done[n]) id = pad_id;  // HF: finished sequences are padded (unfinished_sequences mask)
+      if (id == eos_id) done[n] = 1;
+      next_ids[n] = id;
+      out[static_cast<int64_t>(n) * out_ld + step] = id;
+    }
+  }
+}
+
+inline int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[opadpo] %s launch failed: %s\n", what, cudaGetErrorString(e));
+    return -11;
+  }
+  return 0;
+}
+inline unsigned blocks_for(int64_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+inline unsigned capped_blocks(int64_t n, int threads, int cap) {
+  const int64_t b = (n + threads - 1) / threads;
+  return static_cast<unsigned>(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, RowMap map, cudaStream_t s) {
+  if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
+  if (rows == 0) return 0;
+  rmsnorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, y, d, eps, map);
+  return check_launch("rmsnorm_fwd");
+}
+int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
+                RowMap map, cudaStream_t s) {
+  if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
+  if (rows == 0) return 0;
+  rmsnorm_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, map);
+  return check_launch("rmsnorm_bwd");
+}
+int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s) {
+  if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
+  if (rows == 0) return 0;
+  layernorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, b, y, d, eps);
+  return check_launch("layernorm_fwd");
+}
+int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, int nheads, int hd,
+                 const float2* cs, int inverse, cudaStream_t s) {
+  if (hd % 16 != 0) return -1;
+  const int64_t total = T * nheads * (hd >> 4);
+  if (total == 0) return 0;
+  rope_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, ld, T, S, pos, pos_offset, nheads, hd, cs, inverse);
+  return check_launch("rope");
+}
+int rope_table(float2* cs, int max_pos, int hd, float theta, cudaStream_t s) {
+  const int total = max_pos * (hd / 2);
+  rope_table_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cs, max_pos, hd / 2, theta);
+  return check_launch("rope_table");
+}
+int swiglu_fwd(const bf16* gu, bf16* act, int64_t T, int F, cudaStream_t s) {
+  if (F % 8 != 0) return -1;
+  swiglu_fwd_kernel<<<blocks_for(T * (F >> 3), 256), 256, 0, s>>>(gu, act, T, F);
+  return check_launch("swiglu_fwd");
+}
+int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t T, int F, cudaStream_t s) {
+  if (F % 8 != 0) return -1;
+  swiglu_bwd_kernel<<<blocks_for(T * (F >> 3), 256), 256, 0, s>>>(dact, gu, dgu, T, F);
+  return check_launch("swiglu_bwd");
+}
+int gelu_fwd(const bf16* x, bf16* y, int64_t n, cudaStream_t s) {
+  if (n % 8 != 0) return -1;
+  gelu_fwd_kernel<<<blocks_for(n >> 3, 256), 256, 0, s>>>(x, y, n >> 3);
+  return check_launch("gelu_fwd");
+}
+int gelu_bwd(const bf16* dy, const bf16* x, bf16* dx, int64_t n, cudaStream_t s) {
+  if (n % 8 != 0) return -1;
+  gelu_bwd_kernel<<<blocks_for(n >> 3, 256), 256, 0, s>>>(dy, x, dx, n >> 3);
+  return check_launch("gelu_bwd");
+}
+int embed_splice(const int32_t* ids, const uint8_t* tok_mask, const uint8_t* img_mask, const int32_t* img_of_row,
+                 const bf16* table, const bf16* feats, bf16* out, uint8_t* out_mask, int32_t* img_pos, int N, int L, int P,
+                 int d, int vocab, cudaStream_t s) {
+  if (d % 8 != 0) return -1;
+  find_image_pos_kernel<<<N, 32, 0, s>>>(ids, img_pos, N, L, -200);
+  const int S = L - 1 + P;
+  embed_splice_kernel<<<static_cast<unsigned>(static_cast<int64_t>(N) * S), 128, 0, s>>>(
+      ids, tok_mask, img_mask, img_of_row, table, feats, out, out_mask, img_pos, L, P, d, vocab);
+  return check_launch("embed_splice");
+}
+int embed_splice_bwd(const bf16* dX, const int32_t* img_of_row, const int32_t* img_pos, bf16* dfeats, int N, int S, int n_img,
+                     int P, int d, cudaStream_t s) {
+  embed_splice_bwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n_img) * P), 128, 0, s>>>(dX, img_of_row, img_pos,
+                                                                                                 dfeats, N, S, P, d);
+  return check_launch("embed_splice_bwd");
+}
+int embed_rows(const int32_t* ids, const bf16* table, bf16* out, int rows, int d, int vocab, cudaStream_t s) {
+  embed_rows_kernel<<<rows, 128, 0, s>>>(ids, table, out, d, vocab);
+  return check_launch("embed_rows");
+}
+int clip_im2col(const float* images, bf16* patches, int n, int R, int ps, int Kp, cudaStream_t s) {
+  const int g = R / ps;
+  const int64_t total = static_cast<int64_t>(n) * g * g * Kp;
+  clip_im2col_kernel<<<blocks_for(total, 256), 256, 0, s>>>(images, patches, n, R, ps, Kp);
+  return check_launch("clip_im2col");
+}
+int clip_assemble(const bf16* patch_emb, const bf16* cls, const bf16* pos, bf16* out, int n, int P, int d, cudaStream_t s) {
+  clip_assemble_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n) * (P + 1)), 128, 0, s>>>(patch_emb, cls, pos, out, P, d);
+  return check_launch("clip_assemble");
+}
+int clip_drop_cls(const bf16* x, bf16* out, int n, int P, int d, cudaStream_t s) {
+  clip_drop_cls_kernel<<<static_cast<unsigned>(static_cast<int64_t>(n) * P), 128, 0, s>>>(x, out, P, d);
+  return check_launch("clip_drop_cls");
+}
+int logprob_finalize(const float4* partials, int ntiles, const float* label_logit, const int32_t* labels, float* logprob,
+                     float* entropy, float* lse, int64_t M, cudaStream_t s) {
+  if (M == 0) return 0;
+  logprob_finalize_kernel<<<blocks_for(M, 128), 128, 0, s>>>(partials, ntiles, label_logit, labels, logprob, entropy, lse, M);
+  return check_launch("logprob_finalize");
+}
+int dpo_pair_loss(const DpoPairArgs& a, cudaStream_t s) {
+  dpo_pair_kernel<<<1, 1024, 0, s>>>(a);
+  return check_launch("dpo_pair_loss");
+}
+int sumsq_accum(const float* g, int64_t n, float* out, cudaStream_t s) {
+  if (n == 0) return 0;
+  const unsigned blocks = capped_blocks(n / 4 + 1, 256, 148 * 8);
+  sumsq_kernel<<<blocks, 256, 0, s>>>(g, n, out);
+  return check_launch("sumsq");
+}
+int adamw_step(float* master, const float* grad, float* m, float* v, bf16* shadow, int64_t n, float lr, float b1, float b2,
+               float eps, float wd, int step, float gscale, const float* sumsq, float max_norm, cudaStream_t s) {
+  if (n == 0) return 0;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  const unsigned blocks = capped_blocks(n, 256, 148 * 16);
+  adamw_kernel<<<blocks, 256, 0, s>>>(master, grad, m, v, shadow, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, sumsq, max_norm);
+  return check_launch("adamw");
+}
+int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  f32_to_bf16_kernel<<<capped_blocks(n, 256, 148 * 16), 256, 0, s>>>(src, dst, n);
+  return check_launch("f32_to_bf16");
+}
+int bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  bf16_to_f32_kernel<<<capped_blocks(n, 256, 148 * 16), 256, 0, s>>>(src, dst, n);
+  return check_launch("bf16_to_f32");
+}
+int norm_from_sumsq(const float* sumsq, float gscale, float* out, cudaStream_t s) {
+  norm_from_sumsq_kernel<<<1, 1, 0, s>>>(sumsq, gscale, out);
+  return check_launch("norm_from_sumsq");
+}
+int fill_mod(int32_t* out, int n, int mod, cudaStream_t s) {
+  fill_mod_kernel<<<blocks_for(n, 128), 128, 0, s>>>(out, n, mod);
+  return check_launch("fill_mod");
+}
+int queries_to_i32(const int64_t* queries, const uint8_t* qmask, int32_t* ids, uint8_t* mask, int64_t* out, int64_t out_ld,
+                   int N, int Q, cudaStream_t s) {
+  queries_to_i32_kernel<<<blocks_for(static_cast<int64_t>(N) * Q, 256), 256, 0, s>>>(queries, qmask, ids, mask, out, out_ld, N, Q);
+  return check_launch("queries_to_i32");
+}
+int stack_inputs(const int64_t* queries, const uint8_t* qmask, const int64_t* const* responses, int K, int b, int Q, int R,
+                 int pad_id, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s) {
+  if (K > 8) return -1;
+  RespPtrs rp{};
+  for (int k = 0; k < K; ++k) rp.p[k] = responses[k];
+  const int64_t total = static_cast<int64_t>(K) * b * (Q + R);
+  stack_inputs_kernel<<<blocks_for(total, 256), 256, 0, s>>>(queries, qmask, rp, K, b, Q, R, pad_id, ids, mask, labels);
+  return check_launch("stack_inputs");
+}
+int kv_store_prefill(const bf16* qkv, bf16* kc, bf16* vc, int N, int S, int S_max, int d, cudaStream_t s) {
+  kv_store_prefill_kernel<<<static_cast<unsigned>(static_cast<int64_t>(N) * S), 128, 0, s>>>(qkv, kc, vc, S, S_max, d);
+  return check_launch("kv_store_prefill");
+}
+int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len,
+                     int S_max, float scale, cudaStream_t s) {
+  dim3 grid(H, N);
+  if (hd == 128)
+    decode_attention_kernel<128><<<grid, 128, 0, s>>>(qkv, kc, vc, kmask, o, H, len, S_max, scale);
+  else if (hd == 64)
+    decode_attention_kernel<64><<<grid, 128, 0, s>>>(qkv, kc, vc, kmask, o, H, len, S_max, scale);
+  else
+    return -1;
+  return check_launch("decode_attention");
+}
+int greedy_pick(const float* logits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
+                int64_t out_ld, int step, cudaStream_t s) {
+  greedy_pick_kernel<<<N, 1024, 0, s>>>(logits, V, eos_id, pad_id, done, next_ids, out, out_ld, step);
+  return check_launch("greedy_pick");
+}
+
+}  // namespace opadpo

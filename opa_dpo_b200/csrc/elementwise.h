@@ -1,0 +1,121 @@
+// HBM-bound kernels around the GEMMs: norms, RoPE, SwiGLU/GELU, embedding splice, CLIP embedding assembly,
+// log-prob finalisation, the fused DPO loss (+grad +stats), grad-norm and AdamW over the flat LoRA bucket,
+// decode-time attention and the greedy sampler. All are single-pass, 16-byte vectorised, fp32 math on bf16 storage.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace opadpo {
+
+using bf16 = __nv_bfloat16;
+
+// Row mapping used by the norm kernels so the final norm runs only on the R response-predicting rows of each
+// sequence (rl_models.py:120-121 slices logits[:, -R-1:-1]): compact row r <-> full row (r / rows_per_seq) *
+// seq_stride + seq_off + (r % rows_per_seq). rows_per_seq == 0 means identity.
+struct RowMap {
+  int rows_per_seq = 0;
+  int seq_stride = 0;
+  int seq_off = 0;
+};
+
+// y = w * bf16(x * rsqrt(mean(x^2) + eps))   [UPSTREAM HF LlamaRMSNorm]. x rows are taken through `map`, y is compact.
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, RowMap map, cudaStream_t s);
+// dx[map(r)] = (dres ? dres[map(r)] : 0) + rstd*(w*dy[r]) - x*rstd^3*mean(w*dy*x)   (norm weight is frozen: no dw).
+// rstd is recomputed from x. dx may alias dres.
+int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
+                RowMap map, cudaStream_t s);
+// y = (x - mean) * rsqrt(var + eps) * w + b   [UPSTREAM CLIP LayerNorm]
+int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s);
+
+// In-place rotary embedding (rotate_half layout) on `nheads` heads of width hd starting at x (row stride ld).
+// Position of row t is (pos ? pos[t] : (t % S)) + pos_offset. cs: float2 [max_pos, hd/2] (cos, sin). inverse=1 applies the
+// transpose rotation (backward).
+int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, int nheads, int hd,
+                 const float2* cs, int inverse, cudaStream_t s);
+int rope_table(float2* cs, int max_pos, int hd, float theta, cudaStream_t s);
+
+// act = silu(gu[:, :F]) * gu[:, F:]  ;  backward: dgu from dact and gu
+int swiglu_fwd(const bf16* gu, bf16* act, int64_t T, int F, cudaStream_t s);
+int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t T, int F, cudaStream_t s);
+// exact (erf) GELU, forward and backward (projector, llava_modifications.patch:15354-15367)
+int gelu_fwd(const bf16* x, bf16* y, int64_t n, cudaStream_t s);
+int gelu_bwd(const bf16* dy, const bf16* x, bf16* dx, int64_t n, cudaStream_t s);
+
+// ids [N, L] (int32; one IMAGE_TOKEN_INDEX=-200 per row) -> embeds [N, S=L-1+P, d]; image rows come from
+// feats [n_img, P, d] with image index img_of_row[n]. Also expands the token mask to [N, S] (image rows take
+// img_mask [n_img, P] if given, else 1) and records the image slot start img_pos[n]
+// (llava_modifications.patch:14618-14706).
+int embed_splice(const int32_t* ids, const uint8_t* tok_mask, const uint8_t* img_mask, const int32_t* img_of_row,
+                 const bf16* table, const bf16* feats, bf16* out, uint8_t* out_mask, int32_t* img_pos, int N, int L,
+                 int P, int d, int vocab, cudaStream_t s);
+// dfeats[img, p, :] = sum over rows n with img_of_row[n]==img of dX[n, img_pos[n]+p, :]
+int embed_splice_bwd(const bf16* dX, const int32_t* img_of_row, const int32_t* img_pos, bf16* dfeats, int N, int S,
+                     int n_img, int P, int d, cudaStream_t s);
+// out[r, :] = table[ids[r], :]   (decode-time embedding)
+int embed_rows(const int32_t* ids, const bf16* table, bf16* out, int rows, int d, int vocab, cudaStream_t s);
+
+// CLIP: images [n, 3, R, R] (f32) -> patch matrix [n*P, Kp] bf16 (Kp = padded 3*ps*ps), then token assembly.
+int clip_im2col(const float* images, bf16* patches, int n, int R, int ps, int Kp, cudaStream_t s);
+int clip_assemble(const bf16* patch_emb, const bf16* cls, const bf16* pos, bf16* out, int n, int P, int d, cudaStream_t s);
+// drop CLS: out[n, p, :] = x[n, 1+p, :]
+int clip_drop_cls(const bf16* x, bf16* out, int n, int P, int d, cudaStream_t s);
+
+// Combine lm_head LSE partials (base-2 domain, see gemm.cu EPI_LSE): logprob = (label_logit - lse) * (label>=0),
+// entropy = (lse - E[z]) * (label>=0), lse saved for backward (all nullable except logprob).
+int logprob_finalize(const float4* partials, int ntiles, const float* label_logit, const int32_t* labels, float* logprob,
+                     float* entropy, float* lse, int64_t M, cudaStream_t s);
+
+// One DPO pair (dpo_trainer.py:429-473 + anchor :702-712): per-token loss, gradient and reductions in one pass.
+struct DpoPairArgs {
+  const float *pi_c, *pi_r, *ref_c, *ref_r;  // [n]
+  const float *s_c, *s_r;                    // nullable scores
+  float *d_c, *d_r;                          // nullable; accumulated (+=): dL/dpi_c, dL/dpi_r
+  float* out;  // [8]: mean loss, mean anchor, masked-mean cr, masked-mean rr, sum mask_c, sum mask_r, -, -
+  int64_t n;
+  float beta, label_smoothing;
+  int reference_free;
+  int divergence;  // 0 reverse-KL, 1 JS, 2 alpha
+  float alpha_div;
+  float loss_coef;    // weight of mean(loss) in the total (gradient uses loss_coef / n)
+  int anchor_mode;    // 0 none, 1 mDPO -logsigmoid(sign*(cr - a)), 2 (cr - a)^2
+  float anchor_sign, anchor_value, anchor_coef;
+  float grad_scale;   // extra factor on every gradient (1/grad_accumulation)
+};
+int dpo_pair_loss(const DpoPairArgs& a, cudaStream_t s);
+
+// out[0] += sum(g^2)
+int sumsq_accum(const float* g, int64_t n, float* out, cudaStream_t s);
+// AdamW (utils/trainer_utils.py:9-38; beta (0.9,0.999), eps 1e-8) on fp32 masters; writes the bf16 shadow the GEMMs read.
+// grad is scaled by gscale * min(1, max_norm / (sqrt(*sumsq)*gscale + 1e-6)) when sumsq != null and max_norm > 0.
+int adamw_step(float* master, const float* grad, float* m, float* v, bf16* shadow, int64_t n, float lr, float b1, float b2,
+               float eps, float wd, int step, float gscale, const float* sumsq, float max_norm, cudaStream_t s);
+// *out = sqrt(*sumsq) * gscale
+int norm_from_sumsq(const float* sumsq, float gscale, float* out, cudaStream_t s);
+// out[i] = i % mod
+int fill_mod(int32_t* out, int n, int mod, cudaStream_t s);
+// rollout prologue: int64 queries -> int32 ids + mask copy, and out[n, :Q] = queries[n]
+int queries_to_i32(const int64_t* queries, const uint8_t* qmask, int32_t* ids, uint8_t* mask, int64_t* out, int64_t out_ld,
+                   int N, int Q, cudaStream_t s);
+int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
+int bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s);
+
+// Stack K (query | response_k) rows (rl_models.py:95-112): ids/mask [K*b, Q+R] and, per response position,
+// labels [K*b, R] (= response id, or -1 at pad).
+int stack_inputs(const int64_t* queries, const uint8_t* qmask, const int64_t* const* responses, int K, int b, int Q, int R,
+                 int pad_id, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s);
+
+// ---- decode (rollout) -------------------------------------------------------------------------------------
+// Copy the prefill keys/values of one layer from the packed qkv activation [N*S, 3d] into the static cache
+// kc/vc [N, S_max, d].
+int kv_store_prefill(const bf16* qkv, bf16* kc, bf16* vc, int N, int S, int S_max, int d, cudaStream_t s);
+// One new token per sequence: qkv [N, 3d] (already rotated); appends k,v at position len and attends over
+// keys 0..len with validity mask kmask [N, S_max] (u8). o [N, d].
+int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len,
+                     int S_max, float scale, cudaStream_t s);
+// logits f32 [N, V] -> argmax id (lowest index on ties, as torch.argmax); suppress id < 0 = none. Finished rows
+// (done[n] != 0) emit pad_id. Updates done when eos is produced, writes ids [N] (int32) and out[n*out_ld + step].
+int greedy_pick(const float* logits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
+                int64_t out_ld, int step, cudaStream_t s);
+
+}  // namespace opadpo

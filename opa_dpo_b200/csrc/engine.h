@@ -1,0 +1,143 @@
+// The OPA-DPO engine: owns base weights, two LoRA adapter sets, the trainable adapter's flat fp32 bucket
+// (masters | gradients | Adam moments) and all activations; runs the LLaVA-1.5 forward / LoRA backward / rollout
+// entirely through the kernels in gemm.cu, attention.cu and elementwise.cu. Host logic only — no device code here.
+//
+// Reference being replaced (behaviour, not structure): AutoregressivePolicy.forward
+// (opadpo/dpo_models/rl_models.py:75-144) down through LlavaLlamaForCausalLM.forward
+// (llava_setup/llava_modifications.patch:12127-12202, 15022-15055) and the [UPSTREAM] HF LLaMA / CLIP / PEFT LoRA
+// arithmetic; autograd backward of rl_trainer.py:162; optimiser of utils/trainer_utils.py:9-38.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/opadpo_b200.h"
+#include "elementwise.h"
+
+namespace opadpo {
+
+struct LinearW {
+  int in = 0, out = 0, groups = 1;
+  bf16* W = nullptr;     // [out, in] (groups stacked along out)
+  bf16* bias = nullptr;  // [out] or null
+  int slot = -1;         // LoRA slot index, -1 = not a LoRA target
+};
+
+struct LoraSlot {
+  int64_t offA = 0, offB = 0;  // element offsets into the adapter's flat buffer: A [groups*r, in], B [out, r]
+  int in = 0, out = 0, groups = 1;
+};
+
+struct Adapter {
+  bf16* shadow = nullptr;  // [n_total] bf16 values the GEMMs read
+  float *master = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;  // trainable adapter only, [n_total]
+  bool trainable = false;
+  int step = 0;
+};
+
+struct LlamaLayer {
+  LinearW qkv, o, gu, down;
+  bf16 *ln1 = nullptr, *ln2 = nullptr;
+};
+struct ClipLayer {
+  LinearW qkv, out, fc1, fc2;
+  bf16 *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+};
+
+struct LayerActs {
+  bf16 *x = nullptr, *qkv = nullptr, *o = nullptr, *x1 = nullptr, *gu = nullptr;
+  bf16 *tqkv = nullptr, *to = nullptr, *tgu = nullptr, *td = nullptr;
+  float* lse = nullptr;
+};
+
+struct SaveCtx {
+  bool valid = false;
+  int adapter = 0, b = 0, K = 0, N = 0, Q = 0, R = 0, S = 0;
+  float inv_temp = 1.f;
+  std::vector<void*> owned;  // freed when the slot is released
+  std::vector<LayerActs> layers;
+  bf16* x_final = nullptr;  // input of the final norm [T, d]
+  bf16* hn = nullptr;       // normed response rows [N*R, d]
+  int32_t* labels = nullptr;
+  float* lse_head = nullptr;
+  uint64_t* kbits = nullptr;
+  int32_t *img_pos = nullptr, *img_of_row = nullptr;
+  bf16 *clip_feats = nullptr, *p_pre = nullptr, *p_act = nullptr, *t_p0 = nullptr, *t_p2 = nullptr;
+};
+
+struct ModuleRef {
+  LinearW* lin = nullptr;
+  int group = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const opadpo_config& c);
+  ~Engine();
+  int init();
+
+  int load_tensor(const char* name, const void* src, int dtype, int64_t rows, int64_t cols, cudaStream_t s);
+  int load_lora(int adapter, const char* module, const void* A, const void* B, int dtype, cudaStream_t s);
+  int export_lora(int adapter, const char* module, float* A_out, float* B_out, cudaStream_t s);
+  int lora_shape(const char* module, int64_t* in_f, int64_t* out_f);
+  int lora_offsets(const char* module, int64_t* offA, int64_t* offB);
+  int set_trainable(int adapter);
+  int buffers(float** master, float** grad, float** m, float** v, int64_t* n_total, int64_t* n_train);
+  int sync_shadow(cudaStream_t s);
+
+  int forward_logprobs(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask,
+                       const uint8_t* img_mask, int Q, int K, const int64_t* const* responses, int R, float temperature,
+                       float* out_lp, float* out_ent, int save_slot, cudaStream_t s);
+  int backward(int save_slot, const float* dlogprobs, cudaStream_t s);
+  int zero_grad(cudaStream_t s);
+  int optimizer_step(float lr, float b1, float b2, float eps, float wd, float max_norm, float gscale, float* norm_out,
+                     cudaStream_t s);
+  int generate(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask, int Q, int max_new,
+               int64_t* out_ids, cudaStream_t s);
+
+ private:
+  opadpo_config cfg;
+  int hd = 0, v_hd = 0, P = 0, Kp = 0, r = 0;
+  float lora_scale = 1.f;
+  // base weights
+  bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+  std::vector<LlamaLayer> layers;
+  LinearW proj0, proj2;
+  bf16 *v_patch_w = nullptr, *v_cls = nullptr, *v_pos = nullptr, *v_pre_w = nullptr, *v_pre_b = nullptr;
+  std::vector<ClipLayer> vlayers;
+  float2* rope_cs = nullptr;
+  // LoRA
+  std::vector<LoraSlot> slots;
+  int64_t n_total = 0, n_train = 0;
+  Adapter adapters[2];
+  int trainable_adapter = -1;
+  float* sumsq = nullptr;
+  SaveCtx ctx[2];
+  std::vector<void*> allocs;  // weight allocations
+
+  // helpers
+  template <typename T>
+  int dalloc(T** p, int64_t count, std::vector<void*>* track);
+  int alloc_linear(LinearW& L, int in, int out, int groups, bool bias, bool lora);
+  bool resolve_module(const char* name, ModuleRef* ref);
+  int copy_in(bf16* dst, const void* src, int dtype, int64_t n, cudaStream_t s);
+  void release_slot(int slot, cudaStream_t s);
+
+  const bf16* loraA(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offA; }
+  const bf16* loraB(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offB; }
+
+  int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy, int act,
+                 const bf16* residual, int64_t ldr, cudaStream_t s);
+  int linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
+                 int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s);
+  int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
+  int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
+                        bf16* feats, cudaStream_t s);
+  int llama_layer_fwd(int l, int adapter, int64_t T, int N, int S, const uint64_t* kbits, const LayerActs& a, bf16* x_out,
+                      bf16* h, bf16* act, cudaStream_t s);
+};
+
+}  // namespace opadpo

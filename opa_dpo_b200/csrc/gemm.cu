@@ -8,6 +8,7 @@
 
 #include <cstdio>
 
+#include "common.h"
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       } else if constexpr (EPI == EPI_CEGRAD) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
         const int label = row_ok ? p.labels[row] : -1;
-        const float g = row_ok ? p.dlp[row] * p.alpha : 0.f;
+        // ignore_index rows carry no gradient (compute_logprobs, utils/common_utils.py:112-118)
+        const float g = (row_ok && label >= 0) ? p.dlp[row] * p.alpha : 0.f;
         const float lse2 = row_ok ? p.lse[row] * LOG2E : 0.f;
         const float a2 = p.alpha * LOG2E;
 #pragma unroll 1
@@ -412,6 +414,7 @@ int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream
     attr_set = true;
   }
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "gemm launch: %s", cudaGetErrorString(e));

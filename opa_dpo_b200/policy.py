@@ -1,0 +1,246 @@
+"""Host-side mirror of the reference's policy boundary (opadpo/dpo_models/rl_models.py) on top of the C-ABI engine.
+
+`AutoregressivePolicy` keeps the reference's constructor `(args, base_model, base_tokenizer, adapter_name)` and
+`forward(images, queries, queries_attn_masks, temperature=None, **kwargs)` contract (rl_models.py:75-144): response
+kwargs are discovered by name, K responses are stacked behind the shared query, and the result is
+`{"<name>_logprobs", "<name>_entropies"}` of shape [b, response_len]. `B200LlavaModel` stands where the reference has
+the PEFT-wrapped LlavaLlamaForCausalLM (`base_model`): `set_adapter`, `config.use_cache`, `generate(...)`,
+`peft_config`, adapter save/load in PEFT layout. All arithmetic happens in libopadpo_b200.so.
+"""
+from __future__ import annotations
+
+import json
+import os
+from types import SimpleNamespace
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .engine import BASE, POLICY, REF, Engine, EngineConfig, linear_modules
+from ._lib import OpadpoError
+
+ADAPTER_IDS = {"lora_policy": POLICY, "lora_ref_policy": REF, "lora_default": POLICY, None: BASE}
+
+
+class _PolicyForward(torch.autograd.Function):
+    """Autograd edge across the C ABI: forward keeps activations in an engine slot, backward feeds d(logprobs) to
+    opadpo_backward, which accumulates LoRA gradients straight into the engine's flat bucket (exposed as
+    `flat_param.grad`)."""
+
+    @staticmethod
+    def forward(ctx, anchor: Tensor, model: "B200LlavaModel", adapter: int, images, queries, qmask, img_mask, temperature,
+                slot: int, *responses):
+        lp, ent = model.engine.forward_logprobs(adapter, images, queries, qmask, list(responses), temperature,
+                                                img_mask=img_mask, save_slot=slot, want_entropy=True)
+        ctx.model, ctx.slot, ctx.n_in = model, slot, 9 + len(responses)
+        ctx.mark_non_differentiable(ent)
+        return lp, ent
+
+    @staticmethod
+    def backward(ctx, dlp, _dent):
+        ctx.model.engine.backward(ctx.slot, dlp)
+        ctx.model._slot_busy[ctx.slot] = False
+        return (None,) * ctx.n_in
+
+
+class B200LlavaModel(nn.Module):
+    """Stand-in for the reference's `base_model` (PeftModelForCausalLM over LlavaLlamaForCausalLM, built by
+    qlora_model.get_accelerate_model :44-294): one shared base + adapters 'lora_policy' (trainable) and
+    'lora_ref_policy' (frozen)."""
+
+    def __init__(self, cfg: EngineConfig, device=None, base_model_name_or_path: str = ""):
+        super().__init__()
+        self.engine = Engine(cfg, device)
+        self.cfg = cfg
+        self.config = SimpleNamespace(use_cache=False, cache_shape=None, vocab_size=cfg.vocab, hidden_size=cfg.d_model)
+        self.active_adapter: Optional[str] = "lora_policy"
+        self.peft_config: Dict[str, dict] = {}
+        self.base_model_name_or_path = base_model_name_or_path
+        self.flat_param: Optional[nn.Parameter] = None
+        self._slot_busy = [False, False]
+        self._passthrough: Dict[str, Dict[str, Tensor]] = {}   # adapter tensors the engine does not execute (CLIP layer 24)
+
+    # ---- adapters
+    def set_adapter(self, name: Optional[str]):
+        if name not in ADAPTER_IDS:
+            raise ValueError(f"unknown adapter {name!r}")
+        self.active_adapter = name
+
+    def get_vision_tower(self):
+        return SimpleNamespace(num_patches=self.cfg.n_patches)
+
+    def make_trainable(self, name: str = "lora_policy"):
+        """Allocates fp32 masters / grad bucket / Adam moments and exposes them as ONE flat nn.Parameter whose .grad
+        is a view of the engine's gradient bucket (what optimizer, grad-norm and all-reduce operate on)."""
+        self.engine.set_trainable(ADAPTER_IDS[name])
+        v = self.engine.buffers()
+        self.flat_param = nn.Parameter(v["master"][: v["n_train"]], requires_grad=True)
+        self.flat_param.grad = v["grad"]
+        return self.flat_param
+
+    def default_peft_config(self) -> dict:
+        mods = sorted({m.split(".")[-1] for m in linear_modules(self.cfg)})
+        return dict(peft_type="LORA", task_type="CAUSAL_LM", r=self.cfg.lora_r, lora_alpha=self.cfg.lora_alpha,
+                    lora_dropout=0.0, bias="none", target_modules=mods, inference_mode=False, fan_in_fan_out=False,
+                    base_model_name_or_path=self.base_model_name_or_path, modules_to_save=None, init_lora_weights=True)
+
+    def load_adapter_state(self, name: str, state: Dict[str, Tensor]):
+        """`state` uses PEFT-0.5.0 saved key names: base_model.model.<module>.lora_A.weight / lora_B.weight
+        (get_peft_model_state_dict strips the adapter name; dpo_trainer.py:1070-1095)."""
+        aid = ADAPTER_IDS[name]
+        pairs: Dict[str, Dict[str, Tensor]] = {}
+        for k, t in state.items():
+            k2 = k.replace(f".{name}.", ".")
+            if ".lora_A" in k2:
+                pairs.setdefault(k2.split(".lora_A")[0], {})["A"] = t
+            elif ".lora_B" in k2:
+                pairs.setdefault(k2.split(".lora_B")[0], {})["B"] = t
+        for mod, ab in pairs.items():
+            short = mod[len("base_model.model."):] if mod.startswith("base_model.model.") else mod
+            try:
+                self.engine.lora_shape(short)
+            except OpadpoError:
+                self._passthrough.setdefault(name, {})[mod + ".lora_A.weight"] = ab["A"].detach().cpu()
+                self._passthrough[name][mod + ".lora_B.weight"] = ab["B"].detach().cpu()
+                continue
+            self.engine.load_lora(aid, short, ab["A"], ab["B"])
+        self.peft_config.setdefault(name, self.default_peft_config())
+
+    def adapter_state_dict(self, name: str) -> Dict[str, Tensor]:
+        aid = ADAPTER_IDS[name]
+        out: Dict[str, Tensor] = {}
+        for mod in linear_modules(self.cfg):
+            A, B = self.engine.export_lora(aid, mod)
+            out[f"base_model.model.{mod}.lora_A.weight"] = A.to(torch.bfloat16).cpu()
+            out[f"base_model.model.{mod}.lora_B.weight"] = B.to(torch.bfloat16).cpu()
+        out.update(self._passthrough.get(name, {}))
+        return out
+
+    def save_adapter(self, save_directory: str, name: str):
+        """PEFT layout written by save_adapters (dpo_trainer.py:1047-1095): <dir>/<name>/{adapter_model.bin,
+        adapter_config.json} ('default' adapter goes to <dir> itself)."""
+        out_dir = os.path.join(save_directory, name) if name != "default" else save_directory
+        os.makedirs(out_dir, exist_ok=True)
+        torch.save(self.adapter_state_dict(name), os.path.join(out_dir, "adapter_model.bin"))
+        cfg = dict(self.peft_config.get(name) or self.default_peft_config())
+        cfg["inference_mode"] = True
+        with open(os.path.join(out_dir, "adapter_config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+
+    def load_adapter(self, model_id: str, adapter_name: str, is_trainable: bool = False):
+        """PeftModel.load_adapter contract used at qlora_model.py:84-88."""
+        with open(os.path.join(model_id, "adapter_config.json")) as f:
+            self.peft_config[adapter_name] = json.load(f)
+        r = self.peft_config[adapter_name].get("r")
+        if r != self.cfg.lora_r:
+            raise OpadpoError(f"adapter rank {r} != engine lora_r {self.cfg.lora_r}")
+        state = torch.load(os.path.join(model_id, "adapter_model.bin"), map_location="cpu")
+        self.load_adapter_state(adapter_name, state)
+        if is_trainable:
+            self.make_trainable(adapter_name)
+
+    # ---- forward used by the policy wrapper
+    def policy_logprobs(self, images, queries, qmask, responses, temperature, img_mask=None) -> Tuple[Tensor, Tensor]:
+        aid = ADAPTER_IDS[self.active_adapter]
+        eng = self.engine
+        dev = eng.device
+        images, queries, qmask = images.to(dev), queries.to(dev), qmask.to(dev)
+        responses = [r.to(dev) for r in responses]
+        if img_mask is not None:
+            img_mask = img_mask.to(dev)
+        if ((queries == self.cfg.image_token).sum(1) != 1).any():
+            raise OpadpoError("every query must hold exactly one image token (-200)")
+        needs_grad = torch.is_grad_enabled() and self.flat_param is not None and aid == eng_trainable(self)
+        if needs_grad:
+            if len(responses) > 16:
+                raise OpadpoError("at most 16 responses per call")
+            slot = 0 if not self._slot_busy[0] else 1
+            self._slot_busy[slot] = True
+            return _PolicyForward.apply(self.flat_param, self, aid, images, queries, qmask, img_mask, float(temperature), slot,
+                                        *responses)
+        with torch.no_grad():
+            return eng.forward_logprobs(aid, images, queries, qmask, responses, temperature, img_mask=img_mask)
+
+    # ---- rollout
+    @torch.no_grad()
+    def generate(self, inputs: Tensor, images: Tensor, attention_mask: Tensor, do_sample: bool = False,
+                 max_new_tokens: int = 896, pad_token_id: Optional[int] = None, suppress_tokens=None, top_p: float = 1.0,
+                 top_k: int = 0, temperature: float = 1.0, num_return_sequences: int = 1, synced_gpus: bool = False,
+                 **_unused) -> Tensor:
+        """model.generate surface used by online_generator.py:292-310 and rl_models.py:166-188 -> LongTensor
+        [b, Q + max_new_tokens] (finished rows padded). `synced_gpus` is ignored: ranks decode independently."""
+        if do_sample:
+            raise NotImplementedError("sampling rollout (top-k/top-p) is a later row of the scope table; greedy only")
+        if suppress_tokens:
+            raise NotImplementedError("suppress_tokens is not supported by the greedy rollout kernel")
+        if num_return_sequences != 1:
+            raise NotImplementedError("num_return_sequences > 1")
+        aid = ADAPTER_IDS[self.active_adapter]
+        return self.engine.generate(aid, images, inputs, attention_mask, max_new_tokens)
+
+
+def eng_trainable(model: B200LlavaModel) -> int:
+    return POLICY if model.flat_param is not None else -2
+
+
+class Policy(nn.Module):
+    """rl_models.py:15-71."""
+
+    def __init__(self, args, base_model: B200LlavaModel, base_tokenizer, adapter_name: Optional[str] = None):
+        super().__init__()
+        self.args = args
+        self.base_model = base_model
+        self.base_tokenizer = base_tokenizer
+        self.adapter_name = adapter_name
+
+    def respond(self, queries, query_attn_masks, images=None, temperature=None, num_return_sequences=1):
+        assert not self.training, "Policy must be in eval model for generation."
+        return self._post_respond(self._respond(queries, query_attn_masks, images, temperature, num_return_sequences))
+
+    def _post_respond(self, respond_outputs):
+        return respond_outputs
+
+
+class AutoregressivePolicy(Policy):
+    def forward(self, images: Tensor, queries: Tensor, queries_attn_masks: Tensor, temperature: Optional[float] = None,
+                **kwargs) -> Dict[str, Tensor]:
+        """rl_models.py:75-144."""
+        if self.adapter_name is not None:
+            self.base_model.set_adapter(self.adapter_name)
+        self.base_model.config.use_cache = False
+        if temperature is None:
+            temperature = self.args.temperature
+        keys = [k for k in kwargs if "response" in k and "_mask" not in k and "scores" not in k and "image_relations" not in k]
+        if not keys:
+            raise ValueError("no response tensors passed")
+        R = kwargs[keys[0]].size(1)
+        if R != self.args.response_len:
+            raise ValueError(f"responses must be padded to args.response_len={self.args.response_len}, got {R}")
+        Q = queries.size(1)
+        img_mask = None
+        qmask = queries_attn_masks
+        if queries_attn_masks.size(1) != Q:   # CoPO 'attention': image-token mask prepended (rl_models.py:103-105)
+            P = queries_attn_masks.size(1) - Q
+            img_mask, qmask = queries_attn_masks[:, :P], queries_attn_masks[:, P:]
+        lp, ent = self.base_model.policy_logprobs(images, queries, qmask, [kwargs[k] for k in keys], temperature, img_mask)
+        out = {}
+        for i, k in enumerate(keys):
+            out[k + "_logprobs"] = lp[i]
+            out[k + "_entropies"] = ent[i]
+        return out
+
+    def _respond(self, queries, query_attn_masks, images=None, temperature=None, num_return_sequences=1):
+        """rl_models.py:146-191 — greedy here (the reference samples with top_k=0/top_p=1; see generate())."""
+        if self.adapter_name is not None:
+            self.base_model.set_adapter(self.adapter_name)
+        self.base_model.config.use_cache = True
+        seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=False,
+                                       max_new_tokens=self.args.response_len,
+                                       pad_token_id=self.base_tokenizer.pad_token_id)
+        return dict(responses=seq[:, queries.size(1):])
+
+
+def make_policy_with_base_model(args, base_model, base_tokenizer, adapter_name: Optional[str] = "default"):
+    """rl_models.py:193-204."""
+    return AutoregressivePolicy(args, base_model, base_tokenizer, adapter_name=adapter_name)

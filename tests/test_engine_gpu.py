@@ -1,0 +1,265 @@
+"""Engine parity on the GPU: the CUDA hot path (through the C ABI) vs the CPU fp32 oracle on identical seeded
+bf16-representable weights and synthetic image/text batches, at dimensions the oracle finishes in seconds.
+
+Tolerances (bf16 storage, fp32 accumulate): per-token log-prob |err| <= 0.05 absolute with mean |err| <= 0.01; DPO loss
+within 1e-3 relative (the north-star bar); LoRA gradients cosine >= 0.99 and relative L2 <= 0.08 per module group;
+greedy rollout ids exact (on a peaked lm_head so the top-1 margin exceeds bf16 noise, margin asserted)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NAMES2 = ["chosen_response", "rejected_response"]
+NAMES3 = ["standard_response", "original_generate_response", "AI_pseudo_response"]
+
+
+def _cfgs(n_layers=2, v_layers=2, **kw):
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import EngineConfig
+    oc = O.OracleConfig(n_layers=n_layers, v_layers=v_layers, **kw)
+    ec = EngineConfig(**{k: v for k, v in oc.to_dict().items()})
+    return oc, ec
+
+
+def _build(oc, ec, peaked=1.0, trainable=True):
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import Engine, POLICY, REF
+    w = O.init_weights(oc, peaked=peaked)
+    lp, lr = O.init_lora(oc, 11), O.init_lora(oc, 12)
+    eng = Engine(ec)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    eng.load_state_dict(sd)
+    eng.load_adapter(POLICY, lp)
+    eng.load_adapter(REF, lr)
+    if trainable:
+        eng.set_trainable(POLICY)
+    return eng, w, lp, lr
+
+
+def _cmp_lp(got, ref, what, atol=0.05, mean_tol=0.01):
+    err = (got.cpu() - ref).abs()
+    assert torch.isfinite(got).all(), f"{what}: non-finite"
+    assert err.max().item() <= atol and err.mean().item() <= mean_tol, \
+        f"{what}: max |err| {err.max().item():.4g} mean {err.mean().item():.4g} (ref mean |x| {ref.abs().mean().item():.3g})"
+
+
+@pytest.mark.parametrize("n_layers,v_layers", [(0, 0), (0, 2), (1, 0), (2, 2)])
+def test_forward_logprobs_vs_oracle(n_layers, v_layers):
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, REF, BASE
+    oc, ec = _cfgs(n_layers, v_layers)
+    eng, w, lp, lr = _build(oc, ec, trainable=False)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    for adapter, lora in ((POLICY, lp), (REF, lr), (BASE, None)):
+        ref = O.policy_forward(oc, w, lora, images, q, qm, resp)
+        got_lp, got_ent = eng.forward_logprobs(adapter, images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2])
+        torch.cuda.synchronize()
+        for i, n in enumerate(NAMES2):
+            _cmp_lp(got_lp[i], ref[n + "_logprobs"], f"L{n_layers}/V{v_layers} adapter {adapter} {n} logprobs")
+            _cmp_lp(got_ent[i], ref[n + "_entropies"], f"L{n_layers}/V{v_layers} adapter {adapter} {n} entropies")
+            pad = resp[n] == oc.pad_id
+            assert (got_lp[i].cpu()[pad] == 0).all() and (got_ent[i].cpu()[pad] == 0).all(), "pads must be exactly 0"
+    eng.close()
+
+
+def test_forward_temperature_and_copo_attention_mask():
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, trainable=False)
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, NAMES2, left_pad=2)
+    dev = eng.device
+    g = torch.Generator().manual_seed(5)
+    img_mask = torch.rand(2, oc.n_patches, generator=g) > 0.3
+    ref = O.policy_forward(oc, w, lp, images, q, torch.cat([img_mask, qm], 1), resp, temperature=0.7)
+    got, _ = eng.forward_logprobs(POLICY, images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2],
+                                  temperature=0.7, img_mask=img_mask.to(dev))
+    for i, n in enumerate(NAMES2):
+        _cmp_lp(got[i], ref[n + "_logprobs"], f"copo-attention {n}")
+    eng.close()
+
+
+def _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, names):
+    from oracle import llava_oracle as O
+    lpg = {m: (A.clone().requires_grad_(True), B.clone().requires_grad_(True)) for m, (A, B) in lp.items()}
+    with torch.no_grad():
+        ref = O.policy_forward(oc, w, lr, images, q, qm, resp)
+    pol = O.policy_forward(oc, w, lpg, images, q, qm, resp)
+    loss, _, _ = O.pair_loss(lc, pol[names[0] + "_logprobs"], pol[names[1] + "_logprobs"], ref[names[0] + "_logprobs"],
+                             ref[names[1] + "_logprobs"])
+    loss.backward()
+    return loss.detach(), lpg, ref, pol
+
+
+def test_dpo_step_loss_and_lora_grads_vs_oracle():
+    """Four-forward DPO step (policy & frozen reference x chosen & rejected): loss within 1e-3 relative, LoRA grads."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, REF
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    lc = O.LossConfig(beta=0.1)
+    loss_ref, lpg, ref_o, pol_o = _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, NAMES2)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    ref_lp, _ = eng.forward_logprobs(REF, *args)
+    pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+    fused = FusedDPO(DPOArgs(beta=0.1))
+    pl = pol_lp.clone().requires_grad_(True)
+    total, out = fused.pair(pl[0], pl[1], ref_lp[0], ref_lp[1])
+    total.backward()
+    rel = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
+    assert rel <= 1e-3, f"DPO loss {total.item():.6f} vs oracle {loss_ref.item():.6f} (rel {rel:.3g})"
+    eng.zero_grad()
+    eng.backward(0, pl.grad)
+    torch.cuda.synchronize()
+    views = eng.buffers()
+    grad = views["grad"]
+    assert torch.isfinite(grad).all()
+    bad = []
+    for m, (A, B) in lpg.items():
+        if "vision_model" in m:
+            assert A.grad is None or A.grad.abs().max() == 0  # tower runs under no_grad
+            continue
+        oa, ob = eng.lora_offsets(m)
+        for nm, t, off in (("A", A, oa), ("B", B, ob)):
+            gg = grad[off:off + t.numel()].view_as(t).cpu()
+            gr = t.grad
+            cos = torch.nn.functional.cosine_similarity(gg.flatten(), gr.flatten(), dim=0).item()
+            rl2 = ((gg - gr).norm() / (gr.norm() + 1e-30)).item()
+            if not (cos >= 0.99 and rl2 <= 0.08):
+                bad.append((m, nm, round(cos, 4), round(rl2, 4), float(gr.norm())))
+    assert not bad, f"LoRA grad mismatches (module, which, cos, rel_l2, ref_norm): {bad[:12]} ... {len(bad)} total"
+
+    # optimiser: clip + AdamW first step on the same gradients (fp32 masters)
+    n_train = views["n_train"]
+    master0 = views["master"][:n_train].clone()
+    g0 = grad.clone()
+    norm = eng.optimizer_step(lr=1e-3, max_grad_norm=1.0)
+    torch.cuda.synchronize()
+    (p1,), nref = O.adamw_reference([master0.cpu()], [g0.cpu()], lr=1e-3, max_grad_norm=1.0)
+    assert abs(norm.item() - nref.item()) / nref.item() < 1e-4
+    assert (views["master"][:n_train].cpu() - p1).abs().max().item() < 1e-6
+    eng.close()
+
+
+def test_policy_module_compute_policy_loss_repo_defaults():
+    """The reference's own call pattern: AutoregressivePolicy.forward over 3 responses + CoPO (attention) second
+    forward, compute_policy_loss with AncPO (mDPO anchor) and score weights; loss and stats vs the oracle."""
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc)
+    lp, lr = O.init_lora(oc, 11), O.init_lora(oc, 12)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.load_adapter_state("lora_ref_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lr.items() for x, t in zip("AB", ab)})
+    model.make_trainable("lora_policy")
+    R = 24
+    args = DPOArgs(beta=0.1, CoPO=True, CoPO_coef=0.2, AncPO=True, mDPO_anchor=True, detailed_report=True, response_score=True,
+                   response_image_relation=True, response_len=R)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    policy = AutoregressivePolicy(args, model, tok, adapter_name="lora_policy")
+    ref_policy = AutoregressivePolicy(args, model, tok, adapter_name="lora_ref_policy")
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, R, NAMES3, left_pad=2)
+    g = torch.Generator().manual_seed(9)
+    img_mask = torch.rand(2, oc.n_patches, generator=g) > 0.3
+    masked_qm = torch.cat([img_mask, qm], 1)
+    scores = {}
+    for n in ("original_generate_response", "AI_pseudo_response"):
+        s = torch.tensor([1.0, 1.5, 2.0, 2.5])[torch.randint(0, 4, (2, R), generator=g)] * (resp[n] != 0)
+        scores[n + "_scores"] = s
+        scores[n + "_image_relations"] = torch.tensor([1.0, 3.0])[torch.randint(0, 2, (2, R), generator=g)] * (resp[n] != 0)
+    # oracle
+    lc = O.LossConfig(beta=0.1, CoPO=True, CoPO_coef=0.2, AncPO=True, mDPO_anchor=True, detailed_report=True,
+                      response_score=True, response_image_relation=True)
+    mresp = {"mask_standard_response": resp["standard_response"], "mask_AI_pseudo_response": resp["AI_pseudo_response"]}
+    with torch.no_grad():
+        o_ref = {"ref_base_" + k: v for k, v in O.policy_forward(oc, w, lr, images, q, qm, resp).items()}
+        o_refm = O.policy_forward(oc, w, lr, images, q, masked_qm, mresp)
+        o_ref.update({"ref_" + k: v for k, v in o_refm.items()})
+        o_pol = O.policy_forward(oc, w, lp, images, q, qm, resp)
+        o_polm = O.policy_forward(oc, w, lp, images, q, masked_qm, mresp)
+        loss_ref, stats_ref = O.compute_policy_loss(lc, o_pol, o_ref, o_polm, scores)
+    # engine, through the reference-shaped modules
+    dev = model.engine.device
+    with torch.no_grad():
+        rollouts = {"ref_base_" + k: v for k, v in ref_policy(images, q, qm, **resp).items()}
+        rollouts.update({"ref_" + k: v for k, v in ref_policy(images, q, masked_qm, **mresp).items()})
+    rollouts.update(scores)
+    policy.train()
+    out = policy(images, q, qm, temperature=1.0, mode="policy", **resp)
+    out_m = policy(images, q, masked_qm, temperature=1.0, mode="policy", **mresp)
+    loss, stats = FusedDPO(args).compute_policy_loss(out, rollouts, out_m)
+    rel = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    assert rel <= 1e-3, f"compute_policy_loss {loss.item():.6f} vs oracle {loss_ref.item():.6f} (rel {rel:.3g})"
+    for k, v in stats_ref.items():
+        assert abs(stats[k].item() - v.item()) <= 2e-3 + 2e-2 * abs(v.item()), (k, stats[k].item(), v.item())
+    model.engine.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    gnorm = model.flat_param.grad.norm().item()
+    assert math.isfinite(gnorm) and gnorm > 0
+    model.engine.close()
+
+
+def test_greedy_rollout_ids_exact():
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 3, 16, 8, NAMES2, left_pad=3)
+    ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12)
+    got = eng.generate(POLICY, images, q, qm, 12).cpu()
+    assert margin > 0.05, f"oracle top-1 margin {margin} too small for a bf16 comparison"
+    assert torch.equal(got, ids_ref), f"rollout ids differ (margin {margin:.3g}):\n{got[:, 16:]}\n{ids_ref[:, 16:]}"
+    trunc = O.truncate_after_eos_with_padding(got[:, 16:], oc.eos_id, oc.pad_id, [1577, 29973])
+    assert trunc.shape == (3, 12)
+    eng.close()
+
+
+@pytest.mark.parametrize("div,ls,anchor", [("reverse_kl", 0.0, 0), ("reverse_kl", 0.1, 1), ("js_divergence", 0.0, 2),
+                                           ("alpha_divergence", 0.0, 0)])
+def test_dpo_pair_kernel_vs_oracle(div, ls, anchor):
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    g = torch.Generator().manual_seed(3)
+    b, R = 4, 37
+    mk = lambda: -torch.rand(b, R, generator=g) * 6
+    mask_c = torch.rand(b, R, generator=g) > 0.3
+    mask_r = torch.rand(b, R, generator=g) > 0.2
+    pc, rc = mk() * mask_c, mk() * mask_c
+    pr, rr = mk() * mask_r, mk() * mask_r
+    sc = (torch.randint(2, 6, (b, R), generator=g).float() / 2) * mask_c
+    sr = (torch.randint(2, 6, (b, R), generator=g).float() / 2) * mask_r
+    lc = O.LossConfig(beta=0.1, label_smoothing=ls, f_divergence_type=div)
+    pcg, prg = pc.clone().requires_grad_(True), pr.clone().requires_grad_(True)
+    l, cr, rj = O.dpo_loss(lc, pcg, prg, rc, rr, sc, sr)
+    tot = l.mean() * 0.7
+    if anchor == 1:
+        tot = tot + (-torch.nn.functional.logsigmoid(-(cr - 0.05))).mean() * 0.9
+    elif anchor == 2:
+        tot = tot + ((cr - 0.05) ** 2).mean() * 0.9
+    tot.backward()
+    args = DPOArgs(beta=0.1, label_smoothing=ls, f_divergence_type=div, AncPO=anchor > 0, mDPO_anchor=anchor == 1,
+                   Anchor_value=0.05, Anchor_coef=0.9)
+    dev = "cuda"
+    a, bb = pc.to(dev).requires_grad_(True), pr.to(dev).requires_grad_(True)
+    total, out = FusedDPO(args).pair(a, bb, rc.to(dev), rr.to(dev), sc.to(dev), sr.to(dev), loss_coef=0.7,
+                                     anchor_sign=-1.0 if anchor == 1 else (1.0 if anchor == 2 else 0.0))
+    total.backward()
+    assert abs(total.item() - tot.item()) <= 1e-5 * max(1, abs(tot.item())), (total.item(), tot.item())
+    assert (a.grad.cpu() - pcg.grad).abs().max().item() <= 1e-6
+    assert (bb.grad.cpu() - prg.grad).abs().max().item() <= 1e-6
+    assert abs(out[2].item() - O.masked_mean(cr, rc != 0).item()) <= 1e-5
+    assert abs(out[3].item() - O.masked_mean(rj, rr != 0).item()) <= 1e-5
