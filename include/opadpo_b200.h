@@ -183,6 +183,11 @@ int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, 
  * out_ids int64 [b, Q + max_new] = queries | generated (pad after EOS). adapter = -1 runs the bare base model. */
 int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
                     const uint8_t* qmask, int32_t Q, int32_t max_new, int64_t* out_ids, void* stream);
+/* Measurement hooks (bench.py): between begin and end every tcgen05 GEMM launch is bracketed by CUDA events on its own
+ * stream; end synchronises and returns the summed kernel time, the executed FLOPs (2*M*N*K with K padded to the 64-wide
+ * k-block) and the launch count. */
+int opadpo_prof_begin(void);
+int opadpo_prof_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* Number of kernels this library has launched so far in this process. */
 int64_t opadpo_launch_count(void);
 

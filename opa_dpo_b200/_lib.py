@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
-    "opadpo_launch_count",
+    "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
 ]
 
 
@@ -130,6 +130,8 @@ def _declare_engine(lib):
     lib.opadpo_zero_grad.argtypes = [vp, vp]
     lib.opadpo_optimizer_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]
     lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp]
+    lib.opadpo_prof_begin.argtypes = []
+    lib.opadpo_prof_end.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64)]
     lib.opadpo_launch_count.argtypes = []
     lib.opadpo_launch_count.restype = c.c_int64
     for name in EXPORTED_SYMBOLS:

@@ -115,6 +115,15 @@ int opadpo_op_pack_mask(const uint8_t* mask, uint64_t* bits, int32_t N, int32_t 
   return OPADPO_OK;
 }
 
+int opadpo_prof_begin(void) {
+  gemm_prof_begin();
+  return OPADPO_OK;
+}
+int opadpo_prof_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  if (!gemm_ms || !gemm_flops || !gemm_launches) return OPADPO_EINVAL;
+  return gemm_prof_end(gemm_ms, gemm_flops, gemm_launches);
+}
+
 int opadpo_op_dpo_pair(const opadpo_dpo_pair_desc* d, void* stream) {
   g_last_error[0] = 0;
   if (!d || !d->pi_c || !d->pi_r || !d->ref_c || !d->ref_r || !d->out || d->n <= 0) {

@@ -7,6 +7,7 @@
 #include "gemm.h"
 
 #include <cstdio>
+#include <vector>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -401,6 +402,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
 thread_local char g_err[512] = {0};
 
+// Optional per-launch timing (bench.py's roofline): CUDA events on the launching stream around every GEMM launch.
+struct ProfRec {
+  cudaEvent_t a, b;
+  double flops;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
 template <bool A_MN, bool B_MN, int EPI>
 int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<A_MN, B_MN, EPI>;
@@ -413,7 +422,18 @@ int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream
     }
     attr_set = true;
   }
+  ProfRec rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    rec.flops = 2.0 * kp.M * kp.N * 64.0 * (kp.kb1 + kp.kb2);
+    cudaEventRecord(rec.a, stream);
+  }
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  if (g_prof_on) {
+    cudaEventRecord(rec.b, stream);
+    g_prof.push_back(rec);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -437,6 +457,30 @@ int num_sms() {
 }  // namespace
 
 const char* gemm_last_error() { return g_err; }
+
+void gemm_prof_begin() {
+  g_prof.clear();
+  g_prof_on = true;
+}
+// Sums the event-timed durations (ms) and executed (tile-padded K) FLOPs of every launch since gemm_prof_begin().
+int gemm_prof_end(double* total_ms, double* total_flops, int64_t* launches) {
+  g_prof_on = false;
+  cudaDeviceSynchronize();
+  double ms = 0, fl = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *launches = static_cast<int64_t>(g_prof.size());
+  g_prof.clear();
+  return 0;
+}
 int gemm_num_n_tiles(int N) { return (N + BN - 1) / BN; }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {

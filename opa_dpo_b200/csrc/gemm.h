@@ -59,5 +59,8 @@ struct GemmArgs {
 int gemm_launch(const GemmArgs& args, cudaStream_t stream);
 const char* gemm_last_error();
 int gemm_num_n_tiles(int N);
+// bench instrumentation: time every GEMM launch with CUDA events on its stream
+void gemm_prof_begin();
+int gemm_prof_end(double* total_ms, double* total_flops, int64_t* launches);
 
 }  // namespace opadpo

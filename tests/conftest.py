@@ -8,6 +8,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+try:  # tiny-matrix oracle ops crawl when OpenMP fans out over every core of a big GPU host
+    import torch as _torch
+    _torch.set_num_threads(min(8, os.cpu_count() or 1))
+except Exception:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
