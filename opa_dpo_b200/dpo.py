@@ -16,6 +16,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import DpoPairDesc
+from .dist import allreduce_grad_bucket
 
 _DIV = {"reverse_kl": 0, "js_divergence": 1, "alpha_divergence": 2}
 
@@ -195,10 +196,8 @@ class DPOStepper:
     def optimizer_step(self) -> Tensor:
         a = self.args
         eng = self.model.engine
-        scale = 1.0
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.model.flat_param.grad, group=self.process_group)  # ONE NCCL sum per step
-            scale = 1.0 / self.world_size
+        # ONE NCCL all-reduce(sum) of the flat LoRA-grad bucket per optimizer step; 1/world is applied inside AdamW
+        scale = allreduce_grad_bucket(self.model.flat_param.grad, self.process_group) if self.world_size > 1 else 1.0
         norm = eng.optimizer_step(self.lr, (a.adam_beta1, a.adam_beta2), a.adam_epsilon, a.weight_decay, a.max_grad_norm, scale)
         eng.zero_grad()
         return norm

@@ -1,0 +1,102 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/opadpo_b200.h declares; the product path fails loudly without a GPU (no CPU fallback); host-side mirrors keep
+the reference's calling conventions. No compute calls are made here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from opa_dpo_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_library()
+    return _lib.load()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "opadpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(opadpo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from opa_dpo_b200 import _lib
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(raw, s)]
+    assert not missing, f"declared in include/opadpo_b200.h but not exported: {missing}"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, (set(declared) ^ set(_lib.EXPORTED_SYMBOLS))
+    assert lib.opadpo_abi_version() >= 2
+
+
+def test_struct_layouts_match_header_field_order():
+    """ctypes mirrors must list the same fields in the same order as the C structs."""
+    from opa_dpo_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "opadpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip().replace("*", " "))[0])
+        return names
+
+    for struct, cls in (("opadpo_gemm_desc", _lib.GemmDesc), ("opadpo_attn_desc", _lib.AttnDesc),
+                        ("opadpo_dpo_pair_desc", _lib.DpoPairDesc), ("opadpo_config", _lib.Config)):
+        assert fields(struct) == [f[0] for f in cls._fields_], struct
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu(lib):
+    from opa_dpo_b200 import Engine, EngineConfig, OpadpoError, _lib
+    with pytest.raises(OpadpoError):
+        Engine(EngineConfig())
+    cfg = EngineConfig().to_c()
+    h = ctypes.c_void_p()
+    rc = lib.opadpo_engine_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc < 0 and b"no CUDA device" in lib.opadpo_last_error()
+    assert lib.opadpo_forward_logprobs(None, 0, None, 1, None, None, None, 1, 1, None, 1, 1.0, None, None, -1, None) < 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opa_dpo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f"{f} imports oracle/"
+
+
+def test_policy_mirror_discovers_responses_like_the_reference():
+    """rl_models.py:91-92 key filter, response_len check and the PEFT key naming of saved adapters."""
+    from opa_dpo_b200.engine import EngineConfig, linear_modules
+    keys = ["standard_response", "AI_pseudo_response_scores", "original_generate_response", "x_response_mask",
+            "AI_pseudo_response_image_relations", "mask_AI_pseudo_response", "mode"]
+    got = [k for k in keys if "response" in k and "_mask" not in k and "scores" not in k and "image_relations" not in k]
+    assert got == ["standard_response", "original_generate_response", "mask_AI_pseudo_response"]
+    mods = linear_modules(EngineConfig())
+    assert len(mods) == 32 * 7 + 2 + 23 * 6
+    assert "model.layers.31.mlp.down_proj" in mods and mods["model.layers.0.mlp.gate_proj"] == (11008, 4096)
+    assert not any("lm_head" in m for m in mods)
+    n_llm = sum(256 * (o + i) for m, (o, i) in mods.items() if "vision_model" not in m)
+    assert n_llm == 643_039_232   # 639.6 M (LLM) + 3.4 M (projector): SURVEY.md §8e
+
+
+def test_flop_model_matches_baseline_table():
+    from opa_dpo_b200.engine import EngineConfig
+    from opa_dpo_b200.flops import flops_per_pair
+    assert abs(flops_per_pair(EngineConfig(), 128, 512)["per_pair"] / 1e12 - 113.3) < 0.1
+    assert abs(flops_per_pair(EngineConfig(), 128, 128)["per_pair"] / 1e12 - 77.1) < 0.1
+    assert abs(flops_per_pair(EngineConfig.llava_13b(), 128, 1024)["per_pair"] / 1e12 - 305.9) < 0.1

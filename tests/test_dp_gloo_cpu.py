@@ -1,0 +1,70 @@
+"""world_size-2 gloo test of the data-parallel semantics (host logic in opa_dpo_b200/dist.py): per-rank LoRA gradients of
+the local-mean loss, all-reduced (sum) and scaled by 1/world, equal the single-process gradient on the concatenated
+batch. The per-rank compute stand-in is the CPU oracle (tests may use it); the product's GPU path is covered by -m gpu."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = ["chosen_response", "rejected_response"]
+
+
+def _flat_grads(cfg, w, lp, lr, images, q, qm, resp):
+    from oracle import llava_oracle as O
+    mods = [m for m in O.lora_target_modules(cfg) if "vision_model" not in m]
+    lpg = {m: (A.clone().requires_grad_(m in mods), B.clone().requires_grad_(m in mods)) for m, (A, B) in lp.items()}
+    with torch.no_grad():
+        ref = O.policy_forward(cfg, w, lr, images, q, qm, resp)
+    pol = O.policy_forward(cfg, w, lpg, images, q, qm, resp)
+    loss, _, _ = O.pair_loss(O.LossConfig(beta=0.1), pol[NAMES[0] + "_logprobs"], pol[NAMES[1] + "_logprobs"],
+                             ref[NAMES[0] + "_logprobs"], ref[NAMES[1] + "_logprobs"])
+    loss.backward()
+    return torch.cat([t.grad.flatten() for m in mods for t in lpg[m]]), loss.detach()
+
+
+def _worker(rank, world, port, q_out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.dist import allreduce_grad_bucket, shard_range
+    cfg = O.OracleConfig(n_layers=1, v_layers=1)
+    w = O.init_weights(cfg)
+    lp, lr = O.init_lora(cfg, 11), O.init_lora(cfg, 12)
+    images, q, qm, resp = O.synthetic_batch(cfg, 4, 16, 16, NAMES, left_pad=2)
+    lo, hi = shard_range(4, rank, world)
+    g, loss = _flat_grads(cfg, w, lp, lr, images[lo:hi], q[lo:hi], qm[lo:hi], {k: v[lo:hi] for k, v in resp.items()})
+    scale = allreduce_grad_bucket(g)
+    g = g * scale
+    if rank == 0:
+        g_full, loss_full = _flat_grads(cfg, w, lp, lr, images, q, qm, resp)
+        q_out.put((float((g - g_full).norm() / g_full.norm()), scale))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_equals_concatenated_batch():
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rel, scale = q_out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert scale == 0.5
+    assert rel < 1e-4, f"DP gradient differs from the concatenated-batch gradient (rel {rel})"
+
+
+def test_shard_range():
+    from opa_dpo_b200.dist import shard_range
+    assert [shard_range(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
+    with pytest.raises(ValueError):
+        shard_range(10, 0, 4)
