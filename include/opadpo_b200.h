@@ -84,6 +84,9 @@ typedef struct opadpo_attn_desc {
   const void* dO; int64_t ld_do;   /* backward only from here */
   float* delta;
   void *dq, *dk, *dv; int64_t ld_dqkv;
+  /* shared-prefix packing (causal): rows are [prefix | resp_0 | resp_1 ...] with segments of segment_len tokens after
+   * prefix_len positions; a response query sees the prefix and its own segment only. segment_len = 0: off. */
+  int32_t prefix_len, segment_len;
 } opadpo_attn_desc;
 
 int opadpo_op_attn_fwd(const opadpo_attn_desc* d, void* stream);
@@ -159,6 +162,9 @@ int opadpo_engine_buffers(opadpo_engine* e, float** master, float** grad, float*
                           int64_t* n_total, int64_t* n_train);
 /* Where module's A [groups*r... see DESIGN.md] and B live inside the flat bucket (element offsets). */
 int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* offA, int64_t* offB);
+/* Engine options. "share_prefix" (default 1): compute the image+query prefix once per sample and let its K responses
+ * attend to it through the segment mask (identical results to the reference's K stacked rows, fewer FLOPs). */
+int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 /* After the caller modified the fp32 masters directly (e.g. optimizer state restore): refresh the bf16 shadows. */
 int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream);
 

@@ -65,6 +65,7 @@ class AttnDesc(ctypes.Structure):
         ("dO", ctypes.c_void_p), ("ld_do", ctypes.c_int64),
         ("delta", ctypes.c_void_p),
         ("dq", ctypes.c_void_p), ("dk", ctypes.c_void_p), ("dv", ctypes.c_void_p), ("ld_dqkv", ctypes.c_int64),
+        ("prefix_len", ctypes.c_int32), ("segment_len", ctypes.c_int32),
     ]
 
 
@@ -104,6 +105,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_op_attn_bwd", "opadpo_op_pack_mask", "opadpo_op_dpo_pair", "opadpo_engine_create", "opadpo_engine_destroy",
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
+    "opadpo_engine_set_option",
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
 ]
@@ -124,6 +126,7 @@ def _declare_engine(lib):
                                           c.POINTER(i64), c.POINTER(i64)]
     lib.opadpo_engine_lora_offsets.argtypes = [vp, c.c_char_p, c.POINTER(i64), c.POINTER(i64)]
     lib.opadpo_engine_sync_shadow.argtypes = [vp, vp]
+    lib.opadpo_engine_set_option.argtypes = [vp, c.c_char_p, i64]
     lib.opadpo_forward_logprobs.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, c.POINTER(vp), i32, f32, vp, vp,
                                             i32, vp]
     lib.opadpo_backward.argtypes = [vp, i32, vp, vp]

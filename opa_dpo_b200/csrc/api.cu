@@ -85,6 +85,8 @@ static AttnArgs to_attn(const opadpo_attn_desc* d) {
   a.ld_o = d->ld_o;
   a.lse = d->lse;
   a.kbits = d->kbits;
+  a.prefix_len = d->prefix_len;
+  a.segment_len = d->segment_len;
   a.dO = static_cast<const __nv_bfloat16*>(d->dO);
   a.ld_do = d->ld_do;
   a.delta = d->delta;
@@ -206,6 +208,11 @@ int opadpo_engine_buffers(opadpo_engine* e, float** master, float** grad, float*
 int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* offA, int64_t* offB) {
   ENGINE_GUARD(e);
   return e->impl->lora_offsets(module, offA, offB);
+}
+int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value) {
+  ENGINE_GUARD(e);
+  if (!name) { set_error("opadpo_engine_set_option: null name"); return OPADPO_EINVAL; }
+  return e->impl->set_option(name, value);
 }
 int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream) {
   ENGINE_GUARD(e);

@@ -24,6 +24,7 @@ constexpr int NTHREADS = 192;
 struct AttnParams {
   int N, S, H;
   int nwords;
+  int S0, segR;  // shared-prefix packing: keys [S0, segment start of the query) are invisible (segR == 0: off)
   float scale, scale_log2;
   const uint64_t* kbits;
   __nv_bfloat16* o;
@@ -63,7 +64,23 @@ __device__ __forceinline__ uint64_t key_bits(const AttnParams& p, int n, int j, 
     const int lim = i - j * BKV;  // keys c <= lim visible
     if (lim < 63) bits &= (lim < 0) ? 0ull : ((2ull << lim) - 1ull);
   }
+  if (p.segR > 0 && i >= p.S0) {
+    // packed row = [prefix | resp_0 | resp_1 ...]: a response token sees the prefix and its own segment only
+    const int ex_hi = p.S0 + ((i - p.S0) / p.segR) * p.segR;
+    const int lo = max(p.S0 - j * BKV, 0), hi = min(ex_hi - j * BKV, 64);
+    if (hi > lo) {
+      const uint64_t m = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+      bits &= ~m;
+    }
+  }
   return row_valid ? bits : 0ull;
+}
+
+// True when key tile j is invisible to EVERY row of the query tile starting at q0 (another response's segment).
+__device__ __forceinline__ bool tile_skipped(const AttnParams& p, int q0, int j) {
+  if (p.segR <= 0 || q0 < p.S0) return false;
+  const int seg_start = p.S0 + ((q0 - p.S0) / p.segR) * p.segR;
+  return j * BKV >= p.S0 && (j + 1) * BKV <= seg_start;
 }
 
 // =====================================================================================================
@@ -142,12 +159,15 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(q_full, L::Q_BYTES);
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
+      int it = 0;
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
-        ptx::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        if (tile_skipped(p, q0, j)) continue;
+        const int st = it & 1;
+        ptx::mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
         load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
         load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        ++it;
       }
     }
   } else if (warp == 5) {
@@ -157,11 +177,13 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
       const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
       ptx::mbar_wait(q_full, 0);
+      int it = 0;
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
+        if (tile_skipped(p, q0, j)) continue;
+        const int st = it & 1;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
         const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
-        ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        ptx::mbar_wait(&kv_full[st], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
@@ -170,15 +192,16 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                            ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_qk, kk > 0);
         }
         ptx::mma_commit(s_full);
-        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(p_full, it & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           ptx::mma_bf16_ss(t_o, ptx::make_smem_desc(aP + kk * 32, 16, 1024),
-                           ptx::make_smem_desc(aV + kk * 2048, BKV * 128, 1024), idesc_pv, (j > 0 || kk > 0));
+                           ptx::make_smem_desc(aV + kk * 2048, BKV * 128, 1024), idesc_pv, (it > 0 || kk > 0));
         }
         ptx::mma_commit(&kv_empty[st]);
-        if (j == num_kv - 1) ptx::mma_commit(o_full);
+        if (j == num_kv - 1) ptx::mma_commit(o_full);  // the diagonal tile is never skipped
+        ++it;
       }
     }
   } else {
@@ -188,8 +211,10 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     const bool row_valid = i < p.S;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
+    int it = 0;
     for (int j = 0; j < num_kv; ++j) {
-      ptx::mbar_wait(s_full, j & 1);
+      if (tile_skipped(p, q0, j)) continue;
+      ptx::mbar_wait(s_full, it & 1);
       ptx::tc_fence_after();
       uint32_t r0[32], r1[32];
       ptx::tmem_ld32(t_s + lane_off, r0);
@@ -213,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         m_ref = cm;
         l *= alpha;
       }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
+      if (it > 0 && __any_sync(0xffffffffu, need)) {
 #pragma unroll 1
         for (int c = 0; c < HD / 32; ++c) {
           uint32_t t[32];
@@ -244,6 +269,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
+      ++it;
     }
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
@@ -365,12 +391,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ptx::mbar_arrive_expect_tx(q_full, 2 * L::Q_BYTES);
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
       load_tile(smem + L::OFF_DO, &tmdO, q_full, col0, row0, BQ, NB);
+      int it = 0;
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
-        ptx::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        if (tile_skipped(p, q0, j)) continue;
+        const int st = it & 1;
+        ptx::mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
         load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
         load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        ++it;
       }
     }
   } else if (warp == 5) {
@@ -381,11 +410,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO);
       const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
       ptx::mbar_wait(q_full, 0);
+      int it = 0;
       for (int j = 0; j < num_kv; ++j) {
-        const int st = j & 1;
+        if (tile_skipped(p, q0, j)) continue;
+        const int st = it & 1;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
         const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
-        ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        ptx::mbar_wait(&kv_full[st], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
@@ -400,15 +431,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                            ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
         }
         ptx::mma_commit(sdp_full);
-        ptx::mbar_wait(ds_full, j & 1);
+        ptx::mbar_wait(ds_full, it & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           ptx::mma_bf16_ss(t_dq, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
-                           ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024), idesc_dq, (j > 0 || kk > 0));
+                           ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024), idesc_dq, (it > 0 || kk > 0));
         }
         ptx::mma_commit(&kv_empty[st]);
         if (j == num_kv - 1) ptx::mma_commit(dq_done);
+        ++it;
       }
     }
   } else {
@@ -418,8 +450,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
     const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
+    int it = 0;
     for (int j = 0; j < num_kv; ++j) {
-      ptx::mbar_wait(sdp_full, j & 1);
+      if (tile_skipped(p, q0, j)) continue;
+      ptx::mbar_wait(sdp_full, it & 1);
       ptx::tc_fence_after();
       const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
 #pragma unroll 1
@@ -435,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(ds_full);
+      ++it;
     }
     ptx::mbar_wait(dq_done, 0);
     ptx::tc_fence_after();
@@ -509,7 +544,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int col0 = h * HD;
   const int nq = (p.S + BQ - 1) / BQ;
   const int i0 = CAUSAL ? (k0 / BQ) : 0;
-  const int niter = nq - i0;
+  // query tiles of OTHER response segments never see this key tile (shared-prefix packing): skip them
+  int last_qt = nq - 1;
+  while (last_qt > i0 && tile_skipped(p, last_qt * BQ, j)) --last_qt;
 
   if (warp == 4) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -539,13 +576,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ptx::mbar_arrive_expect_tx(kv_full, 2 * L::KV_BYTES);
       load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKV, NB);
       load_tile(smem + L::OFF_V, &tmV, kv_full, col0, n * p.S + k0, BKV, NB);
-      for (int it = 0; it < niter; ++it) {
+      int it = 0;
+      for (int qt = i0; qt <= last_qt; ++qt) {
+        if (tile_skipped(p, qt * BQ, j)) continue;
         const int st = it & 1;
         ptx::mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&qdo_full[st], 2 * L::Q_BYTES);
-        const int r0 = n * p.S + (i0 + it) * BQ;
+        const int r0 = n * p.S + qt * BQ;
         load_tile(smem + L::OFF_Q + st * L::Q_BYTES, &tmQ, &qdo_full[st], col0, r0, BQ, NB);
         load_tile(smem + L::OFF_DO + st * L::Q_BYTES, &tmdO, &qdo_full[st], col0, r0, BQ, NB);
+        ++it;
       }
     }
   } else if (warp == 5) {
@@ -557,7 +597,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
       const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
       ptx::mbar_wait(kv_full, 0);
-      for (int it = 0; it < niter; ++it) {
+      int it = 0;
+      for (int qt = i0; qt <= last_qt; ++qt) {
+        if (tile_skipped(p, qt * BQ, j)) continue;
         const int st = it & 1;
         const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
         const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
@@ -590,14 +632,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                            ptx::make_smem_desc(adS + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
         }
         ptx::mma_commit(&qdo_empty[st]);
-        if (it == niter - 1) ptx::mma_commit(done);
+        if (qt == last_qt) ptx::mma_commit(done);
+        ++it;
       }
     }
   } else {
     const int tid = threadIdx.x;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    for (int it = 0; it < niter; ++it) {
-      const int q0 = (i0 + it) * BQ;
+    int it = 0;
+    for (int qt = i0; qt <= last_qt; ++qt) {
+      if (tile_skipped(p, qt * BQ, j)) continue;
+      const int q0 = qt * BQ;
       const int i = q0 + tid;
       const bool row_valid = i < p.S;
       const int64_t grow = static_cast<int64_t>(n) * p.S + i;
@@ -620,6 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(pds_full);
+      ++it;
     }
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
@@ -700,6 +746,8 @@ AttnParams make_params(const AttnArgs& a) {
   p.S = a.S;
   p.H = a.H;
   p.nwords = (a.S + 63) / 64;
+  p.S0 = a.prefix_len;
+  p.segR = a.segment_len;
   p.scale = a.scale;
   p.scale_log2 = a.scale * LOG2E;
   p.kbits = a.kbits;

@@ -23,6 +23,9 @@ struct AttnArgs {
   int64_t ld_o = 0;
   float* lse = nullptr;           // [T, H] natural-log LSE of scaled scores (forward out, backward in)
   const uint64_t* kbits = nullptr;  // may be null = all keys valid
+  // Shared-prefix packing (causal only): a row is [prefix (prefix_len) | resp_0 | resp_1 | ...] with segments of
+  // segment_len; response queries see the prefix and their own segment. segment_len == 0 disables it.
+  int prefix_len = 0, segment_len = 0;
   // backward only
   const __nv_bfloat16* dO = nullptr;
   int64_t ld_do = 0;

@@ -47,20 +47,18 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__device__ __forceinline__ int64_t map_row(int64_t r, const RowMap& m) {
-  if (m.rows_per_seq == 0) return r;
-  return (r / m.rows_per_seq) * m.seq_stride + m.seq_off + (r % m.rows_per_seq);
-}
+__device__ __forceinline__ int64_t map_row(int64_t r, const int32_t* idx) { return idx ? idx[r] : r; }
 
 constexpr int NORM_THREADS = 256;
 constexpr int NORM_MAXV = 4;  // up to 8192 columns held in registers
 
 // ---------------------------------------------------------------------------------------------- RMSNorm
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                                    bf16* __restrict__ y, int d, float eps, RowMap map) {
+                                                                    bf16* __restrict__ y, int d, float eps,
+                                                                    const int32_t* __restrict__ x_idx) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + map_row(r, map) * d);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + map_row(r, x_idx) * d);
   const int nv = d >> 3;
   uint4 xv[NORM_MAXV];
   float ss = 0.f;
@@ -95,11 +93,13 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* _
 
 __global__ void __launch_bounds__(NORM_THREADS)
     rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
-                       const bf16* dres, bf16* dx, int d, float eps, RowMap map) {
+                       const bf16* dres, bf16* dx, int d, float eps, const int32_t* __restrict__ x_idx,
+                       const int32_t* __restrict__ dx_idx) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
-  const int64_t fr = map_row(r, map);
-  const uint4* xr = reinterpret_cast<const uint4*>(x + fr * d);
+  const int64_t xrw = map_row(r, x_idx);
+  const int64_t fr = map_row(r, dx_idx);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + xrw * d);
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * d);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   const int nv = d >> 3;
@@ -576,6 +576,10 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restri
 }
 
 __global__ void norm_from_sumsq_kernel(const float* sumsq, float gscale, float* out) { *out = sqrtf(*sumsq) * gscale; }
+__global__ void fill_affine_kernel(int32_t* out, int n, int stride, int offset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i * stride + offset;
+}
 __global__ void fill_mod_kernel(int32_t* out, int n, int mod) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = i % mod;
@@ -594,23 +598,76 @@ __global__ void queries_to_i32_kernel(const int64_t* __restrict__ q, const uint8
 struct RespPtrs {
   const int64_t* p[8];
 };
+// Row layouts (N rows of L ids -> S = L-1+P positions after the image splice):
+//   unpacked: N = K*b rows [query | resp_k]          (rl_models.py:95-111 as written)
+//   packed  : N = b rows   [query | resp_0 | resp_1 | ...]: the image+query prefix is computed ONCE per sample and
+//             shared by its K responses through the segment mask of the attention kernels (identical results).
+// labels / outputs are always in the reference's stacked order c = (k*b + i)*R + t.
 __global__ void stack_inputs_kernel(const int64_t* __restrict__ queries, const uint8_t* __restrict__ qmask, RespPtrs resp,
-                                    int K, int b, int Q, int R, int pad_id, int32_t* __restrict__ ids,
+                                    int K, int b, int Q, int R, int pad_id, int packed, int32_t* __restrict__ ids,
                                     uint8_t* __restrict__ mask, int32_t* __restrict__ labels) {
-  const int L = Q + R;
+  const int L = packed ? Q + K * R : Q + R;
+  const int N = packed ? b : K * b;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(K) * b * L) return;
+  if (idx >= static_cast<int64_t>(N) * L) return;
   const int l = static_cast<int>(idx % L);
   const int row = static_cast<int>(idx / L);
-  const int k = row / b, i = row % b;
+  const int i = packed ? row : row % b;
   if (l < Q) {
     ids[idx] = static_cast<int32_t>(queries[static_cast<int64_t>(i) * Q + l]);
     mask[idx] = qmask[static_cast<int64_t>(i) * Q + l];
   } else {
-    const int32_t id = static_cast<int32_t>(resp.p[k][static_cast<int64_t>(i) * R + (l - Q)]);
+    const int k = packed ? (l - Q) / R : row / b;
+    const int t = packed ? (l - Q) % R : l - Q;
+    const int32_t id = static_cast<int32_t>(resp.p[k][static_cast<int64_t>(i) * R + t]);
     ids[idx] = id;
     mask[idx] = id != pad_id;
-    labels[static_cast<int64_t>(row) * R + (l - Q)] = id != pad_id ? id : kIgnore;
+    labels[(static_cast<int64_t>(k) * b + i) * R + t] = id != pad_id ? id : kIgnore;
+  }
+}
+
+// RoPE positions: absolute index in the padded row; response segments of a packed row all start at S0.
+__global__ void build_positions_kernel(int32_t* __restrict__ pos, int N, int S, int S0, int R, int packed) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(N) * S) return;
+  const int s = static_cast<int>(idx % S);
+  pos[idx] = (packed && s >= S0) ? S0 + (s - S0) % R : s;
+}
+
+// Hidden row that predicts response token (k, i, t) (logits[:, -R-1:-1], rl_models.py:120-121) and the row its
+// gradient is written to. Packed rows share the last prefix row for t == 0: k >= 1 writes go to scratch rows
+// [T, T + (K-1)*b) that fold_rows adds back afterwards.
+__global__ void build_row_index_kernel(int32_t* __restrict__ src, int32_t* __restrict__ dst, int K, int b, int R, int S,
+                                       int S0, int packed, int T) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= static_cast<int64_t>(K) * b * R) return;
+  const int t = static_cast<int>(c % R);
+  const int kb = static_cast<int>(c / R);
+  const int k = kb / b, i = kb % b;
+  if (!packed) {
+    const int row = kb * S + (S - R - 1 + t);
+    src[c] = row;
+    dst[c] = row;
+  } else {
+    const int row = i * S + (t == 0 ? S0 - 1 : S0 + k * R + t - 1);
+    src[c] = row;
+    dst[c] = (t == 0 && k >= 1) ? T + (k - 1) * b + i : row;
+  }
+}
+
+__global__ void fold_rows_kernel(bf16* __restrict__ dx, int K, int b, int S, int S0, int d, int T) {
+  const int i = blockIdx.x;
+  uint4* dst = reinterpret_cast<uint4*>(dx + (static_cast<int64_t>(i) * S + S0 - 1) * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
+    float acc[8];
+    unpack8(dst[v], acc);
+    for (int k = 1; k < K; ++k) {
+      float f[8];
+      unpack8(reinterpret_cast<const uint4*>(dx + (static_cast<int64_t>(T) + (k - 1) * b + i) * d)[v], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    dst[v] = pack8(acc);
   }
 }
 
@@ -769,17 +826,17 @@ inline unsigned capped_blocks(int64_t n, int threads, int cap) {
 
 }  // namespace
 
-int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, RowMap map, cudaStream_t s) {
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s) {
   if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
   if (rows == 0) return 0;
-  rmsnorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, y, d, eps, map);
+  rmsnorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, y, d, eps, x_idx);
   return check_launch("rmsnorm_fwd");
 }
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
-                RowMap map, cudaStream_t s) {
+                const int32_t* x_idx, const int32_t* dx_idx, cudaStream_t s) {
   if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
   if (rows == 0) return 0;
-  rmsnorm_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, map);
+  rmsnorm_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
   return check_launch("rmsnorm_bwd");
 }
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s) {
@@ -894,6 +951,10 @@ int norm_from_sumsq(const float* sumsq, float gscale, float* out, cudaStream_t s
   norm_from_sumsq_kernel<<<1, 1, 0, s>>>(sumsq, gscale, out);
   return check_launch("norm_from_sumsq");
 }
+int fill_affine(int32_t* out, int n, int stride, int offset, cudaStream_t s) {
+  fill_affine_kernel<<<blocks_for(n, 128), 128, 0, s>>>(out, n, stride, offset);
+  return check_launch("fill_affine");
+}
 int fill_mod(int32_t* out, int n, int mod, cudaStream_t s) {
   fill_mod_kernel<<<blocks_for(n, 128), 128, 0, s>>>(out, n, mod);
   return check_launch("fill_mod");
@@ -904,13 +965,26 @@ int queries_to_i32(const int64_t* queries, const uint8_t* qmask, int32_t* ids, u
   return check_launch("queries_to_i32");
 }
 int stack_inputs(const int64_t* queries, const uint8_t* qmask, const int64_t* const* responses, int K, int b, int Q, int R,
-                 int pad_id, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s) {
+                 int pad_id, int packed, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s) {
   if (K > 8) return -1;
   RespPtrs rp{};
   for (int k = 0; k < K; ++k) rp.p[k] = responses[k];
-  const int64_t total = static_cast<int64_t>(K) * b * (Q + R);
-  stack_inputs_kernel<<<blocks_for(total, 256), 256, 0, s>>>(queries, qmask, rp, K, b, Q, R, pad_id, ids, mask, labels);
+  const int64_t total = packed ? static_cast<int64_t>(b) * (Q + K * R) : static_cast<int64_t>(K) * b * (Q + R);
+  stack_inputs_kernel<<<blocks_for(total, 256), 256, 0, s>>>(queries, qmask, rp, K, b, Q, R, pad_id, packed, ids, mask, labels);
   return check_launch("stack_inputs");
+}
+int build_positions(int32_t* pos, int N, int S, int S0, int R, int packed, cudaStream_t s) {
+  build_positions_kernel<<<blocks_for(static_cast<int64_t>(N) * S, 256), 256, 0, s>>>(pos, N, S, S0, R, packed);
+  return check_launch("build_positions");
+}
+int build_row_index(int32_t* src, int32_t* dst, int K, int b, int R, int S, int S0, int packed, int T, cudaStream_t s) {
+  build_row_index_kernel<<<blocks_for(static_cast<int64_t>(K) * b * R, 256), 256, 0, s>>>(src, dst, K, b, R, S, S0, packed, T);
+  return check_launch("build_row_index");
+}
+int fold_rows(bf16* dx, int K, int b, int S, int S0, int d, int T, cudaStream_t s) {
+  if (K <= 1) return 0;
+  fold_rows_kernel<<<b, 128, 0, s>>>(dx, K, b, S, S0, d, T);
+  return check_launch("fold_rows");
 }
 int kv_store_prefill(const bf16* qkv, bf16* kc, bf16* vc, int N, int S, int S_max, int d, cudaStream_t s) {
   kv_store_prefill_kernel<<<static_cast<unsigned>(static_cast<int64_t>(N) * S), 128, 0, s>>>(qkv, kc, vc, S, S_max, d);

@@ -10,21 +10,13 @@ namespace opadpo {
 
 using bf16 = __nv_bfloat16;
 
-// Row mapping used by the norm kernels so the final norm runs only on the R response-predicting rows of each
-// sequence (rl_models.py:120-121 slices logits[:, -R-1:-1]): compact row r <-> full row (r / rows_per_seq) *
-// seq_stride + seq_off + (r % rows_per_seq). rows_per_seq == 0 means identity.
-struct RowMap {
-  int rows_per_seq = 0;
-  int seq_stride = 0;
-  int seq_off = 0;
-};
-
-// y = w * bf16(x * rsqrt(mean(x^2) + eps))   [UPSTREAM HF LlamaRMSNorm]. x rows are taken through `map`, y is compact.
-int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, RowMap map, cudaStream_t s);
-// dx[map(r)] = (dres ? dres[map(r)] : 0) + rstd*(w*dy[r]) - x*rstd^3*mean(w*dy*x)   (norm weight is frozen: no dw).
-// rstd is recomputed from x. dx may alias dres.
+// y[r] = w * bf16(x[x_idx[r]] * rsqrt(mean(x^2) + eps))   [UPSTREAM HF LlamaRMSNorm]. x_idx (nullable = identity) lets the
+// final norm run only on the R response-predicting rows of each sequence (rl_models.py:120-121 slices logits[:, -R-1:-1]).
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s);
+// dx[dx_idx[r]] = (dres ? dres[dx_idx[r]] : 0) + rstd*(w*dy[r]) - x*rstd^3*mean(w*dy*x) with x = x[x_idx[r]]
+// (norm weight is frozen: no dw). rstd is recomputed from x. dx may alias dres.
 int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
-                RowMap map, cudaStream_t s);
+                const int32_t* x_idx, const int32_t* dx_idx, cudaStream_t s);
 // y = (x - mean) * rsqrt(var + eps) * w + b   [UPSTREAM CLIP LayerNorm]
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s);
 
@@ -92,6 +84,8 @@ int adamw_step(float* master, const float* grad, float* m, float* v, bf16* shado
                float eps, float wd, int step, float gscale, const float* sumsq, float max_norm, cudaStream_t s);
 // *out = sqrt(*sumsq) * gscale
 int norm_from_sumsq(const float* sumsq, float gscale, float* out, cudaStream_t s);
+// out[i] = i * stride + offset
+int fill_affine(int32_t* out, int n, int stride, int offset, cudaStream_t s);
 // out[i] = i % mod
 int fill_mod(int32_t* out, int n, int mod, cudaStream_t s);
 // rollout prologue: int64 queries -> int32 ids + mask copy, and out[n, :Q] = queries[n]
@@ -100,10 +94,15 @@ int queries_to_i32(const int64_t* queries, const uint8_t* qmask, int32_t* ids, u
 int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
 int bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s);
 
-// Stack K (query | response_k) rows (rl_models.py:95-112): ids/mask [K*b, Q+R] and, per response position,
-// labels [K*b, R] (= response id, or -1 at pad).
+// Stack the K responses behind the query (rl_models.py:95-112). packed = 0: K*b rows [query | resp_k]; packed = 1: b rows
+// [query | resp_0 | ... | resp_{K-1}] (shared prefix). ids/mask [N, L]; labels [K*b*R] in stacked order (-1 at pad).
 int stack_inputs(const int64_t* queries, const uint8_t* qmask, const int64_t* const* responses, int K, int b, int Q, int R,
-                 int pad_id, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s);
+                 int pad_id, int packed, int32_t* ids, uint8_t* mask, int32_t* labels, cudaStream_t s);
+// RoPE position of every padded-row slot; gather/scatter row indices of the response-predicting hidden rows;
+// fold of the shared last-prefix-row gradients (see elementwise.cu).
+int build_positions(int32_t* pos, int N, int S, int S0, int R, int packed, cudaStream_t s);
+int build_row_index(int32_t* src, int32_t* dst, int K, int b, int R, int S, int S0, int packed, int T, cudaStream_t s);
+int fold_rows(bf16* dx, int K, int b, int S, int S0, int d, int T, cudaStream_t s);
 
 // ---- decode (rollout) -------------------------------------------------------------------------------------
 // Copy the prefill keys/values of one layer from the packed qkv activation [N*S, 3d] into the static cache

@@ -675,14 +675,16 @@ int Engine::projector_forward(int adapter, const bf16* clip_feats, int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------ LLaMA layer
-int Engine::llama_layer_fwd(int l, int adapter, int64_t T, int N, int S, const uint64_t* kbits, const LayerActs& a,
-                            bf16* x_out, bf16* h, bf16* act, cudaStream_t s) {
+int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
+                            cudaStream_t s) {
+  const int64_t T = static_cast<int64_t>(lay.N) * lay.S;
+  const int N = lay.N, S = lay.S;
   const opadpo_config& c = cfg;
   const int d = c.d_model, F = c.d_ffn;
   LlamaLayer& L = layers[l];
-  EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, RowMap{}, s));
+  EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
   EN_CHECK(linear_fwd(L.qkv, adapter, h, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
-  EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, nullptr, 0, 2 * c.n_heads, hd, rope_cs, 0, s));
+  EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, 2 * c.n_heads, hd, rope_cs, 0, s));
   AttnArgs at;
   at.N = N;
   at.S = S;
@@ -697,10 +699,12 @@ int Engine::llama_layer_fwd(int l, int adapter, int64_t T, int N, int S, const u
   at.o = a.o;
   at.ld_o = d;
   at.lse = a.lse;
-  at.kbits = kbits;
+  at.kbits = lay.kbits;
+  at.prefix_len = lay.S0;
+  at.segment_len = lay.segR;
   EN_CHECK(attn_fwd_checked(at, s));
   EN_CHECK(linear_fwd(L.o, adapter, a.o, d, T, a.to, a.x1, d, ACT_NONE, a.x, d, s));
-  EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, RowMap{}, s));
+  EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, nullptr, s));
   EN_CHECK(linear_fwd(L.gu, adapter, h, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
   EN_CHECK(swiglu_fwd(a.gu, act, T, F, s));
   EN_CHECK(linear_fwd(L.down, adapter, act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s));
@@ -742,27 +746,35 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     return OPADPO_ESTATE;
   }
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads;
-  const int N = K * b, L = Q + R, S = L - 1 + P;
+  // Shared-prefix packing: the image+query prefix of a sample is computed once for its K responses (identical
+  // results). Rows: packed b x [query | resp_0 .. resp_{K-1}], unpacked K*b x [query | resp_k].
+  const int packed = (share_prefix && K > 1) ? 1 : 0;
+  const int N = packed ? b : K * b, L = packed ? Q + K * R : Q + R, S = L - 1 + P, S0 = Q - 1 + P;
   if (S > c.max_positions) {
     set_error("forward_logprobs: sequence %d exceeds max_positions %d", S, c.max_positions);
     return OPADPO_EINVAL;
   }
-  const int64_t T = static_cast<int64_t>(N) * S, NR = static_cast<int64_t>(N) * R;
+  const int64_t T = static_cast<int64_t>(N) * S, NR = static_cast<int64_t>(K) * b * R;
   TempPool tp(s);
   std::vector<void*>* tmp = &tp.ptrs;
   if (save) release_slot(save_slot, s);
   SaveCtx* cx = save ? &ctx[save_slot] : nullptr;
   std::vector<void*>* keep = save ? &cx->owned : tmp;
 
-  int32_t *ids, *labels, *img_of_row, *img_pos;
+  int32_t *ids, *labels, *img_of_row, *img_pos, *pos, *src_idx, *dst_idx;
   uint8_t *tokmask, *mask;
   EN_CHECK(pool_alloc(&ids, static_cast<int64_t>(N) * L, s, tmp));
   EN_CHECK(pool_alloc(&tokmask, static_cast<int64_t>(N) * L, s, tmp));
   EN_CHECK(pool_alloc(&labels, NR, s, keep));
   EN_CHECK(pool_alloc(&img_of_row, N, s, keep));
   EN_CHECK(pool_alloc(&img_pos, N, s, keep));
+  EN_CHECK(pool_alloc(&pos, T, s, keep));
+  EN_CHECK(pool_alloc(&src_idx, NR, s, keep));
+  EN_CHECK(pool_alloc(&dst_idx, NR, s, keep));
   EN_CHECK(pool_alloc(&mask, T, s, tmp));
-  EN_CHECK(stack_inputs(queries, qmask, responses, K, b, Q, R, c.pad_id, ids, tokmask, labels, s));
+  EN_CHECK(stack_inputs(queries, qmask, responses, K, b, Q, R, c.pad_id, packed, ids, tokmask, labels, s));
+  EN_CHECK(build_positions(pos, N, S, S0, R, packed, s));
+  EN_CHECK(build_row_index(src_idx, dst_idx, K, b, R, S, S0, packed, static_cast<int>(T), s));
   EN_CHECK(fill_mod(img_of_row, N, b, s));  // images are shared by the K responses of a sample (rl_models.py:107-111)
   // vision tower + projector, once per unique image
   const int64_t PR = static_cast<int64_t>(b) * P;
@@ -790,6 +802,13 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   EN_CHECK(attn_pack_mask(mask, kbits, N, S, s));
   EN_CHECK(pool_alloc(&h, T * d, s, tmp));
   EN_CHECK(pool_alloc(&act, T * F, s, tmp));
+  SeqLayout lay;
+  lay.N = N;
+  lay.S = S;
+  lay.S0 = packed ? S0 : 0;
+  lay.segR = packed ? R : 0;
+  lay.pos = pos;
+  lay.kbits = kbits;
 
   bf16* x_final = nullptr;
   if (save) {
@@ -805,7 +824,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     }
     for (int l = 0; l < c.n_layers; ++l) {
       bf16* xo = l + 1 < c.n_layers ? cx->layers[l + 1].x : x_final;
-      EN_CHECK(llama_layer_fwd(l, adapter, T, N, S, kbits, cx->layers[l], xo, h, act, s));
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, cx->layers[l], xo, h, act, s));
     }
   } else {
     LayerActs sc;
@@ -815,7 +834,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = cur;
-      EN_CHECK(llama_layer_fwd(l, adapter, T, N, S, kbits, sc, nxt, h, act, s));
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
       bf16* t = cur;
       cur = nxt;
       nxt = t;
@@ -826,8 +845,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   // final norm on the R response-predicting rows only, then the fused lm_head + log-sum-exp + label gather
   bf16* hn;
   EN_CHECK(pool_alloc(&hn, NR * d, s, keep));
-  const RowMap map{R, S, S - R - 1};
-  EN_CHECK(rmsnorm_fwd(x_final, final_norm, hn, NR, d, c.rms_eps, map, s));
+  EN_CHECK(rmsnorm_fwd(x_final, final_norm, hn, NR, d, c.rms_eps, src_idx, s));
   const int ntiles = gemm_num_n_tiles(c.vocab);
   float4* partials;
   float *label_logit, *lse_head;
@@ -866,6 +884,9 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     cx->labels = labels;
     cx->lse_head = lse_head;
     cx->kbits = kbits;
+    cx->lay = lay;
+    cx->src_idx = src_idx;
+    cx->dst_idx = dst_idx;
     cx->img_pos = img_pos;
     cx->img_of_row = img_of_row;
     cx->clip_feats = clip_feats;
@@ -892,7 +913,8 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   SaveCtx& cx = ctx[save_slot];
   const int adapter = cx.adapter;
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads, N = cx.N, S = cx.S, R = cx.R;
-  const int64_t T = static_cast<int64_t>(N) * S, NR = static_cast<int64_t>(N) * R;
+  const int64_t T = static_cast<int64_t>(N) * S, NR = static_cast<int64_t>(cx.K) * cx.b * R;
+  const int64_t T_scratch = T + static_cast<int64_t>(cx.K) * cx.b;  // + shared last-prefix-row scratch (packed rows)
   const int rr = r > 0 ? r : 8;
   TempPool tp(s);
   std::vector<void*>* tmp = &tp.ptrs;
@@ -900,7 +922,7 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   float* delta;
   EN_CHECK(pool_alloc(&dlogits, NR * c.vocab, s, tmp));
   EN_CHECK(pool_alloc(&dhn, NR * d, s, tmp));
-  EN_CHECK(pool_alloc(&dxa, T * d, s, tmp));
+  EN_CHECK(pool_alloc(&dxa, T_scratch * d, s, tmp));
   EN_CHECK(pool_alloc(&dxb, T * d, s, tmp));
   EN_CHECK(pool_alloc(&h, T * d, s, tmp));
   EN_CHECK(pool_alloc(&act, T * F, s, tmp));
@@ -938,8 +960,9 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     g.ldc = d;
     EN_CHECK(gemm_checked(g, s));
   }
-  cudaMemsetAsync(dxa, 0, static_cast<size_t>(T) * d * 2, s);
-  EN_CHECK(rmsnorm_bwd(dhn, cx.x_final, final_norm, nullptr, dxa, NR, d, c.rms_eps, RowMap{R, S, S - R - 1}, s));
+  cudaMemsetAsync(dxa, 0, static_cast<size_t>(T_scratch) * d * 2, s);
+  EN_CHECK(rmsnorm_bwd(dhn, cx.x_final, final_norm, nullptr, dxa, NR, d, c.rms_eps, cx.src_idx, cx.dst_idx, s));
+  if (cx.lay.segR > 0) EN_CHECK(fold_rows(dxa, cx.K, cx.b, S, cx.lay.S0, d, static_cast<int>(T), s));
 
   bf16* dx = dxa;   // gradient w.r.t. the layer output
   bf16* dx1 = dxb;  // gradient w.r.t. the post-attention residual stream
@@ -950,9 +973,9 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     EN_CHECK(swiglu_fwd(a.gu, act, T, F, s));
     EN_CHECK(linear_bwd(L.down, adapter, act, F, a.td, dx, d, T, u, dact, F, nullptr, 0, s));
     EN_CHECK(swiglu_bwd(dact, a.gu, dgu, T, F, s));
-    EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, RowMap{}, s));
+    EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, nullptr, s));
     EN_CHECK(linear_bwd(L.gu, adapter, h, d, a.tgu, dgu, 2 * F, T, u, dh, d, nullptr, 0, s));
-    EN_CHECK(rmsnorm_bwd(dh, a.x1, L.ln2, dx, dx1, T, d, c.rms_eps, RowMap{}, s));
+    EN_CHECK(rmsnorm_bwd(dh, a.x1, L.ln2, dx, dx1, T, d, c.rms_eps, nullptr, nullptr, s));
     // attention
     EN_CHECK(linear_bwd(L.o, adapter, a.o, d, a.to, dx1, d, T, u, dob, d, nullptr, 0, s));
     AttnArgs at;
@@ -970,6 +993,8 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     at.ld_o = d;
     at.lse = a.lse;
     at.kbits = cx.kbits;
+    at.prefix_len = cx.lay.S0;
+    at.segment_len = cx.lay.segR;
     at.dO = dob;
     at.ld_do = d;
     at.delta = delta;
@@ -978,10 +1003,10 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     at.dv = dqkv + 2 * d;
     at.ld_dqkv = 3 * d;
     EN_CHECK(attn_bwd_checked(at, s));
-    EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, nullptr, 0, 2 * H, hd, rope_cs, 1, s));
-    EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, RowMap{}, s));
+    EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, 2 * H, hd, rope_cs, 1, s));
+    EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
     EN_CHECK(linear_bwd(L.qkv, adapter, h, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s));
-    EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, RowMap{}, s));
+    EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, nullptr, nullptr, s));
   }
   // image rows -> projector (its LoRA adapters are trainable; the CLIP tower is not differentiated)
   const int64_t PR = static_cast<int64_t>(cx.b) * P;
@@ -1000,6 +1025,15 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     return OPADPO_ECUDA;
   }
   return 0;
+}
+
+int Engine::set_option(const char* name, int64_t value) {
+  if (strcmp(name, "share_prefix") == 0) {
+    share_prefix = value != 0;
+    return 0;
+  }
+  set_error("unknown option '%s'", name);
+  return OPADPO_EINVAL;
 }
 
 int Engine::zero_grad(cudaStream_t s) {
@@ -1098,11 +1132,18 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   }
   LayerActs sc;
   EN_CHECK(alloc_layer_acts(sc, T, d, F, H, r, false, s, tmp));
+  SeqLayout lay;
+  lay.N = N;
+  lay.S = S0;
+  lay.kbits = kbits;
+  int32_t* last_rows;
+  EN_CHECK(pool_alloc(&last_rows, N, s, tmp));
+  EN_CHECK(fill_affine(last_rows, N, S0, S0 - 1, s));
   bf16* cur = x0;
   bf16* nxt = x1buf;
   for (int l = 0; l < c.n_layers; ++l) {
     sc.x = cur;
-    EN_CHECK(llama_layer_fwd(l, adapter, T, N, S0, kbits, sc, nxt, h, act, s));
+    EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
     EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
     bf16* t = cur;
     cur = nxt;
@@ -1122,8 +1163,8 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   EN_CHECK(pool_alloc(&td, static_cast<int64_t>(N) * 3 * rr, s, tmp));
   EN_CHECK(pool_alloc(&logits, static_cast<int64_t>(N) * V, s, tmp));
 
-  auto head = [&](const bf16* xrows, RowMap map) -> int {
-    EN_CHECK(rmsnorm_fwd(xrows, final_norm, hd_, N, d, c.rms_eps, map, s));
+  auto head = [&](const bf16* xrows, const int32_t* row_idx) -> int {
+    EN_CHECK(rmsnorm_fwd(xrows, final_norm, hd_, N, d, c.rms_eps, row_idx, s));
     cudaMemsetAsync(logits, 0, static_cast<size_t>(N) * V * 4, s);
     GemmArgs a;  // fp32 logits (single K pass per tile: deterministic) so argmax ties break as torch.argmax does
     a.M = N;
@@ -1137,7 +1178,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     EN_CHECK(gemm_checked(a, s));
     return 0;
   };
-  EN_CHECK(head(cur, RowMap{1, S0, S0 - 1}));
+  EN_CHECK(head(cur, last_rows));
   EN_CHECK(greedy_pick(logits, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new, 0, s));
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   for (int step = 1; step < max_new; ++step) {
@@ -1146,19 +1187,19 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     bf16* xc = xd;
     for (int l = 0; l < c.n_layers; ++l) {
       LlamaLayer& L = layers[l];
-      EN_CHECK(rmsnorm_fwd(xc, L.ln1, hd_, N, d, c.rms_eps, RowMap{}, s));
+      EN_CHECK(rmsnorm_fwd(xc, L.ln1, hd_, N, d, c.rms_eps, nullptr, s));
       EN_CHECK(linear_fwd(L.qkv, adapter, hd_, d, N, td, qkvd, 3 * d, ACT_NONE, nullptr, 0, s));
       EN_CHECK(rope_inplace(qkvd, 3 * d, N, 1, nullptr, pos, 2 * H, hd, rope_cs, 0, s));
       EN_CHECK(decode_attention(qkvd, kc[l], vc[l], kmask, od, N, H, hd, pos, S_max, scale, s));
       EN_CHECK(linear_fwd(L.o, adapter, od, d, N, td, xd1, d, ACT_NONE, xc, d, s));
-      EN_CHECK(rmsnorm_fwd(xd1, L.ln2, hd_, N, d, c.rms_eps, RowMap{}, s));
+      EN_CHECK(rmsnorm_fwd(xd1, L.ln2, hd_, N, d, c.rms_eps, nullptr, s));
       EN_CHECK(linear_fwd(L.gu, adapter, hd_, d, N, td, gud, 2 * F, ACT_NONE, nullptr, 0, s));
       EN_CHECK(swiglu_fwd(gud, actd, N, F, s));
       bf16* xo = (xc == xd2) ? xd : xd2;
       EN_CHECK(linear_fwd(L.down, adapter, actd, F, N, td, xo, d, ACT_NONE, xd1, d, s));
       xc = xo;
     }
-    EN_CHECK(head(xc, RowMap{}));
+    EN_CHECK(head(xc, nullptr));
     EN_CHECK(greedy_pick(logits, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new,
                          step, s));
   }

@@ -53,6 +53,14 @@ struct LayerActs {
   float* lse = nullptr;
 };
 
+// How token rows are laid out for one forward: N rows of S padded positions; packed rows carry K response segments of
+// segR tokens behind a shared prefix of S0 positions (segR == 0: one response per row).
+struct SeqLayout {
+  int N = 0, S = 0, S0 = 0, segR = 0;
+  const int32_t* pos = nullptr;     // RoPE position per row slot [N*S] (null: slot index)
+  const uint64_t* kbits = nullptr;  // key validity bits [N, ceil(S/64)]
+};
+
 struct SaveCtx {
   bool valid = false;
   int adapter = 0, b = 0, K = 0, N = 0, Q = 0, R = 0, S = 0;
@@ -64,6 +72,8 @@ struct SaveCtx {
   int32_t* labels = nullptr;
   float* lse_head = nullptr;
   uint64_t* kbits = nullptr;
+  SeqLayout lay;
+  int32_t *src_idx = nullptr, *dst_idx = nullptr;  // response-predicting hidden rows (gather / gradient scatter)
   int32_t *img_pos = nullptr, *img_of_row = nullptr;
   bf16 *clip_feats = nullptr, *p_pre = nullptr, *p_act = nullptr, *t_p0 = nullptr, *t_p2 = nullptr;
 };
@@ -97,11 +107,13 @@ class Engine {
                      cudaStream_t s);
   int generate(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask, int Q, int max_new,
                int64_t* out_ids, cudaStream_t s);
+  int set_option(const char* name, int64_t value);
 
  private:
   opadpo_config cfg;
   int hd = 0, v_hd = 0, P = 0, Kp = 0, r = 0;
   float lora_scale = 1.f;
+  bool share_prefix = true;  // compute the image+query prefix once per sample for its K responses
   // base weights
   bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
   std::vector<LlamaLayer> layers;
@@ -136,8 +148,8 @@ class Engine {
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);
-  int llama_layer_fwd(int l, int adapter, int64_t T, int N, int S, const uint64_t* kbits, const LayerActs& a, bf16* x_out,
-                      bf16* h, bf16* act, cudaStream_t s);
+  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
+                      cudaStream_t s);
 };
 
 }  // namespace opadpo

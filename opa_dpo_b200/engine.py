@@ -192,6 +192,9 @@ class Engine:
                                    n_total=nt.value, n_train=ntr.value)
         return self._views
 
+    def set_option(self, name: str, value: int):
+        _lib.check(self.lib.opadpo_engine_set_option(self._h, name.encode(), int(value)), f"set_option({name})")
+
     def sync_shadow(self):
         _lib.check(self.lib.opadpo_engine_sync_shadow(self._h, _stream()), "sync_shadow")
 

@@ -89,8 +89,9 @@ def pack_mask(mask: torch.Tensor) -> torch.Tensor:
     return bits
 
 
-def _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits):
+def _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits, prefix_len=0, segment_len=0):
     d = AttnDesc()
+    d.prefix_len, d.segment_len = prefix_len, segment_len
     d.N, d.S, d.H, d.HD, d.causal, d.scale = N, S, H, HD, int(causal), scale
     assert q.stride(0) == k.stride(0) == v.stride(0)
     d.q, d.k, d.v, d.ld_qkv = q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0)
@@ -100,17 +101,18 @@ def _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits):
     return d
 
 
-def attn_fwd(q, k, v, o, lse, *, N, S, H, HD, causal, scale, kbits=None):
+def attn_fwd(q, k, v, o, lse, *, N, S, H, HD, causal, scale, kbits=None, prefix_len=0, segment_len=0):
     """q,k,v,o: [N*S, H*HD] bf16 views; lse: [N*S, H] f32 (or None)."""
     lib = _lib.load()
-    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits)
+    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits, prefix_len, segment_len)
     _lib.check(lib.opadpo_op_attn_fwd(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_attn_fwd")
     return o
 
 
-def attn_bwd(q, k, v, o, lse, dO, dq, dk, dv, delta, *, N, S, H, HD, causal, scale, kbits=None):
+def attn_bwd(q, k, v, o, lse, dO, dq, dk, dv, delta, *, N, S, H, HD, causal, scale, kbits=None, prefix_len=0,
+             segment_len=0):
     lib = _lib.load()
-    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits)
+    d = _attn_desc(q, k, v, o, lse, N, S, H, HD, causal, scale, kbits, prefix_len, segment_len)
     d.dO, d.ld_do = dO.data_ptr(), dO.stride(0)
     d.delta = delta.data_ptr()
     assert dq.stride(0) == dk.stride(0) == dv.stride(0)

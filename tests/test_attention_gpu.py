@@ -107,3 +107,57 @@ def test_attn_masked_holes():
     ro, _ = _ref_attn(q.float().reshape(N, S, H, D), k.float().reshape(N, S, H, D), v.float().reshape(N, S, H, D), mask,
                       True, 1 / math.sqrt(D))
     assert (o.float().reshape(N, S, H, D) - ro).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("S0,R,K,pads", [(703, 512, 2, False), (100, 60, 3, True), (64, 128, 2, True), (37, 200, 2, False)])
+def test_attn_shared_prefix_segments(S0, R, K, pads):
+    """Packed rows [prefix | resp_0 | ... | resp_{K-1}]: response queries see the prefix and their own segment only
+    (tile skipping + in-tile exclusion), forward and backward, against a dense fp32 reference with the same tree mask."""
+    from opa_dpo_b200 import ops
+    N, H, D = 2, 2, 128
+    S = S0 + K * R
+    T = N * S
+    g = torch.Generator(device="cuda").manual_seed(S0 + R)
+    qkv = torch.randn((T, 3 * H * D), generator=g, device="cuda").to(torch.bfloat16)
+    q, k, v = qkv[:, :H * D], qkv[:, H * D:2 * H * D], qkv[:, 2 * H * D:]
+    mask = torch.ones((N, S), dtype=torch.bool, device="cuda")
+    if pads:
+        mask[1, :5] = False                                  # left pads in the prefix
+        for kk in range(K):                                  # ragged responses: right pads inside each segment
+            mask[1, S0 + kk * R + R - 7 - kk:S0 + (kk + 1) * R] = False
+    scale = 1.0 / math.sqrt(D)
+    o = torch.zeros((T, H * D), device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros((T, H), device="cuda", dtype=torch.float32)
+    kbits = ops.pack_mask(mask)
+    ops.attn_fwd(q, k, v, o, lse, N=N, S=S, H=H, HD=D, causal=True, scale=scale, kbits=kbits, prefix_len=S0, segment_len=R)
+    torch.cuda.synchronize()
+    # dense reference
+    i = torch.arange(S, device="cuda")[:, None]
+    j = torch.arange(S, device="cuda")[None, :]
+    seg_start = torch.where(i >= S0, S0 + ((i - S0) // R) * R, torch.zeros_like(i))
+    tree = (j <= i) & ~((i >= S0) & (j >= S0) & (j < seg_start))
+    qf = q.float().reshape(N, S, H, D).requires_grad_(True)
+    kf = k.float().reshape(N, S, H, D).requires_grad_(True)
+    vf = v.float().reshape(N, S, H, D).requires_grad_(True)
+    s = torch.einsum("nihd,njhd->nhij", qf, kf) * scale
+    allow = tree[None, None] & mask[:, None, None, :]
+    s = s.masked_fill(~allow, float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+    ro = torch.einsum("nhij,njhd->nihd", p, vf)
+    sel = mask[:, :, None, None].expand_as(ro)
+    err = ((o.float().reshape(N, S, H, D) - ro) * sel).abs().max().item()
+    assert err < 2e-2, f"segment attn fwd max err {err}"
+    dO = (torch.randn((T, H * D), generator=g, device="cuda") * mask.reshape(T, 1)).to(torch.bfloat16)
+    dqkv = torch.full((T, 3 * H * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dq, dk, dv = dqkv[:, :H * D], dqkv[:, H * D:2 * H * D], dqkv[:, 2 * H * D:]
+    delta = torch.empty((T, H), device="cuda", dtype=torch.float32)
+    ops.attn_bwd(q, k, v, o, lse, dO, dq, dk, dv, delta, N=N, S=S, H=H, HD=D, causal=True, scale=scale, kbits=kbits,
+                 prefix_len=S0, segment_len=R)
+    torch.cuda.synchronize()
+    (ro * sel).backward(dO.float().reshape(N, S, H, D))
+    for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        got = got.float().reshape(N, S, H, D)
+        assert torch.isfinite(got).all(), f"{name} has non-finite values"
+        tol = 2e-2 * max(1.0, ref.abs().max().item())
+        e = (got - ref).abs().max().item()
+        assert e < tol, f"{name} max err {e} (tol {tol})"

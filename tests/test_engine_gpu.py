@@ -23,12 +23,13 @@ def _cfgs(n_layers=2, v_layers=2, **kw):
     return oc, ec
 
 
-def _build(oc, ec, peaked=1.0, trainable=True):
+def _build(oc, ec, peaked=1.0, trainable=True, share_prefix=1):
     from oracle import llava_oracle as O
     from opa_dpo_b200 import Engine, POLICY, REF
     w = O.init_weights(oc, peaked=peaked)
     lp, lr = O.init_lora(oc, 11), O.init_lora(oc, 12)
     eng = Engine(ec)
+    eng.set_option("share_prefix", share_prefix)
     sd = dict(w)
     sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
     eng.load_state_dict(sd)
@@ -46,12 +47,12 @@ def _cmp_lp(got, ref, what, atol=0.05, mean_tol=0.01):
         f"{what}: max |err| {err.max().item():.4g} mean {err.mean().item():.4g} (ref mean |x| {ref.abs().mean().item():.3g})"
 
 
-@pytest.mark.parametrize("n_layers,v_layers", [(0, 0), (0, 2), (1, 0), (2, 2)])
-def test_forward_logprobs_vs_oracle(n_layers, v_layers):
+@pytest.mark.parametrize("n_layers,v_layers,share", [(0, 0, 0), (0, 2, 0), (1, 0, 0), (2, 2, 0), (0, 0, 1), (1, 0, 1), (2, 2, 1)])
+def test_forward_logprobs_vs_oracle(n_layers, v_layers, share):
     from oracle import llava_oracle as O
     from opa_dpo_b200 import POLICY, REF, BASE
     oc, ec = _cfgs(n_layers, v_layers)
-    eng, w, lp, lr = _build(oc, ec, trainable=False)
+    eng, w, lp, lr = _build(oc, ec, trainable=False, share_prefix=share)
     images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
     dev = eng.device
     for adapter, lora in ((POLICY, lp), (REF, lr), (BASE, None)):
@@ -95,13 +96,15 @@ def _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, names):
     return loss.detach(), lpg, ref, pol
 
 
-def test_dpo_step_loss_and_lora_grads_vs_oracle():
-    """Four-forward DPO step (policy & frozen reference x chosen & rejected): loss within 1e-3 relative, LoRA grads."""
+@pytest.mark.parametrize("share", [0, 1])
+def test_dpo_step_loss_and_lora_grads_vs_oracle(share):
+    """Four-forward DPO step (policy & frozen reference x chosen & rejected): loss within 1e-3 relative, LoRA grads.
+    share=1: image+query prefix computed once per sample (packed rows); share=0: the reference's stacked rows."""
     from oracle import llava_oracle as O
     from opa_dpo_b200 import POLICY, REF
     from opa_dpo_b200.dpo import DPOArgs, FusedDPO
     oc, ec = _cfgs()
-    eng, w, lp, lr = _build(oc, ec)
+    eng, w, lp, lr = _build(oc, ec, share_prefix=share)
     images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
     lc = O.LossConfig(beta=0.1)
     loss_ref, lpg, ref_o, pol_o = _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, NAMES2)
