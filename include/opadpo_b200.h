@@ -37,7 +37,7 @@ int opadpo_abi_version(void);
  * Replaces (reference, all [UPSTREAM] through peft 0.5.0 lora.Linear wrapped nn.Linear; call sites
  * opadpo/dpo_models/qlora_model.py:133-143,211-216 and opadpo/dpo_models/rl_models.py:120).
  * ---------------------------------------------------------------------------------------------------------- */
-enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3 };
+enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3, OPADPO_EPI_F32_PARTIAL = 4 };
 enum { OPADPO_ACT_NONE = 0, OPADPO_ACT_GELU = 1, OPADPO_ACT_QUICK_GELU = 2 };
 
 typedef struct opadpo_gemm_desc {

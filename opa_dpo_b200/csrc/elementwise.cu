@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(NORM_THREADS)
 
 // ---------------------------------------------------------------------------------------------- RoPE
 __global__ void rope_kernel(bf16* x, int64_t ld, int64_t T, int S, const int32_t* __restrict__ pos, int pos_offset,
-                            int nheads, int hd, const float2* __restrict__ cs, int inverse) {
+                            const int32_t* __restrict__ pos_scalar, int nheads, int hd, const float2* __restrict__ cs,
+                            int inverse) {
   const int vec_per_head = hd >> 4;  // uint4 vectors in half a head
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = T * nheads * vec_per_head;
@@ -210,7 +211,7 @@ __global__ void rope_kernel(bf16* x, int64_t ld, int64_t T, int S, const int32_t
   const int v = static_cast<int>(idx % vec_per_head);
   const int h = static_cast<int>((idx / vec_per_head) % nheads);
   const int64_t t = idx / (static_cast<int64_t>(vec_per_head) * nheads);
-  const int p = (pos ? pos[t] : static_cast<int>(t % S)) + pos_offset;
+  const int p = (pos ? pos[t] : static_cast<int>(t % S)) + pos_offset + (pos_scalar ? *pos_scalar : 0);
   bf16* base = x + t * ld + h * hd + v * 8;
   uint4 lo = *reinterpret_cast<uint4*>(base);
   uint4 hi = *reinterpret_cast<uint4*>(base + (hd >> 1));
@@ -686,87 +687,144 @@ __global__ void kv_store_prefill_kernel(const bf16* __restrict__ qkv, bf16* __re
   }
 }
 
-// One CTA per (sequence, head): 128 threads; each warp strides over keys, lanes split the head dimension.
+// ---- split-K partial sums [splits, M, N] fp32 (gemm EPI_F32_PARTIAL) -> bf16, summed in a fixed order
+__device__ __forceinline__ float sum_partials(const float* __restrict__ part, int splits, int64_t slice, int64_t idx) {
+  float a = 0.f;
+  for (int sp = 0; sp < splits; ++sp) a += part[sp * slice + idx];
+  return a;
+}
+__global__ void partial_to_bf16_kernel(const float* __restrict__ part, int splits, int64_t n, bf16* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(sum_partials(part, splits, n, i));
+}
+// x_out = bf16(sum(part) + res);  h = w * bf16(x_out * rstd)   (residual add fused with the next RMSNorm)
+__global__ void __launch_bounds__(NORM_THREADS)
+    partial_residual_rmsnorm_kernel(const float* __restrict__ part, int splits, int64_t slice, const bf16* __restrict__ res,
+                                    bf16* __restrict__ x_out, const bf16* __restrict__ w, bf16* __restrict__ h, int d,
+                                    float eps) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  float v[NORM_MAXV * 8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV * 8; ++i) {
+    const int c = threadIdx.x + i * NORM_THREADS;
+    if (c < d) {
+      const float x = bf16_round(sum_partials(part, splits, slice, r * d + c) + __bfloat162float(res[r * d + c]));
+      v[i] = x;
+      ss += x * x;
+      x_out[r * d + c] = __float2bfloat16(x);
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / d + eps);
+  if (h) {
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV * 8; ++i) {
+      const int c = threadIdx.x + i * NORM_THREADS;
+      if (c < d) h[r * d + c] = __float2bfloat16(__bfloat162float(w[c]) * bf16_round(v[i] * rstd));
+    }
+  }
+}
+// act = bf16(silu(bf16(g)) ) * bf16(u) from partial sums of the fused gate|up GEMM [M, 2F]
+__global__ void partial_swiglu_kernel(const float* __restrict__ part, int splits, int64_t slice, bf16* __restrict__ act,
+                                      int64_t M, int F) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * F) return;
+  const int64_t m = idx / F;
+  const int f = static_cast<int>(idx % F);
+  const float g = bf16_round(sum_partials(part, splits, slice, m * 2 * F + f));
+  const float u = bf16_round(sum_partials(part, splits, slice, m * 2 * F + F + f));
+  act[idx] = __float2bfloat16(bf16_round(g / (1.f + __expf(-g))) * u);
+}
+
+// One CTA per (head, sequence), 8 warps; each half-warp owns one key per iteration: 16 lanes x 16 B = one 256 B head row
+// (coalesced), online softmax per half-warp, merged through shared memory. New k/v are appended at position
+// len = len_base + *cur first.
 template <int HD>
-__global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
+__global__ void __launch_bounds__(256) decode_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
                                                                bf16* __restrict__ vc, const uint8_t* __restrict__ kmask,
-                                                               bf16* __restrict__ o, int H, int len, int S_max, float scale) {
-  constexpr int EPL = HD / 32;  // elements per lane
+                                                               bf16* __restrict__ o, int H, int len_base,
+                                                               const int32_t* __restrict__ cur, int S_max, float scale) {
+  constexpr int LPK = HD / 8;        // lanes per key (16 for hd 128, 8 for hd 64)
+  constexpr int KPW = 32 / LPK;      // keys per warp per iteration
+  constexpr int GROUPS = 8 * KPW;    // key groups per CTA
   const int n = blockIdx.y, h = blockIdx.x;
   const int d = H * HD;
+  const int len = len_base + (cur ? *cur : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPK, ln = lane % LPK;
+  const int grp = warp * KPW + sub;
   const bf16* qrow = qkv + static_cast<int64_t>(n) * 3 * d + h * HD;
   bf16* kbase = kc + static_cast<int64_t>(n) * S_max * d + h * HD;
   bf16* vbase = vc + static_cast<int64_t>(n) * S_max * d + h * HD;
-  // append the new key/value at position len
-  if (warp == 0) {
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      kbase[static_cast<int64_t>(len) * d + lane * EPL + e] = qrow[d + lane * EPL + e];
-      vbase[static_cast<int64_t>(len) * d + lane * EPL + e] = qrow[2 * d + lane * EPL + e];
-    }
+  if (threadIdx.x < LPK) {  // append the new key/value (16 B per lane)
+    *reinterpret_cast<uint4*>(kbase + static_cast<int64_t>(len) * d + threadIdx.x * 8) =
+        *reinterpret_cast<const uint4*>(qrow + d + threadIdx.x * 8);
+    *reinterpret_cast<uint4*>(vbase + static_cast<int64_t>(len) * d + threadIdx.x * 8) =
+        *reinterpret_cast<const uint4*>(qrow + 2 * d + threadIdx.x * 8);
   }
   __syncthreads();
-  float q[EPL];
+  float q[8], acc[8];
+  unpack8(*reinterpret_cast<const uint4*>(qrow + ln * 8), q);
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) q[e] = __bfloat162float(qrow[lane * EPL + e]) * scale;
-  float m = -INFINITY, l = 0.f, acc[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int e = 0; e < 8; ++e) {
+    q[e] *= scale;
+    acc[e] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
   const uint8_t* km = kmask + static_cast<int64_t>(n) * S_max;
-  for (int j = warp; j <= len; j += 4) {
+  for (int j = grp; j <= len; j += GROUPS) {
     if (!km[j]) continue;
+    float kf[8], vf[8];
+    unpack8(*reinterpret_cast<const uint4*>(kbase + static_cast<int64_t>(j) * d + ln * 8), kf);
+    unpack8(*reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(j) * d + ln * 8), vf);
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) s += q[e] * __bfloat162float(kbase[static_cast<int64_t>(j) * d + lane * EPL + e]);
-    s = warp_sum(s);
+    for (int e = 0; e < 8; ++e) s += q[e] * kf[e];
+#pragma unroll
+    for (int o2 = LPK / 2; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
     const float nm = fmaxf(m, s);
     const float sc = __expf(m - nm);
     const float p = __expf(s - nm);
     l = l * sc + p;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e)
-      acc[e] = acc[e] * sc + p * __bfloat162float(vbase[static_cast<int64_t>(j) * d + lane * EPL + e]);
+    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * sc + p * vf[e];
     m = nm;
   }
-  __shared__ float sm[4], sl[4], sacc[4][HD];
-  if (lane == 0) {
-    sm[warp] = m;
-    sl[warp] = l;
+  __shared__ float sm[GROUPS], sl[GROUPS];
+  __shared__ float sacc[GROUPS][HD];
+  if (ln == 0) {
+    sm[grp] = m;
+    sl[grp] = l;
   }
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) sacc[warp][lane * EPL + e] = acc[e];
+  for (int e = 0; e < 8; ++e) sacc[grp][ln * 8 + e] = acc[e];
   __syncthreads();
-  if (warp == 0) {
-    float gm = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
-    float tot = 0.f;
-    float out[EPL];
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) out[e] = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float sc = sm[w] == -INFINITY ? 0.f : __expf(sm[w] - gm);
-      tot += sl[w] * sc;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) out[e] += sacc[w][lane * EPL + e] * sc;
+  if (threadIdx.x < HD) {
+    float gm = -INFINITY;
+    for (int g2 = 0; g2 < GROUPS; ++g2) gm = fmaxf(gm, sm[g2]);
+    float tot = 0.f, out = 0.f;
+    for (int g2 = 0; g2 < GROUPS; ++g2) {
+      const float sc = sm[g2] == -INFINITY ? 0.f : __expf(sm[g2] - gm);
+      tot += sl[g2] * sc;
+      out += sacc[g2][threadIdx.x] * sc;
     }
-    const float inv = tot > 0.f ? 1.f / tot : 0.f;
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) o[static_cast<int64_t>(n) * d + h * HD + lane * EPL + e] = __float2bfloat16(out[e] * inv);
+    o[static_cast<int64_t>(n) * d + h * HD + threadIdx.x] = __float2bfloat16(tot > 0.f ? out / tot : 0.f);
   }
 }
 
-__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ logits, int V, int eos_id, int pad_id,
-                                                           uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld,
-                                                           int step) {
+// Greedy pick over split-K partial logits [splits, N, V] (summed in fixed order). Writes the id at column *cur.
+__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ part, int splits, int64_t slice, int V,
+                                                           int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
+                                                           int64_t* out, int64_t out_ld, const int32_t* __restrict__ cur) {
   __shared__ float bv[32];
   __shared__ int bi[32];
   const int n = blockIdx.x;
-  const float* row = logits + static_cast<int64_t>(n) * V;
   float best = -INFINITY;
   int besti = V;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float x = row[i];
+    const float x = sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + i);
     if (x > best || (x == best && i < besti)) {
       best = x;
       besti = i;
@@ -804,10 +862,11 @@ __global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restri
       if (done[n]) id = pad_id;  // HF: finished sequences are padded (unfinished_sequences mask)
       if (id == eos_id) done[n] = 1;
       next_ids[n] = id;
-      out[static_cast<int64_t>(n) * out_ld + step] = id;
+      out[static_cast<int64_t>(n) * out_ld + *cur] = id;
     }
   }
 }
+__global__ void advance_counter_kernel(int32_t* cur) { *cur += 1; }
 
 inline int check_launch(const char* what) {
   count_launch();
@@ -845,12 +904,12 @@ int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t 
   layernorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, b, y, d, eps);
   return check_launch("layernorm_fwd");
 }
-int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, int nheads, int hd,
-                 const float2* cs, int inverse, cudaStream_t s) {
+int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, const int32_t* pos_scalar,
+                 int nheads, int hd, const float2* cs, int inverse, cudaStream_t s) {
   if (hd % 16 != 0) return -1;
   const int64_t total = T * nheads * (hd >> 4);
   if (total == 0) return 0;
-  rope_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, ld, T, S, pos, pos_offset, nheads, hd, cs, inverse);
+  rope_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, ld, T, S, pos, pos_offset, pos_scalar, nheads, hd, cs, inverse);
   return check_launch("rope");
 }
 int rope_table(float2* cs, int max_pos, int hd, float theta, cudaStream_t s) {
@@ -990,21 +1049,40 @@ int kv_store_prefill(const bf16* qkv, bf16* kc, bf16* vc, int N, int S, int S_ma
   kv_store_prefill_kernel<<<static_cast<unsigned>(static_cast<int64_t>(N) * S), 128, 0, s>>>(qkv, kc, vc, S, S_max, d);
   return check_launch("kv_store_prefill");
 }
-int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len,
-                     int S_max, float scale, cudaStream_t s) {
+int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len_base,
+                     const int32_t* cur, int S_max, float scale, cudaStream_t s) {
   dim3 grid(H, N);
   if (hd == 128)
-    decode_attention_kernel<128><<<grid, 128, 0, s>>>(qkv, kc, vc, kmask, o, H, len, S_max, scale);
+    decode_attention_kernel<128><<<grid, 256, 0, s>>>(qkv, kc, vc, kmask, o, H, len_base, cur, S_max, scale);
   else if (hd == 64)
-    decode_attention_kernel<64><<<grid, 128, 0, s>>>(qkv, kc, vc, kmask, o, H, len, S_max, scale);
+    decode_attention_kernel<64><<<grid, 256, 0, s>>>(qkv, kc, vc, kmask, o, H, len_base, cur, S_max, scale);
   else
     return -1;
   return check_launch("decode_attention");
 }
-int greedy_pick(const float* logits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
-                int64_t out_ld, int step, cudaStream_t s) {
-  greedy_pick_kernel<<<N, 1024, 0, s>>>(logits, V, eos_id, pad_id, done, next_ids, out, out_ld, step);
+int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
+                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s) {
+  greedy_pick_kernel<<<N, 1024, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, eos_id, pad_id, done, next_ids, out,
+                                        out_ld, cur);
   return check_launch("greedy_pick");
+}
+int advance_counter(int32_t* cur, cudaStream_t s) {
+  advance_counter_kernel<<<1, 1, 0, s>>>(cur);
+  return check_launch("advance_counter");
+}
+int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s) {
+  partial_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, s>>>(part, splits, n, out);
+  return check_launch("partial_to_bf16");
+}
+int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
+                             int d, float eps, cudaStream_t s) {
+  if (d > 8 * NORM_THREADS * NORM_MAXV) return -1;
+  partial_residual_rmsnorm_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(part, splits, M * d, res, x_out, w, h, d, eps);
+  return check_launch("partial_residual_rmsnorm");
+}
+int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s) {
+  partial_swiglu_kernel<<<blocks_for(M * F, 256), 256, 0, s>>>(part, splits, M * 2 * F, act, M, F);
+  return check_launch("partial_swiglu");
 }
 
 }  // namespace opadpo

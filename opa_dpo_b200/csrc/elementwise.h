@@ -21,10 +21,10 @@ int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, 
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s);
 
 // In-place rotary embedding (rotate_half layout) on `nheads` heads of width hd starting at x (row stride ld).
-// Position of row t is (pos ? pos[t] : (t % S)) + pos_offset. cs: float2 [max_pos, hd/2] (cos, sin). inverse=1 applies the
+// Position of row t is (pos ? pos[t] : (t % S)) + pos_offset + (pos_scalar ? *pos_scalar : 0)  (device scalar: decode). cs: float2 [max_pos, hd/2] (cos, sin). inverse=1 applies the
 // transpose rotation (backward).
-int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, int nheads, int hd,
-                 const float2* cs, int inverse, cudaStream_t s);
+int rope_inplace(bf16* x, int64_t ld, int64_t T, int S, const int32_t* pos, int pos_offset, const int32_t* pos_scalar,
+                 int nheads, int hd, const float2* cs, int inverse, cudaStream_t s);
 int rope_table(float2* cs, int max_pos, int hd, float theta, cudaStream_t s);
 
 // act = silu(gu[:, :F]) * gu[:, F:]  ;  backward: dgu from dact and gu
@@ -108,13 +108,19 @@ int fold_rows(bf16* dx, int K, int b, int S, int S0, int d, int T, cudaStream_t 
 // Copy the prefill keys/values of one layer from the packed qkv activation [N*S, 3d] into the static cache
 // kc/vc [N, S_max, d].
 int kv_store_prefill(const bf16* qkv, bf16* kc, bf16* vc, int N, int S, int S_max, int d, cudaStream_t s);
-// One new token per sequence: qkv [N, 3d] (already rotated); appends k,v at position len and attends over
-// keys 0..len with validity mask kmask [N, S_max] (u8). o [N, d].
-int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len,
-                     int S_max, float scale, cudaStream_t s);
-// logits f32 [N, V] -> argmax id (lowest index on ties, as torch.argmax); suppress id < 0 = none. Finished rows
-// (done[n] != 0) emit pad_id. Updates done when eos is produced, writes ids [N] (int32) and out[n*out_ld + step].
-int greedy_pick(const float* logits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
-                int64_t out_ld, int step, cudaStream_t s);
+// One new token per sequence: qkv [N, 3d] (already rotated); appends k,v at position len = len_base + *cur (device
+// counter, so the step is CUDA-graph replayable) and attends over keys 0..len with validity mask kmask [N, S_max] (u8).
+int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, bf16* o, int N, int H, int hd, int len_base,
+                     const int32_t* cur, int S_max, float scale, cudaStream_t s);
+// Split-K partial logits [splits, N, V] -> argmax id (lowest index on ties, as torch.argmax). Finished rows
+// (done[n] != 0) emit pad_id; done is set when eos is produced; writes next_ids [N] and out[n*out_ld + *cur].
+int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
+                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s);
+int advance_counter(int32_t* cur, cudaStream_t s);
+// Deterministic reductions of gemm EPI_F32_PARTIAL slices [splits, M, N] fused with the op that follows the linear.
+int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s);
+int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
+                             int d, float eps, cudaStream_t s);
+int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s);
 
 }  // namespace opadpo

@@ -2,6 +2,7 @@
 // attention.cu or elementwise.cu; nothing here computes on the CPU.
 #include "engine.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -684,7 +685,7 @@ int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const Laye
   LlamaLayer& L = layers[l];
   EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
   EN_CHECK(linear_fwd(L.qkv, adapter, h, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
-  EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, 2 * c.n_heads, hd, rope_cs, 0, s));
+  EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, nullptr, 2 * c.n_heads, hd, rope_cs, 0, s));
   AttnArgs at;
   at.N = N;
   at.S = S;
@@ -1003,7 +1004,7 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     at.dv = dqkv + 2 * d;
     at.ld_dqkv = 3 * d;
     EN_CHECK(attn_bwd_checked(at, s));
-    EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, 2 * H, hd, rope_cs, 1, s));
+    EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, nullptr, 2 * H, hd, rope_cs, 1, s));
     EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
     EN_CHECK(linear_bwd(L.qkv, adapter, h, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s));
     EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, nullptr, nullptr, s));
@@ -1139,69 +1140,202 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   int32_t* last_rows;
   EN_CHECK(pool_alloc(&last_rows, N, s, tmp));
   EN_CHECK(fill_affine(last_rows, N, S0, S0 - 1, s));
-  bf16* cur = x0;
-  bf16* nxt = x1buf;
-  for (int l = 0; l < c.n_layers; ++l) {
-    sc.x = cur;
-    EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
-    EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
-    bf16* t = cur;
-    cur = nxt;
-    nxt = t;
+  bf16* x_prefill_out = x0;
+  {
+    bf16* nxt = x1buf;
+    for (int l = 0; l < c.n_layers; ++l) {
+      sc.x = x_prefill_out;
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
+      EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
+      bf16* t = x_prefill_out;
+      x_prefill_out = nxt;
+      nxt = t;
+    }
   }
-  // ---- decode buffers (one row per sequence)
-  bf16 *xd, *xd1, *xd2, *hd_, *qkvd, *od, *gud, *actd, *td;
-  float* logits;
-  EN_CHECK(pool_alloc(&xd, static_cast<int64_t>(N) * d, s, tmp));
-  EN_CHECK(pool_alloc(&xd1, static_cast<int64_t>(N) * d, s, tmp));
-  EN_CHECK(pool_alloc(&xd2, static_cast<int64_t>(N) * d, s, tmp));
-  EN_CHECK(pool_alloc(&hd_, static_cast<int64_t>(N) * d, s, tmp));
-  EN_CHECK(pool_alloc(&qkvd, static_cast<int64_t>(N) * 3 * d, s, tmp));
-  EN_CHECK(pool_alloc(&od, static_cast<int64_t>(N) * d, s, tmp));
-  EN_CHECK(pool_alloc(&gud, static_cast<int64_t>(N) * 2 * F, s, tmp));
-  EN_CHECK(pool_alloc(&actd, static_cast<int64_t>(N) * F, s, tmp));
-  EN_CHECK(pool_alloc(&td, static_cast<int64_t>(N) * 3 * rr, s, tmp));
-  EN_CHECK(pool_alloc(&logits, static_cast<int64_t>(N) * V, s, tmp));
+  // ---- decode: one row per sequence. Every linear is a weight-streaming tcgen05 GEMM split over K so all SMs pull
+  // weights (EPI_F32_PARTIAL slices, reduced in a fixed order by the kernel that consumes them); the step reads its
+  // position from a device counter, so steps 2.. replay ONE captured CUDA graph.
+  const int64_t Nl = N;
+  bf16 *xa, *xb, *x1d, *hdn, *qkvd, *od, *actd, *td;
+  float* part;
+  int32_t* cur;
+  EN_CHECK(pool_alloc(&xa, Nl * d, s, tmp));
+  EN_CHECK(pool_alloc(&xb, Nl * d, s, tmp));
+  EN_CHECK(pool_alloc(&x1d, Nl * d, s, tmp));
+  EN_CHECK(pool_alloc(&hdn, Nl * d, s, tmp));
+  EN_CHECK(pool_alloc(&qkvd, Nl * 3 * d, s, tmp));
+  EN_CHECK(pool_alloc(&od, Nl * d, s, tmp));
+  EN_CHECK(pool_alloc(&actd, Nl * F, s, tmp));
+  EN_CHECK(pool_alloc(&td, Nl * 3 * rr, s, tmp));
+  EN_CHECK(pool_alloc(&cur, 1, s, tmp));
+  const int kMaxSplits = 32;
+  int64_t widest = std::max<int64_t>(std::max<int64_t>(3 * d, 2 * F), V);
+  EN_CHECK(pool_alloc(&part, static_cast<int64_t>(kMaxSplits) * Nl * widest, s, tmp));
+  cudaMemsetAsync(cur, 0, sizeof(int32_t), s);
 
-  auto head = [&](const bf16* xrows, const int32_t* row_idx) -> int {
-    EN_CHECK(rmsnorm_fwd(xrows, final_norm, hd_, N, d, c.rms_eps, row_idx, s));
-    cudaMemsetAsync(logits, 0, static_cast<size_t>(N) * V * 4, s);
-    GemmArgs a;  // fp32 logits (single K pass per tile: deterministic) so argmax ties break as torch.argmax does
+  const bool lora = adapter >= 0 && r > 0;
+  auto splits_for = [&](int n_out, int K1, int K2) {
+    const int tiles = ((N + 127) / 128) * ((n_out + 255) / 256);
+    const int kb = (K1 + 63) / 64 + (K2 + 63) / 64;
+    int sp = (2 * 148 + tiles - 1) / tiles;
+    sp = std::min(sp, std::max(1, kb / 2));
+    sp = std::min(sp, kMaxSplits);
+    return gemm_effective_splits(K1, K2, std::max(sp, 1));
+  };
+  // partial sums of y = x W^T + (s x A^T) B^T into `part` [splits, N, out]; returns the split count
+  auto linear_partial = [&](const LinearW& L, const bf16* x, int max_sp, int* nsplit) -> int {
+    const int G = L.groups;
+    if (lora && L.slot >= 0) {
+      const int spA = splits_for(G * r, L.in, 0);
+      GemmArgs a;
+      a.M = N;
+      a.N = G * r;
+      a.K1 = L.in;
+      a.A1 = {x, L.in};
+      a.B1 = {loraA(adapter, L), L.in};
+      a.alpha = lora_scale;
+      a.epilogue = EPI_F32_PARTIAL;
+      a.splits = spA;
+      a.C = part;
+      a.ldc = G * r;
+      EN_CHECK(gemm_checked(a, s));
+      EN_CHECK(partial_to_bf16(part, spA, Nl * G * r, td, s));
+    }
+    const int K2 = (lora && L.slot >= 0) ? r : 0;
+    int sp = splits_for(L.out, L.in, K2);
+    if (max_sp > 0 && sp > max_sp) sp = gemm_effective_splits(L.in, K2, max_sp);
+    GemmArgs a;
     a.M = N;
-    a.N = V;
-    a.K1 = d;
-    a.A1 = {hd_, d};
-    a.B1 = {lm_head, d};
-    a.epilogue = EPI_F32_ATOMIC;
-    a.C = logits;
-    a.ldc = V;
+    a.N = L.out;
+    a.K1 = L.in;
+    a.A1 = {x, L.in};
+    a.B1 = {L.W, L.in};
+    if (K2 > 0) {
+      a.K2 = r;
+      a.A2 = {td, static_cast<int64_t>(G) * r};
+      a.B2 = {loraB(adapter, L), r};
+      if (G > 1) {
+        if ((L.out / G) % 256 != 0) {
+          set_error("generate: fused group width %d must be a multiple of 256", L.out / G);
+          return OPADPO_EINVAL;
+        }
+        a.a2_group_n = L.out / G;
+        a.a2_group_stride = r;
+      }
+    }
+    a.epilogue = EPI_F32_PARTIAL;
+    a.splits = sp;
+    a.C = part;
+    a.ldc = L.out;
     EN_CHECK(gemm_checked(a, s));
+    *nsplit = sp;
     return 0;
   };
-  EN_CHECK(head(cur, last_rows));
-  EN_CHECK(greedy_pick(logits, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new, 0, s));
+  LinearW head_lin;  // lm_head as a bias-free, LoRA-free linear (lm_head is never a LoRA target)
+  head_lin.in = d;
+  head_lin.out = V;
+  head_lin.W = lm_head;
+  // fp32 logits with at most 2 K-splits: a + b is order independent, so argmax ties break exactly as torch.argmax
+  auto head_and_pick = [&](const bf16* hrows) -> int {
+    int sp = 1;
+    const int save_adapter = adapter;
+    (void)save_adapter;
+    {
+      GemmArgs a;
+      a.M = N;
+      a.N = V;
+      a.K1 = d;
+      a.A1 = {hrows, d};
+      a.B1 = {lm_head, d};
+      a.epilogue = EPI_F32_PARTIAL;
+      sp = gemm_effective_splits(d, 0, 2);
+      a.splits = sp;
+      a.C = part;
+      a.ldc = V;
+      EN_CHECK(gemm_checked(a, s));
+    }
+    EN_CHECK(greedy_pick(part, sp, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new,
+                         cur, s));
+    EN_CHECK(advance_counter(cur, s));
+    return 0;
+  };
+  // first token from the prefill's last position
+  EN_CHECK(rmsnorm_fwd(x_prefill_out, final_norm, hdn, N, d, c.rms_eps, last_rows, s));
+  EN_CHECK(head_and_pick(hdn));
+
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
-  for (int step = 1; step < max_new; ++step) {
-    const int pos = S0 + step - 1;  // absolute position of the token fed at this step
-    EN_CHECK(embed_rows(next_ids, embed, xd, N, d, V, s));
-    bf16* xc = xd;
+  auto decode_step = [&]() -> int {
+    // token fed at this step was written at column cur-1; its absolute position is S0 + cur - 1
+    EN_CHECK(embed_rows(next_ids, embed, xa, N, d, V, s));
+    if (c.n_layers > 0) EN_CHECK(rmsnorm_fwd(xa, layers[0].ln1, hdn, N, d, c.rms_eps, nullptr, s));
+    bf16* xc = xa;
+    bf16* xn = xb;
     for (int l = 0; l < c.n_layers; ++l) {
       LlamaLayer& L = layers[l];
-      EN_CHECK(rmsnorm_fwd(xc, L.ln1, hd_, N, d, c.rms_eps, nullptr, s));
-      EN_CHECK(linear_fwd(L.qkv, adapter, hd_, d, N, td, qkvd, 3 * d, ACT_NONE, nullptr, 0, s));
-      EN_CHECK(rope_inplace(qkvd, 3 * d, N, 1, nullptr, pos, 2 * H, hd, rope_cs, 0, s));
-      EN_CHECK(decode_attention(qkvd, kc[l], vc[l], kmask, od, N, H, hd, pos, S_max, scale, s));
-      EN_CHECK(linear_fwd(L.o, adapter, od, d, N, td, xd1, d, ACT_NONE, xc, d, s));
-      EN_CHECK(rmsnorm_fwd(xd1, L.ln2, hd_, N, d, c.rms_eps, nullptr, s));
-      EN_CHECK(linear_fwd(L.gu, adapter, hd_, d, N, td, gud, 2 * F, ACT_NONE, nullptr, 0, s));
-      EN_CHECK(swiglu_fwd(gud, actd, N, F, s));
-      bf16* xo = (xc == xd2) ? xd : xd2;
-      EN_CHECK(linear_fwd(L.down, adapter, actd, F, N, td, xo, d, ACT_NONE, xd1, d, s));
-      xc = xo;
+      int sp = 1;
+      EN_CHECK(linear_partial(L.qkv, hdn, 0, &sp));
+      EN_CHECK(partial_to_bf16(part, sp, Nl * 3 * d, qkvd, s));
+      EN_CHECK(rope_inplace(qkvd, 3 * d, N, 1, nullptr, S0 - 1, cur, 2 * H, hd, rope_cs, 0, s));
+      EN_CHECK(decode_attention(qkvd, kc[l], vc[l], kmask, od, N, H, hd, S0 - 1, cur, S_max, scale, s));
+      EN_CHECK(linear_partial(L.o, od, 0, &sp));
+      EN_CHECK(partial_residual_rmsnorm(part, sp, xc, x1d, L.ln2, hdn, N, d, c.rms_eps, s));
+      EN_CHECK(linear_partial(L.gu, hdn, 0, &sp));
+      EN_CHECK(partial_swiglu(part, sp, actd, N, F, s));
+      EN_CHECK(linear_partial(L.down, actd, 0, &sp));
+      const bf16* next_w = l + 1 < c.n_layers ? layers[l + 1].ln1 : final_norm;
+      EN_CHECK(partial_residual_rmsnorm(part, sp, x1d, xn, next_w, hdn, N, d, c.rms_eps, s));
+      bf16* t = xc;
+      xc = xn;
+      xn = t;
     }
-    EN_CHECK(head(xc, nullptr));
-    EN_CHECK(greedy_pick(logits, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new,
-                         step, s));
+    if (c.n_layers == 0) EN_CHECK(rmsnorm_fwd(xa, final_norm, hdn, N, d, c.rms_eps, nullptr, s));
+    EN_CHECK(head_and_pick(hdn));
+    return 0;
+  };
+  if (max_new > 1) {
+    EN_CHECK(decode_step());  // step 1 eagerly (first-use kernel attributes are set outside of capture)
+    const int remaining = max_new - 2;
+    if (remaining > 0) {
+      cudaStream_t cs = nullptr;
+      cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+      if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("generate: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return OPADPO_ECUDA;
+      }
+      cudaEventRecord(ev_in, s);
+      cudaStreamWaitEvent(cs, ev_in, 0);
+      cudaStream_t caller = s;
+      s = cs;  // the lambdas above capture `s` by reference
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      int rc = 0;
+      cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        rc = decode_step();
+        ce = cudaStreamEndCapture(cs, &graph);
+      }
+      if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+      if (rc == 0 && ce == cudaSuccess) {
+        for (int i = 0; i < remaining && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(exec, cs);
+        count_launch(0);
+      }
+      cudaEventRecord(ev_out, cs);
+      cudaStreamWaitEvent(caller, ev_out, 0);
+      s = caller;
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamSynchronize(cs);
+      cudaEventDestroy(ev_in);
+      cudaEventDestroy(ev_out);
+      cudaStreamDestroy(cs);
+      if (rc != 0) return rc;
+      if (ce != cudaSuccess) {
+        set_error("generate: CUDA graph decode failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return OPADPO_ECUDA;
+      }
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -46,7 +46,7 @@ struct KParams {
 };
 
 struct Tile {
-  int m_blk, n_blk, kb_begin, kb_end;
+  int m_blk, n_blk, kb_begin, kb_end, split;
 };
 
 __device__ __forceinline__ Tile decode_tile(const KParams& p, int tile) {
@@ -59,14 +59,15 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int tile) {
   const int gsize = min(GROUP_M, p.num_m - first_m);
   const int r = t - group * per_group;
   Tile o;
+  o.split = split;
   o.m_blk = first_m + r % gsize;
   o.n_blk = r / gsize;
   if (p.splits == 1) {
     o.kb_begin = 0;
     o.kb_end = p.kb1 + p.kb2;
-  } else {
+  } else {  // split-K over the concatenated k-blocks of both segments
     o.kb_begin = split * p.kb_per_split;
-    o.kb_end = min(p.kb1, o.kb_begin + p.kb_per_split);
+    o.kb_end = min(p.kb1 + p.kb2, o.kb_begin + p.kb_per_split);
   }
   return o;
 }
@@ -308,6 +309,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
           __syncwarp();
         }
+      } else if constexpr (EPI == EPI_F32_PARTIAL) {
+        // split-K partial sums, plain stores into slice `split` of C [splits, M, ldc] (deterministic reduction later)
+        float* crow = reinterpret_cast<float*>(p.C) + (static_cast<int64_t>(t.split) * p.M + row) * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < p.N) {
+            if (col0 + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(crow + col0 + j) =
+                    make_float4(__uint_as_float(r[j]) * p.alpha, __uint_as_float(r[j + 1]) * p.alpha,
+                                __uint_as_float(r[j + 2]) * p.alpha, __uint_as_float(r[j + 3]) * p.alpha);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) * p.alpha;
+            }
+          }
+          __syncwarp();
+        }
       } else if constexpr (EPI == EPI_LSE) {
         // Online log-sum-exp over this tile's columns, in base 2 (z2 = z*log2e).
         const int label = row_ok ? p.labels[row] : -1;
@@ -482,6 +507,13 @@ int gemm_prof_end(double* total_ms, double* total_flops, int64_t* launches) {
   return 0;
 }
 int gemm_num_n_tiles(int N) { return (N + BN - 1) / BN; }
+int gemm_effective_splits(int K1, int K2, int splits) {
+  const int kb_all = (K1 + BK - 1) / BK + (K2 + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > kb_all) splits = kb_all;
+  const int per = (kb_all + splits - 1) / splits;
+  return (kb_all + per - 1) / per;
+}
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K1 <= 0) {
@@ -492,8 +524,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: (A MN-major, B K-major) is not instantiated");
     return -2;
   }
-  if (a.splits > 1 && (a.epilogue != EPI_F32_ATOMIC || a.K2 > 0)) {
-    snprintf(g_err, sizeof(g_err), "gemm: split-K needs EPI_F32_ATOMIC and a single K segment");
+  if (a.splits > 1 && a.epilogue != EPI_F32_ATOMIC && a.epilogue != EPI_F32_PARTIAL) {
+    snprintf(g_err, sizeof(g_err), "gemm: split-K needs EPI_F32_ATOMIC or EPI_F32_PARTIAL");
     return -3;
   }
   if (a.a2_group_n > 0 && (a.a2_group_n % BN != 0 || a.a_mn_major)) {
@@ -504,7 +536,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
     return -5;
   }
-  if (a.epilogue == EPI_F32_ATOMIC && (a.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+  if ((a.epilogue == EPI_F32_ATOMIC || a.epilogue == EPI_F32_PARTIAL) && (a.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
     snprintf(g_err, sizeof(g_err), "gemm: f32 output needs ldc %% 4 == 0 and 16B-aligned C");
     return -5;
   }
@@ -539,9 +571,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.a2_group_n = a.a2_group_n;
   kp.a2_group_stride = a.a2_group_stride;
   int splits = a.splits < 1 ? 1 : a.splits;
-  if (splits > kp.kb1) splits = kp.kb1;
-  kp.kb_per_split = (kp.kb1 + splits - 1) / splits;
-  kp.splits = (kp.kb1 + kp.kb_per_split - 1) / kp.kb_per_split;
+  const int kb_all = kp.kb1 + kp.kb2;
+  if (splits > kb_all) splits = kb_all;
+  kp.kb_per_split = (kb_all + splits - 1) / splits;
+  kp.splits = (kb_all + kp.kb_per_split - 1) / kp.kb_per_split;
   kp.num_m = (a.M + BM - 1) / BM;
   kp.num_n = (a.N + BN - 1) / BN;
   kp.num_tiles = kp.num_m * kp.num_n * kp.splits;
@@ -568,6 +601,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_F32_ATOMIC: return launch_impl<AMN, BMN, EPI_F32_ATOMIC>(maps, kp, grid, stream); \
     case EPI_LSE: return launch_impl<AMN, BMN, EPI_LSE>(maps, kp, grid, stream);             \
     case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD>(maps, kp, grid, stream);       \
+    case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL>(maps, kp, grid, stream); \
     default: break;                                                                          \
   }
   if (!a.a_mn_major && !a.b_mn_major) {

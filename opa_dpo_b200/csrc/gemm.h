@@ -21,6 +21,7 @@ enum GemmEpilogue : int {
   EPI_F32_ATOMIC = 1,  // C f32 += alpha*acc  (red.global.add; split-K capable)  -- LoRA wgrad into the grad bucket
   EPI_LSE = 2,       // fused lm_head log-sum-exp partials + label-logit gather (never materialises logits)
   EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - exp(alpha*acc - lse[m]))  (CE backward tile)
+  EPI_F32_PARTIAL = 4,  // C f32 [splits, M, ldc]: plain per-split stores (decode: weight streaming fills all SMs, fixed-order reduce)
 };
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICK_GELU = 2 };
@@ -59,6 +60,8 @@ struct GemmArgs {
 int gemm_launch(const GemmArgs& args, cudaStream_t stream);
 const char* gemm_last_error();
 int gemm_num_n_tiles(int N);
+// number of K splits gemm_launch will really use for (K1, K2, requested splits): sizes the EPI_F32_PARTIAL buffer
+int gemm_effective_splits(int K1, int K2, int splits);
 // bench instrumentation: time every GEMM launch with CUDA events on its stream
 void gemm_prof_begin();
 int gemm_prof_end(double* total_ms, double* total_flops, int64_t* launches);
