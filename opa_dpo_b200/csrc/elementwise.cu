@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(256) decode_attention_kernel(const bf16* __res
   }
   float m = -INFINITY, l = 0.f;
   const uint8_t* km = kmask + static_cast<int64_t>(n) * S_max;
+  const unsigned gmask = (((LPK == 32) ? 0u : (1u << LPK)) - 1u) << (sub * LPK);
   for (int j = grp; j <= len; j += GROUPS) {
     if (!km[j]) continue;
     float kf[8], vf[8];
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(256) decode_attention_kernel(const bf16* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) s += q[e] * kf[e];
 #pragma unroll
-    for (int o2 = LPK / 2; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    for (int o2 = LPK / 2; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(gmask, s, o2);  // key groups of a warp diverge
     const float nm = fmaxf(m, s);
     const float sc = __expf(m - nm);
     const float p = __expf(s - nm);
