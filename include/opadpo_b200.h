@@ -185,10 +185,21 @@ int opadpo_zero_grad(opadpo_engine* e, void* stream);
  * grad_scale multiplies the bucket first (1/world_size after a sum all-reduce). grad_norm_out: device f32 or NULL. */
 int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, float eps, float weight_decay,
                           float max_grad_norm, float grad_scale, float* grad_norm_out, void* stream);
-/* Greedy rollout (online_generator.py:292-309 with do_sample=False; rl_models.py:166-188): writes
- * out_ids int64 [b, Q + max_new] = queries | generated (pad after EOS). adapter = -1 runs the bare base model. */
+/* Rollout (model.generate of online_generator.py:292-309 / rl_models.py:166-188): writes out_ids int64
+ * [b, Q + max_new] = queries | generated (pad after EOS). adapter = -1 runs the bare base model.
+ * sampler = NULL or do_sample = 0: greedy (ids reproduce the reference exactly). do_sample = 1: HF warper order
+ * temperature -> top_k -> top_p -> multinomial with a counter-based RNG keyed by (seed, sequence, step); supported:
+ * top_k in [1,64] with any top_p, or top_k = 0 with top_p = 1. */
+typedef struct opadpo_sampler {
+  int32_t do_sample;
+  int32_t top_k;
+  float top_p;
+  float temperature;
+  uint64_t seed;
+} opadpo_sampler;
 int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
-                    const uint8_t* qmask, int32_t Q, int32_t max_new, int64_t* out_ids, void* stream);
+                    const uint8_t* qmask, int32_t Q, int32_t max_new, const opadpo_sampler* sampler, int64_t* out_ids,
+                    void* stream);
 /* Measurement hooks (bench.py): between begin and end every tcgen05 GEMM launch is bracketed by CUDA events on its own
  * stream; end synchronises and returns the summed kernel time, the executed FLOPs (2*M*N*K with K padded to the 64-wide
  * k-block) and the launch count. */

@@ -85,6 +85,11 @@ class DpoPairDesc(ctypes.Structure):
     ]
 
 
+class Sampler(ctypes.Structure):
+    _fields_ = [("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("top_p", ctypes.c_float),
+                ("temperature", ctypes.c_float), ("seed", ctypes.c_uint64)]
+
+
 class Config(ctypes.Structure):
     _fields_ = [
         ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32),
@@ -132,7 +137,7 @@ def _declare_engine(lib):
     lib.opadpo_backward.argtypes = [vp, i32, vp, vp]
     lib.opadpo_zero_grad.argtypes = [vp, vp]
     lib.opadpo_optimizer_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]
-    lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp]
+    lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, c.POINTER(Sampler), vp, vp]
     lib.opadpo_prof_begin.argtypes = []
     lib.opadpo_prof_end.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64)]
     lib.opadpo_launch_count.argtypes = []

@@ -246,10 +246,12 @@ int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, 
                                  static_cast<cudaStream_t>(stream));
 }
 int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
-                    const uint8_t* qmask, int32_t Q, int32_t max_new, int64_t* out_ids, void* stream) {
+                    const uint8_t* qmask, int32_t Q, int32_t max_new, const opadpo_sampler* sampler, int64_t* out_ids,
+                    void* stream) {
   ENGINE_GUARD(e);
   if (!images || !queries || !qmask || !out_ids) { set_error("opadpo_generate: null pointer"); return OPADPO_EINVAL; }
-  return e->impl->generate(adapter, images, b, queries, qmask, Q, max_new, out_ids, static_cast<cudaStream_t>(stream));
+  return e->impl->generate(adapter, images, b, queries, qmask, Q, max_new, sampler, out_ids,
+                           static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -869,6 +869,180 @@ __global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restri
 }
 __global__ void advance_counter_kernel(int32_t* cur) { *cur += 1; }
 
+// Counter-based uniform in [0,1): splitmix64 over (seed, row, step) — reproducible per (seed, sequence, position).
+__device__ __forceinline__ float uniform01(uint64_t seed, uint32_t row, uint32_t step) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(row) * 0x100000001B3ull + step + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// HF sampling warpers [UPSTREAM GenerationMixin.sample as driven by online_generator.py:292-309]: temperature, then
+// top-k (keep the k largest logits), then top-p (keep the smallest high-probability set whose preceding cumulative
+// mass is < top_p, at least one token), then multinomial over the survivors. One CTA per sequence; each thread owns a
+// strided slice of the vocabulary in registers; the k winners come out in descending order from k block-argmax rounds.
+constexpr int SAMPLE_THREADS = 1024;
+constexpr int SAMPLE_MAX_PER_THREAD = 40;  // vocab <= 40960
+constexpr int SAMPLE_MAX_K = 64;
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+    sample_pick_kernel(const float* __restrict__ part, int splits, int64_t slice, int V, int top_k, float top_p,
+                       float inv_temp, uint64_t seed, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
+                       int64_t out_ld, const int32_t* __restrict__ cur) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  __shared__ float topv[SAMPLE_MAX_K];
+  __shared__ int topi[SAMPLE_MAX_K];
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[SAMPLE_MAX_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * SAMPLE_THREADS;
+    v[i] = c < V ? sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + c) * inv_temp : -INFINITY;
+  }
+  int chosen = 0;
+  if (top_k > 0) {
+    for (int round = 0; round < top_k; ++round) {
+      float best = -INFINITY;
+      int besti = V;
+#pragma unroll
+      for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+        const int c = threadIdx.x + i * SAMPLE_THREADS;
+        if (v[i] > best || (v[i] == best && c < besti)) {
+          best = v[i];
+          besti = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) {
+          best = ob;
+          besti = oi;
+        }
+      }
+      __syncthreads();
+      if (lane == 0) {
+        bv[warp] = best;
+        bi[warp] = besti;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        best = bv[lane];
+        besti = bi[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (ob > best || (ob == best && oi < besti)) {
+            best = ob;
+            besti = oi;
+          }
+        }
+        if (lane == 0) {
+          topv[round] = best;
+          topi[round] = besti;
+        }
+      }
+      __syncthreads();
+      const int win = topi[round];
+      if (win < V && (win % SAMPLE_THREADS) == threadIdx.x) {
+#pragma unroll
+        for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i)
+          if (i == win / SAMPLE_THREADS) v[i] = -INFINITY;
+      }
+    }
+    if (threadIdx.x == 0) {
+      const float mx = topv[0];
+      float tot = 0.f;
+      for (int i = 0; i < top_k; ++i) tot += __expf(topv[i] - mx);
+      // nucleus: token i survives while the mass BEFORE it is < top_p
+      int keep = 0;
+      float before = 0.f, kept = 0.f;
+      for (int i = 0; i < top_k; ++i) {
+        const float p = __expf(topv[i] - mx) / tot;
+        if (i > 0 && before >= top_p) break;
+        kept += p;
+        before += p;
+        ++keep;
+      }
+      const float u = uniform01(seed, n, static_cast<uint32_t>(*cur)) * kept;
+      float acc = 0.f;
+      int pick = keep - 1;
+      for (int i = 0; i < keep; ++i) {
+        acc += __expf(topv[i] - mx) / tot;
+        if (u < acc) {
+          pick = i;
+          break;
+        }
+      }
+      topi[0] = topi[pick];
+    }
+    __syncthreads();
+    chosen = topi[0];
+  } else {
+    // full-vocabulary multinomial (top_k = 0, top_p = 1): inverse CDF over softmax
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mx = fmaxf(mx, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) bv[warp] = mx;
+    __syncthreads();
+    mx = bv[0];
+    for (int w = 1; w < 32; ++w) mx = fmaxf(mx, bv[w]);
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mine += __expf(v[i] - mx);  // -inf -> 0
+    const float tot = block_sum(mine, red);
+    // thread t owns columns {t + i*1024}; order the CDF thread-major (any fixed order is a valid multinomial)
+    __shared__ float tsum[SAMPLE_THREADS];
+    tsum[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float u = uniform01(seed, n, static_cast<uint32_t>(*cur)) * tot;
+      float acc = 0.f;
+      int owner = SAMPLE_THREADS - 1;
+      for (int t = 0; t < SAMPLE_THREADS; ++t) {
+        if (u < acc + tsum[t]) {
+          owner = t;
+          break;
+        }
+        acc += tsum[t];
+      }
+      bi[0] = owner;
+      bv[0] = u - acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == bi[0]) {
+      float rem = bv[0], acc = 0.f;
+      int pick = -1, last = 0;
+#pragma unroll
+      for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+        const int c = threadIdx.x + i * SAMPLE_THREADS;
+        if (c < V && pick < 0) {
+          last = c;
+          acc += __expf(v[i] - mx);
+          if (rem < acc) pick = c;
+        }
+      }
+      topi[0] = pick >= 0 ? pick : last;
+    }
+    __syncthreads();
+    chosen = topi[0];
+  }
+  if (threadIdx.x == 0) {
+    int id = chosen;
+    if (done[n]) id = pad_id;
+    if (id == eos_id) done[n] = 1;
+    next_ids[n] = id;
+    out[static_cast<int64_t>(n) * out_ld + *cur] = id;
+  }
+}
+
 inline int check_launch(const char* what) {
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -1066,6 +1240,15 @@ int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int
   greedy_pick_kernel<<<N, 1024, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, eos_id, pad_id, done, next_ids, out,
                                         out_ld, cur);
   return check_launch("greedy_pick");
+}
+int sample_pick(const float* partials, int splits, int N, int V, int top_k, float top_p, float temperature, uint64_t seed,
+                int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* cur,
+                cudaStream_t s) {
+  if (V > SAMPLE_THREADS * SAMPLE_MAX_PER_THREAD || top_k > SAMPLE_MAX_K || top_k < 0) return -1;
+  if (top_k == 0 && top_p < 1.f) return -1;  // nucleus without top-k would need a full sort: not on the reference's path
+  sample_pick_kernel<<<N, SAMPLE_THREADS, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, top_k, top_p,
+                                                  1.f / temperature, seed, eos_id, pad_id, done, next_ids, out, out_ld, cur);
+  return check_launch("sample_pick");
 }
 int advance_counter(int32_t* cur, cudaStream_t s) {
   advance_counter_kernel<<<1, 1, 0, s>>>(cur);

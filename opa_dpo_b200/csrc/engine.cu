@@ -1033,6 +1033,14 @@ int Engine::set_option(const char* name, int64_t value) {
     share_prefix = value != 0;
     return 0;
   }
+  if (strcmp(name, "adam_step") == 0) {  // optimizer-state restore (resume_training, dpo_trainer.py:901-931)
+    if (trainable_adapter < 0 || value < 0) {
+      set_error("adam_step: no trainable adapter or negative step");
+      return OPADPO_ESTATE;
+    }
+    adapters[trainable_adapter].step = static_cast<int>(value);
+    return 0;
+  }
   set_error("unknown option '%s'", name);
   return OPADPO_EINVAL;
 }
@@ -1068,10 +1076,17 @@ int Engine::optimizer_step(float lr, float b1, float b2, float eps, float wd, fl
 // multimodal prefill, then one token per step; finished rows emit pad; stops early when every row is finished
 // (remaining columns are pad) — here the loop always runs max_new steps on device and pads, which yields the same ids.
 int Engine::generate(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask, int Q,
-                     int max_new, int64_t* out_ids, cudaStream_t s) {
+                     int max_new, const opadpo_sampler* sampler, int64_t* out_ids, cudaStream_t s) {
   const opadpo_config& c = cfg;
   if (adapter < -1 || adapter > 1 || b <= 0 || Q <= 0 || max_new <= 0) {
     set_error("generate: bad arguments");
+    return OPADPO_EINVAL;
+  }
+  const bool do_sample = sampler && sampler->do_sample;
+  if (do_sample && (!(sampler->temperature > 0.f) || sampler->top_k < 0 || sampler->top_k > 64 ||
+                    !(sampler->top_p > 0.f) || (sampler->top_k == 0 && sampler->top_p < 1.f))) {
+    set_error("generate: unsupported sampler (temperature %g top_k %d top_p %g): need temperature > 0, top_k in [1,64] "
+              "or top_k = 0 with top_p = 1", sampler->temperature, sampler->top_k, sampler->top_p);
     return OPADPO_EINVAL;
   }
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads, V = c.vocab;
@@ -1231,15 +1246,9 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     *nsplit = sp;
     return 0;
   };
-  LinearW head_lin;  // lm_head as a bias-free, LoRA-free linear (lm_head is never a LoRA target)
-  head_lin.in = d;
-  head_lin.out = V;
-  head_lin.W = lm_head;
   // fp32 logits with at most 2 K-splits: a + b is order independent, so argmax ties break exactly as torch.argmax
   auto head_and_pick = [&](const bf16* hrows) -> int {
     int sp = 1;
-    const int save_adapter = adapter;
-    (void)save_adapter;
     {
       GemmArgs a;
       a.M = N;
@@ -1254,8 +1263,13 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
       a.ldc = V;
       EN_CHECK(gemm_checked(a, s));
     }
-    EN_CHECK(greedy_pick(part, sp, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new,
-                         cur, s));
+    if (do_sample) {
+      EN_CHECK(sample_pick(part, sp, N, V, sampler->top_k, sampler->top_p, sampler->temperature, sampler->seed, c.eos_id,
+                           c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new, cur, s));
+    } else {
+      EN_CHECK(greedy_pick(part, sp, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q,
+                           static_cast<int64_t>(Q) + max_new, cur, s));
+    }
     EN_CHECK(advance_counter(cur, s));
     return 0;
   };

@@ -106,7 +106,7 @@ class Engine {
   int optimizer_step(float lr, float b1, float b2, float eps, float wd, float max_norm, float gscale, float* norm_out,
                      cudaStream_t s);
   int generate(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask, int Q, int max_new,
-               int64_t* out_ids, cudaStream_t s);
+               const opadpo_sampler* sampler, int64_t* out_ids, cudaStream_t s);
   int set_option(const char* name, int64_t value);
 
  private:

@@ -237,14 +237,16 @@ class Engine:
                                                   grad_scale, norm.data_ptr(), _stream()), "opadpo_optimizer_step")
         return norm
 
-    def generate(self, adapter: int, images: torch.Tensor, queries: torch.Tensor, qmask: torch.Tensor, max_new_tokens: int):
+    def generate(self, adapter: int, images: torch.Tensor, queries: torch.Tensor, qmask: torch.Tensor, max_new_tokens: int,
+                 do_sample: bool = False, top_k: int = 0, top_p: float = 1.0, temperature: float = 1.0, seed: int = 0):
         b, Q = queries.shape
+        sm = _lib.Sampler(int(do_sample), int(top_k), float(top_p), float(temperature), int(seed) & (2 ** 64 - 1))
         images = images.to(self.device, torch.float32).contiguous()
         queries = queries.to(self.device, torch.int64).contiguous()
         qmask = qmask.to(self.device, torch.uint8).contiguous()
         out = torch.empty((b, Q + max_new_tokens), device=self.device, dtype=torch.int64)
         _lib.check(self.lib.opadpo_generate(self._h, adapter, images.data_ptr(), b, queries.data_ptr(), qmask.data_ptr(), Q,
-                                            max_new_tokens, out.data_ptr(), _stream()), "opadpo_generate")
+                                            max_new_tokens, ctypes.byref(sm), out.data_ptr(), _stream()), "opadpo_generate")
         return out
 
     def launch_count(self) -> int:

@@ -1,0 +1,141 @@
+"""Optimizer / scheduler / checkpoint mirrors for the engine-owned LoRA bucket.
+
+* `B200AdamW`       <- create_optimizer (utils/trainer_utils.py:9-38): AdamW(beta 0.9/0.999, eps 1e-8, wd) — the update itself
+                      is the fused clip+AdamW kernel over the flat fp32 bucket (`opadpo_optimizer_step`); this class only
+                      carries hyper-parameters, the step count and (de)serialises the moments like a torch optimizer.
+* `cosine_schedule` <- create_scheduler (utils/trainer_utils.py:41-49) = HF get_scheduler("cosine", warmup, total).
+* `save_checkpoint` / `load_checkpoint` <- DPOTrainer.save_model / resume_training (dpo_trainer.py:837-931):
+      <output_dir>/checkpoint-{step}/adapter_model/lora_policy/{adapter_model.bin, adapter_config.json},
+      optimizer.pt, scheduler.pt; `get_last_checkpoint` as utils/lora_utils.py:31-47.
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+from typing import Dict, Optional
+
+import torch
+
+
+class B200AdamW:
+    def __init__(self, model, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_grad_norm: float = 1.0):
+        if model.flat_param is None:
+            raise RuntimeError("B200AdamW: call model.make_trainable() first")
+        self.model = model
+        self.param_groups = [dict(lr=lr, initial_lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay,
+                                  params=[model.flat_param])]
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        self.last_grad_norm: Optional[torch.Tensor] = None
+
+    def step(self, grad_scale: float = 1.0):
+        g = self.param_groups[0]
+        self.last_grad_norm = self.model.engine.optimizer_step(g["lr"], g["betas"], g["eps"], g["weight_decay"],
+                                                               self.max_grad_norm, grad_scale)
+        self.step_count += 1
+        return self.last_grad_norm
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.model.engine.zero_grad()
+
+    def state_dict(self) -> Dict:
+        v = self.model.engine.buffers()
+        return dict(state={0: dict(step=self.step_count, exp_avg=v["exp_avg"].detach().cpu().clone(),
+                                   exp_avg_sq=v["exp_avg_sq"].detach().cpu().clone())},
+                    param_groups=[{k: val for k, val in self.param_groups[0].items() if k != "params"} | {"params": [0]}],
+                    max_grad_norm=self.max_grad_norm)
+
+    def load_state_dict(self, sd: Dict):
+        st = sd["state"][0]
+        v = self.model.engine.buffers()
+        v["exp_avg"].copy_(st["exp_avg"].to(v["exp_avg"].device))
+        v["exp_avg_sq"].copy_(st["exp_avg_sq"].to(v["exp_avg_sq"].device))
+        self.step_count = int(st["step"])
+        self.model.engine.set_option("adam_step", self.step_count)
+        for k, val in sd["param_groups"][0].items():
+            if k != "params":
+                self.param_groups[0][k] = tuple(val) if k == "betas" else val
+        self.max_grad_norm = sd.get("max_grad_norm", self.max_grad_norm)
+
+
+class cosine_schedule:
+    """HF get_cosine_schedule_with_warmup [UPSTREAM transformers.optimization]; stepped once per outer step
+    (rl_trainer.py:188-189)."""
+
+    def __init__(self, optimizer: B200AdamW, num_warmup_steps: int, num_training_steps: int):
+        self.opt, self.warmup, self.total = optimizer, num_warmup_steps, num_training_steps
+        self.last_epoch = 0
+        self._apply()
+
+    def factor(self, step: int) -> float:
+        if step < self.warmup:
+            return float(step) / float(max(1, self.warmup))
+        progress = float(step - self.warmup) / float(max(1, self.total - self.warmup))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * progress)))
+
+    def _apply(self):
+        for g in self.opt.param_groups:
+            g["lr"] = g["initial_lr"] * self.factor(self.last_epoch)
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+    def get_last_lr(self):
+        return [g["lr"] for g in self.opt.param_groups]
+
+    def state_dict(self):
+        return dict(last_epoch=self.last_epoch, warmup=self.warmup, total=self.total)
+
+    def load_state_dict(self, sd):
+        self.last_epoch, self.warmup, self.total = sd["last_epoch"], sd["warmup"], sd["total"]
+        self._apply()
+
+
+def get_last_checkpoint(folder: str) -> Optional[str]:
+    """utils/lora_utils.py:31-47: highest checkpoint-N, None when a `completed` marker exists or nothing is there."""
+    if not os.path.isdir(folder):
+        return None
+    if os.path.exists(os.path.join(folder, "completed")):
+        return None
+    best, best_step = None, -1
+    for name in os.listdir(folder):
+        m = re.fullmatch(r"checkpoint-(\d+)", name)
+        if m and os.path.isdir(os.path.join(folder, name)) and int(m.group(1)) > best_step:
+            best, best_step = os.path.join(folder, name), int(m.group(1))
+    return best
+
+
+def save_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], output_dir: str, step,
+                    is_main_process: bool = True):
+    """DPOTrainer.save_model (dpo_trainer.py:837-899): rank 0 writes the policy adapter in PEFT layout plus optimizer.pt and
+    scheduler.pt, then older optimizer.pt files are removed."""
+    if not is_main_process:
+        return None
+    ckpt = os.path.join(output_dir, f"checkpoint-{step}")
+    model.save_adapter(os.path.join(ckpt, "adapter_model"), "lora_policy")
+    torch.save(optimizer.state_dict(), os.path.join(ckpt, "optimizer.pt"))
+    if scheduler is not None:
+        torch.save(scheduler.state_dict(), os.path.join(ckpt, "scheduler.pt"))
+    for name in os.listdir(output_dir):
+        other = os.path.join(output_dir, name, "optimizer.pt")
+        if name.startswith("checkpoint-") and name != f"checkpoint-{step}" and os.path.exists(other):
+            os.remove(other)
+    return ckpt
+
+
+def load_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], ckpt: str) -> int:
+    """DPOTrainer.resume_training (dpo_trainer.py:901-931): adapter from <ckpt>/adapter_model/lora_policy, optimizer and
+    scheduler state, step counter parsed from the directory name."""
+    state = torch.load(os.path.join(ckpt, "adapter_model", "lora_policy", "adapter_model.bin"), map_location="cpu")
+    model.load_adapter_state("lora_policy", state)
+    opt_path = os.path.join(ckpt, "optimizer.pt")
+    if os.path.exists(opt_path):
+        optimizer.load_state_dict(torch.load(opt_path, map_location="cpu", weights_only=False))
+    sch_path = os.path.join(ckpt, "scheduler.pt")
+    if scheduler is not None and os.path.exists(sch_path):
+        scheduler.load_state_dict(torch.load(sch_path, map_location="cpu", weights_only=False))
+    m = re.search(r"checkpoint-(\d+)", os.path.basename(ckpt.rstrip("/")))
+    return int(m.group(1)) if m else 0

@@ -169,15 +169,18 @@ class B200LlavaModel(nn.Module):
                  top_k: int = 0, temperature: float = 1.0, num_return_sequences: int = 1, synced_gpus: bool = False,
                  **_unused) -> Tensor:
         """model.generate surface used by online_generator.py:292-310 and rl_models.py:166-188 -> LongTensor
-        [b, Q + max_new_tokens] (finished rows padded). `synced_gpus` is ignored: ranks decode independently."""
-        if do_sample:
-            raise NotImplementedError("sampling rollout (top-k/top-p) is a later row of the scope table; greedy only")
+        [b, Q + max_new_tokens] (finished rows padded). `synced_gpus` is ignored: ranks decode independently.
+        Greedy ids reproduce the reference exactly; sampling follows HF's warper order with a counter-based RNG seeded from
+        torch.initial_seed() (same distribution, not the same random stream as torch.multinomial)."""
         if suppress_tokens:
-            raise NotImplementedError("suppress_tokens is not supported by the greedy rollout kernel")
+            raise NotImplementedError("suppress_tokens is not supported by the rollout kernels")
         if num_return_sequences != 1:
             raise NotImplementedError("num_return_sequences > 1")
+        self._gen_calls = getattr(self, "_gen_calls", 0) + 1
+        seed = (int(torch.initial_seed()) * 1000003 + self._gen_calls) & (2 ** 63 - 1)
         aid = ADAPTER_IDS[self.active_adapter]
-        return self.engine.generate(aid, images, inputs, attention_mask, max_new_tokens)
+        return self.engine.generate(aid, images, inputs, attention_mask, max_new_tokens, do_sample=do_sample, top_k=top_k,
+                                    top_p=top_p, temperature=temperature, seed=seed)
 
 
 def eng_trainable(model: B200LlavaModel) -> int:
@@ -231,12 +234,14 @@ class AutoregressivePolicy(Policy):
         return out
 
     def _respond(self, queries, query_attn_masks, images=None, temperature=None, num_return_sequences=1):
-        """rl_models.py:146-191 — greedy here (the reference samples with top_k=0/top_p=1; see generate())."""
+        """rl_models.py:146-191: sampling with top_k=0 / top_p=1 at `temperature`."""
         if self.adapter_name is not None:
             self.base_model.set_adapter(self.adapter_name)
         self.base_model.config.use_cache = True
-        seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=False,
-                                       max_new_tokens=self.args.response_len,
+        if temperature is None:
+            temperature = self.args.temperature
+        seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=True,
+                                       max_new_tokens=self.args.response_len, top_p=1.0, top_k=0, temperature=temperature,
                                        pad_token_id=self.base_tokenizer.pad_token_id)
         return dict(responses=seq[:, queries.size(1):])
 

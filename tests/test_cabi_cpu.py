@@ -54,7 +54,8 @@ def test_struct_layouts_match_header_field_order():
         return names
 
     for struct, cls in (("opadpo_gemm_desc", _lib.GemmDesc), ("opadpo_attn_desc", _lib.AttnDesc),
-                        ("opadpo_dpo_pair_desc", _lib.DpoPairDesc), ("opadpo_config", _lib.Config)):
+                        ("opadpo_dpo_pair_desc", _lib.DpoPairDesc), ("opadpo_config", _lib.Config),
+                        ("opadpo_sampler", _lib.Sampler)):
         assert fields(struct) == [f[0] for f in cls._fields_], struct
 
 
@@ -100,3 +101,27 @@ def test_flop_model_matches_baseline_table():
     assert abs(flops_per_pair(EngineConfig(), 128, 512)["per_pair"] / 1e12 - 113.3) < 0.1
     assert abs(flops_per_pair(EngineConfig(), 128, 128)["per_pair"] / 1e12 - 77.1) < 0.1
     assert abs(flops_per_pair(EngineConfig.llava_13b(), 128, 1024)["per_pair"] / 1e12 - 305.9) < 0.1
+
+
+def test_cosine_schedule_matches_hf_and_last_checkpoint(tmp_path):
+    """create_scheduler (utils/trainer_utils.py:41-49) == HF cosine with warm-up; get_last_checkpoint (lora_utils.py:31-47)."""
+    from transformers.optimization import get_cosine_schedule_with_warmup
+    from opa_dpo_b200.optim import cosine_schedule, get_last_checkpoint
+
+    class FakeOpt:
+        param_groups = [dict(lr=1e-6, initial_lr=1e-6)]
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-6)
+    hf = get_cosine_schedule_with_warmup(opt, 5, 120)
+    mine = cosine_schedule(FakeOpt(), 5, 120)
+    for _ in range(120):
+        assert abs(hf.get_last_lr()[0] - mine.get_last_lr()[0]) < 1e-18
+        opt.step(); hf.step(); mine.step()
+    assert get_last_checkpoint(str(tmp_path)) is None
+    for n in (5, 40, 100):
+        (tmp_path / f"checkpoint-{n}").mkdir()
+    (tmp_path / "checkpoint-final").mkdir()
+    assert get_last_checkpoint(str(tmp_path)).endswith("checkpoint-100")
+    (tmp_path / "completed").write_text("")
+    assert get_last_checkpoint(str(tmp_path)) is None

@@ -266,3 +266,135 @@ def test_dpo_pair_kernel_vs_oracle(div, ls, anchor):
     assert (bb.grad.cpu() - prg.grad).abs().max().item() <= 1e-6
     assert abs(out[2].item() - O.masked_mean(cr, rc != 0).item()) <= 1e-5
     assert abs(out[3].item() - O.masked_mean(rj, rr != 0).item()) <= 1e-5
+
+
+def _oracle_step_logits(oc, w, lora, images, q, qm, gen):
+    """Oracle logits that predicted every generated token (teacher forcing on the engine's own sample)."""
+    from oracle import llava_oracle as O
+    ids = torch.cat([q, gen], 1)
+    mask = torch.cat([qm.bool(), torch.ones_like(gen, dtype=torch.bool)], 1)
+    with torch.no_grad():
+        logits = O.llava_logits(oc, w, lora, ids, mask, images)
+    T = gen.shape[1]
+    return logits[:, -T - 1:-1]
+
+
+def test_sampling_rollout_topk_topp():
+    """Sampling rollout (online_generate.sh:75-77: top_k/top_p/temperature): top_k=1 degenerates to greedy exactly;
+    every sampled token lies in the oracle's top-k / nucleus support given the same prefix; runs are reproducible per
+    seed and differ across seeds."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=12.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 4, 16, 8, NAMES2, left_pad=3)
+    greedy = eng.generate(POLICY, images, q, qm, 10).cpu()
+    k1 = eng.generate(POLICY, images, q, qm, 10, do_sample=True, top_k=1, top_p=1.0, temperature=0.7, seed=5).cpu()
+    assert torch.equal(greedy, k1)
+    K, P, T = 5, 0.9, 0.8
+    a = eng.generate(POLICY, images, q, qm, 10, do_sample=True, top_k=K, top_p=P, temperature=T, seed=123).cpu()
+    a2 = eng.generate(POLICY, images, q, qm, 10, do_sample=True, top_k=K, top_p=P, temperature=T, seed=123).cpu()
+    b = eng.generate(POLICY, images, q, qm, 10, do_sample=True, top_k=K, top_p=P, temperature=T, seed=124).cpu()
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    gen = a[:, 16:]
+    logits = _oracle_step_logits(oc, w, lp, images, q, qm, gen) / T
+    probs = torch.softmax(logits, -1)
+    finished = torch.zeros(4, dtype=torch.bool)
+    for t in range(gen.shape[1]):
+        for n in range(4):
+            if finished[n]:
+                assert gen[n, t] == oc.pad_id
+                continue
+            order = probs[n, t].argsort(descending=True)
+            rank = int((order == gen[n, t]).nonzero()[0])
+            assert rank < K + 1, f"row {n} step {t}: sampled token has oracle rank {rank} (top_k {K})"
+            topk = probs[n, t][order[:K]]
+            before = (topk / topk.sum())[:rank].sum().item()
+            assert before < P + 0.05, f"row {n} step {t}: nucleus mass before the token {before:.3f} >= top_p"
+            if gen[n, t] == oc.eos_id:
+                finished[n] = True
+    eng.close()
+
+
+def test_sampling_full_multinomial_distribution():
+    """top_k=0, top_p=1 (AutoregressivePolicy._respond, rl_models.py:166-188): empirical first-token distribution over
+    2048 draws vs the oracle's softmax (total variation < 0.08)."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=60.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 1, 16, 8, NAMES2)
+    B = 64
+    imgs, qq, qqm = images.repeat(B, 1, 1, 1), q.repeat(B, 1), qm.repeat(B, 1)
+    counts = torch.zeros(oc.vocab)
+    for seed in range(32):
+        out = eng.generate(POLICY, imgs, qq, qqm, 1, do_sample=True, top_k=0, top_p=1.0, temperature=1.0, seed=seed).cpu()
+        counts += torch.bincount(out[:, 16], minlength=oc.vocab).float()
+    with torch.no_grad():
+        ids = torch.cat([q, torch.full((1, 1), 5)], 1)
+        logits = O.llava_logits(oc, w, lp, ids, torch.cat([qm.bool(), torch.ones(1, 1, dtype=torch.bool)], 1), images)[0, -2]
+    p = torch.softmax(logits, -1)
+    tv = 0.5 * (counts / counts.sum() - p).abs().sum().item()
+    assert tv < 0.08 + 0.5 * (p * (1 - p) / counts.sum()).sqrt().sum().item(), f"total variation {tv:.3f}; max p {p.max().item():.3f}"
+    eng.close()
+
+
+def test_checkpoint_roundtrip_peft_layout(tmp_path):
+    """save_model / resume_training (dpo_trainer.py:837-931): PEFT-layout adapter files, optimizer.pt, scheduler.pt;
+    reload restores LoRA tensors bit-identically (bf16 as the reference stores them), Adam moments, step and LR."""
+    import json, os
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.dpo import DPOArgs, DPOStepper
+    from opa_dpo_b200.optim import B200AdamW, cosine_schedule, get_last_checkpoint, load_checkpoint, save_checkpoint
+    oc, ec = _cfgs()
+
+    def make():
+        model = B200LlavaModel(ec)
+        w = O.init_weights(oc)
+        sd = dict(w)
+        sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+        model.engine.load_state_dict(sd)
+        for name, seed in (("lora_policy", 11), ("lora_ref_policy", 12)):
+            lo = O.init_lora(oc, seed)
+            model.load_adapter_state(name, {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lo.items() for x, t in zip("AB", ab)})
+        model.make_trainable("lora_policy")
+        return model
+
+    model = make()
+    args = DPOArgs(beta=0.1, response_len=24, learning_rate=1e-3)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    pol = AutoregressivePolicy(args, model, tok, "lora_policy")
+    ref = AutoregressivePolicy(args, model, tok, "lora_ref_policy")
+    stepper = DPOStepper(pol, ref, args)
+    opt = B200AdamW(model, lr=1e-3)
+    sch = cosine_schedule(opt, 2, 10)
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, NAMES2, left_pad=2)
+    batch = dict(images=images, queries=q, queries_attn_masks=qm, **resp)
+    for _ in range(2):
+        refs = stepper.reference_logprobs(batch)
+        stepper.pair_loss(batch, refs, NAMES2[0], NAMES2[1])
+        opt.step(); opt.zero_grad(); sch.step()
+    ckpt = save_checkpoint(model, opt, sch, str(tmp_path), 2)
+    d = os.path.join(ckpt, "adapter_model", "lora_policy")
+    cfgj = json.load(open(os.path.join(d, "adapter_config.json")))
+    assert cfgj["r"] == oc.lora_r and cfgj["lora_alpha"] == oc.lora_alpha and cfgj["bias"] == "none" and \
+        cfgj["task_type"] == "CAUSAL_LM" and "q_proj" in cfgj["target_modules"]
+    saved = torch.load(os.path.join(d, "adapter_model.bin"))
+    assert "base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight" in saved
+    assert saved["base_model.model.model.layers.1.mlp.down_proj.lora_B.weight"].shape == (oc.d_model, oc.lora_r)
+    assert os.path.exists(os.path.join(ckpt, "optimizer.pt")) and os.path.exists(os.path.join(ckpt, "scheduler.pt"))
+    assert get_last_checkpoint(str(tmp_path)) == ckpt
+
+    model2 = make()
+    opt2 = B200AdamW(model2, lr=1e-3)
+    sch2 = cosine_schedule(opt2, 2, 10)
+    step = load_checkpoint(model2, opt2, sch2, ckpt)
+    assert step == 2 and opt2.step_count == 2 and sch2.get_last_lr() == sch.get_last_lr()
+    again = model2.adapter_state_dict("lora_policy")
+    for k, v in saved.items():
+        assert torch.equal(again[k], v), k
+    v1, v2 = model.engine.buffers(), model2.engine.buffers()
+    assert torch.equal(v1["exp_avg"], v2["exp_avg"]) and torch.equal(v1["exp_avg_sq"], v2["exp_avg_sq"])
+    model.engine.close(); model2.engine.close()
