@@ -28,6 +28,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -694,35 +698,74 @@ __device__ __forceinline__ float sum_partials(const float* __restrict__ part, in
   return a;
 }
 __global__ void partial_to_bf16_kernel(const float* __restrict__ part, int splits, int64_t n, bf16* __restrict__ out) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16(sum_partials(part, splits, n, i));
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;  // n % 4 == 0 (checked by the launcher)
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < splits; ++sp) {
+    const float4 p = *reinterpret_cast<const float4*>(part + sp * n + i);
+    a.x += p.x;
+    a.y += p.y;
+    a.z += p.z;
+    a.w += p.w;
+  }
+  uint2 o;
+  o.x = pack2(a.x, a.y);
+  o.y = pack2(a.z, a.w);
+  *reinterpret_cast<uint2*>(out + i) = o;
 }
-// x_out = bf16(sum(part) + res);  h = w * bf16(x_out * rstd)   (residual add fused with the next RMSNorm)
-__global__ void __launch_bounds__(NORM_THREADS)
+// x_out = bf16(sum(part) + res);  h = w * bf16(x_out * rstd)   (residual add fused with the next RMSNorm).
+// One 1024-thread CTA per row, 4 (or 8) consecutive columns per thread, all split slices loaded as independent float4s.
+constexpr int PRN_THREADS = 1024;
+template <int VPT>  // float4 vectors per thread
+__global__ void __launch_bounds__(PRN_THREADS)
     partial_residual_rmsnorm_kernel(const float* __restrict__ part, int splits, int64_t slice, const bf16* __restrict__ res,
                                     bf16* __restrict__ x_out, const bf16* __restrict__ w, bf16* __restrict__ h, int d,
                                     float eps) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
-  float v[NORM_MAXV * 8];
+  float v[VPT][4];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV * 8; ++i) {
-    const int c = threadIdx.x + i * NORM_THREADS;
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (threadIdx.x + i * PRN_THREADS) * 4;
+    v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
     if (c < d) {
-      const float x = bf16_round(sum_partials(part, splits, slice, r * d + c) + __bfloat162float(res[r * d + c]));
-      v[i] = x;
-      ss += x * x;
-      x_out[r * d + c] = __float2bfloat16(x);
+      for (int sp = 0; sp < splits; ++sp) {
+        const float4 p = *reinterpret_cast<const float4*>(part + sp * slice + r * d + c);
+        v[i][0] += p.x;
+        v[i][1] += p.y;
+        v[i][2] += p.z;
+        v[i][3] += p.w;
+      }
+      const uint2 rr = *reinterpret_cast<const uint2*>(res + r * d + c);
+      const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+      const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+      v[i][0] = bf16_round(v[i][0] + r01.x);
+      v[i][1] = bf16_round(v[i][1] + r01.y);
+      v[i][2] = bf16_round(v[i][2] + r23.x);
+      v[i][3] = bf16_round(v[i][3] + r23.y);
+      uint2 o;
+      o.x = pack2(v[i][0], v[i][1]);
+      o.y = pack2(v[i][2], v[i][3]);
+      *reinterpret_cast<uint2*>(x_out + r * d + c) = o;
+      ss += v[i][0] * v[i][0] + v[i][1] * v[i][1] + v[i][2] * v[i][2] + v[i][3] * v[i][3];
     }
   }
   ss = block_sum(ss, red);
   const float rstd = rsqrtf(ss / d + eps);
   if (h) {
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV * 8; ++i) {
-      const int c = threadIdx.x + i * NORM_THREADS;
-      if (c < d) h[r * d + c] = __float2bfloat16(__bfloat162float(w[c]) * bf16_round(v[i] * rstd));
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (threadIdx.x + i * PRN_THREADS) * 4;
+      if (c < d) {
+        const uint2 ww = *reinterpret_cast<const uint2*>(w + c);
+        const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww.x));
+        const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww.y));
+        uint2 o;
+        o.x = pack2(w01.x * bf16_round(v[i][0] * rstd), w01.y * bf16_round(v[i][1] * rstd));
+        o.y = pack2(w23.x * bf16_round(v[i][2] * rstd), w23.y * bf16_round(v[i][3] * rstd));
+        *reinterpret_cast<uint2*>(h + r * d + c) = o;
+      }
     }
   }
 }
@@ -1255,13 +1298,17 @@ int advance_counter(int32_t* cur, cudaStream_t s) {
   return check_launch("advance_counter");
 }
 int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s) {
-  partial_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, s>>>(part, splits, n, out);
+  if (n % 4 != 0) return -1;
+  partial_to_bf16_kernel<<<blocks_for(n / 4, 128), 128, 0, s>>>(part, splits, n, out);
   return check_launch("partial_to_bf16");
 }
 int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
                              int d, float eps, cudaStream_t s) {
-  if (d > 8 * NORM_THREADS * NORM_MAXV) return -1;
-  partial_residual_rmsnorm_kernel<<<static_cast<unsigned>(M), NORM_THREADS, 0, s>>>(part, splits, M * d, res, x_out, w, h, d, eps);
+  if (d % 4 != 0 || d > 4 * PRN_THREADS * 2) return -1;
+  if (d <= 4 * PRN_THREADS)
+    partial_residual_rmsnorm_kernel<1><<<static_cast<unsigned>(M), PRN_THREADS, 0, s>>>(part, splits, M * d, res, x_out, w, h, d, eps);
+  else
+    partial_residual_rmsnorm_kernel<2><<<static_cast<unsigned>(M), PRN_THREADS, 0, s>>>(part, splits, M * d, res, x_out, w, h, d, eps);
   return check_launch("partial_residual_rmsnorm");
 }
 int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s) {

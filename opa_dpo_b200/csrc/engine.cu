@@ -1189,13 +1189,21 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   cudaMemsetAsync(cur, 0, sizeof(int32_t), s);
 
   const bool lora = adapter >= 0 && r > 0;
+  // K-split count: every SM should stream weights. cost = waves of CTAs x k-blocks per split.
   auto splits_for = [&](int n_out, int K1, int K2) {
     const int tiles = ((N + 127) / 128) * ((n_out + 255) / 256);
     const int kb = (K1 + 63) / 64 + (K2 + 63) / 64;
-    int sp = (2 * 148 + tiles - 1) / tiles;
-    sp = std::min(sp, std::max(1, kb / 2));
-    sp = std::min(sp, kMaxSplits);
-    return gemm_effective_splits(K1, K2, std::max(sp, 1));
+    int best = 1;
+    long best_cost = 1L << 60;
+    for (int sp = 1; sp <= kMaxSplits && sp <= kb; ++sp) {
+      const long waves = (static_cast<long>(tiles) * sp + 147) / 148;
+      const long cost = waves * ((kb + sp - 1) / sp) * 16 + sp;  // small bias towards fewer slices to reduce
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = sp;
+      }
+    }
+    return gemm_effective_splits(K1, K2, best);
   };
   // partial sums of y = x W^T + (s x A^T) B^T into `part` [splits, N, out]; returns the split count
   auto linear_partial = [&](const LinearW& L, const bf16* x, int max_sp, int* nsplit) -> int {
