@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=8, help="preference pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="7b", choices=["7b", "13b"], help="7b = BASELINE configs[1] (headline); 13b = configs[4] shape")
+    ap.add_argument("--resp-len", type=int, default=R_LEN)
+    ap.add_argument("--no-share-prefix", action="store_true", help="run the reference's K stacked rows (no prefix sharing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -192,11 +195,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = EngineConfig()
+    cfg = EngineConfig() if args.model == "7b" else EngineConfig.llava_13b()
+    R = args.resp_len
     model = B200LlavaModel(cfg, dev)
+    if args.no_share_prefix:
+        model.engine.set_option("share_prefix", 0)
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
-    dargs = DPOArgs(beta=0.1, response_len=R_LEN, learning_rate=1e-6, max_grad_norm=1.0)
+    dargs = DPOArgs(beta=0.1, response_len=R, learning_rate=1e-6, max_grad_norm=1.0)
     tok = SimpleNamespace(pad_token_id=cfg.pad_id, eos_token_id=cfg.eos_id)
     policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_policy")
     ref_policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_ref_policy")
@@ -211,7 +217,7 @@ def main():
     h_qmask = torch.ones(b, Q_LEN, dtype=torch.uint8).pin_memory()
     h_resp = {}
     for n in ("chosen_response", "rejected_response"):
-        t = torch.randint(3, cfg.vocab, (b, R_LEN), generator=g)
+        t = torch.randint(3, cfg.vocab, (b, R), generator=g)
         t[:, -1] = cfg.eos_id
         h_resp[n] = t.pin_memory()
     h2d_bytes = h_images.numel() * 4 + h_queries.numel() * 8 + h_qmask.numel() + sum(t.numel() * 8 for t in h_resp.values())
@@ -281,17 +287,26 @@ def main():
     pairs_per_step = b * world
     value = pairs_per_step / (ms_step / 1e3)
     e2e_value = pairs_per_step / (ms_e2e / args.steps / 1e3)
-    fl = flops_per_pair(cfg, Q_LEN, R_LEN)
+    fl = flops_per_pair(cfg, Q_LEN, R)
     peaks = _peaks()
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_fwd_layer.json")
+    if args.model == "7b" and os.path.exists(prof):
+        try:  # dram bytes of the dominant launch (fused gate|up forward GEMM) from the committed ncu --set full capture
+            with open(prof) as f:
+                traffic = json.load(f).get("dominant_launch_dram_bytes")
+        except Exception:
+            traffic = None
     gemm_tflops = gf.value / (gm.value * 1e-3) / 1e12 if gm.value > 0 else None
     step_tflops = fl["per_pair"] * b / (ms_step * 1e-3) / 1e12   # per GPU, algorithmic
     line = {
         "metric": "preference-pairs/sec LLaVA-1.5-7B OPA-DPO", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "LLaVA-1.5-7B LoRA(r=256, all Linear but lm_head) OPA-DPO step, 336^2 img, Q=128, R=512, "
-                               "4 forwards (policy+frozen ref x chosen+rejected) + LoRA backward + clip + AdamW",
-                   "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R_LEN,
+        "config": {"workload": f"LLaVA-1.5-{args.model.upper()} LoRA(r=256, all Linear but lm_head) OPA-DPO step, 336^2 img, Q=128, "
+                               f"R={R}, 4 forwards (policy+frozen ref x chosen+rejected) + LoRA backward + clip + AdamW",
+                   "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
+                   "prefix_sharing": (not args.no_share_prefix),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
                    "collective": "one NCCL all-reduce(sum) of the fp32 LoRA-grad bucket per step" if world > 1 else "none",
                    "loss": float(loss.item()), "grad_norm": float(norm.item())},
@@ -299,11 +314,14 @@ def main():
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_host},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None, "traffic": None,
+                     "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None, "traffic": traffic,
+                     "traffic_note": "dram read+write bytes of ONE dominant launch (gate|up forward GEMM, M=13816 N=22016 K=4096+256; "
+                                     "algorithmic 0.92 GB) from profiles/r01_ncu_full_gemm_fwd_layer.json",
                      "kernel": "opadpo::gemm_kernel (tcgen05 128x256x64, all epilogues)", "peak_source": peaks["source"] + " sustained",
                      "gemm_launches_per_step": int(gl.value), "gemm_ms_per_step": gm.value,
                      "gemm_share_of_step": gm.value / ms_step,
                      "step_algorithmic_tflops_per_gpu": step_tflops,
+                     "step_executed_gemm_tflop": gf.value / 1e12,
                      "step_frac_of_burst_peak": step_tflops / peaks["burst"],
                      "step_frac_of_sustained_peak": step_tflops / peaks["sustained"],
                      "tflop_per_pair": fl["per_pair"] / 1e12},
