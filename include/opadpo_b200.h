@@ -53,7 +53,7 @@ typedef struct opadpo_gemm_desc {
   float alpha;
   void* C; int64_t ldc;           /* bf16 (EPI_BF16/CEGRAD) or f32 (EPI_F32_ATOMIC) */
   const void* bias;               /* bf16 [N] or NULL */
-  const void* residual; int64_t ldr; /* bf16 (fp32 if residual_f32) [M, ldr] or NULL */
+  const void* residual; int64_t ldr; /* bf16 [M, ldr] or NULL */
   int32_t act;                    /* OPADPO_ACT_* */
   const int32_t* labels;          /* EPI_LSE / EPI_CEGRAD: [M], negative = ignore */
   void* lse_partials;             /* EPI_LSE: float4 [M, opadpo_gemm_n_tiles(N)] */
@@ -61,7 +61,6 @@ typedef struct opadpo_gemm_desc {
   const float* lse;               /* EPI_CEGRAD: [M] */
   const float* dlp;               /* EPI_CEGRAD: [M] */
   int32_t max_ctas;               /* 0 = one CTA per SM */
-  int32_t residual_f32, out_f32;  /* EPI_BF16: residual is fp32 / store C as fp32 (fp32 residual stream of the decoder) */
 } opadpo_gemm_desc;
 
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);

@@ -52,7 +52,6 @@ class GemmDesc(ctypes.Structure):
         ("lse", ctypes.c_void_p),
         ("dlp", ctypes.c_void_p),
         ("max_ctas", ctypes.c_int32),
-        ("residual_f32", ctypes.c_int32), ("out_f32", ctypes.c_int32),
     ]
 
 

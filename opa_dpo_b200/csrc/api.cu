@@ -54,9 +54,7 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
   a.C = d->C;
   a.ldc = d->ldc;
   a.bias = static_cast<const __nv_bfloat16*>(d->bias);
-  a.residual = d->residual;
-  a.residual_f32 = d->residual_f32 != 0;
-  a.out_f32 = d->out_f32 != 0;
+  a.residual = static_cast<const __nv_bfloat16*>(d->residual);
   a.ldr = d->ldr;
   a.act = d->act;
   a.labels = d->labels;

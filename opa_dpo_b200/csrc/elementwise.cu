@@ -57,99 +57,98 @@ constexpr int NORM_THREADS = 256;
 constexpr int NORM_MAXV = 4;  // up to 8192 columns held in registers
 
 // ---------------------------------------------------------------------------------------------- RMSNorm
-// The decoder's residual stream x is kept in fp32 (the GEMM epilogues add into it in fp32), so its rounding error does
-// not accumulate over 32 layers; the normed activations that feed the GEMMs are bf16.
-constexpr int NORM_F4 = 8;  // float4 vectors per thread: up to 8192 columns in registers
-__device__ __forceinline__ float4 ldw4(const bf16* w, int v) {
-  const uint2 u = __ldg(reinterpret_cast<const uint2*>(w) + v);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ float4 ldb4(const bf16* p, int v) {
-  const uint2 u = *(reinterpret_cast<const uint2*>(p) + v);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void stb4(bf16* p, int v, float a, float b, float c, float d) {
-  uint2 o;
-  o.x = pack2(a, b);
-  o.y = pack2(c, d);
-  *(reinterpret_cast<uint2*>(p) + v) = o;
-}
-
-__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ w,
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                     bf16* __restrict__ y, int d, float eps,
                                                                     const int32_t* __restrict__ x_idx) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
-  const float4* xr = reinterpret_cast<const float4*>(x + map_row(r, x_idx) * d);
-  const int nv = d >> 2;
-  float4 xv[NORM_F4];
+  const uint4* xr = reinterpret_cast<const uint4*>(x + map_row(r, x_idx) * d);
+  const int nv = d >> 3;
+  uint4 xv[NORM_MAXV];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_F4; ++i) {
+  for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
       xv[i] = xr[v];
-      ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      float f[8];
+      unpack8(xv[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
     }
   }
   ss = block_sum(ss, red);
   const float rstd = rsqrtf(ss / d + eps);
-  bf16* yr = y + r * d;
+  uint4* yr = reinterpret_cast<uint4*>(y + r * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
 #pragma unroll
-  for (int i = 0; i < NORM_F4; ++i) {
+  for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
-      const float4 g = ldw4(w, v);
-      stb4(yr, v, g.x * bf16_round(xv[i].x * rstd), g.y * bf16_round(xv[i].y * rstd), g.z * bf16_round(xv[i].z * rstd),
-           g.w * bf16_round(xv[i].w * rstd));
+      float f[8], g[8];
+      unpack8(xv[i], f);
+      unpack8(__ldg(wr + v), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = g[e] * bf16_round(f[e] * rstd);
+      yr[v] = pack8(f);
     }
   }
 }
 
 __global__ void __launch_bounds__(NORM_THREADS)
-    rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const bf16* __restrict__ w, const bf16* dres,
-                       bf16* dx, int d, float eps, const int32_t* __restrict__ x_idx, const int32_t* __restrict__ dx_idx) {
+    rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                       const bf16* dres, bf16* dx, int d, float eps, const int32_t* __restrict__ x_idx,
+                       const int32_t* __restrict__ dx_idx) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
   const int64_t xrw = map_row(r, x_idx);
   const int64_t fr = map_row(r, dx_idx);
-  const float4* xr = reinterpret_cast<const float4*>(x + xrw * d);
-  const bf16* dyr = dy + r * d;
-  const int nv = d >> 2;
-  float4 xv[NORM_F4], gv[NORM_F4];  // gv = w * dy
+  const uint4* xr = reinterpret_cast<const uint4*>(x + xrw * d);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const int nv = d >> 3;
+  uint4 xv[NORM_MAXV], gv[NORM_MAXV];  // gv = w*dy packed as bf16 is lossy; keep dy and re-multiply
   float ss = 0.f, dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_F4; ++i) {
+  for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
       xv[i] = xr[v];
-      const float4 g = ldb4(dyr, v);
-      const float4 ww = ldw4(w, v);
-      gv[i] = make_float4(ww.x * g.x, ww.y * g.y, ww.z * g.z, ww.w * g.w);
-      ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
-      dot += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+      gv[i] = dyr[v];
+      float f[8], g[8], ww[8];
+      unpack8(xv[i], f);
+      unpack8(gv[i], g);
+      unpack8(__ldg(wr + v), ww);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ss += f[e] * f[e];
+        dot += ww[e] * g[e] * f[e];
+      }
     }
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
   const float rstd = rsqrtf(ss / d + eps);
   const float c = dot / d * rstd * rstd * rstd;
-  bf16* dxr = dx + fr * d;
-  const bf16* drr = dres ? dres + fr * d : nullptr;
+  uint4* dxr = reinterpret_cast<uint4*>(dx + fr * d);
+  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + fr * d) : nullptr;
 #pragma unroll
-  for (int i = 0; i < NORM_F4; ++i) {
+  for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
-      float4 o = drr ? ldb4(drr, v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x += rstd * gv[i].x - xv[i].x * c;
-      o.y += rstd * gv[i].y - xv[i].y * c;
-      o.z += rstd * gv[i].z - xv[i].z * c;
-      o.w += rstd * gv[i].w - xv[i].w * c;
-      stb4(dxr, v, o.x, o.y, o.z, o.w);
+      float f[8], g[8], ww[8], o[8];
+      unpack8(xv[i], f);
+      unpack8(gv[i], g);
+      unpack8(__ldg(wr + v), ww);
+      if (drr) {
+        unpack8(drr[v], o);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += rstd * ww[e] * g[e] - f[e] * c;
+      dxr[v] = pack8(o);
     }
   }
 }
@@ -326,7 +325,7 @@ __global__ void find_image_pos_kernel(const int32_t* __restrict__ ids, int32_t* 
 
 __global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const uint8_t* __restrict__ tok_mask,
                                     const uint8_t* __restrict__ img_mask, const int32_t* __restrict__ img_of_row,
-                                    const bf16* __restrict__ table, const bf16* __restrict__ feats, float* __restrict__ out,
+                                    const bf16* __restrict__ table, const bf16* __restrict__ feats, bf16* __restrict__ out,
                                     uint8_t* __restrict__ out_mask, const int32_t* __restrict__ img_pos, int L, int P,
                                     int d, int vocab) {
   const int S = L - 1 + P;
@@ -346,13 +345,8 @@ __global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const uint8
     src = reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d);
     m = tok_mask[static_cast<int64_t>(n) * L + l];
   }
-  float4* dst = reinterpret_cast<float4*>(out + row * d);
-  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
-    float f[8];
-    unpack8(__ldg(src + v), f);
-    dst[2 * v] = make_float4(f[0], f[1], f[2], f[3]);
-    dst[2 * v + 1] = make_float4(f[4], f[5], f[6], f[7]);
-  }
+  uint4* dst = reinterpret_cast<uint4*>(out + row * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) dst[v] = __ldg(src + v);
   if (threadIdx.x == 0 && out_mask) out_mask[row] = m;
 }
 
@@ -376,18 +370,13 @@ __global__ void embed_splice_bwd_kernel(const bf16* __restrict__ dX, const int32
   }
 }
 
-__global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table, float* __restrict__ out,
+__global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table, bf16* __restrict__ out,
                                   int d, int vocab) {
   const int r = blockIdx.x;
   const int id = min(max(ids[r], 0), vocab - 1);
   const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d);
-  float4* dst = reinterpret_cast<float4*>(out + static_cast<int64_t>(r) * d);
-  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
-    float f[8];
-    unpack8(__ldg(src + v), f);
-    dst[2 * v] = make_float4(f[0], f[1], f[2], f[3]);
-    dst[2 * v + 1] = make_float4(f[4], f[5], f[6], f[7]);
-  }
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * d);
+  for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) dst[v] = __ldg(src + v);
 }
 
 // ---------------------------------------------------------------------------------------------- CLIP front end
@@ -729,8 +718,8 @@ __global__ void partial_to_bf16_kernel(const float* __restrict__ part, int split
 constexpr int PRN_THREADS = 1024;
 template <int VPT>  // float4 vectors per thread
 __global__ void __launch_bounds__(PRN_THREADS)
-    partial_residual_rmsnorm_kernel(const float* __restrict__ part, int splits, int64_t slice, const float* __restrict__ res,
-                                    float* __restrict__ x_out, const bf16* __restrict__ w, bf16* __restrict__ h, int d,
+    partial_residual_rmsnorm_kernel(const float* __restrict__ part, int splits, int64_t slice, const bf16* __restrict__ res,
+                                    bf16* __restrict__ x_out, const bf16* __restrict__ w, bf16* __restrict__ h, int d,
                                     float eps) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
@@ -748,12 +737,17 @@ __global__ void __launch_bounds__(PRN_THREADS)
         v[i][2] += p.z;
         v[i][3] += p.w;
       }
-      const float4 rr = *reinterpret_cast<const float4*>(res + r * d + c);
-      v[i][0] += rr.x;
-      v[i][1] += rr.y;
-      v[i][2] += rr.z;
-      v[i][3] += rr.w;
-      *reinterpret_cast<float4*>(x_out + r * d + c) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      const uint2 rr = *reinterpret_cast<const uint2*>(res + r * d + c);
+      const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+      const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+      v[i][0] = bf16_round(v[i][0] + r01.x);
+      v[i][1] = bf16_round(v[i][1] + r01.y);
+      v[i][2] = bf16_round(v[i][2] + r23.x);
+      v[i][3] = bf16_round(v[i][3] + r23.y);
+      uint2 o;
+      o.x = pack2(v[i][0], v[i][1]);
+      o.y = pack2(v[i][2], v[i][3]);
+      *reinterpret_cast<uint2*>(x_out + r * d + c) = o;
       ss += v[i][0] * v[i][0] + v[i][1] * v[i][1] + v[i][2] * v[i][2] + v[i][3] * v[i][3];
     }
   }
@@ -1109,15 +1103,15 @@ inline unsigned capped_blocks(int64_t n, int threads, int cap) {
 
 }  // namespace
 
-int rmsnorm_fwd(const float* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s) {
-  if (d % 8 != 0 || d > 4 * NORM_THREADS * NORM_F4) return -1;
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s) {
+  if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
   if (rows == 0) return 0;
   rmsnorm_fwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(x, w, y, d, eps, x_idx);
   return check_launch("rmsnorm_fwd");
 }
-int rmsnorm_bwd(const bf16* dy, const float* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
+int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
                 const int32_t* x_idx, const int32_t* dx_idx, cudaStream_t s) {
-  if (d % 8 != 0 || d > 4 * NORM_THREADS * NORM_F4) return -1;
+  if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
   if (rows == 0) return 0;
   rmsnorm_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
   return check_launch("rmsnorm_bwd");
@@ -1162,7 +1156,7 @@ int gelu_bwd(const bf16* dy, const bf16* x, bf16* dx, int64_t n, cudaStream_t s)
   return check_launch("gelu_bwd");
 }
 int embed_splice(const int32_t* ids, const uint8_t* tok_mask, const uint8_t* img_mask, const int32_t* img_of_row,
-                 const bf16* table, const bf16* feats, float* out, uint8_t* out_mask, int32_t* img_pos, int N, int L, int P,
+                 const bf16* table, const bf16* feats, bf16* out, uint8_t* out_mask, int32_t* img_pos, int N, int L, int P,
                  int d, int vocab, cudaStream_t s) {
   if (d % 8 != 0) return -1;
   find_image_pos_kernel<<<N, 32, 0, s>>>(ids, img_pos, N, L, -200);
@@ -1177,7 +1171,7 @@ int embed_splice_bwd(const bf16* dX, const int32_t* img_of_row, const int32_t* i
                                                                                                  dfeats, N, S, P, d);
   return check_launch("embed_splice_bwd");
 }
-int embed_rows(const int32_t* ids, const bf16* table, float* out, int rows, int d, int vocab, cudaStream_t s) {
+int embed_rows(const int32_t* ids, const bf16* table, bf16* out, int rows, int d, int vocab, cudaStream_t s) {
   embed_rows_kernel<<<rows, 128, 0, s>>>(ids, table, out, d, vocab);
   return check_launch("embed_rows");
 }
@@ -1308,7 +1302,7 @@ int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStr
   partial_to_bf16_kernel<<<blocks_for(n / 4, 128), 128, 0, s>>>(part, splits, n, out);
   return check_launch("partial_to_bf16");
 }
-int partial_residual_rmsnorm(const float* part, int splits, const float* res, float* x_out, const bf16* w, bf16* h, int64_t M,
+int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
                              int d, float eps, cudaStream_t s) {
   if (d % 4 != 0 || d > 4 * PRN_THREADS * 2) return -1;
   if (d <= 4 * PRN_THREADS)

@@ -10,13 +10,12 @@ namespace opadpo {
 
 using bf16 = __nv_bfloat16;
 
-// The decoder's residual stream x is fp32 (its bf16 rounding error would accumulate over the layers).
 // y[r] = w * bf16(x[x_idx[r]] * rsqrt(mean(x^2) + eps))   [UPSTREAM HF LlamaRMSNorm]. x_idx (nullable = identity) lets the
 // final norm run only on the R response-predicting rows of each sequence (rl_models.py:120-121 slices logits[:, -R-1:-1]).
-int rmsnorm_fwd(const float* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s);
+int rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, int64_t rows, int d, float eps, const int32_t* x_idx, cudaStream_t s);
 // dx[dx_idx[r]] = (dres ? dres[dx_idx[r]] : 0) + rstd*(w*dy[r]) - x*rstd^3*mean(w*dy*x) with x = x[x_idx[r]]
 // (norm weight is frozen: no dw). rstd is recomputed from x. dx may alias dres.
-int rmsnorm_bwd(const bf16* dy, const float* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
+int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, bf16* dx, int64_t rows, int d, float eps,
                 const int32_t* x_idx, const int32_t* dx_idx, cudaStream_t s);
 // y = (x - mean) * rsqrt(var + eps) * w + b   [UPSTREAM CLIP LayerNorm]
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s);
@@ -40,13 +39,13 @@ int gelu_bwd(const bf16* dy, const bf16* x, bf16* dx, int64_t n, cudaStream_t s)
 // img_mask [n_img, P] if given, else 1) and records the image slot start img_pos[n]
 // (llava_modifications.patch:14618-14706).
 int embed_splice(const int32_t* ids, const uint8_t* tok_mask, const uint8_t* img_mask, const int32_t* img_of_row,
-                 const bf16* table, const bf16* feats, float* out, uint8_t* out_mask, int32_t* img_pos, int N, int L,
+                 const bf16* table, const bf16* feats, bf16* out, uint8_t* out_mask, int32_t* img_pos, int N, int L,
                  int P, int d, int vocab, cudaStream_t s);
 // dfeats[img, p, :] = sum over rows n with img_of_row[n]==img of dX[n, img_pos[n]+p, :]
 int embed_splice_bwd(const bf16* dX, const int32_t* img_of_row, const int32_t* img_pos, bf16* dfeats, int N, int S,
                      int n_img, int P, int d, cudaStream_t s);
 // out[r, :] = table[ids[r], :]   (decode-time embedding)
-int embed_rows(const int32_t* ids, const bf16* table, float* out, int rows, int d, int vocab, cudaStream_t s);
+int embed_rows(const int32_t* ids, const bf16* table, bf16* out, int rows, int d, int vocab, cudaStream_t s);
 
 // CLIP: images [n, 3, R, R] (f32) -> patch matrix [n*P, Kp] bf16 (Kp = padded 3*ps*ps), then token assembly.
 int clip_im2col(const float* images, bf16* patches, int n, int R, int ps, int Kp, cudaStream_t s);
@@ -125,7 +124,7 @@ int sample_pick(const float* partials, int splits, int N, int V, int top_k, floa
 int advance_counter(int32_t* cur, cudaStream_t s);
 // Deterministic reductions of gemm EPI_F32_PARTIAL slices [splits, M, N] fused with the op that follows the linear.
 int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s);
-int partial_residual_rmsnorm(const float* part, int splits, const float* res, float* x_out, const bf16* w, bf16* h, int64_t M,
+int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
                              int d, float eps, cudaStream_t s);
 int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s);
 

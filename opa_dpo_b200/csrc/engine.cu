@@ -469,9 +469,8 @@ void Engine::release_slot(int slot, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ linear layers
 // y = act(x W^T + bias + s*(x A^T) B^T) + residual. The LoRA-A product t = s*x*A^T is a skinny pre-GEMM whose
 // output is consumed as a second K segment of the base GEMM ([x | t] [W ; B]^T into one TMEM accumulator).
-int Engine::linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, void* y, int64_t ldy,
-                       int act, const void* residual, int64_t ldr, cudaStream_t s, bool stream_f32) {
-  const int64_t esz = stream_f32 ? 4 : 2;  // element size of y / residual
+int Engine::linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy,
+                       int act, const bf16* residual, int64_t ldr, cudaStream_t s) {
   const bool lora = adapter >= 0 && L.slot >= 0 && r > 0;
   const int G = L.groups, out_g = L.out / G;
   if (lora) {
@@ -504,15 +503,13 @@ int Engine::linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
         a.a2_group_stride = r;
       }
     }
-    a.C = static_cast<char*>(y) + static_cast<int64_t>(g) * out_g * esz;
+    a.C = y + static_cast<int64_t>(g) * out_g;
     a.ldc = ldy;
-    a.out_f32 = stream_f32;
     a.bias = L.bias ? L.bias + static_cast<int64_t>(g) * out_g : nullptr;
     a.act = act;
     if (residual) {
-      a.residual = static_cast<const char*>(residual) + static_cast<int64_t>(g) * out_g * esz;
+      a.residual = residual + static_cast<int64_t>(g) * out_g;
       a.ldr = ldr;
-      a.residual_f32 = stream_f32;
     }
     EN_CHECK(gemm_checked(a, s));
   }
@@ -679,7 +676,7 @@ int Engine::projector_forward(int adapter, const bf16* clip_feats, int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------ LLaMA layer
-int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, float* x_out, bf16* h, bf16* act,
+int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
                             cudaStream_t s) {
   const int64_t T = static_cast<int64_t>(lay.N) * lay.S;
   const int N = lay.N, S = lay.S;
@@ -707,11 +704,11 @@ int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const Laye
   at.prefix_len = lay.S0;
   at.segment_len = lay.segR;
   EN_CHECK(attn_fwd_checked(at, s));
-  EN_CHECK(linear_fwd(L.o, adapter, a.o, d, T, a.to, a.x1, d, ACT_NONE, a.x, d, s, true));
+  EN_CHECK(linear_fwd(L.o, adapter, a.o, d, T, a.to, a.x1, d, ACT_NONE, a.x, d, s));
   EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, nullptr, s));
   EN_CHECK(linear_fwd(L.gu, adapter, h, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
   EN_CHECK(swiglu_fwd(a.gu, act, T, F, s));
-  EN_CHECK(linear_fwd(L.down, adapter, act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s, true));
+  EN_CHECK(linear_fwd(L.down, adapter, act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s));
   return 0;
 }
 
@@ -797,8 +794,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   EN_CHECK(projector_forward(adapter, clip_feats, PR, p_pre, p_act, t_p0, t_p2, feats, s));
 
   // embedding gather + image splice
-  float *x0, *x1buf = nullptr;
-  bf16 *h, *act;
+  bf16 *x0, *x1buf = nullptr, *h, *act;
   EN_CHECK(pool_alloc(&x0, T * d, s, keep));
   EN_CHECK(embed_splice(ids, tokmask, img_mask, img_of_row, embed, feats, x0, mask, img_pos, N, L, P, d, c.vocab, s));
   uint64_t* kbits;
@@ -815,7 +811,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   lay.pos = pos;
   lay.kbits = kbits;
 
-  float* x_final = nullptr;
+  bf16* x_final = nullptr;
   if (save) {
     cx->layers.resize(c.n_layers);
     for (int l = 0; l < c.n_layers; ++l) {
@@ -828,19 +824,19 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
       x_final = x0;
     }
     for (int l = 0; l < c.n_layers; ++l) {
-      float* xo = l + 1 < c.n_layers ? cx->layers[l + 1].x : x_final;
+      bf16* xo = l + 1 < c.n_layers ? cx->layers[l + 1].x : x_final;
       EN_CHECK(llama_layer_fwd(l, adapter, lay, cx->layers[l], xo, h, act, s));
     }
   } else {
     LayerActs sc;
     EN_CHECK(alloc_layer_acts(sc, T, d, F, H, r, false, s, tmp));
     EN_CHECK(pool_alloc(&x1buf, T * d, s, tmp));
-    float* cur = x0;
-    float* nxt = x1buf;
+    bf16* cur = x0;
+    bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = cur;
       EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
-      float* t = cur;
+      bf16* t = cur;
       cur = nxt;
       nxt = t;
     }
@@ -1119,8 +1115,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   EN_CHECK(queries_to_i32(queries, qmask, ids, tokmask, out_ids, static_cast<int64_t>(Q) + max_new, N, Q, s));
   EN_CHECK(fill_mod(img_of_row, N, N, s));
   const int64_t PR = static_cast<int64_t>(N) * P;
-  bf16 *clip_feats, *p_pre, *p_act, *t_p0, *t_p2, *feats, *h, *act;
-  float *x0, *x1buf;
+  bf16 *clip_feats, *p_pre, *p_act, *t_p0, *t_p2, *feats, *x0, *x1buf, *h, *act;
   EN_CHECK(pool_alloc(&clip_feats, PR * c.v_d, s, tmp));
   EN_CHECK(pool_alloc(&p_pre, PR * d, s, tmp));
   EN_CHECK(pool_alloc(&p_act, PR * d, s, tmp));
@@ -1160,14 +1155,14 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   int32_t* last_rows;
   EN_CHECK(pool_alloc(&last_rows, N, s, tmp));
   EN_CHECK(fill_affine(last_rows, N, S0, S0 - 1, s));
-  float* x_prefill_out = x0;
+  bf16* x_prefill_out = x0;
   {
-    float* nxt = x1buf;
+    bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = x_prefill_out;
       EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
       EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
-      float* t = x_prefill_out;
+      bf16* t = x_prefill_out;
       x_prefill_out = nxt;
       nxt = t;
     }
@@ -1176,8 +1171,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   // weights (EPI_F32_PARTIAL slices, reduced in a fixed order by the kernel that consumes them); the step reads its
   // position from a device counter, so steps 2.. replay ONE captured CUDA graph.
   const int64_t Nl = N;
-  float *xa, *xb, *x1d;  // fp32 residual stream of the decode rows
-  bf16 *hdn, *qkvd, *od, *actd, *td;
+  bf16 *xa, *xb, *x1d, *hdn, *qkvd, *od, *actd, *td;
   float* part;
   int32_t* cur;
   EN_CHECK(pool_alloc(&xa, Nl * d, s, tmp));
@@ -1296,8 +1290,8 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     // token fed at this step was written at column cur-1; its absolute position is S0 + cur - 1
     EN_CHECK(embed_rows(next_ids, embed, xa, N, d, V, s));
     if (c.n_layers > 0) EN_CHECK(rmsnorm_fwd(xa, layers[0].ln1, hdn, N, d, c.rms_eps, nullptr, s));
-    float* xc = xa;
-    float* xn = xb;
+    bf16* xc = xa;
+    bf16* xn = xb;
     for (int l = 0; l < c.n_layers; ++l) {
       LlamaLayer& L = layers[l];
       int sp = 1;
@@ -1312,7 +1306,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
       EN_CHECK(linear_partial(L.down, actd, 0, &sp));
       const bf16* next_w = l + 1 < c.n_layers ? layers[l + 1].ln1 : final_norm;
       EN_CHECK(partial_residual_rmsnorm(part, sp, x1d, xn, next_w, hdn, N, d, c.rms_eps, s));
-      float* t = xc;
+      bf16* t = xc;
       xc = xn;
       xn = t;
     }

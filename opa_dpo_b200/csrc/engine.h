@@ -48,8 +48,7 @@ struct ClipLayer {
 };
 
 struct LayerActs {
-  float *x = nullptr, *x1 = nullptr;  // fp32 residual stream: layer input, post-attention
-  bf16 *qkv = nullptr, *o = nullptr, *gu = nullptr;
+  bf16 *x = nullptr, *qkv = nullptr, *o = nullptr, *x1 = nullptr, *gu = nullptr;
   bf16 *tqkv = nullptr, *to = nullptr, *tgu = nullptr, *td = nullptr;
   float* lse = nullptr;
 };
@@ -68,7 +67,7 @@ struct SaveCtx {
   float inv_temp = 1.f;
   std::vector<void*> owned;  // freed when the slot is released
   std::vector<LayerActs> layers;
-  float* x_final = nullptr;  // input of the final norm [T, d] (fp32 residual stream)
+  bf16* x_final = nullptr;  // input of the final norm [T, d]
   bf16* hn = nullptr;       // normed response rows [N*R, d]
   int32_t* labels = nullptr;
   float* lse_head = nullptr;
@@ -142,15 +141,14 @@ class Engine {
   const bf16* loraA(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offA; }
   const bf16* loraB(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offB; }
 
-  // stream_f32: `residual` and `y` are the fp32 residual stream (o_proj / down_proj of the decoder); else bf16.
-  int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, void* y, int64_t ldy, int act,
-                 const void* residual, int64_t ldr, cudaStream_t s, bool stream_f32 = false);
+  int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy, int act,
+                 const bf16* residual, int64_t ldr, cudaStream_t s);
   int linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
                  int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s);
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);
-  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, float* x_out, bf16* h, bf16* act,
+  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
                       cudaStream_t s);
 };
 

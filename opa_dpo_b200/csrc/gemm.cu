@@ -35,9 +35,8 @@ struct KParams {
   void* C;
   int64_t ldc;
   const __nv_bfloat16* bias;
-  const void* residual;
+  const __nv_bfloat16* residual;
   int64_t ldr;
-  int res_f32, out_f32;  // fp32 residual stream in / out (EPI_BF16)
   int act;
   const int32_t* labels;
   float4* lse_partials;
@@ -218,10 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
       if constexpr (EPI == EPI_BF16) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
-        float* crow32 = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc;
-        const bool has_res = p.residual != nullptr;
-        const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<int64_t>(row) * p.ldr;
-        const float* rrow32 = reinterpret_cast<const float*>(p.residual) + static_cast<int64_t>(row) * p.ldr;
+        const __nv_bfloat16* rrow = p.residual ? p.residual + static_cast<int64_t>(row) * p.ldr : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -251,17 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = act_fn(v[j], p.act);
             }
-            if (has_res && p.res_f32) {
-              const float4* r4 = reinterpret_cast<const float4*>(rrow32 + col0);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 f = __ldg(r4 + q);
-                v[q * 4 + 0] += f.x;
-                v[q * 4 + 1] += f.y;
-                v[q * 4 + 2] += f.z;
-                v[q * 4 + 3] += f.w;
-              }
-            } else if (has_res) {
+            if (rrow) {
               const uint4* r4 = reinterpret_cast<const uint4*>(rrow + col0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -275,21 +261,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
               }
             }
-            if (p.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(crow32 + col0);
+            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(crow + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u;
-                u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                dst[q] = u;
-              }
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = u;
             }
           } else {
 #pragma unroll
@@ -299,11 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 float x = v[j];
                 if (p.bias) x += __bfloat162float(p.bias[col]);
                 x = act_fn(x, p.act);
-                if (has_res) x += p.res_f32 ? rrow32[col] : __bfloat162float(rrow[col]);
-                if (p.out_f32)
-                  crow32[col] = x;
-                else
-                  crow[col] = __float2bfloat16(x);
+                if (rrow) x += __bfloat162float(rrow[col]);
+                crow[col] = __float2bfloat16(x);
               }
             }
           }
@@ -555,13 +532,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: a2_group_n must be a multiple of %d with K-major A", BN);
     return -4;
   }
-  const int out_align = (a.epilogue == EPI_BF16 && a.out_f32) ? 4 : 8;
-  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD) && (a.ldc % out_align != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
-    snprintf(g_err, sizeof(g_err), "gemm: output needs ldc %% %d == 0 and 16B-aligned C", out_align);
-    return -5;
-  }
-  if (a.residual && (a.ldr % (a.residual_f32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15))) {
-    snprintf(g_err, sizeof(g_err), "gemm: residual needs a 16B-aligned base and row pitch");
+  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD) && (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+    snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
     return -5;
   }
   if ((a.epilogue == EPI_F32_ATOMIC || a.epilogue == EPI_F32_PARTIAL) && (a.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
@@ -611,8 +583,6 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.ldc = a.ldc;
   kp.bias = a.bias;
   kp.residual = a.residual;
-  kp.res_f32 = a.residual_f32 ? 1 : 0;
-  kp.out_f32 = a.out_f32 ? 1 : 0;
   kp.ldr = a.ldr;
   kp.act = a.act;
   kp.labels = a.labels;

@@ -44,10 +44,8 @@ struct GemmArgs {
   void* C = nullptr;
   int64_t ldc = 0;
   const __nv_bfloat16* bias = nullptr;      // [N]
-  const void* residual = nullptr;  // [M, ldr] bf16, or fp32 when residual_f32 (the LLaMA residual stream is kept in fp32)
+  const __nv_bfloat16* residual = nullptr;  // [M, ldr]
   int64_t ldr = 0;
-  bool residual_f32 = false;
-  bool out_f32 = false;  // EPI_BF16 only: store the result as fp32 instead of bf16
   int act = ACT_NONE;
   // EPI_LSE / EPI_CEGRAD
   const int32_t* labels = nullptr;  // [M]; <0 = ignore

@@ -68,8 +68,6 @@ def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=N
     d.bias = _ptr(bias)
     if residual is not None:
         d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
-        d.residual_f32 = int(residual.dtype == torch.float32)
-    d.out_f32 = int(epilogue == EPI_BF16 and out is not None and out.dtype == torch.float32)
     d.act = act
     d.labels = _ptr(labels)
     d.lse_partials = _ptr(lse_partials)

@@ -86,46 +86,8 @@ def test_true_width_truncated_depth_vs_oracle():
 
 @pytest.mark.skipif(os.environ.get("OPADPO_FULL_PARITY") != "1", reason="opt-in: minutes of host CPU at full 7B depth")
 def test_full_depth_7b_loss_vs_oracle():
-    """BASELINE configs[0]: full-depth LLaVA-1.5-7B, fp32 CPU reference (oracle) vs the bf16 engine, both row layouts.
-    Prints the per-token log-prob error statistics that calibrate the bf16 tolerances used at full depth."""
-    from oracle import llava_oracle as O
-    from opa_dpo_b200 import Engine, EngineConfig, POLICY, REF
-    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
-    torch.set_num_threads(os.cpu_count() or 1)
-    oc = O.OracleConfig(**O.LLAVA_7B)
-    ec = EngineConfig(**oc.to_dict())
-    w = O.init_weights(oc, seed=21)
-    lp, lr = O.init_lora(oc, 22), O.init_lora(oc, 23)
-    eng = Engine(ec)
-    _load(eng, O, oc, w, lp, lr)
-    images, q, qm, resp = O.synthetic_batch(oc, 1, 128, 128, NAMES2, left_pad=17, image_pos=35)
-    with torch.no_grad():
-        o_ref = O.policy_forward(oc, w, lr, images, q, qm, resp)
-        o_pol = O.policy_forward(oc, w, lp, images, q, qm, resp)
-        loss_ref, _, _ = O.pair_loss(O.LossConfig(beta=0.1), o_pol[NAMES2[0] + "_logprobs"], o_pol[NAMES2[1] + "_logprobs"],
-                                     o_ref[NAMES2[0] + "_logprobs"], o_ref[NAMES2[1] + "_logprobs"])
-    dev = eng.device
-    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
-    results = []
-    os.makedirs(os.path.join(os.path.dirname(__file__), "..", "gpurun_out"), exist_ok=True)
-    for share in (0, 1):
-        eng.set_option("share_prefix", share)
-        ref_lp, _ = eng.forward_logprobs(REF, *args)
-        pol_lp, _ = eng.forward_logprobs(POLICY, *args)
-        errs = torch.cat([(pol_lp[i].cpu() - o_pol[n + "_logprobs"]).abs().flatten() for i, n in enumerate(NAMES2)] +
-                         [(ref_lp[i].cpu() - o_ref[n + "_logprobs"]).abs().flatten() for i, n in enumerate(NAMES2)])
-        total, _ = FusedDPO(DPOArgs(beta=0.1)).pair(pol_lp[0], pol_lp[1], ref_lp[0], ref_lp[1])
-        rel = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
-        signed = torch.cat([(pol_lp[i].cpu() - o_pol[n + "_logprobs"]).flatten() for i, n in enumerate(NAMES2)])
-        msg = (f"FULL-7B parity share_prefix={share}: loss {total.item():.6f} oracle {loss_ref.item():.6f} rel {rel:.3e}; "
-               f"logprob |err| max {errs.max().item():.4f} mean {errs.mean().item():.4f} p99 {errs.quantile(0.99).item():.4f} "
-               f"signed-mean {signed.mean().item():+.5f}; valid tokens {int((resp[NAMES2[0]] != 0).sum())}+{int((resp[NAMES2[1]] != 0).sum())}")
-        print(msg)
-        with open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "full_parity_stats.txt"), "a") as f:
-            f.write(msg + "\n")
-        results.append(rel)
-    assert max(results) <= 3e-3, results
-    eng.close()
+    got, ref, rel = _oracle_vs_engine(32, 23, b=1, R=128, grads=False)
+    print(f"FULL-7B parity: engine loss {got:.6f} oracle {ref:.6f} rel {rel:.3e}")
 
 
 @pytest.fixture(scope="module")
