@@ -308,7 +308,8 @@ def main():
                    "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
                    "prefix_sharing": (not args.no_share_prefix),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
-                   "collective": "one NCCL all-reduce(sum) of the fp32 LoRA-grad bucket per step" if world > 1 else "none",
+                   "collective": "NCCL all-reduce(sum) of the fp32 LoRA-grad bucket once per step, issued as 33 per-layer slices "
+                                 "overlapped with the backward" if world > 1 else "none",
                    "loss": float(loss.item()), "grad_norm": float(norm.item())},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_host},

@@ -165,6 +165,13 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
 /* Engine options. "share_prefix" (default 1): compute the image+query prefix once per sample and let its K responses
  * attend to it through the segment mask (identical results to the reference's K stacked rows, fewer FLOPs). */
 int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
+/* Communication overlap: `cb(layer, user)` is called on the host thread inside opadpo_backward right after the backward
+ * kernels of decoder layer `layer` (n_layers-1 .. 0), then of the projector (layer == n_layers), have been enqueued; the
+ * slice [offset, offset+count) of the gradient bucket reported by opadpo_engine_layer_grad_range is then final in stream
+ * order, so the caller can start its all-reduce while earlier layers are still being differentiated. cb = NULL disables. */
+typedef void (*opadpo_layer_cb)(int32_t layer, void* user);
+int opadpo_engine_set_backward_callback(opadpo_engine* e, opadpo_layer_cb cb, void* user);
+int opadpo_engine_layer_grad_range(opadpo_engine* e, int32_t layer, int64_t* offset, int64_t* count);
 /* After the caller modified the fp32 masters directly (e.g. optimizer state restore): refresh the bf16 shadows. */
 int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream);
 

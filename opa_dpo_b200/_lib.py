@@ -69,6 +69,9 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+LAYER_CB = ctypes.CFUNCTYPE(None, ctypes.c_int32, ctypes.c_void_p)
+
+
 class DpoPairDesc(ctypes.Structure):
     _fields_ = [
         ("pi_c", ctypes.c_void_p), ("pi_r", ctypes.c_void_p), ("ref_c", ctypes.c_void_p), ("ref_r", ctypes.c_void_p),
@@ -110,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_op_attn_bwd", "opadpo_op_pack_mask", "opadpo_op_dpo_pair", "opadpo_engine_create", "opadpo_engine_destroy",
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
-    "opadpo_engine_set_option",
+    "opadpo_engine_set_option", "opadpo_engine_set_backward_callback", "opadpo_engine_layer_grad_range",
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
 ]
@@ -132,6 +135,8 @@ def _declare_engine(lib):
     lib.opadpo_engine_lora_offsets.argtypes = [vp, c.c_char_p, c.POINTER(i64), c.POINTER(i64)]
     lib.opadpo_engine_sync_shadow.argtypes = [vp, vp]
     lib.opadpo_engine_set_option.argtypes = [vp, c.c_char_p, i64]
+    lib.opadpo_engine_set_backward_callback.argtypes = [vp, LAYER_CB, vp]
+    lib.opadpo_engine_layer_grad_range.argtypes = [vp, i32, c.POINTER(i64), c.POINTER(i64)]
     lib.opadpo_forward_logprobs.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, c.POINTER(vp), i32, f32, vp, vp,
                                             i32, vp]
     lib.opadpo_backward.argtypes = [vp, i32, vp, vp]

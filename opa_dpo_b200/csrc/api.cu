@@ -214,6 +214,15 @@ int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value) 
   if (!name) { set_error("opadpo_engine_set_option: null name"); return OPADPO_EINVAL; }
   return e->impl->set_option(name, value);
 }
+int opadpo_engine_set_backward_callback(opadpo_engine* e, opadpo_layer_cb cb, void* user) {
+  ENGINE_GUARD(e);
+  return e->impl->set_backward_callback(cb, user);
+}
+int opadpo_engine_layer_grad_range(opadpo_engine* e, int32_t layer, int64_t* offset, int64_t* count) {
+  ENGINE_GUARD(e);
+  if (!offset || !count) { set_error("opadpo_engine_layer_grad_range: null pointer"); return OPADPO_EINVAL; }
+  return e->impl->layer_grad_range(layer, offset, count);
+}
 int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream) {
   ENGINE_GUARD(e);
   return e->impl->sync_shadow(static_cast<cudaStream_t>(stream));

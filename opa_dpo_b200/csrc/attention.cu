@@ -329,16 +329,19 @@ struct DqSmem {
   static constexpr int KV_BYTES = NB * BKV * 128;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_DO = OFF_Q + Q_BYTES;
+  // ONE K/V stage: 112 KB per CTA so two CTAs share an SM (TMEM 2 x 256 columns) and one CTA's MMAs overlap the
+  // other's softmax phase; the exposed K/V load latency is covered the same way.
+  static constexpr int KV_STAGES = 1;
   static constexpr int OFF_K = OFF_DO + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_DS = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_DS = OFF_V + KV_STAGES * KV_BYTES;
   static constexpr int OFF_BAR = OFF_DS + BQ * 128;
   static constexpr int TOTAL = OFF_BAR + 128;
   static constexpr int TMEM_COLS = 256;
 };
 
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
     attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const AttnParams p) {
@@ -394,8 +397,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int it = 0;
       for (int j = 0; j < num_kv; ++j) {
         if (tile_skipped(p, q0, j)) continue;
-        const int st = it & 1;
-        ptx::mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+        const int st = it % L::KV_STAGES;
+        ptx::mbar_wait(&kv_empty[st], ((it / L::KV_STAGES) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
         load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
         load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
@@ -413,10 +416,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int it = 0;
       for (int j = 0; j < num_kv; ++j) {
         if (tile_skipped(p, q0, j)) continue;
-        const int st = it & 1;
+        const int st = it % L::KV_STAGES;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
         const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
-        ptx::mbar_wait(&kv_full[st], (it >> 1) & 1);
+        ptx::mbar_wait(&kv_full[st], (it / L::KV_STAGES) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {

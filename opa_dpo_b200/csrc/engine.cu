@@ -676,15 +676,14 @@ int Engine::projector_forward(int adapter, const bf16* clip_feats, int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------ LLaMA layer
-int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
-                            cudaStream_t s) {
+int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, cudaStream_t s) {
   const int64_t T = static_cast<int64_t>(lay.N) * lay.S;
   const int N = lay.N, S = lay.S;
   const opadpo_config& c = cfg;
   const int d = c.d_model, F = c.d_ffn;
   LlamaLayer& L = layers[l];
-  EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
-  EN_CHECK(linear_fwd(L.qkv, adapter, h, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
+  EN_CHECK(rmsnorm_fwd(a.x, L.ln1, a.h1, T, d, c.rms_eps, nullptr, s));
+  EN_CHECK(linear_fwd(L.qkv, adapter, a.h1, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
   EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, nullptr, 2 * c.n_heads, hd, rope_cs, 0, s));
   AttnArgs at;
   at.N = N;
@@ -705,10 +704,10 @@ int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const Laye
   at.segment_len = lay.segR;
   EN_CHECK(attn_fwd_checked(at, s));
   EN_CHECK(linear_fwd(L.o, adapter, a.o, d, T, a.to, a.x1, d, ACT_NONE, a.x, d, s));
-  EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, nullptr, s));
-  EN_CHECK(linear_fwd(L.gu, adapter, h, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
-  EN_CHECK(swiglu_fwd(a.gu, act, T, F, s));
-  EN_CHECK(linear_fwd(L.down, adapter, act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s));
+  EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, a.h2, T, d, c.rms_eps, nullptr, s));
+  EN_CHECK(linear_fwd(L.gu, adapter, a.h2, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
+  EN_CHECK(swiglu_fwd(a.gu, a.act, T, F, s));
+  EN_CHECK(linear_fwd(L.down, adapter, a.act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s));
   return 0;
 }
 
@@ -724,6 +723,9 @@ static int alloc_layer_acts(LayerActs& a, int64_t T, int d, int F, int H, int r,
   EN_CHECK(pool_alloc(&a.to, T * rr, s, track));
   EN_CHECK(pool_alloc(&a.tgu, T * 2 * rr, s, track));
   EN_CHECK(pool_alloc(&a.td, T * rr, s, track));
+  EN_CHECK(pool_alloc(&a.h1, T * d, s, track));
+  EN_CHECK(pool_alloc(&a.h2, T * d, s, track));
+  EN_CHECK(pool_alloc(&a.act, T * F, s, track));
   EN_CHECK(pool_alloc(&a.lse, T * H, s, track));
   return 0;
 }
@@ -794,15 +796,13 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   EN_CHECK(projector_forward(adapter, clip_feats, PR, p_pre, p_act, t_p0, t_p2, feats, s));
 
   // embedding gather + image splice
-  bf16 *x0, *x1buf = nullptr, *h, *act;
+  bf16 *x0, *x1buf = nullptr;
   EN_CHECK(pool_alloc(&x0, T * d, s, keep));
   EN_CHECK(embed_splice(ids, tokmask, img_mask, img_of_row, embed, feats, x0, mask, img_pos, N, L, P, d, c.vocab, s));
   uint64_t* kbits;
   const int nwords = (S + 63) / 64;
   EN_CHECK(pool_alloc(&kbits, static_cast<int64_t>(N) * nwords, s, keep));
   EN_CHECK(attn_pack_mask(mask, kbits, N, S, s));
-  EN_CHECK(pool_alloc(&h, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&act, T * F, s, tmp));
   SeqLayout lay;
   lay.N = N;
   lay.S = S;
@@ -825,7 +825,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     }
     for (int l = 0; l < c.n_layers; ++l) {
       bf16* xo = l + 1 < c.n_layers ? cx->layers[l + 1].x : x_final;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, cx->layers[l], xo, h, act, s));
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, cx->layers[l], xo, s));
     }
   } else {
     LayerActs sc;
@@ -835,7 +835,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = cur;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, s));
       bf16* t = cur;
       cur = nxt;
       nxt = t;
@@ -919,14 +919,12 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   const int rr = r > 0 ? r : 8;
   TempPool tp(s);
   std::vector<void*>* tmp = &tp.ptrs;
-  bf16 *dlogits, *dhn, *dxa, *dxb, *h, *act, *dact, *dgu, *dqkv, *dh, *dob, *u;
+  bf16 *dlogits, *dhn, *dxa, *dxb, *dact, *dgu, *dqkv, *dh, *dob, *u;
   float* delta;
   EN_CHECK(pool_alloc(&dlogits, NR * c.vocab, s, tmp));
   EN_CHECK(pool_alloc(&dhn, NR * d, s, tmp));
   EN_CHECK(pool_alloc(&dxa, T_scratch * d, s, tmp));
   EN_CHECK(pool_alloc(&dxb, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&h, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&act, T * F, s, tmp));
   EN_CHECK(pool_alloc(&dact, T * F, s, tmp));
   EN_CHECK(pool_alloc(&dgu, T * 2 * F, s, tmp));
   EN_CHECK(pool_alloc(&dqkv, T * 3 * d, s, tmp));
@@ -971,11 +969,9 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     LlamaLayer& L = layers[l];
     const LayerActs& a = cx.layers[l];
     // MLP
-    EN_CHECK(swiglu_fwd(a.gu, act, T, F, s));
-    EN_CHECK(linear_bwd(L.down, adapter, act, F, a.td, dx, d, T, u, dact, F, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u, dact, F, nullptr, 0, s));
     EN_CHECK(swiglu_bwd(dact, a.gu, dgu, T, F, s));
-    EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, h, T, d, c.rms_eps, nullptr, s));
-    EN_CHECK(linear_bwd(L.gu, adapter, h, d, a.tgu, dgu, 2 * F, T, u, dh, d, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.gu, adapter, a.h2, d, a.tgu, dgu, 2 * F, T, u, dh, d, nullptr, 0, s));
     EN_CHECK(rmsnorm_bwd(dh, a.x1, L.ln2, dx, dx1, T, d, c.rms_eps, nullptr, nullptr, s));
     // attention
     EN_CHECK(linear_bwd(L.o, adapter, a.o, d, a.to, dx1, d, T, u, dob, d, nullptr, 0, s));
@@ -1005,9 +1001,9 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     at.ld_dqkv = 3 * d;
     EN_CHECK(attn_bwd_checked(at, s));
     EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, nullptr, 2 * H, hd, rope_cs, 1, s));
-    EN_CHECK(rmsnorm_fwd(a.x, L.ln1, h, T, d, c.rms_eps, nullptr, s));
-    EN_CHECK(linear_bwd(L.qkv, adapter, h, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.qkv, adapter, a.h1, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s));
     EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, nullptr, nullptr, s));
+    if (layer_cb) layer_cb(l, layer_cb_user);  // this layer's LoRA-grad slice is complete in stream order
   }
   // image rows -> projector (its LoRA adapters are trainable; the CLIP tower is not differentiated)
   const int64_t PR = static_cast<int64_t>(cx.b) * P;
@@ -1019,6 +1015,7 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   EN_CHECK(linear_bwd(proj2, adapter, cx.p_act, d, cx.t_p2, dfeats, d, PR, u, dpact, d, nullptr, 0, s));
   EN_CHECK(gelu_bwd(dpact, cx.p_pre, dppre, PR * d, s));
   EN_CHECK(linear_bwd(proj0, adapter, cx.clip_feats, c.v_d, cx.t_p0, dppre, d, PR, u, nullptr, 0, nullptr, 0, s));
+  if (layer_cb) layer_cb(c.n_layers, layer_cb_user);
   release_slot(save_slot, s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1043,6 +1040,27 @@ int Engine::set_option(const char* name, int64_t value) {
   }
   set_error("unknown option '%s'", name);
   return OPADPO_EINVAL;
+}
+
+int Engine::set_backward_callback(opadpo_layer_cb cb, void* user) {
+  layer_cb = cb;
+  layer_cb_user = user;
+  return 0;
+}
+
+// Gradient-bucket slice of decoder layer `layer` (0..n_layers-1) or of the projector (layer == n_layers): the flat
+// bucket is ordered layer by layer, so each slice is contiguous and final as soon as that layer's backward has run.
+int Engine::layer_grad_range(int layer, int64_t* offset, int64_t* count) {
+  if (layer < 0 || layer > cfg.n_layers) {
+    set_error("layer_grad_range: layer %d out of range", layer);
+    return OPADPO_EINVAL;
+  }
+  const int64_t begin = layer < cfg.n_layers ? slots[layers[layer].qkv.slot].offA : slots[proj0.slot].offA;
+  const int64_t end = layer + 1 < cfg.n_layers ? slots[layers[layer + 1].qkv.slot].offA
+                                               : (layer + 1 == cfg.n_layers ? slots[proj0.slot].offA : n_train);
+  *offset = begin;
+  *count = end - begin;
+  return 0;
 }
 
 int Engine::zero_grad(cudaStream_t s) {
@@ -1115,7 +1133,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   EN_CHECK(queries_to_i32(queries, qmask, ids, tokmask, out_ids, static_cast<int64_t>(Q) + max_new, N, Q, s));
   EN_CHECK(fill_mod(img_of_row, N, N, s));
   const int64_t PR = static_cast<int64_t>(N) * P;
-  bf16 *clip_feats, *p_pre, *p_act, *t_p0, *t_p2, *feats, *x0, *x1buf, *h, *act;
+  bf16 *clip_feats, *p_pre, *p_act, *t_p0, *t_p2, *feats, *x0, *x1buf;
   EN_CHECK(pool_alloc(&clip_feats, PR * c.v_d, s, tmp));
   EN_CHECK(pool_alloc(&p_pre, PR * d, s, tmp));
   EN_CHECK(pool_alloc(&p_act, PR * d, s, tmp));
@@ -1129,8 +1147,6 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   EN_CHECK(projector_forward(adapter, clip_feats, PR, p_pre, p_act, t_p0, t_p2, feats, s));
   EN_CHECK(pool_alloc(&x0, T * d, s, tmp));
   EN_CHECK(pool_alloc(&x1buf, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&h, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&act, T * F, s, tmp));
   EN_CHECK(embed_splice(ids, tokmask, nullptr, img_of_row, embed, feats, x0, mask, img_pos, N, Q, P, d, V, s));
   uint64_t* kbits;
   EN_CHECK(pool_alloc(&kbits, static_cast<int64_t>(N) * ((S0 + 63) / 64), s, tmp));
@@ -1160,7 +1176,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = x_prefill_out;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, h, act, s));
+      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, s));
       EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
       bf16* t = x_prefill_out;
       x_prefill_out = nxt;

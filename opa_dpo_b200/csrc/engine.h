@@ -50,6 +50,7 @@ struct ClipLayer {
 struct LayerActs {
   bf16 *x = nullptr, *qkv = nullptr, *o = nullptr, *x1 = nullptr, *gu = nullptr;
   bf16 *tqkv = nullptr, *to = nullptr, *tgu = nullptr, *td = nullptr;
+  bf16 *h1 = nullptr, *h2 = nullptr, *act = nullptr;  // normed inputs of qkv / gate|up and the SwiGLU output
   float* lse = nullptr;
 };
 
@@ -108,12 +109,16 @@ class Engine {
   int generate(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask, int Q, int max_new,
                const opadpo_sampler* sampler, int64_t* out_ids, cudaStream_t s);
   int set_option(const char* name, int64_t value);
+  int set_backward_callback(opadpo_layer_cb cb, void* user);
+  int layer_grad_range(int layer, int64_t* offset, int64_t* count);
 
  private:
   opadpo_config cfg;
   int hd = 0, v_hd = 0, P = 0, Kp = 0, r = 0;
   float lora_scale = 1.f;
   bool share_prefix = true;  // compute the image+query prefix once per sample for its K responses
+  opadpo_layer_cb layer_cb = nullptr;  // host callback after each layer's backward kernels are enqueued (comm overlap)
+  void* layer_cb_user = nullptr;
   // base weights
   bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
   std::vector<LlamaLayer> layers;
@@ -148,8 +153,7 @@ class Engine {
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);
-  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, bf16* h, bf16* act,
-                      cudaStream_t s);
+  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, cudaStream_t s);
 };
 
 }  // namespace opadpo

@@ -32,3 +32,45 @@ def allreduce_grad_bucket(flat_grad: torch.Tensor, group: Optional[dist.ProcessG
         return 1.0
     dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world
+
+
+class OverlappedGradAllReduce:
+    """All-reduce of the LoRA-grad bucket overlapped with the backward pass.
+
+    The bucket is ordered layer by layer, and opadpo_backward reports (host callback) when the kernels that finish a
+    layer's slice have been enqueued. Each slice is then all-reduced with async_op=True: ProcessGroupNCCL makes its own
+    stream wait for everything enqueued so far on the compute stream, so the collective of layer l runs over NVLink while
+    layers l-1..0 are still being differentiated. `finish()` makes the compute stream wait for all of them and returns
+    the 1/world scale for the optimizer. Arm it only for the LAST micro-batch of an optimizer step."""
+
+    def __init__(self, engine, flat_grad: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+        self.engine, self.grad, self.group = engine, flat_grad, group
+        self.works = []
+        self.ranges = {}
+        self.armed = False
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            engine.set_backward_callback(self._on_layer)
+
+    def _on_layer(self, layer: int):
+        if not self.armed:
+            return
+        if layer not in self.ranges:
+            self.ranges[layer] = self.engine.layer_grad_range(layer)
+        off, cnt = self.ranges[layer]
+        if cnt > 0:
+            self.works.append(dist.all_reduce(self.grad[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def arm(self):
+        self.armed = self.world > 1
+
+    def finish(self) -> float:
+        if self.world == 1:
+            return 1.0
+        if not self.works:      # nothing was overlapped (not armed): one bucket-wide all-reduce
+            return allreduce_grad_bucket(self.grad, self.group)
+        for w in self.works:
+            w.wait()            # stream-level wait: the compute stream waits for the NCCL stream
+        self.works = []
+        self.armed = False
+        return 1.0 / self.world

@@ -16,7 +16,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import DpoPairDesc
-from .dist import allreduce_grad_bucket
+from .dist import OverlappedGradAllReduce, allreduce_grad_bucket
 
 _DIV = {"reverse_kl": 0, "js_divergence": 1, "alpha_divergence": 2}
 
@@ -178,6 +178,9 @@ class DPOStepper:
         self.world_size = world_size
         self.process_group = process_group
         self.lr = args.learning_rate
+        self.overlap = None
+        if world_size > 1 and self.model.flat_param is not None:
+            self.overlap = OverlappedGradAllReduce(self.model.engine, self.model.flat_param.grad, process_group)
 
     @torch.no_grad()
     def reference_logprobs(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
@@ -185,8 +188,11 @@ class DPOStepper:
         out = self.ref_policy(**batch, temperature=self.args.temperature)
         return {"ref_base_" + k: v for k, v in out.items()}
 
-    def pair_loss(self, batch: Dict[str, Tensor], ref: Dict[str, Tensor], chosen: str, rejected: str, grad_accum: int = 1):
+    def pair_loss(self, batch: Dict[str, Tensor], ref: Dict[str, Tensor], chosen: str, rejected: str, grad_accum: int = 1,
+                  last_micro_batch: bool = True):
         self.policy.train()
+        if self.overlap is not None and last_micro_batch:
+            self.overlap.arm()   # this backward completes the bucket: all-reduce its slices as they become final
         out = self.policy(**batch, temperature=self.args.temperature, mode="policy")
         total, o = self.loss.pair(out[chosen + "_logprobs"], out[rejected + "_logprobs"],
                                   ref["ref_base_" + chosen + "_logprobs"], ref["ref_base_" + rejected + "_logprobs"])
@@ -196,8 +202,12 @@ class DPOStepper:
     def optimizer_step(self) -> Tensor:
         a = self.args
         eng = self.model.engine
-        # ONE NCCL all-reduce(sum) of the flat LoRA-grad bucket per optimizer step; 1/world is applied inside AdamW
-        scale = allreduce_grad_bucket(self.model.flat_param.grad, self.process_group) if self.world_size > 1 else 1.0
+        # the LoRA-grad bucket is all-reduced (sum) once per optimizer step — as per-layer slices overlapped with the backward
+        # when armed, else as one bucket-wide call; 1/world is applied inside the fused clip+AdamW kernel
+        if self.overlap is not None:
+            scale = self.overlap.finish()
+        else:
+            scale = allreduce_grad_bucket(self.model.flat_param.grad, self.process_group) if self.world_size > 1 else 1.0
         norm = eng.optimizer_step(self.lr, (a.adam_beta1, a.adam_beta2), a.adam_epsilon, a.weight_decay, a.max_grad_norm, scale)
         eng.zero_grad()
         return norm

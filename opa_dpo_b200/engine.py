@@ -192,6 +192,20 @@ class Engine:
                                    n_total=nt.value, n_train=ntr.value)
         return self._views
 
+    def set_backward_callback(self, fn):
+        """fn(layer:int) is called on the host inside backward() after each layer's kernels are enqueued (None: off)."""
+        if fn is None:
+            self._cb = _lib.LAYER_CB()   # NULL function pointer
+        else:
+            self._cb = _lib.LAYER_CB(lambda layer, _user: fn(int(layer)))
+        _lib.check(self.lib.opadpo_engine_set_backward_callback(self._h, self._cb, None), "set_backward_callback")
+
+    def layer_grad_range(self, layer: int) -> Tuple[int, int]:
+        off, cnt = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.opadpo_engine_layer_grad_range(self._h, layer, ctypes.byref(off), ctypes.byref(cnt)),
+                   "layer_grad_range")
+        return off.value, cnt.value
+
     def set_option(self, name: str, value: int):
         _lib.check(self.lib.opadpo_engine_set_option(self._h, name.encode(), int(value)), f"set_option({name})")
 

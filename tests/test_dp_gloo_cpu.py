@@ -63,6 +63,54 @@ def test_two_rank_allreduce_equals_concatenated_batch():
     assert rel < 1e-4, f"DP gradient differs from the concatenated-batch gradient (rel {rel})"
 
 
+def _overlap_worker(rank, world, port, q_out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opa_dpo_b200.dist import OverlappedGradAllReduce
+
+    class FakeEngine:  # stands in for the C-ABI engine: 3 "layers" + projector slices of a 100-element bucket
+        ranges = {0: (0, 30), 1: (30, 30), 2: (60, 30), 3: (90, 10)}
+
+        def set_backward_callback(self, fn):
+            self.fn = fn
+
+        def layer_grad_range(self, layer):
+            return self.ranges[layer]
+
+    eng = FakeEngine()
+    g = torch.arange(100, dtype=torch.float32) * (rank + 1)
+    ov = OverlappedGradAllReduce(eng, g)
+    ov.arm()
+    for layer in (2, 1, 0, 3):   # backward order, projector last
+        eng.fn(layer)
+    scale = ov.finish()
+    expect = torch.arange(100, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok = torch.equal(g, expect) and scale == 1.0 / world
+    # not armed -> falls back to one bucket-wide all-reduce
+    g2 = torch.ones(100) * (rank + 1)
+    ov2 = OverlappedGradAllReduce(eng, g2)
+    scale2 = ov2.finish()
+    ok = ok and torch.equal(g2, torch.ones(100) * 3) and scale2 == 0.5
+    if rank == 0:
+        q_out.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_allreduce_slices_equal_bucket_allreduce():
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q_out.get(timeout=120) is True
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+
 def test_shard_range():
     from opa_dpo_b200.dist import shard_range
     assert [shard_range(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
