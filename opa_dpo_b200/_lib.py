@@ -52,6 +52,7 @@ class GemmDesc(ctypes.Structure):
         ("lse", ctypes.c_void_p),
         ("dlp", ctypes.c_void_p),
         ("max_ctas", ctypes.c_int32),
+        ("cluster_mode", ctypes.c_int32),
     ]
 
 

@@ -7,6 +7,7 @@
 #include "gemm.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
@@ -49,18 +50,23 @@ struct Tile {
   int m_blk, n_blk, kb_begin, kb_end, split;
 };
 
-__device__ __forceinline__ Tile decode_tile(const KParams& p, int tile) {
-  const int tiles_mn = p.num_m * p.num_n;
+// CL = 1: `tile` enumerates (m block, n block, split). CL = 2: `tile` enumerates (PAIR of m blocks, n block); the two
+// CTAs of a cluster take m blocks 2*mp + rank of the same n block, so they can share (multicast) the B tile.
+template <int CL>
+__device__ __forceinline__ Tile decode_tile(const KParams& p, int tile, int rank) {
+  const int num_m = CL == 1 ? p.num_m : (p.num_m + 1) / 2;
+  const int tiles_mn = num_m * p.num_n;
   const int split = tile / tiles_mn;
   const int t = tile - split * tiles_mn;
-  const int per_group = GROUP_M * p.num_n;
+  constexpr int GM = GROUP_M / CL;
+  const int per_group = GM * p.num_n;
   const int group = t / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(GROUP_M, p.num_m - first_m);
+  const int first_m = group * GM;
+  const int gsize = min(GM, num_m - first_m);
   const int r = t - group * per_group;
   Tile o;
   o.split = split;
-  o.m_blk = first_m + r % gsize;
+  o.m_blk = (first_m + r % gsize) * CL + rank;
   o.n_blk = r / gsize;
   if (p.splits == 1) {
     o.kb_begin = 0;
@@ -82,10 +88,16 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KParams p) {
+  // CL == 2: launched as clusters of two CTAs that work on vertically adjacent output tiles; each loads HALF of the
+  // shared B tile and multicasts it into both CTAs' smem, so per-SM L2->smem traffic per k-block drops from 48 to 32 KB.
+  const int rank = CL == 1 ? 0 : static_cast<int>(ptx::cluster_ctarank());
+  const int tile_first = CL == 1 ? blockIdx.x : blockIdx.x / CL;
+  const int tile_stride = CL == 1 ? gridDim.x : gridDim.x / CL;
+  const int num_tiles = CL == 1 ? p.num_tiles : ((p.num_m + 1) / 2) * p.num_n * p.splits;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (ptx::elect_one()) {
       for (int i = 0; i < STAGES; ++i) {
         ptx::mbar_init(&full_bar[i], 1);
-        ptx::mbar_init(&empty_bar[i], 1);
+        ptx::mbar_init(&empty_bar[i], CL);  // CL == 2: the peer's MMA must also be done with the slot it multicasts into
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull_bar[i], 1);
@@ -122,6 +134,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();  // the peer's barriers must be initialised before anything is multicast into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -130,8 +143,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(p, tile);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+        const Tile t = decode_tile<CL>(p, tile, rank);
         const int m0 = t.m_blk * BM, n0 = t.n_blk * BN;
         const int a2off = p.a2_group_n > 0 ? (n0 / p.a2_group_n) * p.a2_group_stride : 0;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
@@ -149,11 +162,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g) ptx::tma_load_2d(sA + g * 8192, ma, &full_bar[stage], m0 + g * 64, k0);
           }
-          if (!B_MN) {
-            ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
-          } else {
+          if (CL == 1) {
+            if (!B_MN) {
+              ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sB + g * 8192, mb, &full_bar[stage], n0 + g * 64, k0);
+              for (int g = 0; g < BN / 64; ++g) ptx::tma_load_2d(sB + g * 8192, mb, &full_bar[stage], n0 + g * 64, k0);
+            }
+          } else {  // my half of the B tile, multicast into both CTAs (the tensor map's box is BN/2 rows when K-major)
+            if (!B_MN) {
+              ptx::tma_load_2d_mc(sB + rank * (B_BYTES / 2), mb, &full_bar[stage], k0, n0 + rank * (BN / 2), 0x3);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BN / 128; ++g) {
+                const int gg = rank * (BN / 128) + g;
+                ptx::tma_load_2d_mc(sB + gg * 8192, mb, &full_bar[stage], n0 + gg * 64, k0, 0x3);
+              }
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -170,8 +195,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(p, tile);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+        const Tile t = decode_tile<CL>(p, tile, rank);
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -190,7 +215,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
-          ptx::mma_commit(&empty_bar[stage]);
+          if (CL == 1)
+            ptx::mma_commit(&empty_bar[stage]);
+          else
+            ptx::mma_commit_mc(&empty_bar[stage], 0x3);  // frees the slot in both CTAs' rings
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -206,8 +234,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int quad = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const Tile t = decode_tile(p, tile);
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+      const Tile t = decode_tile<CL>(p, tile, rank);
       const int m0 = t.m_blk * BM, n0 = t.n_blk * BN;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -419,6 +447,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();  // nobody leaves while the peer may still multicast into / arrive on this CTA's smem
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -435,9 +464,9 @@ struct ProfRec {
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int CL>
 int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<A_MN, B_MN, EPI, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -454,7 +483,27 @@ int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream
     rec.flops = 2.0 * kp.M * kp.N * 64.0 * (kp.kb1 + kp.kb2);
     cudaEventRecord(rec.a, stream);
   }
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  if (CL == 1) {
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], kp);
+    if (le != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "gemm cluster launch: %s", cudaGetErrorString(le));
+      return -11;
+    }
+  }
   if (g_prof_on) {
     cudaEventRecord(rec.b, stream);
     g_prof.push_back(rec);
@@ -541,6 +590,17 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     return -5;
   }
 
+  // Cluster (B-multicast) variant: two CTAs on vertically adjacent tiles share each B tile. Worth it when there are many
+  // m blocks; not combined with split-K. a.cluster: -1 auto, 0 off, 1 on. OPADPO_GEMM_CLUSTER=0 disables it globally.
+  static const bool cluster_env_on = []() {
+    const char* e = getenv("OPADPO_GEMM_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  const int num_m_blocks = (a.M + BM - 1) / BM;
+  const bool single_split = a.splits <= 1;
+  bool use_cluster = a.cluster < 0 ? (cluster_env_on && single_split && num_m_blocks >= 8) : (a.cluster > 0 && single_split);
+  const int b_box_rows = use_cluster ? BN / 2 : BN;
+
   CUtensorMap maps[4];
   auto mk = [&](CUtensorMap* m, const GemmOperand& op, bool mn_major, int rows_out, int K, int box_rows_kmajor,
                 int extra_cols) -> int {
@@ -550,10 +610,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   int groups = a.a2_group_n > 0 ? (a.N + a.a2_group_n - 1) / a.a2_group_n : 1;
   int rc = 0;
   rc |= mk(&maps[0], a.A1, a.a_mn_major, a.M, a.K1, BM, 0);
-  rc |= mk(&maps[1], a.B1, a.b_mn_major, a.N, a.K1, BN, 0);
+  rc |= mk(&maps[1], a.B1, a.b_mn_major, a.N, a.K1, b_box_rows, 0);
   if (a.K2 > 0) {
     rc |= mk(&maps[2], a.A2, a.a_mn_major, a.M, a.K2, BM, (groups - 1) * a.a2_group_stride);
-    rc |= mk(&maps[3], a.B2, a.b_mn_major, a.N, a.K2, BN, 0);
+    rc |= mk(&maps[3], a.B2, a.b_mn_major, a.N, a.K2, b_box_rows, 0);
   } else {
     maps[2] = maps[0];
     maps[3] = maps[1];
@@ -593,16 +653,28 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
 
   int grid = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
-  if (grid > kp.num_tiles) grid = kp.num_tiles;
+  if (use_cluster) {
+    const int pair_tiles = ((kp.num_m + 1) / 2) * kp.num_n;
+    grid &= ~1;
+    if (grid > 2 * pair_tiles) grid = 2 * pair_tiles;
+    if (grid < 2) use_cluster = false;
+  }
+  if (!use_cluster && grid > kp.num_tiles) grid = kp.num_tiles;
 
-#define OPADPO_DISPATCH(AMN, BMN)                                                            \
-  switch (a.epilogue) {                                                                      \
-    case EPI_BF16: return launch_impl<AMN, BMN, EPI_BF16>(maps, kp, grid, stream);           \
-    case EPI_F32_ATOMIC: return launch_impl<AMN, BMN, EPI_F32_ATOMIC>(maps, kp, grid, stream); \
-    case EPI_LSE: return launch_impl<AMN, BMN, EPI_LSE>(maps, kp, grid, stream);             \
-    case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD>(maps, kp, grid, stream);       \
-    case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL>(maps, kp, grid, stream); \
-    default: break;                                                                          \
+#define OPADPO_DISPATCH_CL(AMN, BMN, CL)                                                          \
+  switch (a.epilogue) {                                                                           \
+    case EPI_BF16: return launch_impl<AMN, BMN, EPI_BF16, CL>(maps, kp, grid, stream);            \
+    case EPI_F32_ATOMIC: return launch_impl<AMN, BMN, EPI_F32_ATOMIC, CL>(maps, kp, grid, stream); \
+    case EPI_LSE: return launch_impl<AMN, BMN, EPI_LSE, CL>(maps, kp, grid, stream);              \
+    case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD, CL>(maps, kp, grid, stream);        \
+    case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL, CL>(maps, kp, grid, stream); \
+    default: break;                                                                               \
+  }
+#define OPADPO_DISPATCH(AMN, BMN)          \
+  if (use_cluster) {                       \
+    OPADPO_DISPATCH_CL(AMN, BMN, 2)        \
+  } else {                                 \
+    OPADPO_DISPATCH_CL(AMN, BMN, 1)        \
   }
   if (!a.a_mn_major && !a.b_mn_major) {
     OPADPO_DISPATCH(false, false)
@@ -612,6 +684,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     OPADPO_DISPATCH(true, true)
   }
 #undef OPADPO_DISPATCH
+#undef OPADPO_DISPATCH_CL
   snprintf(g_err, sizeof(g_err), "gemm: unknown epilogue %d", a.epilogue);
   return -7;
 }

@@ -54,6 +54,7 @@ struct GemmArgs {
   const float* lse = nullptr;       // [M]
   const float* dlp = nullptr;       // [M]
   int max_ctas = 0;                 // 0 = all SMs
+  int cluster = -1;                 // B-multicast 2-CTA cluster variant: -1 auto, 0 off, 1 on
 };
 
 // Returns 0 on success, negative on error (message via gemm_last_error()).
