@@ -182,8 +182,7 @@ def test_gemm_cluster_lora_groups_bias_residual_and_mn_major():
     _close(dx, dy.float() @ Wt.float() + u.float() @ At.float(), what="cluster dgrad")
     # wgrad form: both MN-major, fp32 atomic accumulate, no split
     T = 1300
-    a, b = _mk((T, 1100), 53), _mk((T, 300), 54)
-    acc = torch.zeros((1100, 300), device="cuda", dtype=torch.float32)
+    a, b = _mk((T, 1104), 53)[:, :1100], _mk((T, 304), 54)[:, :300]
     acc2 = torch.zeros((1100, 304), device="cuda", dtype=torch.float32)[:, :300]
     ops.gemm(a, b, acc2, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC, cluster=1)
     torch.cuda.synchronize()
