@@ -676,12 +676,12 @@ int Engine::projector_forward(int adapter, const bf16* clip_feats, int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------ LLaMA layer
-int Engine::llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, cudaStream_t s) {
+int Engine::llama_layer_fwd(const LlamaLayer& L, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out,
+                            cudaStream_t s) {
   const int64_t T = static_cast<int64_t>(lay.N) * lay.S;
   const int N = lay.N, S = lay.S;
   const opadpo_config& c = cfg;
   const int d = c.d_model, F = c.d_ffn;
-  LlamaLayer& L = layers[l];
   EN_CHECK(rmsnorm_fwd(a.x, L.ln1, a.h1, T, d, c.rms_eps, nullptr, s));
   EN_CHECK(linear_fwd(L.qkv, adapter, a.h1, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
   EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, nullptr, 2 * c.n_heads, hd, rope_cs, 0, s));
@@ -825,7 +825,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     }
     for (int l = 0; l < c.n_layers; ++l) {
       bf16* xo = l + 1 < c.n_layers ? cx->layers[l + 1].x : x_final;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, cx->layers[l], xo, s));
+      EN_CHECK(llama_layer_fwd(layers[l], adapter, lay, cx->layers[l], xo, s));
     }
   } else {
     LayerActs sc;
@@ -835,7 +835,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = cur;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, s));
+      EN_CHECK(llama_layer_fwd(layers[l], adapter, lay, sc, nxt, s));
       bf16* t = cur;
       cur = nxt;
       nxt = t;
@@ -1025,9 +1025,48 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   return 0;
 }
 
+// Merged decoder weights for rollout: per group g, W'_g = W_g + (alpha/r) B_g A_g as one GEMM with W_g as the residual
+// (A operand = B_g [out_g, r] K-major, B operand = A_g [r, in] MN-major).
+int Engine::merge_lora(int adapter, std::vector<LlamaLayer>* merged, std::vector<void*>* track, cudaStream_t s) {
+  merged->assign(layers.begin(), layers.end());
+  for (size_t l = 0; l < layers.size(); ++l) {
+    LinearW* src[4] = {&layers[l].qkv, &layers[l].o, &layers[l].gu, &layers[l].down};
+    LinearW* dst[4] = {&(*merged)[l].qkv, &(*merged)[l].o, &(*merged)[l].gu, &(*merged)[l].down};
+    for (int i = 0; i < 4; ++i) {
+      const LinearW& L = *src[i];
+      if (L.slot < 0) continue;
+      bf16* Wm = nullptr;
+      EN_CHECK(pool_alloc(&Wm, static_cast<int64_t>(L.out) * L.in, s, track));
+      const int G = L.groups, out_g = L.out / G;
+      for (int g = 0; g < G; ++g) {
+        GemmArgs a;
+        a.M = out_g;
+        a.N = L.in;
+        a.K1 = r;
+        a.A1 = {loraB(adapter, L) + static_cast<int64_t>(g) * out_g * r, r};
+        a.b_mn_major = true;
+        a.B1 = {loraA(adapter, L) + static_cast<int64_t>(g) * r * L.in, L.in};
+        a.alpha = lora_scale;
+        a.residual = L.W + static_cast<int64_t>(g) * out_g * L.in;
+        a.ldr = L.in;
+        a.C = Wm + static_cast<int64_t>(g) * out_g * L.in;
+        a.ldc = L.in;
+        EN_CHECK(gemm_checked(a, s));
+      }
+      dst[i]->W = Wm;
+      dst[i]->slot = -1;
+    }
+  }
+  return 0;
+}
+
 int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "share_prefix") == 0) {
     share_prefix = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "merge_rollout") == 0) {
+    merge_rollout = value != 0;
     return 0;
   }
   if (strcmp(name, "adam_step") == 0) {  // optimizer-state restore (resume_training, dpo_trainer.py:901-931)
@@ -1117,6 +1156,16 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   const int rr = r > 0 ? r : 8;
   TempPool tp(s);
   std::vector<void*>* tmp = &tp.ptrs;
+  // Decoder weights used by this rollout: with an adapter and merge_rollout, W' = W + (alpha/r) B A is built once
+  // (~3 TFLOP) so every decode linear is ONE weight-streaming GEMM; the vision tower / projector stay unmerged.
+  std::vector<LlamaLayer> merged;
+  const std::vector<LlamaLayer>* LL = &layers;
+  int llm_adapter = adapter;
+  if (adapter >= 0 && r > 0 && merge_rollout) {
+    EN_CHECK(merge_lora(adapter, &merged, tmp, s));
+    LL = &merged;
+    llm_adapter = -1;
+  }
 
   // ---- prefill (same kernels as the training forward; K/V copied into the static cache)
   int32_t *ids, *img_of_row, *img_pos, *next_ids;
@@ -1176,7 +1225,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = x_prefill_out;
-      EN_CHECK(llama_layer_fwd(l, adapter, lay, sc, nxt, s));
+      EN_CHECK(llama_layer_fwd((*LL)[l], llm_adapter, lay, sc, nxt, s));
       EN_CHECK(kv_store_prefill(sc.qkv, kc[l], vc[l], N, S0, S_max, d, s));
       bf16* t = x_prefill_out;
       x_prefill_out = nxt;
@@ -1204,7 +1253,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   EN_CHECK(pool_alloc(&part, static_cast<int64_t>(kMaxSplits) * Nl * widest, s, tmp));
   cudaMemsetAsync(cur, 0, sizeof(int32_t), s);
 
-  const bool lora = adapter >= 0 && r > 0;
+  const bool lora = llm_adapter >= 0 && r > 0;
   // K-split count: every SM should stream weights. cost = waves of CTAs x k-blocks per split.
   auto splits_for = [&](int n_out, int K1, int K2) {
     const int tiles = ((N + 127) / 128) * ((n_out + 255) / 256);
@@ -1231,7 +1280,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
       a.N = G * r;
       a.K1 = L.in;
       a.A1 = {x, L.in};
-      a.B1 = {loraA(adapter, L), L.in};
+      a.B1 = {loraA(llm_adapter, L), L.in};
       a.alpha = lora_scale;
       a.epilogue = EPI_F32_PARTIAL;
       a.splits = spA;
@@ -1252,7 +1301,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     if (K2 > 0) {
       a.K2 = r;
       a.A2 = {td, static_cast<int64_t>(G) * r};
-      a.B2 = {loraB(adapter, L), r};
+      a.B2 = {loraB(llm_adapter, L), r};
       if (G > 1) {
         if ((L.out / G) % 256 != 0) {
           set_error("generate: fused group width %d must be a multiple of 256", L.out / G);
@@ -1305,11 +1354,11 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   auto decode_step = [&]() -> int {
     // token fed at this step was written at column cur-1; its absolute position is S0 + cur - 1
     EN_CHECK(embed_rows(next_ids, embed, xa, N, d, V, s));
-    if (c.n_layers > 0) EN_CHECK(rmsnorm_fwd(xa, layers[0].ln1, hdn, N, d, c.rms_eps, nullptr, s));
+    if (c.n_layers > 0) EN_CHECK(rmsnorm_fwd(xa, (*LL)[0].ln1, hdn, N, d, c.rms_eps, nullptr, s));
     bf16* xc = xa;
     bf16* xn = xb;
     for (int l = 0; l < c.n_layers; ++l) {
-      LlamaLayer& L = layers[l];
+      const LlamaLayer& L = (*LL)[l];
       int sp = 1;
       EN_CHECK(linear_partial(L.qkv, hdn, 0, &sp));
       EN_CHECK(partial_to_bf16(part, sp, Nl * 3 * d, qkvd, s));
@@ -1320,7 +1369,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
       EN_CHECK(linear_partial(L.gu, hdn, 0, &sp));
       EN_CHECK(partial_swiglu(part, sp, actd, N, F, s));
       EN_CHECK(linear_partial(L.down, actd, 0, &sp));
-      const bf16* next_w = l + 1 < c.n_layers ? layers[l + 1].ln1 : final_norm;
+      const bf16* next_w = l + 1 < c.n_layers ? (*LL)[l + 1].ln1 : final_norm;
       EN_CHECK(partial_residual_rmsnorm(part, sp, x1d, xn, next_w, hdn, N, d, c.rms_eps, s));
       bf16* t = xc;
       xc = xn;

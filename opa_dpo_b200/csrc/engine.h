@@ -117,6 +117,7 @@ class Engine {
   int hd = 0, v_hd = 0, P = 0, Kp = 0, r = 0;
   float lora_scale = 1.f;
   bool share_prefix = true;  // compute the image+query prefix once per sample for its K responses
+  bool merge_rollout = true;  // rollout runs on W + (alpha/r) B A merged once per generate() call
   opadpo_layer_cb layer_cb = nullptr;  // host callback after each layer's backward kernels are enqueued (comm overlap)
   void* layer_cb_user = nullptr;
   // base weights
@@ -153,7 +154,10 @@ class Engine {
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);
-  int llama_layer_fwd(int l, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out, cudaStream_t s);
+  int llama_layer_fwd(const LlamaLayer& L, int adapter, const SeqLayout& lay, const LayerActs& a, bf16* x_out,
+                      cudaStream_t s);
+  // W' = W + (alpha/r) B A for every decoder linear (rollout only: one plain weight-streaming GEMM per linear)
+  int merge_lora(int adapter, std::vector<LlamaLayer>* merged, std::vector<void*>* track, cudaStream_t s);
 };
 
 }  // namespace opadpo

@@ -592,13 +592,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
 
   // Cluster (B-multicast) variant: two CTAs on vertically adjacent tiles share each B tile. Worth it when there are many
   // m blocks; not combined with split-K. a.cluster: -1 auto, 0 off, 1 on. OPADPO_GEMM_CLUSTER=0 disables it globally.
+  // Measured (profiles/r01_gemm_cluster_ab.txt): +3..8 % on isolated dgrad-shaped GEMMs, -1..-4 % on N=12288, and no
+  // change inside the power-capped training step, so auto currently means OFF unless OPADPO_GEMM_CLUSTER=1.
   static const bool cluster_env_on = []() {
     const char* e = getenv("OPADPO_GEMM_CLUSTER");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   const int num_m_blocks = (a.M + BM - 1) / BM;
   const bool single_split = a.splits <= 1;
   bool use_cluster = a.cluster < 0 ? (cluster_env_on && single_split && num_m_blocks >= 8) : (a.cluster > 0 && single_split);
+  (void)num_m_blocks;
   const int b_box_rows = use_cluster ? BN / 2 : BN;
 
   CUtensorMap maps[4];

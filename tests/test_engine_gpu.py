@@ -216,11 +216,14 @@ def test_policy_module_compute_policy_loss_repo_defaults():
     model.engine.close()
 
 
-def test_greedy_rollout_ids_exact():
+@pytest.mark.parametrize("merge", [1, 0])
+def test_greedy_rollout_ids_exact(merge):
+    """merge=1: rollout on W + (alpha/r) B A merged once per call (default); merge=0: adapters applied unmerged."""
     from oracle import llava_oracle as O
-    from opa_dpo_b200 import POLICY
+    from opa_dpo_b200 import POLICY, BASE
     oc, ec = _cfgs()
     eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
+    eng.set_option("merge_rollout", merge)
     images, q, qm, _ = O.synthetic_batch(oc, 3, 16, 8, NAMES2, left_pad=3)
     ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12)
     got = eng.generate(POLICY, images, q, qm, 12).cpu()
@@ -228,6 +231,11 @@ def test_greedy_rollout_ids_exact():
     assert torch.equal(got, ids_ref), f"rollout ids differ (margin {margin:.3g}):\n{got[:, 16:]}\n{ids_ref[:, 16:]}"
     trunc = O.truncate_after_eos_with_padding(got[:, 16:], oc.eos_id, oc.pad_id, [1577, 29973])
     assert trunc.shape == (3, 12)
+    # the bare base model (adapter -1) is a different policy: its ids follow the oracle without LoRA
+    ids_base, margin_b = O.greedy_generate(oc, w, None, images, q, qm, 6)
+    got_b = eng.generate(BASE, images, q, qm, 6).cpu()
+    if margin_b > 0.05:
+        assert torch.equal(got_b, ids_base)
     eng.close()
 
 
