@@ -406,3 +406,50 @@ def test_checkpoint_roundtrip_peft_layout(tmp_path):
     v1, v2 = model.engine.buffers(), model2.engine.buffers()
     assert torch.equal(v1["exp_avg"], v2["exp_avg"]) and torch.equal(v1["exp_avg_sq"], v2["exp_avg_sq"])
     model.engine.close(); model2.engine.close()
+
+
+def test_opa_sft_loss_and_grads_vs_oracle():
+    """OPA stage (LoRA-SFT): token-mean NLL over the response tokens == HF causal-LM loss with prompt labels ignored
+    (opa_trainer.py:58-125, entropy_loss off); loss and LoRA gradients vs the oracle's logits + F.cross_entropy."""
+    from types import SimpleNamespace
+    import torch.nn.functional as F
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.opa import sft_loss
+    from opa_dpo_b200.dpo import DPOArgs
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.make_trainable("lora_policy")
+    R = 24
+    policy = AutoregressivePolicy(DPOArgs(response_len=R), model, SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, R, ["standard_response"], left_pad=2)
+    # oracle: logits of the full row, labels = response tokens, everything else IGNORE_INDEX (HF shift-by-one loss)
+    lpg = {m: (A.clone().requires_grad_("vision_model" not in m), B.clone().requires_grad_("vision_model" not in m)) for m, (A, B) in lp.items()}
+    ids = torch.cat([q, resp["standard_response"]], 1)
+    mask = torch.cat([qm.bool(), resp["standard_response"] != 0], 1)
+    logits = O.llava_logits(oc, w, lpg, ids, mask, images)[:, -R - 1:-1]
+    labels = resp["standard_response"].clone()
+    labels[labels == 0] = -100
+    loss_ref = F.cross_entropy(logits.reshape(-1, oc.vocab), labels.reshape(-1), ignore_index=-100)
+    loss_ref.backward()
+    policy.train()
+    out = policy(images, q, qm, **resp)
+    loss = sft_loss(out, resp, 0)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    model.engine.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    g = model.engine.buffers()["grad"]
+    for m in ("model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.mm_projector.2"):
+        oa, ob = model.engine.lora_offsets(m)
+        for t, off in ((lpg[m][0], oa), (lpg[m][1], ob)):
+            gg = g[off:off + t.numel()].view_as(t).cpu()
+            cos = torch.nn.functional.cosine_similarity(gg.flatten(), t.grad.flatten(), dim=0).item()
+            assert cos >= 0.99, (m, cos)
+    model.engine.close()
