@@ -515,13 +515,17 @@ struct DkvSmem {
   static constexpr int OFF_V = OFF_K + KV_BYTES;
   static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [2]
   static constexpr int OFF_DO = OFF_Q + 2 * Q_BYTES;   // [2]
-  static constexpr int OFF_P = OFF_DO + 2 * Q_BYTES;
-  static constexpr int OFF_DS = OFF_P + BQ * 128;
-  static constexpr int OFF_BAR = OFF_DS + BQ * 128;
+  static constexpr int PD_BYTES = BQ * 128;
+  static constexpr int OFF_P = OFF_DO + 2 * Q_BYTES;   // [2]
+  static constexpr int OFF_DS = OFF_P + 2 * PD_BYTES;  // [2]
+  static constexpr int OFF_BAR = OFF_DS + 2 * PD_BYTES;
   static constexpr int TOTAL = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = 256;
+  static constexpr int TMEM_COLS = 512;  // S,dP double-buffered (4 x 64) + dV^T + dK^T (2 x 64)
 };
 
+// Software-pipelined: S/dP live in two TMEM buffers and P/dS in two smem buffers, so the tensor pipe computes
+// S,dP of query tile i+1 while the softmax threads turn tile i into P,dS, and dV^T,dK^T of tile i overlap the
+// softmax of tile i+1 (one CTA per SM: the overlap has to come from inside the CTA).
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(NTHREADS, 1)
     attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -533,12 +537,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;
-  uint64_t* done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* qdo_full = bars + 1;    // [2]
+  uint64_t* qdo_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;    // [2]
+  uint64_t* pds_full = bars + 7;    // [2]
+  uint64_t* pds_empty = bars + 9;   // [2]
+  uint64_t* done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int j = blockIdx.x;
@@ -550,6 +555,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // query tiles of OTHER response segments never see this key tile (shared-prefix packing): skip them
   int last_qt = nq - 1;
   while (last_qt > i0 && tile_skipped(p, last_qt * BQ, j)) --last_qt;
+  auto next_tile = [&](int qt) {  // next processed query tile after qt (last_qt + 1 = none)
+    ++qt;
+    while (qt <= last_qt && tile_skipped(p, qt * BQ, j)) ++qt;
+    return qt;
+  };
 
   if (warp == 4) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -561,9 +571,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&qdo_full[i], 1);
         ptx::mbar_init(&qdo_empty[i], 1);
+        ptx::mbar_init(&sdp_full[i], 1);
+        ptx::mbar_init(&pds_full[i], 128);
+        ptx::mbar_init(&pds_empty[i], 1);
       }
-      ptx::mbar_init(sdp_full, 1);
-      ptx::mbar_init(pds_full, 128);
       ptx::mbar_init(done, 1);
       ptx::fence_barrier_init();
     }
@@ -572,7 +583,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dv = tmem + 128, t_dk = tmem + 192;
+  // TMEM columns: [S0 | dP0 | S1 | dP1 | dV^T | dK^T], 64 each
+  const uint32_t t_dv = tmem + 256, t_dk = tmem + 320;
 
   if (warp == 4) {
     if (ptx::elect_one()) {
@@ -580,8 +592,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKV, NB);
       load_tile(smem + L::OFF_V, &tmV, kv_full, col0, n * p.S + k0, BKV, NB);
       int it = 0;
-      for (int qt = i0; qt <= last_qt; ++qt) {
-        if (tile_skipped(p, qt * BQ, j)) continue;
+      for (int qt = i0; qt <= last_qt; qt = next_tile(qt)) {
         const int st = it & 1;
         ptx::mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&qdo_full[st], 2 * L::Q_BYTES);
@@ -597,15 +608,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       constexpr uint32_t idesc_t = ptx::make_idesc_bf16(HD, BKV, true, true);
       const uint32_t aK = ptx::smem_u32(smem + L::OFF_K);
       const uint32_t aV = ptx::smem_u32(smem + L::OFF_V);
-      const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
-      const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
-      ptx::mbar_wait(kv_full, 0);
-      int it = 0;
-      for (int qt = i0; qt <= last_qt; ++qt) {
-        if (tile_skipped(p, qt * BQ, j)) continue;
+      // S = Q K^T and dP = dO V^T of pipeline slot `it` into TMEM buffer it & 1
+      auto issue_sdp = [&](int it) {
         const int st = it & 1;
         const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
         const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
+        const uint32_t t_s = tmem + st * 128, t_dp = t_s + 64;
         ptx::mbar_wait(&qdo_full[st], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
@@ -620,8 +628,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(adO + blk * (BQ * 128) + off, 16, 1024),
                            ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
         }
-        ptx::mma_commit(sdp_full);
-        ptx::mbar_wait(pds_full, it & 1);
+        ptx::mma_commit(&sdp_full[st]);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      int it = 0;
+      for (int qt = i0; qt <= last_qt; ++it) {
+        const int nxt = next_tile(qt);
+        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose pds_full was awaited below
+        if (nxt <= last_qt) issue_sdp(it + 1);
+        const int st = it & 1;
+        const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
+        const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
+        const uint32_t aP = ptx::smem_u32(smem + L::OFF_P + st * L::PD_BYTES);
+        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + st * L::PD_BYTES);
+        ptx::mbar_wait(&pds_full[st], (it >> 1) & 1);
         ptx::tc_fence_after();
         // dV^T[hd, keys] += dO^T P ; dK^T[hd, keys] += Q^T dS   (contraction over the 128 query rows)
 #pragma unroll
@@ -634,26 +655,31 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           ptx::mma_bf16_ss(t_dk, ptx::make_smem_desc(aQ + kk * 2048, BQ * 128, 1024),
                            ptx::make_smem_desc(adS + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
         }
-        ptx::mma_commit(&qdo_empty[st]);
+        ptx::mma_commit(&qdo_empty[st]);  // Q/dO stage and ...
+        ptx::mma_commit(&pds_empty[st]);  // ... the P/dS buffer may be overwritten once these MMAs are done
         if (qt == last_qt) ptx::mma_commit(done);
-        ++it;
+        qt = nxt;
       }
     }
   } else {
     const int tid = threadIdx.x;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     int it = 0;
-    for (int qt = i0; qt <= last_qt; ++qt) {
-      if (tile_skipped(p, qt * BQ, j)) continue;
+    for (int qt = i0; qt <= last_qt; qt = next_tile(qt)) {
+      const int st = it & 1;
+      const uint32_t t_s = tmem + st * 128, t_dp = t_s + 64;
+      uint8_t* sP = smem + L::OFF_P + st * L::PD_BYTES;
+      uint8_t* sdS = smem + L::OFF_DS + st * L::PD_BYTES;
       const int q0 = qt * BQ;
       const int i = q0 + tid;
       const bool row_valid = i < p.S;
       const int64_t grow = static_cast<int64_t>(n) * p.S + i;
       const float lse2 = row_valid ? p.lse[grow * p.H + h] * LOG2E : INFINITY;
       const float delta = row_valid ? p.delta[grow * p.H + h] : 0.f;
-      ptx::mbar_wait(sdp_full, it & 1);
-      ptx::tc_fence_after();
       const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
+      ptx::mbar_wait(&pds_empty[st], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P/dS buffer two slots ago are done
+      ptx::mbar_wait(&sdp_full[st], (it >> 1) & 1);
+      ptx::tc_fence_after();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t s[32], dp[32];
@@ -662,12 +688,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
         recompute_half(s, dp, bits, half, p.scale_log2, p.scale, lse2, delta, pv, dsv);
-        store_half_row_sw128(smem + L::OFF_P, tid, half, pv);
-        store_half_row_sw128(smem + L::OFF_DS, tid, half, dsv);
+        store_half_row_sw128(sP, tid, half, pv);
+        store_half_row_sw128(sdS, tid, half, dsv);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(pds_full);
+      ptx::mbar_arrive(&pds_full[st]);
       ++it;
     }
     ptx::mbar_wait(done, 0);
