@@ -61,7 +61,7 @@ typedef struct opadpo_gemm_desc {
   const float* lse;               /* EPI_CEGRAD: [M] */
   const float* dlp;               /* EPI_CEGRAD: [M] */
   int32_t max_ctas;               /* 0 = one CTA per SM */
-  int32_t cluster_mode;           /* 0 auto, 1 off, 2 on: 2-CTA cluster variant that multicasts the shared B tile */
+  int32_t cluster_mode;           /* 0 auto, 1 off, 2: 2-CTA cluster that multicasts the shared B tile, 3: CTA pair (tcgen05 cta_group::2, 256x256 MMA) */
 } opadpo_gemm_desc;
 
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);

@@ -63,7 +63,7 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
   a.lse = d->lse;
   a.dlp = d->dlp;
   a.max_ctas = d->max_ctas;
-  a.cluster = d->cluster_mode - 1;  /* 0 (zero-initialised desc) = auto */
+  a.cluster = d->cluster_mode - 1;  /* 0 (zero-initialised desc) = auto, 1 off, 2 B-multicast cluster, 3 CTA pair */
   int rc = gemm_launch(a, static_cast<cudaStream_t>(stream));
   if (rc != 0) {
     set_error("%s", gemm_last_error());

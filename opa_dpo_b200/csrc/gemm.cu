@@ -22,7 +22,6 @@ constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 256;
-constexpr int GROUP_M = 16;  // tile rasterisation: 16 m-blocks share each B panel while it is L2-hot
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -32,6 +31,7 @@ struct KParams {
   int a2_group_n, a2_group_stride;
   int splits, kb_per_split;
   int num_m, num_n, num_tiles;
+  int group_m;  // m blocks that share each streamed B panel while their A tiles stay L2-resident
   float alpha;
   void* C;
   int64_t ldc;
@@ -54,11 +54,12 @@ struct Tile {
 // CTAs of a cluster take m blocks 2*mp + rank of the same n block, so they can share (multicast) the B tile.
 template <int CL>
 __device__ __forceinline__ Tile decode_tile(const KParams& p, int tile, int rank) {
+  constexpr int PS = CL == 1 ? 1 : 2;  // CTAs per cluster
   const int num_m = CL == 1 ? p.num_m : (p.num_m + 1) / 2;
   const int tiles_mn = num_m * p.num_n;
   const int split = tile / tiles_mn;
   const int t = tile - split * tiles_mn;
-  constexpr int GM = GROUP_M / CL;
+  const int GM = max(1, p.group_m / PS);
   const int per_group = GM * p.num_n;
   const int group = t / per_group;
   const int first_m = group * GM;
@@ -66,7 +67,7 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int tile, int rank
   const int r = t - group * per_group;
   Tile o;
   o.split = split;
-  o.m_blk = (first_m + r % gsize) * CL + rank;
+  o.m_blk = (first_m + r % gsize) * PS + rank;
   o.n_blk = r / gsize;
   if (p.splits == 1) {
     o.kb_begin = 0;
@@ -94,15 +95,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KParams p) {
   // CL == 2: launched as clusters of two CTAs that work on vertically adjacent output tiles; each loads HALF of the
   // shared B tile and multicasts it into both CTAs' smem, so per-SM L2->smem traffic per k-block drops from 48 to 32 KB.
+  // CL == 3: CTA PAIR (tcgen05 cta_group::2): ONE 256x256x16 MMA spans both SMs; each CTA keeps its 128 A rows and only
+  // ITS half of the B tile in smem (32 KB per stage, 6 stages), the leader CTA issues every MMA, accumulators live in
+  // both CTAs' TMEM, and smem operand reads per SM drop by a third.
+  constexpr bool PAIR = CL == 3;
+  constexpr int PS = CL == 1 ? 1 : 2;
+  constexpr int NSTAGE = PAIR ? 6 : STAGES;
+  constexpr int BB = PAIR ? B_BYTES / 2 : B_BYTES;  // B bytes per stage held by this CTA
+  constexpr int SBYTES = A_BYTES + BB;
+  static_assert(NSTAGE * SBYTES <= STAGES * STAGE_BYTES, "smem budget");
   const int rank = CL == 1 ? 0 : static_cast<int>(ptx::cluster_ctarank());
-  const int tile_first = CL == 1 ? blockIdx.x : blockIdx.x / CL;
-  const int tile_stride = CL == 1 ? gridDim.x : gridDim.x / CL;
+  const int tile_first = CL == 1 ? blockIdx.x : blockIdx.x / PS;
+  const int tile_stride = CL == 1 ? gridDim.x : gridDim.x / PS;
   const int num_tiles = CL == 1 ? p.num_tiles : ((p.num_m + 1) / 2) * p.num_n * p.splits;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -118,19 +128,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      for (int i = 0; i < STAGES; ++i) {
+      for (int i = 0; i < NSTAGE; ++i) {
         ptx::mbar_init(&full_bar[i], 1);
-        ptx::mbar_init(&empty_bar[i], CL);  // CL == 2: the peer's MMA must also be done with the slot it multicasts into
+        ptx::mbar_init(&empty_bar[i], CL == 2 ? 2 : 1);  // CL == 2: the peer's MMA must also be done with the slot
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull_bar[i], 1);
-        ptx::mbar_init(&tempty_bar[i], 4);
+        ptx::mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // PAIR: the leader waits for both CTAs' epilogue warps
       }
       ptx::fence_barrier_init();
     }
   } else if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (PAIR) {  // collective over the CTA pair: one warp of each CTA
+      ptx::tmem_alloc2(tmem_slot, 512);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -149,13 +164,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int a2off = p.a2_group_n > 0 ? (n0 / p.a2_group_n) * p.a2_group_stride : 0;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           const bool seg2 = kb >= p.kb1;
           const CUtensorMap* ma = seg2 ? &tmA2 : &tmA1;
           const CUtensorMap* mb = seg2 ? &tmB2 : &tmB1;
           const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
-          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sA = smem + stage * SBYTES;
           uint8_t* sB = sA + A_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs' tiles complete on the LEADER's full barrier (it alone waits on it and issues the MMAs)
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * SBYTES);
+            const uint32_t fb = ptx::mapa(&full_bar[stage], 0);
+            ptx::tma_load_2d_pair(sA, ma, fb, k0 + (seg2 ? a2off : 0), m0);
+            if (!B_MN) {
+              ptx::tma_load_2d_pair(sB, mb, fb, k0, n0 + rank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int g = 0; g < BN / 128; ++g)
+                ptx::tma_load_2d_pair(sB + g * 8192, mb, fb, n0 + (rank * (BN / 128) + g) * 64, k0);
+            }
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (!A_MN) {
             ptx::tma_load_2d(sA, ma, &full_bar[stage], k0 + (seg2 ? a2off : 0), m0);
           } else {
@@ -187,10 +220,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
+    // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -204,7 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * SBYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -212,19 +245,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                                         : ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? ptx::make_smem_desc(b_addr + k * 2048, 8192, 1024)
                                         : ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-            ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+            if (PAIR)
+              ptx::mma_bf16_ss2(d_tmem, adesc, bdesc, idesc, accumulate);
+            else
+              ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
           if (CL == 1)
             ptx::mma_commit(&empty_bar[stage]);
-          else
+          else if (CL == 2)
             ptx::mma_commit_mc(&empty_bar[stage], 0x3);  // frees the slot in both CTAs' rings
-          if (++stage == STAGES) {
+          else
+            ptx::mma_commit2_mc(&empty_bar[stage], 0x3);
+          if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::mma_commit(&tfull_bar[acc]);
+        if (PAIR)
+          ptx::mma_commit2_mc(&tfull_bar[acc], 0x3);  // both CTAs' epilogue warps drain their half of the accumulator
+        else
+          ptx::mma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -439,7 +480,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR && rank != 0)
+          ptx::mbar_arrive_remote(ptx::mapa(&tempty_bar[acc], 0));  // the leader's MMA thread owns the accumulator ring
+        else
+          ptx::mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -450,7 +496,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (CL > 1) ptx::cluster_sync();  // nobody leaves while the peer may still multicast into / arrive on this CTA's smem
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (PAIR)
+      ptx::tmem_dealloc2(tmem_base, 512);
+    else
+      ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -493,7 +542,7 @@ int launch_impl(const CUtensorMap* maps, const KParams& kp, int grid, cudaStream
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -596,12 +645,18 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   // change inside the power-capped training step, so auto currently means OFF unless OPADPO_GEMM_CLUSTER=1.
   static const bool cluster_env_on = []() {
     const char* e = getenv("OPADPO_GEMM_CLUSTER");
-    return e && e[0] == '1';
+    return e && (e[0] == '1' || e[0] == '2');
   }();
   const int num_m_blocks = (a.M + BM - 1) / BM;
   const bool single_split = a.splits <= 1;
-  bool use_cluster = a.cluster < 0 ? (cluster_env_on && single_split && num_m_blocks >= 8) : (a.cluster > 0 && single_split);
-  (void)num_m_blocks;
+  static const int cluster_env_mode = []() {
+    const char* e = getenv("OPADPO_GEMM_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  int cl_mode = a.cluster < 0 ? ((cluster_env_on && num_m_blocks >= 8) ? cluster_env_mode : 0) : a.cluster;
+  if (!single_split || cl_mode < 0 || cl_mode > 2) cl_mode = 0;
+  if (cl_mode == 2 && a.a_mn_major) cl_mode = 0;  // the CTA-pair kernel is instantiated for K-major A only
+  bool use_cluster = cl_mode > 0;
   const int b_box_rows = use_cluster ? BN / 2 : BN;
 
   CUtensorMap maps[4];
@@ -641,6 +696,19 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.num_m = (a.M + BM - 1) / BM;
   kp.num_n = (a.N + BN - 1) / BN;
   kp.num_tiles = kp.num_m * kp.num_n * kp.splits;
+  {
+    // Rasterisation: keep about 32 MB of A tiles L2-resident per group so each B panel is streamed from HBM
+    // num_m/group_m times (OPADPO_GEMM_GROUP_M overrides).
+    static const int env_gm = []() {
+      const char* e = getenv("OPADPO_GEMM_GROUP_M");
+      return e ? atoi(e) : 0;
+    }();
+    const double tile_bytes = 2.0 * BM * 64.0 * (kp.kb1 + kp.kb2);
+    int gm = static_cast<int>(32.0 * 1024 * 1024 / tile_bytes);
+    gm = gm < 8 ? 8 : (gm > 64 ? 64 : gm);
+    gm &= ~1;
+    kp.group_m = env_gm > 0 ? env_gm : gm;
+  }
   kp.alpha = a.alpha;
   kp.C = a.C;
   kp.ldc = a.ldc;
@@ -679,13 +747,20 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   } else {                                 \
     OPADPO_DISPATCH_CL(AMN, BMN, 1)        \
   }
+#define OPADPO_DISPATCH_PAIR(BMN)          \
+  if (use_cluster && cl_mode == 2) {       \
+    OPADPO_DISPATCH_CL(false, BMN, 3)      \
+  }
   if (!a.a_mn_major && !a.b_mn_major) {
+    OPADPO_DISPATCH_PAIR(false)
     OPADPO_DISPATCH(false, false)
   } else if (!a.a_mn_major && a.b_mn_major) {
+    OPADPO_DISPATCH_PAIR(true)
     OPADPO_DISPATCH(false, true)
   } else {
     OPADPO_DISPATCH(true, true)
   }
+#undef OPADPO_DISPATCH_PAIR
 #undef OPADPO_DISPATCH
 #undef OPADPO_DISPATCH_CL
   snprintf(g_err, sizeof(g_err), "gemm: unknown epilogue %d", a.epilogue);

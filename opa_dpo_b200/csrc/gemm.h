@@ -54,7 +54,7 @@ struct GemmArgs {
   const float* lse = nullptr;       // [M]
   const float* dlp = nullptr;       // [M]
   int max_ctas = 0;                 // 0 = all SMs
-  int cluster = -1;                 // B-multicast 2-CTA cluster variant: -1 auto, 0 off, 1 on
+  int cluster = -1;                 // -1 auto, 0 off, 1 B-multicast 2-CTA cluster, 2 CTA pair (cta_group::2 MMA, K-major A)
 };
 
 // Returns 0 on success, negative on error (message via gemm_last_error()).

@@ -145,13 +145,15 @@ def test_gemm_lse_and_cegrad():
     _close(G, refG, what="cegrad")
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1100, 768, 320), (1215 * 3, 512, 256), (2048, 264, 136)])
-def test_gemm_cluster_multicast_kk(M, N, K):
-    """2-CTA cluster variant (B tile multicast): same results as the single-CTA kernel, incl. an odd number of m blocks."""
+def test_gemm_cluster_multicast_kk(M, N, K, mode):
+    """2-CTA variants — mode 1: cluster with the B tile multicast; mode 2: CTA pair (tcgen05 cta_group::2, one 256x256
+    MMA over two SMs): same results as the single-CTA kernel, incl. an odd number of m blocks."""
     from opa_dpo_b200 import ops
     a, b = _mk((M, K), 41), _mk((N, K), 42)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, b, out, cluster=1)
+    ops.gemm(a, b, out, cluster=mode)
     torch.cuda.synchronize()
     _close(out, a.float() @ b.float().t(), what=f"cluster kk {M}x{N}x{K}")
     out1 = torch.empty_like(out)
@@ -160,14 +162,15 @@ def test_gemm_cluster_multicast_kk(M, N, K):
     assert torch.equal(out, out1), "cluster and single-CTA kernels must agree bit for bit (same k order)"
 
 
-def test_gemm_cluster_lora_groups_bias_residual_and_mn_major():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_cluster_lora_groups_bias_residual_and_mn_major(mode):
     from opa_dpo_b200 import ops
     M, K, r, G, Ng = 1500, 320, 64, 3, 256
     x, W = _mk((M, K), 43), _mk((G * Ng, K), 44, 0.05)
     t, B = _mk((M, G * r), 45), _mk((G * Ng, r), 46, 0.05)
     bias, res = _mk((G * Ng,), 47), _mk((M, G * Ng), 48)
     out = torch.empty((M, G * Ng), device="cuda", dtype=torch.bfloat16)
-    ops.gemm(x, W, out, a2=t, b2=B, a2_group_n=Ng, a2_group_stride=r, K2=r, bias=bias, residual=res, cluster=1)
+    ops.gemm(x, W, out, a2=t, b2=B, a2_group_n=Ng, a2_group_stride=r, K2=r, bias=bias, residual=res, cluster=mode)
     torch.cuda.synchronize()
     ref = x.float() @ W.float().t() + bias.float() + res.float()
     for g in range(G):
@@ -177,7 +180,7 @@ def test_gemm_cluster_lora_groups_bias_residual_and_mn_major():
     dy, Wt = _mk((M, 512), 49), _mk((512, 384), 50, 0.05)
     u, At = _mk((M, 64), 51), _mk((64, 384), 52, 0.05)
     dx = torch.empty((M, 384), device="cuda", dtype=torch.bfloat16)
-    ops.gemm(dy, Wt, dx, a2=u, b2=At, b_mn=True, K2=64, cluster=1)
+    ops.gemm(dy, Wt, dx, a2=u, b2=At, b_mn=True, K2=64, cluster=mode)
     torch.cuda.synchronize()
     _close(dx, dy.float() @ Wt.float() + u.float() @ At.float(), what="cluster dgrad")
     # wgrad form: both MN-major, fp32 atomic accumulate, no split

@@ -34,17 +34,20 @@ def main():
         out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
         ms = bench(lambda: ops.gemm(a, b, out, cluster=0))
         ms_cl = bench(lambda: ops.gemm(a, b, out, cluster=1))
+        ms_pair = bench(lambda: ops.gemm(a, b, out, cluster=2))
         ms_ref = bench(lambda: torch.matmul(a, b.t(), out=out))
         tf = 2.0 * M * N * K / ms / 1e9
         res.append(dict(M=M, N=N, K=K, ms=ms, tflops=tf, cluster_ms=ms_cl, cluster_tflops=2.0 * M * N * K / ms_cl / 1e9,
-                        cublas_ms=ms_ref, cublas_tflops=2.0 * M * N * K / ms_ref / 1e9))
+                        pair_tflops=2.0 * M * N * K / ms_pair / 1e9, cublas_ms=ms_ref, cublas_tflops=2.0 * M * N * K / ms_ref / 1e9))
         print(json.dumps(res[-1]), flush=True)
         # dgrad form (B MN-major)
         bt = torch.randn((K, N), device="cuda", dtype=torch.bfloat16)
         ms = bench(lambda: ops.gemm(a, bt, out, b_mn=True, cluster=0))
         ms_cl = bench(lambda: ops.gemm(a, bt, out, b_mn=True, cluster=1))
+        ms_pair = bench(lambda: ops.gemm(a, bt, out, b_mn=True, cluster=2))
         print(json.dumps(dict(kind="b_mn", M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9, cluster_ms=ms_cl,
-                              cluster_tflops=2.0 * M * N * K / ms_cl / 1e9)), flush=True)
+                              cluster_tflops=2.0 * M * N * K / ms_cl / 1e9, pair_tflops=2.0 * M * N * K / ms_pair / 1e9)),
+              flush=True)
     # wgrad form
     for T, Mo, No, splits in [(19440, 256, 4096, 5), (19440, 4096, 256, 5), (19440, 768, 4096, 2)]:
         a = torch.randn((T, Mo), device="cuda", dtype=torch.bfloat16)
