@@ -318,7 +318,7 @@ def main():
                      "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None, "traffic": traffic,
                      "traffic_note": "dram read+write bytes of ONE dominant launch (gate|up forward GEMM, M=13816 N=22016 K=4096+256; "
                                      "algorithmic 0.92 GB) from profiles/r01_ncu_full_gemm_fwd_layer.json",
-                     "kernel": "opadpo::gemm_kernel (tcgen05 128x256x64, all epilogues)", "peak_source": peaks["source"] + " sustained",
+                     "kernel": "opadpo::gemm_kernel (tcgen05; CTA-pair cta_group::2 256x256x64 tiles for the large GEMMs, 128x256x64 otherwise; all epilogues)", "peak_source": peaks["source"] + " sustained",
                      "gemm_launches_per_step": int(gl.value), "gemm_ms_per_step": gm.value,
                      "gemm_share_of_step": gm.value / ms_step,
                      "step_algorithmic_tflops_per_gpu": step_tflops,

@@ -641,19 +641,17 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
 
   // Cluster (B-multicast) variant: two CTAs on vertically adjacent tiles share each B tile. Worth it when there are many
   // m blocks; not combined with split-K. a.cluster: -1 auto, 0 off, 1 on. OPADPO_GEMM_CLUSTER=0 disables it globally.
-  // Measured (profiles/r01_gemm_cluster_ab.txt): +3..8 % on isolated dgrad-shaped GEMMs, -1..-4 % on N=12288, and no
-  // change inside the power-capped training step, so auto currently means OFF unless OPADPO_GEMM_CLUSTER=1.
-  static const bool cluster_env_on = []() {
+  // Two-CTA variants (a.cluster: -1 auto, 0 off, 1 = cluster with the B tile multicast, 2 = CTA pair / cta_group::2).
+  // Measured (profiles/r01_gemm_cluster_ab.txt): the CTA pair is +8..16 % on the step's GEMM shapes (above cuBLAS on
+  // most) and -33 ms on the 680 ms training step; the multicast cluster is +-0 in the step. Auto = CTA pair whenever
+  // there are >= 8 m blocks, no split-K and K-major A. OPADPO_GEMM_CLUSTER=0/1/2 overrides auto.
+  static const int cluster_env_mode = []() {
     const char* e = getenv("OPADPO_GEMM_CLUSTER");
-    return e && (e[0] == '1' || e[0] == '2');
+    return e ? atoi(e) : 2;
   }();
   const int num_m_blocks = (a.M + BM - 1) / BM;
   const bool single_split = a.splits <= 1;
-  static const int cluster_env_mode = []() {
-    const char* e = getenv("OPADPO_GEMM_CLUSTER");
-    return e ? atoi(e) : 0;
-  }();
-  int cl_mode = a.cluster < 0 ? ((cluster_env_on && num_m_blocks >= 8) ? cluster_env_mode : 0) : a.cluster;
+  int cl_mode = a.cluster < 0 ? (num_m_blocks >= 8 ? cluster_env_mode : 0) : a.cluster;
   if (!single_split || cl_mode < 0 || cl_mode > 2) cl_mode = 0;
   if (cl_mode == 2 && a.a_mn_major) cl_mode = 0;  // the CTA-pair kernel is instantiated for K-major A only
   bool use_cluster = cl_mode > 0;
