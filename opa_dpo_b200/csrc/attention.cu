@@ -19,7 +19,8 @@ constexpr int BQ = 128;   // query rows per tile
 constexpr int BKV = 64;   // keys per tile
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;      // forward: 4 softmax warps + TMA warp + MMA warp
+constexpr int NTHREADS_BWD = 320;  // backward: 8 softmax warps (two threads per TMEM lane, 32 score columns each) + TMA + MMA
 
 struct AttnParams {
   int N, S, H;
@@ -341,7 +342,7 @@ struct DqSmem {
 };
 
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS_BWD, 2)
     attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const AttnParams p) {
@@ -366,10 +367,10 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   int num_kv = (p.S + BKV - 1) / BKV;
   if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
 
-  if (warp == 4) {
+  if (warp == 8) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
     ptx::tmem_relinquish();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (ptx::elect_one()) {
       if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
       ptx::mbar_init(q_full, 1);
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         ptx::mbar_init(&kv_empty[i], 1);
       }
       ptx::mbar_init(sdp_full, 1);
-      ptx::mbar_init(ds_full, 128);
+      ptx::mbar_init(ds_full, 256);
       ptx::mbar_init(dq_done, 1);
       ptx::fence_barrier_init();
     }
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(q_full, 2 * L::Q_BYTES);
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         ++it;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, false, false);
       constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(BQ, HD, false, true);
@@ -447,10 +448,12 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       }
     }
   } else {
-    const int tid = threadIdx.x;
+    // two threads per query row: warp & 3 selects the 32 TMEM lanes, warp >> 2 the 32-column half of the score tile
+    const int half = warp >> 2;
+    const int tid = (warp & 3) * 32 + (threadIdx.x & 31);
     const int i = q0 + tid;
     const bool row_valid = i < p.S;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
     const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
     int it = 0;
@@ -459,8 +462,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       ptx::mbar_wait(sdp_full, it & 1);
       ptx::tc_fence_after();
       const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t s[32], dp[32];
         ptx::tmem_ld32(t_s + lane_off + half * 32, s);
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     ptx::tc_fence_after();
     __nv_bfloat16* drow = p.dq + static_cast<int64_t>(row0 + tid) * p.ld_dqkv + col0;
 #pragma unroll 1
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int c = half * (HD / 64); c < (half + 1) * (HD / 64); ++c) {
       uint32_t t[32];
       ptx::tmem_ld32(t_dq + lane_off + c * 32, t);
       ptx::tmem_ld_wait();
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, L::TMEM_COLS);
   }
@@ -527,7 +529,7 @@ struct DkvSmem {
 // S,dP of query tile i+1 while the softmax threads turn tile i into P,dS, and dV^T,dK^T of tile i overlap the
 // softmax of tile i+1 (one CTA per SM: the overlap has to come from inside the CTA).
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_BWD, 1)
     attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                          const AttnParams p) {
@@ -561,10 +563,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     return qt;
   };
 
-  if (warp == 4) {
+  if (warp == 8) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
     ptx::tmem_relinquish();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (ptx::elect_one()) {
       if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
       ptx::mbar_init(kv_full, 1);
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         ptx::mbar_init(&qdo_full[i], 1);
         ptx::mbar_init(&qdo_empty[i], 1);
         ptx::mbar_init(&sdp_full[i], 1);
-        ptx::mbar_init(&pds_full[i], 128);
+        ptx::mbar_init(&pds_full[i], 256);
         ptx::mbar_init(&pds_empty[i], 1);
       }
       ptx::mbar_init(done, 1);
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // TMEM columns: [S0 | dP0 | S1 | dP1 | dV^T | dK^T], 64 each
   const uint32_t t_dv = tmem + 256, t_dk = tmem + 320;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * L::KV_BYTES);
       load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKV, NB);
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         ++it;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, false, false);
       constexpr uint32_t idesc_t = ptx::make_idesc_bf16(HD, BKV, true, true);
@@ -662,8 +664,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
     }
   } else {
-    const int tid = threadIdx.x;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // two threads per TMEM lane: warp & 3 selects the 32 lanes, warp >> 2 the 32-column half of the 64-key tile
+    const int half = warp >> 2;
+    const int tid = (warp & 3) * 32 + (threadIdx.x & 31);
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int it = 0;
     for (int qt = i0; qt <= last_qt; qt = next_tile(qt)) {
       const int st = it & 1;
@@ -680,8 +684,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ptx::mbar_wait(&pds_empty[st], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P/dS buffer two slots ago are done
       ptx::mbar_wait(&sdp_full[st], (it >> 1) & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t s[32], dp[32];
         ptx::tmem_ld32(t_s + lane_off + half * 32, s);
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
@@ -700,8 +703,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     ptx::tc_fence_after();
     // thread == head-dim index; columns == keys
     const int nkeys = min(BKV, p.S - k0);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    {
       uint32_t tv[32], tk[32];
       ptx::tmem_ld32(t_dv + lane_off + half * 32, tv);
       ptx::tmem_ld32(t_dk + lane_off + half * 32, tk);
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, L::TMEM_COLS);
   }
@@ -847,9 +849,9 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
     once = true;
   }
   dim3 gq((a.S + BQ - 1) / BQ, a.H, a.N);
-  kdq<<<gq, NTHREADS, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  kdq<<<gq, NTHREADS_BWD, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
   dim3 gk((a.S + BKV - 1) / BKV, a.H, a.N);
-  kdkv<<<gk, NTHREADS, DkvSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  kdkv<<<gk, NTHREADS_BWD, DkvSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
   count_launch(3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
