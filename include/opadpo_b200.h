@@ -62,6 +62,8 @@ typedef struct opadpo_gemm_desc {
   const float* dlp;               /* EPI_CEGRAD: [M] */
   int32_t max_ctas;               /* 0 = one CTA per SM */
   int32_t cluster_mode;           /* 0 auto, 1 off, 2: 2-CTA cluster that multicasts the shared B tile, 3: CTA pair (tcgen05 cta_group::2, 256x256 MMA) */
+  const float* dent;              /* EPI_CEGRAD: d(loss)/d(entropy) [M] or NULL (opa_models/opa_trainer.py:63,82-85) */
+  const float* ent;               /* EPI_CEGRAD: per-row entropy [M], required with dent */
 } opadpo_gemm_desc;
 
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);
@@ -188,6 +190,10 @@ int opadpo_forward_logprobs(opadpo_engine* e, int32_t adapter, const float* imag
 /* d(loss)/d(logprobs) [K,b,R] f32 -> accumulates LoRA gradients into the flat bucket (autograd of rl_models.py:120
  * through the trainable adapter; rl_trainer.py:162). Releases the slot. */
 int opadpo_backward(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, void* stream);
+/* Same with a second incoming gradient d(loss)/d(entropies) [K,b,R] f32 (either pointer may be NULL, not both): the
+ * entropy output of opadpo_forward_logprobs is differentiable too, which is what OPA's entropy regulariser needs
+ * (opadpo/opa_models/opa_trainer.py:63,82-85,113-116; autograd through `entropies`). */
+int opadpo_backward_ent(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, const float* dentropies, void* stream);
 int opadpo_zero_grad(opadpo_engine* e, void* stream);
 /* clip_grad_norm_ (rl_trainer.py:165-168) + AdamW (utils/trainer_utils.py:9-38) over the flat bucket.
  * grad_scale multiplies the bucket first (1/world_size after a sum all-reduce). grad_norm_out: device f32 or NULL. */

@@ -53,6 +53,8 @@ class GemmDesc(ctypes.Structure):
         ("dlp", ctypes.c_void_p),
         ("max_ctas", ctypes.c_int32),
         ("cluster_mode", ctypes.c_int32),
+        ("dent", ctypes.c_void_p),
+        ("ent", ctypes.c_void_p),
     ]
 
 
@@ -115,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
     "opadpo_engine_set_option", "opadpo_engine_set_backward_callback", "opadpo_engine_layer_grad_range",
-    "opadpo_forward_logprobs", "opadpo_backward", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
+    "opadpo_forward_logprobs", "opadpo_backward", "opadpo_backward_ent", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
 ]
 
@@ -141,6 +143,7 @@ def _declare_engine(lib):
     lib.opadpo_forward_logprobs.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, c.POINTER(vp), i32, f32, vp, vp,
                                             i32, vp]
     lib.opadpo_backward.argtypes = [vp, i32, vp, vp]
+    lib.opadpo_backward_ent.argtypes = [vp, i32, vp, vp, vp]
     lib.opadpo_zero_grad.argtypes = [vp, vp]
     lib.opadpo_optimizer_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]
     lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, c.POINTER(Sampler), vp, vp]

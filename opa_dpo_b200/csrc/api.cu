@@ -25,7 +25,7 @@ using namespace opadpo;
 extern "C" {
 
 const char* opadpo_last_error(void) { return g_last_error; }
-int opadpo_abi_version(void) { return 2; }
+int opadpo_abi_version(void) { return 3; }
 int64_t opadpo_launch_count(void) { return g_launches.load(); }
 
 int opadpo_gemm_n_tiles(int32_t N) { return gemm_num_n_tiles(N); }
@@ -62,6 +62,8 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
   a.label_logit = d->label_logit;
   a.lse = d->lse;
   a.dlp = d->dlp;
+  a.dent = d->dent;
+  a.ent = d->ent;
   a.max_ctas = d->max_ctas;
   a.cluster = d->cluster_mode - 1;  /* 0 (zero-initialised desc) = auto, 1 off, 2 B-multicast cluster, 3 CTA pair */
   int rc = gemm_launch(a, static_cast<cudaStream_t>(stream));
@@ -243,7 +245,12 @@ int opadpo_forward_logprobs(opadpo_engine* e, int32_t adapter, const float* imag
 int opadpo_backward(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, void* stream) {
   ENGINE_GUARD(e);
   if (!dlogprobs) { set_error("opadpo_backward: null dlogprobs"); return OPADPO_EINVAL; }
-  return e->impl->backward(save_slot, dlogprobs, static_cast<cudaStream_t>(stream));
+  return e->impl->backward(save_slot, dlogprobs, nullptr, static_cast<cudaStream_t>(stream));
+}
+int opadpo_backward_ent(opadpo_engine* e, int32_t save_slot, const float* dlogprobs, const float* dentropies, void* stream) {
+  ENGINE_GUARD(e);
+  if (!dlogprobs && !dentropies) { set_error("opadpo_backward_ent: both gradients are null"); return OPADPO_EINVAL; }
+  return e->impl->backward(save_slot, dlogprobs, dentropies, static_cast<cudaStream_t>(stream));
 }
 int opadpo_zero_grad(opadpo_engine* e, void* stream) {
   ENGINE_GUARD(e);

@@ -431,7 +431,8 @@ __global__ void clip_drop_cls_kernel(const bf16* __restrict__ x, bf16* __restric
 // ---------------------------------------------------------------------------------------------- log-prob finalise
 __global__ void logprob_finalize_kernel(const float4* __restrict__ partials, int ntiles, const float* __restrict__ label_logit,
                                         const int32_t* __restrict__ labels, float* __restrict__ logprob,
-                                        float* __restrict__ entropy, float* __restrict__ lse_out, int64_t M) {
+                                        float* __restrict__ entropy, float* __restrict__ lse_out, float* __restrict__ ent_raw,
+                                        int64_t M) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= M) return;
   constexpr float LN2 = 0.6931471805599453f;
@@ -449,7 +450,9 @@ __global__ void logprob_finalize_kernel(const float4* __restrict__ partials, int
   const int label = labels[r];
   const bool ok = label >= 0;
   logprob[r] = ok ? (label_logit[r] - lse) : 0.f;
-  if (entropy) entropy[r] = ok ? (lse - (zs / s) * LN2) : 0.f;
+  const float h = lse - (zs / s) * LN2;
+  if (entropy) entropy[r] = ok ? h : 0.f;
+  if (ent_raw) ent_raw[r] = h;  // unmasked, kept for the entropy head's backward
   if (lse_out) lse_out[r] = lse;
 }
 
@@ -1190,9 +1193,10 @@ int clip_drop_cls(const bf16* x, bf16* out, int n, int P, int d, cudaStream_t s)
   return check_launch("clip_drop_cls");
 }
 int logprob_finalize(const float4* partials, int ntiles, const float* label_logit, const int32_t* labels, float* logprob,
-                     float* entropy, float* lse, int64_t M, cudaStream_t s) {
+                     float* entropy, float* lse, float* ent_raw, int64_t M, cudaStream_t s) {
   if (M == 0) return 0;
-  logprob_finalize_kernel<<<blocks_for(M, 128), 128, 0, s>>>(partials, ntiles, label_logit, labels, logprob, entropy, lse, M);
+  logprob_finalize_kernel<<<blocks_for(M, 128), 128, 0, s>>>(partials, ntiles, label_logit, labels, logprob, entropy, lse,
+                                                             ent_raw, M);
   return check_launch("logprob_finalize");
 }
 int dpo_pair_loss(const DpoPairArgs& a, cudaStream_t s) {

@@ -54,9 +54,10 @@ int clip_assemble(const bf16* patch_emb, const bf16* cls, const bf16* pos, bf16*
 int clip_drop_cls(const bf16* x, bf16* out, int n, int P, int d, cudaStream_t s);
 
 // Combine lm_head LSE partials (base-2 domain, see gemm.cu EPI_LSE): logprob = (label_logit - lse) * (label>=0),
-// entropy = (lse - E[z]) * (label>=0), lse saved for backward (all nullable except logprob).
+// entropy = (lse - E[z]) * (label>=0), lse and the unmasked entropy (ent_raw) saved for backward (all nullable except
+// logprob).
 int logprob_finalize(const float4* partials, int ntiles, const float* label_logit, const int32_t* labels, float* logprob,
-                     float* entropy, float* lse, int64_t M, cudaStream_t s);
+                     float* entropy, float* lse, float* ent_raw, int64_t M, cudaStream_t s);
 
 // One DPO pair (dpo_trainer.py:429-473 + anchor :702-712): per-token loss, gradient and reductions in one pass.
 struct DpoPairArgs {

@@ -849,10 +849,11 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   EN_CHECK(rmsnorm_fwd(x_final, final_norm, hn, NR, d, c.rms_eps, src_idx, s));
   const int ntiles = gemm_num_n_tiles(c.vocab);
   float4* partials;
-  float *label_logit, *lse_head;
+  float *label_logit, *lse_head, *ent_head = nullptr;
   EN_CHECK(pool_alloc(&partials, NR * ntiles, s, tmp));
   EN_CHECK(pool_alloc(&label_logit, NR, s, tmp));
   EN_CHECK(pool_alloc(&lse_head, NR, s, keep));
+  if (save) EN_CHECK(pool_alloc(&ent_head, NR, s, keep));
   cudaMemsetAsync(label_logit, 0, NR * sizeof(float), s);
   {
     GemmArgs a;
@@ -868,7 +869,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     a.label_logit = label_logit;
     EN_CHECK(gemm_checked(a, s));
   }
-  EN_CHECK(logprob_finalize(partials, ntiles, label_logit, labels, out_lp, out_ent, lse_head, NR, s));
+  EN_CHECK(logprob_finalize(partials, ntiles, label_logit, labels, out_lp, out_ent, lse_head, ent_head, NR, s));
 
   if (save) {
     cx->valid = true;
@@ -884,6 +885,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     cx->hn = hn;
     cx->labels = labels;
     cx->lse_head = lse_head;
+    cx->ent_head = ent_head;
     cx->kbits = kbits;
     cx->lay = lay;
     cx->src_idx = src_idx;
@@ -905,7 +907,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
+int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStream_t s) {
   const opadpo_config& c = cfg;
   if (save_slot < 0 || save_slot > 1 || !ctx[save_slot].valid) {
     set_error("backward: slot %d holds no saved forward", save_slot);
@@ -933,7 +935,8 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
   EN_CHECK(pool_alloc(&u, T * 3 * rr, s, tmp));
   EN_CHECK(pool_alloc(&delta, T * H, s, tmp));
 
-  {  // d logits = dlp/T * (onehot - softmax), recomputed tile-wise from the saved LSE (never stored in fp32)
+  {  // d logits = dlp/T * (onehot - softmax) [- dent/T * p (ln p + H)], recomputed tile-wise from the saved LSE (never stored
+     // in fp32)
     GemmArgs a;
     a.M = static_cast<int>(NR);
     a.N = c.vocab;
@@ -945,6 +948,8 @@ int Engine::backward(int save_slot, const float* dlp, cudaStream_t s) {
     a.labels = cx.labels;
     a.lse = cx.lse_head;
     a.dlp = dlp;
+    a.dent = dent;  // entropy head (OPA entropy regulariser); null for the DPO / SFT losses
+    a.ent = dent ? cx.ent_head : nullptr;
     a.C = dlogits;
     a.ldc = c.vocab;
     EN_CHECK(gemm_checked(a, s));

@@ -72,6 +72,7 @@ struct SaveCtx {
   bf16* hn = nullptr;       // normed response rows [N*R, d]
   int32_t* labels = nullptr;
   float* lse_head = nullptr;
+  float* ent_head = nullptr;  // unmasked per-row entropy of the head (backward of the entropy output)
   uint64_t* kbits = nullptr;
   SeqLayout lay;
   int32_t *src_idx = nullptr, *dst_idx = nullptr;  // response-predicting hidden rows (gather / gradient scatter)
@@ -102,7 +103,7 @@ class Engine {
   int forward_logprobs(int adapter, const float* images, int b, const int64_t* queries, const uint8_t* qmask,
                        const uint8_t* img_mask, int Q, int K, const int64_t* const* responses, int R, float temperature,
                        float* out_lp, float* out_ent, int save_slot, cudaStream_t s);
-  int backward(int save_slot, const float* dlogprobs, cudaStream_t s);
+  int backward(int save_slot, const float* dlogprobs, const float* dentropies, cudaStream_t s);
   int zero_grad(cudaStream_t s);
   int optimizer_step(float lr, float b1, float b2, float eps, float wd, float max_norm, float gscale, float* norm_out,
                      cudaStream_t s);

@@ -44,6 +44,8 @@ struct KParams {
   float* label_logit;
   const float* lse;
   const float* dlp;
+  const float* dent;  // EPI_CEGRAD: d(loss)/d(entropy) per row, or null
+  const float* ent;   // EPI_CEGRAD: the row's entropy (needed with dent)
 };
 
 struct Tile {
@@ -442,9 +444,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
         const int label = row_ok ? p.labels[row] : -1;
         // ignore_index rows carry no gradient (compute_logprobs, utils/common_utils.py:112-118)
-        const float g = (row_ok && label >= 0) ? p.dlp[row] * p.alpha : 0.f;
+        const bool live = row_ok && label >= 0;
+        const float g = (live && p.dlp) ? p.dlp[row] * p.alpha : 0.f;
+        // entropy head (OPA entropy regulariser, opa_models/opa_trainer.py:63,82-85): with H = -sum p ln p,
+        // dH/dz_v = -p_v (ln p_v + H); ge carries d(loss)/dH * alpha, hrow the row's H
+        const float ge = (live && p.dent) ? p.dent[row] * p.alpha : 0.f;
+        const float hrow = (ge != 0.f) ? p.ent[row] : 0.f;
+        const bool any = g != 0.f || ge != 0.f;
         const float lse2 = row_ok ? p.lse[row] * LOG2E : 0.f;
         const float a2 = p.alpha * LOG2E;
+        constexpr float LN2 = 0.6931471805599453f;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -453,10 +462,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int col0 = n0 + c * 32;
           if (row_ok && col0 < p.N) {
           float v[32];
+          if (ge == 0.f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pr = (g != 0.f) ? exp2f(__uint_as_float(r[j]) * a2 - lse2) : 0.f;
-            v[j] = g * ((col0 + j == label ? 1.f : 0.f) - pr);
+            for (int j = 0; j < 32; ++j) {
+              const float pr = any ? exp2f(__uint_as_float(r[j]) * a2 - lse2) : 0.f;
+              v[j] = g * ((col0 + j == label ? 1.f : 0.f) - pr);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float lp2 = __uint_as_float(r[j]) * a2 - lse2;  // log2 p_v
+              const float pr = exp2f(lp2);
+              v[j] = g * ((col0 + j == label ? 1.f : 0.f) - pr) - ge * pr * (lp2 * LN2 + hrow);
+            }
           }
           if (col0 + 32 <= p.N) {
             uint4* dst = reinterpret_cast<uint4*>(crow + col0);
@@ -719,6 +737,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.label_logit = a.label_logit;
   kp.lse = a.lse;
   kp.dlp = a.dlp;
+  kp.dent = a.dent;
+  kp.ent = a.ent;
 
   int grid = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;

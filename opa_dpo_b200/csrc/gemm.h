@@ -20,7 +20,7 @@ enum GemmEpilogue : int {
   EPI_BF16 = 0,      // C bf16 = act(alpha*acc + bias) + residual
   EPI_F32_ATOMIC = 1,  // C f32 += alpha*acc  (red.global.add; split-K capable)  -- LoRA wgrad into the grad bucket
   EPI_LSE = 2,       // fused lm_head log-sum-exp partials + label-logit gather (never materialises logits)
-  EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - exp(alpha*acc - lse[m]))  (CE backward tile)
+  EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - p) - dent[m]*alpha*p*(ln p + ent[m]),  p = exp(alpha*acc - lse[m])
   EPI_F32_PARTIAL = 4,  // C f32 [splits, M, ldc]: plain per-split stores (decode: weight streaming fills all SMs, fixed-order reduce)
 };
 
@@ -52,7 +52,9 @@ struct GemmArgs {
   float4* lse_partials = nullptr;   // [M, ceil(N/256)] (max, sumexp, sum z*exp, -)
   float* label_logit = nullptr;     // [M]
   const float* lse = nullptr;       // [M]
-  const float* dlp = nullptr;       // [M]
+  const float* dlp = nullptr;       // [M] (may be null when only dent is given)
+  const float* dent = nullptr;      // EPI_CEGRAD: d(loss)/d(entropy) [M] or null; adds -dent*alpha*p_v*(ln p_v + ent)
+  const float* ent = nullptr;       // EPI_CEGRAD: entropy of each row [M] (required with dent)
   int max_ctas = 0;                 // 0 = all SMs
   int cluster = -1;                 // -1 auto, 0 off, 1 B-multicast 2-CTA cluster, 2 CTA pair (cta_group::2 MMA, K-major A)
 };

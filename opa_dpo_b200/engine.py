@@ -237,9 +237,17 @@ class Engine:
             None if ent is None else ent.data_ptr(), save_slot, _stream()), "opadpo_forward_logprobs")
         return lp, ent
 
-    def backward(self, save_slot: int, dlogprobs: torch.Tensor):
-        d = dlogprobs.to(self.device, torch.float32).contiguous()
-        _lib.check(self.lib.opadpo_backward(self._h, save_slot, d.data_ptr(), _stream()), "opadpo_backward")
+    def backward(self, save_slot: int, dlogprobs: Optional[torch.Tensor], dentropies: Optional[torch.Tensor] = None):
+        """d(loss)/d(logprobs) and/or d(loss)/d(entropies), both [K,b,R] -> LoRA gradients (accumulated)."""
+        d = None if dlogprobs is None else dlogprobs.to(self.device, torch.float32).contiguous()
+        if dentropies is None:
+            if d is None:
+                raise OpadpoError("backward: no incoming gradient")
+            _lib.check(self.lib.opadpo_backward(self._h, save_slot, d.data_ptr(), _stream()), "opadpo_backward")
+            return
+        g = dentropies.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.opadpo_backward_ent(self._h, save_slot, None if d is None else d.data_ptr(), g.data_ptr(),
+                                                _stream()), "opadpo_backward_ent")
 
     def zero_grad(self):
         _lib.check(self.lib.opadpo_zero_grad(self._h, _stream()), "opadpo_zero_grad")

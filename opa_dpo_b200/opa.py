@@ -1,15 +1,20 @@
 """OPA stage (LoRA-SFT) loss on the same engine — row f-1 of the scope table.
 
 The reference trains OPA with HF Trainer over LlavaLlamaForCausalLM's own `loss` (opadpo/opa_train.py:543-548,
-opa_models/opa_trainer.py:58-125 with entropy_loss off): mean cross-entropy over every labelled (non IGNORE_INDEX)
-position of the batch, labels = the response tokens (prompt masked, utils/data_utils_sft.py:20-69). With the policy
-forward returning per-token log-probs of the response tokens, that loss is  -(sum of log-probs over valid tokens) /
-(number of valid tokens); its backward is the engine's LoRA backward with d(logprob) = -1/count at valid tokens.
-(The optional entropy regulariser needs d(entropy)/d(theta), which the fused lm_head epilogue does not produce: next.)
+opa_models/opa_trainer.py:58-125): mean cross-entropy over every labelled (non IGNORE_INDEX) position of the batch,
+labels = the response tokens (prompt masked, utils/data_utils_sft.py:20-69). With the policy forward returning
+per-token log-probs of the response tokens, that loss is  -(sum of log-probs over valid tokens) / (number of valid
+tokens); its backward is the engine's LoRA backward with d(logprob) = -1/count at valid tokens.
+
+The optional entropy regulariser (opa_trainer.py:63-87,113-116) runs a second forward on masked images (or with holes in
+the image attention mask) and adds  coef * mean_rows( -sum((H_masked - H) * mask) / sum(mask) ); both forwards stay in
+the autograd graph, so the gradient flows through the entropies of both — the engine's fused lm_head backward takes
+d(loss)/d(entropy) next to d(loss)/d(logprob) (`opadpo_backward_ent`), and the two forwards occupy its two save slots.
 """
 from __future__ import annotations
 
-from typing import Dict, Sequence
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -30,18 +35,68 @@ def sft_loss(outputs: Dict[str, Tensor], responses: Dict[str, Tensor], pad_token
     return total / count.clamp(min=1)
 
 
+def entropy_loss(outputs: Dict[str, Tensor], masked_outputs: Dict[str, Tensor], responses: Dict[str, Tensor],
+                 pad_token_id: int = 0) -> Tensor:
+    """opa_trainer.py:82-86: per row -sum((H_masked - H) * mask) / sum(mask) with mask = labelled positions, then the
+    mean over rows (a row without labelled tokens gives nan there too). One response name per row set; with several
+    names their rows are concatenated, which is what a batch of that many samples is to the reference."""
+    rows = []
+    for name, ids in responses.items():
+        h, hm = outputs[name + "_entropies"], masked_outputs[name + "_entropies"]
+        mask = (ids.to(h.device) != pad_token_id).to(h.dtype)
+        rows.append(-((hm - h) * mask).sum(-1) / mask.sum(-1))
+    return torch.cat(rows).mean()
+
+
+@dataclass
+class OPAArgs:
+    """Loss-relevant TrainingArguments of the OPA stage (opa_train.py:144-163; run/train_opa.sh)."""
+    entropy_loss: bool = False
+    entropy_loss_coef: float = 0.1
+    entropy_decay_coef: float = 1.0
+    entropy_mask_method: str = "random"   # random | blockwise (masked images) | attention (holes in the image mask)
+    entropy_mask_ratio: float = 0.3
+    temperature: float = 1.0
+
+
 class OPAStepper:
-    """One LoRA-SFT optimisation step: policy forward over the given responses -> token-mean NLL -> LoRA backward ->
-    [all-reduce] -> clip + AdamW (what LLaVATrainer.training_step + optimizer.step do for the OPA stage)."""
+    """One LoRA-SFT optimisation step: policy forward over the given responses -> token-mean NLL [+ entropy regulariser
+    over a second, image-masked forward] -> LoRA backward -> [all-reduce] -> clip + AdamW (what
+    LLaVATrainer.compute_loss / training_step + optimizer.step do for the OPA stage)."""
 
-    def __init__(self, policy, optimizer, temperature: float = 1.0, pad_token_id: int = 0):
+    def __init__(self, policy, optimizer, temperature: float = 1.0, pad_token_id: int = 0, args: Optional[OPAArgs] = None):
         self.policy, self.opt, self.temperature, self.pad = policy, optimizer, temperature, pad_token_id
+        self.args = args or OPAArgs(temperature=temperature)
 
-    def step(self, images: Tensor, queries: Tensor, queries_attn_masks: Tensor, responses: Dict[str, Tensor],
-             grad_scale: float = 1.0):
-        self.policy.train()
+    def compute_loss(self, images: Tensor, queries: Tensor, queries_attn_masks: Tensor, responses: Dict[str, Tensor],
+                     masked_images: Optional[Tensor] = None, masked_attn_masks: Optional[Tensor] = None
+                     ) -> Tuple[Tensor, Dict[str, float]]:
+        """opa_trainer.py:58-125. `masked_images` (random / blockwise) or `masked_attn_masks` (the [b, P + Q] mask with the
+        image part prepended, 'attention') is the second forward's input when args.entropy_loss is on."""
+        a = self.args
         out = self.policy(images, queries, queries_attn_masks, temperature=self.temperature, **responses)
         loss = sft_loss(out, responses, self.pad)
+        logs = {"base_sft_loss": loss.detach(), "mask_sft_loss": 0.0, "entropy_loss": 0.0}
+        if a.entropy_loss:
+            if a.entropy_mask_method == "attention":
+                if masked_attn_masks is None:
+                    raise ValueError("entropy_mask_method='attention' needs masked_attn_masks")
+                out_m = self.policy(images, queries, masked_attn_masks, temperature=self.temperature, **responses)
+            else:
+                if masked_images is None:
+                    raise ValueError("entropy_loss needs masked_images")
+                out_m = self.policy(masked_images, queries, queries_attn_masks, temperature=self.temperature, **responses)
+            ent = entropy_loss(out, out_m, responses, self.pad)
+            logs["mask_sft_loss"] = sft_loss(out_m, responses, self.pad).detach()
+            logs["entropy_loss"] = ent.detach()
+            a.entropy_loss_coef *= a.entropy_decay_coef           # decays before use (opa_trainer.py:114)
+            loss = loss + ent * a.entropy_loss_coef
+        return loss, logs
+
+    def step(self, images: Tensor, queries: Tensor, queries_attn_masks: Tensor, responses: Dict[str, Tensor],
+             grad_scale: float = 1.0, masked_images: Optional[Tensor] = None, masked_attn_masks: Optional[Tensor] = None):
+        self.policy.train()
+        loss, _ = self.compute_loss(images, queries, queries_attn_masks, responses, masked_images, masked_attn_masks)
         loss.backward()
         norm = self.opt.step(grad_scale)
         self.opt.zero_grad()

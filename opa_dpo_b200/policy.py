@@ -34,12 +34,16 @@ class _PolicyForward(torch.autograd.Function):
         lp, ent = model.engine.forward_logprobs(adapter, images, queries, qmask, list(responses), temperature,
                                                 img_mask=img_mask, save_slot=slot, want_entropy=True)
         ctx.model, ctx.slot, ctx.n_in = model, slot, 9 + len(responses)
-        ctx.mark_non_differentiable(ent)
+        ctx.out_shape = tuple(lp.shape)
+        ctx.set_materialize_grads(False)   # an unused output arrives as None instead of a zero tensor
         return lp, ent
 
     @staticmethod
-    def backward(ctx, dlp, _dent):
-        ctx.model.engine.backward(ctx.slot, dlp)
+    def backward(ctx, dlp, dent):
+        # the entropies are differentiable too (OPA's entropy regulariser, opa_models/opa_trainer.py:63,82-85)
+        if dlp is None and dent is None:   # nothing flows back: still run the backward so the slot is released
+            dlp = torch.zeros(ctx.out_shape, device=ctx.model.engine.device)
+        ctx.model.engine.backward(ctx.slot, dlp, dent)
         ctx.model._slot_busy[ctx.slot] = False
         return (None,) * ctx.n_in
 

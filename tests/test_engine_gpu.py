@@ -453,3 +453,88 @@ def test_opa_sft_loss_and_grads_vs_oracle():
             cos = torch.nn.functional.cosine_similarity(gg.flatten(), t.grad.flatten(), dim=0).item()
             assert cos >= 0.99, (m, cos)
     model.engine.close()
+
+
+def test_opa_entropy_regulariser_loss_and_grads_vs_oracle():
+    """OPA stage with entropy_loss on (opa_trainer.py:58-125): base forward + a second forward on masked images, loss =
+    sft + coef * mean_rows(-sum((H_masked - H) * mask) / sum(mask)); the gradient flows through the entropies of BOTH
+    forwards (two engine save slots, opadpo_backward_ent). Loss and LoRA gradients vs the oracle's logits + autograd.
+    lm_head is scaled x8 so the entropies sit well below ln(vocab) and differ between the two forwards (with N(0, 0.02^2)
+    logits the regulariser is ~1e-4 and would test nothing); tolerances: entropy term 0.02 absolute, loss 1e-2 relative
+    (bf16 logits of magnitude ~5), gradients cosine >= 0.99 and relative L2 <= 0.1."""
+    from types import SimpleNamespace
+    import torch.nn.functional as F
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.opa import OPAArgs, OPAStepper
+    from opa_dpo_b200.dpo import DPOArgs
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc, peaked=8.0)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.make_trainable("lora_policy")
+    R, coef = 24, 0.5
+    policy = AutoregressivePolicy(DPOArgs(response_len=R), model, SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, R, ["standard_response"], left_pad=2)
+    masked = images.clone()
+    masked[:, :, ::3, ::2] = images.mean()          # any masked copy of the images serves (the masking itself is f-3)
+    lpg = {m: (A.clone().requires_grad_("vision_model" not in m), B.clone().requires_grad_("vision_model" not in m)) for m, (A, B) in lp.items()}
+    ids = torch.cat([q, resp["standard_response"]], 1)
+    mask = torch.cat([qm.bool(), resp["standard_response"] != 0], 1)
+    labels = resp["standard_response"].clone()
+    labels[labels == 0] = -100
+    valid = (labels != -100).float()
+    mods = ("model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.mm_projector.2")
+
+    def ref_pass(img):
+        logits = O.llava_logits(oc, w, lpg, ids, mask, img)[:, -R - 1:-1]
+        ls = torch.log_softmax(logits, -1)
+        return F.cross_entropy(logits.reshape(-1, oc.vocab), labels.reshape(-1), ignore_index=-100), -(ls.exp() * ls).sum(-1)
+
+    def check_grads(cos_min, rel_max, what):
+        torch.cuda.synchronize()
+        g = model.engine.buffers()["grad"]
+        for m in mods:
+            oa, ob = model.engine.lora_offsets(m)
+            for t, off in ((lpg[m][0], oa), (lpg[m][1], ob)):
+                gg = g[off:off + t.numel()].view_as(t).cpu()
+                cos = torch.nn.functional.cosine_similarity(gg.flatten(), t.grad.flatten(), dim=0).item()
+                rel = ((gg - t.grad).norm() / t.grad.norm()).item()
+                assert cos >= cos_min and rel <= rel_max, (what, m, cos, rel)
+
+    # (1) the entropy head alone, one forward: loss = sum(wts * H) with random per-token weights
+    gen = torch.Generator().manual_seed(5)
+    wts = torch.randn(3, R, generator=gen) * valid
+    _, h_ref = ref_pass(images)
+    (wts * h_ref).sum().backward()
+    policy.train()
+    model.engine.zero_grad()
+    out = policy(images, q, qm, **resp)
+    h = out["standard_response_entropies"]
+    assert ((h.detach().cpu() - h_ref.detach() * valid).abs().max().item()) <= 0.08
+    (wts.to(h.device) * h).sum().backward()
+    check_grads(0.99, 0.1, "entropy head")
+    assert model._slot_busy == [False, False]
+
+    # (2) the full regularised OPA loss: two forwards, both differentiated
+    for a, b in lpg.values():
+        a.grad = None
+        b.grad = None
+    sft_ref, h_ref = ref_pass(images)
+    _, hm_ref = ref_pass(masked)
+    ent_ref = (-((hm_ref - h_ref) * valid).sum(-1) / valid.sum(-1)).mean()
+    loss_ref = sft_ref + coef * ent_ref
+    loss_ref.backward()
+    stepper = OPAStepper(policy, None, args=OPAArgs(entropy_loss=True, entropy_loss_coef=coef, entropy_decay_coef=1.0))
+    model.engine.zero_grad()
+    loss, logs = stepper.compute_loss(images, q, qm, resp, masked_images=masked)
+    assert abs(logs["entropy_loss"].item() - ent_ref.item()) <= 0.02, (logs["entropy_loss"].item(), ent_ref.item())
+    assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    loss.backward()
+    check_grads(0.99, 0.1, "sft + entropy regulariser")
+    assert model._slot_busy == [False, False]
+    model.engine.close()

@@ -143,6 +143,27 @@ def test_gemm_lse_and_cegrad():
     onehot[valid, labels[valid].long()] = 1.0
     refG = dlp[:, None] * (onehot - lsm.exp()) / T
     _close(G, refG, what="cegrad")
+    # entropy head: d(sum_m dent[m] * H_m)/d(logits) next to the log-prob gradient (opa_trainer.py:63,82-85), vs autograd
+    dent = torch.randn((M,), device="cuda", dtype=torch.float32) * valid
+    dent[::5] = 0.0
+    hw = (h.float() @ W.float().t()).requires_grad_(True)
+    lsm2 = torch.log_softmax(hw / T, -1)
+    H = -(lsm2.exp() * lsm2).sum(-1)
+    lp_lab = lsm2.gather(1, labels.clamp(min=0).long()[:, None])[:, 0]
+    ((dent * H).sum() + (dlp * lp_lab * valid).sum()).backward()
+    G2 = torch.full((M, V), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(h, W, G2, epilogue=ops.EPI_CEGRAD, alpha=1.0 / T, labels=labels, lse=lse.contiguous(), dlp=dlp, dent=dent,
+             ent=ent.contiguous())
+    torch.cuda.synchronize()
+    _close(G2, hw.grad, what="cegrad+entropy")
+    G3 = torch.full((M, V), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(h, W, G3, epilogue=ops.EPI_CEGRAD, alpha=1.0 / T, labels=labels, lse=lse.contiguous(), dent=dent,
+             ent=ent.contiguous())   # entropy gradient alone (dlp = NULL)
+    torch.cuda.synchronize()
+    hw.grad = None
+    lsm3 = torch.log_softmax(hw / T, -1)
+    (dent * -(lsm3.exp() * lsm3).sum(-1)).sum().backward()
+    _close(G3, hw.grad, what="entropy only")
 
 
 @pytest.mark.parametrize("mode", [1, 2])
