@@ -166,7 +166,11 @@ int opadpo_engine_buffers(opadpo_engine* e, float** master, float** grad, float*
 /* Where module's A [groups*r... see DESIGN.md] and B live inside the flat bucket (element offsets). */
 int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* offA, int64_t* offB);
 /* Engine options. "share_prefix" (default 1): compute the image+query prefix once per sample and let its K responses
- * attend to it through the segment mask (identical results to the reference's K stacked rows, fewer FLOPs). */
+ * attend to it through the segment mask (identical results to the reference's K stacked rows, fewer FLOPs).
+ * "merge_frozen" (default 0): inference forwards (save_slot = -1) and rollouts of a NON-trainable adapter run on decoder
+ * weights merged once, W' = W + (alpha/r) B A (peft merge_adapter semantics; bf16 W'), so the reference pass of the DPO
+ * step carries no LoRA GEMMs; costs one extra copy of the decoder weights, rebuilt when that adapter is reloaded.
+ * "merge_rollout" (default 1): rollouts merge the adapter per call. "adam_step": optimizer-state restore. */
 int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 /* Communication overlap: `cb(layer, user)` is called on the host thread inside opadpo_backward right after the backward
  * kernels of decoder layer `layer` (n_layers-1 .. 0), then of the projector (layer == n_layers), have been enqueued; the

@@ -69,6 +69,7 @@ Engine::Engine(const opadpo_config& c) : cfg(c) {}
 Engine::~Engine() {
   cudaDeviceSynchronize();
   for (int i = 0; i < 2; ++i) release_slot(i, nullptr);
+  drop_frozen_merged();
   for (void* p : allocs) cudaFree(p);
   cudaDeviceSynchronize();
 }
@@ -259,6 +260,7 @@ int Engine::copy_in(bf16* dst, const void* src, int dtype, int64_t n, cudaStream
 int Engine::load_tensor(const char* name, const void* src, int dtype, int64_t rows, int64_t cols, cudaStream_t s) {
   const std::string n(name);
   const opadpo_config& c = cfg;
+  drop_frozen_merged();  // base weights change under any merged copy
   auto expect = [&](int64_t er, int64_t ec) -> int {
     if (rows != er || cols != ec) {
       set_error("load_tensor(%s): shape [%lld,%lld], expected [%lld,%lld]", name, (long long)rows, (long long)cols,
@@ -382,6 +384,7 @@ int Engine::load_lora(int adapter, const char* module, const void* A, const void
   EN_CHECK(lora_offsets(module, &oa, &ob));
   EN_CHECK(lora_shape(module, &in_f, &out_f));
   Adapter& ad = adapters[adapter];
+  if (frozen_merged_adapter == adapter) drop_frozen_merged();  // the merged copy is stale
   EN_CHECK(copy_in(ad.shadow + oa, A, dtype, static_cast<int64_t>(r) * in_f, s));
   EN_CHECK(copy_in(ad.shadow + ob, B, dtype, out_f * r, s));
   if (ad.trainable) {
@@ -422,6 +425,7 @@ int Engine::set_trainable(int adapter) {
   }
   Adapter& ad = adapters[adapter];
   if (ad.trainable) return 0;
+  if (frozen_merged_adapter == adapter) drop_frozen_merged();
   if (trainable_adapter >= 0) {
     set_error("adapter %d is already the trainable one", trainable_adapter);
     return OPADPO_ESTATE;
@@ -811,6 +815,14 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
   lay.pos = pos;
   lay.kbits = kbits;
 
+  // decoder weights of this pass: a frozen adapter's inference forward may run on the merged copy (no LoRA GEMMs)
+  const std::vector<LlamaLayer>* LL = &layers;
+  int llm_adapter = adapter;
+  if (!save && merge_frozen && adapter >= 0 && r > 0 && !adapters[adapter].trainable && c.n_layers > 0) {
+    EN_CHECK(ensure_frozen_merged(adapter, s));
+    LL = &frozen_merged;
+    llm_adapter = -1;
+  }
   bf16* x_final = nullptr;
   if (save) {
     cx->layers.resize(c.n_layers);
@@ -835,7 +847,7 @@ int Engine::forward_logprobs(int adapter, const float* images, int b, const int6
     bf16* nxt = x1buf;
     for (int l = 0; l < c.n_layers; ++l) {
       sc.x = cur;
-      EN_CHECK(llama_layer_fwd(layers[l], adapter, lay, sc, nxt, s));
+      EN_CHECK(llama_layer_fwd((*LL)[l], llm_adapter, lay, sc, nxt, s));
       bf16* t = cur;
       cur = nxt;
       nxt = t;
@@ -1065,7 +1077,33 @@ int Engine::merge_lora(int adapter, std::vector<LlamaLayer>* merged, std::vector
   return 0;
 }
 
+void Engine::drop_frozen_merged() {
+  if (frozen_merged_allocs.empty() && frozen_merged_adapter < 0) return;
+  cudaDeviceSynchronize();
+  for (void* p : frozen_merged_allocs) cudaFree(p);
+  frozen_merged_allocs.clear();
+  frozen_merged.clear();
+  frozen_merged_adapter = -1;
+}
+
+int Engine::ensure_frozen_merged(int adapter, cudaStream_t s) {
+  if (frozen_merged_adapter == adapter) return 0;
+  drop_frozen_merged();
+  int rc = merge_lora(adapter, &frozen_merged, &frozen_merged_allocs, s);
+  if (rc != 0) {
+    drop_frozen_merged();
+    return rc;
+  }
+  frozen_merged_adapter = adapter;
+  return 0;
+}
+
 int Engine::set_option(const char* name, int64_t value) {
+  if (strcmp(name, "merge_frozen") == 0) {
+    merge_frozen = value != 0;
+    if (!merge_frozen) drop_frozen_merged();
+    return 0;
+  }
   if (strcmp(name, "share_prefix") == 0) {
     share_prefix = value != 0;
     return 0;
@@ -1167,8 +1205,13 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   const std::vector<LlamaLayer>* LL = &layers;
   int llm_adapter = adapter;
   if (adapter >= 0 && r > 0 && merge_rollout) {
-    EN_CHECK(merge_lora(adapter, &merged, tmp, s));
-    LL = &merged;
+    if (merge_frozen && !adapters[adapter].trainable) {  // a frozen adapter's merged copy is cached across calls
+      EN_CHECK(ensure_frozen_merged(adapter, s));
+      LL = &frozen_merged;
+    } else {
+      EN_CHECK(merge_lora(adapter, &merged, tmp, s));
+      LL = &merged;
+    }
     llm_adapter = -1;
   }
 

@@ -119,6 +119,15 @@ class Engine {
   float lora_scale = 1.f;
   bool share_prefix = true;  // compute the image+query prefix once per sample for its K responses
   bool merge_rollout = true;  // rollout runs on W + (alpha/r) B A merged once per generate() call
+  // Inference forwards of a FROZEN adapter (the reference pass of the DPO step, dpo_trainer.py:333-335) run on decoder
+  // weights merged once, W' = W + (alpha/r) B A (what peft's merge_adapter does), so they carry no LoRA GEMMs at all.
+  // The cache is rebuilt when that adapter's tensors are reloaded. Costs one extra copy of the decoder weights.
+  bool merge_frozen = false;
+  int frozen_merged_adapter = -1;
+  std::vector<LlamaLayer> frozen_merged;
+  std::vector<void*> frozen_merged_allocs;
+  void drop_frozen_merged();
+  int ensure_frozen_merged(int adapter, cudaStream_t s);
   opadpo_layer_cb layer_cb = nullptr;  // host callback after each layer's backward kernels are enqueued (comm overlap)
   void* layer_cb_user = nullptr;
   // base weights

@@ -538,3 +538,48 @@ def test_opa_entropy_regulariser_loss_and_grads_vs_oracle():
     check_grads(0.99, 0.1, "sft + entropy regulariser")
     assert model._slot_busy == [False, False]
     model.engine.close()
+
+
+@pytest.mark.parametrize("share", [0, 1])
+def test_reference_pass_on_merged_frozen_adapter(share):
+    """Option merge_frozen: the frozen reference adapter's inference forward runs on W' = W + (alpha/r) B A merged once
+    (no LoRA GEMMs). Same tolerances vs the oracle as the unmerged pass; the DPO loss built on it stays within 1e-3; the
+    merged copy is rebuilt when the adapter is reloaded; the trainable adapter is never merged."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, REF
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, share_prefix=share)
+    eng.set_option("merge_frozen", 1)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    ref_o = O.policy_forward(oc, w, lr, images, q, qm, resp)
+    pol_o = O.policy_forward(oc, w, lp, images, q, qm, resp)
+    ref_lp, ref_ent = eng.forward_logprobs(REF, *args)
+    ref_lp2, _ = eng.forward_logprobs(REF, *args)               # second call reuses the cached merged weights
+    pol_lp, _ = eng.forward_logprobs(POLICY, *args)             # trainable adapter: unmerged path
+    torch.cuda.synchronize()
+    assert torch.equal(ref_lp, ref_lp2)
+    for i, n in enumerate(NAMES2):
+        _cmp_lp(ref_lp[i], ref_o[n + "_logprobs"], f"merged ref {n} logprobs")
+        _cmp_lp(ref_ent[i], ref_o[n + "_entropies"], f"merged ref {n} entropies")
+        _cmp_lp(pol_lp[i], pol_o[n + "_logprobs"], f"policy {n} logprobs")
+    loss_o, _, _ = O.pair_loss(O.LossConfig(beta=0.1), pol_o[NAMES2[0] + "_logprobs"], pol_o[NAMES2[1] + "_logprobs"],
+                               ref_o[NAMES2[0] + "_logprobs"], ref_o[NAMES2[1] + "_logprobs"])
+    total, _ = FusedDPO(DPOArgs(beta=0.1)).pair(pol_lp[0], pol_lp[1], ref_lp[0], ref_lp[1])
+    rel = abs(total.item() - loss_o.item()) / abs(loss_o.item())
+    assert rel <= 1e-3, f"DPO loss on the merged reference pass: {total.item():.6f} vs {loss_o.item():.6f} (rel {rel:.3g})"
+    # the unmerged pass of the same adapter agrees to bf16 noise
+    eng.set_option("merge_frozen", 0)
+    ref_lp_unmerged, _ = eng.forward_logprobs(REF, *args)
+    assert (ref_lp_unmerged - ref_lp).abs().max().item() <= 0.05
+    # reloading the adapter invalidates the merged copy: load the POLICY tensors into the REF slot
+    eng.set_option("merge_frozen", 1)
+    eng.forward_logprobs(REF, *args)
+    eng.load_adapter(REF, lp)
+    swapped, _ = eng.forward_logprobs(REF, *args)
+    torch.cuda.synchronize()
+    for i, n in enumerate(NAMES2):
+        _cmp_lp(swapped[i], pol_o[n + "_logprobs"], f"reloaded+remerged {n} logprobs")
+    eng.close()
