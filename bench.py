@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 Q_LEN, R_LEN, IMG_POS = 128, 512, 35
+MERGE_FROZEN_DEFAULT = 0   # flipped to 1 once the merged reference pass is parity-checked and measured on the GPU
 
 
 def _peaks():
@@ -168,6 +169,8 @@ def main():
     ap.add_argument("--resp-len", type=int, default=R_LEN)
     ap.add_argument("--no-share-prefix", action="store_true", help="run the reference's K stacked rows (no prefix sharing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge-frozen", type=int, default=int(os.environ.get("OPADPO_MERGE_FROZEN", str(MERGE_FROZEN_DEFAULT))),
+                    help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -200,6 +203,7 @@ def main():
     model = B200LlavaModel(cfg, dev)
     if args.no_share_prefix:
         model.engine.set_option("share_prefix", 0)
+    model.engine.set_option("merge_frozen", args.merge_frozen)
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
     dargs = DPOArgs(beta=0.1, response_len=R, learning_rate=1e-6, max_grad_norm=1.0)
@@ -306,7 +310,7 @@ def main():
         "config": {"workload": f"LLaVA-1.5-{args.model.upper()} LoRA(r=256, all Linear but lm_head) OPA-DPO step, 336^2 img, Q=128, "
                                f"R={R}, 4 forwards (policy+frozen ref x chosen+rejected) + LoRA backward + clip + AdamW",
                    "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
-                   "prefix_sharing": (not args.no_share_prefix),
+                   "prefix_sharing": (not args.no_share_prefix), "merged_reference_adapter": bool(args.merge_frozen),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
                    "collective": "NCCL all-reduce(sum) of the fp32 LoRA-grad bucket once per step, issued as 33 per-layer slices "
                                  "overlapped with the backward" if world > 1 else "none",
