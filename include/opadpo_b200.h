@@ -123,6 +123,55 @@ typedef struct opadpo_dpo_pair_desc {
 int opadpo_op_dpo_pair(const opadpo_dpo_pair_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Operator level: the collator stage — what the reference does on the CPU between the tokenizer /
+ * image decoder and the policy forward. Tokenisation, JSON parsing and JPEG decoding stay with the caller; everything
+ * after them runs here. Integer / byte work: results are bit-identical to the reference's.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Raw tokenizer output (input_ids INCLUDING the leading BOS) of every `copied content` / `rewritten content` entry of a
+ * batch of GPT-4V reports, flattened (DataCollatorForCausalLM.__call__, utils/data_utils_dpo.py:139-199). All device. */
+typedef struct opadpo_segments {
+  const int32_t* tokens;      /* [seg_offsets[n_segments]] */
+  const int64_t* seg_offsets; /* [n_segments + 1] */
+  const float* seg_score;     /* [n_segments] score_mapping weight (data_utils_dpo.py:32-37), or NULL */
+  const float* seg_relation;  /* [n_segments] error_type_mapping weight (:38-42), or NULL */
+  const uint8_t* seg_flags;   /* [n_segments] OPADPO_SEG_* */
+  const int64_t* row_offsets; /* [b + 1]: segments of row i are [row_offsets[i], row_offsets[i+1]) in report-key order */
+  int32_t b;
+} opadpo_segments;
+enum { OPADPO_SEG_KEEP_BOS = 1,     /* entry of the FIRST report key: its BOS stays (`count == 0`, :170,183) */
+       OPADPO_SEG_STRIP_SPACE = 2   /* copied entry: a leading 29871 piece is dropped (:186-187) */ };
+enum { OPADPO_COLLATE_ADD_EOS = 1,  /* add_eos (:73-87): the first pad position becomes EOS */
+       OPADPO_COLLATE_PAD_EOS = 2,  /* pad_eos (:89-99): the EOS position inherits the previous position's weight (1 if 0) */
+       OPADPO_COLLATE_TRUNCATE = 4  /* tokenizer truncation (plain branch :120-137); without it a row longer than R sets
+                                       overflow[row], which is where the reference raises and falls back (:259-278) */ };
+/* -> ids int64 [b,R] right-padded; attn_mask u8 [b,R] (ids != pad), scores / relations f32 [b,R] (0 at pads), overflow
+ * i32 [b]: each nullable. Replaces pad_and_stack / add_eos / pad_eos and the torch.cat chain of :200-235. */
+int opadpo_op_collate_responses(const opadpo_segments* s, int32_t R, int32_t pad_id, int32_t eos_id, int32_t mode,
+                                int64_t* ids, uint8_t* attn_mask, float* scores, float* relations, int32_t* overflow,
+                                void* stream);
+/* Ragged query tokens (device: tokens i32, offsets i64 [b+1]) -> left-padded, right-truncated ids int64 [b,Q] with
+ * placeholder_id (30861) replaced by image_token (-200), and the attention mask u8 [b,Q] (data_utils_dpo.py:118-121). */
+int opadpo_op_collate_queries(const int32_t* tokens, const int64_t* offsets, int32_t b, int32_t Q, int32_t pad_id,
+                              int32_t placeholder_id, int32_t image_token, int64_t* ids, uint8_t* attn_mask, void* stream);
+/* CoPO image masks (mask_single_image, opadpo/dpo_models/dpo_trainer.py:83-109): out [n,C,H,W] f32 = images with, per
+ * image, the pixels (block = 1, 'random') or block x block tiles (block = 14, 'blockwise') listed in idx int64 [n,m]
+ * (the caller's torch.randperm prefix, so the random stream stays the reference's) set to that image's mean in every
+ * channel. bf16_pixels != 0: pixels and mean are rounded to bf16 first (the trainer masks bf16 images, :283-286).
+ * means_out f32 [n] nullable. out may alias images. */
+int opadpo_op_mask_images(const float* images, float* out, int32_t n, int32_t C, int32_t H, int32_t W, const int64_t* idx,
+                          int32_t m, int32_t block, int32_t bf16_pixels, float* means_out, void* stream);
+/* CoPO 'attention' (mask_percentage_per_row, dpo_trainer.py:119-125): out u8 [n,P] = 1, 0 at idx int64 [n,m]. */
+int opadpo_op_attention_holes(uint8_t* out, const int64_t* idx, int32_t n, int32_t P, int32_t m, void* stream);
+/* DPO_Dataset.__getitem__ image path (utils/data_utils_dpo.py:311-335): decoded uint8 RGB images [H_i, W_i, 3]
+ * concatenated in DEVICE memory at byte offsets h_offsets (HOST int64 [n]; heights / widths HOST int32 [n]) ->
+ * expand2square on the background colour bg3 (HOST u8[3]; NULL = int(mean*255)) when pad_to_square, Pillow bicubic
+ * resize of the shortest edge to S (two 8-bit passes with 22-bit fixed-point coefficients), centre crop SxS, rescale
+ * 1/255, (x - mean)/std -> out f32 [n,3,S,S]. mean3 / std3: HOST float[3]. */
+int opadpo_op_preprocess_images(const uint8_t* pixels, const int64_t* h_offsets, const int32_t* h_heights,
+                                const int32_t* h_widths, int32_t n, int32_t S, const float* mean3, const float* std3,
+                                const uint8_t* bg3, int32_t pad_to_square, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Engine level. One engine per process per GPU (current CUDA device at create time). The engine owns the base
  * weights (bf16), two LoRA adapter sets (0 = lora_policy, 1 = lora_ref_policy; qlora_model.py:21,66-93), the
  * trainable adapter's fp32 masters / gradients / Adam moments as ONE flat bucket, and all activations.

@@ -91,6 +91,12 @@ class DpoPairDesc(ctypes.Structure):
     ]
 
 
+class Segments(ctypes.Structure):
+    _fields_ = [("tokens", ctypes.c_void_p), ("seg_offsets", ctypes.c_void_p), ("seg_score", ctypes.c_void_p),
+                ("seg_relation", ctypes.c_void_p), ("seg_flags", ctypes.c_void_p), ("row_offsets", ctypes.c_void_p),
+                ("b", ctypes.c_int32)]
+
+
 class Sampler(ctypes.Structure):
     _fields_ = [("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("top_p", ctypes.c_float),
                 ("temperature", ctypes.c_float), ("seed", ctypes.c_uint64)]
@@ -119,6 +125,8 @@ EXPORTED_SYMBOLS = [
     "opadpo_engine_set_option", "opadpo_engine_set_backward_callback", "opadpo_engine_layer_grad_range",
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_backward_ent", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
+    "opadpo_op_collate_responses", "opadpo_op_collate_queries", "opadpo_op_mask_images", "opadpo_op_attention_holes",
+    "opadpo_op_preprocess_images",
 ]
 
 
@@ -148,6 +156,11 @@ def _declare_engine(lib):
     lib.opadpo_optimizer_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]
     lib.opadpo_generate.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, c.POINTER(Sampler), vp, vp]
     lib.opadpo_prof_begin.argtypes = []
+    lib.opadpo_op_collate_responses.argtypes = [c.POINTER(Segments), i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.opadpo_op_collate_queries.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.opadpo_op_mask_images.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    lib.opadpo_op_attention_holes.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.opadpo_op_preprocess_images.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.opadpo_prof_end.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64)]
     lib.opadpo_launch_count.argtypes = []
     lib.opadpo_launch_count.restype = c.c_int64

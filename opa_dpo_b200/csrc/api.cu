@@ -5,6 +5,7 @@
 #include "../../include/opadpo_b200.h"
 #include "common.h"
 #include "attention.h"
+#include "collate.h"
 #include "gemm.h"
 #include "elementwise.h"
 #include "engine.h"
@@ -145,6 +146,58 @@ int opadpo_op_dpo_pair(const opadpo_dpo_pair_desc* d, void* stream) {
   int rc = dpo_pair_loss(a, static_cast<cudaStream_t>(stream));
   if (rc != 0) { set_error("dpo_pair_loss launch failed"); return OPADPO_ECUDA; }
   return OPADPO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- collator stage
+int opadpo_op_collate_responses(const opadpo_segments* s, int32_t R, int32_t pad_id, int32_t eos_id, int32_t mode,
+                                int64_t* ids, uint8_t* attn_mask, float* scores, float* relations, int32_t* overflow,
+                                void* stream) {
+  g_last_error[0] = 0;
+  if (!s || !ids || s->b < 0 || R <= 0 || (s->b > 0 && (!s->seg_offsets || !s->seg_flags || !s->row_offsets))) {
+    set_error("opadpo_op_collate_responses: null pointer or bad sizes");
+    return OPADPO_EINVAL;
+  }
+  collate::Segments g{s->tokens, s->seg_offsets, s->seg_score, s->seg_relation, s->seg_flags, s->row_offsets};
+  return collate_responses(g, s->b, R, pad_id, eos_id, mode, ids, attn_mask, scores, relations, overflow,
+                           static_cast<cudaStream_t>(stream));
+}
+int opadpo_op_collate_queries(const int32_t* tokens, const int64_t* offsets, int32_t b, int32_t Q, int32_t pad_id,
+                              int32_t placeholder_id, int32_t image_token, int64_t* ids, uint8_t* attn_mask, void* stream) {
+  g_last_error[0] = 0;
+  if (!offsets || !ids || b < 0 || Q <= 0) {
+    set_error("opadpo_op_collate_queries: null pointer or bad sizes");
+    return OPADPO_EINVAL;
+  }
+  return collate_queries(tokens, offsets, b, Q, pad_id, placeholder_id, image_token, ids, attn_mask,
+                         static_cast<cudaStream_t>(stream));
+}
+int opadpo_op_mask_images(const float* images, float* out, int32_t n, int32_t C, int32_t H, int32_t W, const int64_t* idx,
+                          int32_t m, int32_t block, int32_t bf16_pixels, float* means_out, void* stream) {
+  g_last_error[0] = 0;
+  if (!images || !out || n < 0 || C <= 0 || H <= 0 || W <= 0 || m < 0 || (m > 0 && !idx) || block < 1 || H % block || W % block) {
+    set_error("opadpo_op_mask_images: null pointer or bad sizes (block must divide H and W)");
+    return OPADPO_EINVAL;
+  }
+  return mask_images(images, out, n, C, H, W, idx, m, block, bf16_pixels, means_out, static_cast<cudaStream_t>(stream));
+}
+int opadpo_op_attention_holes(uint8_t* out, const int64_t* idx, int32_t n, int32_t P, int32_t m, void* stream) {
+  g_last_error[0] = 0;
+  if (!out || n < 0 || P <= 0 || m < 0 || (m > 0 && !idx)) {
+    set_error("opadpo_op_attention_holes: null pointer or bad sizes");
+    return OPADPO_EINVAL;
+  }
+  return attention_holes(out, idx, n, P, m, static_cast<cudaStream_t>(stream));
+}
+int opadpo_op_preprocess_images(const uint8_t* pixels, const int64_t* h_offsets, const int32_t* h_heights,
+                                const int32_t* h_widths, int32_t n, int32_t S, const float* mean3, const float* std3,
+                                const uint8_t* bg3, int32_t pad_to_square, float* out, void* stream) {
+  g_last_error[0] = 0;
+  if (!pixels || !h_offsets || !h_heights || !h_widths || !mean3 || !std3 || !out || n < 0 || S <= 0) {
+    set_error("opadpo_op_preprocess_images: null pointer or bad sizes");
+    return OPADPO_EINVAL;
+  }
+  return preprocess_images(pixels, h_offsets, h_heights, h_widths, n, S, mean3, std3, bg3, pad_to_square, out,
+                           static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------- engine level

@@ -1,0 +1,183 @@
+// Per-element logic of the collator-stage kernels (collate.cu), written once as host/device functions so that the very
+// same arithmetic the GPU threads run can also be compiled with g++ into the CPU test harness (tests/host_harness) and
+// compared with the oracle bit-for-bit. Nothing here launches anything; the product only ever calls these from kernels.
+//
+// Reference behaviour being reproduced (paths under /root/reference):
+//   utils/data_utils_dpo.py:44-99, 118-121, 139-235   (segments -> padded ids / score / image-relation rows, EOS rules)
+//   utils/data_utils_dpo.py:311-333                   (expand2square + CLIP preprocess; Pillow ImagingResample [UPSTREAM])
+//   opadpo/dpo_models/dpo_trainer.py:83-125           (CoPO masks)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OPADPO_HD __host__ __device__ __forceinline__
+#else
+#define OPADPO_HD inline
+#endif
+
+namespace opadpo {
+namespace collate {
+
+constexpr int32_t kSpaceToken = 29871;  // data_utils_dpo.py:186
+enum : int32_t { SEG_KEEP_BOS = 1, SEG_STRIP_SPACE = 2 };
+enum : int32_t { MODE_ADD_EOS = 1, MODE_PAD_EOS = 2, MODE_TRUNCATE = 4 };
+constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow's 8bpc fixed-point coefficient precision
+
+// Raw tokenizer output of every report entry, flattened; see include/opadpo_b200.h (opadpo_segments).
+struct Segments {
+  const int32_t* tokens;
+  const int64_t* seg_offsets;
+  const float* seg_score;
+  const float* seg_relation;
+  const uint8_t* seg_flags;
+  const int64_t* row_offsets;
+};
+
+// The slice of segment j that reaches the row (data_utils_dpo.py:166-186): nothing when the entry tokenised to BOS only;
+// BOS dropped unless the entry belongs to the first report key; a copied entry then loses a leading 29871 piece.
+OPADPO_HD void segment_range(const Segments& s, int64_t j, int64_t* begin, int64_t* end) {
+  int64_t b = s.seg_offsets[j];
+  const int64_t e = s.seg_offsets[j + 1];
+  if (e - b <= 1) {
+    *begin = *end = e;
+    return;
+  }
+  const int fl = s.seg_flags[j];
+  if (!(fl & SEG_KEEP_BOS)) b += 1;
+  if ((fl & SEG_STRIP_SPACE) && s.tokens[b] == kSpaceToken) b += 1;
+  *begin = b;
+  *end = e;
+}
+
+OPADPO_HD int64_t row_length(const Segments& s, int row) {
+  int64_t n = 0;
+  for (int64_t j = s.row_offsets[row]; j < s.row_offsets[row + 1]; ++j) {
+    int64_t b, e;
+    segment_range(s, j, &b, &e);
+    n += e - b;
+  }
+  return n;
+}
+
+// Token and per-token weights at position p of the concatenated row; false when p lies beyond its tokens.
+OPADPO_HD bool token_at(const Segments& s, int row, int64_t p, int32_t* tok, float* score, float* rel) {
+  int64_t acc = 0;
+  for (int64_t j = s.row_offsets[row]; j < s.row_offsets[row + 1]; ++j) {
+    int64_t b, e;
+    segment_range(s, j, &b, &e);
+    const int64_t n = e - b;
+    if (p < acc + n) {
+      *tok = s.tokens[b + (p - acc)];
+      *score = s.seg_score ? s.seg_score[j] : 0.f;
+      *rel = s.seg_relation ? s.seg_relation[j] : 0.f;
+      return true;
+    }
+    acc += n;
+  }
+  return false;
+}
+
+// add_eos (data_utils_dpo.py:73-87) and pad_eos (:89-99) on a finished row. first_pad / first_eos: smallest position
+// holding pad_id / eos_id before the insertion (R when none).
+OPADPO_HD void finish_row(int64_t* ids, float* score, float* rel, int R, int first_pad, int first_eos, int mode, int eos_id) {
+  if ((mode & MODE_ADD_EOS) && first_pad < R) {
+    ids[first_pad] = eos_id;
+    if (first_pad < first_eos) first_eos = first_pad;
+  }
+  if ((mode & MODE_PAD_EOS) && first_eos < R) {
+    const int prev = first_eos == 0 ? R - 1 : first_eos - 1;  // index -1 wraps to the last position, as in the reference
+    if (score) {
+      const float v = score[prev];
+      score[first_eos] = v != 0.f ? v : 1.f;
+    }
+    if (rel) {
+      const float v = rel[prev];
+      rel[first_eos] = v != 0.f ? v : 1.f;
+    }
+  }
+}
+
+// Left-padded query row (data_utils_dpo.py:118-121): right-truncated to Q, placeholder id -> image token.
+OPADPO_HD void query_at(const int32_t* tokens, const int64_t* offsets, int row, int p, int Q, int pad_id, int placeholder_id,
+                        int image_token, int64_t* id, uint8_t* mask) {
+  const int64_t b = offsets[row];
+  int64_t len = offsets[row + 1] - b;
+  if (len > Q) len = Q;
+  const int64_t start = Q - len;
+  if (p >= start) {
+    const int32_t t = tokens[b + (p - start)];
+    *id = t == placeholder_id ? image_token : t;
+    *mask = 1;
+  } else {
+    *id = pad_id;
+    *mask = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ images
+// One image's geometry and where its resampling tables live. The source is the uint8 RGB image [H, W, 3] seen through
+// expand2square (a Ws x Hs canvas of the background colour with the image at (ox, oy)); the output is the SxS window at
+// (left, top) of the canvas resized to new_w x new_h. Tables (int32, Pillow's normalised 22-bit coefficients):
+// kkx [S, ksx], bx [S, 2] = (first source column, taps), kky [S, ksy], by [S, 2].
+struct ImageDesc {
+  int64_t pix_off;   // byte offset of the image in the pixel buffer
+  int64_t tab_off;   // int32 offset of its tables: kkx | bx | kky | by
+  int64_t tmp_off;   // byte offset of its horizontal-pass rows [Hs, S, 3] in the scratch buffer
+  int32_t H, W, Hs, Ws, ox, oy;
+  int32_t ksx, ksy;
+};
+
+OPADPO_HD uint8_t clip8(int32_t v) {
+  v >>= kPrecisionBits;  // arithmetic shift, as Pillow's clip8
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+OPADPO_HD int32_t canvas_pixel(const uint8_t* img, const ImageDesc& d, int x, int y, int c, const uint8_t* bg) {
+  const int sx = x - d.ox, sy = y - d.oy;
+  if (sx < 0 || sy < 0 || sx >= d.W || sy >= d.H) return bg[c];
+  return img[(static_cast<int64_t>(sy) * d.W + sx) * 3 + c];
+}
+
+// Horizontal pass of ImagingResample for canvas row y, output column xx (window-relative), channel c.
+OPADPO_HD uint8_t resample_h(const uint8_t* img, const ImageDesc& d, const int32_t* tab, int S, int y, int xx, int c,
+                             const uint8_t* bg) {
+  const int32_t* kk = tab + static_cast<int64_t>(xx) * d.ksx;
+  const int32_t* bx = tab + static_cast<int64_t>(S) * d.ksx + 2 * xx;
+  const int x0 = bx[0], n = bx[1];
+  int32_t ss = 1 << (kPrecisionBits - 1);
+  for (int k = 0; k < n; ++k) ss += canvas_pixel(img, d, x0 + k, y, c, bg) * kk[k];
+  return clip8(ss);
+}
+
+// rescale + normalize of the pinned image processor: uint8 * (1/255) in float64 -> float32, then (x - mean) / std in
+// float32 [UPSTREAM transformers 4.34.1 image_transforms.rescale / normalize].
+OPADPO_HD float normalise_pixel(uint8_t v, float mean, float std) {
+  const float x = static_cast<float>(static_cast<double>(v) * (1.0 / 255.0));
+  return (x - mean) / std;
+}
+
+// Vertical pass over the horizontal-pass rows `tmp` [Hs, S, 3] for output (yy, xx, c), then normalisation.
+OPADPO_HD float resample_v(const uint8_t* tmp, const ImageDesc& d, const int32_t* tab, int S, int yy, int xx, int c, float mean,
+                           float std) {
+  const int32_t* kky = tab + static_cast<int64_t>(S) * d.ksx + 2 * S;
+  const int32_t* kk = kky + static_cast<int64_t>(yy) * d.ksy;
+  const int32_t* by = kky + static_cast<int64_t>(S) * d.ksy + 2 * yy;
+  const int y0 = by[0], n = by[1];
+  int32_t ss = 1 << (kPrecisionBits - 1);
+  for (int k = 0; k < n; ++k) ss += static_cast<int32_t>(tmp[(static_cast<int64_t>(y0 + k) * S + xx) * 3 + c]) * kk[k];
+  return normalise_pixel(clip8(ss), mean, std);
+}
+
+// float32 -> bf16 (round to nearest even) -> float32: the trainer masks images it has already cast to bf16.
+OPADPO_HD float round_bf16(float x) {
+  union {
+    float f;
+    uint32_t u;
+  } v;
+  v.f = x;
+  v.u = (v.u + 0x7FFFu + ((v.u >> 16) & 1u)) & 0xFFFF0000u;
+  return v.f;
+}
+
+}  // namespace collate
+}  // namespace opadpo

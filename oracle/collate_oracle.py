@@ -262,3 +262,53 @@ def _round_bf16(x: np.ndarray) -> np.ndarray:
     u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
     r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
     return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+
+
+# ------------------------------------------------------------------------------------------------ stub tokenizer
+def word_id(w: str) -> int:
+    """Deterministic word -> id map of the stub tokenizer; "SPACE" / "IMG" give the two ids the collator treats specially."""
+    import hashlib
+    if w == "SPACE":
+        return SPACE_TOKEN
+    if w == "IMG":
+        return IMAGE_PLACEHOLDER_ID
+    h = int(hashlib.md5(w.encode()).hexdigest()[:8], 16)
+    v = 3 + h % 29000
+    return v + 1 if v in (SPACE_TOKEN, IMAGE_PLACEHOLDER_ID) else v
+
+
+class StubTokenizer:
+    """The slice of the HF tokenizer interface the collator uses."""
+    pad_token_id, eos_token_id, bos_token_id = 0, 2, 1
+
+    def __init__(self):
+        self.padding_side = "right"
+        self.log = []          # (text, ids) of every single-string call, in call order
+
+    def encode_one(self, text: str):
+        return [self.bos_token_id] + [word_id(w) for w in text.split()]
+
+    def __call__(self, text, padding=False, truncation=False, max_length=None, return_tensors=None):
+        import torch
+        from transformers import BatchEncoding
+        if isinstance(text, str):
+            ids = self.encode_one(text)
+            self.log.append((text, list(ids)))
+            return BatchEncoding({"input_ids": torch.tensor([ids], dtype=torch.long),
+                                  "attention_mask": torch.ones(1, len(ids), dtype=torch.long)})
+        rows, masks = [], []
+        for t in text:
+            ids = self.encode_one(t)
+            if truncation and max_length is not None:
+                ids = ids[:max_length]
+            m = [1] * len(ids)
+            if padding == "max_length":
+                n = max_length - len(ids)
+                if self.padding_side == "left":
+                    ids, m = [self.pad_token_id] * n + ids, [0] * n + m
+                else:
+                    ids, m = ids + [self.pad_token_id] * n, m + [0] * n
+            rows.append(ids)
+            masks.append(m)
+        return BatchEncoding({"input_ids": torch.tensor(rows, dtype=torch.long),
+                              "attention_mask": torch.tensor(masks, dtype=torch.long)})

@@ -1,0 +1,75 @@
+// CPU TEST HARNESS (test infrastructure, never shipped, never loaded by opa_dpo_b200): runs the collator kernels'
+// shared per-element core (opa_dpo_b200/csrc/collate_core.h, collate_tables.h) in plain loops that mirror the CUDA thread
+// mapping of collate.cu, so the exact arithmetic the GPU executes can be checked against the oracle on a machine
+// without a GPU. Built by tests/test_collate_cpu.py with g++.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../opa_dpo_b200/csrc/collate_core.h"
+#include "../../opa_dpo_b200/csrc/collate_tables.h"
+
+using namespace opadpo::collate;
+
+extern "C" {
+
+void host_collate_responses(const int32_t* tokens, const int64_t* seg_offsets, const float* seg_score, const float* seg_relation,
+                            const uint8_t* seg_flags, const int64_t* row_offsets, int b, int R, int pad_id, int eos_id, int mode,
+                            int64_t* ids, uint8_t* mask, float* scores, float* relations, int32_t* overflow) {
+  Segments s{tokens, seg_offsets, seg_score, seg_relation, seg_flags, row_offsets};
+  for (int row = 0; row < b; ++row) {
+    int first_pad = R, first_eos = R;
+    int64_t* ids_row = ids + static_cast<int64_t>(row) * R;
+    float* sc_row = scores ? scores + static_cast<int64_t>(row) * R : nullptr;
+    float* rel_row = relations ? relations + static_cast<int64_t>(row) * R : nullptr;
+    for (int p = 0; p < R; ++p) {
+      int32_t tok = 0;
+      float sc = 0.f, rel = 0.f;
+      const bool ok = token_at(s, row, p, &tok, &sc, &rel);
+      const int64_t id = ok ? tok : pad_id;
+      ids_row[p] = id;
+      if (sc_row) sc_row[p] = ok ? sc : 0.f;
+      if (rel_row) rel_row[p] = ok ? rel : 0.f;
+      if (id == pad_id && p < first_pad) first_pad = p;
+      if (id == eos_id && p < first_eos) first_eos = p;
+    }
+    finish_row(ids_row, sc_row, rel_row, R, first_pad, first_eos, mode, eos_id);
+    if (overflow) overflow[row] = (!(mode & MODE_TRUNCATE) && row_length(s, row) > R) ? 1 : 0;
+    if (mask)
+      for (int p = 0; p < R; ++p) mask[static_cast<int64_t>(row) * R + p] = ids_row[p] != pad_id ? 1 : 0;
+  }
+}
+
+void host_collate_queries(const int32_t* tokens, const int64_t* offsets, int b, int Q, int pad_id, int placeholder_id,
+                          int image_token, int64_t* ids, uint8_t* mask) {
+  for (int row = 0; row < b; ++row)
+    for (int p = 0; p < Q; ++p)
+      query_at(tokens, offsets, row, p, Q, pad_id, placeholder_id, image_token, &ids[static_cast<int64_t>(row) * Q + p],
+               &mask[static_cast<int64_t>(row) * Q + p]);
+}
+
+void host_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n,
+                            int S, const float* mean3, const float* std3, const uint8_t* bg3, int pad_to_square, float* out) {
+  for (int i = 0; i < n; ++i) {
+    ImageDesc d{};
+    std::vector<int32_t> tables;
+    int64_t tmp_bytes = 0;
+    plan_image(heights[i], widths[i], S, pad_to_square != 0, &d, &tables, &tmp_bytes);
+    d.pix_off = offsets[i];
+    d.tmp_off = 0;
+    std::vector<uint8_t> tmp(static_cast<size_t>(tmp_bytes));
+    const uint8_t* img = pixels + d.pix_off;
+    const int32_t* tab = tables.data() + d.tab_off;
+    for (int y = 0; y < d.Hs; ++y)
+      for (int xx = 0; xx < S; ++xx)
+        for (int c = 0; c < 3; ++c) tmp[(static_cast<int64_t>(y) * S + xx) * 3 + c] = resample_h(img, d, tab, S, y, xx, c, bg3);
+    for (int yy = 0; yy < S; ++yy)
+      for (int xx = 0; xx < S; ++xx)
+        for (int c = 0; c < 3; ++c)
+          out[((static_cast<int64_t>(i) * 3 + c) * S + yy) * S + xx] = resample_v(tmp.data(), d, tab, S, yy, xx, c, mean3[c], std3[c]);
+  }
+}
+
+float host_round_bf16(float x) { return round_bf16(x); }
+
+}  // extern "C"

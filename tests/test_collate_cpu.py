@@ -141,3 +141,170 @@ def test_oracle_copo_masks_vs_reference(G):
         else:
             assert hashlib.sha256(out.tobytes()).hexdigest() == str(G[name + "_sha"]), name
     assert np.array_equal(C.attention_holes(576, G["E_attn_idx"]), G["E_attn_out"])
+
+
+# ------------------------------------------------------------------------------------------------ kernel core on the host
+@pytest.fixture(scope="module")
+def harness():
+    """g++ build of tests/host_harness/collate_host.cpp: the kernels' per-element core, compiled for the CPU."""
+    import ctypes
+    out_dir = os.path.join(ROOT, "build", "host_harness")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcollate_host.so")
+    src = os.path.join(ROOT, "tests", "host_harness", "collate_host.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    import ctypes
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _harness_responses(lib, G, prefix, R, mode, with_weights=True):
+    arrs = {k: np.ascontiguousarray(G[prefix + k]) for k in ("tokens", "seg_offsets", "seg_score", "seg_relation", "seg_flags", "row_offsets")}
+    b = len(arrs["row_offsets"]) - 1
+    ids = np.full((b, R), -7, np.int64)
+    mask = np.full((b, R), 9, np.uint8)
+    sc = np.full((b, R), np.nan, np.float32) if with_weights else None
+    rel = np.full((b, R), np.nan, np.float32) if with_weights else None
+    ov = np.full((b,), -1, np.int32)
+    lib.host_collate_responses(_p(arrs["tokens"]), _p(arrs["seg_offsets"]), _p(arrs["seg_score"]), _p(arrs["seg_relation"]),
+                               _p(arrs["seg_flags"]), _p(arrs["row_offsets"]), b, int(R), 0, 2, mode, _p(ids), _p(mask), _p(sc),
+                               _p(rel), _p(ov))
+    return ids, mask, sc, rel, ov
+
+
+def test_kernel_core_responses_vs_reference(harness, G):
+    Q, R = G["A_QR"]
+    ids, mask, sc, rel, ov = _harness_responses(harness, G, "A_orig_", R, C.COLLATE_ADD_EOS)
+    assert not ov.any()
+    assert np.array_equal(ids, G["A_out_original_generate_response"])
+    assert np.array_equal(mask.astype(bool), G["A_out_original_generate_response_attention_mask"])
+    assert np.array_equal(sc, G["A_out_original_generate_response_scores"])
+    assert np.array_equal(rel, G["A_out_original_generate_response_image_relations"])
+    ids, mask, sc, rel, ov = _harness_responses(harness, G, "A_ai_", R, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
+    assert np.array_equal(ids, G["A_out_AI_pseudo_response"])
+    assert np.array_equal(sc, G["A_out_AI_pseudo_response_scores"])
+    assert np.array_equal(rel, G["A_out_AI_pseudo_response_image_relations"])
+    # a tighter R: the same rows overflow, flagged and truncated exactly like the oracle
+    rows = unpack_rows(G, "A_ai_")
+    for R2 in (5, 17, 30):
+        want = C.collate_responses(rows, R2, 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
+        got = _harness_responses(harness, G, "A_ai_", R2, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].astype(bool), want[1])
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]) and np.array_equal(got[4].astype(bool), want[4])
+
+
+def _pack(rows):
+    toks, so, sc, rel, fl, ro = [], [0], [], [], [], [0]
+    for segs in rows:
+        for raw, ws, wr, f in segs:
+            toks.extend(raw)
+            so.append(len(toks))
+            sc.append(ws)
+            rel.append(wr)
+            fl.append(f)
+        ro.append(len(sc))
+    return {"tokens": np.asarray(toks + [0], np.int32), "seg_offsets": np.asarray(so, np.int64), "seg_score": np.asarray(sc + [0], np.float32),
+            "seg_relation": np.asarray(rel + [0], np.float32), "seg_flags": np.asarray(fl + [0], np.uint8), "row_offsets": np.asarray(ro, np.int64)}
+
+
+def random_rows(rs, b, max_segs, max_len, R):
+    """Ragged random reports incl. empty rows, BOS-only entries, leading-29871 entries, pad / EOS ids inside the text."""
+    rows = []
+    for i in range(b):
+        segs = []
+        for j in range(rs.randint(0, max_segs + 1)):
+            n = rs.randint(0, max_len + 1)
+            raw = [1] + rs.randint(3, 32000, n).tolist()
+            if n and rs.rand() < 0.3:
+                raw[1] = C.SPACE_TOKEN
+            if n > 2 and rs.rand() < 0.15:
+                raw[rs.randint(1, n + 1)] = rs.choice([0, 2])
+            fl = (C.FLAG_KEEP_BOS if j == 0 else 0) | (C.FLAG_STRIP_SPACE if rs.rand() < 0.5 else 0)
+            segs.append((raw, float(rs.choice([1.0, 1.5, 2.0, 2.5, 0.0])), float(rs.choice([1.0, 3.0])), fl))
+        rows.append(segs)
+    return rows
+
+
+def test_kernel_core_responses_random_ragged_vs_oracle(harness):
+    rs = np.random.RandomState(3)
+    for trial in range(40):
+        R = int(rs.choice([1, 2, 7, 33, 128]))
+        rows = random_rows(rs, int(rs.randint(1, 6)), 6, 12, R)
+        for mode in (0, 1, 3, 5, 7):
+            want = C.collate_responses(rows, R, 0, 2, mode)
+            got = _harness_responses(harness, _pack(rows), "", R, mode)
+            for a, w, name in zip(got, want, ("ids", "mask", "scores", "relations", "overflow")):
+                assert np.array_equal(np.asarray(a).astype(w.dtype), w), (trial, mode, name)
+
+
+def test_kernel_core_queries_vs_reference(harness, G):
+    Q, R = G["A_QR"]
+    for key, want_ids, want_mask in (("A_query_tokens", "A_out_queries", "A_out_queries_attention_mask"),):
+        toks = json.loads(str(G[key]))
+        flat = np.asarray([t for r in toks for t in r], np.int32)
+        off = np.asarray(np.cumsum([0] + [len(r) for r in toks]), np.int64)
+        ids = np.zeros((len(toks), Q), np.int64)
+        mask = np.zeros((len(toks), Q), np.uint8)
+        harness.host_collate_queries(_p(flat), _p(off), len(toks), int(Q), 0, C.IMAGE_PLACEHOLDER_ID, C.IMAGE_TOKEN_INDEX, _p(ids), _p(mask))
+        assert np.array_equal(ids, G[want_ids]) and np.array_equal(mask, G[want_mask].astype(np.uint8))
+    toks = json.loads(str(G["C_tokens"]))["queries"] + [[]]          # + an empty query: all pad
+    flat = np.asarray([t for r in toks for t in r], np.int32)
+    off = np.asarray(np.cumsum([0] + [len(r) for r in toks]), np.int64)
+    ids = np.zeros((len(toks), Q), np.int64)
+    mask = np.zeros((len(toks), Q), np.uint8)
+    harness.host_collate_queries(_p(flat), _p(off), len(toks), int(Q), 0, C.IMAGE_PLACEHOLDER_ID, C.IMAGE_TOKEN_INDEX, _p(ids), _p(mask))
+    want = C.collate_queries(toks, Q, 0)
+    assert np.array_equal(ids, want[0]) and np.array_equal(mask.astype(bool), want[1])
+    assert np.array_equal(ids[:2], G["C_out_queries"])
+
+
+def _harness_preprocess(lib, imgs, S, pad):
+    import ctypes
+    flat = np.concatenate([i.reshape(-1) for i in imgs]).astype(np.uint8)
+    off = np.asarray(np.cumsum([0] + [i.size for i in imgs])[:-1], np.int64)
+    hs = np.asarray([i.shape[0] for i in imgs], np.int32)
+    ws = np.asarray([i.shape[1] for i in imgs], np.int32)
+    mean, std = np.asarray(C.CLIP_MEAN, np.float32), np.asarray(C.CLIP_STD, np.float32)
+    bg = np.asarray([int(x * 255) for x in C.CLIP_MEAN], np.uint8)
+    out = np.full((len(imgs), 3, S, S), np.nan, np.float32)
+    lib.host_preprocess_images(_p(flat), _p(off), _p(hs), _p(ws), len(imgs), S, _p(mean), _p(std), _p(bg), int(pad), _p(out))
+    return out
+
+
+def test_kernel_core_image_preprocess_vs_reference(harness, G):
+    i = 0
+    while f"D{i}_in" in G:
+        S, pad = G[f"D{i}_cfg"]
+        got = _harness_preprocess(harness, [G[f"D{i}_in"]], int(S), bool(pad))[0]
+        assert np.array_equal(got, G[f"D{i}_out"]), f"case {i}"
+        i += 1
+    for key, ref in json.loads(str(G["D_big"])).items():
+        H, W, seed = map(int, key.split("x"))
+        img = np.random.RandomState(seed).randint(0, 256, (H, W, 3)).astype(np.uint8)
+        out = _harness_preprocess(harness, [img], 336, True)[0]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == ref["sha256"], key
+
+
+def test_kernel_core_image_preprocess_ragged_batch_vs_oracle(harness):
+    rs = np.random.RandomState(11)
+    shapes = [(1, 1), (2, 9), (9, 2), (57, 31), (31, 57), (64, 64), (130, 77), (400, 123)]
+    imgs = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in shapes]
+    for S, pad in ((32, True), (32, False), (48, True)):
+        got = _harness_preprocess(harness, imgs, S, pad)
+        for j, im in enumerate(imgs):
+            assert np.array_equal(got[j], C.clip_preprocess(im, S, pad)), (shapes[j], S, pad)
+
+
+def test_kernel_core_bf16_rounding(harness):
+    import ctypes
+    harness.host_round_bf16.restype = ctypes.c_float
+    harness.host_round_bf16.argtypes = [ctypes.c_float]
+    import torch
+    x = torch.randn(2000) * 3
+    want = x.to(torch.bfloat16).float()
+    got = torch.tensor([harness.host_round_bf16(float(v)) for v in x])
+    assert torch.equal(got, want)
+    assert np.array_equal(C._round_bf16(x.numpy()), want.numpy())
