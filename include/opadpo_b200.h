@@ -142,8 +142,11 @@ enum { OPADPO_SEG_KEEP_BOS = 1,     /* entry of the FIRST report key: its BOS st
        OPADPO_SEG_STRIP_SPACE = 2   /* copied entry: a leading 29871 piece is dropped (:186-187) */ };
 enum { OPADPO_COLLATE_ADD_EOS = 1,  /* add_eos (:73-87): the first pad position becomes EOS */
        OPADPO_COLLATE_PAD_EOS = 2,  /* pad_eos (:89-99): the EOS position inherits the previous position's weight (1 if 0) */
-       OPADPO_COLLATE_TRUNCATE = 4  /* tokenizer truncation (plain branch :120-137); without it a row longer than R sets
-                                       overflow[row], which is where the reference raises and falls back (:259-278) */ };
+       OPADPO_COLLATE_TRUNCATE = 4, /* tokenizer truncation (plain branch :120-137); without it a row longer than R sets
+                                       overflow[row], which is where the reference raises and falls back (:259-278) */
+       OPADPO_COLLATE_TOKEN_MASK = 8 /* attn_mask = the tokenizer's own mask as the plain branch hands it out (:122-137): 1
+                                        where a token was placed; with ADD_EOS its first 0 holds eos_id, because add_eos
+                                        walks every tensor of the encoding (:76-79). Default: ids != pad (:253-255) */ };
 /* -> ids int64 [b,R] right-padded; attn_mask u8 [b,R] (ids != pad), scores / relations f32 [b,R] (0 at pads), overflow
  * i32 [b]: each nullable. Replaces pad_and_stack / add_eos / pad_eos and the torch.cat chain of :200-235. */
 int opadpo_op_collate_responses(const opadpo_segments* s, int32_t R, int32_t pad_id, int32_t eos_id, int32_t mode,

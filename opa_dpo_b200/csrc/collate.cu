@@ -25,7 +25,7 @@ inline int launch_ok(const char* what) {
 
 // One CTA per response row. Pass 1 places every position (token_at walks the row's segments; a row has a few dozen), and
 // finds the first pad / first EOS with shared-memory atomicMin; one thread then applies the EOS rules; pass 2 writes the
-// attention mask from the final ids.
+// attention mask from the final ids (or, MODE_TOKEN_MASK, pass 1 writes the tokenizer's own mask).
 __global__ void __launch_bounds__(256) collate_responses_kernel(Segments s, int R, int pad_id, int eos_id, int mode,
                                                                 int64_t* __restrict__ ids, uint8_t* __restrict__ mask,
                                                                 float* __restrict__ scores, float* __restrict__ relations,
@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) collate_responses_kernel(Segments s, int 
   int64_t* ids_row = ids + static_cast<int64_t>(row) * R;
   float* sc_row = scores ? scores + static_cast<int64_t>(row) * R : nullptr;
   float* rel_row = relations ? relations + static_cast<int64_t>(row) * R : nullptr;
+  uint8_t* mask_row = mask ? mask + static_cast<int64_t>(row) * R : nullptr;
+  const bool token_mask = (mode & MODE_TOKEN_MASK) != 0;  // the tokenizer's mask: positions that hold a token
   for (int p = threadIdx.x; p < R; p += blockDim.x) {
     int32_t tok = 0;
     float sc = 0.f, rel = 0.f;
@@ -48,19 +50,21 @@ __global__ void __launch_bounds__(256) collate_responses_kernel(Segments s, int 
     ids_row[p] = id;
     if (sc_row) sc_row[p] = ok ? sc : 0.f;
     if (rel_row) rel_row[p] = ok ? rel : 0.f;
+    if (mask_row && token_mask) mask_row[p] = ok ? 1 : 0;
     if (id == pad_id) atomicMin(&first_pad, p);
     if (id == eos_id) atomicMin(&first_eos, p);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     finish_row(ids_row, sc_row, rel_row, R, first_pad, first_eos, mode, eos_id);
-    if (overflow) overflow[row] = (!(mode & MODE_TRUNCATE) && row_length(s, row) > R) ? 1 : 0;
+    const int64_t len = row_length(s, row);
+    if (overflow) overflow[row] = (!(mode & MODE_TRUNCATE) && len > R) ? 1 : 0;
+    // add_eos also walks the tokenizer's attention mask (data_utils_dpo.py:76-79): its first 0 becomes eos_id
+    if (mask_row && token_mask && (mode & MODE_ADD_EOS) && len < R) mask_row[len] = static_cast<uint8_t>(eos_id);
   }
   __syncthreads();
-  if (mask) {
-    uint8_t* m = mask + static_cast<int64_t>(row) * R;
-    for (int p = threadIdx.x; p < R; p += blockDim.x) m[p] = ids_row[p] != pad_id ? 1 : 0;
-  }
+  if (mask_row && !token_mask)
+    for (int p = threadIdx.x; p < R; p += blockDim.x) mask_row[p] = ids_row[p] != pad_id ? 1 : 0;
 }
 
 __global__ void collate_queries_kernel(const int32_t* __restrict__ tokens, const int64_t* __restrict__ offsets, int b, int Q,

@@ -20,7 +20,7 @@ namespace collate {
 
 constexpr int32_t kSpaceToken = 29871;  // data_utils_dpo.py:186
 enum : int32_t { SEG_KEEP_BOS = 1, SEG_STRIP_SPACE = 2 };
-enum : int32_t { MODE_ADD_EOS = 1, MODE_PAD_EOS = 2, MODE_TRUNCATE = 4 };
+enum : int32_t { MODE_ADD_EOS = 1, MODE_PAD_EOS = 2, MODE_TRUNCATE = 4, MODE_TOKEN_MASK = 8 };
 constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow's 8bpc fixed-point coefficient precision
 
 // Raw tokenizer output of every report entry, flattened; see include/opadpo_b200.h (opadpo_segments).

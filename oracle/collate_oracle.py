@@ -33,7 +33,7 @@ SPACE_TOKEN = 29871          # the '' piece the LLaMA tokenizer puts in front of
 IMAGE_PLACEHOLDER_ID = 30861  # id of the placeholder glyph the dataset puts where <image> was (:121, :341)
 IMAGE_TOKEN_INDEX = -200
 FLAG_KEEP_BOS, FLAG_STRIP_SPACE = 1, 2
-COLLATE_ADD_EOS, COLLATE_PAD_EOS, COLLATE_TRUNCATE = 1, 2, 4
+COLLATE_ADD_EOS, COLLATE_PAD_EOS, COLLATE_TRUNCATE, COLLATE_TOKEN_MASK = 1, 2, 4, 8
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
@@ -60,14 +60,15 @@ def effective_segment(raw: Sequence[int], flags: int) -> Optional[np.ndarray]:
 def collate_responses(rows: List[List[Tuple[Sequence[int], float, float, int]]], R: int, pad_id: int, eos_id: int,
                       mode: int):
     """rows[i] = [(raw token ids, score weight, image-relation weight, flags), ...] in report-key order.
-    -> ids int64 [b,R], attention mask bool [b,R], scores f32 [b,R], relations f32 [b,R], overflow bool [b]
+    -> ids int64 [b,R], attention mask uint8 [b,R], scores f32 [b,R], relations f32 [b,R], overflow bool [b]
     (data_utils_dpo.py:200-235). mode: COLLATE_ADD_EOS (add_eos :73-87), COLLATE_PAD_EOS (pad_eos :89-99),
-    COLLATE_TRUNCATE (tokenizer truncation of the plain branch instead of the overflow exception)."""
+    COLLATE_TRUNCATE (tokenizer truncation of the plain branch instead of the overflow exception), COLLATE_TOKEN_MASK."""
     b = len(rows)
     ids = np.full((b, R), pad_id, np.int64)
     sc = np.zeros((b, R), np.float32)
     rel = np.zeros((b, R), np.float32)
     overflow = np.zeros((b,), bool)
+    tok_mask = np.zeros((b, R), np.uint8)
     for i, segs in enumerate(rows):
         toks, s, r = [], [], []
         for raw, ws, wr, fl in segs:
@@ -85,6 +86,11 @@ def collate_responses(rows: List[List[Tuple[Sequence[int], float, float, int]]],
                 overflow[i] = True
             t, s, r = t[:R], s[:R], r[:R]
         ids[i, :t.size], sc[i, :t.size], rel[i, :t.size] = t, s, r
+        tok_mask[i, :t.size] = 1
+        if (mode & COLLATE_ADD_EOS) and t.size < R:
+            # add_eos walks EVERY tensor of the BatchEncoding, the attention mask included (data_utils_dpo.py:76-79): the
+            # mask's first 0 is overwritten with eos_id too, so the plain branch's mask reads 1..1, 2, 0..0
+            tok_mask[i, t.size] = eos_id
         if mode & COLLATE_ADD_EOS:                      # first pad position becomes EOS
             pads = np.nonzero(ids[i] == pad_id)[0]
             if pads.size:
@@ -95,7 +101,8 @@ def collate_responses(rows: List[List[Tuple[Sequence[int], float, float, int]]],
                 for arr in (sc, rel):
                     prev = arr[i, e[0] - 1]              # e[0] == 0 wraps to the last position, as in the reference
                     arr[i, e[0]] = prev if prev != 0 else 1.0
-    return ids, ids != pad_id, sc, rel, overflow
+    # the plain branch hands out the TOKENIZER's attention mask (made before add_eos); the report branch ids != pad (:253-255)
+    return ids, (tok_mask if mode & COLLATE_TOKEN_MASK else (ids != pad_id).astype(np.uint8)), sc, rel, overflow
 
 
 def collate_queries(rows: List[Sequence[int]], Q: int, pad_id: int):

@@ -233,6 +233,18 @@ def main():
     G["E_attn_idx"] = np.stack([torch.randperm(576)[: int(576 * 0.3)].numpy() for _ in range(3)])
     G["E_attn_out"] = m.numpy()
 
+    # ---- (F) complete_copied_content (data_utils_dpo.py:56-71) on its own
+    cases = [("the cat sat on the mat. it purred.", ["the cat", " sat on the mat.", ""]),
+             ("alpha beta gamma delta", ["beta", "delta"]),
+             ("alpha beta gamma delta", ["beta", "missing piece", "delta"]),
+             ("  leading and trailing  ", [" leading", "", "trailing "]),
+             ("one two three", ["", ""]),
+             ("one two three", []),
+             ("repeat repeat repeat tail", ["repeat", "repeat", "repeat"]),
+             ("a b c", ["a b c"]),
+             ("x", ["", "x", ""])]
+    G["F_realign"] = np.asarray(json.dumps([[o, p, D.complete_copied_content(o, list(p))] for o, p in cases]))
+
     out_path = os.path.join(ROOT, "tests", "golden", "collate_golden.npz")
     np.savez_compressed(out_path, **G)
     print(f"wrote {out_path}: {len(G)} arrays, {os.path.getsize(out_path) / 1024:.0f} KiB")

@@ -30,12 +30,15 @@ void host_collate_responses(const int32_t* tokens, const int64_t* seg_offsets, c
       ids_row[p] = id;
       if (sc_row) sc_row[p] = ok ? sc : 0.f;
       if (rel_row) rel_row[p] = ok ? rel : 0.f;
+      if (mask && (mode & MODE_TOKEN_MASK)) mask[static_cast<int64_t>(row) * R + p] = ok ? 1 : 0;
       if (id == pad_id && p < first_pad) first_pad = p;
       if (id == eos_id && p < first_eos) first_eos = p;
     }
     finish_row(ids_row, sc_row, rel_row, R, first_pad, first_eos, mode, eos_id);
-    if (overflow) overflow[row] = (!(mode & MODE_TRUNCATE) && row_length(s, row) > R) ? 1 : 0;
-    if (mask)
+    const int64_t len = row_length(s, row);
+    if (overflow) overflow[row] = (!(mode & MODE_TRUNCATE) && len > R) ? 1 : 0;
+    if (mask && (mode & MODE_TOKEN_MASK) && (mode & MODE_ADD_EOS) && len < R) mask[static_cast<int64_t>(row) * R + len] = static_cast<uint8_t>(eos_id);
+    if (mask && !(mode & MODE_TOKEN_MASK))
       for (int p = 0; p < R; ++p) mask[static_cast<int64_t>(row) * R + p] = ids_row[p] != pad_id ? 1 : 0;
   }
 }

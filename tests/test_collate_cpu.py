@@ -13,7 +13,9 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import collate_oracle as C  # noqa: E402
+from _collate_util import _mask_cases, _mask_input, random_rows, unpack_rows  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden", "collate_golden.npz")
 
@@ -23,27 +25,17 @@ def G():
     return np.load(GOLD)
 
 
-def unpack_rows(G, prefix):
-    """flat segment arrays -> the oracle's list-of-lists form."""
-    tok, so = G[prefix + "tokens"], G[prefix + "seg_offsets"]
-    sc, rel, fl, ro = G[prefix + "seg_score"], G[prefix + "seg_relation"], G[prefix + "seg_flags"], G[prefix + "row_offsets"]
-    rows = []
-    for i in range(len(ro) - 1):
-        rows.append([(tok[so[j]:so[j + 1]].tolist(), float(sc[j]), float(rel[j]), int(fl[j])) for j in range(ro[i], ro[i + 1])])
-    return rows
-
-
 def test_oracle_detailed_report_vs_reference(G):
     Q, R = G["A_QR"]
     ids, mask, sc, rel, ov = C.collate_responses(unpack_rows(G, "A_orig_"), R, 0, 2, C.COLLATE_ADD_EOS)
     assert not ov.any()
     assert np.array_equal(ids, G["A_out_original_generate_response"])
-    assert np.array_equal(mask, G["A_out_original_generate_response_attention_mask"])
+    assert np.array_equal(mask.astype(bool), G["A_out_original_generate_response_attention_mask"])
     assert np.array_equal(sc, G["A_out_original_generate_response_scores"])
     assert np.array_equal(rel, G["A_out_original_generate_response_image_relations"])
     ids, mask, sc, rel, ov = C.collate_responses(unpack_rows(G, "A_ai_"), R, 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
     assert np.array_equal(ids, G["A_out_AI_pseudo_response"])
-    assert np.array_equal(mask, G["A_out_AI_pseudo_response_attention_mask"])
+    assert np.array_equal(mask.astype(bool), G["A_out_AI_pseudo_response_attention_mask"])
     assert np.array_equal(sc, G["A_out_AI_pseudo_response_scores"])
     assert np.array_equal(rel, G["A_out_AI_pseudo_response_image_relations"])
     # standard response and queries: plain tokenisation
@@ -114,20 +106,6 @@ def test_oracle_resize_vs_pillow():
         assert np.array_equal(C.pil_resize_bicubic(img, ow, oh), ref), (H, W, oh, ow)
 
 
-def _mask_cases(G):
-    for name in ("E0", "E1", "E2", "E3", "E4"):
-        cfg = json.loads(str(G[name + "_cfg"]))
-        yield name, cfg
-
-
-def _mask_input(G, name, cfg):
-    if name + "_in" in G:
-        return G[name + "_in"]
-    import torch
-    g = torch.Generator().manual_seed(cfg["seed"])
-    return torch.randn(tuple(cfg["shape"]), generator=g).numpy()
-
-
 def test_oracle_copo_masks_vs_reference(G):
     for name, cfg in _mask_cases(G):
         img = _mask_input(G, name, cfg)
@@ -192,7 +170,7 @@ def test_kernel_core_responses_vs_reference(harness, G):
     for R2 in (5, 17, 30):
         want = C.collate_responses(rows, R2, 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
         got = _harness_responses(harness, G, "A_ai_", R2, C.COLLATE_ADD_EOS | C.COLLATE_PAD_EOS)
-        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].astype(bool), want[1])
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
         assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]) and np.array_equal(got[4].astype(bool), want[4])
 
 
@@ -210,30 +188,12 @@ def _pack(rows):
             "seg_relation": np.asarray(rel + [0], np.float32), "seg_flags": np.asarray(fl + [0], np.uint8), "row_offsets": np.asarray(ro, np.int64)}
 
 
-def random_rows(rs, b, max_segs, max_len, R):
-    """Ragged random reports incl. empty rows, BOS-only entries, leading-29871 entries, pad / EOS ids inside the text."""
-    rows = []
-    for i in range(b):
-        segs = []
-        for j in range(rs.randint(0, max_segs + 1)):
-            n = rs.randint(0, max_len + 1)
-            raw = [1] + rs.randint(3, 32000, n).tolist()
-            if n and rs.rand() < 0.3:
-                raw[1] = C.SPACE_TOKEN
-            if n > 2 and rs.rand() < 0.15:
-                raw[rs.randint(1, n + 1)] = rs.choice([0, 2])
-            fl = (C.FLAG_KEEP_BOS if j == 0 else 0) | (C.FLAG_STRIP_SPACE if rs.rand() < 0.5 else 0)
-            segs.append((raw, float(rs.choice([1.0, 1.5, 2.0, 2.5, 0.0])), float(rs.choice([1.0, 3.0])), fl))
-        rows.append(segs)
-    return rows
-
-
 def test_kernel_core_responses_random_ragged_vs_oracle(harness):
     rs = np.random.RandomState(3)
     for trial in range(40):
         R = int(rs.choice([1, 2, 7, 33, 128]))
         rows = random_rows(rs, int(rs.randint(1, 6)), 6, 12, R)
-        for mode in (0, 1, 3, 5, 7):
+        for mode in (0, 1, 3, 5, 7, 8, 9, 13):
             want = C.collate_responses(rows, R, 0, 2, mode)
             got = _harness_responses(harness, _pack(rows), "", R, mode)
             for a, w, name in zip(got, want, ("ids", "mask", "scores", "relations", "overflow")):
@@ -308,3 +268,37 @@ def test_kernel_core_bf16_rounding(harness):
     got = torch.tensor([harness.host_round_bf16(float(v)) for v in x])
     assert torch.equal(got, want)
     assert np.array_equal(C._round_bf16(x.numpy()), want.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ host mirror (strings)
+def test_host_mirror_realign_copied_vs_reference(G):
+    from opa_dpo_b200.collate import realign_copied
+    for original, pieces, want in json.loads(str(G["F_realign"])):
+        assert realign_copied(original, list(pieces)) == want, (original, pieces)
+
+
+def test_host_mirror_report_segments_vs_reference_tokenizer_log(G):
+    """B200DataCollator's host half (JSON report -> flat segment arrays) against the arrays rebuilt from the tokenizer
+    calls the REFERENCE collator made on the same instances."""
+    from opa_dpo_b200.collate import report_segments, plain_pack
+    tok = C.StubTokenizer()
+    inst = json.loads(str(G["A_instances"]))
+    reports = [json.loads(i["AI_json_report"]) for i in inst]
+    orig, ai = report_segments(tok.encode_one, reports, [i["original_generate_response"] for i in inst])
+    for name, pack in (("orig", orig), ("ai", ai)):
+        for k, v in pack.arrays().items():
+            assert np.array_equal(v, G[f"A_{name}_{k}"]), (name, k)
+    assert min(orig.row_present + ai.row_present) > 0
+    p = plain_pack([tok.encode_one(i["standard_response"]) for i in inst]).arrays()
+    rows = [[(p["tokens"][p["seg_offsets"][j]:p["seg_offsets"][j + 1]].tolist(), 0.0, 0.0, int(p["seg_flags"][j]))] for j in range(len(inst))]
+    ids, mask, *_ = C.collate_responses(rows, int(G["A_QR"][1]), 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_TRUNCATE | C.COLLATE_TOKEN_MASK)
+    assert np.array_equal(ids, G["A_out_standard_response"])
+
+
+def test_oracle_tokenizer_mask_mode_vs_reference(G):
+    """Plain branch: the batch carries the TOKENIZER's attention mask (the EOS written over the first pad stays 0)."""
+    toks = json.loads(str(G["C_tokens"]))
+    rows = [[(t, 0.0, 0.0, C.FLAG_KEEP_BOS)] for t in toks["standard_response"]]
+    _, mask, *_ = C.collate_responses(rows, int(G["A_QR"][1]), 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_TRUNCATE | C.COLLATE_TOKEN_MASK)
+    assert np.array_equal(mask, G["C_out_standard_response_attention_mask"])
+    assert mask[0].max() == 2, "add_eos also overwrites the attention mask's first 0 with eos_id"
