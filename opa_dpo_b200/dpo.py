@@ -50,6 +50,14 @@ class DPOArgs:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_epsilon: float = 1e-8
+    # loop shape (opadpo_train.py:410-437; effective defaults of run/train_opa_dpo.sh:39-44)
+    CoPO_method: str = "random"            # random | blockwise | attention
+    CoPO_mask_ratio: float = 0.3
+    rollout_accumulation_steps: int = 8
+    step_per_device_batch_size: int = 2
+    gradient_accumulation_steps: int = 4
+    noptepochs: int = 1
+    bf16: bool = True
 
 
 def _ptr(t: Optional[Tensor]):

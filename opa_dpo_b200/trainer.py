@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's outer training loop on the engine.
+
+`B200DPOTrainer` keeps the shape of `DPOTrainer` / `RLTrainer` (opadpo/dpo_models/dpo_trainer.py:214-427, 475-802;
+rl_trainer.py:138-195) — `rollout(queries_batches)`, `compute_policy_loss(rollouts_batch)`,
+`step_with_rollouts(rollouts)`, `step(train_dataloader, step_idx)` — with what the row asks for:
+
+* the reference-adapter pass runs on the device inside the step and its outputs STAY in HBM: no `.cpu()` parking of the
+  rollouts (dpo_trainer.py:421-424), no per-batch `gc.collect()` / `empty_cache()` (:227-228, rl_trainer.py:153-154), no
+  re-upload in compute_policy_loss (:489-560);
+* the discarded policy forward of rollout() (:336-338) is dropped — its outputs are never read;
+* with `merge_frozen` the frozen reference adapter runs on merged weights (no LoRA GEMMs at all);
+* `noptepochs > 1` reuses the same rollouts, as the reference does.
+Sharing one GEMM launch between the reference and the policy pass was evaluated and left out: their activations differ
+from the first LoRA layer on, so no FLOPs are shared, and at M >= 13k rows the GEMMs are tensor-bound — streaming the
+base weights once instead of twice saves < 1 %.
+
+The shuffled mini-batch order comes from torch's own DataLoader over row indices, so a seeded run visits the rollouts in
+the reference's order (rl_trainer.py:325-345). Gradient accumulation follows accelerate 0.21's counter (a boundary every
+`gradient_accumulation_steps` micro-batches, the loss divided by it) [UPSTREAM accelerate]; the LR scheduler steps once
+per outer step (rl_trainer.py:188-189).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.utils.data import DataLoader
+
+from . import collate
+from .dist import OverlappedGradAllReduce, allreduce_grad_bucket
+from .dpo import DPOArgs, FusedDPO
+
+RESPONSES = ("standard_response", "original_generate_response", "AI_pseudo_response")
+_OPTIONAL = ("original_generate_response_scores", "AI_pseudo_response_scores", "original_generate_response_image_relations",
+             "AI_pseudo_response_image_relations")
+
+
+class B200DPOTrainer:
+    def __init__(self, args: DPOArgs, policy, ref_policy, optimizer, lr_scheduler=None, world_size: int = 1,
+                 process_group=None):
+        self.args, self.policy, self.ref_policy = args, policy, ref_policy
+        self.optimizer, self.lr_scheduler = optimizer, lr_scheduler
+        self.loss = FusedDPO(args)
+        self.model = policy.base_model
+        self.device = self.model.engine.device
+        self.world_size, self.process_group = world_size, process_group
+        self._micro_step = 0
+        self.overlap = None
+        if world_size > 1 and self.model.flat_param is not None:
+            self.overlap = OverlappedGradAllReduce(self.model.engine, self.model.flat_param.grad, process_group)
+
+    # ------------------------------------------------------------------ rollout (dpo_trainer.py:214-427)
+    @torch.no_grad()
+    def rollout(self, queries_data: Iterable[Dict[str, Tensor]]) -> Dict[str, Tensor]:
+        a = self.args
+        self.policy.eval()
+        self.ref_policy.eval()
+        out: List[Dict[str, Tensor]] = []
+        dev = self.device
+        for batch in queries_data:
+            images = batch["images"].to(dev)
+            if a.bf16:
+                images = images.to(torch.bfloat16)          # :283-286 (the CoPO mean is taken over bf16 pixels)
+            rb = {"images": images, "queries": batch["queries"].to(dev),
+                  "queries_attn_masks": batch["queries_attention_mask"].to(dev)}
+            for n in RESPONSES:
+                rb[n] = batch[n].to(dev)
+                rb[n + "_attention_mask"] = batch[n + "_attention_mask"].to(dev)
+            fwd = {k: rb[k] for k in ("images", "queries", "queries_attn_masks") + RESPONSES}
+            new_fwd = None
+            if a.CoPO:
+                sub = {"standard_response": rb["standard_response"], "AI_pseudo_response": rb["AI_pseudo_response"]}
+                if a.CoPO_method in ("random", "blockwise"):
+                    rb["masked_images"] = collate.mask_images(images, a.CoPO_mask_ratio, a.CoPO_method)
+                    new_fwd = dict(images=rb["masked_images"], queries=rb["queries"], queries_attn_masks=rb["queries_attn_masks"], **sub)
+                elif a.CoPO_method == "attention":
+                    assert images.size(-1) % 14 == 0
+                    holes = collate.mask_percentage_per_row(images.size(0), (images.size(-1) // 14) ** 2, a.CoPO_mask_ratio, dev)
+                    rb["masked_query_attn_masks"] = torch.cat([holes.to(rb["queries_attn_masks"].dtype), rb["queries_attn_masks"]], 1)
+                    new_fwd = dict(images=images, queries=rb["queries"], queries_attn_masks=rb["masked_query_attn_masks"], **sub)
+                else:
+                    raise NotImplementedError
+            ref = self.ref_policy(**fwd, temperature=a.temperature)
+            rb.update({"ref_base_" + k: v for k, v in ref.items()})
+            if new_fwd is not None:
+                ref_m = self.ref_policy(**new_fwd, temperature=a.temperature)
+                rb.update({"ref_mask_" + k: v for k, v in ref_m.items()})
+            if a.detailed_report and (a.response_score or a.response_image_relation):
+                for k in _OPTIONAL:
+                    rb[k] = batch[k].to(dev)
+            out.append(rb)
+        return {k: torch.cat([b[k] for b in out]) for k in out[0]}
+
+    # ------------------------------------------------------------------ loss (dpo_trainer.py:475-802)
+    def compute_policy_loss(self, rb: Dict[str, Tensor]) -> Tuple[Tensor, Dict[str, Tensor]]:
+        a = self.args
+        self.policy.train()
+        resp = {n: rb[n] for n in RESPONSES}
+        outputs = self.policy(images=rb["images"], queries=rb["queries"], queries_attn_masks=rb["queries_attn_masks"],
+                              temperature=a.temperature, mode="policy", **resp)
+        outputs_new = None
+        if a.CoPO:
+            new = {"mask_standard_response": rb["standard_response"], "mask_AI_pseudo_response": rb["AI_pseudo_response"]}
+            if a.CoPO_method in ("random", "blockwise"):
+                outputs_new = self.policy(images=rb["masked_images"], queries=rb["queries"],
+                                          queries_attn_masks=rb["queries_attn_masks"], temperature=a.temperature,
+                                          mode="policy", **new)
+            else:
+                outputs_new = self.policy(images=rb["images"], queries=rb["queries"],
+                                          queries_attn_masks=rb["masked_query_attn_masks"], temperature=a.temperature,
+                                          mode="policy", **new)
+        return self.loss.compute_policy_loss(outputs, rb, outputs_new)
+
+    # ------------------------------------------------------------------ optimisation (rl_trainer.py:138-179)
+    def step_with_rollouts(self, rollouts: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        a = self.args
+        n = next(iter(rollouts.values())).size(0)
+        gas = max(1, a.gradient_accumulation_steps)
+        stats_list: List[Dict[str, Tensor]] = []
+        for _epoch in range(a.noptepochs):
+            # the same sampler class the reference's rollouts DataLoader uses -> the same shuffled order under a seed
+            for idx in DataLoader(range(n), batch_size=a.step_per_device_batch_size, shuffle=True, drop_last=True):
+                idx = idx.to(self.device)
+                rb = {k: v.index_select(0, idx) for k, v in rollouts.items()}
+                self._micro_step += 1
+                boundary = self._micro_step % gas == 0
+                if self.overlap is not None and boundary and not a.CoPO:
+                    self.overlap.arm()       # one backward completes the bucket: all-reduce its slices as they become final
+                loss, stats = self.compute_policy_loss(rb)
+                (loss / gas).backward()
+                if boundary:
+                    stats["loss/grad_norm"] = self._optimizer_step()
+                    stats_list.append(stats)
+        if not stats_list:
+            return {}
+        return {k: torch.stack([s[k] for s in stats_list]) for k in stats_list[0]}
+
+    def _optimizer_step(self) -> Tensor:
+        if self.overlap is not None:
+            scale = self.overlap.finish()      # slices already in flight, or one bucket-wide all-reduce when not armed
+        elif self.world_size > 1:
+            scale = allreduce_grad_bucket(self.model.flat_param.grad, self.process_group)
+        else:
+            scale = 1.0
+        norm = self.optimizer.step(scale)      # clip_grad_norm_ + AdamW, fused (rl_trainer.py:164-175)
+        self.optimizer.zero_grad()
+        return norm.reshape(())
+
+    def step(self, train_dataloader, step_idx: int = 0) -> Dict[str, Tensor]:
+        batches = [next(train_dataloader) for _ in range(self.args.rollout_accumulation_steps)]
+        rollouts = self.rollout(batches)
+        stats = self.step_with_rollouts(rollouts)
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        return stats

@@ -583,3 +583,104 @@ def test_reference_pass_on_merged_frozen_adapter(share):
     for i, n in enumerate(NAMES2):
         _cmp_lp(swapped[i], pol_o[n + "_logprobs"], f"reloaded+remerged {n} logprobs")
     eng.close()
+
+
+def test_trainer_mirror_outer_step_matches_manual_composition():
+    """B200DPOTrainer (rollout -> step_with_rollouts with CoPO, grad accumulation, noptepochs=2, shuffled mini-batches)
+    against the same step composed by hand from the parity-tested pieces (reference-adapter pass, policy pass,
+    FusedDPO.compute_policy_loss, LoRA backward, fused clip+AdamW): the same LoRA masters afterwards. Not bit for bit:
+    the LoRA wgrad GEMMs accumulate split-K partials with fp32 atomics, so two runs differ in the last bits of the
+    gradient and Adam's first steps (update ~ lr * sign(g)) amplify that at elements whose gradient is ~0; tolerance:
+    the two parameter updates have cosine >= 0.999 and 99.5 % of the elements agree to 1e-6."""
+    from types import SimpleNamespace
+    from torch.utils.data import DataLoader
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import collate
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    from opa_dpo_b200.optim import B200AdamW
+    from opa_dpo_b200.trainer import B200DPOTrainer, RESPONSES
+    oc, ec = _cfgs()
+    R = 24
+    args = DPOArgs(beta=0.1, CoPO=True, CoPO_method="random", CoPO_mask_ratio=0.3, CoPO_coef=0.2, AncPO=True, response_len=R,
+                   rollout_accumulation_steps=2, step_per_device_batch_size=2, gradient_accumulation_steps=2, noptepochs=2,
+                   bf16=True)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    w = O.init_weights(oc)
+    lp, lr = O.init_lora(oc, 11), O.init_lora(oc, 12)
+
+    def make():
+        model = B200LlavaModel(ec)
+        sd = dict(w)
+        sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+        model.engine.load_state_dict(sd)
+        for name, lo in (("lora_policy", lp), ("lora_ref_policy", lr)):
+            model.load_adapter_state(name, {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lo.items() for x, t in zip("AB", ab)})
+        model.make_trainable("lora_policy")
+        return (model, AutoregressivePolicy(args, model, tok, "lora_policy"), AutoregressivePolicy(args, model, tok, "lora_ref_policy"),
+                B200AdamW(model, lr=1e-3))
+
+    batches = []
+    for s in range(2):
+        images, q, qm, resp = O.synthetic_batch(oc, 2, 16, R, list(RESPONSES), seed=100 + s, left_pad=2)
+        b = {"images": images, "queries": q, "queries_attention_mask": qm.long()}
+        for n in RESPONSES:
+            b[n] = resp[n]
+            b[n + "_attention_mask"] = (resp[n] != 0).long()
+        batches.append(b)
+
+    # ---- the trainer
+    model, policy, ref_policy, opt = make()
+    tr = B200DPOTrainer(args, policy, ref_policy, opt)
+    torch.manual_seed(7)
+    stats = tr.step(iter(batches))
+    torch.cuda.synchronize()
+    assert stats["loss/grad_norm"].shape == (2,) and torch.isfinite(stats["loss/grad_norm"]).all()   # 4 micro-batches / gas 2
+    got = model.engine.buffers()["master"].clone()
+    assert opt.step_count == 2
+    model.engine.close()
+    init = None
+
+    # ---- by hand, same random stream
+    model, policy, ref_policy, opt = make()
+    dev = model.engine.device
+    init = model.engine.buffers()["master"].clone()
+    fused = FusedDPO(args)
+    torch.manual_seed(7)
+    rows = []
+    with torch.no_grad():
+        for b in batches:
+            img = b["images"].to(dev).to(torch.bfloat16)
+            masked = collate.mask_images(img, 0.3, "random")
+            resp = {n: b[n].to(dev) for n in RESPONSES}
+            sub = {"standard_response": resp["standard_response"], "AI_pseudo_response": resp["AI_pseudo_response"]}
+            r = {"images": img, "masked_images": masked, "queries": b["queries"].to(dev), "qm": b["queries_attention_mask"].to(dev), **resp}
+            r.update({"ref_base_" + k: v for k, v in ref_policy(img, r["queries"], r["qm"], **resp).items()})
+            r.update({"ref_mask_" + k: v for k, v in ref_policy(masked, r["queries"], r["qm"], **sub).items()})
+            rows.append(r)
+    ro = {k: torch.cat([r[k] for r in rows]) for k in rows[0]}
+    micro = 0
+    for _ in range(2):
+        for idx in DataLoader(range(4), batch_size=2, shuffle=True, drop_last=True):
+            idx = idx.to(dev)
+            rb = {k: v.index_select(0, idx) for k, v in ro.items()}
+            policy.train()
+            out = policy(rb["images"], rb["queries"], rb["qm"], mode="policy", **{n: rb[n] for n in RESPONSES})
+            out_m = policy(rb["masked_images"], rb["queries"], rb["qm"], mode="policy",
+                           mask_standard_response=rb["standard_response"], mask_AI_pseudo_response=rb["AI_pseudo_response"])
+            loss, _ = fused.compute_policy_loss(out, rb, out_m)
+            (loss / 2).backward()
+            micro += 1
+            if micro % 2 == 0:
+                opt.step(1.0)
+                opt.zero_grad()
+    torch.cuda.synchronize()
+    want = model.engine.buffers()["master"]
+    n_train = model.engine.buffers()["n_train"]
+    d_got, d_want = (got - init)[:n_train], (want - init)[:n_train]
+    assert d_want.abs().max().item() > 1e-4, "the step must move the parameters"
+    cos = torch.nn.functional.cosine_similarity(d_got, d_want, dim=0).item()
+    close = ((d_got - d_want).abs() <= 1e-6).float().mean().item()
+    assert cos >= 0.999 and close >= 0.995, (cos, close)
+    assert torch.equal(got[n_train:], want[n_train:])          # the CLIP-tower LoRA tail is never trained
+    model.engine.close()
