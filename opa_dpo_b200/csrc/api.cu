@@ -153,7 +153,7 @@ int opadpo_op_collate_responses(const opadpo_segments* s, int32_t R, int32_t pad
                                 int64_t* ids, uint8_t* attn_mask, float* scores, float* relations, int32_t* overflow,
                                 void* stream) {
   g_last_error[0] = 0;
-  if (!s || !ids || s->b < 0 || R <= 0 || (s->b > 0 && (!s->seg_offsets || !s->seg_flags || !s->row_offsets))) {
+  if (!s || !ids || s->b < 0 || R <= 0 || (s->b > 0 && (!s->seg_offsets || !s->row_offsets))) {  // seg_* may be NULL when no row has an entry
     set_error("opadpo_op_collate_responses: null pointer or bad sizes");
     return OPADPO_EINVAL;
   }
