@@ -302,3 +302,19 @@ def test_oracle_tokenizer_mask_mode_vs_reference(G):
     _, mask, *_ = C.collate_responses(rows, int(G["A_QR"][1]), 0, 2, C.COLLATE_ADD_EOS | C.COLLATE_TRUNCATE | C.COLLATE_TOKEN_MASK)
     assert np.array_equal(mask, G["C_out_standard_response_attention_mask"])
     assert mask[0].max() == 2, "add_eos also overwrites the attention mask's first 0 with eos_id"
+
+
+def test_collator_product_has_no_cpu_path():
+    """Without a CUDA device the collator ops raise; they never route through the oracle or any CPU implementation."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from opa_dpo_b200 import collate as K
+    from opa_dpo_b200._lib import OpadpoError
+    with pytest.raises(OpadpoError):
+        K.collate_queries([[1, 2, 3]], 8, 0)
+    with pytest.raises(OpadpoError):
+        K.preprocess_images([np.zeros((4, 4, 3), np.uint8)], 8)
+    import inspect
+    src = inspect.getsource(K)
+    assert "oracle" not in src.replace("the oracle", "")
