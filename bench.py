@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 Q_LEN, R_LEN, IMG_POS = 128, 512, 35
-MERGE_FROZEN_DEFAULT = 0   # flipped to 1 once the merged reference pass is parity-checked and measured on the GPU
+MERGE_FROZEN_DEFAULT = 1   # measured: 621 vs 635 ms/step, parity test green (profiles/r01_bench_s3_*.log); --merge-frozen 0 runs it unmerged
 
 
 def _peaks():
