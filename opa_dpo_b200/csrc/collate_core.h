@@ -156,6 +156,15 @@ OPADPO_HD float normalise_pixel(uint8_t v, float mean, float std) {
   return (x - mean) / std;
 }
 
+// Canvas rows above / below the pasted image hold only the background colour, so their horizontal pass is the same for
+// all of them: it is computed once, for the first such row, and every other padding row reads that one.
+OPADPO_HD bool is_padding_row(const ImageDesc& d, int y) { return y < d.oy || y >= d.oy + d.H; }
+OPADPO_HD int tmp_row(const ImageDesc& d, int y) {
+  if (!is_padding_row(d, y)) return y;
+  return d.oy > 0 ? 0 : d.oy + d.H;
+}
+OPADPO_HD bool h_row_needed(const ImageDesc& d, int y) { return tmp_row(d, y) == y; }
+
 // Vertical pass over the horizontal-pass rows `tmp` [Hs, S, 3] for output (yy, xx, c), then normalisation.
 OPADPO_HD float resample_v(const uint8_t* tmp, const ImageDesc& d, const int32_t* tab, int S, int yy, int xx, int c, float mean,
                            float std) {
@@ -164,8 +173,46 @@ OPADPO_HD float resample_v(const uint8_t* tmp, const ImageDesc& d, const int32_t
   const int32_t* by = kky + static_cast<int64_t>(S) * d.ksy + 2 * yy;
   const int y0 = by[0], n = by[1];
   int32_t ss = 1 << (kPrecisionBits - 1);
-  for (int k = 0; k < n; ++k) ss += static_cast<int32_t>(tmp[(static_cast<int64_t>(y0 + k) * S + xx) * 3 + c]) * kk[k];
+  for (int k = 0; k < n; ++k)
+    ss += static_cast<int32_t>(tmp[(static_cast<int64_t>(tmp_row(d, y0 + k)) * S + xx) * 3 + c]) * kk[k];
   return normalise_pixel(clip8(ss), mean, std);
+}
+
+// ---- the forms the fast kernels use (same arithmetic, different data movement)
+// Byte i (= x * 3 + c) of canvas row y: what the horizontal kernel stages into shared memory.
+OPADPO_HD uint8_t canvas_byte(const uint8_t* img, const ImageDesc& d, int y, int i, const uint8_t* bg) {
+  return static_cast<uint8_t>(canvas_pixel(img, d, i / 3, y, i % 3, bg));
+}
+// Horizontal pass for output byte e (= xx * 3 + c) from a staged canvas row.
+OPADPO_HD uint8_t resample_h_staged(const uint8_t* row, const ImageDesc& d, const int32_t* tab, int S, int e) {
+  const int xx = e / 3, c = e - xx * 3;
+  const int32_t* kk = tab + static_cast<int64_t>(xx) * d.ksx;
+  const int32_t* bx = tab + static_cast<int64_t>(S) * d.ksx + 2 * xx;
+  const int x0 = bx[0], n = bx[1];
+  int32_t ss = 1 << (kPrecisionBits - 1);
+  for (int k = 0; k < n; ++k) ss += static_cast<int32_t>(row[(x0 + k) * 3 + c]) * kk[k];
+  return clip8(ss);
+}
+// Vertical pass for the four output bytes 4q .. 4q+3 of output row yy (needs S * 3 % 4 == 0 and 4-byte aligned rows):
+// one 32-bit load per tap row instead of four byte loads. res[j] is the resampled byte, not yet normalised.
+OPADPO_HD void resample_v_quad(const uint8_t* tmp, const ImageDesc& d, const int32_t* tab, int S, int yy, int q, uint8_t res[4]) {
+  const int32_t* kky = tab + static_cast<int64_t>(S) * d.ksx + 2 * S;
+  const int32_t* kk = kky + static_cast<int64_t>(yy) * d.ksy;
+  const int32_t* by = kky + static_cast<int64_t>(S) * d.ksy + 2 * yy;
+  const int y0 = by[0], n = by[1];
+  int32_t s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0, s3 = s0;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(tmp + static_cast<int64_t>(tmp_row(d, y0 + k)) * S * 3 + 4 * q);
+    const int32_t c = kk[k];
+    s0 += static_cast<int32_t>(w & 0xffu) * c;
+    s1 += static_cast<int32_t>((w >> 8) & 0xffu) * c;
+    s2 += static_cast<int32_t>((w >> 16) & 0xffu) * c;
+    s3 += static_cast<int32_t>(w >> 24) * c;
+  }
+  res[0] = clip8(s0);
+  res[1] = clip8(s1);
+  res[2] = clip8(s2);
+  res[3] = clip8(s3);
 }
 
 // float32 -> bf16 (round to nearest even) -> float32: the trainer masks images it has already cast to bf16.

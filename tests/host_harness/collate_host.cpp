@@ -51,8 +51,11 @@ void host_collate_queries(const int32_t* tokens, const int64_t* offsets, int b, 
                &mask[static_cast<int64_t>(row) * Q + p]);
 }
 
+// fast = 0: the generic per-tap bounds-checked forms; fast = 1: the forms the staged / quad kernels use (canvas row staged
+// in a buffer, four bytes per 32-bit load). Rows the kernels skip (all-background rows but the first) are poisoned.
 void host_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n,
-                            int S, const float* mean3, const float* std3, const uint8_t* bg3, int pad_to_square, float* out) {
+                            int S, const float* mean3, const float* std3, const uint8_t* bg3, int pad_to_square, int fast,
+                            float* out) {
   for (int i = 0; i < n; ++i) {
     ImageDesc d{};
     std::vector<int32_t> tables;
@@ -60,16 +63,37 @@ void host_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const
     plan_image(heights[i], widths[i], S, pad_to_square != 0, &d, &tables, &tmp_bytes);
     d.pix_off = offsets[i];
     d.tmp_off = 0;
-    std::vector<uint8_t> tmp(static_cast<size_t>(tmp_bytes));
+    std::vector<uint32_t> tmp_words((static_cast<size_t>(tmp_bytes) + 3) / 4, 0xAAAAAAAAu);   // 4-byte aligned
+    uint8_t* tmp = reinterpret_cast<uint8_t*>(tmp_words.data());
     const uint8_t* img = pixels + d.pix_off;
     const int32_t* tab = tables.data() + d.tab_off;
-    for (int y = 0; y < d.Hs; ++y)
-      for (int xx = 0; xx < S; ++xx)
-        for (int c = 0; c < 3; ++c) tmp[(static_cast<int64_t>(y) * S + xx) * 3 + c] = resample_h(img, d, tab, S, y, xx, c, bg3);
-    for (int yy = 0; yy < S; ++yy)
-      for (int xx = 0; xx < S; ++xx)
-        for (int c = 0; c < 3; ++c)
-          out[((static_cast<int64_t>(i) * 3 + c) * S + yy) * S + xx] = resample_v(tmp.data(), d, tab, S, yy, xx, c, mean3[c], std3[c]);
+    std::vector<uint8_t> row(static_cast<size_t>(d.Ws) * 3);
+    for (int y = 0; y < d.Hs; ++y) {
+      if (!h_row_needed(d, y)) continue;
+      if (fast) {
+        for (int b = 0; b < d.Ws * 3; ++b) row[b] = canvas_byte(img, d, y, b, bg3);
+        for (int e = 0; e < S * 3; ++e) tmp[static_cast<int64_t>(y) * S * 3 + e] = resample_h_staged(row.data(), d, tab, S, e);
+      } else {
+        for (int xx = 0; xx < S; ++xx)
+          for (int c = 0; c < 3; ++c) tmp[(static_cast<int64_t>(y) * S + xx) * 3 + c] = resample_h(img, d, tab, S, y, xx, c, bg3);
+      }
+    }
+    for (int yy = 0; yy < S; ++yy) {
+      if (fast && (S * 3) % 4 == 0) {
+        for (int q = 0; q < S * 3 / 4; ++q) {
+          uint8_t r[4];
+          resample_v_quad(tmp, d, tab, S, yy, q, r);
+          for (int j = 0; j < 4; ++j) {
+            const int e = 4 * q + j, xx = e / 3, c = e - xx * 3;
+            out[((static_cast<int64_t>(i) * 3 + c) * S + yy) * S + xx] = normalise_pixel(r[j], mean3[c], std3[c]);
+          }
+        }
+      } else {
+        for (int xx = 0; xx < S; ++xx)
+          for (int c = 0; c < 3; ++c)
+            out[((static_cast<int64_t>(i) * 3 + c) * S + yy) * S + xx] = resample_v(tmp, d, tab, S, yy, xx, c, mean3[c], std3[c]);
+      }
+    }
   }
 }
 

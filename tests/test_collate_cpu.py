@@ -221,7 +221,7 @@ def test_kernel_core_queries_vs_reference(harness, G):
     assert np.array_equal(ids[:2], G["C_out_queries"])
 
 
-def _harness_preprocess(lib, imgs, S, pad):
+def _harness_preprocess(lib, imgs, S, pad, fast=1):
     import ctypes
     flat = np.concatenate([i.reshape(-1) for i in imgs]).astype(np.uint8)
     off = np.asarray(np.cumsum([0] + [i.size for i in imgs])[:-1], np.int64)
@@ -230,7 +230,7 @@ def _harness_preprocess(lib, imgs, S, pad):
     mean, std = np.asarray(C.CLIP_MEAN, np.float32), np.asarray(C.CLIP_STD, np.float32)
     bg = np.asarray([int(x * 255) for x in C.CLIP_MEAN], np.uint8)
     out = np.full((len(imgs), 3, S, S), np.nan, np.float32)
-    lib.host_preprocess_images(_p(flat), _p(off), _p(hs), _p(ws), len(imgs), S, _p(mean), _p(std), _p(bg), int(pad), _p(out))
+    lib.host_preprocess_images(_p(flat), _p(off), _p(hs), _p(ws), len(imgs), S, _p(mean), _p(std), _p(bg), int(pad), int(fast), _p(out))
     return out
 
 
@@ -238,24 +238,26 @@ def test_kernel_core_image_preprocess_vs_reference(harness, G):
     i = 0
     while f"D{i}_in" in G:
         S, pad = G[f"D{i}_cfg"]
-        got = _harness_preprocess(harness, [G[f"D{i}_in"]], int(S), bool(pad))[0]
-        assert np.array_equal(got, G[f"D{i}_out"]), f"case {i}"
+        for fast in (0, 1):
+            got = _harness_preprocess(harness, [G[f"D{i}_in"]], int(S), bool(pad), fast)[0]
+            assert np.array_equal(got, G[f"D{i}_out"]), f"case {i} fast={fast}"
         i += 1
     for key, ref in json.loads(str(G["D_big"])).items():
         H, W, seed = map(int, key.split("x"))
         img = np.random.RandomState(seed).randint(0, 256, (H, W, 3)).astype(np.uint8)
-        out = _harness_preprocess(harness, [img], 336, True)[0]
-        assert hashlib.sha256(out.tobytes()).hexdigest() == ref["sha256"], key
+        for fast in (0, 1):
+            out = _harness_preprocess(harness, [img], 336, True, fast)[0]
+            assert hashlib.sha256(out.tobytes()).hexdigest() == ref["sha256"], (key, fast)
 
 
 def test_kernel_core_image_preprocess_ragged_batch_vs_oracle(harness):
     rs = np.random.RandomState(11)
     shapes = [(1, 1), (2, 9), (9, 2), (57, 31), (31, 57), (64, 64), (130, 77), (400, 123)]
     imgs = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in shapes]
-    for S, pad in ((32, True), (32, False), (48, True)):
-        got = _harness_preprocess(harness, imgs, S, pad)
+    for S, pad, fast in ((32, True, 1), (32, False, 1), (48, True, 0), (30, True, 1), (31, False, 1), (30, False, 0)):
+        got = _harness_preprocess(harness, imgs, S, pad, fast)     # S = 30, 31: 3*S not a multiple of 4 -> no quad path
         for j, im in enumerate(imgs):
-            assert np.array_equal(got[j], C.clip_preprocess(im, S, pad)), (shapes[j], S, pad)
+            assert np.array_equal(got[j], C.clip_preprocess(im, S, pad)), (shapes[j], S, pad, fast)
 
 
 def test_kernel_core_bf16_rounding(harness):

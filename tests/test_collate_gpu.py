@@ -248,3 +248,45 @@ def test_collator_full_size_properties():
     same = K.preprocess_images([sq], 336, True)[0].cpu().numpy()
     plain = ((sq.astype(np.float64) * (1 / 255)).astype(np.float32) - np.asarray(C.CLIP_MEAN, np.float32)) / np.asarray(C.CLIP_STD, np.float32)
     assert np.array_equal(same, plain.transpose(2, 0, 1))
+
+
+def test_preprocess_images_generic_kernels_vs_oracle():
+    """The fallback kernels: a canvas row wider than shared memory (W*3 > 48 KB -> per-tap bounds-checked horizontal pass)
+    and an output size whose row is not a multiple of 4 bytes (-> scalar vertical pass)."""
+    from oracle import collate_oracle as C
+    from opa_dpo_b200 import collate as K
+    rs = np.random.RandomState(13)
+    wide = rs.randint(0, 256, (3, 16400, 3)).astype(np.uint8)
+    small = rs.randint(0, 256, (45, 61, 3)).astype(np.uint8)
+    for S in (30, 32):
+        got = K.preprocess_images([wide, small], S, False).cpu().numpy()
+        assert np.array_equal(got[0], C.clip_preprocess(wide, S, False)), ("wide", S)
+        assert np.array_equal(got[1], C.clip_preprocess(small, S, False)), ("small", S)
+    got = K.preprocess_images([small], 30, True).cpu().numpy()
+    assert np.array_equal(got[0], C.clip_preprocess(small, 30, True))
+
+
+def test_collate_responses_many_segments_fallback_vs_oracle():
+    """Rows with more entries than the kernel indexes in shared memory (512) take the per-position walk; rows with many
+    empty / BOS-only entries exercise the boundary handling of the binary search."""
+    from oracle import collate_oracle as C
+    from opa_dpo_b200 import collate as K
+    rs = np.random.RandomState(21)
+    rows = []
+    for nseg in (600, 512, 513, 40):
+        segs = []
+        for j in range(nseg):
+            n = int(rs.choice([0, 0, 1, 2, 3]))
+            raw = [1] + rs.randint(3, 32000, n).tolist()
+            if n and rs.rand() < 0.3:
+                raw[1] = C.SPACE_TOKEN
+            segs.append((raw, float(rs.choice([1.0, 2.5])), float(rs.choice([1.0, 3.0])),
+                         (C.FLAG_KEEP_BOS if j == 0 else 0) | (C.FLAG_STRIP_SPACE if rs.rand() < 0.5 else 0)))
+        rows.append(segs)
+    pack = _rows_to_pack(rows)
+    for R in (64, 896, 2000):
+        for mode in (3, 9):
+            want = C.collate_responses(rows, R, 0, 2, mode)
+            got = K.collate_responses(pack, R, 0, 2, mode)
+            for a, w, name in zip(got, want, ("ids", "mask", "scores", "relations", "overflow")):
+                assert np.array_equal(a.cpu().numpy().astype(w.dtype), w), (R, mode, name)
