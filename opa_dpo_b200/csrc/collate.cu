@@ -218,25 +218,32 @@ __global__ void __launch_bounds__(256) resample_h_kernel(const uint8_t* __restri
   for (int c = 0; c < 3; ++c) o[c] = resample_h(img, d, tab, S, y, xx, c, nm.bg);
 }
 
-// Horizontal pass, staged form: one CTA per canvas row (grid (max Hs, image)). The row — image bytes with the background
-// colour left and right of them — is copied into shared memory with coalesced loads, so the tap loop has no bounds
-// checks; each thread then produces output bytes e = xx*3 + c, written as one contiguous row. Background-only rows are
-// done once per image (h_row_needed).
-__global__ void __launch_bounds__(256) resample_h_staged_kernel(const uint8_t* __restrict__ pixels,
-                                                                const ImageDesc* __restrict__ descs,
-                                                                const int32_t* __restrict__ tables, uint8_t* __restrict__ tmp,
-                                                                int S, Norm3 nm) {
+// Horizontal pass, staged form: one CTA per canvas row (grid (max Hs, image), 128 threads). The row — image bytes with
+// the background colour left and right of them — is copied into shared memory with coalesced loads, so the tap loop has
+// no bounds checks; each thread then produces the three channels of output columns xx, xx + 128, ... with one
+// coefficient load per tap. Background-only rows are done once per image (h_row_needed).
+constexpr int kHThreads = 128;
+__global__ void __launch_bounds__(kHThreads) resample_h_staged_kernel(const uint8_t* __restrict__ pixels,
+                                                                      const ImageDesc* __restrict__ descs,
+                                                                      const int32_t* __restrict__ tables,
+                                                                      uint8_t* __restrict__ tmp, int S, Norm3 nm) {
   extern __shared__ uint8_t canvas_row[];
   const ImageDesc d = descs[blockIdx.y];
   const int y = blockIdx.x;
   if (y >= d.Hs || !h_row_needed(d, y)) return;
-  const uint8_t* img = pixels + d.pix_off;
-  const int row_bytes = d.Ws * 3;
-  for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) canvas_row[i] = canvas_byte(img, d, y, i, nm.bg);
+  const uint8_t* src = is_padding_row(d, y) ? nullptr : pixels + d.pix_off + static_cast<int64_t>(y - d.oy) * d.W * 3;
+  const int lo = d.ox * 3, hi = (d.ox + d.W) * 3, row_bytes = d.Ws * 3;
+  for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) canvas_row[i] = canvas_byte_row(src, lo, hi, i, nm.bg);
   __syncthreads();
   const int32_t* tab = tables + d.tab_off;
   uint8_t* o = tmp + d.tmp_off + static_cast<int64_t>(y) * S * 3;
-  for (int e = threadIdx.x; e < S * 3; e += blockDim.x) o[e] = resample_h_staged(canvas_row, d, tab, S, e);
+  for (int xx = threadIdx.x; xx < S; xx += blockDim.x) {
+    uint8_t r[3];
+    resample_h_staged3(canvas_row, d, tab, S, xx, r);
+    o[xx * 3] = r[0];
+    o[xx * 3 + 1] = r[1];
+    o[xx * 3 + 2] = r[2];
+  }
 }
 
 // Vertical pass + rescale + normalise, generic form: grid (ceil(S * S / 256), image); planar f32 output.
@@ -284,6 +291,22 @@ __global__ void __launch_bounds__(256) resample_v_quad_kernel(const ImageDesc* _
 
 inline unsigned nblocks(int64_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
+// The per-call scratch (cudaMallocAsync) must stay in the device's pool between calls: with the default release
+// threshold of 0 every synchronisation hands it back to the driver and the next call pays a fresh mapping (~0.1 ms per
+// allocation, several times the kernels). The engine does the same at init; the collator ops work without an engine.
+void keep_pool_memory() {
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [dev]() {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  });
+}
+
 }  // namespace
 
 int collate_responses(const collate::Segments& s, int b, int R, int pad_id, int eos_id, int mode, int64_t* ids, uint8_t* mask,
@@ -304,6 +327,7 @@ int collate_queries(const int32_t* tokens, const int64_t* offsets, int b, int Q,
 int mask_images(const float* images, float* out, int n, int C, int H, int W, const int64_t* idx, int m, int block, int bf16_pixels,
                 float* means_out, cudaStream_t st) {
   if (n == 0) return 0;
+  keep_pool_memory();
   const int64_t chw = static_cast<int64_t>(C) * H * W;
   float* means = means_out;
   double* partials = nullptr;
@@ -393,6 +417,7 @@ int preprocess_images(const uint8_t* pixels, const int64_t* h_offsets, const int
                       int S, const float* mean3, const float* std3, const uint8_t* bg3, int pad_to_square, float* out,
                       cudaStream_t st) {
   if (n == 0) return 0;
+  keep_pool_memory();
   int dev = 0;
   OPADPO_CUDA_CHECK(cudaGetDevice(&dev));
   std::vector<ImageDesc> descs(n);
@@ -432,7 +457,7 @@ int preprocess_images(const uint8_t* pixels, const int64_t* h_offsets, const int
   OPADPO_CUDA_CHECK(cudaMemcpyAsync(d_descs, descs.data(), sizeof(ImageDesc) * n, cudaMemcpyHostToDevice, st));
   int rc;
   if (max_ws * 3 <= 48 * 1024) {
-    resample_h_staged_kernel<<<dim3(max_hs, n), 256, max_ws * 3, st>>>(pixels, d_descs, d_tables, d_tmp, S, nm);
+    resample_h_staged_kernel<<<dim3(max_hs, n), kHThreads, max_ws * 3, st>>>(pixels, d_descs, d_tables, d_tmp, S, nm);
     rc = launch_ok("resample_h_staged");
   } else {
     resample_h_kernel<<<dim3(nblocks(static_cast<int64_t>(max_hs) * S, 256), n), 256, 0, st>>>(pixels, d_descs, d_tables, d_tmp, S, nm);

@@ -183,6 +183,29 @@ OPADPO_HD float resample_v(const uint8_t* tmp, const ImageDesc& d, const int32_t
 OPADPO_HD uint8_t canvas_byte(const uint8_t* img, const ImageDesc& d, int y, int i, const uint8_t* bg) {
   return static_cast<uint8_t>(canvas_pixel(img, d, i / 3, y, i % 3, bg));
 }
+// The same byte with the row already resolved: src = first byte of image row (y - oy), or null for a background-only row;
+// [lo, hi) = canvas bytes covered by the image. One range test per byte, the modulo only outside the image.
+OPADPO_HD uint8_t canvas_byte_row(const uint8_t* src, int lo, int hi, int i, const uint8_t* bg) {
+  return (src && i >= lo && i < hi) ? src[i - lo] : bg[i % 3];
+}
+// Horizontal pass for output column xx, all three channels, from a staged canvas row: the coefficient is loaded once per
+// tap and applied to the three interleaved bytes.
+OPADPO_HD void resample_h_staged3(const uint8_t* row, const ImageDesc& d, const int32_t* tab, int S, int xx, uint8_t res[3]) {
+  const int32_t* kk = tab + static_cast<int64_t>(xx) * d.ksx;
+  const int32_t* bx = tab + static_cast<int64_t>(S) * d.ksx + 2 * xx;
+  const int x0 = bx[0], n = bx[1];
+  const uint8_t* px = row + x0 * 3;
+  int32_t s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+  for (int k = 0; k < n; ++k) {
+    const int32_t c = kk[k];
+    s0 += static_cast<int32_t>(px[3 * k]) * c;
+    s1 += static_cast<int32_t>(px[3 * k + 1]) * c;
+    s2 += static_cast<int32_t>(px[3 * k + 2]) * c;
+  }
+  res[0] = clip8(s0);
+  res[1] = clip8(s1);
+  res[2] = clip8(s2);
+}
 // Horizontal pass for output byte e (= xx * 3 + c) from a staged canvas row.
 OPADPO_HD uint8_t resample_h_staged(const uint8_t* row, const ImageDesc& d, const int32_t* tab, int S, int e) {
   const int xx = e / 3, c = e - xx * 3;

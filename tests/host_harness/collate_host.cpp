@@ -70,7 +70,11 @@ void host_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const
     std::vector<uint8_t> row(static_cast<size_t>(d.Ws) * 3);
     for (int y = 0; y < d.Hs; ++y) {
       if (!h_row_needed(d, y)) continue;
-      if (fast) {
+      if (fast == 1) {
+        const uint8_t* src = is_padding_row(d, y) ? nullptr : img + static_cast<int64_t>(y - d.oy) * d.W * 3;
+        for (int b = 0; b < d.Ws * 3; ++b) row[b] = canvas_byte_row(src, d.ox * 3, (d.ox + d.W) * 3, b, bg3);
+        for (int xx = 0; xx < S; ++xx) resample_h_staged3(row.data(), d, tab, S, xx, tmp + (static_cast<int64_t>(y) * S + xx) * 3);
+      } else if (fast == 2) {
         for (int b = 0; b < d.Ws * 3; ++b) row[b] = canvas_byte(img, d, y, b, bg3);
         for (int e = 0; e < S * 3; ++e) tmp[static_cast<int64_t>(y) * S * 3 + e] = resample_h_staged(row.data(), d, tab, S, e);
       } else {

@@ -238,7 +238,7 @@ def test_kernel_core_image_preprocess_vs_reference(harness, G):
     i = 0
     while f"D{i}_in" in G:
         S, pad = G[f"D{i}_cfg"]
-        for fast in (0, 1):
+        for fast in (0, 1, 2):
             got = _harness_preprocess(harness, [G[f"D{i}_in"]], int(S), bool(pad), fast)[0]
             assert np.array_equal(got, G[f"D{i}_out"]), f"case {i} fast={fast}"
         i += 1
@@ -254,7 +254,7 @@ def test_kernel_core_image_preprocess_ragged_batch_vs_oracle(harness):
     rs = np.random.RandomState(11)
     shapes = [(1, 1), (2, 9), (9, 2), (57, 31), (31, 57), (64, 64), (130, 77), (400, 123)]
     imgs = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in shapes]
-    for S, pad, fast in ((32, True, 1), (32, False, 1), (48, True, 0), (30, True, 1), (31, False, 1), (30, False, 0)):
+    for S, pad, fast in ((32, True, 1), (32, False, 1), (48, True, 0), (30, True, 1), (31, False, 1), (30, False, 0), (32, True, 2)):
         got = _harness_preprocess(harness, imgs, S, pad, fast)     # S = 30, 31: 3*S not a multiple of 4 -> no quad path
         for j, im in enumerate(imgs):
             assert np.array_equal(got[j], C.clip_preprocess(im, S, pad)), (shapes[j], S, pad, fast)
