@@ -242,3 +242,51 @@ def test_7b_rollout_properties(eng7b):
         eos = (row == 2).nonzero()
         if eos.numel():
             assert (row[int(eos[0]) + 1:] == 0).all()
+
+
+def test_7b_merged_reference_adapter_and_entropy_head(eng7b):
+    """Full-size properties of the two later additions: (1) the frozen reference adapter on merged weights
+    (merge_frozen) agrees with its unmerged pass at bf16 level — two bf16 roundings of the same function at depth 32 —
+    is deterministic, and the merged copy is reused across calls; (2) the entropy head's backward (opadpo_backward_ent):
+    the gradient is linear in d(entropy) (2x the incoming gradient -> 2x the LoRA gradient, to fp32-atomics noise) and a
+    zero d(entropy) next to d(logprob) reproduces the log-prob-only backward."""
+    from opa_dpo_b200 import POLICY, REF
+    eng = eng7b
+    dev = eng.device
+    images, q, qm, resp = _batch7b(2, 256, seed=11)
+    I, Q, M = images.to(dev), q.to(dev), qm.to(dev)
+    Rr = [r.to(dev) for r in resp[:2]]
+    eng.set_option("share_prefix", 1)
+    eng.set_option("merge_frozen", 0)
+    lp_u, ent_u = eng.forward_logprobs(REF, I, Q, M, Rr)
+    eng.set_option("merge_frozen", 1)
+    lp_m, ent_m = eng.forward_logprobs(REF, I, Q, M, Rr)
+    lp_m2, _ = eng.forward_logprobs(REF, I, Q, M, Rr)
+    assert torch.equal(lp_m, lp_m2)
+    d = (lp_m - lp_u).abs()
+    assert d.max().item() <= 0.3 and d.mean().item() <= 0.02, f"merged vs unmerged reference pass: max {d.max().item():.4g} mean {d.mean().item():.4g}"
+    assert ((lp_m == 0) == (lp_u == 0)).all() and (ent_m - ent_u).abs().mean().item() <= 0.02
+    pol_a, _ = eng.forward_logprobs(POLICY, I, Q, M, Rr)       # the trainable adapter never takes the merged path
+    eng.set_option("merge_frozen", 0)
+    pol_b, _ = eng.forward_logprobs(POLICY, I, Q, M, Rr)
+    assert torch.equal(pol_a, pol_b)
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    valid = torch.stack(Rr).ne(0).float()
+    dent = torch.randn((2, 2, 256), generator=g, device=dev) * 1e-3 * valid
+    dlp = torch.randn((2, 2, 256), generator=g, device=dev) * 1e-3 * valid
+    grads = {}
+    for name, (a, b) in {"ent": (None, dent), "ent2": (None, 2 * dent), "lp": (dlp, None), "lp+0": (dlp, torch.zeros_like(dent))}.items():
+        eng.zero_grad()
+        eng.forward_logprobs(POLICY, I, Q, M, Rr, save_slot=0)
+        eng.backward(0, a, b)
+        torch.cuda.synchronize()
+        grads[name] = eng.buffers()["grad"].clone()
+    eng.zero_grad()
+    for v in grads.values():
+        assert torch.isfinite(v).all()
+    assert grads["ent"].norm().item() > 0
+    rel = ((grads["ent2"] - 2 * grads["ent"]).norm() / grads["ent2"].norm()).item()
+    assert rel <= 2e-2, f"entropy backward must be linear in d(entropy): rel {rel:.3g}"
+    rel0 = ((grads["lp+0"] - grads["lp"]).norm() / grads["lp"].norm()).item()
+    assert rel0 <= 1e-3, f"zero d(entropy) must not change the log-prob backward: rel {rel0:.3g}"
