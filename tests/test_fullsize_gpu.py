@@ -287,6 +287,6 @@ def test_7b_merged_reference_adapter_and_entropy_head(eng7b):
         assert torch.isfinite(v).all()
     assert grads["ent"].norm().item() > 0
     rel = ((grads["ent2"] - 2 * grads["ent"]).norm() / grads["ent2"].norm()).item()
-    assert rel <= 2e-2, f"entropy backward must be linear in d(entropy): rel {rel:.3g}"
+    assert rel <= 1e-3, f"entropy backward must be linear in d(entropy): rel {rel:.3g}"
     rel0 = ((grads["lp+0"] - grads["lp"]).norm() / grads["lp"].norm()).item()
     assert rel0 <= 1e-3, f"zero d(entropy) must not change the log-prob backward: rel {rel0:.3g}"
