@@ -270,7 +270,7 @@ def test_7b_merged_reference_adapter_and_entropy_head(eng7b):
     # Merged vs unmerged are two bf16 realisations of the same function: W' = bf16(W + s B A) against fp32 accumulation
     # of x W^T + bf16(s x A^T) B^T. With the synthetic init the LoRA delta is as large as W itself (B ~ N(0, 0.02^2)), so
     # the per-token difference sits at the level of the bf16-vs-fp32 error of either (mean 0.058, max 0.29 at depth 32,
-    # profiles/r01_full_parity_stats.txt): bound it by twice that. The bar that matters is the loss built on it: the DPO
+    # profiles/r01_full_parity_stats.txt): bound it by that level. The bar that matters is the loss built on it: the DPO
     # loss with the merged reference pass within 1e-3 relative of the one with the unmerged pass (the north-star bar).
     from opa_dpo_b200.dpo import DPOArgs, FusedDPO
     d = (lp_m - lp_u).abs()
@@ -287,7 +287,7 @@ def test_7b_merged_reference_adapter_and_entropy_head(eng7b):
         with open("gpurun_out/merged_ref_stats.txt", "w") as f:
             f.write(msg + "\n")
     assert rel <= 1e-3, msg
-    assert d.max().item() <= 0.6 and d.mean().item() <= 0.12, msg
+    assert d.max().item() <= 0.3 and d.mean().item() <= 0.06, msg   # measured: max 0.214, mean 0.0275
     assert ((lp_m == 0) == (lp_u == 0)).all()
 
     g = torch.Generator(device=dev).manual_seed(3)
