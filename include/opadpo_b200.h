@@ -156,6 +156,13 @@ int opadpo_op_collate_responses(const opadpo_segments* s, int32_t R, int32_t pad
  * placeholder_id (30861) replaced by image_token (-200), and the attention mask u8 [b,Q] (data_utils_dpo.py:118-121). */
 int opadpo_op_collate_queries(const int32_t* tokens, const int64_t* offsets, int32_t b, int32_t Q, int32_t pad_id,
                               int32_t placeholder_id, int32_t image_token, int64_t* ids, uint8_t* attn_mask, void* stream);
+/* Rollout post-processing (truncate_after_eos_with_padding, opadpo/generator_models/generator.py:244-273, called at
+ * online_generator.py:310-323): per row of ids int64 [b,R] the cut is the first EOS, then overridden — in list order, even
+ * when it lies behind the EOS — by the first occurrence of every additional stop token that is present; everything after
+ * the cut becomes pad_id; a row without any stop token is left alone. extra: HOST int64 [n_extra], n_extra <= 8. out may
+ * alias in. Replaces a .tolist() round trip through the host. */
+int opadpo_op_truncate_after_eos(const int64_t* ids, int64_t* out, int32_t b, int32_t R, int64_t eos_id, int64_t pad_id,
+                                 const int64_t* extra, int32_t n_extra, void* stream);
 /* CoPO image masks (mask_single_image, opadpo/dpo_models/dpo_trainer.py:83-109): out [n,C,H,W] f32 = images with, per
  * image, the pixels (block = 1, 'random') or block x block tiles (block = 14, 'blockwise') listed in idx int64 [n,m]
  * (the caller's torch.randperm prefix, so the random stream stays the reference's) set to that image's mean in every

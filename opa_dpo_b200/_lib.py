@@ -126,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_backward_ent", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
     "opadpo_op_collate_responses", "opadpo_op_collate_queries", "opadpo_op_mask_images", "opadpo_op_attention_holes",
-    "opadpo_op_preprocess_images",
+    "opadpo_op_preprocess_images", "opadpo_op_truncate_after_eos",
 ]
 
 
@@ -160,6 +160,7 @@ def _declare_engine(lib):
     lib.opadpo_op_collate_queries.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.opadpo_op_mask_images.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.opadpo_op_attention_holes.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.opadpo_op_truncate_after_eos.argtypes = [vp, vp, i32, i32, i64, i64, vp, i32, vp]
     lib.opadpo_op_preprocess_images.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.opadpo_prof_end.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64)]
     lib.opadpo_launch_count.argtypes = []

@@ -180,6 +180,15 @@ int opadpo_op_mask_images(const float* images, float* out, int32_t n, int32_t C,
   }
   return mask_images(images, out, n, C, H, W, idx, m, block, bf16_pixels, means_out, static_cast<cudaStream_t>(stream));
 }
+int opadpo_op_truncate_after_eos(const int64_t* ids, int64_t* out, int32_t b, int32_t R, int64_t eos_id, int64_t pad_id,
+                                 const int64_t* extra, int32_t n_extra, void* stream) {
+  g_last_error[0] = 0;
+  if (!ids || !out || b < 0 || R <= 0 || n_extra < 0 || (n_extra > 0 && !extra)) {
+    set_error("opadpo_op_truncate_after_eos: null pointer or bad sizes");
+    return OPADPO_EINVAL;
+  }
+  return truncate_after_eos(ids, out, b, R, eos_id, pad_id, extra, n_extra, static_cast<cudaStream_t>(stream));
+}
 int opadpo_op_attention_holes(uint8_t* out, const int64_t* idx, int32_t n, int32_t P, int32_t m, void* stream) {
   g_last_error[0] = 0;
   if (!out || n < 0 || P <= 0 || m < 0 || (m > 0 && !idx)) {

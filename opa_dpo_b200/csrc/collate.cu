@@ -196,6 +196,37 @@ __global__ void holes_kernel(uint8_t* __restrict__ out, const int64_t* __restric
   if (col >= 0 && col < P) out[static_cast<int64_t>(row) * P + col] = 0;
 }
 
+struct StopTokens {
+  int64_t eos;
+  int64_t extra[kMaxStopTokens];
+  int n_extra;
+};
+
+// One CTA per rollout row: first occurrence of every stop token by shared-memory atomicMin, then the tail goes to pad.
+__global__ void __launch_bounds__(128) truncate_after_eos_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int R,
+                                                                 int64_t pad_id, StopTokens st) {
+  __shared__ int first[1 + kMaxStopTokens];
+  __shared__ int end_s;
+  if (threadIdx.x <= st.n_extra) first[threadIdx.x] = R;
+  __syncthreads();
+  const int64_t* row = in + static_cast<int64_t>(blockIdx.x) * R;
+  int64_t* orow = out + static_cast<int64_t>(blockIdx.x) * R;
+  for (int p = threadIdx.x; p < R; p += blockDim.x) {
+    const int64_t t = row[p];
+    if (t == st.eos) atomicMin(&first[0], p);
+    for (int k = 0; k < st.n_extra; ++k)
+      if (t == st.extra[k]) atomicMin(&first[1 + k], p);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) end_s = truncate_end_from_firsts(first, st.n_extra, R);
+  __syncthreads();
+  const int end = end_s;
+  for (int p = threadIdx.x; p < R; p += blockDim.x) {
+    const int64_t t = row[p];
+    orow[p] = (end >= 0 && p > end) ? pad_id : t;
+  }
+}
+
 struct Norm3 {
   float mean[3], std[3];
   uint8_t bg[4];
@@ -348,6 +379,21 @@ int mask_images(const float* images, float* out, int n, int C, int H, int W, con
   cudaFreeAsync(partials, st);
   if (!means_out) cudaFreeAsync(means, st);
   return rc;
+}
+
+int truncate_after_eos(const int64_t* in, int64_t* out, int b, int R, int64_t eos_id, int64_t pad_id, const int64_t* h_extra,
+                       int n_extra, cudaStream_t st) {
+  if (b == 0) return 0;
+  if (n_extra < 0 || n_extra > kMaxStopTokens) {
+    set_error("truncate_after_eos: at most %d additional stop tokens", kMaxStopTokens);
+    return OPADPO_EINVAL;
+  }
+  StopTokens s{};
+  s.eos = eos_id;
+  s.n_extra = n_extra;
+  for (int k = 0; k < n_extra; ++k) s.extra[k] = h_extra[k];
+  truncate_after_eos_kernel<<<b, 128, 0, st>>>(in, out, R, pad_id, s);
+  return launch_ok("truncate_after_eos");
 }
 
 int attention_holes(uint8_t* out, const int64_t* idx, int n, int P, int m, cudaStream_t st) {

@@ -19,6 +19,9 @@ int collate_queries(const int32_t* tokens, const int64_t* offsets, int b, int Q,
 // to the image's mean in every channel. bf16_pixels: pixels and mean rounded to bf16 first. means_out: f32 [n] or null.
 int mask_images(const float* images, float* out, int n, int C, int H, int W, const int64_t* idx, int m, int block, int bf16_pixels,
                 float* means_out, cudaStream_t st);
+// rollout post-processing: out = in with everything behind the deciding stop token set to pad (h_extra: HOST array)
+int truncate_after_eos(const int64_t* in, int64_t* out, int b, int R, int64_t eos_id, int64_t pad_id, const int64_t* h_extra,
+                       int n_extra, cudaStream_t st);
 // CoPO 'attention': out u8 [n,P] = 1 everywhere, 0 at idx [n,m]
 int attention_holes(uint8_t* out, const int64_t* idx, int n, int P, int m, cudaStream_t st);
 // uint8 RGB images (device, concatenated; offsets/heights/widths are HOST arrays) -> f32 [n,3,S,S]

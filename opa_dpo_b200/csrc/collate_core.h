@@ -114,6 +114,18 @@ OPADPO_HD void query_at(const int32_t* tokens, const int64_t* offsets, int row, 
   }
 }
 
+// truncate_after_eos_with_padding (opadpo/generator_models/generator.py:244-273): the position after which a rollout row
+// becomes pad, or -1 to leave the row alone. first[0] = first index of EOS, first[1 + k] = first index of the k-th extra
+// stop token (R when absent). A stop token that is present OVERRIDES whatever came before it in the list, even when it
+// lies behind the EOS — the reference's loop assigns, it does not take the minimum.
+constexpr int kMaxStopTokens = 8;
+OPADPO_HD int truncate_end_from_firsts(const int* first, int n_extra, int R) {
+  int end = first[0] < R ? first[0] : -1;
+  for (int k = 0; k < n_extra; ++k)
+    if (first[1 + k] < R) end = first[1 + k];
+  return end;
+}
+
 // ------------------------------------------------------------------------------------------------ images
 // One image's geometry and where its resampling tables live. The source is the uint8 RGB image [H, W, 3] seen through
 // expand2square (a Ws x Hs canvas of the background colour with the image at (ox, oy)); the output is the SxS window at

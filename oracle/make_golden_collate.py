@@ -245,6 +245,22 @@ def main():
              ("x", ["", "x", ""])]
     G["F_realign"] = np.asarray(json.dumps([[o, p, D.complete_copied_content(o, list(p))] for o, p in cases]))
 
+    # ---- (G) rollout record writer (online_generator.py:380-396), run verbatim
+    import tempfile
+    from opadpo.generator_models import online_generator as OG
+    rd = {"query": ["<image>\nwhat is this?", "<image>\ndescribe"], "image_id": ["a.jpg", "b.jpg"],
+          "standard_response": ["a cat", "a dog \u00e9"], "original_generate_response": ["cat", "dog"],
+          "AI_generate_response": ["cat.", "dog."], "AI_pseudo_response": ["a cat.", "a dog."],
+          "AI_json_report": [{"Sentence 1": {"score": 4}}, {"Added": {"rewritten content": "x"}}],
+          "image_bytes": [b"\x00\x01\xffjpeg", b"\x89PNG"]}
+    with tempfile.TemporaryDirectory() as tmp:
+        OG.Online_Generator.record_step_stats(SimpleNamespace(args=SimpleNamespace(output_dir=tmp)), 7, dict(rd))
+        with open(os.path.join(tmp, "rollouts", f"step7_rank{int(os.environ.get('RANK', 0))}.json")) as f:
+            G["G_rollout_json"] = np.asarray(f.read())
+    rd_store = dict(rd)
+    rd_store["image_bytes"] = [base64.b64encode(x).decode() for x in rd["image_bytes"]]
+    G["G_rollout_input"] = np.asarray(json.dumps(rd_store))
+
     out_path = os.path.join(ROOT, "tests", "golden", "collate_golden.npz")
     np.savez_compressed(out_path, **G)
     print(f"wrote {out_path}: {len(G)} arrays, {os.path.getsize(out_path) / 1024:.0f} KiB")

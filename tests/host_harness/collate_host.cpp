@@ -101,6 +101,23 @@ void host_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const
   }
 }
 
+// the truncate kernel's logic: first occurrences (what the CTA finds with atomicMin), then the shared decision function
+void host_truncate_after_eos(const int64_t* in, int64_t* out, int b, int R, int64_t eos, int64_t pad, const int64_t* extra,
+                             int n_extra) {
+  for (int r = 0; r < b; ++r) {
+    int first[1 + kMaxStopTokens];
+    for (int k = 0; k <= n_extra; ++k) first[k] = R;
+    const int64_t* row = in + static_cast<int64_t>(r) * R;
+    for (int p = R - 1; p >= 0; --p) {   // any visiting order gives the minimum
+      if (row[p] == eos) first[0] = p;
+      for (int k = 0; k < n_extra; ++k)
+        if (row[p] == extra[k]) first[1 + k] = p;
+    }
+    const int end = truncate_end_from_firsts(first, n_extra, R);
+    for (int p = 0; p < R; ++p) out[static_cast<int64_t>(r) * R + p] = (end >= 0 && p > end) ? pad : row[p];
+  }
+}
+
 float host_round_bf16(float x) { return round_bf16(x); }
 
 }  // extern "C"

@@ -320,3 +320,46 @@ def test_collator_product_has_no_cpu_path():
     import inspect
     src = inspect.getsource(K)
     assert "oracle" not in src.replace("the oracle", "")
+
+
+# ------------------------------------------------------------------------------------------------ rollout post-processing
+def _trunc_ref(x, eos, pad, extra):
+    from oracle import llava_oracle as O
+    import torch
+    return O.truncate_after_eos_with_padding(torch.from_numpy(x), eos, pad, extra).numpy()
+
+
+def test_kernel_core_truncate_after_eos_vs_reference(harness):
+    """The truncate kernel's decision logic (csrc/collate_core.h) against the reference's own outputs
+    (tests/golden/opadpo_tiny.npz: generator.truncate_after_eos_with_padding run verbatim) and the oracle on random rows,
+    incl. the override quirk: a later stop token wins even when it lies behind the EOS."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "opadpo_tiny.npz"))
+    comp = np.ascontiguousarray(gold["trunc.in"]).astype(np.int64)
+
+    def run(x, extra):
+        out = np.full_like(x, -9)
+        ex = np.asarray(extra or [0], np.int64)
+        harness.host_truncate_after_eos(_p(x), _p(out), x.shape[0], x.shape[1], 2, 0, _p(ex), len(extra or []))
+        return out
+    assert np.array_equal(run(comp, [1577, 29973]), gold["trunc.out"])
+    assert np.array_equal(run(comp, None), gold["trunc.out_noextra"])
+    rs = np.random.RandomState(2)
+    for trial in range(50):
+        R = int(rs.choice([1, 5, 64, 300]))
+        x = rs.choice([2, 7, 8, 9, 1577, 29973, 11], size=(int(rs.randint(1, 6)), R), p=[.04, .3, .3, .26, .03, .03, .04]).astype(np.int64)
+        for extra in (None, [1577, 29973], [29973, 1577], [11, 11, 8]):
+            assert np.array_equal(run(x, extra), _trunc_ref(x, 2, 0, extra)), (trial, extra)
+    quirk = np.asarray([[5, 2, 6, 1577, 7, 7]], np.int64)            # EOS at 1, '?' at 3: the cut moves BEHIND the EOS
+    assert run(quirk, [1577, 29973]).tolist() == [[5, 2, 6, 1577, 0, 0]]
+
+
+def test_host_mirror_rollout_writer_vs_reference(G, tmp_path):
+    """record_step_stats: byte-identical file to the reference's (online_generator.py:380-396, run verbatim for the golden)."""
+    import base64
+    from opa_dpo_b200.generation import record_step_stats
+    rd = json.loads(str(G["G_rollout_input"]))
+    rd["image_bytes"] = [base64.b64decode(x) for x in rd["image_bytes"]]
+    path = record_step_stats(str(tmp_path), 7, rd)
+    assert os.path.basename(path) == f"step7_rank{int(os.environ.get('RANK', 0))}.json" and os.path.basename(os.path.dirname(path)) == "rollouts"
+    assert open(path).read() == str(G["G_rollout_json"])
+    assert record_step_stats(None, 7, rd) is None

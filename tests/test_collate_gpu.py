@@ -290,3 +290,23 @@ def test_collate_responses_many_segments_fallback_vs_oracle():
             got = K.collate_responses(pack, R, 0, 2, mode)
             for a, w, name in zip(got, want, ("ids", "mask", "scores", "relations", "overflow")):
                 assert np.array_equal(a.cpu().numpy().astype(w.dtype), w), (R, mode, name)
+
+
+def test_truncate_after_eos_kernel_vs_reference():
+    """Rollout post-processing on the device against generator.truncate_after_eos_with_padding's own outputs (golden) and
+    the oracle on random rows at the repo's R = 896."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.generation import truncate_after_eos_with_padding as trunc
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "opadpo_tiny.npz"))
+    comp = torch.from_numpy(gold["trunc.in"]).long()
+    assert np.array_equal(trunc(comp.cuda(), 2, 0, additional_tokens=[1577, 29973]).cpu().numpy(), gold["trunc.out"])
+    assert np.array_equal(trunc(comp.cuda(), 2, 0).cpu().numpy(), gold["trunc.out_noextra"])
+    rs = np.random.RandomState(2)
+    for R in (1, 5, 64, 896):
+        x = torch.from_numpy(rs.choice([2, 7, 8, 9, 1577, 29973, 11], size=(33, R), p=[.01, .33, .33, .3, .01, .01, .01])).long()
+        for extra in (None, [1577, 29973], [29973, 1577], [11, 11, 8]):
+            want = O.truncate_after_eos_with_padding(x, 2, 0, extra)
+            got = trunc(x.cuda(), 2, 0, extra)
+            assert got.dtype == torch.int64 and torch.equal(got.cpu(), want), (R, extra)
+    quirk = torch.tensor([[5, 2, 6, 1577, 7, 7]]).cuda()
+    assert trunc(quirk, 2, 0, [1577, 29973]).tolist() == [[5, 2, 6, 1577, 0, 0]]

@@ -684,3 +684,31 @@ def test_trainer_mirror_outer_step_matches_manual_composition():
     assert cos >= 0.999 and close >= 0.995, (cos, close)
     assert torch.equal(got[n_train:], want[n_train:])          # the CLIP-tower LoRA tail is never trained
     model.engine.close()
+
+
+def test_online_generator_mirror_greedy_responses_vs_oracle():
+    """B200OnlineGenerator.generate_responses (online_generator.py:292-323): generate -> slice off the query -> truncate
+    after EOS / the extra stop ids, all on the device; greedy ids and the truncated rows equal the oracle's."""
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.generation import B200OnlineGenerator
+    from opa_dpo_b200.policy import B200LlavaModel
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc, peaked=40.0)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.set_adapter("lora_policy")
+    images, q, qm, _ = O.synthetic_batch(oc, 3, 16, 8, NAMES2, left_pad=3)
+    ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12)
+    assert margin > 0.05
+    gen = B200OnlineGenerator(SimpleNamespace(response_len=12, top_p=1.0, top_k=0, temperature=1.0),
+                              model, SimpleNamespace(pad_token_id=oc.pad_id, eos_token_id=oc.eos_id))
+    dev = model.engine.device
+    got = gen.generate_responses(images.to(dev), q.to(dev), qm.to(dev), do_sample=False)
+    want = O.truncate_after_eos_with_padding(ids_ref[:, 16:], oc.eos_id, oc.pad_id, [1577, 29973])
+    assert got.shape == (3, 12) and torch.equal(got.cpu(), want)
+    model.engine.close()
