@@ -302,6 +302,10 @@ int Engine::load_tensor(const char* name, const void* src, int dtype, int64_t ro
     }
     if (n.find("encoder.layers.") != std::string::npos) {
       const int l = parse_layer(n, "encoder.layers.");
+      if (l < 0) {
+        set_error("load_tensor(%s): no layer index", name);
+        return OPADPO_EINVAL;
+      }
       if (l >= static_cast<int>(vlayers.size())) return 0;  // layers past the selected one never run
       ClipLayer& L = vlayers[l];
       if (n.find("layer_norm1.") != std::string::npos) { EN_CHECK(expect(1, c.v_d)); return copy_in(is_w ? L.ln1w : L.ln1b, src, dtype, c.v_d, s); }

@@ -1,0 +1,105 @@
+"""Reading the reference's on-disk layouts: sharded HF base checkpoint + index, CLIP tower directory named
+by config.json["image_checkpoint"], adapter directory resolution, config -> EngineConfig. Host I/O only: the tensors are
+streamed into a recorder here; Engine.load_tensor itself is covered by the GPU tests."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _fake_llava(tmp_path):
+    base, clip = tmp_path / "llava-v1.5-tiny", tmp_path / "vision_tower-clip"
+    base.mkdir()
+    clip.mkdir()
+    g = torch.Generator().manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    shard1 = {"model.embed_tokens.weight": rnd(32, 8), "model.layers.0.self_attn.q_proj.weight": rnd(8, 8),
+              "model.layers.0.self_attn.rotary_emb.inv_freq": rnd(2)}
+    shard2 = {"model.norm.weight": rnd(8), "lm_head.weight": rnd(32, 8), "model.mm_projector.0.weight": rnd(8, 4),
+              "model.vision_tower.vision_tower.vision_model.pre_layrnorm.weight": rnd(4)}
+    torch.save(shard1, base / "pytorch_model-00001-of-00002.bin")
+    torch.save(shard2, base / "pytorch_model-00002-of-00002.bin")
+    wm = {k: "pytorch_model-00001-of-00002.bin" for k in shard1}
+    wm.update({k: "pytorch_model-00002-of-00002.bin" for k in shard2})
+    (base / "pytorch_model.bin.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    (base / "config.json").write_text(json.dumps({
+        "hidden_size": 4096, "num_hidden_layers": 32, "num_attention_heads": 32, "intermediate_size": 11008, "vocab_size": 32000,
+        "rms_norm_eps": 1e-5, "max_position_embeddings": 4096, "mm_vision_select_layer": -2, "mm_projector_type": "mlp2x_gelu",
+        "image_checkpoint": {"image_model": str(clip)}}))
+    clip_sd = {"vision_model.pre_layrnorm.weight": rnd(4), "vision_model.embeddings.class_embedding": rnd(4),
+               "vision_model.post_layernorm.weight": rnd(4), "text_model.embeddings.token_embedding.weight": rnd(6, 4)}
+    torch.save(clip_sd, clip / "pytorch_model.bin")
+    (clip / "config.json").write_text(json.dumps({"vision_config": {
+        "hidden_size": 1024, "num_hidden_layers": 24, "num_attention_heads": 16, "intermediate_size": 4096, "image_size": 336,
+        "patch_size": 14, "layer_norm_eps": 1e-5}}))
+    return str(base), str(clip), shard1, shard2, clip_sd
+
+
+def test_sharded_base_and_clip_are_streamed_in_reference_order(tmp_path):
+    from opa_dpo_b200 import checkpoint as K
+    from opa_dpo_b200._lib import OpadpoError
+    base, clip, s1, s2, cs = _fake_llava(tmp_path)
+    assert K.clip_dir_from_config(base) == clip
+    files = K.shard_files(base)
+    assert [f for f, _ in files] == ["pytorch_model-00001-of-00002.bin", "pytorch_model-00002-of-00002.bin"]
+    got = dict(K.iter_checkpoint_tensors(base))
+    assert set(got) == set(s1) | set(s2) and all(torch.equal(got[k], {**s1, **s2}[k]) for k in got)
+    only = dict(K.iter_checkpoint_tensors(base, lambda n: "vision_tower" in n or "mm_projector" in n))
+    assert set(only) == {"model.mm_projector.0.weight", "model.vision_tower.vision_tower.vision_model.pre_layrnorm.weight"}
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def load_tensor(self, name, t):
+            if "inv_freq" in name or "post_layernorm" in name:
+                raise OpadpoError("unknown tensor")
+            self.calls.append((name, t.clone()))
+
+    rec = Recorder()
+    logs = []
+    stats = K.load_llava_base(rec, base, log=logs.append)
+    names = [n for n, _ in rec.calls]
+    vt = "model.vision_tower.vision_tower.vision_model.pre_layrnorm.weight"
+    # the CLIP directory first (text tower ignored), then the LLaVA shards, whose vision_tower entry overrides the tower's
+    assert names[:2] == [vt, "model.vision_tower.vision_tower.vision_model.embeddings.class_embedding"]
+    assert names.count(vt) == 2 and torch.equal([t for n, t in rec.calls if n == vt][-1], s2[vt])
+    assert not any("text_model" in n for n in names)
+    assert stats == {"loaded": len(names), "skipped": 2} and len(logs) == 2
+
+
+def test_engine_config_from_hf_and_adapter_dir(tmp_path):
+    from opa_dpo_b200 import checkpoint as K
+    from opa_dpo_b200.engine import EngineConfig
+    base, clip, *_ = _fake_llava(tmp_path)
+    cfg = K.engine_config_from_hf(base)
+    assert cfg == EngineConfig()                          # LLaVA-1.5-7B + CLIP-L/14-336, select layer -2 -> 23 executed layers
+    c = json.load(open(os.path.join(base, "config.json")))
+    c["mm_vision_select_layer"] = -1
+    json.dump(c, open(os.path.join(base, "config.json"), "w"))
+    assert K.engine_config_from_hf(base).v_layers == 24
+    c.update(hidden_size=5120, num_hidden_layers=40, num_attention_heads=40, intermediate_size=13824, mm_vision_select_layer=-2)
+    json.dump(c, open(os.path.join(base, "config.json"), "w"))
+    assert K.engine_config_from_hf(base) == EngineConfig.llava_13b()
+    c["num_key_value_heads"] = 8
+    json.dump(c, open(os.path.join(base, "config.json"), "w"))
+    with pytest.raises(ValueError):
+        K.engine_config_from_hf(base)
+    # adapter directory resolution (qlora_model.py:57-64): adapter_model/ then lora_default/
+    ck = tmp_path / "checkpoint-10"
+    (ck / "adapter_model" / "lora_default").mkdir(parents=True)
+    assert K.resolve_adapter_dir(str(ck)) == str(ck / "adapter_model" / "lora_default")
+    flat = tmp_path / "flat"
+    flat.mkdir()
+    assert K.resolve_adapter_dir(str(flat)) == str(flat)
+    single = tmp_path / "single"
+    single.mkdir()
+    torch.save({"a": torch.ones(2)}, single / "pytorch_model.bin")
+    assert dict(K.iter_checkpoint_tensors(str(single)))["a"].tolist() == [1.0, 1.0]
+    with pytest.raises(FileNotFoundError):
+        K.shard_files(str(flat))
