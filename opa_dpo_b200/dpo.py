@@ -58,6 +58,15 @@ class DPOArgs:
     gradient_accumulation_steps: int = 4
     noptepochs: int = 1
     bf16: bool = True
+    # outer loop (opadpo_train.py:125-458; run/train_opa_dpo.sh:39-53)
+    total_epochs: int = 4
+    rollout_batch_size: int = 64
+    save_steps: int = 75
+    save_steps_extra_list: tuple = ()
+    eval_steps: Optional[int] = None
+    max_step: int = 500
+    warmup_steps: int = 5
+    output_dir: Optional[str] = None
 
 
 def _ptr(t: Optional[Tensor]):

@@ -21,7 +21,8 @@ per outer step (rl_trainer.py:188-189).
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Tuple
+import os
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -30,6 +31,38 @@ from torch.utils.data import DataLoader
 from . import collate
 from .dist import OverlappedGradAllReduce, allreduce_grad_bucket
 from .dpo import DPOArgs, FusedDPO
+
+FIRST_STEP_IDX = 1      # rl_trainer.py:46
+
+
+def train_loop(trainer, dataset_len: int, next_batch_source: Callable[[], Iterable], resume_training_ckpt: Optional[str] = None):
+    """RLTrainer.train (rl_trainer.py:217-279) as a free function over a trainer exposing `args` (total_epochs,
+    rollout_batch_size, rollout_accumulation_steps, save_steps, save_steps_extra_list, eval_steps, output_dir), `max_step`,
+    `create_optimizer_and_scheduler(n)`, `resume_training(ckpt) -> step`, `step(loader, step_idx)`, `save_model(dir)`,
+    `evaluate(step_idx)`. Same step numbering (first step is 1), same save cadence (at the START of a step whose index is a
+    multiple of save_steps or listed, never at the resumed step itself), same skipping of already-trained steps (their
+    batches are consumed so the data order is unchanged), same `max_step` cut."""
+    a = trainer.args
+    total_steps = dataset_len * a.total_epochs // a.rollout_batch_size
+    trainer.create_optimizer_and_scheduler(min(total_steps, trainer.max_step))
+    skipping_steps = trainer.resume_training(resume_training_ckpt) if resume_training_ckpt is not None else 0
+    loader = next_batch_source()
+    log_history = []
+    for step_idx in range(FIRST_STEP_IDX, total_steps + FIRST_STEP_IDX):
+        if step_idx < skipping_steps:
+            for _ in range(a.rollout_accumulation_steps):
+                next(loader)
+            continue
+        if step_idx >= trainer.max_step:
+            break
+        if step_idx % a.save_steps == 0 or step_idx in a.save_steps_extra_list:
+            if step_idx > skipping_steps:
+                trainer.save_model(os.path.join(a.output_dir, f"checkpoint-{step_idx}"))
+        if a.eval_steps is not None and step_idx % a.eval_steps == 0:
+            trainer.evaluate(step_idx)
+        log_history.append(trainer.step(loader, step_idx))
+    return log_history
+
 
 RESPONSES = ("standard_response", "original_generate_response", "AI_pseudo_response")
 _OPTIONAL = ("original_generate_response_scores", "AI_pseudo_response_scores", "original_generate_response_image_relations",
@@ -46,6 +79,7 @@ class B200DPOTrainer:
         self.device = self.model.engine.device
         self.world_size, self.process_group = world_size, process_group
         self._micro_step = 0
+        self.max_step = getattr(args, "max_step", B200DPOTrainer.max_step)
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
             self.overlap = OverlappedGradAllReduce(self.model.engine, self.model.flat_param.grad, process_group)
@@ -146,6 +180,35 @@ class B200DPOTrainer:
         norm = self.optimizer.step(scale)      # clip_grad_norm_ + AdamW, fused (rl_trainer.py:164-175)
         self.optimizer.zero_grad()
         return norm.reshape(())
+
+    # ------------------------------------------------------------------ outer loop (rl_trainer.py:197-279)
+    max_step: int = 300                       # TrainingArguments.max_step default (opadpo_train.py:152)
+
+    def create_optimizer_and_scheduler(self, num_training_steps: int):
+        """create_optimizer / create_scheduler (utils/trainer_utils.py:9-49): the optimizer is the one handed in; the
+        schedule is HF's cosine with `warmup_steps` warm-up over num_training_steps, unless one was handed in."""
+        if self.lr_scheduler is None:
+            from .optim import cosine_schedule
+            self.lr_scheduler = cosine_schedule(self.optimizer, getattr(self.args, "warmup_steps", 5), num_training_steps)
+        return self.optimizer, self.lr_scheduler
+
+    def save_model(self, output_dir: str):
+        """DPOTrainer.save_model (dpo_trainer.py:837-899): <output_dir>/adapter_model/lora_policy + optimizer.pt + scheduler.pt."""
+        from .optim import save_checkpoint
+        parent, name = os.path.split(output_dir.rstrip("/"))
+        step = name[len("checkpoint-"):] if name.startswith("checkpoint-") else name
+        return save_checkpoint(self.model, self.optimizer, self.lr_scheduler, parent, step,
+                               is_main_process=int(os.environ.get("RANK", 0)) == 0)
+
+    def resume_training(self, checkpoint_dir: str) -> int:
+        from .optim import load_checkpoint
+        return load_checkpoint(self.model, self.optimizer, self.lr_scheduler, checkpoint_dir)
+
+    def evaluate(self, step_idx: int):
+        return None                            # the reference's DPOTrainer does not implement it either
+
+    def train(self, dataset_len: int, train_dataloader_factory: Callable[[], Iterable], resume_training_ckpt: Optional[str] = None):
+        return train_loop(self, dataset_len, train_dataloader_factory, resume_training_ckpt)
 
     def step(self, train_dataloader, step_idx: int = 0) -> Dict[str, Tensor]:
         batches = [next(train_dataloader) for _ in range(self.args.rollout_accumulation_steps)]
