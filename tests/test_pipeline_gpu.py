@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def test_collator_trainer_checkpoint_pipeline(tmp_path):
+def _setup():
     from types import SimpleNamespace
     from oracle import collate_oracle as C
     from oracle import llava_oracle as O
@@ -81,6 +81,14 @@ def test_collator_trainer_checkpoint_pipeline(tmp_path):
         model.make_trainable("lora_policy")
         return model
 
+    return SimpleNamespace(**locals())
+
+
+def test_collator_trainer_checkpoint_pipeline(tmp_path):
+    S = _setup()
+    oc, C, args, tok, make, batches, instances = S.oc, S.C, S.args, S.tok, S.make, S.batches, S.instances
+    AutoregressivePolicy, B200AdamW, B200DPOTrainer, cosine_schedule = S.AutoregressivePolicy, S.B200AdamW, S.B200DPOTrainer, S.cosine_schedule
+    get_last_checkpoint, load_checkpoint, save_checkpoint = S.get_last_checkpoint, S.load_checkpoint, S.save_checkpoint
     model = make()
     model.engine.set_option("merge_frozen", 1)
     policy = AutoregressivePolicy(args, model, tok, "lora_policy")
@@ -112,5 +120,35 @@ def test_collator_trainer_checkpoint_pipeline(tmp_path):
     again = model2.adapter_state_dict("lora_policy")
     for k, v in saved.items():
         assert torch.equal(again[k], v), k
+    model.engine.close()
+    model2.engine.close()
+
+
+def test_trainer_train_outer_loop_on_device(tmp_path):
+    """B200DPOTrainer.train (RLTrainer.train's loop, pinned on the CPU in tests/test_train_loop_cpu.py) driving real steps:
+    8 samples, rollout_batch_size 4 -> 2 outer steps of 2 batches each, a checkpoint at the start of each, and a resumed
+    run that skips what was trained."""
+    import dataclasses
+    import itertools
+    S = _setup()
+    args = dataclasses.replace(S.args, total_epochs=1, rollout_batch_size=4, save_steps=1, max_step=10, warmup_steps=0,
+                               output_dir=str(tmp_path))
+    model = S.make()
+    policy = S.AutoregressivePolicy(args, model, S.tok, "lora_policy")
+    ref_policy = S.AutoregressivePolicy(args, model, S.tok, "lora_ref_policy")
+    trainer = S.B200DPOTrainer(args, policy, ref_policy, S.B200AdamW(model, lr=1e-3))
+    torch.manual_seed(3)
+    hist = trainer.train(8, lambda: itertools.cycle(S.batches))
+    torch.cuda.synchronize()
+    assert len(hist) == 2 and trainer.optimizer.step_count == 4 and trainer.lr_scheduler.last_epoch == 2
+    for step in (1, 2):
+        assert os.path.exists(os.path.join(str(tmp_path), f"checkpoint-{step}", "adapter_model", "lora_policy", "adapter_model.bin"))
+    assert S.get_last_checkpoint(str(tmp_path)) == os.path.join(str(tmp_path), "checkpoint-2")
+    # resume from checkpoint-2 (written before step 2 ran): step 1 is skipped, step 2 runs again, nothing is saved at 2
+    model2 = S.make()
+    trainer2 = S.B200DPOTrainer(args, S.AutoregressivePolicy(args, model2, S.tok, "lora_policy"),
+                                S.AutoregressivePolicy(args, model2, S.tok, "lora_ref_policy"), S.B200AdamW(model2, lr=1e-3))
+    hist2 = trainer2.train(8, lambda: itertools.cycle(S.batches), resume_training_ckpt=os.path.join(str(tmp_path), "checkpoint-2"))
+    assert len(hist2) == 1 and trainer2.optimizer.step_count == 2 + 2     # the optimizer state of checkpoint-2 (2 steps) + one outer step
     model.engine.close()
     model2.engine.close()
