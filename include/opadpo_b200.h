@@ -139,7 +139,9 @@ typedef struct opadpo_segments {
   int32_t b;
 } opadpo_segments;
 enum { OPADPO_SEG_KEEP_BOS = 1,     /* entry of the FIRST report key: its BOS stays (`count == 0`, :170,183) */
-       OPADPO_SEG_STRIP_SPACE = 2   /* copied entry: a leading 29871 piece is dropped (:186-187) */ };
+       OPADPO_SEG_STRIP_SPACE = 2,  /* copied entry: a leading 29871 piece is dropped (:186-187) */
+       OPADPO_SEG_VERBATIM = 4      /* plain tokenisation (:120-137): the tokens as they are — a BOS-only text still puts its
+                                       BOS in the row, whereas a BOS-only report entry is absent (:168,180) */ };
 enum { OPADPO_COLLATE_ADD_EOS = 1,  /* add_eos (:73-87): the first pad position becomes EOS */
        OPADPO_COLLATE_PAD_EOS = 2,  /* pad_eos (:89-99): the EOS position inherits the previous position's weight (1 if 0) */
        OPADPO_COLLATE_TRUNCATE = 4, /* tokenizer truncation (plain branch :120-137); without it a row longer than R sets

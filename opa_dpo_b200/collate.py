@@ -29,7 +29,7 @@ SCORE_WEIGHT = {1: 2.5, 2: 2.0, 3: 1.5, 4: 1.0}                       # score_ma
 RELATION_WEIGHT = {"image_recognition_error": 3.0, "correct": 1.0, "language_comprehension_error": 1.0}   # :38-42
 IMAGE_PLACEHOLDER_ID = 30861                                          # :121
 IMAGE_TOKEN_INDEX = -200
-SEG_KEEP_BOS, SEG_STRIP_SPACE = 1, 2
+SEG_KEEP_BOS, SEG_STRIP_SPACE, SEG_VERBATIM = 1, 2, 4
 ADD_EOS, PAD_EOS, TRUNCATE, TOKEN_MASK = 1, 2, 4, 8
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -112,7 +112,7 @@ def plain_pack(token_rows: Sequence[Sequence[int]]) -> SegmentPack:
     p = SegmentPack()
     for raw in token_rows:
         p.begin_row()
-        p.add(raw, 0.0, 0.0, SEG_KEEP_BOS)
+        p.add(raw, 0.0, 0.0, SEG_KEEP_BOS | SEG_VERBATIM)
         p.end_row()
     return p
 
@@ -260,10 +260,14 @@ class B200DataCollator:
     uint8 [H,W,3] image, which is then preprocessed on the device too. The batch lives on the device."""
 
     def __init__(self, tokenizer, query_len: int = 128, response_len: int = 896, detailed_report: bool = False, device=None,
-                 image_size: int = 336, pad_to_square: bool = True):
+                 image_size: int = 336, pad_to_square: bool = True, ops=None):
+        """`ops`: the array operations (`collate_responses`, `collate_queries`, `preprocess_images`); the default — and the
+        only implementation this package has — are the CUDA kernels of this module. The CPU tests pass the oracle here to
+        check the host half (report parsing, fallback rules, batch keys / dtypes) against the reference collator."""
         self.tokenizer, self.query_len, self.response_len = tokenizer, query_len, response_len
         self.detailed_report, self.device = detailed_report, device
         self.image_size, self.pad_to_square = image_size, pad_to_square
+        self.ops = ops if ops is not None else _DEVICE_OPS
 
     def _tokenize(self, text: str) -> List[int]:
         ids = self.tokenizer(text, return_tensors="pt")["input_ids"]
@@ -271,15 +275,15 @@ class B200DataCollator:
 
     def _plain(self, texts: List[str]):
         t = self.tokenizer
-        ids, mask, *_ = collate_responses(plain_pack([self._tokenize(x) for x in texts]), self.response_len, t.pad_token_id,
-                                          t.eos_token_id, ADD_EOS | TRUNCATE | TOKEN_MASK, self.device, weights=False)
+        ids, mask, *_ = self.ops.collate_responses(plain_pack([self._tokenize(x) for x in texts]), self.response_len, t.pad_token_id,
+                                                   t.eos_token_id, ADD_EOS | TRUNCATE | TOKEN_MASK, self.device, weights=False)
         return ids, mask.long()     # the tokenizer's attention mask after add_eos walked it too: 1..1, eos_id, 0..0 (:76-79)
 
     def __call__(self, instances: List[Dict]) -> Dict[str, Tensor]:
         t, R = self.tokenizer, self.response_len
         reports = [json.loads(i["AI_json_report"]) for i in instances] if self.detailed_report else None
-        q_ids, q_mask = collate_queries([self._tokenize(i["queries"]) for i in instances], self.query_len, t.pad_token_id,
-                                        self.device)
+        q_ids, q_mask = self.ops.collate_queries([self._tokenize(i["queries"]) for i in instances], self.query_len,
+                                                 t.pad_token_id, self.device)
         std_ids, std_mask = self._plain([i["standard_response"] for i in instances])
         batch = {"queries": q_ids, "queries_attention_mask": q_mask.long(), "standard_response": std_ids,
                  "standard_response_attention_mask": std_mask}
@@ -289,8 +293,8 @@ class B200DataCollator:
                 orig, ai = report_segments(self._tokenize, reports, [i["original_generate_response"] for i in instances])
                 if min(orig.row_present + ai.row_present) == 0:
                     raise RuntimeError("a response stream without any entry (torch.cat of an empty list in the reference)")
-                o = collate_responses(orig, R, t.pad_token_id, t.eos_token_id, ADD_EOS, self.device)
-                a = collate_responses(ai, R, t.pad_token_id, t.eos_token_id, ADD_EOS | PAD_EOS, self.device)
+                o = self.ops.collate_responses(orig, R, t.pad_token_id, t.eos_token_id, ADD_EOS, self.device)
+                a = self.ops.collate_responses(ai, R, t.pad_token_id, t.eos_token_id, ADD_EOS | PAD_EOS, self.device)
                 if bool(torch.cat([o[4], a[4]]).any().item()):
                     raise RuntimeError("a report is longer than response_len (pad_and_stack raises in the reference)")
                 detailed = (o, a)
@@ -315,9 +319,20 @@ class B200DataCollator:
             batch["AI_pseudo_response_attention_mask"] = a_mask
         images = [i["images"] for i in instances]
         if all(isinstance(x, (np.ndarray, Tensor)) and x.dtype in (np.uint8, torch.uint8) for x in images):
-            batch["images"] = preprocess_images(images, self.image_size, self.pad_to_square, device=self.device)
+            batch["images"] = self.ops.preprocess_images(images, self.image_size, self.pad_to_square, device=self.device)
         elif all(x is not None and x.shape == images[0].shape for x in images):
             batch["images"] = torch.stack([x if isinstance(x, Tensor) else torch.as_tensor(x) for x in images]).to(q_ids.device)
         else:
             batch["images"] = images
         return batch
+
+
+class _DeviceOps:
+    """The array operations B200DataCollator runs: this module's CUDA-kernel wrappers."""
+    collate_responses = staticmethod(collate_responses)
+    collate_queries = staticmethod(collate_queries)
+    preprocess_images = staticmethod(preprocess_images)
+
+
+_DEVICE_OPS = _DeviceOps()
+

@@ -19,7 +19,7 @@ namespace opadpo {
 namespace collate {
 
 constexpr int32_t kSpaceToken = 29871;  // data_utils_dpo.py:186
-enum : int32_t { SEG_KEEP_BOS = 1, SEG_STRIP_SPACE = 2 };
+enum : int32_t { SEG_KEEP_BOS = 1, SEG_STRIP_SPACE = 2, SEG_VERBATIM = 4 };
 enum : int32_t { MODE_ADD_EOS = 1, MODE_PAD_EOS = 2, MODE_TRUNCATE = 4, MODE_TOKEN_MASK = 8 };
 constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow's 8bpc fixed-point coefficient precision
 
@@ -38,11 +38,16 @@ struct Segments {
 OPADPO_HD void segment_range(const Segments& s, int64_t j, int64_t* begin, int64_t* end) {
   int64_t b = s.seg_offsets[j];
   const int64_t e = s.seg_offsets[j + 1];
+  const int fl = s.seg_flags[j];
+  if (fl & SEG_VERBATIM) {  // plain tokenisation (data_utils_dpo.py:120-137): the tokenizer output as is, even when it is BOS only
+    *begin = b;
+    *end = e;
+    return;
+  }
   if (e - b <= 1) {
     *begin = *end = e;
     return;
   }
-  const int fl = s.seg_flags[j];
   if (!(fl & SEG_KEEP_BOS)) b += 1;
   if ((fl & SEG_STRIP_SPACE) && s.tokens[b] == kSpaceToken) b += 1;
   *begin = b;

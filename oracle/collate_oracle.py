@@ -32,7 +32,7 @@ ERROR_TYPE_MAPPING = {"image_recognition_error": 3.0, "correct": 1.0, "language_
 SPACE_TOKEN = 29871          # the '' piece the LLaMA tokenizer puts in front of a segment (data_utils_dpo.py:186)
 IMAGE_PLACEHOLDER_ID = 30861  # id of the placeholder glyph the dataset puts where <image> was (:121, :341)
 IMAGE_TOKEN_INDEX = -200
-FLAG_KEEP_BOS, FLAG_STRIP_SPACE = 1, 2
+FLAG_KEEP_BOS, FLAG_STRIP_SPACE, FLAG_VERBATIM = 1, 2, 4
 COLLATE_ADD_EOS, COLLATE_PAD_EOS, COLLATE_TRUNCATE, COLLATE_TOKEN_MASK = 1, 2, 4, 8
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -49,6 +49,8 @@ def effective_segment(raw: Sequence[int], flags: int) -> Optional[np.ndarray]:
     raw = tokenizer(text)['input_ids'][0]; absent when it is only BOS; BOS is dropped unless this is the first key of the
     report; a copied segment then loses a leading 29871."""
     raw = np.asarray(raw, dtype=np.int64)
+    if flags & FLAG_VERBATIM:       # plain tokenisation (:120-137): whatever the tokenizer returned, a lone BOS included
+        return raw
     if raw.size <= 1:
         return None
     t = raw if (flags & FLAG_KEEP_BOS) else raw[1:]

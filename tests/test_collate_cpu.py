@@ -363,3 +363,123 @@ def test_host_mirror_rollout_writer_vs_reference(G, tmp_path):
     assert os.path.basename(path) == f"step7_rank{int(os.environ.get('RANK', 0))}.json" and os.path.basename(os.path.dirname(path)) == "rollouts"
     assert open(path).read() == str(G["G_rollout_json"])
     assert record_step_stats(None, 7, rd) is None
+
+
+def test_host_mirror_realign_copied_property_vs_reference_function():
+    """Where /root/reference is present (this container; not the GPU box) the host mirror of complete_copied_content is
+    checked against the reference function itself on generated inputs (hypothesis)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    from utils import data_utils_dpo as D
+    from opa_dpo_b200.collate import realign_copied
+    alphabet = st.sampled_from(list("ab .,\n"))
+    text = st.text(alphabet, max_size=24)
+
+    @settings(max_examples=400, deadline=None)
+    @given(original=text, cuts=st.lists(st.integers(0, 24), max_size=5), noise=st.lists(text, max_size=2), pad=st.booleans())
+    def check(original, cuts, noise, pad):
+        # pieces that are mostly substrings of the original (as GPT-4V's 'copied content' is), sometimes padded / foreign
+        cuts = sorted(min(c, len(original)) for c in cuts)
+        pieces = [original[a:b] for a, b in zip([0] + cuts, cuts + [len(original)])]
+        if pad:
+            pieces = [" " + p + " " for p in pieces]
+        pieces += noise
+        assert realign_copied(original, list(pieces)) == D.complete_copied_content(original, list(pieces))
+    check()
+
+
+# ------------------------------------------------------------------------------------------------ host mirror, whole __call__
+class OracleOps:
+    """The collator's array operations answered by the CPU oracle (torch CPU tensors), so that B200DataCollator.__call__ —
+    report parsing, fallback rules, batch keys and dtypes — can run without a GPU. Test infrastructure: the product's
+    only implementation of these operations are the CUDA kernels."""
+
+    @staticmethod
+    def _rows(pack):
+        a = pack.arrays()
+        return [[(a["tokens"][a["seg_offsets"][j]:a["seg_offsets"][j + 1]].tolist(), float(a["seg_score"][j]), float(a["seg_relation"][j]),
+                  int(a["seg_flags"][j])) for j in range(a["row_offsets"][i], a["row_offsets"][i + 1])] for i in range(len(a["row_offsets"]) - 1)]
+
+    def collate_responses(self, pack, R, pad_id, eos_id, mode, device=None, weights=True):
+        import torch
+        ids, mask, sc, rel, ov = C.collate_responses(self._rows(pack), R, pad_id, eos_id, mode)
+        t = torch.from_numpy
+        return t(ids), t(mask), (t(sc) if weights else None), (t(rel) if weights else None), t(ov.astype(np.int32))
+
+    def collate_queries(self, rows, Q, pad_id, device=None):
+        import torch
+        ids, mask = C.collate_queries(rows, Q, pad_id)
+        return torch.from_numpy(ids), torch.from_numpy(mask.astype(np.uint8))
+
+    def preprocess_images(self, images, size=336, pad_to_square=True, device=None):
+        import torch
+        return torch.from_numpy(np.stack([C.clip_preprocess(np.asarray(i), size, pad_to_square) for i in images]))
+
+
+def _same_batch(got, want, keys=None):
+    import torch
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    for k in (keys or want):
+        g, w = got[k], want[k]
+        assert isinstance(g, torch.Tensor) and g.dtype == w.dtype and torch.equal(g, w), k
+
+
+def test_host_mirror_whole_collator_vs_reference_goldens(G):
+    """B200DataCollator.__call__ (host half) over the oracle ops == the reference collator's batches: detailed report, the
+    overflow fallback, plain branch."""
+    import torch
+    from opa_dpo_b200.collate import B200DataCollator
+    Q, R = map(int, G["A_QR"])
+    for key, detailed, prefix in (("A_instances", True, "A_out_"), ("B_instances", True, "B_out_")):
+        inst = json.loads(str(G[key]))
+        for i in inst:
+            i["images"] = torch.zeros(3, 4, 4)
+        batch = B200DataCollator(C.StubTokenizer(), Q, R, detailed_report=detailed, ops=OracleOps())(inst)
+        names = [k[len(prefix):] for k in G.files if k.startswith(prefix)]
+        assert names
+        for k in names:
+            assert batch[k].dtype == torch.from_numpy(G[prefix + k]).dtype and np.array_equal(batch[k].numpy(), G[prefix + k]), (key, k)
+
+
+def test_host_mirror_whole_collator_property_vs_reference_collator():
+    """Generated reports (hypothesis) through the reference's DataCollatorForCausalLM.__call__ run verbatim and through
+    B200DataCollator.__call__ over the oracle ops: same keys, dtypes and values — including every way a report makes the
+    reference fall back (malformed entries, a stream without entries, a row longer than response_len)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    pytest.importorskip("hypothesis")
+    import contextlib
+    import io
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    from utils import data_utils_dpo as D
+    from opa_dpo_b200.collate import B200DataCollator
+    word = st.sampled_from(["a", "b", "cc", "SPACE", "d."])
+    phrase = st.lists(word, max_size=6).map(" ".join)
+    entry = st.one_of(
+        st.fixed_dictionaries({}, optional={
+            "copied content": phrase, "copied_content": phrase, "rewritten content": phrase, "rewritten_content": phrase,
+            "score": st.sampled_from([1, 2, 3, 4, 5, "4"]), "error type": st.sampled_from(["correct", "image_recognition_error", "other"]),
+            "error_type": st.sampled_from(["language_comprehension_error", "correct"])}),
+        st.just("not a dict"))
+    report = st.dictionaries(st.sampled_from(["Sentence 1", "Sentence 2", "Sentence 3", "Added", "image_description"]), entry, max_size=5)
+    instance = st.fixed_dictionaries({"queries": phrase.map(lambda p: "SYS " + p + " IMG q"), "standard_response": phrase,
+                                      "original_generate_response": phrase, "AI_pseudo_response": phrase, "report": report})
+
+    @settings(max_examples=500, deadline=None)
+    @given(insts=st.lists(instance, min_size=1, max_size=3), R=st.sampled_from([6, 12, 40]), detailed=st.booleans())
+    def check(insts, R, detailed):
+        batch_in = [{**{k: v for k, v in i.items() if k != "report"}, "AI_json_report": json.dumps(i["report"]),
+                     "images": torch.zeros(3, 2, 2)} for i in insts]
+        with contextlib.redirect_stdout(io.StringIO()):          # both print the exception when they fall back
+            want = D.DataCollatorForCausalLM(tokenizer=C.StubTokenizer(), query_len=8, response_len=R, detailed_report=detailed)(
+                [dict(i) for i in batch_in])
+            got = B200DataCollator(C.StubTokenizer(), 8, R, detailed_report=detailed, ops=OracleOps())([dict(i) for i in batch_in])
+        _same_batch(got, want)
+    check()
