@@ -111,7 +111,12 @@ class _PairFn(torch.autograd.Function):
 
 
 class FusedDPO:
-    def __init__(self, args: DPOArgs):
+    def __init__(self, args: DPOArgs, pair_impl=None):
+        """`pair_impl(pi_c, pi_r, ref_c, ref_r, s_c, s_r, params) -> (total, out[8])`: the one-pair operation; the default —
+        and the only implementation this package has — is the fused CUDA kernel (`_PairFn`). The CPU tests pass a torch
+        restatement of the kernel's contract here to check the composition below against the reference's
+        compute_policy_loss run verbatim."""
+        self._pair_impl = pair_impl if pair_impl is not None else _PairFn.apply
         if args.loss_type != "sigmoid":
             raise ValueError(f"Unknown loss type: {args.loss_type}.")   # dpo_trainer.py:468-471
         if args.f_divergence_type not in _DIV:
@@ -128,7 +133,7 @@ class FusedDPO:
                  divergence=_DIV[a.f_divergence_type], alpha_div=a.alpha_divergence_coef, loss_coef=float(loss_coef),
                  anchor_mode=mode, anchor_sign=float(anchor_sign), anchor_value=a.Anchor_value,
                  anchor_coef=a.Anchor_coef if mode else 0.0)
-        return _PairFn.apply(pi_c, pi_r, ref_c, ref_r, s_c, s_r, p)
+        return self._pair_impl(pi_c, pi_r, ref_c, ref_r, s_c, s_r, p)
 
     def compute_policy_loss(self, outputs: Dict[str, Tensor], rollouts: Dict[str, Tensor],
                             outputs_mask: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Dict[str, Tensor]]:
