@@ -10,6 +10,14 @@ The optional entropy regulariser (opa_trainer.py:63-87,113-116) runs a second fo
 the image attention mask) and adds  coef * mean_rows( -sum((H_masked - H) * mask) / sum(mask) ); both forwards stay in
 the autograd graph, so the gradient flows through the entropies of both — the engine's fused lm_head backward takes
 d(loss)/d(entropy) next to d(loss)/d(logprob) (`opadpo_backward_ent`), and the two forwards occupy its two save slots.
+
+Known deviation (pinned by tests/test_opa_host_cpu.py, which runs the reference's compute_loss verbatim): the reference
+reads the entropy at the position OF each labelled token — `entropies[t]` from `logits[t]`, masked by `labels[t] != -100`
+(opa_trainer.py:63,82-84) — i.e. the distribution that predicts token t+1, one position later than its cross-entropy. The
+engine's entropies are the ones rl_models.py:128 defines for the DPO path: of the distributions that predict the
+labelled tokens themselves. `entropy_loss` below is the reference's formula exactly (equal value and gradient when fed
+entropies at the reference's positions); making the engine emit the shifted rows (R + 1 head rows per response, gradient
+at pad-labelled rows) is the remaining step to bit-level parity of the regulariser.
 """
 from __future__ import annotations
 
