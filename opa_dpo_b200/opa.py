@@ -16,8 +16,9 @@ reads the entropy at the position OF each labelled token — `entropies[t]` from
 (opa_trainer.py:63,82-84) — i.e. the distribution that predicts token t+1, one position later than its cross-entropy. The
 engine's entropies are the ones rl_models.py:128 defines for the DPO path: of the distributions that predict the
 labelled tokens themselves. `entropy_loss` below is the reference's formula exactly (equal value and gradient when fed
-entropies at the reference's positions); making the engine emit the shifted rows (R + 1 head rows per response, gradient
-at pad-labelled rows) is the remaining step to bit-level parity of the regulariser.
+entropies at the reference's positions). `OPAArgs.entropy_alignment = "reference"` reproduces the reference's positions
+with the engine as it is (one extra response slot with a placeholder label, see `OPAStepper._forward`); the default stays
+"label" until that mode has run on the GPU.
 """
 from __future__ import annotations
 
@@ -26,6 +27,9 @@ from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
+
+
+_PLACEHOLDER = 1     # any non-pad id: the slot only has to carry a label so that its entropy (and its gradient) is emitted
 
 
 def sft_loss(outputs: Dict[str, Tensor], responses: Dict[str, Tensor], pad_token_id: int = 0) -> Tensor:
@@ -65,6 +69,10 @@ class OPAArgs:
     entropy_mask_method: str = "random"   # random | blockwise (masked images) | attention (holes in the image mask)
     entropy_mask_ratio: float = 0.3
     temperature: float = 1.0
+    # "label": entropies of the distributions that predict the labelled tokens (the engine's native output).
+    # "reference": the reference's positions, one later (see the module docstring) — the forward runs over responses
+    # extended by one slot, with a placeholder token behind each row's last token so that slot's entropy is emitted.
+    entropy_alignment: str = "label"
 
 
 class OPAStepper:
@@ -76,24 +84,52 @@ class OPAStepper:
         self.policy, self.opt, self.temperature, self.pad = policy, optimizer, temperature, pad_token_id
         self.args = args or OPAArgs(temperature=temperature)
 
+    def _forward(self, images, queries, queries_attn_masks, responses: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """Policy outputs [b, R] for `responses`. With entropy_alignment == "reference" the entropies are the ones the
+        reference's regulariser reads: entropies[t] = H(distribution at the position of token t). The policy computes
+        H(distribution predicting slot j) for every slot j whose label is not pad, so the forward runs on responses
+        extended to R + 1 slots with a placeholder token right behind each row's last token (causal attention: nothing
+        before it changes); slot t + 1 of that output is the wanted entropy, and the placeholder's own log-prob is cut off."""
+        a = self.args
+        if not (a.entropy_loss and a.entropy_alignment == "reference"):
+            return self.policy(images, queries, queries_attn_masks, temperature=self.temperature, **responses)
+        ext = {}
+        for name, ids in responses.items():
+            n = (ids != self.pad).sum(1, keepdim=True)                        # valid length of every row (right-padded)
+            e = torch.cat([ids, torch.full_like(ids[:, :1], self.pad)], 1)
+            ext[name] = e.scatter(1, n, torch.full_like(n, _PLACEHOLDER))
+        pargs = self.policy.args
+        R = pargs.response_len
+        pargs.response_len = R + 1            # AutoregressivePolicy.forward insists on responses of args.response_len
+        try:
+            out = self.policy(images, queries, queries_attn_masks, temperature=self.temperature, **ext)
+        finally:
+            pargs.response_len = R
+        res = {}
+        for name, ids in responses.items():
+            valid = (ids != self.pad).to(out[name + "_entropies"].dtype)
+            res[name + "_logprobs"] = out[name + "_logprobs"][:, :-1] * valid
+            res[name + "_entropies"] = out[name + "_entropies"][:, 1:] * valid
+        return res
+
     def compute_loss(self, images: Tensor, queries: Tensor, queries_attn_masks: Tensor, responses: Dict[str, Tensor],
                      masked_images: Optional[Tensor] = None, masked_attn_masks: Optional[Tensor] = None
                      ) -> Tuple[Tensor, Dict[str, float]]:
         """opa_trainer.py:58-125. `masked_images` (random / blockwise) or `masked_attn_masks` (the [b, P + Q] mask with the
         image part prepended, 'attention') is the second forward's input when args.entropy_loss is on."""
         a = self.args
-        out = self.policy(images, queries, queries_attn_masks, temperature=self.temperature, **responses)
+        out = self._forward(images, queries, queries_attn_masks, responses)
         loss = sft_loss(out, responses, self.pad)
         logs = {"base_sft_loss": loss.detach(), "mask_sft_loss": 0.0, "entropy_loss": 0.0}
         if a.entropy_loss:
             if a.entropy_mask_method == "attention":
                 if masked_attn_masks is None:
                     raise ValueError("entropy_mask_method='attention' needs masked_attn_masks")
-                out_m = self.policy(images, queries, masked_attn_masks, temperature=self.temperature, **responses)
+                out_m = self._forward(images, queries, masked_attn_masks, responses)
             else:
                 if masked_images is None:
                     raise ValueError("entropy_loss needs masked_images")
-                out_m = self.policy(masked_images, queries, queries_attn_masks, temperature=self.temperature, **responses)
+                out_m = self._forward(masked_images, queries, queries_attn_masks, responses)
             ent = entropy_loss(out, out_m, responses, self.pad)
             logs["mask_sft_loss"] = sft_loss(out_m, responses, self.pad).detach()
             logs["entropy_loss"] = ent.detach()

@@ -712,3 +712,58 @@ def test_online_generator_mirror_greedy_responses_vs_oracle():
     want = O.truncate_after_eos_with_padding(ids_ref[:, 16:], oc.eos_id, oc.pad_id, [1577, 29973])
     assert got.shape == (3, 12) and torch.equal(got.cpu(), want)
     model.engine.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1); "
+                           "the mode's logic is pinned on the CPU against the reference in tests/test_opa_host_cpu.py")
+def test_opa_entropy_regulariser_reference_alignment_vs_oracle():
+    """OPAArgs.entropy_alignment="reference": the regulariser reads the entropy at the position of each labelled token
+    (opa_trainer.py:63,82-84), one later than the cross-entropy. Loss vs the oracle's logits at those positions."""
+    from types import SimpleNamespace
+    import torch.nn.functional as F
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.opa import OPAArgs, OPAStepper
+    from opa_dpo_b200.dpo import DPOArgs
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc, peaked=8.0)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.make_trainable("lora_policy")
+    R, coef = 24, 0.5
+    policy = AutoregressivePolicy(DPOArgs(response_len=R), model, SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, R, ["standard_response"], left_pad=2)
+    masked = images.clone()
+    masked[:, :, ::3, ::2] = images.mean()
+    r = resp["standard_response"]
+    ids = torch.cat([q, r], 1)
+    mask = torch.cat([qm.bool(), r != 0], 1)
+    labels = r.clone()
+    labels[labels == 0] = -100
+    valid = (labels != -100).float()
+
+    def ref_pass(img):
+        logits = O.llava_logits(oc, w, lp, ids, mask, img)
+        ls = torch.log_softmax(logits[:, -R:], -1)                      # positions OF the response tokens
+        ce = F.cross_entropy(logits[:, -R - 1:-1].reshape(-1, oc.vocab), labels.reshape(-1), ignore_index=-100)
+        return ce, -(ls.exp() * ls).sum(-1)
+    with torch.no_grad():
+        sft_ref, h = ref_pass(images)
+        _, hm = ref_pass(masked)
+    want = sft_ref + coef * (-((hm - h) * valid).sum(-1) / valid.sum(-1)).mean()
+    stepper = OPAStepper(policy, None, args=OPAArgs(entropy_loss=True, entropy_loss_coef=coef, entropy_decay_coef=1.0,
+                                                    entropy_alignment="reference"))
+    policy.train()
+    model.engine.zero_grad()
+    loss, logs = stepper.compute_loss(images, q, qm, resp, masked_images=masked)
+    assert policy.args.response_len == R
+    assert abs(loss.item() - want.item()) <= 1e-2 * abs(want.item()), (loss.item(), want.item())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert model._slot_busy == [False, False] and torch.isfinite(model.engine.buffers()["grad"]).all()
+    model.engine.close()

@@ -102,3 +102,30 @@ def test_opa_compute_loss_vs_reference_llava_trainer(entropy):
         assert abs(loss.item() - aligned.item()) <= 1e-6 * abs(aligned.item())
     else:
         assert len(calls) == 1 and abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+
+    # entropy_alignment="reference": an engine-like policy (per-slot log-prob / entropy of the distribution PREDICTING the
+    # slot, zero where the slot's label is pad, any response_len) driven through one extra slot reproduces the reference
+    # exactly — value and gradient
+    class EnginePolicy:
+        args = SimpleNamespace(response_len=R)
+
+        def __call__(self, images, queries, queries_attn_masks, temperature=None, **kw):
+            (name, r), = kw.items()
+            assert r.shape[1] == self.args.response_len
+            Rx = r.shape[1]
+            lg = logits_of(images)
+            if Rx > R:        # the row grew by one slot: its last position's logits exist in the real model; here theta ends at L
+                lg = torch.cat([lg, lg[:, -1:] * 0], 1)
+            ls = torch.log_softmax(lg, -1)
+            valid = (r != 0).float()
+            lp = ls[:, Q - 1:Q - 1 + Rx].gather(2, r[:, :, None])[:, :, 0] * valid
+            ent = -(ls.exp() * ls).sum(-1)[:, Q - 1:Q - 1 + Rx] * valid
+            return {name + "_logprobs": lp, name + "_entropies": ent}
+    pol = EnginePolicy()
+    st2 = OPAStepper(pol, None, args=OPAArgs(entropy_loss=entropy, entropy_loss_coef=0.2, entropy_decay_coef=0.9,
+                                             entropy_alignment="reference"))
+    loss2, _ = st2.compute_loss(images, queries, queries != 0, responses, masked_images=masked)
+    assert pol.args.response_len == R
+    assert abs(loss2.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item()), (loss2.item(), loss_ref.item())
+    (g2,) = torch.autograd.grad(loss2, theta)
+    assert torch.allclose(g2, g_ref, atol=1e-7, rtol=1e-5)
