@@ -71,12 +71,16 @@ _OPTIONAL = ("original_generate_response_scores", "AI_pseudo_response_scores", "
 
 class B200DPOTrainer:
     def __init__(self, args: DPOArgs, policy, ref_policy, optimizer, lr_scheduler=None, world_size: int = 1,
-                 process_group=None):
+                 process_group=None, mask_ops=None, loss=None, device=None):
+        """mask_ops (`mask_images`, `mask_percentage_per_row`), loss (a FusedDPO) and device default to the CUDA
+        implementations — the only ones this package has; the CPU tests pass restatements to compare `rollout()` with the
+        reference's DPOTrainer.rollout run verbatim."""
         self.args, self.policy, self.ref_policy = args, policy, ref_policy
         self.optimizer, self.lr_scheduler = optimizer, lr_scheduler
-        self.loss = FusedDPO(args)
+        self.loss = loss if loss is not None else FusedDPO(args)
+        self.mask_ops = mask_ops if mask_ops is not None else collate
         self.model = policy.base_model
-        self.device = self.model.engine.device
+        self.device = device if device is not None else self.model.engine.device
         self.world_size, self.process_group = world_size, process_group
         self._micro_step = 0
         self.max_step = getattr(args, "max_step", B200DPOTrainer.max_step)
@@ -106,11 +110,11 @@ class B200DPOTrainer:
             if a.CoPO:
                 sub = {"standard_response": rb["standard_response"], "AI_pseudo_response": rb["AI_pseudo_response"]}
                 if a.CoPO_method in ("random", "blockwise"):
-                    rb["masked_images"] = collate.mask_images(images, a.CoPO_mask_ratio, a.CoPO_method)
+                    rb["masked_images"] = self.mask_ops.mask_images(images, a.CoPO_mask_ratio, a.CoPO_method)
                     new_fwd = dict(images=rb["masked_images"], queries=rb["queries"], queries_attn_masks=rb["queries_attn_masks"], **sub)
                 elif a.CoPO_method == "attention":
                     assert images.size(-1) % 14 == 0
-                    holes = collate.mask_percentage_per_row(images.size(0), (images.size(-1) // 14) ** 2, a.CoPO_mask_ratio, dev)
+                    holes = self.mask_ops.mask_percentage_per_row(images.size(0), (images.size(-1) // 14) ** 2, a.CoPO_mask_ratio, dev)
                     rb["masked_query_attn_masks"] = torch.cat([holes.to(rb["queries_attn_masks"].dtype), rb["queries_attn_masks"]], 1)
                     new_fwd = dict(images=images, queries=rb["queries"], queries_attn_masks=rb["masked_query_attn_masks"], **sub)
                 else:

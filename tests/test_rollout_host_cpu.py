@@ -1,0 +1,129 @@
+"""Row a5: B200DPOTrainer.rollout — which forwards run, on which inputs, under which names, the CoPO
+masks and their random stream, the bf16 image cast, the score rows — against the reference's DPOTrainer.rollout
+(opadpo/dpo_models/dpo_trainer.py:214-427) run VERBATIM over stub policies. The mask operations, which the product only has
+as CUDA kernels, are answered by the CPU oracle (same host-side draws: one torch.randperm per image / row, in order).
+What differs by design and is asserted as such: the rollouts stay on the device (no .cpu() parking) and the reference's
+discarded policy forward (:336-338) is not run. Needs /root/reference."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+NAMES = ("standard_response", "original_generate_response", "AI_pseudo_response")
+
+
+class OracleMaskOps:
+    @staticmethod
+    def mask_images(images, ratio, method, block=14):
+        from oracle import collate_oracle as C
+        n, Cc, H, W = images.shape
+        total = H * W if method == "random" else (H // block) * (W // block)
+        m = int(total * ratio)
+        out = []
+        for i in range(n):                                   # one permutation per image, in image order (dpo_trainer.py:295)
+            idx = torch.randperm(total)[:m].numpy()
+            x = C.mask_single_image(images[i].float().numpy(), idx, method, block, bf16_pixels=images.dtype == torch.bfloat16)
+            out.append(torch.from_numpy(x).to(images.dtype))
+        return torch.stack(out)
+
+    @staticmethod
+    def mask_percentage_per_row(n_rows, n_cols, ratio, device=None):
+        from oracle import collate_oracle as C
+        m = int(n_cols * ratio)
+        idx = np.stack([torch.randperm(n_cols)[:m].numpy() for _ in range(n_rows)]) if n_rows else np.zeros((0, m), np.int64)
+        return torch.from_numpy(C.attention_holes(n_cols, idx))
+
+
+class StubPolicy:
+    """AutoregressivePolicy.forward's contract with a deterministic function of its inputs standing in for the model, so
+    that a forward on other images / masks / responses gives other numbers."""
+
+    def __init__(self, salt):
+        self.salt, self.calls = salt, []
+        self.base_model = SimpleNamespace(engine=SimpleNamespace(device=torch.device("cpu")), flat_param=None)
+
+    def eval(self):
+        return self
+
+    def train(self):
+        return self
+
+    def __call__(self, images, queries, queries_attn_masks, temperature=None, **kw):
+        resp = {k: v for k, v in kw.items() if "response" in k and "_mask" not in k and "scores" not in k and "image_relations" not in k}
+        self.calls.append(sorted(resp))
+        base = images.float().mean(dim=(1, 2, 3)) + queries_attn_masks.float().mean(1) * 0.1 + self.salt
+        out = {}
+        for k, r in resp.items():
+            valid = (r != 0).float()
+            out[k + "_logprobs"] = -(r.float() * 1e-3 + base[:, None]) * valid
+            out[k + "_entropies"] = (r.float() * 2e-3 + base[:, None]) * valid
+        return out
+
+
+@pytest.mark.parametrize("copo,method", [(False, "random"), (True, "random"), (True, "blockwise"), (True, "attention")])
+@pytest.mark.parametrize("detailed", [False, True])
+@pytest.mark.parametrize("bf16", [True, False])
+def test_rollout_vs_reference_dpo_trainer(copo, method, detailed, bf16):
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    import opadpo.dpo_models.dpo_trainer as dpo_trainer
+    from opa_dpo_b200.dpo import DPOArgs
+    from opa_dpo_b200.trainer import B200DPOTrainer
+    g = torch.Generator().manual_seed(1)
+    b, Q, R = 2, 6, 5
+    batches = []
+    for _ in range(3):
+        bt = {"images": torch.randn(b, 3, 28, 28, generator=g), "queries": torch.randint(3, 99, (b, Q), generator=g),
+              "queries_attention_mask": torch.ones(b, Q, dtype=torch.long)}
+        for n in NAMES:
+            r = torch.randint(3, 99, (b, R), generator=g)
+            r[0, 3:] = 0
+            bt[n] = r
+            bt[n + "_attention_mask"] = (r != 0).long()
+        for n in ("original_generate_response", "AI_pseudo_response"):
+            bt[n + "_scores"] = torch.rand(b, R, generator=g)
+            bt[n + "_image_relations"] = torch.rand(b, R, generator=g)
+        batches.append(bt)
+
+    class Tok:
+        pad_token_id, eos_token_id = 0, 2
+        def encode(self, text, add_special_tokens=True):
+            return [1577] if text == "?" else [1, 29973]
+
+    ref_args = SimpleNamespace(bf16=bf16, fp16=False, CoPO=copo, CoPO_method=method, CoPO_mask_ratio=0.3, detailed_report=detailed,
+                               response_score=True, response_image_relation=False, reward_model_per_device_batch_size=None,
+                               temperature=0.8)
+    tr = object.__new__(dpo_trainer.DPOTrainer)
+    tr.args, tr.tokenizer = ref_args, Tok()
+    tr.accelerator = SimpleNamespace(device=torch.device("cpu"), is_main_process=False)
+    tr.policy, tr.ref_policy = StubPolicy(0.5), StubPolicy(0.25)
+    torch.manual_seed(11)
+    want = tr.rollout([dict(bt) for bt in batches])
+
+    args = DPOArgs(CoPO=copo, CoPO_method=method, CoPO_mask_ratio=0.3, detailed_report=detailed, response_score=True,
+                   response_image_relation=False, temperature=0.8, bf16=bf16, response_len=R)
+    pol, ref = StubPolicy(0.5), StubPolicy(0.25)
+    mine = B200DPOTrainer(args, pol, ref, optimizer=None, mask_ops=OracleMaskOps(), loss=object(), device=torch.device("cpu"))
+    torch.manual_seed(11)
+    got = mine.rollout([dict(bt) for bt in batches])
+
+    assert set(got) == set(want), (sorted(set(got) ^ set(want)))
+    for k in want:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        if not bf16 and (k == "masked_images" or k.startswith("ref_mask_")):
+            # float32 images: the CoPO fill value is a float mean whose summation order is not part of torch's contract
+            # (tolerance 2^-20 * mean|x|, as in the collator tests); everything that does not depend on it is exact
+            assert torch.allclose(got[k], want[k], atol=2e-6, rtol=0), k
+            assert torch.equal(got[k] == 0, want[k] == 0), k
+        else:
+            assert torch.equal(got[k], want[k]), k
+    # by design: the reference also runs (and throws away) a policy forward per batch; the mirror does not
+    assert len(tr.policy.calls) == 3 and len(pol.calls) == 0
+    assert ref.calls == tr.ref_policy.calls
