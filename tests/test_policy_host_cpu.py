@@ -1,0 +1,80 @@
+"""Row a1, host half (SURVEY.md §8b "Python surface kept verbatim"): opa_dpo_b200.policy.AutoregressivePolicy.forward — the
+discovery of response kwargs by name, the split of a CoPO 'attention' mask, the stacking order, the output names — against
+the outputs of the REFERENCE's rl_models.AutoregressivePolicy.forward (tests/golden/opadpo_tiny.npz, produced by
+oracle/make_golden.py). The engine call underneath (`base_model.policy_logprobs`), which the product only has on the GPU,
+is answered here by the CPU oracle; the engine itself is compared with the oracle in the GPU tests."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import llava_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "opadpo_tiny.npz")
+NAMES3 = ["standard_response", "original_generate_response", "AI_pseudo_response"]
+
+
+class OracleBackedModel:
+    """Stands where B200LlavaModel stands (`set_adapter`, `config.use_cache`, `policy_logprobs`)."""
+
+    def __init__(self, cfg, w, adapters):
+        self.cfg, self.w, self.adapters = cfg, w, adapters
+        self.config = SimpleNamespace(use_cache=True)
+        self.active, self.calls = None, []
+
+    def set_adapter(self, name):
+        self.active = name
+
+    def policy_logprobs(self, images, queries, qmask, responses, temperature, img_mask=None):
+        self.calls.append((self.active, len(responses), None if img_mask is None else tuple(img_mask.shape)))
+        names = [f"response_{i}" for i in range(len(responses))]
+        qam = qmask if img_mask is None else torch.cat([img_mask, qmask], 1)
+        with torch.no_grad():
+            out = O.policy_forward(self.cfg, self.w, self.adapters[self.active], images, queries, qam, dict(zip(names, responses)),
+                                   temperature=temperature)
+        return (torch.stack([out[n + "_logprobs"] for n in names]), torch.stack([out[n + "_entropies"] for n in names]))
+
+
+def test_policy_forward_host_logic_vs_reference_outputs():
+    from opa_dpo_b200.policy import AutoregressivePolicy, make_policy_with_base_model
+    gold = {k: torch.from_numpy(v) for k, v in np.load(GOLD).items()}
+    cfg = O.OracleConfig()
+    w = O.init_weights(cfg)
+    model = OracleBackedModel(cfg, w, {"lora_policy": O.init_lora(cfg, 11), "lora_ref_policy": O.init_lora(cfg, 12)})
+    images, q, qm = gold["in.images"], gold["in.queries"], gold["in.qmask"]
+    resp = {n: gold["in." + n] for n in NAMES3}
+    R = resp[NAMES3[0]].shape[1]
+    args = SimpleNamespace(temperature=0.7, response_len=R)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    policy = make_policy_with_base_model(args, model, tok, adapter_name="lora_policy")
+    ref_policy = AutoregressivePolicy(args, model, tok, adapter_name="lora_ref_policy")
+    masked_qm = torch.cat([gold["in.img_mask"], qm], 1)
+    mresp = {"mask_standard_response": resp["standard_response"], "mask_AI_pseudo_response": resp["AI_pseudo_response"]}
+    # what the reference's callers pass along and forward() must ignore: mode=, *_attention_mask, *_scores, *_image_relations
+    noise = {"mode": "policy", "standard_response_attention_mask": resp["standard_response"] != 0,
+             "AI_pseudo_response_scores": gold["in.AI_pseudo_response_scores"],
+             "AI_pseudo_response_image_relations": gold["in.AI_pseudo_response_image_relations"]}
+    runs = {"pol": policy(images, q, qm, **resp, **noise),                       # temperature defaults to args.temperature
+            "ref": ref_policy(images=images, queries=q, queries_attn_masks=qm, temperature=0.7, **resp),
+            "polm": policy(images, q, masked_qm, temperature=0.7, **mresp),
+            "refm": ref_policy(images, q, masked_qm, **mresp)}
+    n = 0
+    for tag, out in runs.items():
+        want = {k[len(tag) + 1:]: v for k, v in gold.items() if k.startswith(tag + ".")}
+        assert set(out) == set(want), (tag, sorted(out), sorted(want))
+        for k, v in out.items():
+            assert v.shape == want[k].shape and (v - want[k]).abs().max().item() <= 2e-4, (tag, k)
+            n += 1
+    assert n == 20
+    assert model.calls == [("lora_policy", 3, None), ("lora_ref_policy", 3, None), ("lora_policy", 2, (2, cfg.n_patches)),
+                           ("lora_ref_policy", 2, (2, cfg.n_patches))]
+    assert model.config.use_cache is False                                        # rl_models.py:86
+    with pytest.raises(ValueError):
+        policy(images, q, qm, standard_response=resp["standard_response"][:, :-1])    # not padded to args.response_len
+    with pytest.raises(ValueError):
+        policy(images, q, qm, mode="policy")                                        # no response tensors at all
