@@ -242,6 +242,8 @@ class AutoregressivePolicy(Policy):
         if self.adapter_name is not None:
             self.base_model.set_adapter(self.adapter_name)
         self.base_model.config.use_cache = True
+        self.base_model.config.cache_shape = (queries.shape[-1] + self.args.response_len
+                                              + self.base_model.get_vision_tower().num_patches,)   # rl_models.py:158-162
         if temperature is None:
             temperature = self.args.temperature
         seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=True,

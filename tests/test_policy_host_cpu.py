@@ -78,3 +78,36 @@ def test_policy_forward_host_logic_vs_reference_outputs():
         policy(images, q, qm, standard_response=resp["standard_response"][:, :-1])    # not padded to args.response_len
     with pytest.raises(ValueError):
         policy(images, q, qm, mode="policy")                                        # no response tensors at all
+
+
+def test_respond_arguments_match_reference_call():
+    """Policy._respond (rl_models.py:146-191): the generate() call it makes — sampling at `temperature` with top_k = 0,
+    top_p = 1, max_new_tokens = response_len — and the slice it returns."""
+    from opa_dpo_b200.policy import AutoregressivePolicy
+    seen = {}
+
+    class Model:
+        config = SimpleNamespace(use_cache=False, cache_shape=None)
+
+        def set_adapter(self, name):
+            seen["adapter"] = name
+
+        def get_vision_tower(self):
+            return SimpleNamespace(num_patches=576)
+
+        def generate(self, **kw):
+            seen.update(kw)
+            return torch.cat([kw["inputs"], torch.full((kw["inputs"].size(0), kw["max_new_tokens"]), 7)], 1)
+
+    m = Model()
+    pol = AutoregressivePolicy(SimpleNamespace(temperature=0.9, response_len=5), m, SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    pol.eval()
+    q = torch.ones(2, 4, dtype=torch.long)
+    out = pol.respond(q, q != 0, images=torch.zeros(2, 3, 2, 2))
+    assert out["responses"].shape == (2, 5) and (out["responses"] == 7).all()
+    assert seen["adapter"] == "lora_policy" and seen["do_sample"] is True and seen["top_k"] == 0 and seen["top_p"] == 1.0
+    assert seen["temperature"] == 0.9 and seen["max_new_tokens"] == 5 and seen["pad_token_id"] == 0
+    assert m.config.use_cache is True and m.config.cache_shape == (4 + 5 + 576,)
+    pol.train()
+    with pytest.raises(AssertionError):
+        pol.respond(q, q != 0)
