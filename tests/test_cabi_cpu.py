@@ -125,3 +125,27 @@ def test_cosine_schedule_matches_hf_and_last_checkpoint(tmp_path):
     assert get_last_checkpoint(str(tmp_path)).endswith("checkpoint-100")
     (tmp_path / "completed").write_text("")
     assert get_last_checkpoint(str(tmp_path)) is None
+
+
+def test_importing_the_whole_package_does_not_load_the_oracle():
+    """oracle/ is test infrastructure: no module of the package imports it (statically), and importing the whole package
+    does not pull it in."""
+    import ast
+    import glob
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "opa_dpo_b200", "*.py")):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+    code = ("import sys, importlib, pkgutil, opa_dpo_b200\n"
+            "for m in pkgutil.iter_modules(opa_dpo_b200.__path__):\n"
+            "    importlib.import_module('opa_dpo_b200.' + m.name)\n"
+            "assert not any(k == 'oracle' or k.startswith('oracle.') for k in sys.modules), 'oracle imported'\n")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
