@@ -767,3 +767,24 @@ def test_opa_entropy_regulariser_reference_alignment_vs_oracle():
     torch.cuda.synchronize()
     assert model._slot_busy == [False, False] and torch.isfinite(model.engine.buffers()["grad"]).all()
     model.engine.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1); "
+                           "the oracle side is pinned to transformers' generate() in tests/test_oracle_golden.py")
+@pytest.mark.parametrize("eos", [298, 215, 159])
+def test_greedy_rollout_early_eos_ids_exact(eos):
+    """Rows that finish early at different steps: the EOS id is moved onto tokens the greedy path really emits; finished rows
+    emit pad, the others go on — ids equal to the oracle's (which equal transformers' generate())."""
+    import dataclasses
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import EngineConfig, POLICY
+    oc = dataclasses.replace(O.OracleConfig(), eos_id=eos)
+    ec = EngineConfig(**oc.to_dict())
+    eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 2, 16, 24, NAMES3, left_pad=2)
+    ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12)
+    got = eng.generate(POLICY, images, q, qm, 12).cpu()
+    assert margin > 0.05 and torch.equal(got, ids_ref), (got[:, 16:], ids_ref[:, 16:])
+    assert (ids_ref[:, 16:] == oc.pad_id).any()
+    eng.close()

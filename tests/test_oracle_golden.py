@@ -109,3 +109,27 @@ def test_truncate_and_compute_logprobs_match_reference(gold):
     got = O.compute_logprobs(gold["clp.logits"], gold["clp.labels"], 0)
     assert torch.allclose(got, gold["clp.out"], atol=1e-6)
     assert (got[gold["clp.labels"] == 0] == 0).all()
+
+
+@pytest.mark.parametrize("eos", [2, 298, 215, 159])
+def test_greedy_rollout_matches_hf_generate_with_early_eos(gold, setup, eos):
+    """The oracle's greedy loop against transformers' own `generate()` (GenerationMixin greedy search [UPSTREAM], what
+    online_generator.py:292-309 calls) over the HF stand-in model, with the EOS id moved onto tokens that the greedy path
+    really emits, so that rows finish early at different steps: finished rows emit pad, the others go on."""
+    import dataclasses
+    from oracle.make_golden import HFLlava
+    cfg, _, lp, _, images, q, qm, _ = setup
+    wp = O.init_weights(cfg, peaked=40.0)
+    model = HFLlava(cfg, wp, {"lora_policy": lp})
+    model.set_adapter("lora_policy")
+    with torch.no_grad():
+        x, mask = model.splice(q, qm, images)
+        want = model.llm.generate(inputs_embeds=x, attention_mask=mask.long(), max_new_tokens=12, do_sample=False,
+                                  pad_token_id=cfg.pad_id, eos_token_id=eos)
+    ids, margin = O.greedy_generate(dataclasses.replace(cfg, eos_id=eos), wp, lp, images, q, qm, 12)
+    got = ids[:, q.size(1):]
+    if want.size(1) < 12:        # generate() stops once every row has finished; the oracle (and the engine) pad to max_new_tokens
+        want = torch.cat([want, torch.full((want.size(0), 12 - want.size(1)), cfg.pad_id)], 1)
+    assert margin > 1e-3 and torch.equal(got, want), (got, want)
+    if eos != 2:
+        assert (got == cfg.pad_id).any(), "the case must make at least one row finish early"
