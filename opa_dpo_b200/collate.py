@@ -85,8 +85,11 @@ class SegmentPack:
         self.flags: List[int] = []
         self.row_offsets: List[int] = [0]
         self.row_present: List[int] = []          # entries that tokenised to more than BOS, per row
+        self.float_weights = False                # some present entry carries float weights (see report_segments)
 
-    def add(self, raw: Sequence[int], score: float, relation: float, flags: int):
+    def add(self, raw: Sequence[int], score: float, relation: float, flags: int, integer_weights: bool = False):
+        if len(raw) > 1 and not integer_weights:
+            self.float_weights = True
         self.tokens.extend(int(t) for t in raw)
         self.seg_offsets.append(len(self.tokens))
         self.score.append(score)
@@ -146,7 +149,10 @@ def report_segments(tokenize, reports: List[dict], originals: List[str]) -> Tupl
                 orig.add(cop, ws, wr, keep | SEG_STRIP_SPACE)
                 ai.add(rewritten, ws, wr, keep)
             else:
-                ai.add(rewritten, 1.0, 1.0, keep)
+                # 'Added' entries get torch.ones_like(ids) — INTEGER ones, not ones * float (:193-194); when every entry
+                # that reaches a stream of the batch is of this kind, torch.cat / stack never promote and the reference's
+                # score and image-relation rows come out int64
+                ai.add(rewritten, 1.0, 1.0, keep, integer_weights=True)
         orig.end_row()
         ai.end_row()
     return orig, ai
@@ -302,6 +308,8 @@ class B200DataCollator:
                 print(e)
         if detailed is not None:
             o, a = detailed
+            if not ai.float_weights:           # only 'Added' entries in the whole batch: the reference's rows are int64
+                a = (a[0], a[1], a[2].long(), a[3].long(), a[4])
             batch.update({"original_generate_response": o[0], "original_generate_response_attention_mask": o[1].bool(),
                           "AI_pseudo_response": a[0], "AI_pseudo_response_attention_mask": a[1].bool(),
                           "original_generate_response_scores": o[2], "AI_pseudo_response_scores": a[2],
