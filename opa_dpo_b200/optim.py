@@ -108,6 +108,20 @@ def get_last_checkpoint(folder: str) -> Optional[str]:
     return best
 
 
+def last_checkpoint_and_completion(checkpoint_dir: str):
+    """The reference's own return contract (utils/lora_utils.py:31-47): (path of the highest checkpoint-N or None, whether a
+    `completed` marker exists). checkpoint-0 counts as "no checkpoint", as there. One difference, on purpose: a
+    `checkpoint-final` directory next to the numbered ones is skipped here, where the reference's int() raises."""
+    if not os.path.isdir(checkpoint_dir):
+        return None, False
+    if os.path.exists(os.path.join(checkpoint_dir, "completed")):
+        return None, True
+    best = get_last_checkpoint(checkpoint_dir)
+    if best is None or best.endswith("checkpoint-0"):
+        return None, False
+    return best, False
+
+
 def save_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], output_dir: str, step,
                     is_main_process: bool = True):
     """DPOTrainer.save_model (dpo_trainer.py:837-899): rank 0 writes the policy adapter in PEFT layout plus optimizer.pt and

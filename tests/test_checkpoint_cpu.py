@@ -103,3 +103,33 @@ def test_engine_config_from_hf_and_adapter_dir(tmp_path):
     assert dict(K.iter_checkpoint_tensors(str(single)))["a"].tolist() == [1.0, 1.0]
     with pytest.raises(FileNotFoundError):
         K.shard_files(str(flat))
+
+
+def test_last_checkpoint_contract_vs_reference_function(tmp_path):
+    """utils/lora_utils.get_last_checkpoint run verbatim against optim.last_checkpoint_and_completion on the same trees."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    import contextlib
+    import io
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    from utils import lora_utils as L
+    from opa_dpo_b200.optim import last_checkpoint_and_completion as mine
+
+    def ref(d):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return L.get_last_checkpoint(d)
+    d = tmp_path / "run"
+    assert mine(str(d)) == ref(str(d)) == (None, False)                 # first training
+    d.mkdir()
+    assert mine(str(d)) == ref(str(d)) == (None, False)                 # started, nothing saved
+    (d / "checkpoint-0").mkdir()
+    assert mine(str(d)) == ref(str(d))
+    for n in (75, 150, 9):
+        (d / f"checkpoint-{n}").mkdir()
+        assert mine(str(d)) == ref(str(d))
+    assert mine(str(d))[0].endswith("checkpoint-150")
+    (d / "checkpoint-300").write_text("a file, not a directory")
+    assert mine(str(d)) == ref(str(d))
+    (d / "completed").write_text("")
+    assert mine(str(d)) == ref(str(d)) == (None, True)
