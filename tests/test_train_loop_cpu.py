@@ -1,7 +1,8 @@
 """Outer training loop (RLTrainer.train, rl_trainer.py:217-279): step numbering, save cadence, resume
 skipping, max_step cut. The reference's own `RLTrainer.train` is run VERBATIM here (imported from /root/reference with the
 package stubs of oracle/make_golden.py) over a recording subclass; where /root/reference is absent (the GPU box) the same
-event logs come from tests/golden/train_loop_events.json, which this test (re)writes when the reference is present."""
+event logs come from tests/golden/train_loop_events.json; when the reference is present the committed file is also checked
+against a live run (OPADPO_REGEN_GOLDEN=1 rewrites it)."""
 import json
 import os
 import sys
