@@ -344,3 +344,47 @@ class _DeviceOps:
 
 _DEVICE_OPS = _DeviceOps()
 
+
+
+class B200DPODataset:
+    """DPO_Dataset (utils/data_utils_dpo.py:289-343) with the image work left to the device: same items, same query
+    template, same keys — but 'images' is the DECODED uint8 RGB array [H, W, 3] (image file, `image_id`, or base64
+    `image_bytes`, in the reference's order of precedence) instead of the CPU-preprocessed tensor; B200DataCollator then
+    runs expand2square + CLIP preprocess for the whole batch on the GPU (`preprocess_images`), bit-identical to what the
+    reference's processor produces. JPEG / PNG decoding itself stays with Pillow on the host."""
+
+    query_templete_prefix = ("<s> A chat between a curious user and an artificial intelligence assistant. The assistant gives "
+                             "helpful, detailed, and polite answers to the user's questions. USER: ")
+    query_templete_suffix = " ASSISTANT: "
+
+    def __init__(self, dataset, image_dir: Optional[str] = None):
+        self.dataset = dataset
+        self.image_dir = image_dir
+
+    def __len__(self):
+        return len(self.dataset)
+
+    def _decode(self, item) -> np.ndarray:
+        import base64
+        import io
+        import os
+        from PIL import Image
+        folder = self.image_dir if self.image_dir is not None else os.environ.get("IMAGE_DIR", "")
+        if "images" in item:
+            img = Image.open(os.path.join(folder, item["images"]))
+        elif "image_id" in item:
+            img = Image.open(os.path.join(folder, item["image_id"]))
+        elif "image_bytes" in item:
+            img = Image.open(io.BytesIO(base64.b64decode(item["image_bytes"].encode("utf-8"))))
+        else:
+            raise ValueError("No image found in the dataset")
+        return np.asarray(img.convert("RGB"), dtype=np.uint8)
+
+    def __getitem__(self, idx):
+        item = self.dataset[idx]
+        return {"queries": self.query_templete_prefix + item["queries"].replace("<image>", "图 ") + self.query_templete_suffix,
+                "images": self._decode(item),
+                "standard_response": item["standard_response"],
+                "original_generate_response": item["original_generate_response"],
+                "AI_pseudo_response": item["AI_pseudo_response"],
+                "AI_json_report": item["AI_json_report"]}

@@ -483,3 +483,47 @@ def test_host_mirror_whole_collator_property_vs_reference_collator():
             got = B200DataCollator(C.StubTokenizer(), 8, R, detailed_report=detailed, ops=OracleOps())([dict(i) for i in batch_in])
         _same_batch(got, want)
     check()
+
+
+def test_host_mirror_dataset_vs_reference_dataset(tmp_path, monkeypatch):
+    """B200DPODataset.__getitem__ against the reference's DPO_Dataset.__getitem__ run verbatim: identical text fields
+    (query template, the placeholder glyph for <image>), and the decoded uint8 image it hands to the GPU collator turns —
+    through the oracle's expand2square + CLIP preprocess, which the kernels are tested against — into exactly the tensor
+    the reference's processor returns. All three image sources (file via 'images' / 'image_id', base64 'image_bytes')."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    import base64
+    import io
+    from types import SimpleNamespace
+    from PIL import Image
+    from transformers.models.clip.image_processing_pil_clip import CLIPImageProcessorPil
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    from utils import data_utils_dpo as D
+    from opa_dpo_b200.collate import B200DPODataset
+    rs = np.random.RandomState(0)
+    imgs = [rs.randint(0, 256, s).astype(np.uint8) for s in ((40, 70, 3), (91, 64, 3), (56, 56, 3))]
+    Image.fromarray(imgs[0]).save(tmp_path / "a.png")
+    Image.fromarray(imgs[1]).save(tmp_path / "b.png")
+    buf = io.BytesIO()
+    Image.fromarray(imgs[2]).save(buf, format="PNG")
+    text = {"standard_response": "s", "original_generate_response": "o", "AI_pseudo_response": "p", "AI_json_report": "{}"}
+    items = [{"images": "a.png", "queries": "<image>\nwhat is this?", **text},
+             {"image_id": "b.png", "queries": "describe <image> now", **text},
+             {"image_bytes": base64.b64encode(buf.getvalue()).decode(), "queries": "no placeholder", **text}]
+    monkeypatch.setenv("IMAGE_DIR", str(tmp_path))
+    proc = CLIPImageProcessorPil(size={"shortest_edge": 56}, crop_size={"height": 56, "width": 56})
+    ref = D.DPO_Dataset(SimpleNamespace(image_processor=proc, image_aspect_ratio="pad"), items)
+    mine = B200DPODataset(items)
+    assert len(mine) == len(ref) == 3
+    for i in range(3):
+        r, m = ref[i], mine[i]
+        assert set(r) == set(m)
+        for k in r:
+            if k != "images":
+                assert r[k] == m[k], k
+        assert m["images"].dtype == np.uint8 and np.array_equal(m["images"], imgs[i])
+        want = r["images"].numpy() if hasattr(r["images"], "numpy") else np.asarray(r["images"])
+        assert np.array_equal(C.clip_preprocess(m["images"], 56, True), want.astype(np.float32)), i
+    with pytest.raises(ValueError):
+        B200DPODataset([{"queries": "q", **text}])[0]
