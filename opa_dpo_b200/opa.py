@@ -47,6 +47,36 @@ def sft_loss(outputs: Dict[str, Tensor], responses: Dict[str, Tensor], pad_token
     return total / count.clamp(min=1)
 
 
+def sft_batch_to_policy_inputs(input_ids: Tensor, labels: Tensor, pad_token_id: int, query_len: int, response_len: int,
+                               ignore_index: int = -100):
+    """The OPA stage's collated batch (utils/data_utils_sft.py:20-69: rows `prompt | response`, right-padded, labels =
+    IGNORE_INDEX on the prompt and the padding) -> the policy boundary's inputs: queries [b, query_len] left-padded with
+    their mask, responses [b, response_len] right-padded. Causal attention with RoPE depends on relative positions only, so
+    moving the padding from the right of the row to the left of the prompt leaves every labelled token's distribution
+    unchanged. Single-turn rows only (one labelled span); a row that does not fit raises instead of being truncated."""
+    b, L = input_ids.shape
+    labelled = labels != ignore_index
+    n_resp = labelled.sum(1)
+    n_tok = (input_ids != pad_token_id).sum(1)
+    first = torch.where(n_resp > 0, labelled.int().argmax(1), n_tok)          # prompt length of every row
+    pos = torch.arange(L, device=input_ids.device)[None, :]
+    span = (pos >= first[:, None]) & (pos < (first + n_resp)[:, None])
+    if not torch.equal(span, labelled):
+        raise ValueError("sft_batch_to_policy_inputs: a row has more than one labelled span (multi-turn rows are not a "
+                         "query + one response)")
+    if int(first.max()) > query_len or int(n_resp.max()) > response_len:
+        raise ValueError(f"sft_batch_to_policy_inputs: prompt {int(first.max())} / response {int(n_resp.max())} tokens do not "
+                         f"fit query_len {query_len} / response_len {response_len}")
+    q_pos = torch.arange(query_len, device=input_ids.device)[None, :] - (query_len - first)[:, None]   # source column or < 0
+    q_valid = q_pos >= 0
+    queries = torch.where(q_valid, input_ids.gather(1, q_pos.clamp(min=0)), torch.full_like(q_pos, pad_token_id))
+    r_pos = torch.arange(response_len, device=input_ids.device)[None, :]
+    r_valid = r_pos < n_resp[:, None]
+    src = (first[:, None] + r_pos).clamp(max=L - 1)
+    responses = torch.where(r_valid, input_ids.gather(1, src), torch.full_like(src, pad_token_id))
+    return queries, q_valid, responses
+
+
 def entropy_loss(outputs: Dict[str, Tensor], masked_outputs: Dict[str, Tensor], responses: Dict[str, Tensor],
                  pad_token_id: int = 0) -> Tensor:
     """opa_trainer.py:82-86: per row -sum((H_masked - H) * mask) / sum(mask) with mask = labelled positions, then the

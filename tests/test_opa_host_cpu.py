@@ -129,3 +129,51 @@ def test_opa_compute_loss_vs_reference_llava_trainer(entropy):
     assert abs(loss2.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item()), (loss2.item(), loss_ref.item())
     (g2,) = torch.autograd.grad(loss2, theta)
     assert torch.allclose(g2, g_ref, atol=1e-7, rtol=1e-5)
+
+
+def test_sft_batch_to_policy_inputs_is_loss_preserving():
+    """The OPA collator's rows (prompt | response, right-padded, IGNORE_INDEX labels) re-laid-out for the policy boundary:
+    the tokens are the same, and the oracle's model gives the same HF causal-LM loss on the original rows as the
+    log-prob form gives on the converted inputs (left-padded prompt: RoPE is relative, padding is masked)."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.opa import sft_batch_to_policy_inputs, sft_loss
+    cfg = O.OracleConfig()
+    w = O.init_weights(cfg)
+    lp = O.init_lora(cfg, 11)
+    g = torch.Generator().manual_seed(2)
+    b, L, Q, R = 3, 30, 16, 20
+    input_ids = torch.zeros(b, L, dtype=torch.long)
+    labels = torch.full((b, L), -100)
+    for i, (np_, nr) in enumerate(((9, 14), (14, 6), (11, 19))):
+        row = torch.randint(3, cfg.vocab, (np_ + nr,), generator=g)
+        row[4] = cfg.image_token
+        row[-1] = cfg.eos_id
+        input_ids[i, :np_ + nr] = row
+        labels[i, np_:np_ + nr] = row[np_:]
+    images = torch.randn(b, 3, cfg.v_image, cfg.v_image, generator=g)
+    q, qm, resp = sft_batch_to_policy_inputs(input_ids, labels, cfg.pad_id, Q, R)
+    assert q.shape == (b, Q) and resp.shape == (b, R) and qm.dtype == torch.bool
+    for i in range(b):
+        toks = torch.cat([q[i][qm[i]], resp[i][resp[i] != 0]])
+        assert torch.equal(toks, input_ids[i][input_ids[i] != 0])
+        assert torch.equal(resp[i][resp[i] != 0], labels[i][labels[i] != -100])
+    with torch.no_grad():
+        logits = O.llava_logits(cfg, w, lp, input_ids, input_ids != 0, images)
+        Lm = logits.shape[1]                                   # text positions + patches - 1
+        P = cfg.n_patches
+        # HF shifted loss on the spliced row: label of spliced position p is the token at p + 1
+        full_labels = torch.full((b, Lm), -100)
+        for i in range(b):
+            slot = int((input_ids[i] == cfg.image_token).nonzero()[0])
+            full_labels[i, :slot] = labels[i, :slot]
+            full_labels[i, slot + P:] = labels[i, slot + 1:]
+        want = F.cross_entropy(logits[:, :-1].reshape(-1, cfg.vocab), full_labels[:, 1:].reshape(-1), ignore_index=-100)
+        out = O.policy_forward(cfg, w, lp, images, q, qm, {"standard_response": resp})
+    got = sft_loss(out, {"standard_response": resp}, cfg.pad_id)
+    assert abs(got.item() - want.item()) <= 2e-5 * abs(want.item()), (got.item(), want.item())
+    multi = labels.clone()
+    multi[0, 2] = 5
+    with pytest.raises(ValueError):
+        sft_batch_to_policy_inputs(input_ids, multi, cfg.pad_id, Q, R)
+    with pytest.raises(ValueError):
+        sft_batch_to_policy_inputs(input_ids, labels, cfg.pad_id, 8, R)
