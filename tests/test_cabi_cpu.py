@@ -149,3 +149,26 @@ def test_importing_the_whole_package_does_not_load_the_oracle():
             "    importlib.import_module('opa_dpo_b200.' + m.name)\n"
             "assert not any(k == 'oracle' or k.startswith('oracle.') for k in sys.modules), 'oracle imported'\n")
     subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+
+
+def test_collator_abi_argument_errors_without_gpu():
+    """Error convention of the collator-stage entry points (include/opadpo_b200.h): bad arguments return OPADPO_EINVAL (-1)
+    with a message, before anything touches CUDA — so this runs on a machine without a GPU."""
+    import ctypes
+    from opa_dpo_b200 import _lib
+    lib = _lib.load()
+    lib.opadpo_last_error.restype = ctypes.c_char_p
+    seg = _lib.Segments(None, None, None, None, None, None, 2)
+    assert lib.opadpo_op_collate_responses(ctypes.byref(seg), 8, 0, 2, 1, None, None, None, None, None, None) == -1
+    assert b"collate_responses" in lib.opadpo_last_error()
+    assert lib.opadpo_op_collate_queries(None, None, 1, 8, 0, 30861, -200, None, None, None) == -1
+    assert lib.opadpo_op_mask_images(None, None, 1, 3, 28, 28, None, 0, 1, 0, None, None) == -1
+    buf = (ctypes.c_float * 4)()
+    assert lib.opadpo_op_mask_images(buf, buf, 1, 3, 28, 30, None, 0, 14, 0, None, None) == -1      # block must divide H and W
+    assert b"block" in lib.opadpo_last_error()
+    assert lib.opadpo_op_attention_holes(None, None, 1, 16, 0, None) == -1
+    assert lib.opadpo_op_preprocess_images(None, None, None, None, 1, 336, None, None, None, 1, None, None) == -1
+    assert lib.opadpo_op_truncate_after_eos(None, None, 1, 8, 2, 0, None, 0, None) == -1
+    ids = (ctypes.c_int64 * 8)()
+    assert lib.opadpo_op_truncate_after_eos(ids, ids, 1, 8, 2, 0, None, 3, None) == -1               # n_extra > 0 without the array
+    assert lib.opadpo_backward_ent(None, 0, None, None, None) == -1 and b"null engine" in lib.opadpo_last_error()
