@@ -1,7 +1,8 @@
 """CPU oracle of the collator stage — TEST INFRASTRUCTURE ONLY.
 
 A numpy restatement of what the reference does between the tokenizer / image decoder and the policy forward. Only
-tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import it; the product (opa_dpo_b200/) never does.
+tests/, __graft_entry__.smoke() and the cpu_baseline legs of bench.py / tools/bench_*.py may import it; the product
+(opa_dpo_b200/) never does.
 Pinned by tests/golden/collate_golden.npz, which oracle/make_golden_collate.py produced by running the reference's own
 code here (DataCollatorForCausalLM.__call__ over a deterministic stub tokenizer, DPO_Dataset.__getitem__ over
 HuggingFace's PIL-backed CLIP image processor, dpo_trainer.mask_single_image / mask_percentage_per_row).

@@ -1,6 +1,7 @@
 """CPU fp32 oracle of the OPA-DPO hot path.  TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module;
+Only tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py and tools/bench_*.py may import
+this module;
 the product (opa_dpo_b200/) never does and has no CPU path.
 
 Parity pinning: the reference repository ships NO tests, golden vectors or fixtures for this path (SURVEY.md §4,
