@@ -37,7 +37,9 @@ int opadpo_abi_version(void);
  * Replaces (reference, all [UPSTREAM] through peft 0.5.0 lora.Linear wrapped nn.Linear; call sites
  * opadpo/dpo_models/qlora_model.py:133-143,211-216 and opadpo/dpo_models/rl_models.py:120).
  * ---------------------------------------------------------------------------------------------------------- */
-enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3, OPADPO_EPI_F32_PARTIAL = 4 };
+enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3, OPADPO_EPI_F32_PARTIAL = 4,
+       OPADPO_EPI_BF16_ROPE = 5 /* bf16 output with HF LLaMA's rotary embedding [UPSTREAM apply_rotary_pos_emb] applied to the
+                                    first rope_cols columns (heads of 128 columns, column j paired with j + 64) */ };
 enum { OPADPO_ACT_NONE = 0, OPADPO_ACT_GELU = 1, OPADPO_ACT_QUICK_GELU = 2 };
 
 typedef struct opadpo_gemm_desc {
@@ -64,6 +66,9 @@ typedef struct opadpo_gemm_desc {
   int32_t cluster_mode;           /* 0 auto, 1 off, 2: 2-CTA cluster that multicasts the shared B tile, 3: CTA pair (tcgen05 cta_group::2, 256x256 MMA) */
   const float* dent;              /* EPI_CEGRAD: d(loss)/d(entropy) [M] or NULL (opa_models/opa_trainer.py:63,82-85) */
   const float* ent;               /* EPI_CEGRAD: per-row entropy [M], required with dent */
+  const int32_t* rope_pos;        /* EPI_BF16_ROPE: position of every output row [M], or NULL = row % rope_S */
+  const void* rope_cs;            /* EPI_BF16_ROPE: float2 (cos, sin) table [positions, 64] */
+  int32_t rope_cols, rope_S;
 } opadpo_gemm_desc;
 
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);
@@ -231,6 +236,7 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
  * "merge_frozen" (default 0): inference forwards (save_slot = -1) and rollouts of a NON-trainable adapter run on decoder
  * weights merged once, W' = W + (alpha/r) B A (peft merge_adapter semantics; bf16 W'), so the reference pass of the DPO
  * step carries no LoRA GEMMs; costs one extra copy of the decoder weights, rebuilt when that adapter is reloaded.
+ * "fuse_rope" (default 0, not yet validated on a GPU): the q|k|v projection applies RoPE in its GEMM epilogue.
  * "merge_rollout" (default 1): rollouts merge the adapter per call. "adam_step": optimizer-state restore. */
 int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 /* Communication overlap: `cb(layer, user)` is called on the host thread inside opadpo_backward right after the backward

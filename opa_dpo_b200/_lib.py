@@ -55,6 +55,9 @@ class GemmDesc(ctypes.Structure):
         ("cluster_mode", ctypes.c_int32),
         ("dent", ctypes.c_void_p),
         ("ent", ctypes.c_void_p),
+        ("rope_pos", ctypes.c_void_p),
+        ("rope_cs", ctypes.c_void_p),
+        ("rope_cols", ctypes.c_int32), ("rope_S", ctypes.c_int32),
     ]
 
 

@@ -26,7 +26,7 @@ using namespace opadpo;
 extern "C" {
 
 const char* opadpo_last_error(void) { return g_last_error; }
-int opadpo_abi_version(void) { return 3; }
+int opadpo_abi_version(void) { return 4; }
 int64_t opadpo_launch_count(void) { return g_launches.load(); }
 
 int opadpo_gemm_n_tiles(int32_t N) { return gemm_num_n_tiles(N); }
@@ -65,6 +65,10 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
   a.dlp = d->dlp;
   a.dent = d->dent;
   a.ent = d->ent;
+  a.rope_pos = d->rope_pos;
+  a.rope_cs = static_cast<const float2*>(d->rope_cs);
+  a.rope_cols = d->rope_cols;
+  a.rope_S = d->rope_S;
   a.max_ctas = d->max_ctas;
   a.cluster = d->cluster_mode - 1;  /* 0 (zero-initialised desc) = auto, 1 off, 2 B-multicast cluster, 3 CTA pair */
   int rc = gemm_launch(a, static_cast<cudaStream_t>(stream));

@@ -478,7 +478,7 @@ void Engine::release_slot(int slot, cudaStream_t s) {
 // y = act(x W^T + bias + s*(x A^T) B^T) + residual. The LoRA-A product t = s*x*A^T is a skinny pre-GEMM whose
 // output is consumed as a second K segment of the base GEMM ([x | t] [W ; B]^T into one TMEM accumulator).
 int Engine::linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy,
-                       int act, const bf16* residual, int64_t ldr, cudaStream_t s) {
+                       int act, const bf16* residual, int64_t ldr, cudaStream_t s, RopeFuse* rope) {
   const bool lora = adapter >= 0 && L.slot >= 0 && r > 0;
   const int G = L.groups, out_g = L.out / G;
   if (lora) {
@@ -513,6 +513,14 @@ int Engine::linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
     }
     a.C = y + static_cast<int64_t>(g) * out_g;
     a.ldc = ldy;
+    if (rope && fused && !L.bias && act == ACT_NONE && !residual && hd == 128 && L.out % 128 == 0 && rope->cols % 128 == 0) {
+      a.epilogue = EPI_BF16_ROPE;
+      a.rope_pos = rope->pos;
+      a.rope_cs = rope_cs;
+      a.rope_cols = rope->cols;
+      a.rope_S = rope->S;
+      rope->applied = true;
+    }
     a.bias = L.bias ? L.bias + static_cast<int64_t>(g) * out_g : nullptr;
     a.act = act;
     if (residual) {
@@ -691,8 +699,12 @@ int Engine::llama_layer_fwd(const LlamaLayer& L, int adapter, const SeqLayout& l
   const opadpo_config& c = cfg;
   const int d = c.d_model, F = c.d_ffn;
   EN_CHECK(rmsnorm_fwd(a.x, L.ln1, a.h1, T, d, c.rms_eps, nullptr, s));
-  EN_CHECK(linear_fwd(L.qkv, adapter, a.h1, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s));
-  EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, nullptr, 2 * c.n_heads, hd, rope_cs, 0, s));
+  RopeFuse rf;
+  rf.pos = lay.pos;
+  rf.S = S;
+  rf.cols = 2 * d;
+  EN_CHECK(linear_fwd(L.qkv, adapter, a.h1, d, T, a.tqkv, a.qkv, 3 * d, ACT_NONE, nullptr, 0, s, fuse_rope ? &rf : nullptr));
+  if (!rf.applied) EN_CHECK(rope_inplace(a.qkv, 3 * d, T, S, lay.pos, 0, nullptr, 2 * c.n_heads, hd, rope_cs, 0, s));
   AttnArgs at;
   at.N = N;
   at.S = S;
@@ -1106,6 +1118,10 @@ int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "merge_frozen") == 0) {
     merge_frozen = value != 0;
     if (!merge_frozen) drop_frozen_merged();
+    return 0;
+  }
+  if (strcmp(name, "fuse_rope") == 0) {
+    fuse_rope = value != 0;
     return 0;
   }
   if (strcmp(name, "share_prefix") == 0) {

@@ -123,6 +123,8 @@ class Engine {
   // weights merged once, W' = W + (alpha/r) B A (what peft's merge_adapter does), so they carry no LoRA GEMMs at all.
   // The cache is rebuilt when that adapter's tensors are reloaded. Costs one extra copy of the decoder weights.
   bool merge_frozen = false;
+  // q|k|v projection with RoPE applied in the GEMM epilogue (EPI_BF16_ROPE) instead of a separate in-place pass
+  bool fuse_rope = false;
   int frozen_merged_adapter = -1;
   std::vector<LlamaLayer> frozen_merged;
   std::vector<void*> frozen_merged_allocs;
@@ -157,8 +159,13 @@ class Engine {
   const bf16* loraA(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offA; }
   const bf16* loraB(int adapter, const LinearW& L) const { return adapters[adapter].shadow + slots[L.slot].offB; }
 
+  struct RopeFuse {
+    const int32_t* pos = nullptr;  // position of every row (null: row % S)
+    int S = 0, cols = 0;           // cols: leading output columns that are rotated (q and k)
+    bool applied = false;          // set by linear_fwd when the projection ran as ONE GEMM with the rotary epilogue
+  };
   int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy, int act,
-                 const bf16* residual, int64_t ldr, cudaStream_t s);
+                 const bf16* residual, int64_t ldr, cudaStream_t s, RopeFuse* rope = nullptr);
   int linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
                  int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s);
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);

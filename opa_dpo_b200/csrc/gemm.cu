@@ -46,6 +46,9 @@ struct KParams {
   const float* dlp;
   const float* dent;  // EPI_CEGRAD: d(loss)/d(entropy) per row, or null
   const float* ent;   // EPI_CEGRAD: the row's entropy (needed with dent)
+  const int32_t* rope_pos;  // EPI_BF16_ROPE
+  const float2* rope_cs;
+  int rope_cols, rope_S;
 };
 
 struct Tile {
@@ -358,6 +361,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
           __syncwarp();
         }
+      } else if constexpr (EPI == EPI_BF16_ROPE) {
+        // q|k|v projection with the rotary embedding applied to the fp32 accumulator (one bf16 rounding instead of two and
+        // no separate pass over q and k): heads are 128 columns, HF's rotate_half pairs column j with j + 64, the table
+        // holds (cos, sin) for j < 64 of every position; columns from rope_cols on (v) are stored as they are.
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+        const int pos = row_ok ? (p.rope_pos ? p.rope_pos[row] : row % p.rope_S) : 0;
+        const float2* cs = p.rope_cs + static_cast<int64_t>(pos) * 64;
+#pragma unroll 1
+        for (int hh = 0; hh < BN / 128; ++hh) {
+          const int colh = n0 + hh * 128;
+          const bool rot = colh < p.rope_cols;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t lo[32], hi[32];
+            ptx::tmem_ld32(taddr + hh * 128 + half * 32, lo);
+            ptx::tmem_ld32(taddr + hh * 128 + 64 + half * 32, hi);
+            ptx::tmem_ld_wait();
+            if (row_ok && colh < p.N) {
+              float a[32], b[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                a[j] = __uint_as_float(lo[j]) * p.alpha;
+                b[j] = __uint_as_float(hi[j]) * p.alpha;
+              }
+              if (rot) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float2 k = __ldg(cs + half * 32 + j);
+                  const float na = a[j] * k.x - b[j] * k.y;
+                  const float nb = b[j] * k.x + a[j] * k.y;
+                  a[j] = na;
+                  b[j] = nb;
+                }
+              }
+              uint4* dlo = reinterpret_cast<uint4*>(crow + colh + half * 32);
+              uint4* dhi = reinterpret_cast<uint4*>(crow + colh + 64 + half * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u, w;
+                u.x = ptx::pack_bf16(a[q * 8 + 0], a[q * 8 + 1]);
+                u.y = ptx::pack_bf16(a[q * 8 + 2], a[q * 8 + 3]);
+                u.z = ptx::pack_bf16(a[q * 8 + 4], a[q * 8 + 5]);
+                u.w = ptx::pack_bf16(a[q * 8 + 6], a[q * 8 + 7]);
+                w.x = ptx::pack_bf16(b[q * 8 + 0], b[q * 8 + 1]);
+                w.y = ptx::pack_bf16(b[q * 8 + 2], b[q * 8 + 3]);
+                w.z = ptx::pack_bf16(b[q * 8 + 4], b[q * 8 + 5]);
+                w.w = ptx::pack_bf16(b[q * 8 + 6], b[q * 8 + 7]);
+                dlo[q] = u;
+                dhi[q] = w;
+              }
+            }
+            __syncwarp();
+          }
+        }
       } else if constexpr (EPI == EPI_F32_ATOMIC) {
         float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc;
 #pragma unroll 1
@@ -648,7 +705,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: a2_group_n must be a multiple of %d with K-major A", BN);
     return -4;
   }
-  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD) && (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+  if (a.epilogue == EPI_BF16_ROPE &&
+      (a.N % 128 != 0 || a.rope_cols % 128 != 0 || !a.rope_cs || a.bias || a.residual || a.act != ACT_NONE ||
+       (!a.rope_pos && a.rope_S <= 0) || a.splits > 1)) {
+    snprintf(g_err, sizeof(g_err), "gemm: EPI_BF16_ROPE needs N and rope_cols multiples of 128, a table, positions or rope_S, and no bias / act / residual");
+    return -8;
+  }
+  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD || a.epilogue == EPI_BF16_ROPE) &&
+      (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
     snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
     return -5;
   }
@@ -739,6 +803,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   kp.dlp = a.dlp;
   kp.dent = a.dent;
   kp.ent = a.ent;
+  kp.rope_pos = a.rope_pos;
+  kp.rope_cs = a.rope_cs;
+  kp.rope_cols = a.rope_cols;
+  kp.rope_S = a.rope_S;
 
   int grid = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
@@ -757,6 +825,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_LSE: return launch_impl<AMN, BMN, EPI_LSE, CL>(maps, kp, grid, stream);              \
     case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD, CL>(maps, kp, grid, stream);        \
     case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL, CL>(maps, kp, grid, stream); \
+    case EPI_BF16_ROPE: return launch_impl<AMN, BMN, EPI_BF16_ROPE, CL>(maps, kp, grid, stream);   \
     default: break;                                                                               \
   }
 #define OPADPO_DISPATCH(AMN, BMN)          \

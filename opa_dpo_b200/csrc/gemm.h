@@ -22,6 +22,7 @@ enum GemmEpilogue : int {
   EPI_LSE = 2,       // fused lm_head log-sum-exp partials + label-logit gather (never materialises logits)
   EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - p) - dent[m]*alpha*p*(ln p + ent[m]),  p = exp(alpha*acc - lse[m])
   EPI_F32_PARTIAL = 4,  // C f32 [splits, M, ldc]: plain per-split stores (decode: weight streaming fills all SMs, fixed-order reduce)
+  EPI_BF16_ROPE = 5,    // C bf16 = rotary(alpha*acc) on the first rope_cols columns (heads of 128, HF rotate_half pairing), plain beyond
 };
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICK_GELU = 2 };
@@ -55,6 +56,10 @@ struct GemmArgs {
   const float* dlp = nullptr;       // [M] (may be null when only dent is given)
   const float* dent = nullptr;      // EPI_CEGRAD: d(loss)/d(entropy) [M] or null; adds -dent*alpha*p_v*(ln p_v + ent)
   const float* ent = nullptr;       // EPI_CEGRAD: entropy of each row [M] (required with dent)
+  // EPI_BF16_ROPE: position of every output row (null: row % rope_S), table [positions][64] of (cos, sin), rotated columns
+  const int32_t* rope_pos = nullptr;
+  const float2* rope_cs = nullptr;
+  int rope_cols = 0, rope_S = 0;
   int max_ctas = 0;                 // 0 = all SMs
   int cluster = -1;                 // -1 auto, 0 off, 1 B-multicast 2-CTA cluster, 2 CTA pair (cta_group::2 MMA, K-major A)
 };

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import AttnDesc, GemmDesc
 
-EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD = 0, 1, 2, 3
+EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD, EPI_F32_PARTIAL, EPI_BF16_ROPE = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2
 
 
@@ -36,7 +36,8 @@ def gemm_n_tiles(n: int) -> int:
 def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=None, a_mn=False, b_mn=False,
          alpha: float = 1.0, epilogue: int = EPI_BF16, bias=None, residual=None, act: int = ACT_NONE,
          a2_group_n: int = 0, a2_group_stride: int = 0, splits: int = 1, labels=None, lse_partials=None,
-         label_logit=None, lse=None, dlp=None, dent=None, ent=None, M=None, N=None, K1=None, K2=None, max_ctas: int = 0, cluster: int = -1):
+         label_logit=None, lse=None, dlp=None, dent=None, ent=None, rope_pos=None, rope_cs=None, rope_cols: int = 0,
+         rope_S: int = 0, M=None, N=None, K1=None, K2=None, max_ctas: int = 0, cluster: int = -1):
     """out[M,N] = epilogue(alpha*(A1 B1^T + A2 B2^T)). Operand shapes follow their 'major':
     K-major A is [M,K], MN-major A is [K,M]; K-major B is [N,K], MN-major B is [K,N]."""
     lib = _lib.load()
@@ -75,6 +76,7 @@ def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=N
     d.lse = _ptr(lse)
     d.dlp = _ptr(dlp)
     d.dent, d.ent = _ptr(dent), _ptr(ent)
+    d.rope_pos, d.rope_cs, d.rope_cols, d.rope_S = _ptr(rope_pos), _ptr(rope_cs), rope_cols, rope_S
     d.max_ctas = max_ctas
     d.cluster_mode = cluster + 1   # -1 auto, 0 off, 1 on
     _lib.check(lib.opadpo_op_gemm(ctypes.byref(d), ctypes.c_void_p(_stream())), "opadpo_op_gemm")

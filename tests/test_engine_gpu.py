@@ -788,3 +788,47 @@ def test_greedy_rollout_early_eos_ids_exact(eos):
     assert margin > 0.05 and torch.equal(got, ids_ref), (got[:, 16:], ids_ref[:, 16:])
     assert (ids_ref[:, 16:] == oc.pad_id).any()
     eng.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1)")
+@pytest.mark.parametrize("share", [0, 1])
+def test_fused_rope_epilogue_option_vs_oracle(share):
+    """Option fuse_rope: RoPE applied in the q|k|v GEMM epilogue instead of a separate pass. Same tolerances vs the oracle as
+    the default path (forward log-probs, DPO loss 1e-3, LoRA gradients), and close to the unfused path."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, REF
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, share_prefix=share)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    base_lp, _ = eng.forward_logprobs(POLICY, *args)
+    eng.set_option("fuse_rope", 1)
+    lc = O.LossConfig(beta=0.1)
+    loss_ref, lpg, ref_o, pol_o = _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, NAMES2)
+    ref_lp, _ = eng.forward_logprobs(REF, *args)
+    pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+    for i, n in enumerate(NAMES2):
+        _cmp_lp(pol_lp[i], pol_o[n + "_logprobs"], f"fused rope policy {n}")
+        _cmp_lp(ref_lp[i], ref_o[n + "_logprobs"], f"fused rope ref {n}")
+    assert (pol_lp - base_lp).abs().max().item() <= 0.05
+    pl = pol_lp.clone().requires_grad_(True)
+    total, _ = FusedDPO(DPOArgs(beta=0.1)).pair(pl[0], pl[1], ref_lp[0], ref_lp[1])
+    total.backward()
+    assert abs(total.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
+    eng.zero_grad()
+    eng.backward(0, pl.grad)
+    torch.cuda.synchronize()
+    grad = eng.buffers()["grad"]
+    for m in ("model.layers.0.self_attn.q_proj", "model.layers.1.self_attn.k_proj", "model.layers.1.mlp.down_proj"):
+        A, B = lpg[m]
+        oa, ob = eng.lora_offsets(m)
+        for t, off in ((A, oa), (B, ob)):
+            gg = grad[off:off + t.numel()].view_as(t).cpu()
+            cos = torch.nn.functional.cosine_similarity(gg.flatten(), t.grad.flatten(), dim=0).item()
+            assert cos >= 0.99, (m, cos)
+    ids = eng.generate(POLICY, images, q, qm, 4)          # the rollout prefill goes through the same projection
+    assert ids.shape == (3, 20)
+    eng.close()

@@ -211,3 +211,39 @@ def test_gemm_cluster_lora_groups_bias_residual_and_mn_major(mode):
     ops.gemm(a, b, acc2, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC, cluster=1)
     torch.cuda.synchronize()
     _close(acc2, a.float().t() @ b.float(), what="cluster wgrad")
+
+
+_UNVERIFIED = pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
+                                 reason="written after the round's GPU budget was spent: not yet run on a GPU "
+                                        "(set OPADPO_RUN_UNVERIFIED=1)")
+
+
+@_UNVERIFIED
+@pytest.mark.parametrize("cluster", [0, 2])
+@pytest.mark.parametrize("with_pos", [True, False])
+def test_gemm_rope_epilogue(cluster, with_pos):
+    """EPI_BF16_ROPE: q|k|v projection (with the LoRA second segment) whose epilogue applies HF LLaMA's rotary embedding to
+    the q and k columns, vs an fp32 matmul + apply_rotary_pos_emb (rotate_half pairing j <-> j + 64 inside 128-wide heads)."""
+    from opa_dpo_b200 import ops
+    M, d, K, r, S = 1100, 256, 320, 64, 275
+    x, W = _mk((M, K), 31), _mk((3 * d, K), 32, 0.1)
+    t, B = _mk((M, 3 * r), 33), _mk((3 * d, r), 34, 0.1)
+    g = torch.Generator(device="cuda").manual_seed(35)
+    pos = torch.randint(0, 500, (M,), generator=g, device="cuda", dtype=torch.int32) if with_pos else None
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 128, 2, device="cuda", dtype=torch.float32) / 128))
+    ang = torch.arange(512, device="cuda", dtype=torch.float32)[:, None] * inv[None, :]
+    cs = torch.stack([ang.cos(), ang.sin()], -1).contiguous()              # [positions, 64, 2] = float2 table
+    out = torch.full((M, 3 * d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, W, out, a2=t, b2=B, a2_group_n=d, a2_group_stride=r, epilogue=ops.EPI_BF16_ROPE, rope_pos=pos, rope_cs=cs,
+             rope_cols=2 * d, rope_S=S, cluster=cluster)
+    torch.cuda.synchronize()
+    ref = x.float() @ W.float().t()
+    for gidx in range(3):
+        ref[:, gidx * d:(gidx + 1) * d] += t.float()[:, gidx * r:(gidx + 1) * r] @ B.float()[gidx * d:(gidx + 1) * d].t()
+    p = pos.long() if with_pos else torch.arange(M, device="cuda") % S
+    c, s = cs[p, :, 0], cs[p, :, 1]                                        # [M, 64]
+    qk = ref[:, :2 * d].reshape(M, 2 * d // 128, 128)
+    lo, hi = qk[..., :64], qk[..., 64:]
+    rot = torch.cat([lo * c[:, None, :] - hi * s[:, None, :], hi * c[:, None, :] + lo * s[:, None, :]], -1).reshape(M, 2 * d)
+    _close(out[:, :2 * d], rot, what="rope q|k")
+    _close(out[:, 2 * d:], ref[:, 2 * d:], what="v untouched")

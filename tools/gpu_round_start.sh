@@ -9,7 +9,8 @@ export PYTHONUNBUFFERED=1
 T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 ))s] $*" | tee -a gpurun_out/round_start_timeline.log; }
 stamp "start"; nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv | tee -a gpurun_out/round_start_timeline.log
-OPADPO_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "reference_alignment or early_eos" \
+OPADPO_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_engine_gpu.py tests/test_gemm_gpu.py -q -m gpu \
+  -k "reference_alignment or early_eos or rope_epilogue" \
   > gpurun_out/t_unverified.log 2>&1; stamp "opt-in tests rc=$?"
 timeout 600 python -m pytest tests/ -x -q -m gpu --durations=8 > gpurun_out/t_all_gpu.log 2>&1; stamp "full gpu suite rc=$?"
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; stamp "smoke rc=$?"
