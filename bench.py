@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--merge-frozen", type=int, default=int(os.environ.get("OPADPO_MERGE_FROZEN", str(MERGE_FROZEN_DEFAULT))),
                     help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
+    ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "0")),
+                    help="1: SwiGLU in the gate|up GEMM epilogue of the merged reference pass (opt-in until validated on a GPU)")
     ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "0")),
                     help="1: RoPE in the q|k|v GEMM epilogue (opt-in until validated on a GPU)")
     args = ap.parse_args()
@@ -208,6 +210,8 @@ def main():
     model.engine.set_option("merge_frozen", args.merge_frozen)
     if args.fuse_rope:
         model.engine.set_option("fuse_rope", 1)
+    if args.fuse_swiglu:
+        model.engine.set_option("fuse_swiglu", 1)
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
     dargs = DPOArgs(beta=0.1, response_len=R, learning_rate=1e-6, max_grad_norm=1.0)
@@ -315,7 +319,7 @@ def main():
                                f"R={R}, 4 forwards (policy+frozen ref x chosen+rejected) + LoRA backward + clip + AdamW",
                    "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
                    "prefix_sharing": (not args.no_share_prefix), "merged_reference_adapter": bool(args.merge_frozen),
-                   "fused_rope_epilogue": bool(args.fuse_rope),
+                   "fused_rope_epilogue": bool(args.fuse_rope), "fused_swiglu_epilogue": bool(args.fuse_swiglu),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
                    "collective": "NCCL all-reduce(sum) of the fp32 LoRA-grad bucket once per step, issued as 33 per-layer slices "
                                  "overlapped with the backward" if world > 1 else "none",

@@ -38,6 +38,8 @@ int opadpo_abi_version(void);
  * opadpo/dpo_models/qlora_model.py:133-143,211-216 and opadpo/dpo_models/rl_models.py:120).
  * ---------------------------------------------------------------------------------------------------------- */
 enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3, OPADPO_EPI_F32_PARTIAL = 4,
+       OPADPO_EPI_SWIGLU_BF16 = 6, /* B rows interleaved [128 gate | 128 up] per 256 columns; C bf16 [M, N/2] = silu(gate) * up with
+                                      the unfused path's bf16 roundings (bit-identical to projection + SwiGLU) */
        OPADPO_EPI_BF16_ROPE = 5 /* bf16 output with HF LLaMA's rotary embedding [UPSTREAM apply_rotary_pos_emb] applied to the
                                     first rope_cols columns (heads of 128 columns, column j paired with j + 64) */ };
 enum { OPADPO_ACT_NONE = 0, OPADPO_ACT_GELU = 1, OPADPO_ACT_QUICK_GELU = 2 };
@@ -237,6 +239,8 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
  * weights merged once, W' = W + (alpha/r) B A (peft merge_adapter semantics; bf16 W'), so the reference pass of the DPO
  * step carries no LoRA GEMMs; costs one extra copy of the decoder weights, rebuilt when that adapter is reloaded.
  * "fuse_rope" (default 0, not yet validated on a GPU): the q|k|v projection applies RoPE in its GEMM epilogue.
+ * "fuse_swiglu" (default 0, not yet validated on a GPU; needs merge_frozen): the merged frozen adapter's gate|up projection
+ * applies SwiGLU in its epilogue over an interleaved copy of the merged weight (bit-identical results).
  * "merge_rollout" (default 1): rollouts merge the adapter per call. "adam_step": optimizer-state restore. */
 int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 /* Communication overlap: `cb(layer, user)` is called on the host thread inside opadpo_backward right after the backward

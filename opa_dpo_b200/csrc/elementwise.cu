@@ -262,6 +262,18 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   reinterpret_cast<uint4*>(act + t * F)[v] = pack8(g);
 }
 
+// W [2F, d] = [gate rows | up rows]  ->  out [2F, d] with rows in blocks of 128: gate block t, up block t, gate block t+1, ...
+__global__ void interleave_gate_up_kernel(const bf16* __restrict__ W, bf16* __restrict__ out, int F, int d) {
+  const int dv = d >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(2) * F * dv) return;
+  const int64_t r = idx / dv;              // destination row
+  const int v = static_cast<int>(idx % dv);
+  const int blk = static_cast<int>(r / 256), within = static_cast<int>(r % 256);
+  const int64_t src = within < 128 ? static_cast<int64_t>(blk) * 128 + within : static_cast<int64_t>(F) + blk * 128 + (within - 128);
+  reinterpret_cast<uint4*>(out + r * d)[v] = reinterpret_cast<const uint4*>(W + src * d)[v];
+}
+
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
                                   int64_t T, int F) {
   const int fv = F >> 3;
@@ -1142,6 +1154,11 @@ int swiglu_fwd(const bf16* gu, bf16* act, int64_t T, int F, cudaStream_t s) {
   if (F % 8 != 0) return -1;
   swiglu_fwd_kernel<<<blocks_for(T * (F >> 3), 256), 256, 0, s>>>(gu, act, T, F);
   return check_launch("swiglu_fwd");
+}
+int interleave_gate_up(const bf16* W, bf16* out, int F, int d, cudaStream_t s) {
+  if (F % 128 != 0 || d % 8 != 0) return -1;
+  interleave_gate_up_kernel<<<blocks_for(static_cast<int64_t>(2) * F * (d >> 3), 256), 256, 0, s>>>(W, out, F, d);
+  return check_launch("interleave_gate_up");
 }
 int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t T, int F, cudaStream_t s) {
   if (F % 8 != 0) return -1;

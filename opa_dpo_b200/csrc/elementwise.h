@@ -29,6 +29,8 @@ int rope_table(float2* cs, int max_pos, int hd, float theta, cudaStream_t s);
 
 // act = silu(gu[:, :F]) * gu[:, F:]  ;  backward: dgu from dact and gu
 int swiglu_fwd(const bf16* gu, bf16* act, int64_t T, int F, cudaStream_t s);
+// gate|up weight [2F, d] -> rows interleaved in blocks of 128 (gate block, up block, ...) for the fused SwiGLU epilogue
+int interleave_gate_up(const bf16* W, bf16* out, int F, int d, cudaStream_t s);
 int swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int64_t T, int F, cudaStream_t s);
 // exact (erf) GELU, forward and backward (projector, llava_modifications.patch:15354-15367)
 int gelu_fwd(const bf16* x, bf16* y, int64_t n, cudaStream_t s);

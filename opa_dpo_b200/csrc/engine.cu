@@ -725,8 +725,21 @@ int Engine::llama_layer_fwd(const LlamaLayer& L, int adapter, const SeqLayout& l
   EN_CHECK(attn_fwd_checked(at, s));
   EN_CHECK(linear_fwd(L.o, adapter, a.o, d, T, a.to, a.x1, d, ACT_NONE, a.x, d, s));
   EN_CHECK(rmsnorm_fwd(a.x1, L.ln2, a.h2, T, d, c.rms_eps, nullptr, s));
-  EN_CHECK(linear_fwd(L.gu, adapter, a.h2, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
-  EN_CHECK(swiglu_fwd(a.gu, a.act, T, F, s));
+  if (adapter < 0 && L.gu.W_il) {  // merged frozen adapter: SwiGLU inside the projection's epilogue, `gu` never materialised
+    GemmArgs g;
+    g.M = static_cast<int>(T);
+    g.N = 2 * F;
+    g.K1 = d;
+    g.A1 = {a.h2, d};
+    g.B1 = {L.gu.W_il, d};
+    g.epilogue = EPI_SWIGLU_BF16;
+    g.C = a.act;
+    g.ldc = F;
+    EN_CHECK(gemm_checked(g, s));
+  } else {
+    EN_CHECK(linear_fwd(L.gu, adapter, a.h2, d, T, a.tgu, a.gu, 2 * F, ACT_NONE, nullptr, 0, s));
+    EN_CHECK(swiglu_fwd(a.gu, a.act, T, F, s));
+  }
   EN_CHECK(linear_fwd(L.down, adapter, a.act, F, T, a.td, x_out, d, ACT_NONE, a.x1, d, s));
   return 0;
 }
@@ -1106,6 +1119,16 @@ int Engine::ensure_frozen_merged(int adapter, cudaStream_t s) {
   if (frozen_merged_adapter == adapter) return 0;
   drop_frozen_merged();
   int rc = merge_lora(adapter, &frozen_merged, &frozen_merged_allocs, s);
+  if (rc == 0 && fuse_swiglu && cfg.d_ffn % 128 == 0) {
+    for (auto& L : frozen_merged) {
+      if (L.gu.slot >= 0 || L.gu.bias) continue;  // only projections that really were merged
+      bf16* il = nullptr;
+      rc = pool_alloc(&il, static_cast<int64_t>(L.gu.out) * L.gu.in, s, &frozen_merged_allocs);
+      if (rc == 0) rc = interleave_gate_up(L.gu.W, il, cfg.d_ffn, L.gu.in, s) == 0 ? 0 : OPADPO_ECUDA;
+      if (rc != 0) break;
+      L.gu.W_il = il;
+    }
+  }
   if (rc != 0) {
     drop_frozen_merged();
     return rc;
@@ -1118,6 +1141,11 @@ int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "merge_frozen") == 0) {
     merge_frozen = value != 0;
     if (!merge_frozen) drop_frozen_merged();
+    return 0;
+  }
+  if (strcmp(name, "fuse_swiglu") == 0) {
+    if (fuse_swiglu != (value != 0)) drop_frozen_merged();  // the merged copy is built with or without the interleaved weight
+    fuse_swiglu = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_rope") == 0) {

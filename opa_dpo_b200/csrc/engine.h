@@ -22,6 +22,7 @@ namespace opadpo {
 struct LinearW {
   int in = 0, out = 0, groups = 1;
   bf16* W = nullptr;     // [out, in] (groups stacked along out)
+  bf16* W_il = nullptr;  // gate|up only, merged frozen adapter + fuse_swiglu: the same rows interleaved in blocks of 128
   bf16* bias = nullptr;  // [out] or null
   int slot = -1;         // LoRA slot index, -1 = not a LoRA target
 };
@@ -125,6 +126,9 @@ class Engine {
   bool merge_frozen = false;
   // q|k|v projection with RoPE applied in the GEMM epilogue (EPI_BF16_ROPE) instead of a separate in-place pass
   bool fuse_rope = false;
+  // merged frozen adapter only: gate|up projection with SwiGLU in the GEMM epilogue (EPI_SWIGLU_BF16) over an interleaved
+  // copy of the merged weight; bit-identical to projection + swiglu_fwd
+  bool fuse_swiglu = false;
   int frozen_merged_adapter = -1;
   std::vector<LlamaLayer> frozen_merged;
   std::vector<void*> frozen_merged_allocs;

@@ -361,6 +361,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
           __syncwarp();
         }
+      } else if constexpr (EPI == EPI_SWIGLU_BF16) {
+        // gate|up projection with SwiGLU in the epilogue: the weight rows are interleaved so that a 256-column tile holds
+        // 128 gate columns followed by their 128 up columns; the result has N/2 columns. The roundings of the unfused path
+        // (gate and up stored as bf16, silu rounded to bf16 before the product: swiglu_fwd_kernel) are reproduced, so the
+        // output is bit-identical to projection + swiglu_fwd on the non-interleaved weight.
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + (n0 >> 1);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t gt[32], up[32];
+          ptx::tmem_ld32(taddr + c * 32, gt);
+          ptx::tmem_ld32(taddr + 128 + c * 32, up);
+          ptx::tmem_ld_wait();
+          if (row_ok && n0 < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float gg = __bfloat162float(__float2bfloat16(__uint_as_float(gt[j]) * p.alpha));
+              const float uu = __bfloat162float(__float2bfloat16(__uint_as_float(up[j]) * p.alpha));
+              v[j] = __bfloat162float(__float2bfloat16(gg / (1.f + __expf(-gg)))) * uu;
+            }
+            uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = u;
+            }
+          }
+          __syncwarp();
+        }
       } else if constexpr (EPI == EPI_BF16_ROPE) {
         // q|k|v projection with the rotary embedding applied to the fp32 accumulator (one bf16 rounding instead of two and
         // no separate pass over q and k): heads are 128 columns, HF's rotate_half pairs column j with j + 64, the table
@@ -711,7 +744,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: EPI_BF16_ROPE needs N and rope_cols multiples of 128, a table, positions or rope_S, and no bias / act / residual");
     return -8;
   }
-  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD || a.epilogue == EPI_BF16_ROPE) &&
+  if (a.epilogue == EPI_SWIGLU_BF16 && (a.N % 256 != 0 || a.bias || a.residual || a.act != ACT_NONE || a.splits > 1)) {
+    snprintf(g_err, sizeof(g_err), "gemm: EPI_SWIGLU_BF16 needs N %% 256 == 0 (gate / up rows interleaved in blocks of 128) and no bias / act / residual");
+    return -9;
+  }
+  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD || a.epilogue == EPI_BF16_ROPE || a.epilogue == EPI_SWIGLU_BF16) &&
       (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
     snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
     return -5;
@@ -826,6 +863,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_CEGRAD: return launch_impl<AMN, BMN, EPI_CEGRAD, CL>(maps, kp, grid, stream);        \
     case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL, CL>(maps, kp, grid, stream); \
     case EPI_BF16_ROPE: return launch_impl<AMN, BMN, EPI_BF16_ROPE, CL>(maps, kp, grid, stream);   \
+    case EPI_SWIGLU_BF16: return launch_impl<AMN, BMN, EPI_SWIGLU_BF16, CL>(maps, kp, grid, stream); \
     default: break;                                                                               \
   }
 #define OPADPO_DISPATCH(AMN, BMN)          \

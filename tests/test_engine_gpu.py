@@ -832,3 +832,34 @@ def test_fused_rope_epilogue_option_vs_oracle(share):
     ids = eng.generate(POLICY, images, q, qm, 4)          # the rollout prefill goes through the same projection
     assert ids.shape == (3, 20)
     eng.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1)")
+def test_fused_swiglu_on_merged_reference_pass_is_bit_identical():
+    """Option fuse_swiglu (with merge_frozen): the merged reference adapter's gate|up projection runs SwiGLU in its epilogue
+    over the interleaved merged weight. The roundings of the unfused path are reproduced, so the reference log-probs are
+    bit-identical with the option on and off; the rollout (which reads the non-interleaved copy) is unaffected."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, REF
+    oc, ec = _cfgs(d_ffn=512)
+    eng, w, lp, lr = _build(oc, ec, trainable=True)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    eng.set_option("merge_frozen", 1)
+    a_lp, a_ent = eng.forward_logprobs(REF, *args)
+    ids_a = eng.generate(REF, images, q, qm, 6)
+    eng.set_option("fuse_swiglu", 1)
+    b_lp, b_ent = eng.forward_logprobs(REF, *args)
+    ids_b = eng.generate(REF, images, q, qm, 6)
+    torch.cuda.synchronize()
+    assert torch.equal(a_lp, b_lp) and torch.equal(a_ent, b_ent) and torch.equal(ids_a, ids_b)
+    ref_o = O.policy_forward(oc, w, lr, images, q, qm, resp)
+    for i, n in enumerate(NAMES2):
+        _cmp_lp(b_lp[i], ref_o[n + "_logprobs"], f"fused swiglu ref {n}")
+    pol_a, _ = eng.forward_logprobs(POLICY, *args)            # the trainable adapter never takes the merged path
+    eng.set_option("fuse_swiglu", 0)
+    pol_b, _ = eng.forward_logprobs(POLICY, *args)
+    assert torch.equal(pol_a, pol_b)
+    eng.close()

@@ -247,3 +247,27 @@ def test_gemm_rope_epilogue(cluster, with_pos):
     rot = torch.cat([lo * c[:, None, :] - hi * s[:, None, :], hi * c[:, None, :] + lo * s[:, None, :]], -1).reshape(M, 2 * d)
     _close(out[:, :2 * d], rot, what="rope q|k")
     _close(out[:, 2 * d:], ref[:, 2 * d:], what="v untouched")
+
+
+@_UNVERIFIED
+@pytest.mark.parametrize("cluster", [0, 2])
+def test_gemm_swiglu_epilogue_bit_identical_to_unfused(cluster):
+    """EPI_SWIGLU_BF16 over a weight whose gate / up rows are interleaved in blocks of 128 == plain projection followed by
+    SwiGLU with the unfused path's roundings (gate, up -> bf16; silu -> bf16; product -> bf16), bit for bit."""
+    from opa_dpo_b200 import ops
+    M, F, K = 1100, 384, 320
+    x, W = _mk((M, K), 41), _mk((2 * F, K), 42, 0.3)
+    Wil = torch.empty_like(W)
+    for t in range(F // 128):
+        Wil[t * 256:t * 256 + 128] = W[t * 128:(t + 1) * 128]
+        Wil[t * 256 + 128:(t + 1) * 256] = W[F + t * 128:F + (t + 1) * 128]
+    gu = torch.empty((M, 2 * F), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, W, gu, cluster=cluster)
+    act = torch.full((M, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, Wil.contiguous(), act, epilogue=ops.EPI_SWIGLU_BF16, N=2 * F, cluster=cluster)
+    torch.cuda.synchronize()
+    g, u = gu[:, :F].float(), gu[:, F:].float()
+    want = ((g / (1.0 + torch.exp(-g))).to(torch.bfloat16).float() * u).to(torch.bfloat16)
+    diff = (act.float() - want.float()).abs()
+    # __expf vs torch.exp differ in the last bits of the exponential: allow one bf16 ulp on a few elements, none larger
+    assert (diff > 0).float().mean().item() < 2e-3 and diff.max().item() <= 2.0 ** -7 * want.float().abs().max().item()
