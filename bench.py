@@ -171,10 +171,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--merge-frozen", type=int, default=int(os.environ.get("OPADPO_MERGE_FROZEN", str(MERGE_FROZEN_DEFAULT))),
                     help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
-    ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "0")),
-                    help="1: SwiGLU in the gate|up GEMM epilogue of the merged reference pass (opt-in until validated on a GPU)")
-    ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "0")),
-                    help="1: RoPE in the q|k|v GEMM epilogue (opt-in until validated on a GPU)")
+    ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "1")),
+                    help="1: SwiGLU in the gate|up GEMM epilogue of the merged reference pass")
+    ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "1")),
+                    help="1: RoPE in the q|k|v GEMM epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -208,10 +208,8 @@ def main():
     if args.no_share_prefix:
         model.engine.set_option("share_prefix", 0)
     model.engine.set_option("merge_frozen", args.merge_frozen)
-    if args.fuse_rope:
-        model.engine.set_option("fuse_rope", 1)
-    if args.fuse_swiglu:
-        model.engine.set_option("fuse_swiglu", 1)
+    model.engine.set_option("fuse_rope", int(bool(args.fuse_rope)))
+    model.engine.set_option("fuse_swiglu", int(bool(args.fuse_swiglu)))
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
     dargs = DPOArgs(beta=0.1, response_len=R, learning_rate=1e-6, max_grad_norm=1.0)

@@ -125,10 +125,10 @@ class Engine {
   // The cache is rebuilt when that adapter's tensors are reloaded. Costs one extra copy of the decoder weights.
   bool merge_frozen = false;
   // q|k|v projection with RoPE applied in the GEMM epilogue (EPI_BF16_ROPE) instead of a separate in-place pass
-  bool fuse_rope = false;
+  bool fuse_rope = true;
   // merged frozen adapter only: gate|up projection with SwiGLU in the GEMM epilogue (EPI_SWIGLU_BF16) over an interleaved
   // copy of the merged weight; bit-identical to projection + swiglu_fwd
-  bool fuse_swiglu = false;
+  bool fuse_swiglu = true;
   int frozen_merged_adapter = -1;
   std::vector<LlamaLayer> frozen_merged;
   std::vector<void*> frozen_merged_allocs;

@@ -99,10 +99,12 @@ class OPAArgs:
     entropy_mask_method: str = "random"   # random | blockwise (masked images) | attention (holes in the image mask)
     entropy_mask_ratio: float = 0.3
     temperature: float = 1.0
-    # "label": entropies of the distributions that predict the labelled tokens (the engine's native output).
-    # "reference": the reference's positions, one later (see the module docstring) — the forward runs over responses
-    # extended by one slot, with a placeholder token behind each row's last token so that slot's entropy is emitted.
-    entropy_alignment: str = "label"
+    # "reference" (default): the reference's positions (opa_trainer.py:82-85), one later than the labels (see the module
+    # docstring) — the forward runs over responses extended by one slot, with a placeholder token behind each row's last
+    # token so that slot's entropy is emitted.
+    # "label": entropies of the distributions that predict the labelled tokens (the engine's native output; one slot
+    # cheaper, not what the reference computes).
+    entropy_alignment: str = "reference"
 
 
 class OPAStepper:
@@ -137,7 +139,8 @@ class OPAStepper:
             pargs.response_len = R
         res = {}
         for name, ids in responses.items():
-            valid = (ids != self.pad).to(out[name + "_entropies"].dtype)
+            ent = out[name + "_entropies"]
+            valid = (ids != self.pad).to(device=ent.device, dtype=ent.dtype)
             res[name + "_logprobs"] = out[name + "_logprobs"][:, :-1] * valid
             res[name + "_entropies"] = out[name + "_entropies"][:, 1:] * valid
         return res

@@ -529,7 +529,8 @@ def test_opa_entropy_regulariser_loss_and_grads_vs_oracle():
     ent_ref = (-((hm_ref - h_ref) * valid).sum(-1) / valid.sum(-1)).mean()
     loss_ref = sft_ref + coef * ent_ref
     loss_ref.backward()
-    stepper = OPAStepper(policy, None, args=OPAArgs(entropy_loss=True, entropy_loss_coef=coef, entropy_decay_coef=1.0))
+    stepper = OPAStepper(policy, None, args=OPAArgs(entropy_loss=True, entropy_loss_coef=coef, entropy_decay_coef=1.0,
+                                                    entropy_alignment="label"))
     model.engine.zero_grad()
     loss, logs = stepper.compute_loss(images, q, qm, resp, masked_images=masked)
     assert abs(logs["entropy_loss"].item() - ent_ref.item()) <= 0.02, (logs["entropy_loss"].item(), ent_ref.item())
@@ -714,9 +715,6 @@ def test_online_generator_mirror_greedy_responses_vs_oracle():
     model.engine.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1); "
-                           "the mode's logic is pinned on the CPU against the reference in tests/test_opa_host_cpu.py")
 def test_opa_entropy_regulariser_reference_alignment_vs_oracle():
     """OPAArgs.entropy_alignment="reference": the regulariser reads the entropy at the position of each labelled token
     (opa_trainer.py:63,82-84), one later than the cross-entropy. Loss vs the oracle's logits at those positions."""
@@ -769,9 +767,6 @@ def test_opa_entropy_regulariser_reference_alignment_vs_oracle():
     model.engine.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1); "
-                           "the oracle side is pinned to transformers' generate() in tests/test_oracle_golden.py")
 @pytest.mark.parametrize("eos", [298, 215, 159])
 def test_greedy_rollout_early_eos_ids_exact(eos):
     """Rows that finish early at different steps: the EOS id is moved onto tokens the greedy path really emits; finished rows
@@ -790,8 +785,6 @@ def test_greedy_rollout_early_eos_ids_exact(eos):
     eng.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1)")
 @pytest.mark.parametrize("share", [0, 1])
 def test_fused_rope_epilogue_option_vs_oracle(share):
     """Option fuse_rope: RoPE applied in the q|k|v GEMM epilogue instead of a separate pass. Same tolerances vs the oracle as
@@ -804,6 +797,7 @@ def test_fused_rope_epilogue_option_vs_oracle(share):
     images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
     dev = eng.device
     args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    eng.set_option("fuse_rope", 0)
     base_lp, _ = eng.forward_logprobs(POLICY, *args)
     eng.set_option("fuse_rope", 1)
     lc = O.LossConfig(beta=0.1)
@@ -834,8 +828,6 @@ def test_fused_rope_epilogue_option_vs_oracle(share):
     eng.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a GPU (set OPADPO_RUN_UNVERIFIED=1)")
 def test_fused_swiglu_on_merged_reference_pass_is_bit_identical():
     """Option fuse_swiglu (with merge_frozen): the merged reference adapter's gate|up projection runs SwiGLU in its epilogue
     over the interleaved merged weight. The roundings of the unfused path are reproduced, so the reference log-probs are
@@ -848,6 +840,7 @@ def test_fused_swiglu_on_merged_reference_pass_is_bit_identical():
     dev = eng.device
     args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
     eng.set_option("merge_frozen", 1)
+    eng.set_option("fuse_swiglu", 0)
     a_lp, a_ent = eng.forward_logprobs(REF, *args)
     ids_a = eng.generate(REF, images, q, qm, 6)
     eng.set_option("fuse_swiglu", 1)

@@ -213,12 +213,6 @@ def test_gemm_cluster_lora_groups_bias_residual_and_mn_major(mode):
     _close(acc2, a.float().t() @ b.float(), what="cluster wgrad")
 
 
-_UNVERIFIED = pytest.mark.skipif(__import__("os").environ.get("OPADPO_RUN_UNVERIFIED") != "1",
-                                 reason="written after the round's GPU budget was spent: not yet run on a GPU "
-                                        "(set OPADPO_RUN_UNVERIFIED=1)")
-
-
-@_UNVERIFIED
 @pytest.mark.parametrize("cluster", [0, 2])
 @pytest.mark.parametrize("with_pos", [True, False])
 def test_gemm_rope_epilogue(cluster, with_pos):
@@ -249,7 +243,6 @@ def test_gemm_rope_epilogue(cluster, with_pos):
     _close(out[:, 2 * d:], ref[:, 2 * d:], what="v untouched")
 
 
-@_UNVERIFIED
 @pytest.mark.parametrize("cluster", [0, 2])
 def test_gemm_swiglu_epilogue_bit_identical_to_unfused(cluster):
     """EPI_SWIGLU_BF16 over a weight whose gate / up rows are interleaved in blocks of 128 == plain projection followed by

@@ -92,7 +92,8 @@ def test_opa_compute_loss_vs_reference_llava_trainer(entropy):
         def __call__(self, images, queries, queries_attn_masks, temperature=None, **kw):
             calls.append(images)
             return policy_like(images, 0)
-    stepper = OPAStepper(Policy(), None, args=OPAArgs(entropy_loss=entropy, entropy_loss_coef=0.2, entropy_decay_coef=0.9))
+    stepper = OPAStepper(Policy(), None, args=OPAArgs(entropy_loss=entropy, entropy_loss_coef=0.2, entropy_decay_coef=0.9,
+                                                      entropy_alignment="label"))
     loss, logs = stepper.compute_loss(images, queries, queries != 0, responses, masked_images=masked)
     sft_only = F.cross_entropy(logits_of(images)[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1), ignore_index=-100)
     assert abs(logs["base_sft_loss"].item() - sft_only.item()) <= 1e-6 * abs(sft_only.item())
@@ -122,8 +123,8 @@ def test_opa_compute_loss_vs_reference_llava_trainer(entropy):
             ent = -(ls.exp() * ls).sum(-1)[:, Q - 1:Q - 1 + Rx] * valid
             return {name + "_logprobs": lp, name + "_entropies": ent}
     pol = EnginePolicy()
-    st2 = OPAStepper(pol, None, args=OPAArgs(entropy_loss=entropy, entropy_loss_coef=0.2, entropy_decay_coef=0.9,
-                                             entropy_alignment="reference"))
+    assert OPAArgs().entropy_alignment == "reference"       # the reference's positions are the default
+    st2 = OPAStepper(pol, None, args=OPAArgs(entropy_loss=entropy, entropy_loss_coef=0.2, entropy_decay_coef=0.9))
     loss2, _ = st2.compute_loss(images, queries, queries != 0, responses, masked_images=masked)
     assert pol.args.response_len == R
     assert abs(loss2.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item()), (loss2.item(), loss_ref.item())
