@@ -25,6 +25,7 @@ extern "C" {
 #define OPADPO_ECUDA (-2)
 #define OPADPO_ENOMEM (-3)
 #define OPADPO_ESTATE (-4)
+#define OPADPO_ENOENT (-5) /* a tensor / module name this engine does not hold (distinct from a shape error on one it does) */
 
 /* Message of the last failing call on this thread. */
 const char* opadpo_last_error(void);
@@ -277,14 +278,19 @@ int opadpo_optimizer_step(opadpo_engine* e, float lr, float beta1, float beta2, 
 /* Rollout (model.generate of online_generator.py:292-309 / rl_models.py:166-188): writes out_ids int64
  * [b, Q + max_new] = queries | generated (pad after EOS). adapter = -1 runs the bare base model.
  * sampler = NULL or do_sample = 0: greedy (ids reproduce the reference exactly). do_sample = 1: HF warper order
- * temperature -> top_k -> top_p -> multinomial with a counter-based RNG keyed by (seed, sequence, step); supported:
- * top_k in [1,64] with any top_p, or top_k = 0 with top_p = 1. */
+ * temperature -> top_k -> top_p -> multinomial with a counter-based RNG keyed by (seed, sequence, step); any top_k >= 0
+ * (0 = off; ties with the k-th largest survive, TopKLogitsWarper) and any top_p in (0, 1] (TopPLogitsWarper).
+ * suppress_tokens[0..n_suppress): HF suppress_tokens (logit := -inf before argmax / the warpers), what
+ * online_generator.py:298-302 and rl_models.py:173-177 pass as [eos] under suppress_eos_at_generation; greedy too. */
+#define OPADPO_MAX_SUPPRESS 8
 typedef struct opadpo_sampler {
   int32_t do_sample;
   int32_t top_k;
   float top_p;
   float temperature;
   uint64_t seed;
+  int32_t n_suppress;
+  int32_t suppress_tokens[OPADPO_MAX_SUPPRESS];
 } opadpo_sampler;
 int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
                     const uint8_t* qmask, int32_t Q, int32_t max_new, const opadpo_sampler* sampler, int64_t* out_ids,

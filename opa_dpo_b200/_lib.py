@@ -13,11 +13,31 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libopadpo_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
+HASH_PATH = LIB_PATH + ".srchash"
+EXPECTED_ABI = 5     # opadpo_abi_version() of the library these bindings were written against
+
 _lib = None
+
+
+def source_hash() -> str:
+    """sha256 over every file the library is compiled from (csrc/* and the public header)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if not f.startswith("."))
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "opadpo_b200.h"))
+    for p in files:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 class OpadpoError(RuntimeError):
     pass
+
+
+class OpadpoUnknownName(OpadpoError):
+    """OPADPO_ENOENT: the engine holds no tensor / module of that name (as opposed to a shape or dtype error on one it does)."""
 
 
 def build_library(verbose: bool = False) -> str:
@@ -28,6 +48,8 @@ def build_library(verbose: bool = False) -> str:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise OpadpoError("building libopadpo_b200.so failed (see output above)")
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 
@@ -102,7 +124,8 @@ class Segments(ctypes.Structure):
 
 class Sampler(ctypes.Structure):
     _fields_ = [("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("top_p", ctypes.c_float),
-                ("temperature", ctypes.c_float), ("seed", ctypes.c_uint64)]
+                ("temperature", ctypes.c_float), ("seed", ctypes.c_uint64), ("n_suppress", ctypes.c_int32),
+                ("suppress_tokens", ctypes.c_int32 * 8)]
 
 
 class Config(ctypes.Structure):
@@ -200,13 +223,37 @@ def load(build_if_missing: bool = False):
             raise OpadpoError(
                 f"{LIB_PATH} is missing: the CUDA extension is the only implementation of the hot path "
                 "(run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    _check_fresh()
     lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    lib.opadpo_abi_version.restype = ctypes.c_int
+    got = lib.opadpo_abi_version()
+    if got != EXPECTED_ABI:
+        raise OpadpoError(f"{LIB_PATH} exports ABI version {got}, these bindings expect {EXPECTED_ABI}: rebuild it "
+                          "(`python -c 'import __graft_entry__ as g; g.build()'`)")
     _declare(lib)
     _lib = lib
     return lib
 
 
+def _check_fresh():
+    """A library built from other sources than the ones beside it would be loaded silently and run stale kernels under new
+    struct layouts: refuse. Compared by content hash (build_library records it), so copies and checkouts that reset
+    mtimes do not matter. OPADPO_ALLOW_STALE_LIB=1 overrides."""
+    try:
+        with open(HASH_PATH) as f:
+            built = f.read().strip()
+    except OSError:
+        built = None
+    if built != source_hash() and os.environ.get("OPADPO_ALLOW_STALE_LIB") != "1":
+        raise OpadpoError(f"{LIB_PATH} was not built from the sources in {CSRC_DIR} (source hash mismatch): rebuild it "
+                          "(`python -c 'import __graft_entry__ as g; g.build()'`), or set OPADPO_ALLOW_STALE_LIB=1")
+
+
+ENOENT = -5     # OPADPO_ENOENT
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().opadpo_last_error()
-        raise OpadpoError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+        cls = OpadpoUnknownName if rc == ENOENT else OpadpoError
+        raise cls(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Callable, Dict, Iterator, List, Optional, Tuple
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Tuple
 
 import torch
 
@@ -115,19 +115,25 @@ def engine_config_from_hf(base_dir: str, clip_dir: Optional[str] = None, lora_r:
     return EngineConfig(**kw)
 
 
-def load_llava_base(sink, base_dir: str, clip_dir: Optional[str] = None, log: Optional[Callable[[str], None]] = None) -> Dict[str, int]:
+def load_llava_base(sink, base_dir: str, clip_dir: Optional[str] = None, log: Optional[Callable[[str], None]] = None,
+                    required: Optional[Iterable[str]] = None) -> Dict[str, int]:
     """Stream a LLaVA-1.5 base checkpoint into `sink.load_tensor(name, tensor)`: first the CLIP tower from its own directory,
     then every tensor of the LLaVA shards (its vision_tower / mm_projector entries overriding the tower's, as
-    loading_vision_tower_parameter does). Names the engine does not execute (rotary inv_freq buffers, the CLIP layers behind
-    the selected one, post_layernorm, a text tower) are counted as skipped. Returns {"loaded", "skipped"}."""
-    from ._lib import OpadpoError
+    loading_vision_tower_parameter does). Only names the engine does not hold (OPADPO_ENOENT: a text tower, buffers it has
+    no use for) are counted as skipped; a shape or dtype mismatch on a tensor it does hold — a resized vocabulary, another
+    hidden size or patch size — raises, as from_pretrained does. Afterwards every name in `required` (default: the sink's
+    `required_tensor_names()`, i.e. everything the engine executes) must have been loaded, or the missing list is raised.
+    Returns {"loaded", "skipped"}."""
+    from ._lib import OpadpoError, OpadpoUnknownName
     stats = {"loaded": 0, "skipped": 0}
+    seen = set()
 
     def put(name: str, t: torch.Tensor):
         try:
             sink.load_tensor(name, t)
             stats["loaded"] += 1
-        except OpadpoError:
+            seen.add(name)
+        except OpadpoUnknownName:
             stats["skipped"] += 1
             if log:
                 log(f"skipped {name} {tuple(t.shape)}")
@@ -138,4 +144,10 @@ def load_llava_base(sink, base_dir: str, clip_dir: Optional[str] = None, log: Op
             put("model.vision_tower.vision_tower." + name, t)
     for name, t in iter_checkpoint_tensors(base_dir):
         put(name, t)
+    if required is None and hasattr(sink, "required_tensor_names"):
+        required = sink.required_tensor_names()
+    missing = [n for n in (required or []) if n not in seen]
+    if missing:
+        raise OpadpoError(f"base checkpoint {base_dir} does not provide {len(missing)} tensors the engine executes: "
+                          + ", ".join(missing[:8]) + (" ..." if len(missing) > 8 else ""))
     return stats

@@ -11,6 +11,7 @@
 #define OPADPO_ECUDA (-2)
 #define OPADPO_ENOMEM (-3)
 #define OPADPO_ESTATE (-4)
+#define OPADPO_ENOENT (-5)
 #endif
 
 namespace opadpo {

@@ -873,17 +873,32 @@ __global__ void __launch_bounds__(256) decode_attention_kernel(const bf16* __res
   }
 }
 
+// HF SuppressTokensLogitsProcessor [UPSTREAM; online_generator.py:298-302, rl_models.py:173-177 pass
+// suppress_tokens=[eos] under suppress_eos_at_generation]: the listed ids get logit -inf before anything else looks at them.
+struct SuppressList {
+  int n;
+  int ids[OPADPO_MAX_SUPPRESS];
+};
+__device__ __forceinline__ bool suppressed(const SuppressList& sl, int c) {
+  bool hit = false;
+#pragma unroll
+  for (int i = 0; i < OPADPO_MAX_SUPPRESS; ++i) hit |= (i < sl.n && sl.ids[i] == c);
+  return hit;
+}
+
 // Greedy pick over split-K partial logits [splits, N, V] (summed in fixed order). Writes the id at column *cur.
 __global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ part, int splits, int64_t slice, int V,
-                                                           int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
-                                                           int64_t* out, int64_t out_ld, const int32_t* __restrict__ cur) {
+                                                           int eos_id, int pad_id, SuppressList sup, uint8_t* done,
+                                                           int32_t* next_ids, int64_t* out, int64_t out_ld,
+                                                           const int32_t* __restrict__ cur) {
   __shared__ float bv[32];
   __shared__ int bi[32];
   const int n = blockIdx.x;
   float best = -INFINITY;
   int besti = V;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float x = sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + i);
+    float x = sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + i);
+    if (suppressed(sup, i)) x = -INFINITY;
     if (x > best || (x == best && i < besti)) {
       best = x;
       besti = i;
@@ -936,164 +951,173 @@ __device__ __forceinline__ float uniform01(uint64_t seed, uint32_t row, uint32_t
   return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
 }
 
-// HF sampling warpers [UPSTREAM GenerationMixin.sample as driven by online_generator.py:292-309]: temperature, then
-// top-k (keep the k largest logits), then top-p (keep the smallest high-probability set whose preceding cumulative
-// mass is < top_p, at least one token), then multinomial over the survivors. One CTA per sequence; each thread owns a
-// strided slice of the vocabulary in registers; the k winners come out in descending order from k block-argmax rounds.
+// Order-preserving map float -> u32 (larger float <=> larger key; -inf is the smallest non-NaN key).
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// HF sampling [UPSTREAM GenerationMixin.sample as driven by online_generator.py:292-309 / rl_models.py:166-188]:
+// suppress_tokens, then the warpers in HF's order — temperature; top-k (TopKLogitsWarper: drop every score below the
+// k-th largest, ties with it survive); top-p (TopPLogitsWarper: over the softmax of what is left, ascending cumulative
+// mass <= 1 - top_p is dropped, the largest token always survives) — then a multinomial over the survivors. Any
+// top_k (0 = off) and any top_p in (0, 1]. One CTA per sequence; each thread owns a strided slice of the vocabulary in
+// registers. Both thresholds come from an MSB-first radix select over the order-preserving keys (4 passes of 8 bits
+// through a 256-bin shared-memory histogram): counts for top-k, 2^-32 fixed-point masses for top-p (integer adds, so the
+// threshold does not depend on the order the atomics land in).
 constexpr int SAMPLE_THREADS = 1024;
 constexpr int SAMPLE_MAX_PER_THREAD = 40;  // vocab <= 40960
-constexpr int SAMPLE_MAX_K = 64;
 __global__ void __launch_bounds__(SAMPLE_THREADS)
     sample_pick_kernel(const float* __restrict__ part, int splits, int64_t slice, int V, int top_k, float top_p,
-                       float inv_temp, uint64_t seed, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out,
-                       int64_t out_ld, const int32_t* __restrict__ cur) {
+                       float inv_temp, uint64_t seed, int eos_id, int pad_id, SuppressList sup, uint8_t* done,
+                       int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* __restrict__ cur) {
   __shared__ float bv[32];
   __shared__ int bi[32];
-  __shared__ float topv[SAMPLE_MAX_K];
-  __shared__ int topi[SAMPLE_MAX_K];
   __shared__ float red[32];
+  __shared__ unsigned long long hist[256];
+  __shared__ uint32_t sel_prefix;
+  __shared__ unsigned long long sel_rest;
+  __shared__ float tsum[SAMPLE_THREADS];
+  __shared__ int pick_s;
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float v[SAMPLE_MAX_PER_THREAD];
 #pragma unroll
   for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
     const int c = threadIdx.x + i * SAMPLE_THREADS;
-    v[i] = c < V ? sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + c) * inv_temp : -INFINITY;
+    v[i] = (c < V && !suppressed(sup, c)) ? sum_partials(part, splits, slice, static_cast<int64_t>(n) * V + c) * inv_temp
+                                           : -INFINITY;
   }
-  int chosen = 0;
-  if (top_k > 0) {
-    for (int round = 0; round < top_k; ++round) {
-      float best = -INFINITY;
-      int besti = V;
+  // MSB-first radix select. DESC = true: the key of the `target`-th largest element by count (top-k). DESC = false: the
+  // smallest key whose ascending cumulative weight exceeds `target` (top-p); weights come from `wt(i)`.
+  auto radix_select = [&](bool desc, unsigned long long target, auto wt) -> uint32_t {
+    uint32_t prefix = 0, pmask = 0;
+    unsigned long long rest = target;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int b = threadIdx.x; b < 256; b += SAMPLE_THREADS) hist[b] = 0ull;
+      __syncthreads();
 #pragma unroll
       for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
         const int c = threadIdx.x + i * SAMPLE_THREADS;
-        if (v[i] > best || (v[i] == best && c < besti)) {
-          best = v[i];
-          besti = c;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ob > best || (ob == best && oi < besti)) {
-          best = ob;
-          besti = oi;
-        }
-      }
-      __syncthreads();
-      if (lane == 0) {
-        bv[warp] = best;
-        bi[warp] = besti;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        best = bv[lane];
-        besti = bi[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-          if (ob > best || (ob == best && oi < besti)) {
-            best = ob;
-            besti = oi;
+        if (c < V) {
+          const uint32_t k = float_key(v[i]);
+          if ((k & pmask) == prefix) {
+            const unsigned long long wgt = wt(i);
+            if (wgt) atomicAdd(&hist[(k >> shift) & 255u], wgt);
           }
         }
-        if (lane == 0) {
-          topv[round] = best;
-          topi[round] = besti;
-        }
       }
       __syncthreads();
-      const int win = topi[round];
-      if (win < V && (win % SAMPLE_THREADS) == threadIdx.x) {
-#pragma unroll
-        for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i)
-          if (i == win / SAMPLE_THREADS) v[i] = -INFINITY;
-      }
-    }
-    if (threadIdx.x == 0) {
-      const float mx = topv[0];
-      float tot = 0.f;
-      for (int i = 0; i < top_k; ++i) tot += __expf(topv[i] - mx);
-      // nucleus: token i survives while the mass BEFORE it is < top_p
-      int keep = 0;
-      float before = 0.f, kept = 0.f;
-      for (int i = 0; i < top_k; ++i) {
-        const float p = __expf(topv[i] - mx) / tot;
-        if (i > 0 && before >= top_p) break;
-        kept += p;
-        before += p;
-        ++keep;
-      }
-      const float u = uniform01(seed, n, static_cast<uint32_t>(*cur)) * kept;
-      float acc = 0.f;
-      int pick = keep - 1;
-      for (int i = 0; i < keep; ++i) {
-        acc += __expf(topv[i] - mx) / tot;
-        if (u < acc) {
-          pick = i;
-          break;
+      if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        int digit = desc ? 0 : 255;
+        if (desc) {
+          for (int b = 255; b >= 0; --b) {
+            if (acc + hist[b] >= rest) {
+              digit = b;
+              break;
+            }
+            acc += hist[b];
+          }
+        } else {
+          for (int b = 0; b < 256; ++b) {
+            if (acc + hist[b] > rest) {
+              digit = b;
+              break;
+            }
+            acc += hist[b];
+          }
         }
+        sel_prefix = prefix | (static_cast<uint32_t>(digit) << shift);
+        sel_rest = rest - acc;
       }
-      topi[0] = topi[pick];
+      __syncthreads();
+      prefix = sel_prefix;
+      rest = sel_rest;
+      pmask |= 255u << shift;
     }
-    __syncthreads();
-    chosen = topi[0];
-  } else {
-    // full-vocabulary multinomial (top_k = 0, top_p = 1): inverse CDF over softmax
-    float mx = -INFINITY;
+    return prefix;
+  };
+  if (top_k > 0 && top_k < V) {
+    const uint32_t kth = radix_select(true, static_cast<unsigned long long>(top_k), [&](int) { return 1ull; });
 #pragma unroll
-    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mx = fmaxf(mx, v[i]);
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i)
+      if (float_key(v[i]) < kth) v[i] = -INFINITY;
+  }
+  // softmax statistics of the survivors
+  float mx = -INFINITY;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) bv[warp] = mx;
-    __syncthreads();
-    mx = bv[0];
-    for (int w = 1; w < 32; ++w) mx = fmaxf(mx, bv[w]);
-    float mine = 0.f;
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mx = fmaxf(mx, v[i]);
 #pragma unroll
-    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mine += __expf(v[i] - mx);  // -inf -> 0
-    const float tot = block_sum(mine, red);
-    // thread t owns columns {t + i*1024}; order the CDF thread-major (any fixed order is a valid multinomial)
-    __shared__ float tsum[SAMPLE_THREADS];
-    tsum[threadIdx.x] = mine;
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) bv[warp] = mx;
+  __syncthreads();
+  mx = bv[0];
+  for (int w = 1; w < 32; ++w) mx = fmaxf(mx, bv[w]);
+  __syncthreads();
+  if (top_p < 1.f) {
+    // fixed-point masses e_i = exp(v_i - mx) * 2^32 (the largest token weighs exactly 2^32)
+    auto mass = [&](int i) -> unsigned long long {
+      return v[i] == -INFINITY ? 0ull : static_cast<unsigned long long>(__expf(v[i] - mx) * 4294967296.f);
+    };
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mine += mass(i);
+    if (threadIdx.x == 0) hist[0] = 0ull;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const float u = uniform01(seed, n, static_cast<uint32_t>(*cur)) * tot;
-      float acc = 0.f;
-      int owner = SAMPLE_THREADS - 1;
-      for (int t = 0; t < SAMPLE_THREADS; ++t) {
-        if (u < acc + tsum[t]) {
-          owner = t;
-          break;
-        }
+    atomicAdd(&hist[0], mine);
+    __syncthreads();
+    const unsigned long long tot = hist[0];
+    __syncthreads();
+    // drop while the ascending cumulative mass stays <= (1 - top_p) * total
+    const unsigned long long target = static_cast<unsigned long long>(static_cast<double>(tot) * (1.0 - static_cast<double>(top_p)));
+    const uint32_t thr = radix_select(false, target, mass);
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i)
+      if (float_key(v[i]) < thr) v[i] = -INFINITY;
+  }
+  // multinomial over the survivors: inverse CDF, thread t owns columns {t + i*1024}, CDF ordered thread-major (any fixed
+  // order is a valid multinomial)
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) mine += __expf(v[i] - mx);  // -inf -> 0
+  const float tot = block_sum(mine, red);
+  tsum[threadIdx.x] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float u = uniform01(seed, n, static_cast<uint32_t>(*cur)) * tot;
+    float acc = 0.f, base = 0.f;
+    int owner = 0;
+    for (int t = 0; t < SAMPLE_THREADS; ++t) {
+      if (tsum[t] > 0.f) {  // without a hit the draw falls to the last thread that holds any mass
+        owner = t;
+        base = acc;
+        if (u < acc + tsum[t]) break;
         acc += tsum[t];
       }
-      bi[0] = owner;
-      bv[0] = u - acc;
     }
-    __syncthreads();
-    if (threadIdx.x == bi[0]) {
-      float rem = bv[0], acc = 0.f;
-      int pick = -1, last = 0;
-#pragma unroll
-      for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
-        const int c = threadIdx.x + i * SAMPLE_THREADS;
-        if (c < V && pick < 0) {
-          last = c;
-          acc += __expf(v[i] - mx);
-          if (rem < acc) pick = c;
-        }
-      }
-      topi[0] = pick >= 0 ? pick : last;
-    }
-    __syncthreads();
-    chosen = topi[0];
+    bi[0] = owner;
+    bv[0] = u - base;
   }
+  __syncthreads();
+  if (threadIdx.x == bi[0]) {
+    const float rem = bv[0];
+    float acc = 0.f;
+    int pick = -1, last = 0;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+      const int c = threadIdx.x + i * SAMPLE_THREADS;
+      if (c < V && pick < 0 && v[i] != -INFINITY) {
+        last = c;
+        acc += __expf(v[i] - mx);
+        if (rem < acc) pick = c;
+      }
+    }
+    pick_s = pick >= 0 ? pick : last;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    int id = chosen;
+    int id = pick_s;
     if (done[n]) id = pad_id;
     if (id == eos_id) done[n] = 1;
     next_ids[n] = id;
@@ -1299,19 +1323,28 @@ int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, 
     return -1;
   return check_launch("decode_attention");
 }
-int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
-                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s) {
-  greedy_pick_kernel<<<N, 1024, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, eos_id, pad_id, done, next_ids, out,
-                                        out_ld, cur);
+static SuppressList make_suppress(const int32_t* ids, int n) {
+  SuppressList sl{};
+  sl.n = n < 0 ? 0 : (n > OPADPO_MAX_SUPPRESS ? OPADPO_MAX_SUPPRESS : n);
+  for (int i = 0; i < sl.n; ++i) sl.ids[i] = ids[i];
+  return sl;
+}
+int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, const int32_t* suppress,
+                int n_suppress, uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* cur,
+                cudaStream_t s) {
+  if (n_suppress < 0 || n_suppress > OPADPO_MAX_SUPPRESS) return -1;
+  greedy_pick_kernel<<<N, 1024, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, eos_id, pad_id,
+                                        make_suppress(suppress, n_suppress), done, next_ids, out, out_ld, cur);
   return check_launch("greedy_pick");
 }
 int sample_pick(const float* partials, int splits, int N, int V, int top_k, float top_p, float temperature, uint64_t seed,
-                int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* cur,
-                cudaStream_t s) {
-  if (V > SAMPLE_THREADS * SAMPLE_MAX_PER_THREAD || top_k > SAMPLE_MAX_K || top_k < 0) return -1;
-  if (top_k == 0 && top_p < 1.f) return -1;  // nucleus without top-k would need a full sort: not on the reference's path
+                int eos_id, int pad_id, const int32_t* suppress, int n_suppress, uint8_t* done, int32_t* next_ids,
+                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s) {
+  if (V > SAMPLE_THREADS * SAMPLE_MAX_PER_THREAD || top_k < 0 || !(top_p > 0.f) || !(temperature > 0.f)) return -1;
+  if (n_suppress < 0 || n_suppress > OPADPO_MAX_SUPPRESS) return -1;
   sample_pick_kernel<<<N, SAMPLE_THREADS, 0, s>>>(partials, splits, static_cast<int64_t>(N) * V, V, top_k, top_p,
-                                                  1.f / temperature, seed, eos_id, pad_id, done, next_ids, out, out_ld, cur);
+                                                  1.f / temperature, seed, eos_id, pad_id,
+                                                  make_suppress(suppress, n_suppress), done, next_ids, out, out_ld, cur);
   return check_launch("sample_pick");
 }
 int advance_counter(int32_t* cur, cudaStream_t s) {

@@ -6,6 +6,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#ifndef OPADPO_MAX_SUPPRESS
+#define OPADPO_MAX_SUPPRESS 8  // include/opadpo_b200.h
+#endif
+
 namespace opadpo {
 
 using bf16 = __nv_bfloat16;
@@ -117,13 +121,16 @@ int decode_attention(const bf16* qkv, bf16* kc, bf16* vc, const uint8_t* kmask, 
                      const int32_t* cur, int S_max, float scale, cudaStream_t s);
 // Split-K partial logits [splits, N, V] -> argmax id (lowest index on ties, as torch.argmax). Finished rows
 // (done[n] != 0) emit pad_id; done is set when eos is produced; writes next_ids [N] and out[n*out_ld + *cur].
-int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, uint8_t* done, int32_t* next_ids,
-                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s);
-// Sampling pick: temperature -> top-k -> top-p -> multinomial (HF warper order), counter-based RNG keyed by
-// (seed, sequence, step). top_k in [1, 64], or top_k = 0 with top_p = 1 (plain multinomial, rl_models.py:166-188).
-int sample_pick(const float* partials, int splits, int N, int V, int top_k, float top_p, float temperature, uint64_t seed,
-                int eos_id, int pad_id, uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* cur,
+// `suppress` (host array, n_suppress <= OPADPO_MAX_SUPPRESS): HF suppress_tokens, logit := -inf.
+int greedy_pick(const float* partials, int splits, int N, int V, int eos_id, int pad_id, const int32_t* suppress,
+                int n_suppress, uint8_t* done, int32_t* next_ids, int64_t* out, int64_t out_ld, const int32_t* cur,
                 cudaStream_t s);
+// Sampling pick: suppress_tokens -> temperature -> top-k -> top-p -> multinomial (HF processor / warper order), counter-based
+// RNG keyed by (seed, sequence, step). Any top_k >= 0 (0 = off; ties with the k-th largest survive, as in TopKLogitsWarper)
+// and any top_p in (0, 1]; vocab <= 40960.
+int sample_pick(const float* partials, int splits, int N, int V, int top_k, float top_p, float temperature, uint64_t seed,
+                int eos_id, int pad_id, const int32_t* suppress, int n_suppress, uint8_t* done, int32_t* next_ids,
+                int64_t* out, int64_t out_ld, const int32_t* cur, cudaStream_t s);
 int advance_counter(int32_t* cur, cudaStream_t s);
 // Deterministic reductions of gemm EPI_F32_PARTIAL slices [splits, M, N] fused with the op that follows the linear.
 int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s);

@@ -19,7 +19,7 @@ namespace opadpo {
     int _rc = (expr);                                                                                  \
     if (_rc != 0) {                                                                                    \
       if (g_last_error[0] == 0) set_error("%s failed (%d) at %s:%d", #expr, _rc, __FILE__, __LINE__);  \
-      return (_rc >= OPADPO_ESTATE) ? _rc : OPADPO_ECUDA;                                              \
+      return (_rc >= OPADPO_ENOENT) ? _rc : OPADPO_ECUDA;                                              \
     }                                                                                                  \
   } while (0)
 
@@ -353,7 +353,7 @@ int Engine::load_tensor(const char* name, const void* src, int dtype, int64_t ro
     return copy_in(final_norm, src, dtype, c.d_model, s);
   }
   set_error("load_tensor: unknown tensor name '%s'", name);
-  return OPADPO_EINVAL;
+  return OPADPO_ENOENT;
 }
 
 int Engine::lora_shape(const char* module, int64_t* in_f, int64_t* out_f) {
@@ -1231,10 +1231,19 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     return OPADPO_EINVAL;
   }
   const bool do_sample = sampler && sampler->do_sample;
-  if (do_sample && (!(sampler->temperature > 0.f) || sampler->top_k < 0 || sampler->top_k > 64 ||
-                    !(sampler->top_p > 0.f) || (sampler->top_k == 0 && sampler->top_p < 1.f))) {
-    set_error("generate: unsupported sampler (temperature %g top_k %d top_p %g): need temperature > 0, top_k in [1,64] "
-              "or top_k = 0 with top_p = 1", sampler->temperature, sampler->top_k, sampler->top_p);
+  if (do_sample && (!(sampler->temperature > 0.f) || sampler->top_k < 0 || !(sampler->top_p > 0.f) || sampler->top_p > 1.f)) {
+    set_error("generate: bad sampler (temperature %g top_k %d top_p %g): need temperature > 0, top_k >= 0, top_p in (0, 1]",
+              sampler->temperature, sampler->top_k, sampler->top_p);
+    return OPADPO_EINVAL;
+  }
+  const int n_sup = sampler ? sampler->n_suppress : 0;
+  const int32_t* sup = sampler ? sampler->suppress_tokens : nullptr;
+  if (n_sup < 0 || n_sup > OPADPO_MAX_SUPPRESS) {
+    set_error("generate: n_suppress %d out of range [0, %d]", n_sup, OPADPO_MAX_SUPPRESS);
+    return OPADPO_EINVAL;
+  }
+  if (do_sample && c.vocab > 40960) {
+    set_error("generate: the sampling kernel holds at most 40960 vocabulary entries (vocab %d)", c.vocab);
     return OPADPO_EINVAL;
   }
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads, V = c.vocab;
@@ -1434,9 +1443,9 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
     }
     if (do_sample) {
       EN_CHECK(sample_pick(part, sp, N, V, sampler->top_k, sampler->top_p, sampler->temperature, sampler->seed, c.eos_id,
-                           c.pad_id, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new, cur, s));
+                           c.pad_id, sup, n_sup, done, next_ids, out_ids + Q, static_cast<int64_t>(Q) + max_new, cur, s));
     } else {
-      EN_CHECK(greedy_pick(part, sp, N, V, c.eos_id, c.pad_id, done, next_ids, out_ids + Q,
+      EN_CHECK(greedy_pick(part, sp, N, V, c.eos_id, c.pad_id, sup, n_sup, done, next_ids, out_ids + Q,
                            static_cast<int64_t>(Q) + max_new, cur, s));
     }
     EN_CHECK(advance_counter(cur, s));

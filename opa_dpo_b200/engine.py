@@ -91,6 +91,24 @@ def linear_modules(cfg: EngineConfig) -> Dict[str, Tuple[int, int]]:
     return s
 
 
+def required_tensor_names(cfg: EngineConfig) -> List[str]:
+    """Every base tensor the engine executes (what a base checkpoint has to provide): embeddings, norms, every linear of
+    linear_modules (+ biases of the projector and the CLIP tower), the CLIP embeddings and layer norms of the executed layers."""
+    names = ["model.embed_tokens.weight", "lm_head.weight", "model.norm.weight"]
+    for i in range(cfg.n_layers):
+        names += [f"model.layers.{i}.input_layernorm.weight", f"model.layers.{i}.post_attention_layernorm.weight"]
+    for m in linear_modules(cfg):
+        names.append(m + ".weight")
+        if "vision_model" in m or "mm_projector" in m:
+            names.append(m + ".bias")
+    names += [VT + "embeddings.class_embedding", VT + "embeddings.patch_embedding.weight",
+              VT + "embeddings.position_embedding.weight", VT + "pre_layrnorm.weight", VT + "pre_layrnorm.bias"]
+    for i in range(cfg.v_layers):
+        for ln in ("layer_norm1", "layer_norm2"):
+            names += [f"{VT}encoder.layers.{i}.{ln}.weight", f"{VT}encoder.layers.{i}.{ln}.bias"]
+    return names
+
+
 class Engine:
     def __init__(self, cfg: EngineConfig, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
@@ -135,7 +153,7 @@ class Engine:
         for name, t in sd.items():
             try:
                 self.load_tensor(name, t)
-            except OpadpoError:
+            except _lib.OpadpoUnknownName:      # shape / dtype errors on tensors the engine holds always raise
                 if strict:
                     raise
 
@@ -260,9 +278,14 @@ class Engine:
         return norm
 
     def generate(self, adapter: int, images: torch.Tensor, queries: torch.Tensor, qmask: torch.Tensor, max_new_tokens: int,
-                 do_sample: bool = False, top_k: int = 0, top_p: float = 1.0, temperature: float = 1.0, seed: int = 0):
+                 do_sample: bool = False, top_k: int = 0, top_p: float = 1.0, temperature: float = 1.0, seed: int = 0,
+                 suppress_tokens=None):
         b, Q = queries.shape
-        sm = _lib.Sampler(int(do_sample), int(top_k), float(top_p), float(temperature), int(seed) & (2 ** 64 - 1))
+        sup = [int(t) for t in (suppress_tokens or [])]
+        if len(sup) > 8:
+            raise OpadpoError(f"at most 8 suppress_tokens (got {len(sup)})")
+        sm = _lib.Sampler(int(do_sample), int(top_k), float(top_p), float(temperature), int(seed) & (2 ** 64 - 1), len(sup),
+                          (ctypes.c_int32 * 8)(*sup))
         images = images.to(self.device, torch.float32).contiguous()
         queries = queries.to(self.device, torch.int64).contiguous()
         qmask = qmask.to(self.device, torch.uint8).contiguous()
@@ -270,6 +293,9 @@ class Engine:
         _lib.check(self.lib.opadpo_generate(self._h, adapter, images.data_ptr(), b, queries.data_ptr(), qmask.data_ptr(), Q,
                                             max_new_tokens, ctypes.byref(sm), out.data_ptr(), _stream()), "opadpo_generate")
         return out
+
+    def required_tensor_names(self) -> List[str]:
+        return required_tensor_names(self.cfg)
 
     def launch_count(self) -> int:
         return int(self.lib.opadpo_launch_count())

@@ -39,19 +39,39 @@ class B200AdamW:
 
     def zero_grad(self, set_to_none: bool = True):
         self.model.engine.zero_grad()
+        if hasattr(self.model, "release_slots"):
+            self.model.release_slots()      # a forward left undifferentiated by a failed step must not pin its slot
 
     def state_dict(self) -> Dict:
+        """torch-optimizer shaped: ONE flat parameter (the engine's LoRA bucket). Next to the moments it carries the fp32
+        master copy of the trainable tensors: adapter_model.bin holds them rounded to bf16 (PEFT's format, what the reference
+        stores), and at lr 1e-6 most of an update is below a bf16 ulp — without the master a resumed run would restart from
+        the rounded values and diverge from an uninterrupted one."""
         v = self.model.engine.buffers()
+        n = v["n_train"]
         return dict(state={0: dict(step=self.step_count, exp_avg=v["exp_avg"].detach().cpu().clone(),
-                                   exp_avg_sq=v["exp_avg_sq"].detach().cpu().clone())},
+                                   exp_avg_sq=v["exp_avg_sq"].detach().cpu().clone(),
+                                   master=v["master"][:n].detach().cpu().clone())},
                     param_groups=[{k: val for k, val in self.param_groups[0].items() if k != "params"} | {"params": [0]}],
                     max_grad_norm=self.max_grad_norm)
 
     def load_state_dict(self, sd: Dict):
-        st = sd["state"][0]
+        """Call after the adapter has been loaded (load_checkpoint's order): the fp32 master stored here replaces the
+        bf16-rounded values adapter_model.bin gave, then the bf16 shadow the GEMMs read is refreshed."""
+        state = sd.get("state", {})
         v = self.model.engine.buffers()
+        n = v["n_train"]
+        if len(state) != 1 or 0 not in state or state[0]["exp_avg"].numel() != n:
+            raise ValueError("optimizer.pt does not hold this engine's flat LoRA bucket (one parameter of "
+                             f"{n} elements; got {len(state)} parameter entries). A file written by the reference trainer "
+                             "keeps one state entry per LoRA tensor and cannot be resumed here; only adapter_model/ is "
+                             "format-compatible (INTEGRATION.md).")
+        st = state[0]
         v["exp_avg"].copy_(st["exp_avg"].to(v["exp_avg"].device))
         v["exp_avg_sq"].copy_(st["exp_avg_sq"].to(v["exp_avg_sq"].device))
+        if "master" in st:
+            v["master"][:n].copy_(st["master"].to(v["master"].device))
+            self.model.engine.sync_shadow()
         self.step_count = int(st["step"])
         self.model.engine.set_option("adam_step", self.step_count)
         for k, val in sd["param_groups"][0].items():
@@ -90,7 +110,12 @@ class cosine_schedule:
         return dict(last_epoch=self.last_epoch, warmup=self.warmup, total=self.total)
 
     def load_state_dict(self, sd):
-        self.last_epoch, self.warmup, self.total = sd["last_epoch"], sd["warmup"], sd["total"]
+        """Accepts this class's own state and a torch LambdaLR state dict (what the reference's scheduler.pt holds,
+        dpo_trainer.py:884-886: `last_epoch` is all that matters there — the lambda itself is not serialised, so warm-up
+        and total keep the constructor's values, exactly as on the reference's resume)."""
+        self.last_epoch = int(sd["last_epoch"])
+        self.warmup = sd.get("warmup", self.warmup)
+        self.total = sd.get("total", self.total)
         self._apply()
 
 

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import json
 import os
+import weakref
 from types import SimpleNamespace
 from typing import Dict, Optional, Tuple
 
@@ -34,6 +35,10 @@ class _PolicyForward(torch.autograd.Function):
         lp, ent = model.engine.forward_logprobs(adapter, images, queries, qmask, list(responses), temperature,
                                                 img_mask=img_mask, save_slot=slot, want_entropy=True)
         ctx.model, ctx.slot, ctx.n_in = model, slot, 9 + len(responses)
+        ctx.gen = model._slot_gen[slot]
+        # a graph that is dropped without ever running backward (an exception mid-step, a logging forward in train mode)
+        # must not leak its slot: the slot is handed back when the autograd node dies
+        weakref.finalize(ctx, model._drop_slot, slot, ctx.gen)
         ctx.out_shape = tuple(lp.shape)
         ctx.set_materialize_grads(False)   # an unused output arrives as None instead of a zero tensor
         return lp, ent
@@ -41,10 +46,14 @@ class _PolicyForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlp, dent):
         # the entropies are differentiable too (OPA's entropy regulariser, opa_models/opa_trainer.py:63,82-85)
+        model = ctx.model
+        if not model._slot_busy[ctx.slot] or model._slot_gen[ctx.slot] != ctx.gen:
+            raise OpadpoError(f"backward of a forward whose activation slot {ctx.slot} was released or reused in the meantime "
+                              "(release_slots() / zero_grad() between forward and backward, or a second backward)")
         if dlp is None and dent is None:   # nothing flows back: still run the backward so the slot is released
-            dlp = torch.zeros(ctx.out_shape, device=ctx.model.engine.device)
-        ctx.model.engine.backward(ctx.slot, dlp, dent)
-        ctx.model._slot_busy[ctx.slot] = False
+            dlp = torch.zeros(ctx.out_shape, device=model.engine.device)
+        model.engine.backward(ctx.slot, dlp, dent)
+        model._slot_busy[ctx.slot] = False
         return (None,) * ctx.n_in
 
 
@@ -62,7 +71,8 @@ class B200LlavaModel(nn.Module):
         self.peft_config: Dict[str, dict] = {}
         self.base_model_name_or_path = base_model_name_or_path
         self.flat_param: Optional[nn.Parameter] = None
-        self._slot_busy = [False, False]
+        self._slot_busy = [False, False]     # the engine keeps the activations of at most two undifferentiated forwards
+        self._slot_gen = [0, 0]              # bumped at every hand-out, so a stale backward / finaliser is recognised
         self._passthrough: Dict[str, Dict[str, Tensor]] = {}   # adapter tensors the engine does not execute (CLIP layer 24)
 
     # ---- adapters
@@ -144,6 +154,29 @@ class B200LlavaModel(nn.Module):
         if is_trainable:
             self.make_trainable(adapter_name)
 
+    # ---- activation slots
+    def _take_slot(self) -> int:
+        for slot in (0, 1):
+            if not self._slot_busy[slot]:
+                self._slot_busy[slot] = True
+                self._slot_gen[slot] += 1
+                return slot
+        raise OpadpoError("both activation slots hold a grad-enabled forward that has not been differentiated yet (the engine "
+                          "keeps two: CoPO's / the OPA regulariser's pair). Run backward on one of them, wrap forwards that "
+                          "need no gradient in torch.no_grad(), or call release_slots()")
+
+    def _drop_slot(self, slot: int, gen: int):
+        if self._slot_busy[slot] and self._slot_gen[slot] == gen:
+            self._slot_busy[slot] = False
+
+    def release_slots(self):
+        """Hands both slots back (after a failed step; B200AdamW.zero_grad calls it). A backward that arrives later for a
+        forward made before this call raises instead of differentiating somebody else's activations."""
+        for slot in (0, 1):
+            if self._slot_busy[slot]:
+                self._slot_busy[slot] = False
+                self._slot_gen[slot] += 1
+
     # ---- forward used by the policy wrapper
     def policy_logprobs(self, images, queries, qmask, responses, temperature, img_mask=None) -> Tuple[Tensor, Tensor]:
         aid = ADAPTER_IDS[self.active_adapter]
@@ -159,8 +192,7 @@ class B200LlavaModel(nn.Module):
         if needs_grad:
             if len(responses) > 16:
                 raise OpadpoError("at most 16 responses per call")
-            slot = 0 if not self._slot_busy[0] else 1
-            self._slot_busy[slot] = True
+            slot = self._take_slot()
             return _PolicyForward.apply(self.flat_param, self, aid, images, queries, qmask, img_mask, float(temperature), slot,
                                         *responses)
         with torch.no_grad():
@@ -176,15 +208,13 @@ class B200LlavaModel(nn.Module):
         [b, Q + max_new_tokens] (finished rows padded). `synced_gpus` is ignored: ranks decode independently.
         Greedy ids reproduce the reference exactly; sampling follows HF's warper order with a counter-based RNG seeded from
         torch.initial_seed() (same distribution, not the same random stream as torch.multinomial)."""
-        if suppress_tokens:
-            raise NotImplementedError("suppress_tokens is not supported by the rollout kernels")
         if num_return_sequences != 1:
             raise NotImplementedError("num_return_sequences > 1")
         self._gen_calls = getattr(self, "_gen_calls", 0) + 1
         seed = (int(torch.initial_seed()) * 1000003 + self._gen_calls) & (2 ** 63 - 1)
         aid = ADAPTER_IDS[self.active_adapter]
         return self.engine.generate(aid, images, inputs, attention_mask, max_new_tokens, do_sample=do_sample, top_k=top_k,
-                                    top_p=top_p, temperature=temperature, seed=seed)
+                                    top_p=top_p, temperature=temperature, seed=seed, suppress_tokens=suppress_tokens)
 
 
 def eng_trainable(model: B200LlavaModel) -> int:
@@ -248,7 +278,9 @@ class AutoregressivePolicy(Policy):
             temperature = self.args.temperature
         seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=True,
                                        max_new_tokens=self.args.response_len, top_p=1.0, top_k=0, temperature=temperature,
-                                       pad_token_id=self.base_tokenizer.pad_token_id)
+                                       pad_token_id=self.base_tokenizer.pad_token_id,
+                                       suppress_tokens=([self.base_tokenizer.eos_token_id]
+                                                        if getattr(self.args, "suppress_eos_at_generation", False) else None))
         return dict(responses=seq[:, queries.size(1):])
 
 

@@ -452,7 +452,34 @@ def pair_loss(lc: LossConfig, p_c, p_r, r_c, r_r):
 
 
 # ---------------------------------------------------------------------------------------------------- rollout
-def greedy_generate(cfg: OracleConfig, w, lora, images, queries, queries_attn_masks, max_new_tokens: int):
+def hf_warp(logits: torch.Tensor, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
+            suppress_tokens: Optional[List[int]] = None) -> torch.Tensor:
+    """The logits processors / warpers HF generate() applies for the arguments online_generator.py:292-309 and
+    rl_models.py:166-188 pass [UPSTREAM transformers/generation/logits_process.py, pinned against the installed classes in
+    tests/test_rollout_host_cpu.py]: SuppressTokensLogitsProcessor (score := -inf), TemperatureLogitsWarper (score / T),
+    TopKLogitsWarper (drop scores < the k-th largest; k = min(top_k, vocab); 0 = off), TopPLogitsWarper (ascending sort,
+    softmax, cumulative mass <= 1 - top_p dropped, the largest kept). Returns the filtered scores (-inf = removed); the
+    sampler then draws from softmax of them."""
+    s = logits.clone().float()
+    if suppress_tokens:
+        s[..., list(suppress_tokens)] = float("-inf")
+    if temperature != 1.0:
+        s = s / temperature
+    if top_k and top_k > 0:
+        k = min(int(top_k), s.shape[-1])
+        kth = torch.topk(s, k, dim=-1).values[..., -1, None]
+        s = s.masked_fill(s < kth, float("-inf"))
+    if top_p < 1.0:
+        sorted_s, sorted_i = torch.sort(s, descending=False, dim=-1)
+        cum = sorted_s.softmax(-1).cumsum(-1)
+        remove = cum <= (1.0 - top_p)
+        remove[..., -1:] = False
+        s = s.masked_fill(remove.scatter(-1, sorted_i, remove), float("-inf"))
+    return s
+
+
+def greedy_generate(cfg: OracleConfig, w, lora, images, queries, queries_attn_masks, max_new_tokens: int,
+                    suppress_tokens: Optional[List[int]] = None):
     """model.generate(do_sample=False) as driven by online_generator.py:292-309 / rl_models.py:166-188:
     HF GenerationMixin.greedy_search [UPSTREAM] over LlavaLlamaForCausalLM.forward with a KV cache; the mask is
     extended by the image-token count on cached steps (llava_modifications.patch:12161-12175); finished rows emit
@@ -466,7 +493,7 @@ def greedy_generate(cfg: OracleConfig, w, lora, images, queries, queries_attn_ma
         out = [queries]
         unfinished = torch.ones(b, dtype=torch.long)
         margin = float("inf")
-        logits = h[:, -1] @ w["lm_head.weight"].t()
+        logits = hf_warp(h[:, -1] @ w["lm_head.weight"].t(), suppress_tokens=suppress_tokens)
         for step in range(max_new_tokens):
             top2 = logits.topk(2, dim=-1).values
             live = unfinished.bool()
@@ -481,7 +508,7 @@ def greedy_generate(cfg: OracleConfig, w, lora, images, queries, queries_attn_ma
             mask = torch.cat([mask, torch.ones(b, 1, dtype=torch.bool)], dim=1)
             xe = w["model.embed_tokens.weight"][nxt][:, None]
             h, past = llama_hidden(cfg, w, lora, xe, mask, past=past, pos0=mask.shape[1] - 1)
-            logits = h[:, -1] @ w["lm_head.weight"].t()
+            logits = hf_warp(h[:, -1] @ w["lm_head.weight"].t(), suppress_tokens=suppress_tokens)
     return torch.cat(out, dim=1), margin
 
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in declared if not hasattr(raw, s)]
     assert not missing, f"declared in include/opadpo_b200.h but not exported: {missing}"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, (set(declared) ^ set(_lib.EXPORTED_SYMBOLS))
-    assert lib.opadpo_abi_version() >= 2
+    assert lib.opadpo_abi_version() == _lib.EXPECTED_ABI
 
 
 def test_struct_layouts_match_header_field_order():
@@ -50,13 +50,14 @@ def test_struct_layouts_match_header_field_order():
             if not decl:
                 continue
             for part in decl.split(","):
-                names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip().replace("*", " "))[0])
+                names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", re.sub(r"\[.*?\]", "", part.strip()).replace("*", " "))[0])
         return names
 
     for struct, cls in (("opadpo_gemm_desc", _lib.GemmDesc), ("opadpo_attn_desc", _lib.AttnDesc),
                         ("opadpo_dpo_pair_desc", _lib.DpoPairDesc), ("opadpo_config", _lib.Config),
                         ("opadpo_sampler", _lib.Sampler)):
         assert fields(struct) == [f[0] for f in cls._fields_], struct
+    assert ctypes.sizeof(_lib.Sampler) == 24 + 4 + 4 * 8 + 4      # uint64 alignment pads the tail
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -42,7 +42,7 @@ def _fake_llava(tmp_path):
 
 def test_sharded_base_and_clip_are_streamed_in_reference_order(tmp_path):
     from opa_dpo_b200 import checkpoint as K
-    from opa_dpo_b200._lib import OpadpoError
+    from opa_dpo_b200._lib import OpadpoError, OpadpoUnknownName
     base, clip, s1, s2, cs = _fake_llava(tmp_path)
     assert K.clip_dir_from_config(base) == clip
     files = K.shard_files(base)
@@ -58,7 +58,7 @@ def test_sharded_base_and_clip_are_streamed_in_reference_order(tmp_path):
 
         def load_tensor(self, name, t):
             if "inv_freq" in name or "post_layernorm" in name:
-                raise OpadpoError("unknown tensor")
+                raise OpadpoUnknownName("unknown tensor")
             self.calls.append((name, t.clone()))
 
     rec = Recorder()
@@ -71,6 +71,32 @@ def test_sharded_base_and_clip_are_streamed_in_reference_order(tmp_path):
     assert names.count(vt) == 2 and torch.equal([t for n, t in rec.calls if n == vt][-1], s2[vt])
     assert not any("text_model" in n for n in names)
     assert stats == {"loaded": len(names), "skipped": 2} and len(logs) == 2
+
+    # a shape mismatch on a tensor the engine holds is NOT a skip (from_pretrained raises on size mismatches) ...
+    class Strict(Recorder):
+        def load_tensor(self, name, t):
+            if name.endswith("embed_tokens.weight"):
+                raise OpadpoError("load_tensor(model.embed_tokens.weight): shape [32003,4096], expected [32000,4096]")
+            super().load_tensor(name, t)
+    with pytest.raises(OpadpoError, match="expected"):
+        K.load_llava_base(Strict(), base)
+    # ... and a checkpoint that does not cover what the engine executes raises with the missing names
+    with pytest.raises(OpadpoError, match="layers.5.mlp.up_proj.weight"):
+        K.load_llava_base(Recorder(), base, required=names + ["model.layers.5.mlp.up_proj.weight"])
+    assert K.load_llava_base(Recorder(), base, required=names)["loaded"] == len(names)
+
+
+def test_required_tensor_names_cover_the_llava_state_dict_layout():
+    from opa_dpo_b200.engine import EngineConfig, required_tensor_names, VT
+    cfg = EngineConfig(n_layers=2, v_layers=3)
+    req = required_tensor_names(cfg)
+    assert len(req) == len(set(req))
+    for n in ("model.embed_tokens.weight", "lm_head.weight", "model.norm.weight", "model.layers.1.mlp.down_proj.weight",
+              "model.layers.0.input_layernorm.weight", "model.mm_projector.2.bias", VT + "encoder.layers.2.mlp.fc1.bias",
+              VT + "embeddings.position_embedding.weight", VT + "pre_layrnorm.bias", VT + "encoder.layers.0.layer_norm2.weight"):
+        assert n in req, n
+    assert not any("layers.2.self_attn" in n and "encoder" not in n for n in req) and not any("encoder.layers.3" in n for n in req)
+    assert not any(n.endswith("q_proj.bias") and "vision_model" not in n for n in req)       # LLaMA linears carry no bias
 
 
 def test_engine_config_from_hf_and_adapter_dir(tmp_path):

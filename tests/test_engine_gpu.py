@@ -324,6 +324,102 @@ def test_sampling_rollout_topk_topp():
     eng.close()
 
 
+@pytest.mark.parametrize("top_k,top_p,temperature", [(0, 0.8, 0.9), (100, 1.0, 1.0), (100, 0.6, 1.3), (400, 0.9, 1.0), (600, 0.95, 1.0)])
+def test_sampling_general_topk_topp_support(top_k, top_p, temperature):
+    """Any top_k (radix select, no 64-entry cap) and top_p without top_k: every sampled token lies in the support HF's
+    warpers leave (oracle.hf_warp, pinned to transformers' classes on the CPU) given the same prefix. bf16 logits move
+    the boundary slightly, so the oracle support is taken with a little slack (top_k + 2, top_p + 0.03); a large sample
+    of first tokens also has to COVER most of the support's mass (a sampler that kept too little would not)."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=12.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 4, 16, 8, NAMES2, left_pad=3)
+    a = eng.generate(POLICY, images, q, qm, 8, do_sample=True, top_k=top_k, top_p=top_p, temperature=temperature, seed=77).cpu()
+    a2 = eng.generate(POLICY, images, q, qm, 8, do_sample=True, top_k=top_k, top_p=top_p, temperature=temperature, seed=77).cpu()
+    assert torch.equal(a, a2)
+    gen = a[:, 16:]
+    logits = _oracle_step_logits(oc, w, lp, images, q, qm, gen)
+    slack = O.hf_warp(logits, temperature, min(top_k + 2, oc.vocab) if top_k else 0, min(top_p + 0.03, 1.0))
+    finished = torch.zeros(4, dtype=torch.bool)
+    for t in range(gen.shape[1]):
+        for n in range(4):
+            if finished[n]:
+                assert gen[n, t] == oc.pad_id
+                continue
+            assert torch.isfinite(slack[n, t, gen[n, t]]), f"row {n} step {t}: token {int(gen[n, t])} outside the warped support"
+            finished[n] |= bool(gen[n, t] == oc.eos_id)
+    # coverage of the first token's support over 64 x 16 draws
+    B = 64
+    imgs, qq, qqm = images[:1].repeat(B, 1, 1, 1), q[:1].repeat(B, 1), qm[:1].repeat(B, 1)
+    counts = torch.zeros(oc.vocab)
+    for seed in range(16):
+        out = eng.generate(POLICY, imgs, qq, qqm, 1, do_sample=True, top_k=top_k, top_p=top_p, temperature=temperature, seed=seed).cpu()
+        counts += torch.bincount(out[:, 16], minlength=oc.vocab).float()
+    with torch.no_grad():
+        ids = torch.cat([q[:1], torch.full((1, 1), 5)], 1)
+        l0 = O.llava_logits(oc, w, lp, ids, torch.cat([qm[:1].bool(), torch.ones(1, 1, dtype=torch.bool)], 1), images[:1])[0, -2]
+    want = torch.softmax(O.hf_warp(l0[None], temperature, top_k, top_p)[0], -1)
+    loose = O.hf_warp(l0[None], temperature, min(top_k + 2, oc.vocab) if top_k else 0, min(top_p + 0.03, 1.0))[0]
+    assert counts[~torch.isfinite(loose)].sum() == 0
+    emp = counts / counts.sum()
+    tv = 0.5 * (emp - want).abs().sum().item()
+    assert tv < 0.10 + 0.5 * (want * (1 - want) / counts.sum()).sqrt().sum().item(), f"total variation {tv:.3f}"
+    eng.close()
+
+
+@pytest.mark.parametrize("do_sample", [False, True])
+def test_rollout_suppress_eos_at_generation(do_sample):
+    """suppress_tokens=[eos] (online_generator.py:298-302, rl_models.py:173-177 under suppress_eos_at_generation): the EOS
+    never appears, no row is padded, and the greedy ids equal the oracle's greedy loop with the same suppression — on a
+    configuration whose unsuppressed greedy path does emit EOS early."""
+    import dataclasses
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import EngineConfig
+    from opa_dpo_b200.policy import B200LlavaModel
+    from opa_dpo_b200.generation import B200OnlineGenerator
+    oc = dataclasses.replace(O.OracleConfig(), eos_id=298)
+    ec = EngineConfig(**oc.to_dict())
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc, peaked=40.0)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.set_adapter("lora_policy")
+    images, q, qm, _ = O.synthetic_batch(oc, 2, 16, 24, NAMES3, left_pad=2)
+    plain, _ = O.greedy_generate(oc, w, lp, images, q, qm, 12)
+    assert (plain[:, 16:] == oc.eos_id).any()                      # without suppression the EOS is emitted
+    dev = model.engine.device
+    out = model.generate(inputs=q.to(dev), images=images.to(dev), attention_mask=qm.to(dev), do_sample=do_sample, max_new_tokens=12,
+                         pad_token_id=oc.pad_id, suppress_tokens=[oc.eos_id], top_k=0, top_p=1.0, temperature=1.0).cpu()
+    assert not (out[:, 16:] == oc.eos_id).any() and not (out[:, 16:] == oc.pad_id).any()
+    if not do_sample:
+        want, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12, suppress_tokens=[oc.eos_id])
+        assert margin > 0.05 and torch.equal(out, want)
+    gen = B200OnlineGenerator(SimpleNamespace(response_len=12, top_p=1.0, top_k=0, temperature=1.0, suppress_eos_at_generation=True),
+                              model, SimpleNamespace(pad_token_id=oc.pad_id, eos_token_id=oc.eos_id))
+    r = gen.generate_responses(images.to(dev), q.to(dev), qm.to(dev), do_sample=do_sample).cpu()
+    assert r.shape == (2, 12) and not (r == oc.eos_id).any()
+    model.engine.close()
+
+
+def test_eval_generation_single_row_greedy():
+    """The eval scripts' call shape (eval_llava_rlhf_coco/model_vqa.py:71-290: one image, one prompt, greedy,
+    `model.generate(input_ids, images=..., do_sample=False, max_new_tokens=...)`): b = 1, no left padding, ids exact."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 1, 24, 8, NAMES2)
+    ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 16)
+    got = eng.generate(POLICY, images, q, qm, 16).cpu()
+    assert margin > 0.05 and got.shape == (1, 40) and torch.equal(got, ids_ref)
+    eng.close()
+
+
 def test_sampling_full_multinomial_distribution():
     """top_k=0, top_p=1 (AutoregressivePolicy._respond, rl_models.py:166-188): empirical first-token distribution over
     2048 draws vs the oracle's softmax (total variation < 0.08)."""
@@ -405,6 +501,28 @@ def test_checkpoint_roundtrip_peft_layout(tmp_path):
         assert torch.equal(again[k], v), k
     v1, v2 = model.engine.buffers(), model2.engine.buffers()
     assert torch.equal(v1["exp_avg"], v2["exp_avg"]) and torch.equal(v1["exp_avg_sq"], v2["exp_avg_sq"])
+    # the fp32 masters come back exactly (optimizer.pt carries them; adapter_model.bin alone would give their bf16 rounding),
+    # so a resumed run takes the same next step as the uninterrupted one
+    n = v1["n_train"]
+    assert torch.equal(v1["master"][:n], v2["master"][:n])
+    assert not torch.equal(v1["master"][:n], v1["master"][:n].to(torch.bfloat16).float())     # the rounding would have lost something
+    for m, o, sc in ((model, opt, sch), (model2, opt2, sch2)):
+        p_, r_ = AutoregressivePolicy(args, m, tok, "lora_policy"), AutoregressivePolicy(args, m, tok, "lora_ref_policy")
+        st = DPOStepper(p_, r_, args)
+        refs = st.reference_logprobs(batch)
+        st.pair_loss(batch, refs, NAMES2[0], NAMES2[1])
+        o.step(); o.zero_grad(); sc.step()
+    torch.cuda.synchronize()
+    # (split-K wgrad atomics land in any order, so two runs agree to fp32 noise, not bit for bit; a resume from the bf16
+    # rounding alone would sit ~3e-5 away)
+    assert (v1["master"][:n] - v2["master"][:n]).abs().mean().item() < 1e-6
+    # scheduler.pt written by the reference is a torch LambdaLR state dict: last_epoch is what is restored
+    sch3 = cosine_schedule(opt2, 2, 10)
+    sch3.load_state_dict({"last_epoch": 2, "base_lrs": [1e-3], "_step_count": 3, "lr_lambdas": [None], "_last_lr": [0.0]})
+    assert sch3.last_epoch == 2 and sch3.warmup == 2 and sch3.total == 10
+    # optimizer.pt written by the reference (one state entry per LoRA tensor) is rejected with a clear message
+    with pytest.raises(ValueError, match="one state entry per LoRA tensor"):
+        opt2.load_state_dict({"state": {0: {"exp_avg": torch.zeros(4)}, 1: {"exp_avg": torch.zeros(4)}}, "param_groups": [{}]})
     model.engine.close(); model2.engine.close()
 
 
@@ -452,6 +570,58 @@ def test_opa_sft_loss_and_grads_vs_oracle():
             gg = g[off:off + t.numel()].view_as(t).cpu()
             cos = torch.nn.functional.cosine_similarity(gg.flatten(), t.grad.flatten(), dim=0).item()
             assert cos >= 0.99, (m, cos)
+    model.engine.close()
+
+
+def test_activation_slots_are_never_silently_reused():
+    """The engine keeps the activations of two undifferentiated forwards. A third grad-enabled forward raises instead of
+    overwriting slot 1; a graph dropped without backward hands its slot back; after release_slots() a late backward raises
+    instead of differentiating another forward's activations; torch.no_grad() forwards take no slot."""
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import OpadpoError
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.dpo import DPOArgs
+    oc, ec = _cfgs()
+    model = B200LlavaModel(ec)
+    w = O.init_weights(oc)
+    lp = O.init_lora(oc, 11)
+    sd = dict(w)
+    sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+    model.engine.load_state_dict(sd)
+    model.load_adapter_state("lora_policy", {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lp.items() for x, t in zip("AB", ab)})
+    model.make_trainable("lora_policy")
+    policy = AutoregressivePolicy(DPOArgs(response_len=24), model, SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, ["standard_response"], left_pad=2)
+    key = "standard_response_logprobs"
+    a = policy(images, q, qm, **resp)
+    b = policy(images, q, qm, **resp)
+    assert model._slot_busy == [True, True]
+    with torch.no_grad():
+        policy(images, q, qm, **resp)                              # inference: no slot needed
+    with pytest.raises(OpadpoError, match="both activation slots"):
+        policy(images, q, qm, **resp)
+    del b                                                          # graph dropped without backward -> slot 1 is free again
+    import gc; gc.collect()
+    assert model._slot_busy == [True, False]
+    c = policy(images, q, qm, **resp)
+    assert model._slot_busy == [True, True]
+    model.engine.zero_grad()
+    a[key].sum().backward()
+    c[key].sum().backward()
+    torch.cuda.synchronize()
+    g1 = model.engine.buffers()["grad"].clone()
+    assert model._slot_busy == [False, False] and g1.abs().sum().item() > 0
+    d = policy(images, q, qm, **resp)
+    model.release_slots()                                          # e.g. zero_grad() after a failed step
+    e = policy(images, q, qm, **resp)                              # takes slot 0 again
+    with pytest.raises(RuntimeError, match="released or reused"):
+        d[key].sum().backward()
+    model.engine.zero_grad()
+    e[key].sum().backward()
+    torch.cuda.synchronize()
+    g2 = model.engine.buffers()["grad"]
+    assert torch.allclose(g2 * 2, g1, rtol=1e-3, atol=1e-6)        # a and c were the same forward twice
     model.engine.close()
 
 

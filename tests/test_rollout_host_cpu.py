@@ -127,3 +127,32 @@ def test_rollout_vs_reference_dpo_trainer(copo, method, detailed, bf16):
     # by design: the reference also runs (and throws away) a policy forward per batch; the mirror does not
     assert len(tr.policy.calls) == 3 and len(pol.calls) == 0
     assert ref.calls == tr.ref_policy.calls
+
+
+@pytest.mark.parametrize("top_k,top_p,temperature,suppress", [(0, 1.0, 1.0, None), (30, 0.95, 1.2, None), (0, 0.8, 0.7, [2]),
+                                                              (300, 1.0, 1.0, [2, 7]), (1, 0.5, 1.0, None), (1000, 0.3, 2.0, None)])
+def test_oracle_warpers_equal_transformers_logits_processors(top_k, top_p, temperature, suppress):
+    """oracle.hf_warp (what the sampling kernel is checked against) == the installed transformers' own processor classes in
+    the order generate() applies them for the reference's arguments (online_generator.py:292-309): suppress_tokens, then
+    temperature, top-k, top-p."""
+    from transformers.generation.logits_process import (SuppressTokensLogitsProcessor, TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper)
+    from oracle import llava_oracle as O
+    g = torch.Generator().manual_seed(top_k * 7 + int(top_p * 100))
+    logits = torch.randn(5, 512, generator=g) * 3.0
+    logits[1, 10:14] = logits[1, 10]           # ties, also at the top-k boundary of some rows
+    ids = torch.zeros(5, 1, dtype=torch.long)
+    want = logits.clone()
+    if suppress:
+        want = SuppressTokensLogitsProcessor(suppress, device="cpu")(ids, want)
+    if temperature != 1.0:
+        want = TemperatureLogitsWarper(temperature)(ids, want)
+    if top_k:
+        want = TopKLogitsWarper(top_k)(ids, want)
+    if top_p < 1.0:
+        want = TopPLogitsWarper(top_p)(ids, want)
+    got = O.hf_warp(logits, temperature, top_k, top_p, suppress)
+    assert torch.equal(torch.isinf(got), torch.isinf(want))
+    keep = ~torch.isinf(want)
+    assert torch.allclose(got[keep], want[keep], rtol=1e-6, atol=0)
+    assert keep.any(-1).all()
