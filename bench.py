@@ -13,7 +13,12 @@ Workload = BASELINE.json configs[1]: LLaVA-1.5-7B, LoRA r=256 on every Linear bu
 `e2e`    : same step through the public nn.Module API with HOST (pinned) inputs copied every step + loss read back.
 `roofline`: tensor-pipe bound; achieved = executed GEMM FLOPs / summed CUDA-event kernel time of every tcgen05 GEMM
            launch of one instrumented step (opadpo_prof_begin/end), peak from MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the oracle (CPU fp32 port of the reference path) on the host cores, bounded sample.
+`rollout` : (N=1) BASELINE configs[3] next to the training line — greedy on-policy rollout, batch 32, 336^2 image, query 128
+           (prefill 703 positions), 256 new tokens: tokens/s end to end (host ids/images in, host ids out), decode
+           tokens/s, the decode step's HBM roofline (weights once + KV cache per step vs the measured copy peak), kernel
+           launches per decode step, and a bounded CPU-port sample. `--mode rollout` prints it as the line itself.
+`cpu_baseline` / `--impl reference`: the oracle (CPU fp32 port of the reference path) on the host cores, bounded sample;
+           the reference arm also times ONE full-depth configs[0] step (2 pairs, R=128, all 32+23 layers, fwd+bwd).
 """
 from __future__ import annotations
 
@@ -75,6 +80,55 @@ def cpu_reference_sample(threads: int, n_layers: int = 2, v_layers: int = 2, R: 
     return min(times), flops_per_pair(ec, Q_LEN, R)["per_pair"]
 
 
+def cpu_full_depth_config0_step(threads: int, pairs: int = 2, R: int = 128):
+    """BASELINE configs[0] as the reference runs it on a CPU: the FULL-depth LLaVA-1.5-7B (32 LLaMA + 23 executed CLIP
+    layers, LoRA r=256), `pairs` preference pairs with R-token responses, fp32: reference forward x2, policy forward x2,
+    DPO loss, autograd backward through the policy adapter (SURVEY.md §8d asked for exactly this measurement). Returns
+    (seconds for the step, algorithmic FLOPs of it, seconds spent building the weights)."""
+    import torch
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.engine import EngineConfig
+    from opa_dpo_b200.flops import flops_per_pair
+    torch.set_num_threads(threads)
+    t_init = time.perf_counter()
+    oc = O.OracleConfig(**O.LLAVA_7B)
+    w = O.init_weights(oc, seed=1)
+    lp, lr = O.init_lora(oc, 2), O.init_lora(oc, 3)
+    t_init = time.perf_counter() - t_init
+    images, q, qm, resp = O.synthetic_batch(oc, pairs, Q_LEN, R, ["chosen_response", "rejected_response"], ragged=False,
+                                            image_pos=IMG_POS)
+    lpg = {m: (A.clone().requires_grad_(not m.startswith(O.VT)), B.clone().requires_grad_(not m.startswith(O.VT)))
+           for m, (A, B) in lp.items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = O.policy_forward(oc, w, lr, images, q, qm, resp)
+    pol = O.policy_forward(oc, w, lpg, images, q, qm, resp)
+    loss, _, _ = O.pair_loss(O.LossConfig(beta=0.1), pol["chosen_response_logprobs"], pol["rejected_response_logprobs"],
+                             ref["chosen_response_logprobs"], ref["rejected_response_logprobs"])
+    loss.backward()
+    t = time.perf_counter() - t0
+    return t, flops_per_pair(EngineConfig(), Q_LEN, R)["per_pair"] * pairs, t_init
+
+
+def cpu_rollout_sample(threads: int, batch: int = 4, new: int = 8, n_layers: int = 2, v_layers: int = 2):
+    """Bounded CPU sample of the rollout (configs[3]): the oracle's greedy loop (HF generate semantics, KV cache) at true 7B
+    widths, depth truncated to n_layers LLaMA / v_layers CLIP layers, `batch` sequences, `new` tokens. Returns seconds
+    for prefill + new tokens and seconds for prefill + 1 token (their difference / (new-1) = one decode step)."""
+    import torch
+    from oracle import llava_oracle as O
+    torch.set_num_threads(threads)
+    oc = O.OracleConfig(**{**O.LLAVA_7B, "n_layers": n_layers, "v_layers": v_layers})
+    w = O.init_weights(oc, seed=1)
+    lp = O.init_lora(oc, 2)
+    images, q, qm, _ = O.synthetic_batch(oc, batch, Q_LEN, 8, ["chosen_response"], ragged=False, image_pos=IMG_POS)
+    t0 = time.perf_counter()
+    O.greedy_generate(oc, w, lp, images, q, qm, 1)
+    t1 = time.perf_counter()
+    O.greedy_generate(oc, w, lp, images, q, qm, new)
+    t2 = time.perf_counter()
+    return t2 - t1, t1 - t0
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -95,13 +149,29 @@ def run_reference_arm(args):
     value = cpu_flops / full
     sample = ("1 pair, R=512, fp32, true 7B widths, depth truncated to 2 LLaMA + 2 CLIP layers; pairs/s extrapolated to "
               "full depth by algorithmic FLOPs (%.1f TFLOP sample vs %.1f TFLOP full pair)" % (fl / 1e12, full / 1e12))
+    full_depth = None
+    if not args.no_full_depth:
+        try:   # one un-truncated step: configs[0] (2 pairs x 128 tokens), every layer, forward and backward
+            t_fd, fl_fd, t_init = cpu_full_depth_config0_step(threads)
+            full_depth = {"config": "BASELINE configs[0]: full-depth LLaVA-1.5-7B (32 LLaMA + 23 CLIP layers), 2 pairs, R=128, fp32, "
+                                    "reference fwd x2 + policy fwd x2 + DPO loss + LoRA backward",
+                          "seconds_per_step": t_fd, "pairs_per_s_at_R128": 2.0 / t_fd, "cpu_tflops": fl_fd / t_fd / 1e12,
+                          "pairs_per_s_at_R512_by_flops": (fl_fd / t_fd) / full, "weight_init_seconds": t_init}
+        except Exception as ex:
+            full_depth = {"failed": f"{type(ex).__name__}: {ex}"}
+    if full_depth and "pairs_per_s_at_R512_by_flops" in full_depth:
+        # the line's value is the HIGHER of the two CPU estimates (the one less flattering to the GPU arm)
+        value = max(value, full_depth["pairs_per_s_at_R512_by_flops"])
+        sample += ("; beside it ONE full-depth configs[0] step measured un-truncated (full_depth_config0); value = the higher of "
+                   "the two estimates")
     line = {
         "impl": "reference", "metric": "preference-pairs/sec LLaVA-1.5-7B OPA-DPO", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LLaVA-1.5-7B LoRA(r=256) OPA-DPO step, 336^2 img, Q=128, R=512 (CPU oracle port of the reference path)"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
-                         "cpu_tflops": cpu_flops / 1e12},
+                         "cpu_tflops": cpu_flops / 1e12, "truncated_depth_estimate": cpu_flops / full,
+                         "full_depth_config0": full_depth},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,6 +227,85 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ rollout (configs[3])
+def measure_rollout(model, cfg, dev, batch: int, new: int, peaks: dict, cpu_sample: bool):
+    """BASELINE configs[3]: greedy on-policy rollout (online_generator.py:292-309 with do_sample=False), `batch` sequences,
+    336^2 image + 128-token query (prefill 703 positions), `new` tokens, through the public `model.generate` call of the
+    trainable policy adapter (merged into the decoder weights once per call, as after every optimizer step).
+    e2e: pinned host images / ids copied in, generated ids read back to the host, all inside the timed region."""
+    import torch
+    eng = model.engine
+    g = torch.Generator().manual_seed(3)
+    h_images = torch.randn(batch, 3, cfg.v_image, cfg.v_image, generator=g).pin_memory()
+    h_q = torch.randint(3, cfg.vocab, (batch, Q_LEN), generator=g)
+    h_q[:, IMG_POS] = cfg.image_token
+    h_q = h_q.pin_memory()
+    h_m = torch.ones(batch, Q_LEN, dtype=torch.uint8).pin_memory()
+    model.set_adapter("lora_policy")
+
+    def run(n_new, host=True):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        out = model.generate(inputs=h_q.to(dev, non_blocking=True), images=h_images.to(dev, non_blocking=True),
+                             attention_mask=h_m.to(dev, non_blocking=True), do_sample=False, max_new_tokens=n_new,
+                             pad_token_id=cfg.pad_id)
+        ids = out.cpu() if host else out
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ids
+
+    run(8)                                                   # warm-up (kernel attributes, graph capture path, pool growth)
+    run(8)
+    run(new)
+    l0 = eng.launch_count()
+    run(1)
+    l1 = eng.launch_count()
+    run(2)
+    l2 = eng.launch_count()
+    launches_per_decode_step = (l2 - l1) - (l1 - l0)         # one eager decode step (the rest replays it as ONE CUDA graph)
+    t_prefill = min(run(1)[0] for _ in range(2))             # multimodal prefill + adapter merge + first token
+    t_full, ids = min((run(new) for _ in range(3)), key=lambda x: x[0])
+    decode_ms = (t_full - t_prefill) / (new - 1)
+    n_lin = cfg.n_layers * (4 * cfg.d_model ** 2 + 3 * cfg.d_model * cfg.d_ffn)
+    w_bytes = 2 * (n_lin + cfg.vocab * cfg.d_model)          # merged bf16 decoder weights + lm_head, read once per step
+    ctx = Q_LEN - 1 + cfg.n_patches + new / 2                # mean context length over the decode steps
+    kv_bytes = 2 * 2 * cfg.n_layers * cfg.d_model * ctx * batch
+    gbs = (w_bytes + kv_bytes) / (decode_ms * 1e-3) / 1e9
+    out = {
+        "workload": f"BASELINE configs[3]: LLaVA-1.5-7B greedy rollout, batch {batch}, 336^2 img, Q=128 (prefill 703), {new} new tokens, 1 GPU",
+        "metric": "rollout tokens/s", "value": batch * new / (t_full * 1e-3), "unit": "tokens/s",
+        "e2e": {"value": batch * new / (t_full * 1e-3), "unit": "tokens/s",
+                "h2d_bytes_per_step": h_images.numel() * 4 + h_q.numel() * 8 + h_m.numel(),
+                "d2h_bytes_per_step": batch * (Q_LEN + new) * 8},
+        "total_ms": t_full, "prefill_ms": t_prefill, "decode_ms_per_step": decode_ms,
+        "decode_tokens_per_s": batch / (decode_ms * 1e-3),
+        "kernel_launches_per_decode_step": int(launches_per_decode_step),
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                     "peak_source": peaks["source"] + " copy bandwidth", "weight_bytes_per_step": w_bytes,
+                     "kv_bytes_per_step_avg": kv_bytes,
+                     "kernel": "decode step = split-K weight-streaming opadpo::gemm_kernel<EPI_F32_PARTIAL> + fused partial reducers + decode_attention"},
+        "generated_nonpad": int((ids[:, Q_LEN:] != cfg.pad_id).sum().item()),
+    }
+    if cpu_sample:
+        try:
+            threads = os.cpu_count() or 1
+            cb, cn, cl = 4, 8, 2
+            t_new, t_one = cpu_rollout_sample(threads, cb, cn, cl, cl)
+            step_s = max(t_new - t_one, 1e-9) / (cn - 1)
+            # linear in depth and batch (the CPU decode step streams the fp32 weights: batch-insensitive in truth, so this
+            # flatters the CPU), prefill linear in depth and batch
+            est = (t_one * (cfg.n_layers / cl) * (batch / cb)) + (new - 1) * step_s * (cfg.n_layers / cl)
+            out["cpu_baseline"] = {"value": batch * new / est, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                   "sample": f"oracle greedy loop at true 7B widths, {cl} LLaMA + {cl} CLIP layers, batch {cb}, {cn} new "
+                                             f"tokens ({t_new:.1f} s; prefill+1 token {t_one:.1f} s); extrapolated linearly in depth "
+                                             "(both phases) and in batch (prefill only)"}
+        except Exception as ex:
+            out["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"failed: {type(ex).__name__}: {ex}"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -169,6 +318,12 @@ def main():
     ap.add_argument("--resp-len", type=int, default=R_LEN)
     ap.add_argument("--no-share-prefix", action="store_true", help="run the reference's K stacked rows (no prefix sharing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-depth", action="store_true", help="reference arm: skip the full-depth configs[0] CPU step (~3 min)")
+    ap.add_argument("--mode", default="train", choices=["train", "rollout"],
+                    help="rollout: print BASELINE configs[3] (greedy rollout, batch 32, 256 new tokens) as the line itself")
+    ap.add_argument("--no-rollout", action="store_true", help="train mode: skip the rollout object")
+    ap.add_argument("--rollout-batch", type=int, default=32)
+    ap.add_argument("--rollout-new", type=int, default=256)
     ap.add_argument("--merge-frozen", type=int, default=int(os.environ.get("OPADPO_MERGE_FROZEN", str(MERGE_FROZEN_DEFAULT))),
                     help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
     ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "1")),
@@ -185,7 +340,7 @@ def main():
     from opa_dpo_b200.engine import EngineConfig
     from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
     from opa_dpo_b200.dpo import DPOArgs, DPOStepper
-    from opa_dpo_b200.flops import flops_per_pair
+    from opa_dpo_b200.flops import executed_attention_flops_per_sample, flops_per_pair
     from opa_dpo_b200 import _lib
     import ctypes
     from types import SimpleNamespace
@@ -217,6 +372,23 @@ def main():
     policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_policy")
     ref_policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_ref_policy")
     stepper = DPOStepper(policy, ref_policy, dargs, world_size=world)
+
+    if args.mode == "rollout":
+        if rank == 0:
+            peaks = _peaks()
+            ro = measure_rollout(model, cfg, dev, args.rollout_batch, args.rollout_new, peaks, not args.no_cpu_baseline)
+            line = {"metric": "rollout tokens/s LLaVA-1.5-7B greedy (BASELINE configs[3])", "value": ro["value"], "unit": "tokens/s",
+                    "n_gpus": 1, "steps": 3, "warmup": 3, "ms_per_step": ro["total_ms"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": ro["workload"]}, "e2e": ro["e2e"], "roofline": ro["roofline"],
+                    "gpu_launches": ro["kernel_launches_per_decode_step"], "rollout": ro}
+            if "cpu_baseline" in ro:
+                line["cpu_baseline"] = ro["cpu_baseline"]
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     b = args.pairs
     g = torch.Generator().manual_seed(1234 + rank)
@@ -309,6 +481,13 @@ def main():
             traffic = None
     gemm_tflops = gf.value / (gm.value * 1e-3) / 1e12 if gm.value > 0 else None
     step_tflops = fl["per_pair"] * b / (ms_step * 1e-3) / 1e12   # per GPU, algorithmic
+    # what the engine really executes per step and GPU: every tcgen05 GEMM launch (event-instrumented count, K padded to the
+    # 64-wide k-block) + the attention kernels (element-level count under the causal / segment mask; one packed forward
+    # for the reference adapter, one for the policy, one backward) + CLIP attention of both forwards
+    att = executed_attention_flops_per_sample(cfg, Q_LEN, R, 2, packed=not args.no_share_prefix)
+    clip_att = cfg.v_layers * 4.0 * (cfg.n_patches + 1) ** 2 * cfg.v_d
+    exec_flops = gf.value + b * (2 * att["fwd"] + att["bwd"] + 2 * clip_att)
+    exec_tflops = exec_flops / (ms_step * 1e-3) / 1e12
     line = {
         "metric": "preference-pairs/sec LLaVA-1.5-7B OPA-DPO", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -336,6 +515,14 @@ def main():
                      "step_executed_gemm_tflop": gf.value / 1e12,
                      "step_frac_of_burst_peak": step_tflops / peaks["burst"],
                      "step_frac_of_sustained_peak": step_tflops / peaks["sustained"],
+                     "frac_note": "frac / achieved = the GEMM family alone (its executed FLOPs / its summed kernel time); "
+                                  "step_executed_* = ALL executed tensor FLOPs (GEMMs + attention) / the whole step's time; "
+                                  "step_frac_of_* = the reference's ALGORITHMIC FLOPs (no prefix sharing, unmerged LoRA) / step time",
+                     "step_executed_tflop": exec_flops / 1e12,
+                     "step_executed_attention_tflop": (exec_flops - gf.value) / 1e12,
+                     "step_executed_tflops": exec_tflops,
+                     "step_executed_frac_burst": exec_tflops / peaks["burst"],
+                     "step_executed_frac_sustained": exec_tflops / peaks["sustained"],
                      "tflop_per_pair": fl["per_pair"] / 1e12},
         "clocks": clk,
     }
@@ -352,6 +539,11 @@ def main():
         except Exception as ex:  # the baseline is informative; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}
+    if world == 1 and not args.no_rollout and args.model == "7b":
+        try:
+            line["rollout"] = measure_rollout(model, cfg, dev, args.rollout_batch, args.rollout_new, peaks, not args.no_cpu_baseline)
+        except Exception as ex:   # never lose the training line over the second workload
+            line["rollout"] = {"failed": f"{type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

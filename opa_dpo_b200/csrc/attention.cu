@@ -57,8 +57,11 @@ __device__ __forceinline__ void store_half_row_sw128(uint8_t* tile, int r, int h
   }
 }
 
-__device__ __forceinline__ uint64_t key_bits(const AttnParams& p, int n, int j, int i, bool causal, bool row_valid) {
-  uint64_t bits = p.kbits ? p.kbits[static_cast<int64_t>(n) * p.nwords + j] : ~0ull;
+// Validity word of key tile j for sequence n (bit c = key j*64+c may be attended to). Loaded one tile ahead of its use.
+__device__ __forceinline__ uint64_t load_kword(const AttnParams& p, int n, int j) {
+  return (p.kbits && j < p.nwords) ? __ldg(p.kbits + static_cast<int64_t>(n) * p.nwords + j) : ~0ull;
+}
+__device__ __forceinline__ uint64_t key_bits_w(const AttnParams& p, uint64_t bits, int j, int i, bool causal, bool row_valid) {
   const int rem = p.S - j * BKV;  // keys beyond the sequence end
   if (rem < 64) bits &= (rem <= 0) ? 0ull : ((1ull << rem) - 1ull);
   if (causal) {
@@ -213,29 +216,50 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
     int it = 0;
-    for (int j = 0; j < num_kv; ++j) {
-      if (tile_skipped(p, q0, j)) continue;
+    // the key-validity word of the next processed tile is fetched while this one is being worked on
+    auto next_j = [&](int j) {
+      ++j;
+      while (j < num_kv && tile_skipped(p, q0, j)) ++j;
+      return j;
+    };
+    int j = next_j(-1);
+    uint64_t kw = j < num_kv ? load_kword(p, n, j) : 0ull;
+    for (; j < num_kv;) {
+      const int jn = next_j(j);
+      const uint64_t kw_next = jn < num_kv ? load_kword(p, n, jn) : 0ull;
+      const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, row_valid);
+      // interior tiles (no padding, no causal edge, no foreign segment in any row of this warp) skip the per-element masking
+      const bool full = __all_sync(0xffffffffu, bits == ~0ull);
       ptx::mbar_wait(s_full, it & 1);
       ptx::tc_fence_after();
       uint32_t r0[32], r1[32];
       ptx::tmem_ld32(t_s + lane_off, r0);
       ptx::tmem_ld32(t_s + lane_off + 32, r1);
       ptx::tmem_ld_wait();
-      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
-      float cm = -INFINITY;
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+      if (full) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float x = ((bits >> c) & 1ull) ? __uint_as_float(r0[c]) * p.scale_log2 : -INFINITY;
-        float y = ((bits >> (32 + c)) & 1ull) ? __uint_as_float(r1[c]) * p.scale_log2 : -INFINITY;
-        r0[c] = __float_as_uint(x);
-        r1[c] = __float_as_uint(y);
-        cm = fmaxf(cm, fmaxf(x, y));
+        for (int c = 0; c < 32; ++c) {
+          cm0 = fmaxf(cm0, __uint_as_float(r0[c]));
+          cm1 = fmaxf(cm1, __uint_as_float(r1[c]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float x = ((bits >> c) & 1ull) ? __uint_as_float(r0[c]) : -INFINITY;
+          const float y = ((bits >> (32 + c)) & 1ull) ? __uint_as_float(r1[c]) : -INFINITY;
+          r0[c] = __float_as_uint(x);
+          r1[c] = __float_as_uint(y);
+          cm0 = fmaxf(cm0, x);
+          cm1 = fmaxf(cm1, y);
+        }
       }
+      const float cm = fmaxf(cm0, cm1) * p.scale_log2;  // scale > 0: max(s) * scale == max(s * scale); -inf stays -inf
       // Lazy rescale: only move the reference max when it grows by more than 2^8 (exact result either way).
       const bool need = cm > m_ref + 8.f;
       float alpha = 1.f;
       if (need) {
-        alpha = exp2f(m_ref - cm);
+        alpha = ptx::ex2_approx(m_ref - cm);
         m_ref = cm;
         l *= alpha;
       }
@@ -251,26 +275,42 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         }
         ptx::tmem_st_wait();
       }
-      const float mu = (m_ref == -INFINITY) ? 0.f : m_ref;
-      float sum = 0.f;
+      // p = 2^(s * scale_log2 - m): one FFMA and one MUFU per element; four independent partial sums
+      const float nmu = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      const float sc2 = p.scale_log2;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       float pv[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        pv[c] = exp2f(__uint_as_float(r0[c]) - mu);
-        sum += pv[c];
+      for (int c = 0; c < 32; c += 4) {
+        pv[c] = ptx::ex2_approx(fmaf(__uint_as_float(r0[c]), sc2, nmu));
+        pv[c + 1] = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 1]), sc2, nmu));
+        pv[c + 2] = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 2]), sc2, nmu));
+        pv[c + 3] = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 3]), sc2, nmu));
+        s0 += pv[c];
+        s1 += pv[c + 1];
+        s2 += pv[c + 2];
+        s3 += pv[c + 3];
       }
       store_half_row_sw128(smem + L::OFF_P, tid, 0, pv);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        pv[c] = exp2f(__uint_as_float(r1[c]) - mu);
-        sum += pv[c];
+      for (int c = 0; c < 32; c += 4) {
+        pv[c] = ptx::ex2_approx(fmaf(__uint_as_float(r1[c]), sc2, nmu));
+        pv[c + 1] = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 1]), sc2, nmu));
+        pv[c + 2] = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 2]), sc2, nmu));
+        pv[c + 3] = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 3]), sc2, nmu));
+        s0 += pv[c];
+        s1 += pv[c + 1];
+        s2 += pv[c + 2];
+        s3 += pv[c + 3];
       }
       store_half_row_sw128(smem + L::OFF_P, tid, 1, pv);
-      l += sum;
+      l += (s0 + s1) + (s2 + s3);
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
       ++it;
+      j = jn;
+      kw = kw_next;
     }
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
@@ -308,17 +348,30 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 }
 
 // =====================================================================================================
-// Backward, shared score recomputation: p = exp2(s*scale_log2 - lse2), ds = p*(dp - delta)*scale
+// Backward, shared score recomputation: p = exp2(s*scale_log2 - lse2), ds' = p*(dp - delta). The softmax scale that
+// belongs on ds is applied once per output element in the dQ / dK epilogues instead of once per score.
 // =====================================================================================================
-__device__ __forceinline__ void recompute_half(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint64_t bits, int half,
-                                               float scale_log2, float scale, float lse2, float delta, float (&pv)[32],
+template <bool WANT_P>
+__device__ __forceinline__ void recompute_half(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint64_t bits, bool full,
+                                               int half, float scale_log2, float lse2, float delta, float (&pv)[32],
                                                float (&dsv)[32]) {
+  const float nl = -lse2;  // invalid rows carry lse2 = +inf: every p is 2^-inf = 0
+  if (full) {              // interior tile: no masking, one FFMA + MUFU + FADD + FMUL per score
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const bool ok = (bits >> (half * 32 + c)) & 1ull;
-    const float pr = ok ? exp2f(__uint_as_float(s[c]) * scale_log2 - lse2) : 0.f;
-    pv[c] = pr;
-    dsv[c] = pr * (__uint_as_float(dp[c]) - delta) * scale;
+    for (int c = 0; c < 32; ++c) {
+      const float pr = ptx::ex2_approx(fmaf(__uint_as_float(s[c]), scale_log2, nl));
+      if (WANT_P) pv[c] = pr;
+      dsv[c] = pr * (__uint_as_float(dp[c]) - delta);
+    }
+  } else {
+    const uint32_t hb = static_cast<uint32_t>(bits >> (half * 32));
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float e = ptx::ex2_approx(fmaf(__uint_as_float(s[c]), scale_log2, nl));
+      const float pr = ((hb >> c) & 1u) ? e : 0.f;
+      if (WANT_P) pv[c] = pr;
+      dsv[c] = pr * (__uint_as_float(dp[c]) - delta);
+    }
   }
 }
 
@@ -457,24 +510,35 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
     const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
     int it = 0;
-    for (int j = 0; j < num_kv; ++j) {
-      if (tile_skipped(p, q0, j)) continue;
+    auto next_j = [&](int j) {
+      ++j;
+      while (j < num_kv && tile_skipped(p, q0, j)) ++j;
+      return j;
+    };
+    int j = next_j(-1);
+    uint64_t kw = j < num_kv ? load_kword(p, n, j) : 0ull;
+    for (; j < num_kv;) {
+      const int jn = next_j(j);
+      const uint64_t kw_next = jn < num_kv ? load_kword(p, n, jn) : 0ull;
+      const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, row_valid);
+      const bool full = __all_sync(0xffffffffu, (half ? (bits >> 32) : (bits & 0xffffffffull)) == 0xffffffffull);
       ptx::mbar_wait(sdp_full, it & 1);
       ptx::tc_fence_after();
-      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
       {
         uint32_t s[32], dp[32];
         ptx::tmem_ld32(t_s + lane_off + half * 32, s);
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
-        recompute_half(s, dp, bits, half, p.scale_log2, p.scale, lse2, delta, pv, dsv);
+        recompute_half<false>(s, dp, bits, full, half, p.scale_log2, lse2, delta, pv, dsv);
         store_half_row_sw128(smem + L::OFF_DS, tid, half, dsv);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(ds_full);
       ++it;
+      j = jn;
+      kw = kw_next;
     }
     ptx::mbar_wait(dq_done, 0);
     ptx::tc_fence_after();
@@ -489,10 +553,10 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
-          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]), __uint_as_float(t[q * 8 + 1]));
-          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]), __uint_as_float(t[q * 8 + 3]));
-          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]), __uint_as_float(t[q * 8 + 5]));
-          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]), __uint_as_float(t[q * 8 + 7]));
+          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]) * p.scale, __uint_as_float(t[q * 8 + 1]) * p.scale);
+          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]) * p.scale, __uint_as_float(t[q * 8 + 3]) * p.scale);
+          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]) * p.scale, __uint_as_float(t[q * 8 + 5]) * p.scale);
+          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]) * p.scale, __uint_as_float(t[q * 8 + 7]) * p.scale);
           dst[q] = u;
         }
       }
@@ -669,18 +733,28 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     const int tid = (warp & 3) * 32 + (threadIdx.x & 31);
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int it = 0;
-    for (int qt = i0; qt <= last_qt; qt = next_tile(qt)) {
+    const uint64_t kw = load_kword(p, n, j);  // one key tile per CTA: the validity word is loop invariant
+    // per-row statistics of the NEXT query tile are fetched while this one is being worked on
+    auto load_stats = [&](int qt, float& lse2, float& delta) {
+      const int i = qt * BQ + tid;
+      const bool ok = qt <= last_qt && i < p.S;
+      const int64_t grow = static_cast<int64_t>(n) * p.S + i;
+      lse2 = ok ? __ldg(p.lse + grow * p.H + h) * LOG2E : INFINITY;
+      delta = ok ? __ldg(p.delta + grow * p.H + h) : 0.f;
+    };
+    float lse2, delta;
+    load_stats(i0, lse2, delta);
+    for (int qt = i0; qt <= last_qt;) {
+      const int qn = next_tile(qt);
+      float lse2_n, delta_n;
+      load_stats(qn, lse2_n, delta_n);
       const int st = it & 1;
       const uint32_t t_s = tmem + st * 128, t_dp = t_s + 64;
       uint8_t* sP = smem + L::OFF_P + st * L::PD_BYTES;
       uint8_t* sdS = smem + L::OFF_DS + st * L::PD_BYTES;
-      const int q0 = qt * BQ;
-      const int i = q0 + tid;
-      const bool row_valid = i < p.S;
-      const int64_t grow = static_cast<int64_t>(n) * p.S + i;
-      const float lse2 = row_valid ? p.lse[grow * p.H + h] * LOG2E : INFINITY;
-      const float delta = row_valid ? p.delta[grow * p.H + h] : 0.f;
-      const uint64_t bits = key_bits(p, n, j, i, CAUSAL, row_valid);
+      const int i = qt * BQ + tid;
+      const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, i < p.S);
+      const bool full = __all_sync(0xffffffffu, (half ? (bits >> 32) : (bits & 0xffffffffull)) == 0xffffffffull);
       ptx::mbar_wait(&pds_empty[st], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P/dS buffer two slots ago are done
       ptx::mbar_wait(&sdp_full[st], (it >> 1) & 1);
       ptx::tc_fence_after();
@@ -690,7 +764,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
-        recompute_half(s, dp, bits, half, p.scale_log2, p.scale, lse2, delta, pv, dsv);
+        recompute_half<true>(s, dp, bits, full, half, p.scale_log2, lse2, delta, pv, dsv);
         store_half_row_sw128(sP, tid, half, pv);
         store_half_row_sw128(sdS, tid, half, dsv);
       }
@@ -698,6 +772,9 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       ptx::tc_fence_before();
       ptx::mbar_arrive(&pds_full[st]);
       ++it;
+      qt = qn;
+      lse2 = lse2_n;
+      delta = delta_n;
     }
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
@@ -714,7 +791,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         if (key < nkeys) {
           const int64_t off = (static_cast<int64_t>(n) * p.S + k0 + key) * p.ld_dqkv + col0 + tid;
           p.dv[off] = __float2bfloat16(__uint_as_float(tv[c]));
-          p.dk[off] = __float2bfloat16(__uint_as_float(tk[c]));
+          p.dk[off] = __float2bfloat16(__uint_as_float(tk[c]) * p.scale);
         }
       }
       __syncwarp();

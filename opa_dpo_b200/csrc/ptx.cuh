@@ -253,6 +253,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 }
 
 // ---------------------------------------------------------------- misc
+// 2^x on the SFU, one MUFU.EX2 (exp2f() without -use_fast_math wraps it in range scaling: 4 instructions per element).
+// ex2(-inf) = +0, denormal results flush to zero.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -34,3 +34,18 @@ def flops_per_pair(cfg: EngineConfig, Q: int, R: int) -> dict:
     fwd = sum(f.values())
     bwd = f["base"] + 2 * f["lora"] + 2.5 * f["attn"] + f["lm_head"] + 2 * f["proj"]
     return dict(fwd_per_seq=fwd, bwd_per_seq=bwd, per_pair=4 * fwd + 2 * bwd, parts=f)
+
+
+def executed_attention_flops_per_sample(cfg: EngineConfig, Q: int, R: int, K: int = 2, packed: bool = True) -> dict:
+    """Attention FLOPs the engine's LLaMA kernels execute for ONE sample (K responses), counted at element level under the
+    causal + segment mask (tile padding not counted): per visible (query, key) pair and head, 2 GEMM units forward
+    (QK^T, PV) and 7 backward in the two-kernel design (dQ kernel: S, dP, dQ; dK/dV kernel: S, dP, dV, dK), each
+    2*head_dim FLOPs. packed = shared-prefix rows [prefix | resp_0 .. resp_{K-1}]; otherwise K stacked rows."""
+    S0 = Q - 1 + cfg.n_patches
+    if packed:
+        pairs = S0 * (S0 + 1) / 2 + K * (R * S0 + R * (R + 1) / 2)
+    else:
+        S = S0 + R
+        pairs = K * S * (S + 1) / 2
+    unit = 2.0 * pairs * cfg.d_model * cfg.n_layers      # one GEMM unit over every head: 2 * pairs * head_dim * n_heads
+    return dict(fwd=2 * unit, bwd=7 * unit, visible_pairs=pairs)

@@ -412,8 +412,8 @@ def test_eval_generation_single_row_greedy():
     from oracle import llava_oracle as O
     from opa_dpo_b200 import POLICY
     oc, ec = _cfgs()
-    eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
-    images, q, qm, _ = O.synthetic_batch(oc, 1, 24, 8, NAMES2)
+    eng, w, lp, lr = _build(oc, ec, peaked=60.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 1, 24, 8, NAMES2, seed=8)
     ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 16)
     got = eng.generate(POLICY, images, q, qm, 16).cpu()
     assert margin > 0.05 and got.shape == (1, 40) and torch.equal(got, ids_ref)

@@ -135,10 +135,20 @@ def _full_depth_case(full7b, tag, b, R, data_seed, modes):
         total, _ = FusedDPO(DPOArgs(beta=0.1)).pair(pol_lp[0], pol_lp[1], ref_lp[0], ref_lp[1])
         rel = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
         signed = torch.cat([(pol_lp[i].cpu() - o_pol[n + "_logprobs"]).flatten() for i, n in enumerate(NAMES2)])
+        # what the loss sees is the per-token error of delta = (pol_c - ref_c) - (pol_r - ref_r): its mean over the tokens
+        # (common-mode errors of a whole sequence do not average out over its tokens) and its spread
+        d_eng = (pol_lp[0] - ref_lp[0]) - (pol_lp[1] - ref_lp[1])
+        d_orc = (o_pol[NAMES2[0] + "_logprobs"] - o_ref[NAMES2[0] + "_logprobs"]) - (o_pol[NAMES2[1] + "_logprobs"] - o_ref[NAMES2[1] + "_logprobs"])
+        e_d = (d_eng.cpu() - d_orc).flatten()
+        slope = float((d_eng.cpu().flatten() @ d_orc.flatten()) / (d_orc.flatten() @ d_orc.flatten()))
+        seq_means = [float((pol_lp[i].cpu() - o_pol[n + "_logprobs"]).mean()) for i, n in enumerate(NAMES2)] + \
+                    [float((ref_lp[i].cpu() - o_ref[n + "_logprobs"]).mean()) for i, n in enumerate(NAMES2)]
+        diag = (f"; delta err mean {e_d.mean().item():+.5f} std {e_d.std().item():.4f} (oracle delta std {d_orc.std().item():.3f}, "
+                f"slope {slope:.4f}); per-set mean err pol_c/pol_r/ref_c/ref_r " + "/".join(f"{x:+.4f}" for x in seq_means))
         msg = (f"FULL-7B parity [{tag}] b={b} R={R} data_seed={data_seed} share_prefix={share} merge_frozen={merge}: loss "
                f"{total.item():.6f} oracle {loss_ref.item():.6f} rel {rel:.3e}; logprob |err| max {errs.max().item():.4f} mean "
                f"{errs.mean().item():.4f} p99 {errs.quantile(0.99).item():.4f} signed-mean {signed.mean().item():+.5f}; "
-               f"oracle {t_cpu:.0f} s on {torch.get_num_threads()} threads")
+               f"oracle {t_cpu:.0f} s on {torch.get_num_threads()} threads" + diag)
         print(msg)
         with open(os.path.join(out_dir, "full_parity_stats.txt"), "a") as f:
             f.write(msg + "\n")
