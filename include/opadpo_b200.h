@@ -76,6 +76,13 @@ typedef struct opadpo_gemm_desc {
 
 int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream);
 int opadpo_gemm_n_tiles(int32_t N);
+/* Weight-streaming GEMM of the rollout's decode step (one new token per sequence: model.generate's cached steps,
+ * online_generator.py:292-309): part[split, m, n] = alpha * sum_{k in split} x[m, k] * W[n, k] for Mb <= 128 activation
+ * rows x [Mb, K] bf16 against a Linear weight W [N, K] bf16; fp32 slices part [splits, Mb, N] that the consumer sums in
+ * slice order (deterministic). splits = 0 picks the count (balance of the persistent grid vs slice traffic), max_splits
+ * caps it (0 = 16); the count used is returned through splits_out. */
+int opadpo_op_decode_gemm(const void* x, int64_t ldx, const void* W, int64_t ldw, int32_t Mb, int32_t N, int32_t K,
+                          int32_t splits, int32_t max_splits, float alpha, float* part, int32_t* splits_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Operator level: tcgen05 flash attention. q/k/v/o/dO/dq/dk/dv are bf16 row-major [N*S, H*HD] views with the

@@ -144,7 +144,7 @@ class Config(ctypes.Structure):
 
 # every symbol include/opadpo_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
-    "opadpo_last_error", "opadpo_abi_version", "opadpo_op_gemm", "opadpo_gemm_n_tiles", "opadpo_op_attn_fwd",
+    "opadpo_last_error", "opadpo_abi_version", "opadpo_op_gemm", "opadpo_gemm_n_tiles", "opadpo_op_decode_gemm", "opadpo_op_attn_fwd",
     "opadpo_op_attn_bwd", "opadpo_op_pack_mask", "opadpo_op_dpo_pair", "opadpo_engine_create", "opadpo_engine_destroy",
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
@@ -204,6 +204,10 @@ def _declare(lib):
     lib.opadpo_gemm_n_tiles.restype = ctypes.c_int
     lib.opadpo_op_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
     lib.opadpo_op_gemm.restype = ctypes.c_int
+    lib.opadpo_op_decode_gemm.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+                                          ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p]
+    lib.opadpo_op_decode_gemm.restype = ctypes.c_int
     for name in ("opadpo_op_attn_fwd", "opadpo_op_attn_bwd"):
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.POINTER(AttnDesc), ctypes.c_void_p]

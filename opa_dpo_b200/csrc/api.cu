@@ -6,6 +6,7 @@
 #include "common.h"
 #include "attention.h"
 #include "collate.h"
+#include "decode_gemm.h"
 #include "gemm.h"
 #include "elementwise.h"
 #include "engine.h"
@@ -79,6 +80,33 @@ int opadpo_op_gemm(const opadpo_gemm_desc* d, void* stream) {
   return OPADPO_OK;
 }
 
+
+int opadpo_op_decode_gemm(const void* x, int64_t ldx, const void* W, int64_t ldw, int32_t Mb, int32_t N, int32_t K,
+                          int32_t splits, int32_t max_splits, float alpha, float* part, int32_t* splits_out, void* stream) {
+  if (!x || !W || !part) {
+    set_error("opadpo_op_decode_gemm: null pointer");
+    return OPADPO_EINVAL;
+  }
+  DecodeGemmArgs a;
+  a.Mb = Mb;
+  a.N = N;
+  a.K = K;
+  a.x = static_cast<const __nv_bfloat16*>(x);
+  a.ldx = ldx;
+  a.W = static_cast<const __nv_bfloat16*>(W);
+  a.ldw = ldw;
+  a.part = part;
+  a.ldc = N;
+  a.alpha = alpha;
+  a.splits = splits > 0 ? splits : decode_gemm_pick_splits(Mb, N, K, max_splits);
+  if (splits_out) *splits_out = a.splits;
+  int rc = decode_gemm_launch(a, static_cast<cudaStream_t>(stream));
+  if (rc != 0) {
+    set_error("%s", decode_gemm_last_error());
+    return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL;
+  }
+  return OPADPO_OK;
+}
 
 static AttnArgs to_attn(const opadpo_attn_desc* d) {
   AttnArgs a;

@@ -102,7 +102,7 @@ struct FwdSmem {
   static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int TOTAL = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = (64 + HD) <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 256;  // S double-buffered (2 x 64) + O (HD)
 };
 
 template <int HD, bool CAUSAL>
@@ -116,10 +116,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;    // [2]: S is double-buffered in TMEM so Q K^T of tile j+1 runs under the softmax of tile j
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* pv_done = bars + 9;   // P V of the previous tile has completed: the P buffer and O may be touched again
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
@@ -147,9 +148,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         ptx::mbar_init(&kv_full[i], 1);
         ptx::mbar_init(&kv_empty[i], 1);
       }
-      ptx::mbar_init(s_full, 1);
+      ptx::mbar_init(&s_full[0], 1);
+      ptx::mbar_init(&s_full[1], 1);
       ptx::mbar_init(p_full, 128);
       ptx::mbar_init(o_full, 1);
+      ptx::mbar_init(pv_done, 1);
       ptx::fence_barrier_init();
     }
   }
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_o = tmem + 64;
+  const uint32_t t_s = tmem, t_o = tmem + 128;  // S buffers at columns [0, 64) and [64, 128)
 
   if (warp == 4) {
     if (ptx::elect_one()) {
@@ -181,21 +184,29 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
       const uint32_t aP = ptx::smem_u32(smem + L::OFF_P);
       ptx::mbar_wait(q_full, 0);
-      int it = 0;
-      for (int j = 0; j < num_kv; ++j) {
-        if (tile_skipped(p, q0, j)) continue;
+      int n_tiles = 0;
+      for (int j = 0; j < num_kv; ++j) n_tiles += tile_skipped(p, q0, j) ? 0 : 1;
+      // S = Q K^T of pipeline slot `it` (K/V stage it & 1) into S buffer it & 1
+      auto issue_qk = [&](int it) {
         const int st = it & 1;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
-        const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
         ptx::mbar_wait(&kv_full[st], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const int blk = kk >> 2, off = (kk & 3) * 32;
-          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
+          ptx::mma_bf16_ss(t_s + st * 64, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
                            ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_qk, kk > 0);
         }
-        ptx::mma_commit(s_full);
+        ptx::mma_commit(&s_full[st]);
+      };
+      if (n_tiles > 0) issue_qk(0);
+      for (int it = 0; it < n_tiles; ++it) {
+        // S buffer (it+1)&1 was last read by the softmax of slot it-1, whose p_full was awaited one iteration ago; the K/V
+        // stage was released by P V of slot it-1 (the producer waits for that before it refills the stage)
+        if (it + 1 < n_tiles) issue_qk(it + 1);
+        const int st = it & 1;
+        const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
         ptx::mbar_wait(p_full, it & 1);
         ptx::tc_fence_after();
 #pragma unroll
@@ -204,8 +215,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                            ptx::make_smem_desc(aV + kk * 2048, BKV * 128, 1024), idesc_pv, (it > 0 || kk > 0));
         }
         ptx::mma_commit(&kv_empty[st]);
-        if (j == num_kv - 1) ptx::mma_commit(o_full);  // the diagonal tile is never skipped
-        ++it;
+        ptx::mma_commit(pv_done);
+        if (it == n_tiles - 1) ptx::mma_commit(o_full);
       }
     }
   } else {
@@ -230,11 +241,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
       const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, row_valid);
       // interior tiles (no padding, no causal edge, no foreign segment in any row of this warp) skip the per-element masking
       const bool full = __all_sync(0xffffffffu, bits == ~0ull);
-      ptx::mbar_wait(s_full, it & 1);
+      ptx::mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t r0[32], r1[32];
-      ptx::tmem_ld32(t_s + lane_off, r0);
-      ptx::tmem_ld32(t_s + lane_off + 32, r1);
+      ptx::tmem_ld32(t_s + (it & 1) * 64 + lane_off, r0);
+      ptx::tmem_ld32(t_s + (it & 1) * 64 + lane_off + 32, r1);
       ptx::tmem_ld_wait();
       float cm0 = -INFINITY, cm1 = -INFINITY;
       if (full) {
@@ -262,6 +273,10 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         alpha = ptx::ex2_approx(m_ref - cm);
         m_ref = cm;
         l *= alpha;
+      }
+      if (it > 0) {  // P V of the previous tile must be done before O is rescaled or the P buffer is overwritten
+        ptx::mbar_wait(pv_done, (it - 1) & 1);
+        ptx::tc_fence_after();
       }
       if (it > 0 && __any_sync(0xffffffffu, need)) {
 #pragma unroll 1
@@ -383,33 +398,37 @@ struct DqSmem {
   static constexpr int KV_BYTES = NB * BKV * 128;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_DO = OFF_Q + Q_BYTES;
-  // ONE K/V stage: 112 KB per CTA so two CTAs share an SM (TMEM 2 x 256 columns) and one CTA's MMAs overlap the
-  // other's softmax phase; the exposed K/V load latency is covered the same way.
-  static constexpr int KV_STAGES = 1;
+  // One CTA per SM, pipelined inside the CTA (as the dK/dV kernel): three K/V stages keep two tile loads in flight, S/dP
+  // live in two TMEM buffers and dS in two smem buffers, so S,dP of key tile j+1 are computed while the softmax warps turn
+  // tile j into dS and dQ += dS_j K_j follows as soon as that is written.
+  static constexpr int KV_STAGES = 3;
   static constexpr int OFF_K = OFF_DO + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
-  static constexpr int OFF_DS = OFF_V + KV_STAGES * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_DS + BQ * 128;
+  static constexpr int DS_BYTES = BQ * 128;
+  static constexpr int OFF_DS = OFF_V + KV_STAGES * KV_BYTES;  // [2]
+  static constexpr int OFF_BAR = OFF_DS + 2 * DS_BYTES;
   static constexpr int TOTAL = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = 256;
+  static constexpr int TMEM_COLS = 512;  // [S0 | dP0 | S1 | dP1] (4 x 64) + dQ (HD)
 };
 
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(NTHREADS_BWD, 2)
+__global__ void __launch_bounds__(NTHREADS_BWD, 1)
     attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const AttnParams p) {
   using L = DqSmem<HD>;
   constexpr int NB = L::NB;
+  constexpr int NS = L::KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 3;
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ds_full = bars + 6;
-  uint64_t* dq_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* sdp_full = bars + 7;   // [2]
+  uint64_t* ds_full = bars + 9;    // [2]
+  uint64_t* ds_empty = bars + 11;  // [2]
+  uint64_t* dq_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
@@ -419,6 +438,11 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
   const int col0 = h * HD;
   int num_kv = (p.S + BKV - 1) / BKV;
   if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
+  auto next_j = [&](int j) {  // next processed key tile after j (num_kv = none)
+    ++j;
+    while (j < num_kv && tile_skipped(p, q0, j)) ++j;
+    return j;
+  };
 
   if (warp == 8) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -427,12 +451,15 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
     if (ptx::elect_one()) {
       if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
       ptx::mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NS; ++i) {
         ptx::mbar_init(&kv_full[i], 1);
         ptx::mbar_init(&kv_empty[i], 1);
       }
-      ptx::mbar_init(sdp_full, 1);
-      ptx::mbar_init(ds_full, 256);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&sdp_full[i], 1);
+        ptx::mbar_init(&ds_full[i], 256);
+        ptx::mbar_init(&ds_empty[i], 1);
+      }
       ptx::mbar_init(dq_done, 1);
       ptx::fence_barrier_init();
     }
@@ -441,7 +468,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
+  const uint32_t t_dq = tmem + 256;
 
   if (warp == 8) {
     if (ptx::elect_one()) {
@@ -449,14 +476,12 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
       load_tile(smem + L::OFF_DO, &tmdO, q_full, col0, row0, BQ, NB);
       int it = 0;
-      for (int j = 0; j < num_kv; ++j) {
-        if (tile_skipped(p, q0, j)) continue;
-        const int st = it % L::KV_STAGES;
-        ptx::mbar_wait(&kv_empty[st], ((it / L::KV_STAGES) & 1) ^ 1);
+      for (int j = next_j(-1); j < num_kv; j = next_j(j), ++it) {
+        const int st = it % NS;
+        ptx::mbar_wait(&kv_empty[st], ((it / NS) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
         load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
         load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
-        ++it;
       }
     }
   } else if (warp == 9) {
@@ -465,15 +490,15 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
       constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(BQ, HD, false, true);
       const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
       const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO);
-      const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS);
-      ptx::mbar_wait(q_full, 0);
-      int it = 0;
-      for (int j = 0; j < num_kv; ++j) {
-        if (tile_skipped(p, q0, j)) continue;
-        const int st = it % L::KV_STAGES;
+      int n_tiles = 0;
+      for (int j = next_j(-1); j < num_kv; j = next_j(j)) ++n_tiles;
+      // S = Q K^T and dP = dO V^T of pipeline slot `it` (K/V stage it % 3) into TMEM buffer it & 1
+      auto issue_sdp = [&](int it) {
+        const int st = it % NS, b = it & 1;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
         const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + st * L::KV_BYTES);
-        ptx::mbar_wait(&kv_full[st], (it / L::KV_STAGES) & 1);
+        const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
+        ptx::mbar_wait(&kv_full[st], (it / NS) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
@@ -487,17 +512,26 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
           ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(adO + blk * (BQ * 128) + off, 16, 1024),
                            ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
         }
-        ptx::mma_commit(sdp_full);
-        ptx::mbar_wait(ds_full, it & 1);
+        ptx::mma_commit(&sdp_full[b]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      if (n_tiles > 0) issue_sdp(0);
+      for (int it = 0; it < n_tiles; ++it) {
+        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose ds_full was awaited one iteration ago
+        if (it + 1 < n_tiles) issue_sdp(it + 1);
+        const int st = it % NS, b = it & 1;
+        const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
+        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + b * L::DS_BYTES);
+        ptx::mbar_wait(&ds_full[b], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           ptx::mma_bf16_ss(t_dq, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
                            ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024), idesc_dq, (it > 0 || kk > 0));
         }
-        ptx::mma_commit(&kv_empty[st]);
-        if (j == num_kv - 1) ptx::mma_commit(dq_done);
-        ++it;
+        ptx::mma_commit(&kv_empty[st]);  // the K/V stage and ...
+        ptx::mma_commit(&ds_empty[b]);   // ... the dS buffer may be overwritten once these MMAs are done
+        if (it == n_tiles - 1) ptx::mma_commit(dq_done);
       }
     }
   } else {
@@ -510,19 +544,17 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
     const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
     int it = 0;
-    auto next_j = [&](int j) {
-      ++j;
-      while (j < num_kv && tile_skipped(p, q0, j)) ++j;
-      return j;
-    };
     int j = next_j(-1);
     uint64_t kw = j < num_kv ? load_kword(p, n, j) : 0ull;
-    for (; j < num_kv;) {
+    for (; j < num_kv; ++it) {
       const int jn = next_j(j);
       const uint64_t kw_next = jn < num_kv ? load_kword(p, n, jn) : 0ull;
       const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, row_valid);
       const bool full = __all_sync(0xffffffffu, (half ? (bits >> 32) : (bits & 0xffffffffull)) == 0xffffffffull);
-      ptx::mbar_wait(sdp_full, it & 1);
+      const int b = it & 1;
+      const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
+      ptx::mbar_wait(&ds_empty[b], ((it >> 1) & 1) ^ 1);  // dQ of two slots ago has consumed this dS buffer
+      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);
       ptx::tc_fence_after();
       {
         uint32_t s[32], dp[32];
@@ -531,12 +563,11 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 2)
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
         recompute_half<false>(s, dp, bits, full, half, p.scale_log2, lse2, delta, pv, dsv);
-        store_half_row_sw128(smem + L::OFF_DS, tid, half, dsv);
+        store_half_row_sw128(smem + L::OFF_DS + b * L::DS_BYTES, tid, half, dsv);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ds_full);
-      ++it;
+      ptx::mbar_arrive(&ds_full[b]);
       j = jn;
       kw = kw_next;
     }
@@ -739,7 +770,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       const int i = qt * BQ + tid;
       const bool ok = qt <= last_qt && i < p.S;
       const int64_t grow = static_cast<int64_t>(n) * p.S + i;
-      lse2 = ok ? __ldg(p.lse + grow * p.H + h) * LOG2E : INFINITY;
+      lse2 = ok ? __ldg(p.lse + grow * p.H + h) : INFINITY;  // natural log here; scaled to base 2 at its use, one tile later
       delta = ok ? __ldg(p.delta + grow * p.H + h) : 0.f;
     };
     float lse2, delta;
@@ -764,7 +795,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
-        recompute_half<true>(s, dp, bits, full, half, p.scale_log2, lse2, delta, pv, dsv);
+        recompute_half<true>(s, dp, bits, full, half, p.scale_log2, lse2 * LOG2E, delta, pv, dsv);
         store_half_row_sw128(sP, tid, half, pv);
         store_half_row_sw128(sdS, tid, half, dsv);
       }

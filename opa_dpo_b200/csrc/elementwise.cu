@@ -728,6 +728,55 @@ __global__ void partial_to_bf16_kernel(const float* __restrict__ part, int split
   o.y = pack2(a.z, a.w);
   *reinterpret_cast<uint2*>(out + i) = o;
 }
+// Decode step, q|k|v projection: sum the split-K slices of [M, 3d] in slice order, rotate q and k (HF rotate_half pairing,
+// position pos_base + *cur for every row) on the fp32 sums and store bf16 — one launch instead of partial_to_bf16 + rope.
+// One thread per 4 consecutive columns of a head's lower half (plus their partners 64 columns on) for q and k; per 4
+// consecutive columns for v.
+__global__ void partial_qkv_rope_kernel(const float* __restrict__ part, int splits, int64_t slice, bf16* __restrict__ qkv,
+                                        int64_t M, int d, int hd, const float2* __restrict__ cs, int pos_base,
+                                        const int32_t* __restrict__ cur) {
+  const int half = hd >> 1;
+  const int rot_items = (2 * d / hd) * (half >> 2);  // per row: q and k heads x 4-column groups of the lower half
+  const int v_items = d >> 2;
+  const int per_row = rot_items + v_items;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * per_row) return;
+  const int64_t m = idx / per_row;
+  const int it = static_cast<int>(idx - m * per_row);
+  const int64_t row = m * 3 * d;
+  auto sum4 = [&](int64_t off) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 p = *reinterpret_cast<const float4*>(part + sp * slice + off);
+      a.x += p.x;
+      a.y += p.y;
+      a.z += p.z;
+      a.w += p.w;
+    }
+    return a;
+  };
+  auto store4 = [&](int64_t off, float4 a) {
+    uint2 o;
+    o.x = pack2(a.x, a.y);
+    o.y = pack2(a.z, a.w);
+    *reinterpret_cast<uint2*>(qkv + off) = o;
+  };
+  if (it >= rot_items) {
+    const int64_t off = row + 2 * d + (it - rot_items) * 4;
+    store4(off, sum4(off));
+    return;
+  }
+  const int g4 = half >> 2;
+  const int head = it / g4, j = (it - head * g4) * 4;
+  const int64_t off = row + head * hd + j;
+  const float4 lo = sum4(off), hi = sum4(off + half);
+  const int pos = pos_base + (cur ? *cur : 0);
+  const float2* c = cs + static_cast<int64_t>(pos) * half + j;
+  const float2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+  store4(off, make_float4(lo.x * c0.x - hi.x * c0.y, lo.y * c1.x - hi.y * c1.y, lo.z * c2.x - hi.z * c2.y, lo.w * c3.x - hi.w * c3.y));
+  store4(off + half, make_float4(hi.x * c0.x + lo.x * c0.y, hi.y * c1.x + lo.y * c1.y, hi.z * c2.x + lo.z * c2.y, hi.w * c3.x + lo.w * c3.y));
+}
+
 // x_out = bf16(sum(part) + res);  h = w * bf16(x_out * rstd)   (residual add fused with the next RMSNorm).
 // One 1024-thread CTA per row, 4 (or 8) consecutive columns per thread, all split slices loaded as independent float4s.
 constexpr int PRN_THREADS = 1024;
@@ -1364,6 +1413,13 @@ int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf1
   else
     partial_residual_rmsnorm_kernel<2><<<static_cast<unsigned>(M), PRN_THREADS, 0, s>>>(part, splits, M * d, res, x_out, w, h, d, eps);
   return check_launch("partial_residual_rmsnorm");
+}
+int partial_qkv_rope(const float* part, int splits, bf16* qkv, int64_t M, int d, int hd, const float2* cs, int pos_base,
+                     const int32_t* cur, cudaStream_t s) {
+  if (hd % 8 != 0 || d % hd != 0 || d % 4 != 0) return -1;
+  const int64_t items = M * ((2 * d / hd) * (hd >> 3) + (d >> 2));
+  partial_qkv_rope_kernel<<<blocks_for(items, 256), 256, 0, s>>>(part, splits, M * 3 * d, qkv, M, d, hd, cs, pos_base, cur);
+  return check_launch("partial_qkv_rope");
 }
 int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s) {
   partial_swiglu_kernel<<<blocks_for(M * F, 256), 256, 0, s>>>(part, splits, M * 2 * F, act, M, F);

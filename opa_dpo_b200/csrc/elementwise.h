@@ -134,6 +134,9 @@ int sample_pick(const float* partials, int splits, int N, int V, int top_k, floa
 int advance_counter(int32_t* cur, cudaStream_t s);
 // Deterministic reductions of gemm EPI_F32_PARTIAL slices [splits, M, N] fused with the op that follows the linear.
 int partial_to_bf16(const float* part, int splits, int64_t n, bf16* out, cudaStream_t s);
+// q|k|v slices [splits, M, 3d] -> bf16 [M, 3d] with RoPE (position pos_base + *cur) applied to the q and k heads on the fp32 sums
+int partial_qkv_rope(const float* part, int splits, bf16* qkv, int64_t M, int d, int hd, const float2* cs, int pos_base,
+                     const int32_t* cur, cudaStream_t s);
 int partial_residual_rmsnorm(const float* part, int splits, const bf16* res, bf16* x_out, const bf16* w, bf16* h, int64_t M,
                              int d, float eps, cudaStream_t s);
 int partial_swiglu(const float* part, int splits, bf16* act, int64_t M, int F, cudaStream_t s);

@@ -9,6 +9,7 @@
 
 #include "attention.h"
 #include "common.h"
+#include "decode_gemm.h"
 #include "gemm.h"
 
 namespace opadpo {
@@ -1156,6 +1157,10 @@ int Engine::set_option(const char* name, int64_t value) {
     share_prefix = value != 0;
     return 0;
   }
+  if (strcmp(name, "decode_swap_ab") == 0) {
+    decode_swap_ab = value != 0;
+    return 0;
+  }
   if (strcmp(name, "merge_rollout") == 0) {
     merge_rollout = value != 0;
     return 0;
@@ -1378,6 +1383,27 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   // partial sums of y = x W^T + (s x A^T) B^T into `part` [splits, N, out]; returns the split count
   auto linear_partial = [&](const LinearW& L, const bf16* x, int max_sp, int* nsplit) -> int {
     const int G = L.groups;
+    if (decode_swap_ab && !(lora && L.slot >= 0) && N <= 128) {
+      // merged (or adapter-free) weights: weight-streaming GEMM with the weight rows on the MMA's M (decode_gemm.cu)
+      DecodeGemmArgs a;
+      a.Mb = N;
+      a.N = L.out;
+      a.K = L.in;
+      a.x = x;
+      a.ldx = L.in;
+      a.W = L.W;
+      a.ldw = L.in;
+      a.part = part;
+      a.ldc = L.out;
+      a.splits = decode_gemm_pick_splits(N, L.out, L.in, max_sp > 0 ? std::min(max_sp, kMaxSplits) : kMaxSplits);
+      int rc = decode_gemm_launch(a, s);
+      if (rc != 0) {
+        set_error("%s", decode_gemm_last_error());
+        return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL;
+      }
+      *nsplit = a.splits;
+      return 0;
+    }
     if (lora && L.slot >= 0) {
       const int spA = splits_for(G * r, L.in, 0);
       GemmArgs a;
@@ -1427,7 +1453,24 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
   // fp32 logits with at most 2 K-splits: a + b is order independent, so argmax ties break exactly as torch.argmax
   auto head_and_pick = [&](const bf16* hrows) -> int {
     int sp = 1;
-    {
+    if (decode_swap_ab && N <= 128) {
+      DecodeGemmArgs a;
+      a.Mb = N;
+      a.N = V;
+      a.K = d;
+      a.x = hrows;
+      a.ldx = d;
+      a.W = lm_head;
+      a.ldw = d;
+      a.part = part;
+      a.ldc = V;
+      a.splits = sp = decode_gemm_pick_splits(N, V, d, 2);   // at most two slices: a + b is order independent (see above)
+      int rc = decode_gemm_launch(a, s);
+      if (rc != 0) {
+        set_error("%s", decode_gemm_last_error());
+        return rc <= -10 ? OPADPO_ECUDA : OPADPO_EINVAL;
+      }
+    } else {
       GemmArgs a;
       a.M = N;
       a.N = V;
@@ -1466,8 +1509,7 @@ int Engine::generate(int adapter, const float* images, int b, const int64_t* que
       const LlamaLayer& L = (*LL)[l];
       int sp = 1;
       EN_CHECK(linear_partial(L.qkv, hdn, 0, &sp));
-      EN_CHECK(partial_to_bf16(part, sp, Nl * 3 * d, qkvd, s));
-      EN_CHECK(rope_inplace(qkvd, 3 * d, N, 1, nullptr, S0 - 1, cur, 2 * H, hd, rope_cs, 0, s));
+      EN_CHECK(partial_qkv_rope(part, sp, qkvd, Nl, d, hd, rope_cs, S0 - 1, cur, s));
       EN_CHECK(decode_attention(qkvd, kc[l], vc[l], kmask, od, N, H, hd, S0 - 1, cur, S_max, scale, s));
       EN_CHECK(linear_partial(L.o, od, 0, &sp));
       EN_CHECK(partial_residual_rmsnorm(part, sp, xc, x1d, L.ln2, hdn, N, d, c.rms_eps, s));

@@ -119,6 +119,9 @@ class Engine {
   int hd = 0, v_hd = 0, P = 0, Kp = 0, r = 0;
   float lora_scale = 1.f;
   bool share_prefix = true;  // compute the image+query prefix once per sample for its K responses
+  // decode-step linears on merged / adapter-free weights go through the weight-streaming GEMM (decode_gemm.cu); 0 = the
+  // general kernel with split-K (A/B comparison, and batches above 128 sequences always take it)
+  bool decode_swap_ab = true;
   bool merge_rollout = true;  // rollout runs on W + (alpha/r) B A merged once per generate() call
   // Inference forwards of a FROZEN adapter (the reference pass of the DPO step, dpo_trainer.py:333-335) run on decoder
   // weights merged once, W' = W + (alpha/r) B A (what peft's merge_adapter does), so they carry no LoRA GEMMs at all.

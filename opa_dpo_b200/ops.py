@@ -83,6 +83,21 @@ def gemm(a1: torch.Tensor, b1: torch.Tensor, out: torch.Tensor, *, a2=None, b2=N
     return out
 
 
+def decode_gemm(x: torch.Tensor, w: torch.Tensor, *, splits: int = 0, max_splits: int = 0, alpha: float = 1.0):
+    """Weight-streaming decode GEMM: x [Mb <= 128, K] bf16, w [N, K] bf16 -> fp32 slices [splits, Mb, N] (sum over dim 0 =
+    alpha * x w^T). splits = 0 lets the library pick."""
+    lib = _lib.load()
+    _chk2d(x), _chk2d(w)
+    Mb, K = x.shape
+    N = w.shape[0]
+    cap = splits if splits > 0 else (max_splits if max_splits > 0 else 16)
+    part = torch.empty((cap, Mb, N), device=x.device, dtype=torch.float32)
+    used = ctypes.c_int32(0)
+    _lib.check(lib.opadpo_op_decode_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), Mb, N, K, splits, max_splits, alpha,
+                                         part.data_ptr(), ctypes.byref(used), ctypes.c_void_p(_stream())), "opadpo_op_decode_gemm")
+    return part[:used.value]
+
+
 def pack_mask(mask: torch.Tensor) -> torch.Tensor:
     """[N, S] bool/uint8 key-validity mask -> packed u64 bit words [N, ceil(S/64)] (int64 storage)."""
     lib = _lib.load()

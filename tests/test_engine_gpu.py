@@ -406,6 +406,30 @@ def test_rollout_suppress_eos_at_generation(do_sample):
     model.engine.close()
 
 
+def test_rollout_decode_gemm_variants_agree():
+    """Option decode_swap_ab: the weight-streaming decode GEMM + fused q|k|v reducer against the general split-K kernel
+    (option off): the same greedy ids on a peaked head — both equal to the oracle's — with and without a merged adapter."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY, BASE
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, peaked=40.0, trainable=False)
+    images, q, qm, _ = O.synthetic_batch(oc, 3, 16, 8, NAMES2, left_pad=3)
+    ids_ref, margin = O.greedy_generate(oc, w, lp, images, q, qm, 12)
+    assert margin > 0.05
+    for adapter, want in ((POLICY, ids_ref), (BASE, None)):
+        outs = []
+        for opt in (1, 0):
+            eng.set_option("decode_swap_ab", opt)
+            outs.append(eng.generate(adapter, images, q, qm, 12).cpu())
+        assert torch.equal(outs[0], outs[1])
+        if want is not None:
+            assert torch.equal(outs[0], want)
+    eng.set_option("decode_swap_ab", 1)
+    eng.set_option("merge_rollout", 0)          # unmerged adapter: the LoRA linears keep the general kernel, the head streams
+    assert torch.equal(eng.generate(POLICY, images, q, qm, 12).cpu(), ids_ref)
+    eng.close()
+
+
 def test_eval_generation_single_row_greedy():
     """The eval scripts' call shape (eval_llava_rlhf_coco/model_vqa.py:71-290: one image, one prompt, greedy,
     `model.generate(input_ids, images=..., do_sample=False, max_new_tokens=...)`): b = 1, no left padding, ids exact."""

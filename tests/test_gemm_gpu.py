@@ -264,3 +264,29 @@ def test_gemm_swiglu_epilogue_bit_identical_to_unfused(cluster):
     diff = (act.float() - want.float()).abs()
     # __expf vs torch.exp differ in the last bits of the exponential: allow one bf16 ulp on a few elements, none larger
     assert (diff > 0).float().mean().item() < 2e-3 and diff.max().item() <= 2.0 ** -7 * want.float().abs().max().item()
+
+
+@pytest.mark.parametrize("Mb,N,K,splits", [(32, 4096, 4096, 0), (32, 12288, 4096, 0), (1, 256, 64, 1), (5, 136, 200, 2),
+                                           (32, 22016, 4096, 0), (32, 4096, 11008, 0), (64, 520, 1000, 3), (100, 1000, 320, 0),
+                                           (128, 32000, 4096, 2), (17, 128, 4096, 16)])
+def test_decode_gemm_weight_streaming(Mb, N, K, splits):
+    """The rollout decode step's weight-streaming GEMM (weight rows on the MMA's M, activation rows on its N): the sum of
+    its fp32 split-K slices equals x W^T (fp32 matmul of the same bf16 operands, fp32 tolerance: 1e-3 of the row scale);
+    ragged N / K / Mb edges, every activation-tile width, run-to-run bit-identical."""
+    from opa_dpo_b200 import ops
+    x, w = _mk((Mb, K), 3, 0.5), _mk((N, K), 4, 0.05)
+    part = ops.decode_gemm(x, w, splits=splits, alpha=0.5)
+    part2 = ops.decode_gemm(x, w, splits=splits, alpha=0.5)
+    torch.cuda.synchronize()
+    assert part.shape[1:] == (Mb, N) and part.shape[0] >= 1 and (splits == 0 or part.shape[0] == splits)
+    assert torch.equal(part, part2)
+    ref = 0.5 * (x.float() @ w.float().t())
+    got = part.sum(0)
+    tol = 1e-3 * ref.abs().max().item() + 1e-6
+    assert (got - ref).abs().max().item() <= tol, (part.shape[0], (got - ref).abs().max().item(), tol)
+    # strided operands (views into wider buffers), as the engine passes them
+    xw = _mk((Mb, K + 64), 5, 0.5)
+    part3 = ops.decode_gemm(xw[:, 64:], w, splits=splits)
+    torch.cuda.synchronize()
+    ref3 = xw[:, 64:].float() @ w.float().t()
+    assert (part3.sum(0) - ref3).abs().max().item() <= 1e-3 * ref3.abs().max().item() + 1e-6
