@@ -307,6 +307,19 @@ def measure_rollout(model, cfg, dev, batch: int, new: int, peaks: dict, cpu_samp
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def collective_note(stepper, world):
+    """Which all-reduce of the LoRA-grad bucket actually ran (opa_dpo_b200/dist.py decides it collectively at start-up)."""
+    if world == 1 or stepper.overlap is None:
+        return "none"
+    ov = stepper.overlap
+    note = f"all-reduce(sum) of the LoRA-grad bucket once per step, overlapped with the backward: {ov.name}; transport {ov.transport}"
+    if getattr(ov, "fallback_reason", ""):
+        note += f" (NVLink kernel unavailable: {ov.fallback_reason[:200]})"
+    if hasattr(ov, "check"):
+        ov.check()
+    return note
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,6 +335,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "rollout"],
                     help="rollout: print BASELINE configs[3] (greedy rollout, batch 32, 256 new tokens) as the line itself")
     ap.add_argument("--no-rollout", action="store_true", help="train mode: skip the rollout object")
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs UNDER ncu only: warm-up as given (may be < 3), --steps device steps, then exit; prints no bench line")
     ap.add_argument("--rollout-batch", type=int, default=32)
     ap.add_argument("--rollout-new", type=int, default=256)
     ap.add_argument("--merge-frozen", type=int, default=int(os.environ.get("OPADPO_MERGE_FROZEN", str(MERGE_FROZEN_DEFAULT))),
@@ -333,7 +348,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    args.warmup = max(args.warmup, 3)
+    if not args.profile:
+        args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -448,6 +464,13 @@ def main():
     ms_total, (loss, norm) = timed(step_device, args.steps)
     launches = model.engine.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "note": "not a bench value", "ms_per_step_under_profiler": ms_total / args.steps,
+                              "launches_per_step": int(launches) // max(args.steps, 1)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     step_e2e()
     ms_e2e, loss_host = timed(step_e2e, args.steps)
 
@@ -498,8 +521,7 @@ def main():
                    "prefix_sharing": (not args.no_share_prefix), "merged_reference_adapter": bool(args.merge_frozen),
                    "fused_rope_epilogue": bool(args.fuse_rope), "fused_swiglu_epilogue": bool(args.fuse_swiglu),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
-                   "collective": "NCCL all-reduce(sum) of the fp32 LoRA-grad bucket once per step, issued as 33 per-layer slices "
-                                 "overlapped with the backward" if world > 1 else "none",
+                   "collective": collective_note(stepper, world),
                    "loss": float(loss.item()), "grad_norm": float(norm.item())},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_host},

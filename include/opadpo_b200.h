@@ -302,6 +302,37 @@ typedef struct opadpo_sampler {
 int opadpo_generate(opadpo_engine* e, int32_t adapter, const float* images, int32_t b, const int64_t* queries,
                     const uint8_t* qmask, int32_t Q, int32_t max_new, const opadpo_sampler* sampler, int64_t* out_ids,
                     void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient all-reduce as one kernel over NVLink / NVSwitch peer memory (csrc/collective.cu): the local fp32
+ * slice is packed to bf16 into a SYMMETRIC staging buffer (same allocation mapped by every rank: multicast address for NVLS,
+ * or per-peer addresses), summed over ranks with fp32 accumulation (multimem.ld_reduce in the switch; each rank reduces its
+ * 1/world share and multimem.st's the result to all ranks), and unpacked back into the fp32 slice. In place; the result is
+ * bit-identical on every rank. Replaces the DDP reduction of the LoRA gradients in the reference's accelerate loop
+ * (opadpo/dpo_models/rl_trainer.py:155-175; torch DDP over NCCL [UPSTREAM]). Every rank must issue the same sequence of
+ * calls (same count / blocks / epoch) on one stream per rank. Mapping the symmetric buffers is the caller's job (the Python
+ * host uses torch.distributed._symmetric_memory; any CUDA VMM / multicast-object exporter works).
+ *   signal_peer[r]: address, in THIS process, of rank r's signal area: uint32 [OPADPO_AR_MAX_BLOCKS][OPADPO_MAX_RANKS],
+ *                   zero before the first call; epoch: first call 1, then +2 per call (entry barrier = epoch, exit = epoch+1);
+ *   err_flag: host-visible (pinned) uint32 the kernel sets if a cross-rank wait exceeded timeout_ms (0 = 60 s) — the
+ *             kernel then finishes without hanging the GPU and the caller must treat the step as failed.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define OPADPO_MAX_RANKS 8
+#define OPADPO_AR_MAX_BLOCKS 256
+typedef struct opadpo_allreduce_desc {
+  int32_t rank, world;
+  float* grad;                             /* local fp32 slice, 32 B aligned */
+  void* stage_local;                       /* local address of the slice's bf16 staging, 16 B aligned */
+  uint64_t stage_mc;                       /* multicast address of the same staging bytes, or 0 (then stage_peer is used) */
+  uint64_t stage_peer[OPADPO_MAX_RANKS];   /* per-rank addresses of the same staging bytes (rank's own = stage_local) */
+  uint64_t signal_peer[OPADPO_MAX_RANKS];
+  int64_t count;                           /* elements, multiple of 8 */
+  uint32_t epoch;
+  int32_t blocks;                          /* CTAs (no shared memory: they co-reside with the backward's GEMM CTAs) */
+  uint32_t* err_flag;
+  int32_t timeout_ms;
+} opadpo_allreduce_desc;
+int opadpo_op_allreduce_bf16wire(const opadpo_allreduce_desc* d, void* stream);
+
 /* Measurement hooks (bench.py): between begin and end every tcgen05 GEMM launch is bracketed by CUDA events on its own
  * stream; end synchronises and returns the summed kernel time, the executed FLOPs (2*M*N*K with K padded to the 64-wide
  * k-block) and the launch count. */

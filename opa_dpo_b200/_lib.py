@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libopadpo_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 HASH_PATH = LIB_PATH + ".srchash"
-EXPECTED_ABI = 5     # opadpo_abi_version() of the library these bindings were written against
+EXPECTED_ABI = 6     # opadpo_abi_version() of the library these bindings were written against
 
 _lib = None
 
@@ -128,6 +128,18 @@ class Sampler(ctypes.Structure):
                 ("suppress_tokens", ctypes.c_int32 * 8)]
 
 
+MAX_RANKS = 8            # OPADPO_MAX_RANKS
+AR_MAX_BLOCKS = 256      # OPADPO_AR_MAX_BLOCKS
+
+
+class AllReduceDesc(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("grad", ctypes.c_void_p), ("stage_local", ctypes.c_void_p), ("stage_mc", ctypes.c_uint64),
+                ("stage_peer", ctypes.c_uint64 * MAX_RANKS), ("signal_peer", ctypes.c_uint64 * MAX_RANKS),
+                ("count", ctypes.c_int64), ("epoch", ctypes.c_uint32), ("blocks", ctypes.c_int32),
+                ("err_flag", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32)]
+
+
 class Config(ctypes.Structure):
     _fields_ = [
         ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32),
@@ -152,7 +164,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_backward_ent", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
     "opadpo_op_collate_responses", "opadpo_op_collate_queries", "opadpo_op_mask_images", "opadpo_op_attention_holes",
-    "opadpo_op_preprocess_images", "opadpo_op_truncate_after_eos",
+    "opadpo_op_preprocess_images", "opadpo_op_truncate_after_eos", "opadpo_op_allreduce_bf16wire",
 ]
 
 
@@ -188,6 +200,7 @@ def _declare_engine(lib):
     lib.opadpo_op_attention_holes.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.opadpo_op_truncate_after_eos.argtypes = [vp, vp, i32, i32, i64, i64, vp, i32, vp]
     lib.opadpo_op_preprocess_images.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.opadpo_op_allreduce_bf16wire.argtypes = [c.POINTER(AllReduceDesc), vp]
     lib.opadpo_prof_end.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64)]
     lib.opadpo_launch_count.argtypes = []
     lib.opadpo_launch_count.restype = c.c_int64

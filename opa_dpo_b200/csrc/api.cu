@@ -27,7 +27,7 @@ using namespace opadpo;
 extern "C" {
 
 const char* opadpo_last_error(void) { return g_last_error; }
-int opadpo_abi_version(void) { return 5; }
+int opadpo_abi_version(void) { return 6; }
 int64_t opadpo_launch_count(void) { return g_launches.load(); }
 
 int opadpo_gemm_n_tiles(int32_t N) { return gemm_num_n_tiles(N); }

@@ -8,6 +8,8 @@ semantics. World size 1 is identical to the reference.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -35,13 +37,16 @@ def allreduce_grad_bucket(flat_grad: torch.Tensor, group: Optional[dist.ProcessG
 
 
 class OverlappedGradAllReduce:
-    """All-reduce of the LoRA-grad bucket overlapped with the backward pass.
+    """All-reduce of the LoRA-grad bucket overlapped with the backward pass (NCCL; the fallback of `make_grad_allreduce`).
 
     The bucket is ordered layer by layer, and opadpo_backward reports (host callback) when the kernels that finish a
     layer's slice have been enqueued. Each slice is then all-reduced with async_op=True: ProcessGroupNCCL makes its own
     stream wait for everything enqueued so far on the compute stream, so the collective of layer l runs over NVLink while
     layers l-1..0 are still being differentiated. `finish()` makes the compute stream wait for all of them and returns
     the 1/world scale for the optimizer. Arm it only for the LAST micro-batch of an optimizer step."""
+
+    name = "NCCL all-reduce(sum), fp32, one slice per decoder layer"
+    transport = "NCCL"
 
     def __init__(self, engine, flat_grad: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
         self.engine, self.grad, self.group = engine, flat_grad, group
@@ -74,3 +79,161 @@ class OverlappedGradAllReduce:
         self.works = []
         self.armed = False
         return 1.0 / self.world
+
+
+class NvlGradAllReduce:
+    """The same overlap, with the collective done by this library's own kernel over NVLink / NVSwitch peer memory
+    (csrc/collective.cu, `opadpo_op_allreduce_bf16wire`) instead of NCCL: bf16 on the wire, the sum taken in the switch
+    (multimem.ld_reduce, fp32 accumulation) when the staging buffer has a multicast mapping, peer loads otherwise; no shared
+    memory, so its few CTAs run beside the backward's persistent GEMM CTAs instead of displacing them. The bf16 staging
+    bucket and the signal words are torch symmetric-memory allocations (torch only maps them; the kernel is ours).
+
+    Layers are grouped (`group_layers` decoder layers per launch; the last layers and the projector on their own with a
+    wide grid, since nothing is left to hide them behind). The reduced gradient is the bf16-rounded sum, identical on every
+    rank. Construct through `make_grad_allreduce`, which falls back to NCCL on every rank if any rank cannot map the buffers."""
+
+    name = "own NVLink kernel: bf16 wire, in-switch fp32 reduction (multimem), fused pack/reduce/broadcast/unpack"
+
+    def __init__(self, engine, flat_grad: torch.Tensor, group=None, group_layers: int = 4, blocks: int = 16,
+                 tail_blocks: int = 128):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.engine, self.grad, self.group = engine, flat_grad, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _lib.MAX_RANKS:
+            raise RuntimeError(f"NvlGradAllReduce: {self.world} ranks > {_lib.MAX_RANKS} (one NVLink domain)")
+        n = flat_grad.numel()
+        if n % 8 != 0 or flat_grad.data_ptr() % 32 != 0:
+            raise RuntimeError("NvlGradAllReduce: the gradient bucket must be 32 B-aligned with a multiple of 8 elements")
+        dev = flat_grad.device
+        pg = group if group is not None else dist.group.WORLD
+        self.stage = symm_mem.empty(n, dtype=torch.bfloat16, device=dev)
+        self.h_stage = symm_mem.rendezvous(self.stage, pg)
+        self.signal = symm_mem.empty(_lib.AR_MAX_BLOCKS * _lib.MAX_RANKS, dtype=torch.int32, device=dev)
+        self.signal.zero_()
+        self.h_signal = symm_mem.rendezvous(self.signal, pg)
+        torch.cuda.synchronize(dev)
+        self.h_signal.barrier()          # every rank's signal words are zero before anybody signals
+        torch.cuda.synchronize(dev)
+        self.stage_ptrs = [int(p) for p in self.h_stage.buffer_ptrs]
+        self.signal_ptrs = [int(p) for p in self.h_signal.buffer_ptrs]
+        use_mc = os.environ.get("OPADPO_DP_MULTICAST", "1") != "0"
+        self.mc_ptr = int(self.h_stage.multicast_ptr or 0) if use_mc else 0
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.epoch = 1
+        self.group_layers, self.blocks, self.tail_blocks = group_layers, blocks, tail_blocks
+        self.n_layers = None
+        self.ranges = {}
+        self.pending = None      # (offset, count) of finished layers not yet sent
+        self.launched = False
+        self.armed = False
+        self.done = torch.cuda.Event()
+        if engine is not None:           # engine=None: a bare all-reduce of `flat_grad` (tests drive _launch / finish directly)
+            engine.set_backward_callback(self._on_layer)
+
+    @property
+    def transport(self) -> str:
+        return "multimem (NVLS)" if self.mc_ptr else "peer loads/stores"
+
+    def _launch(self, off: int, cnt: int, blocks: int):
+        if cnt <= 0:
+            return
+        if off % 8 != 0 or cnt % 8 != 0:
+            raise RuntimeError(f"NvlGradAllReduce: slice [{off}, +{cnt}) is not a multiple of 8 elements")
+        L = self._lib
+        d = L.AllReduceDesc()
+        d.rank, d.world = self.rank, self.world
+        d.grad = self.grad.data_ptr() + 4 * off
+        d.stage_local = self.stage_ptrs[self.rank] + 2 * off
+        d.stage_mc = (self.mc_ptr + 2 * off) if self.mc_ptr else 0
+        for r in range(self.world):
+            d.stage_peer[r] = self.stage_ptrs[r] + 2 * off
+            d.signal_peer[r] = self.signal_ptrs[r]
+        d.count, d.epoch, d.blocks = cnt, self.epoch & 0xFFFFFFFF, blocks
+        d.err_flag = self.err.data_ptr()
+        d.timeout_ms = int(os.environ.get("OPADPO_DP_TIMEOUT_MS", "60000"))
+        cur = torch.cuda.current_stream(self.grad.device)
+        self.comm.wait_stream(cur)       # the slice is final in the compute stream's order
+        L.check(self.lib.opadpo_op_allreduce_bf16wire(ctypes.byref(d), ctypes.c_void_p(self.comm.cuda_stream)),
+                "allreduce_bf16wire")
+        self.epoch += 2
+        self.launched = True
+
+    def _range(self, layer: int):
+        if layer not in self.ranges:
+            self.ranges[layer] = self.engine.layer_grad_range(layer)
+        return self.ranges[layer]
+
+    def _on_layer(self, layer: int):
+        if not self.armed:
+            return
+        if self.n_layers is None:
+            self.n_layers = int(self.engine.cfg.n_layers)
+        off, cnt = self._range(layer)
+        if layer == self.n_layers:                       # projector: last in time, small
+            self._launch(off, cnt, self.tail_blocks)
+            return
+        # decoder layers arrive top-down and are adjacent in the bucket: grow the pending run downwards
+        if self.pending is None:
+            self.pending = (off, cnt)
+        else:
+            p_off, p_cnt = self.pending
+            if off + cnt != p_off:
+                self._launch(p_off, p_cnt, self.blocks)
+                self.pending = (off, cnt)
+            else:
+                self.pending = (off, p_cnt + cnt)
+        tail = layer <= 1
+        if tail or layer % self.group_layers == 0:
+            self._launch(self.pending[0], self.pending[1], self.tail_blocks if layer == 0 else self.blocks)
+            self.pending = None
+
+    def arm(self):
+        self.armed = True
+
+    def check(self):
+        """Raises if a cross-rank wait timed out in any launch so far (the kernel sets a host-visible flag instead of hanging)."""
+        code = int(self.err[0])
+        if code != 0:
+            raise RuntimeError(f"NvlGradAllReduce: a peer did not arrive within the timeout (flag {code & 0xFFFFFFFF:#x}); "
+                               "the reduced gradients of that step are invalid")
+
+    def finish(self) -> float:
+        self.check()
+        if self.pending is not None:
+            self._launch(self.pending[0], self.pending[1], self.tail_blocks)
+            self.pending = None
+        if not self.launched:            # not armed for this step: the whole bucket in one launch
+            self._launch(0, self.grad.numel(), self.tail_blocks)
+        self.done.record(self.comm)
+        torch.cuda.current_stream(self.grad.device).wait_event(self.done)
+        self.launched = False
+        self.armed = False
+        return 1.0 / self.world
+
+
+def make_grad_allreduce(engine, flat_grad: torch.Tensor, group=None):
+    """The overlapped gradient all-reduce of a data-parallel step: this library's NVLink kernel when every rank can map the
+    symmetric buffers (CUDA bucket, one NVLink domain, <= 8 ranks), else NCCL slices. The choice is collective: one rank
+    failing moves all of them to NCCL. OPADPO_DP_COLLECTIVE=nccl forces NCCL."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1 or not flat_grad.is_cuda or os.environ.get("OPADPO_DP_COLLECTIVE", "nvl") == "nccl":
+        return OverlappedGradAllReduce(engine, flat_grad, group)
+    impl, why = None, ""
+    try:
+        impl = NvlGradAllReduce(engine, flat_grad, group)
+    except Exception as e:   # noqa: BLE001 — any mapping failure means "use NCCL", decided together below
+        why = f"{type(e).__name__}: {e}"
+    ok = torch.tensor([1 if impl is not None else 0], device=flat_grad.device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        return impl
+    if impl is not None:
+        engine.set_backward_callback(None)
+    fb = OverlappedGradAllReduce(engine, flat_grad, group)
+    fb.fallback_reason = why or "another rank could not map the symmetric buffers"
+    return fb

@@ -16,7 +16,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import DpoPairDesc
-from .dist import OverlappedGradAllReduce, allreduce_grad_bucket
+from .dist import OverlappedGradAllReduce, allreduce_grad_bucket, make_grad_allreduce
 
 _DIV = {"reverse_kl": 0, "js_divergence": 1, "alpha_divergence": 2}
 
@@ -202,7 +202,7 @@ class DPOStepper:
         self.lr = args.learning_rate
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
-            self.overlap = OverlappedGradAllReduce(self.model.engine, self.model.flat_param.grad, process_group)
+            self.overlap = make_grad_allreduce(self.model.engine, self.model.flat_param.grad, process_group)
 
     @torch.no_grad()
     def reference_logprobs(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:

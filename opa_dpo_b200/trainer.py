@@ -29,7 +29,7 @@ from torch import Tensor
 from torch.utils.data import DataLoader
 
 from . import collate
-from .dist import OverlappedGradAllReduce, allreduce_grad_bucket
+from .dist import OverlappedGradAllReduce, allreduce_grad_bucket, make_grad_allreduce
 from .dpo import DPOArgs, FusedDPO
 
 FIRST_STEP_IDX = 1      # rl_trainer.py:46
@@ -86,7 +86,7 @@ class B200DPOTrainer:
         self.max_step = getattr(args, "max_step", B200DPOTrainer.max_step)
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
-            self.overlap = OverlappedGradAllReduce(self.model.engine, self.model.flat_param.grad, process_group)
+            self.overlap = make_grad_allreduce(self.model.engine, self.model.flat_param.grad, process_group)
 
     # ------------------------------------------------------------------ rollout (dpo_trainer.py:214-427)
     @torch.no_grad()

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--new", type=int, default=256)
     ap.add_argument("--runs", type=int, default=2)
+    ap.add_argument("--sample", action="store_true", help="temperature 1.0 / top_k 30 / top_p 0.95 (online_generate.sh:75-77) instead of greedy")
     args = ap.parse_args()
     cfg = EngineConfig()
     eng = Engine(cfg)
@@ -33,7 +34,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        out = eng.generate(POLICY, images, q, qm, new)
+        kw = dict(do_sample=True, top_k=30, top_p=0.95, temperature=1.0, seed=7) if args.sample else {}
+        out = eng.generate(POLICY, images, q, qm, new, **kw)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), out
