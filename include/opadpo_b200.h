@@ -258,6 +258,10 @@ int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 typedef void (*opadpo_layer_cb)(int32_t layer, void* user);
 int opadpo_engine_set_backward_callback(opadpo_engine* e, opadpo_layer_cb cb, void* user);
 int opadpo_engine_layer_grad_range(opadpo_engine* e, int32_t layer, int64_t* offset, int64_t* count);
+/* Make the engine accumulate the trainable adapter's gradients in a caller-owned device buffer of `count` >= n_train floats
+ * (e.g. a symmetric-memory allocation every data-parallel rank maps, so the all-reduce can run in place). The current
+ * gradients are copied over, the engine's own bucket is freed; the buffer must outlive the engine. */
+int opadpo_engine_adopt_grad_buffer(opadpo_engine* e, float* buffer, int64_t count);
 /* After the caller modified the fp32 masters directly (e.g. optimizer state restore): refresh the bf16 shadows. */
 int opadpo_engine_sync_shadow(opadpo_engine* e, void* stream);
 
@@ -330,6 +334,9 @@ typedef struct opadpo_allreduce_desc {
   int32_t blocks;                          /* CTAs (no shared memory: they co-reside with the backward's GEMM CTAs) */
   uint32_t* err_flag;
   int32_t timeout_ms;
+  int32_t fp32_in_place;                   /* 1: no staging — `grad` is itself a symmetric allocation and stage_local / stage_mc /
+                                              stage_peer are the mappings of THIS fp32 slice; exact fp32 sums, half the HBM traffic
+                                              of the bf16-wire form (which needs no symmetric gradient bucket) */
 } opadpo_allreduce_desc;
 int opadpo_op_allreduce_bf16wire(const opadpo_allreduce_desc* d, void* stream);
 

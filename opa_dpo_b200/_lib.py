@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libopadpo_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 HASH_PATH = LIB_PATH + ".srchash"
-EXPECTED_ABI = 6     # opadpo_abi_version() of the library these bindings were written against
+EXPECTED_ABI = 7     # opadpo_abi_version() of the library these bindings were written against
 
 _lib = None
 
@@ -137,7 +137,7 @@ class AllReduceDesc(ctypes.Structure):
                 ("grad", ctypes.c_void_p), ("stage_local", ctypes.c_void_p), ("stage_mc", ctypes.c_uint64),
                 ("stage_peer", ctypes.c_uint64 * MAX_RANKS), ("signal_peer", ctypes.c_uint64 * MAX_RANKS),
                 ("count", ctypes.c_int64), ("epoch", ctypes.c_uint32), ("blocks", ctypes.c_int32),
-                ("err_flag", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32)]
+                ("err_flag", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32), ("fp32_in_place", ctypes.c_int32)]
 
 
 class Config(ctypes.Structure):
@@ -161,6 +161,7 @@ EXPORTED_SYMBOLS = [
     "opadpo_engine_load_tensor", "opadpo_engine_load_lora", "opadpo_engine_export_lora", "opadpo_engine_lora_shape",
     "opadpo_engine_set_trainable", "opadpo_engine_buffers", "opadpo_engine_lora_offsets", "opadpo_engine_sync_shadow",
     "opadpo_engine_set_option", "opadpo_engine_set_backward_callback", "opadpo_engine_layer_grad_range",
+    "opadpo_engine_adopt_grad_buffer",
     "opadpo_forward_logprobs", "opadpo_backward", "opadpo_backward_ent", "opadpo_zero_grad", "opadpo_optimizer_step", "opadpo_generate",
     "opadpo_launch_count", "opadpo_prof_begin", "opadpo_prof_end",
     "opadpo_op_collate_responses", "opadpo_op_collate_queries", "opadpo_op_mask_images", "opadpo_op_attention_holes",
@@ -186,6 +187,7 @@ def _declare_engine(lib):
     lib.opadpo_engine_set_option.argtypes = [vp, c.c_char_p, i64]
     lib.opadpo_engine_set_backward_callback.argtypes = [vp, LAYER_CB, vp]
     lib.opadpo_engine_layer_grad_range.argtypes = [vp, i32, c.POINTER(i64), c.POINTER(i64)]
+    lib.opadpo_engine_adopt_grad_buffer.argtypes = [vp, vp, i64]
     lib.opadpo_forward_logprobs.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, c.POINTER(vp), i32, f32, vp, vp,
                                             i32, vp]
     lib.opadpo_backward.argtypes = [vp, i32, vp, vp]

@@ -27,7 +27,7 @@ using namespace opadpo;
 extern "C" {
 
 const char* opadpo_last_error(void) { return g_last_error; }
-int opadpo_abi_version(void) { return 6; }
+int opadpo_abi_version(void) { return 7; }
 int64_t opadpo_launch_count(void) { return g_launches.load(); }
 
 int opadpo_gemm_n_tiles(int32_t N) { return gemm_num_n_tiles(N); }
@@ -314,6 +314,10 @@ int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value) 
 int opadpo_engine_set_backward_callback(opadpo_engine* e, opadpo_layer_cb cb, void* user) {
   ENGINE_GUARD(e);
   return e->impl->set_backward_callback(cb, user);
+}
+int opadpo_engine_adopt_grad_buffer(opadpo_engine* e, float* buffer, int64_t count) {
+  ENGINE_GUARD(e);
+  return e->impl->adopt_grad_buffer(buffer, count);
 }
 int opadpo_engine_layer_grad_range(opadpo_engine* e, int32_t layer, int64_t* offset, int64_t* count) {
   ENGINE_GUARD(e);

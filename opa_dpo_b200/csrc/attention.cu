@@ -602,72 +602,116 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   }
 }
 
-// ---------------------------------------------------------------- dK, dV: one CTA per key tile, loops over query tiles
+// ---------------------------------------------------------------- dK, dV: one CTA per 128-key tile, loops over 64-row query tiles
+// TRANSPOSED scores: S^T = K Q^T and dP^T = V dO^T put the KEYS on the 128 TMEM lanes and the query rows on the columns, so
+//   * the resident operand is the big one (K, V: 128 rows) and the streamed one the small one (Q, dO: 64 rows = 32 KB per
+//     pipeline slot for 4 GEMM-units; the [64 keys x 128 queries] form streamed 64 KB for the same work),
+//   * P^T / dS^T land in shared memory as K-major A operands (row = key) and dV += P^T dO, dK += dS^T Q accumulate as
+//     [128 keys x HD] tiles whose rows are contiguous in global memory (16 B epilogue stores, no transposed 2 B scatter),
+//   * three Q/dO stages fit (K,V 64 KB + 3 x 32 KB + P^T,dS^T 2 x 32 KB), so the load of slot it+2 no longer waits for the
+//     accumulate MMAs of slot it to release its stage.
+// The per-query statistics (lse, delta) vary along the COLUMNS here: they are staged through shared memory once per slot
+// and read back as broadcast float4 loads.
+constexpr int BKT = 128;  // keys per CTA
+constexpr int BQT = 64;   // query rows per pipeline slot
+
 template <int HD>
 struct DkvSmem {
   static constexpr int NB = HD / 64;
-  static constexpr int Q_BYTES = NB * BQ * 128;
-  static constexpr int KV_BYTES = NB * BKV * 128;
+  static constexpr int KV_BYTES = NB * BKT * 128;
+  static constexpr int Q_BYTES = NB * BQT * 128;
+  static constexpr int NS = 3;
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [2]
-  static constexpr int OFF_DO = OFF_Q + 2 * Q_BYTES;   // [2]
-  static constexpr int PD_BYTES = BQ * 128;
-  static constexpr int OFF_P = OFF_DO + 2 * Q_BYTES;   // [2]
+  static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [NS]
+  static constexpr int OFF_DO = OFF_Q + NS * Q_BYTES;  // [NS]
+  static constexpr int PD_BYTES = BKT * 128;           // 128 key rows x 64 query columns, bf16
+  static constexpr int OFF_P = OFF_DO + NS * Q_BYTES;  // [2]
   static constexpr int OFF_DS = OFF_P + 2 * PD_BYTES;  // [2]
-  static constexpr int OFF_BAR = OFF_DS + 2 * PD_BYTES;
+  static constexpr int OFF_STAT = OFF_DS + 2 * PD_BYTES;  // float [2][2][BQT]: -lse*log2(e) | delta of the slot's query rows
+  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * BQT * 4;
   static constexpr int TOTAL = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = 512;  // S,dP double-buffered (4 x 64) + dV^T + dK^T (2 x 64)
+  static constexpr int TMEM_COLS = 512;  // S^T,dP^T double-buffered (4 x 64) + dV + dK (2 x HD)
 };
+static_assert(DkvSmem<128>::TOTAL <= 232448, "dK/dV kernel shared memory");
 
-// Software-pipelined: S/dP live in two TMEM buffers and P/dS in two smem buffers, so the tensor pipe computes
-// S,dP of query tile i+1 while the softmax threads turn tile i into P,dS, and dV^T,dK^T of tile i overlap the
-// softmax of tile i+1 (one CTA per SM: the overlap has to come from inside the CTA).
+// p^T = exp2(s*scale_log2 - lse2[q]), ds' = p^T * (dp - delta[q]) for 32 query columns of one key row; nl / dl point at
+// the 32 per-column statistics in shared memory (every lane reads the same addresses: broadcast).
+__device__ __forceinline__ void recompute_half_t(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint32_t m32, bool full,
+                                                 float scale_log2, const float* nl, const float* dl, float (&pv)[32],
+                                                 float (&dsv)[32]) {
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(nl + c4);
+    const float4 d = *reinterpret_cast<const float4*>(dl + c4);
+    const float na[4] = {a.x, a.y, a.z, a.w}, da[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c4 + e;
+      float pr = ptx::ex2_approx(fmaf(__uint_as_float(s[c]), scale_log2, na[e]));
+      if (!full) pr = ((m32 >> c) & 1u) ? pr : 0.f;
+      pv[c] = pr;
+      dsv[c] = pr * (__uint_as_float(dp[c]) - da[e]);
+    }
+  }
+}
+
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                          const AttnParams p) {
-  static_assert(HD == 128, "dK^T/dV^T accumulate with M = HD = 128 TMEM lanes");
+  static_assert(HD == 128, "dV / dK accumulate as [128 keys x HD] with HD = 128 TMEM columns each");
   using L = DkvSmem<HD>;
   constexpr int NB = L::NB;
+  constexpr int NS = L::NS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [2]
-  uint64_t* qdo_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;    // [2]
-  uint64_t* pds_full = bars + 7;    // [2]
-  uint64_t* pds_empty = bars + 9;   // [2]
-  uint64_t* done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qdo_full = bars + 1;    // [3]
+  uint64_t* qdo_empty = bars + 4;   // [3]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* pds_full = bars + 9;    // [2]
+  uint64_t* pds_empty = bars + 11;  // [2]
+  uint64_t* done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* stat = reinterpret_cast<float*>(smem + L::OFF_STAT);
 
   const int warp = threadIdx.x >> 5;
   const int j = blockIdx.x;
   const int h = blockIdx.y, n = blockIdx.z;
-  const int k0 = j * BKV;
+  const int k0 = j * BKT;
   const int col0 = h * HD;
-  const int nq = (p.S + BQ - 1) / BQ;
-  const int i0 = CAUSAL ? (k0 / BQ) : 0;
-  // query tiles of OTHER response segments never see this key tile (shared-prefix packing): skip them
-  int last_qt = nq - 1;
-  while (last_qt > i0 && tile_skipped(p, last_qt * BQ, j)) --last_qt;
-  auto next_tile = [&](int qt) {  // next processed query tile after qt (last_qt + 1 = none)
-    ++qt;
-    while (qt <= last_qt && tile_skipped(p, qt * BQ, j)) ++qt;
-    return qt;
-  };
+  // query tiles that can see any key of this tile: from the causal diagonal to the end of the sequence, or, when every key
+  // lies inside response segments (shared-prefix packing), to the end of the last key's segment
+  const int first_qt = CAUSAL ? (k0 / BQT) : 0;
+  int hi_max = p.S;
+  if (p.segR > 0 && k0 >= p.S0) {
+    const int k_last = min(k0 + BKT, p.S) - 1;
+    hi_max = min(p.S, p.S0 + ((k_last - p.S0) / p.segR + 1) * p.segR);
+  }
+  const int last_qt = (hi_max - 1) / BQT;
+  const int n_slots = last_qt - first_qt + 1;  // >= 1: the diagonal tile
 
   if (warp == 8) {
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmdO);
+      ptx::prefetch_tmap(&tmK);
+      ptx::prefetch_tmap(&tmV);
+    }
+    __syncwarp();
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
     ptx::tmem_relinquish();
   } else if (warp == 9) {
     if (ptx::elect_one()) {
       if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
       ptx::mbar_init(kv_full, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NS; ++i) {
         ptx::mbar_init(&qdo_full[i], 1);
         ptx::mbar_init(&qdo_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&sdp_full[i], 1);
         ptx::mbar_init(&pds_full[i], 256);
         ptx::mbar_init(&pds_empty[i], 1);
@@ -680,114 +724,117 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: [S0 | dP0 | S1 | dP1 | dV^T | dK^T], 64 each
-  const uint32_t t_dv = tmem + 256, t_dk = tmem + 320;
+  // TMEM columns: [S^T 0 | dP^T 0 | S^T 1 | dP^T 1] (64 each) | dV (HD) | dK (HD)
+  const uint32_t t_dv = tmem + 256, t_dk = tmem + 256 + HD;
 
   if (warp == 8) {
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * L::KV_BYTES);
-      load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKV, NB);
-      load_tile(smem + L::OFF_V, &tmV, kv_full, col0, n * p.S + k0, BKV, NB);
-      int it = 0;
-      for (int qt = i0; qt <= last_qt; qt = next_tile(qt)) {
-        const int st = it & 1;
-        ptx::mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+      load_tile(smem + L::OFF_K, &tmK, kv_full, col0, n * p.S + k0, BKT, NB);
+      load_tile(smem + L::OFF_V, &tmV, kv_full, col0, n * p.S + k0, BKT, NB);
+      for (int it = 0; it < n_slots; ++it) {
+        const int st = it % NS;
+        ptx::mbar_wait(&qdo_empty[st], ((it / NS) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&qdo_full[st], 2 * L::Q_BYTES);
-        const int r0 = n * p.S + qt * BQ;
-        load_tile(smem + L::OFF_Q + st * L::Q_BYTES, &tmQ, &qdo_full[st], col0, r0, BQ, NB);
-        load_tile(smem + L::OFF_DO + st * L::Q_BYTES, &tmdO, &qdo_full[st], col0, r0, BQ, NB);
-        ++it;
+        const int r0 = n * p.S + (first_qt + it) * BQT;
+        load_tile(smem + L::OFF_Q + st * L::Q_BYTES, &tmQ, &qdo_full[st], col0, r0, BQT, NB);
+        load_tile(smem + L::OFF_DO + st * L::Q_BYTES, &tmdO, &qdo_full[st], col0, r0, BQT, NB);
       }
     }
   } else if (warp == 9) {
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, false, false);
-      constexpr uint32_t idesc_t = ptx::make_idesc_bf16(HD, BKV, true, true);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BKT, BQT, false, false);
+      constexpr uint32_t idesc_acc = ptx::make_idesc_bf16(BKT, HD, false, true);
       const uint32_t aK = ptx::smem_u32(smem + L::OFF_K);
       const uint32_t aV = ptx::smem_u32(smem + L::OFF_V);
-      // S = Q K^T and dP = dO V^T of pipeline slot `it` into TMEM buffer it & 1
+      // S^T = K Q^T and dP^T = V dO^T of pipeline slot `it` (Q/dO stage it % 3) into TMEM buffer it & 1
       auto issue_sdp = [&](int it) {
-        const int st = it & 1;
+        const int st = it % NS, b = it & 1;
         const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
         const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
-        const uint32_t t_s = tmem + st * 128, t_dp = t_s + 64;
-        ptx::mbar_wait(&qdo_full[st], (it >> 1) & 1);
+        const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
+        ptx::mbar_wait(&qdo_full[st], (it / NS) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const int blk = kk >> 2, off = (kk & 3) * 32;
-          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
-                           ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+          ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(aK + blk * (BKT * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aQ + blk * (BQT * 128) + off, 16, 1024), idesc_s, kk > 0);
         }
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const int blk = kk >> 2, off = (kk & 3) * 32;
-          ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(adO + blk * (BQ * 128) + off, 16, 1024),
-                           ptx::make_smem_desc(aV + blk * (BKV * 128) + off, 16, 1024), idesc_s, kk > 0);
+          ptx::mma_bf16_ss(t_dp, ptx::make_smem_desc(aV + blk * (BKT * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(adO + blk * (BQT * 128) + off, 16, 1024), idesc_s, kk > 0);
         }
-        ptx::mma_commit(&sdp_full[st]);
+        ptx::mma_commit(&sdp_full[b]);
       };
       ptx::mbar_wait(kv_full, 0);
       issue_sdp(0);
-      int it = 0;
-      for (int qt = i0; qt <= last_qt; ++it) {
-        const int nxt = next_tile(qt);
-        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose pds_full was awaited below
-        if (nxt <= last_qt) issue_sdp(it + 1);
-        const int st = it & 1;
+      for (int it = 0; it < n_slots; ++it) {
+        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose pds_full was awaited one iteration ago
+        if (it + 1 < n_slots) issue_sdp(it + 1);
+        const int st = it % NS, b = it & 1;
         const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
         const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
-        const uint32_t aP = ptx::smem_u32(smem + L::OFF_P + st * L::PD_BYTES);
-        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + st * L::PD_BYTES);
-        ptx::mbar_wait(&pds_full[st], (it >> 1) & 1);
+        const uint32_t aP = ptx::smem_u32(smem + L::OFF_P + b * L::PD_BYTES);
+        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + b * L::PD_BYTES);
+        ptx::mbar_wait(&pds_full[b], (it >> 1) & 1);
         ptx::tc_fence_after();
-        // dV^T[hd, keys] += dO^T P ; dK^T[hd, keys] += Q^T dS   (contraction over the 128 query rows)
+        // dV[keys, hd] += P^T dO ; dK[keys, hd] += dS^T Q   (contraction over the slot's 64 query rows; B operands MN-major)
 #pragma unroll
-        for (int kk = 0; kk < BQ / 16; ++kk) {
-          ptx::mma_bf16_ss(t_dv, ptx::make_smem_desc(adO + kk * 2048, BQ * 128, 1024),
-                           ptx::make_smem_desc(aP + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
+        for (int kk = 0; kk < BQT / 16; ++kk) {
+          ptx::mma_bf16_ss(t_dv, ptx::make_smem_desc(aP + kk * 32, 16, 1024),
+                           ptx::make_smem_desc(adO + kk * 2048, BQT * 128, 1024), idesc_acc, (it > 0 || kk > 0));
         }
 #pragma unroll
-        for (int kk = 0; kk < BQ / 16; ++kk) {
-          ptx::mma_bf16_ss(t_dk, ptx::make_smem_desc(aQ + kk * 2048, BQ * 128, 1024),
-                           ptx::make_smem_desc(adS + kk * 2048, BQ * 128, 1024), idesc_t, (it > 0 || kk > 0));
+        for (int kk = 0; kk < BQT / 16; ++kk) {
+          ptx::mma_bf16_ss(t_dk, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
+                           ptx::make_smem_desc(aQ + kk * 2048, BQT * 128, 1024), idesc_acc, (it > 0 || kk > 0));
         }
         ptx::mma_commit(&qdo_empty[st]);  // Q/dO stage and ...
-        ptx::mma_commit(&pds_empty[st]);  // ... the P/dS buffer may be overwritten once these MMAs are done
-        if (qt == last_qt) ptx::mma_commit(done);
-        qt = nxt;
+        ptx::mma_commit(&pds_empty[b]);   // ... the P^T/dS^T buffer may be overwritten once these MMAs are done
+        if (it == n_slots - 1) ptx::mma_commit(done);
       }
     }
   } else {
-    // two threads per TMEM lane: warp & 3 selects the 32 lanes, warp >> 2 the 32-column half of the 64-key tile
+    // two threads per TMEM lane (= key): warp & 3 selects the 32 lanes, warp >> 2 the 32-column half of the 64 query rows
     const int half = warp >> 2;
-    const int tid = (warp & 3) * 32 + (threadIdx.x & 31);
+    const int tid = (warp & 3) * 32 + (threadIdx.x & 31);  // key row within the tile
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    int it = 0;
-    const uint64_t kw = load_kword(p, n, j);  // one key tile per CTA: the validity word is loop invariant
-    // per-row statistics of the NEXT query tile are fetched while this one is being worked on
-    auto load_stats = [&](int qt, float& lse2, float& delta) {
-      const int i = qt * BQ + tid;
-      const bool ok = qt <= last_qt && i < p.S;
-      const int64_t grow = static_cast<int64_t>(n) * p.S + i;
-      lse2 = ok ? __ldg(p.lse + grow * p.H + h) : INFINITY;  // natural log here; scaled to base 2 at its use, one tile later
-      delta = ok ? __ldg(p.delta + grow * p.H + h) : 0.f;
+    const int k = k0 + tid;
+    // queries that may see key k: [lo_k, hi_k) (causal from the diagonal; a response-segment key only inside its segment)
+    const bool key_ok = k < p.S && ((load_kword(p, n, k >> 6) >> (k & 63)) & 1ull);
+    const int lo_k = CAUSAL ? k : 0;
+    int hi_k = p.S;
+    if (p.segR > 0 && k >= p.S0) hi_k = min(p.S, p.S0 + ((k - p.S0) / p.segR + 1) * p.segR);
+    if (!key_ok) hi_k = 0;
+    // per-query statistics of the NEXT slot are fetched while this one is being worked on (threads 0..127 of the group:
+    // 64 x -lse*log2(e), 64 x delta)
+    const int sidx = threadIdx.x & 63;
+    const bool loads_stat = threadIdx.x < 2 * BQT;
+    auto load_stat = [&](int it) -> float {
+      const int i = (first_qt + it) * BQT + sidx;
+      if (!loads_stat || it >= n_slots || i >= p.S) return threadIdx.x < BQT ? -INFINITY : 0.f;
+      const int64_t g = (static_cast<int64_t>(n) * p.S + i) * p.H + h;
+      return threadIdx.x < BQT ? -__ldg(p.lse + g) * LOG2E : __ldg(p.delta + g);
     };
-    float lse2, delta;
-    load_stats(i0, lse2, delta);
-    for (int qt = i0; qt <= last_qt;) {
-      const int qn = next_tile(qt);
-      float lse2_n, delta_n;
-      load_stats(qn, lse2_n, delta_n);
-      const int st = it & 1;
-      const uint32_t t_s = tmem + st * 128, t_dp = t_s + 64;
-      uint8_t* sP = smem + L::OFF_P + st * L::PD_BYTES;
-      uint8_t* sdS = smem + L::OFF_DS + st * L::PD_BYTES;
-      const int i = qt * BQ + tid;
-      const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, i < p.S);
-      const bool full = __all_sync(0xffffffffu, (half ? (bits >> 32) : (bits & 0xffffffffull)) == 0xffffffffull);
-      ptx::mbar_wait(&pds_empty[st], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P/dS buffer two slots ago are done
-      ptx::mbar_wait(&sdp_full[st], (it >> 1) & 1);
+    float stat_next = load_stat(0);
+    for (int it = 0; it < n_slots; ++it) {
+      const int b = it & 1;
+      float* st_buf = stat + b * 2 * BQT;
+      if (loads_stat) st_buf[threadIdx.x] = stat_next;
+      stat_next = load_stat(it + 1);
+      const int qbase = (first_qt + it) * BQT + half * 32;
+      const int lo = min(max(lo_k - qbase, 0), 32), hi = min(max(hi_k - qbase, 0), 32);
+      const uint32_t m32 = hi > lo ? ((hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+      const bool full = __all_sync(0xffffffffu, m32 == ~0u);
+      const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
+      uint8_t* sP = smem + L::OFF_P + b * L::PD_BYTES;
+      uint8_t* sdS = smem + L::OFF_DS + b * L::PD_BYTES;
+      ptx::named_bar_sync(1, 256);  // this slot's statistics are in shared memory (two buffers: the previous slot's are still being read)
+      ptx::mbar_wait(&pds_empty[b], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P^T/dS^T buffer two slots ago are done
+      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);
       ptx::tc_fence_after();
       {
         uint32_t s[32], dp[32];
@@ -795,34 +842,42 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::tmem_ld32(t_dp + lane_off + half * 32, dp);
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
-        recompute_half<true>(s, dp, bits, full, half, p.scale_log2, lse2 * LOG2E, delta, pv, dsv);
+        recompute_half_t(s, dp, m32, full, p.scale_log2, st_buf + half * 32, st_buf + BQT + half * 32, pv, dsv);
         store_half_row_sw128(sP, tid, half, pv);
         store_half_row_sw128(sdS, tid, half, dsv);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&pds_full[st]);
-      ++it;
-      qt = qn;
-      lse2 = lse2_n;
-      delta = delta_n;
+      ptx::mbar_arrive(&pds_full[b]);
     }
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
-    // thread == head-dim index; columns == keys
-    const int nkeys = min(BKV, p.S - k0);
-    {
+    // thread == key row; this thread's half of the head dimension: 64 contiguous bf16 of dV and of dK
+    const bool row_ok = k < p.S;
+    __nv_bfloat16* vrow = p.dv + (static_cast<int64_t>(n) * p.S + k) * p.ld_dqkv + col0 + half * 64;
+    __nv_bfloat16* krow = p.dk + (static_cast<int64_t>(n) * p.S + k) * p.ld_dqkv + col0 + half * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
       uint32_t tv[32], tk[32];
-      ptx::tmem_ld32(t_dv + lane_off + half * 32, tv);
-      ptx::tmem_ld32(t_dk + lane_off + half * 32, tk);
+      ptx::tmem_ld32(t_dv + lane_off + half * 64 + c * 32, tv);
+      ptx::tmem_ld32(t_dk + lane_off + half * 64 + c * 32, tk);
       ptx::tmem_ld_wait();
+      if (row_ok) {
+        uint4* dv4 = reinterpret_cast<uint4*>(vrow + c * 32);
+        uint4* dk4 = reinterpret_cast<uint4*>(krow + c * 32);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int key = half * 32 + c;
-        if (key < nkeys) {
-          const int64_t off = (static_cast<int64_t>(n) * p.S + k0 + key) * p.ld_dqkv + col0 + tid;
-          p.dv[off] = __float2bfloat16(__uint_as_float(tv[c]));
-          p.dk[off] = __float2bfloat16(__uint_as_float(tk[c]) * p.scale);
+        for (int q = 0; q < 4; ++q) {
+          uint4 u, w;
+          u.x = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 0]), __uint_as_float(tv[q * 8 + 1]));
+          u.y = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 2]), __uint_as_float(tv[q * 8 + 3]));
+          u.z = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 4]), __uint_as_float(tv[q * 8 + 5]));
+          u.w = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 6]), __uint_as_float(tv[q * 8 + 7]));
+          w.x = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 0]) * p.scale, __uint_as_float(tk[q * 8 + 1]) * p.scale);
+          w.y = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 2]) * p.scale, __uint_as_float(tk[q * 8 + 3]) * p.scale);
+          w.z = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 4]) * p.scale, __uint_as_float(tk[q * 8 + 5]) * p.scale);
+          w.w = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 6]) * p.scale, __uint_as_float(tk[q * 8 + 7]) * p.scale);
+          dv4[q] = u;
+          dk4[q] = w;
         }
       }
       __syncwarp();
@@ -940,6 +995,11 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
   if (make_maps(a, a.q, a.ld_qkv, BQ, &mq) || make_maps(a, a.dO, a.ld_do, BQ, &mdo) ||
       make_maps(a, a.k, a.ld_qkv, BKV, &mk) || make_maps(a, a.v, a.ld_qkv, BKV, &mv))
     return -6;
+  // the dK/dV kernel keeps 128-key tiles resident and streams 64-row query tiles
+  CUtensorMap mq64, mdo64, mk128, mv128;
+  if (make_maps(a, a.q, a.ld_qkv, BQT, &mq64) || make_maps(a, a.dO, a.ld_do, BQT, &mdo64) ||
+      make_maps(a, a.k, a.ld_qkv, BKT, &mk128) || make_maps(a, a.v, a.ld_qkv, BKT, &mv128))
+    return -6;
   const int64_t T = static_cast<int64_t>(a.N) * a.S;
   {
     const int64_t warps = T * a.H;
@@ -958,8 +1018,8 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 gq((a.S + BQ - 1) / BQ, a.H, a.N);
   kdq<<<gq, NTHREADS_BWD, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
-  dim3 gk((a.S + BKV - 1) / BKV, a.H, a.N);
-  kdkv<<<gk, NTHREADS_BWD, DkvSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  dim3 gk((a.S + BKT - 1) / BKT, a.H, a.N);
+  kdkv<<<gk, NTHREADS_BWD, DkvSmem<HD>::TOTAL, stream>>>(mq64, mdo64, mk128, mv128, p);
   count_launch(3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

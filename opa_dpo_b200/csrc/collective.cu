@@ -37,6 +37,7 @@ struct ArParams {
   int64_t per;               // units per region = ceil(units / (world * blocks))
   uint32_t epoch;            // entry barrier = epoch, exit barrier = epoch + 1
   int rank, world;
+  int fp32_in_place;         // 1: `grad` itself is the symmetric buffer (stage_* map the fp32 slice), no staging, exact fp32 sums
   uint32_t* err;             // host-visible flag: set when a barrier timed out
   uint64_t timeout_ns;
 };
@@ -71,6 +72,14 @@ __device__ __forceinline__ void multimem_st_16(uint64_t mc_addr, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+__device__ __forceinline__ uint4 multimem_ld_reduce_f32x4(uint64_t mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -100,8 +109,46 @@ __device__ __forceinline__ void block_barrier_across_ranks(const ArParams& p, ui
   __syncthreads();
 }
 
+// fp32 in place: the gradient bucket itself lives in symmetric memory. No staging and no rounding: region (rank, b) of the
+// slice is summed over ranks (in the switch, or by peer loads in rank order) and written back to every rank. Units of 4 floats.
+__device__ __forceinline__ void allreduce_fp32_in_place(const ArParams& p) {
+  const int b = blockIdx.x, G = gridDim.x;
+  block_barrier_across_ranks(p, p.epoch);  // every rank's slice is final (its compute stream reached this launch)
+  const int64_t lo = (static_cast<int64_t>(p.rank) * G + b) * p.per;
+  const int64_t hi = min(lo + p.per, p.units);
+  if (p.stage_mc != 0) {
+    constexpr int UN = 4;
+    int64_t u = lo + threadIdx.x;
+    for (; u + (UN - 1) * AR_THREADS < hi; u += UN * AR_THREADS) {
+      uint4 v[UN];
+#pragma unroll
+      for (int k = 0; k < UN; ++k) v[k] = multimem_ld_reduce_f32x4(p.stage_mc + 16ull * (u + k * AR_THREADS));
+#pragma unroll
+      for (int k = 0; k < UN; ++k) multimem_st_16(p.stage_mc + 16ull * (u + k * AR_THREADS), v[k]);
+    }
+    for (; u < hi; u += AR_THREADS) multimem_st_16(p.stage_mc + 16ull * u, multimem_ld_reduce_f32x4(p.stage_mc + 16ull * u));
+  } else {
+    for (int64_t u = lo + threadIdx.x; u < hi; u += AR_THREADS) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < p.world; ++r) {
+        const uint4 w = ld_volatile_16(reinterpret_cast<const uint4*>(p.stage_peer[r]) + u);
+        acc.x += __uint_as_float(w.x);
+        acc.y += __uint_as_float(w.y);
+        acc.z += __uint_as_float(w.z);
+        acc.w += __uint_as_float(w.w);
+      }
+      for (int r = 0; r < p.world; ++r) reinterpret_cast<float4*>(p.stage_peer[r])[u] = acc;
+    }
+  }
+  block_barrier_across_ranks(p, p.epoch + 1);  // every rank's share has landed here; nobody still reads this rank's slice
+}
+
 __global__ void __launch_bounds__(AR_THREADS) allreduce_bf16wire_kernel(const ArParams p) {
   const int b = blockIdx.x, G = gridDim.x;
+  if (p.fp32_in_place) {
+    allreduce_fp32_in_place(p);
+    return;
+  }
   // ---- phase 0: pack the regions (*, b) of the local fp32 slice into the local staging
   for (int r = 0; r < p.world; ++r) {
     const int64_t lo = (static_cast<int64_t>(r) * G + b) * p.per;
@@ -218,7 +265,8 @@ extern "C" int opadpo_op_allreduce_bf16wire(const opadpo_allreduce_desc* d, void
     p.stage_peer[r] = d->stage_peer[r];
     p.signal_peer[r] = d->signal_peer[r];
   }
-  p.units = d->count / 8;
+  p.fp32_in_place = d->fp32_in_place != 0;
+  p.units = p.fp32_in_place ? d->count / 4 : d->count / 8;
   const int64_t regions = static_cast<int64_t>(d->world) * d->blocks;
   p.per = (p.units + regions - 1) / regions;
   p.epoch = d->epoch;

@@ -881,23 +881,62 @@ __global__ void __launch_bounds__(256) decode_attention_kernel(const bf16* __res
   }
   float m = -INFINITY, l = 0.f;
   const uint8_t* km = kmask + static_cast<int64_t>(n) * S_max;
-  const unsigned gmask = (((LPK == 32) ? 0u : (1u << LPK)) - 1u) << (sub * LPK);
-  for (int j = grp; j <= len; j += GROUPS) {
-    if (!km[j]) continue;
-    float kf[8], vf[8];
-    unpack8(*reinterpret_cast<const uint4*>(kbase + static_cast<int64_t>(j) * d + ln * 8), kf);
-    unpack8(*reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(j) * d + ln * 8), vf);
-    float s = 0.f;
+  // UN keys per group and iteration: their mask bytes, then all their K / V rows (2 * UN independent 16 B loads per lane in
+  // flight), then ONE running-max update for the chunk. The trip count is uniform over the CTA (invalid or out-of-range keys
+  // are predicated off), so the half-warp shuffles run converged.
+  constexpr int UN = 4;
+  const int iters = (len + GROUPS * UN) / (GROUPS * UN);  // ceil((len + 1) / (GROUPS * UN))
+  for (int it = 0; it < iters; ++it) {
+    const int j0 = it * GROUPS * UN + grp;
+    bool ok[UN];
+    uint4 kraw[UN], vraw[UN];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += q[e] * kf[e];
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * GROUPS;
+      ok[u] = j <= len && km[min(j, len)] != 0;
+    }
 #pragma unroll
-    for (int o2 = LPK / 2; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(gmask, s, o2);  // key groups of a warp diverge
-    const float nm = fmaxf(m, s);
-    const float sc = __expf(m - nm);
-    const float p = __expf(s - nm);
-    l = l * sc + p;
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = static_cast<int64_t>(min(j0 + u * GROUPS, len)) * d + ln * 8;  // clamped: always a written row
+      kraw[u] = *reinterpret_cast<const uint4*>(kbase + row);
+      vraw[u] = *reinterpret_cast<const uint4*>(vbase + row);
+    }
+    float sv[UN];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * sc + p * vf[e];
+    for (int u = 0; u < UN; ++u) {
+      float kf[8];
+      unpack8(kraw[u], kf);
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t += q[e] * kf[e];
+      sv[u] = t;
+    }
+#pragma unroll
+    for (int o2 = LPK / 2; o2 > 0; o2 >>= 1) {
+#pragma unroll
+      for (int u = 0; u < UN; ++u) sv[u] += __shfl_xor_sync(0xffffffffu, sv[u], o2);
+    }
+    float nm = m;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) nm = fmaxf(nm, ok[u] ? sv[u] : -INFINITY);
+    const float base = nm == -INFINITY ? 0.f : nm;  // nothing valid yet: every factor below is exp(-inf) = 0
+    const float sc = __expf(m - base);
+    float pw[UN], psum = 0.f;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      pw[u] = ok[u] ? __expf(sv[u] - base) : 0.f;
+      psum += pw[u];
+    }
+    l = l * sc + psum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= sc;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      float vf[8];
+      unpack8(vraw[u], vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += pw[u] * vf[e];
+    }
     m = nm;
   }
   __shared__ float sm[GROUPS], sl[GROUPS];

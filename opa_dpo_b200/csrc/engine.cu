@@ -1198,6 +1198,33 @@ int Engine::layer_grad_range(int layer, int64_t* offset, int64_t* count) {
   return 0;
 }
 
+int Engine::adopt_grad_buffer(float* buffer, int64_t count) {
+  if (trainable_adapter < 0) {
+    set_error("adopt_grad_buffer: no trainable adapter");
+    return OPADPO_ESTATE;
+  }
+  if (!buffer || count < n_train || (reinterpret_cast<uintptr_t>(buffer) & 255) != 0) {
+    set_error("adopt_grad_buffer: need a 256 B-aligned device buffer of at least %lld floats", static_cast<long long>(n_train));
+    return OPADPO_EINVAL;
+  }
+  Adapter& ad = adapters[trainable_adapter];
+  if (ad.grad == buffer) return 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(buffer, ad.grad, static_cast<size_t>(n_train) * 4, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) {
+    set_error("adopt_grad_buffer: %s", cudaGetErrorString(e));
+    return OPADPO_ECUDA;
+  }
+  for (size_t i = 0; i < allocs.size(); ++i)
+    if (allocs[i] == ad.grad) {  // the engine's own bucket (an adopted one is the caller's to free)
+      cudaFree(ad.grad);
+      allocs.erase(allocs.begin() + i);
+      break;
+    }
+  ad.grad = buffer;
+  return 0;
+}
+
 int Engine::zero_grad(cudaStream_t s) {
   if (trainable_adapter < 0) return 0;
   cudaError_t e = cudaMemsetAsync(adapters[trainable_adapter].grad, 0, static_cast<size_t>(n_train) * 4, s);

@@ -113,6 +113,7 @@ class Engine {
   int set_option(const char* name, int64_t value);
   int set_backward_callback(opadpo_layer_cb cb, void* user);
   int layer_grad_range(int layer, int64_t* offset, int64_t* count);
+  int adopt_grad_buffer(float* buffer, int64_t count);
 
  private:
   opadpo_config cfg;

@@ -83,26 +83,34 @@ class OverlappedGradAllReduce:
 
 class NvlGradAllReduce:
     """The same overlap, with the collective done by this library's own kernel over NVLink / NVSwitch peer memory
-    (csrc/collective.cu, `opadpo_op_allreduce_bf16wire`) instead of NCCL: bf16 on the wire, the sum taken in the switch
-    (multimem.ld_reduce, fp32 accumulation) when the staging buffer has a multicast mapping, peer loads otherwise; no shared
-    memory, so its few CTAs run beside the backward's persistent GEMM CTAs instead of displacing them. The bf16 staging
-    bucket and the signal words are torch symmetric-memory allocations (torch only maps them; the kernel is ours).
+    (csrc/collective.cu, `opadpo_op_allreduce_bf16wire`) instead of NCCL. The kernel takes no shared memory, so its few CTAs
+    run beside the backward's persistent GEMM CTAs instead of displacing them. Two forms:
 
-    Layers are grouped (`group_layers` decoder layers per launch; the last layers and the projector on their own with a
-    wide grid, since nothing is left to hide them behind). The reduced gradient is the bf16-rounded sum, identical on every
-    rank. Construct through `make_grad_allreduce`, which falls back to NCCL on every rank if any rank cannot map the buffers."""
+      wire="fp32" (default): the engine accumulates its gradients directly in a symmetric-memory bucket (torch maps it on
+        every rank; `opadpo_engine_adopt_grad_buffer`), and each rank sums its 1/world share of a slice IN PLACE with
+        multimem.ld_reduce (the addition happens in the NVSwitch) and multimem.st's it to all ranks: exact fp32 sums, no
+        staging, the bucket is read once and written once per step.
+      wire="bf16": the bucket stays where it is; the slice is packed to bf16 into a symmetric staging bucket, reduced with
+        fp32 accumulation, broadcast and unpacked by the same launch (half the NVLink bytes, twice the HBM traffic).
 
-    name = "own NVLink kernel: bf16 wire, in-switch fp32 reduction (multimem), fused pack/reduce/broadcast/unpack"
+    Without a multicast mapping both forms fall back to peer loads / stores inside the same kernel. Layers are grouped
+    (`group_layers` decoder layers per launch; the last layers and the projector go on their own with a wide grid, since
+    nothing is left to hide them behind). The reduced gradient is bit-identical on every rank. Construct through
+    `make_grad_allreduce`, which falls back to NCCL on every rank if any rank cannot map the buffers."""
 
-    def __init__(self, engine, flat_grad: torch.Tensor, group=None, group_layers: int = 4, blocks: int = 16,
-                 tail_blocks: int = 128):
+    def __init__(self, engine, flat_grad: torch.Tensor, group=None, group_layers: Optional[int] = None,
+                 blocks: Optional[int] = None, tail_blocks: Optional[int] = None, wire: Optional[str] = None,
+                 overlap: Optional[bool] = None):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
         self.lib = _lib.load()
-        self.engine, self.grad, self.group = engine, flat_grad, group
+        self.engine, self.group = engine, group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.wire = wire or os.environ.get("OPADPO_DP_WIRE", "fp32")
+        if self.wire not in ("fp32", "bf16"):
+            raise ValueError(f"NvlGradAllReduce: wire must be 'fp32' or 'bf16', got {self.wire!r}")
         if self.world > _lib.MAX_RANKS:
             raise RuntimeError(f"NvlGradAllReduce: {self.world} ranks > {_lib.MAX_RANKS} (one NVLink domain)")
         n = flat_grad.numel()
@@ -110,22 +118,35 @@ class NvlGradAllReduce:
             raise RuntimeError("NvlGradAllReduce: the gradient bucket must be 32 B-aligned with a multiple of 8 elements")
         dev = flat_grad.device
         pg = group if group is not None else dist.group.WORLD
-        self.stage = symm_mem.empty(n, dtype=torch.bfloat16, device=dev)
-        self.h_stage = symm_mem.rendezvous(self.stage, pg)
+        # the symmetric buffer: the gradient bucket itself (fp32 in place) or its bf16 staging copy
+        self.sym = symm_mem.empty(n, dtype=torch.float32 if self.wire == "fp32" else torch.bfloat16, device=dev)
+        self.h_sym = symm_mem.rendezvous(self.sym, pg)
         self.signal = symm_mem.empty(_lib.AR_MAX_BLOCKS * _lib.MAX_RANKS, dtype=torch.int32, device=dev)
         self.signal.zero_()
         self.h_signal = symm_mem.rendezvous(self.signal, pg)
         torch.cuda.synchronize(dev)
         self.h_signal.barrier()          # every rank's signal words are zero before anybody signals
         torch.cuda.synchronize(dev)
-        self.stage_ptrs = [int(p) for p in self.h_stage.buffer_ptrs]
+        self.sym_ptrs = [int(p) for p in self.h_sym.buffer_ptrs]
         self.signal_ptrs = [int(p) for p in self.h_signal.buffer_ptrs]
         use_mc = os.environ.get("OPADPO_DP_MULTICAST", "1") != "0"
-        self.mc_ptr = int(self.h_stage.multicast_ptr or 0) if use_mc else 0
+        self.mc_ptr = int(self.h_sym.multicast_ptr or 0) if use_mc else 0
+        if self.wire == "fp32":
+            self.sym.copy_(flat_grad)
+            if engine is not None:       # from now on the wgrad epilogues accumulate straight into the symmetric bucket
+                engine.adopt_grad_buffer(self.sym)
+            self.grad = self.sym
+        else:
+            self.grad = flat_grad
         self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.comm = torch.cuda.Stream(device=dev, priority=-1)
         self.epoch = 1
-        self.group_layers, self.blocks, self.tail_blocks = group_layers, blocks, tail_blocks
+        env = os.environ.get
+        self.group_layers = group_layers if group_layers is not None else int(env("OPADPO_DP_GROUP_LAYERS", "4"))
+        self.blocks = blocks if blocks is not None else int(env("OPADPO_DP_BLOCKS", "16"))
+        self.tail_blocks = tail_blocks if tail_blocks is not None else int(env("OPADPO_DP_TAIL_BLOCKS", "128"))
+        # overlap=False: nothing runs under the backward; ONE wide launch over the whole bucket when the step's gradients are final
+        self.overlap = overlap if overlap is not None else env("OPADPO_DP_OVERLAP", "1") != "0"
         self.n_layers = None
         self.ranges = {}
         self.pending = None      # (offset, count) of finished layers not yet sent
@@ -136,8 +157,16 @@ class NvlGradAllReduce:
             engine.set_backward_callback(self._on_layer)
 
     @property
+    def name(self) -> str:
+        how = ("fp32 in place on a symmetric gradient bucket" if self.wire == "fp32"
+               else "bf16 wire, fp32 accumulation, fused pack/reduce/broadcast/unpack")
+        when = (f"{self.blocks} CTAs per launch under the backward, {self.group_layers} layers per launch" if self.overlap
+                else f"one {self.tail_blocks}-CTA launch over the whole bucket after the backward")
+        return f"own NVLink kernel (no shared memory; {when}): {how}"
+
+    @property
     def transport(self) -> str:
-        return "multimem (NVLS)" if self.mc_ptr else "peer loads/stores"
+        return "multimem (NVLS, sum taken in the NVSwitch)" if self.mc_ptr else "peer loads/stores"
 
     def _launch(self, off: int, cnt: int, blocks: int):
         if cnt <= 0:
@@ -145,17 +174,19 @@ class NvlGradAllReduce:
         if off % 8 != 0 or cnt % 8 != 0:
             raise RuntimeError(f"NvlGradAllReduce: slice [{off}, +{cnt}) is not a multiple of 8 elements")
         L = self._lib
+        esz = 4 if self.wire == "fp32" else 2
         d = L.AllReduceDesc()
         d.rank, d.world = self.rank, self.world
         d.grad = self.grad.data_ptr() + 4 * off
-        d.stage_local = self.stage_ptrs[self.rank] + 2 * off
-        d.stage_mc = (self.mc_ptr + 2 * off) if self.mc_ptr else 0
+        d.stage_local = self.sym_ptrs[self.rank] + esz * off
+        d.stage_mc = (self.mc_ptr + esz * off) if self.mc_ptr else 0
         for r in range(self.world):
-            d.stage_peer[r] = self.stage_ptrs[r] + 2 * off
+            d.stage_peer[r] = self.sym_ptrs[r] + esz * off
             d.signal_peer[r] = self.signal_ptrs[r]
         d.count, d.epoch, d.blocks = cnt, self.epoch & 0xFFFFFFFF, blocks
         d.err_flag = self.err.data_ptr()
         d.timeout_ms = int(os.environ.get("OPADPO_DP_TIMEOUT_MS", "60000"))
+        d.fp32_in_place = 1 if self.wire == "fp32" else 0
         cur = torch.cuda.current_stream(self.grad.device)
         self.comm.wait_stream(cur)       # the slice is final in the compute stream's order
         L.check(self.lib.opadpo_op_allreduce_bf16wire(ctypes.byref(d), ctypes.c_void_p(self.comm.cuda_stream)),
@@ -169,7 +200,7 @@ class NvlGradAllReduce:
         return self.ranges[layer]
 
     def _on_layer(self, layer: int):
-        if not self.armed:
+        if not self.armed or not self.overlap:
             return
         if self.n_layers is None:
             self.n_layers = int(self.engine.cfg.n_layers)
@@ -232,8 +263,10 @@ def make_grad_allreduce(engine, flat_grad: torch.Tensor, group=None):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     if int(ok.item()) == 1:
         return impl
-    if impl is not None:
+    if impl is not None:             # this rank mapped its buffers but another could not: keep the (possibly adopted) bucket, use NCCL on it
         engine.set_backward_callback(None)
+        flat_grad = impl.grad
     fb = OverlappedGradAllReduce(engine, flat_grad, group)
+    fb._keep_alive = impl
     fb.fallback_reason = why or "another rank could not map the symmetric buffers"
     return fb

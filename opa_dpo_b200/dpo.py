@@ -203,6 +203,7 @@ class DPOStepper:
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
             self.overlap = make_grad_allreduce(self.model.engine, self.model.flat_param.grad, process_group)
+            self.model.flat_param.grad = self.overlap.grad   # the symmetric bucket the engine now accumulates into (or the same tensor)
 
     @torch.no_grad()
     def reference_logprobs(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:

@@ -218,6 +218,15 @@ class Engine:
             self._cb = _lib.LAYER_CB(lambda layer, _user: fn(int(layer)))
         _lib.check(self.lib.opadpo_engine_set_backward_callback(self._h, self._cb, None), "set_backward_callback")
 
+    def adopt_grad_buffer(self, buf: torch.Tensor):
+        """Accumulate the trainable adapter's gradients in `buf` (fp32, >= n_train elements, e.g. a symmetric-memory tensor
+        every data-parallel rank maps) instead of the engine's own bucket; `buffers()["grad"]` then views `buf`."""
+        if buf.dtype != torch.float32 or not buf.is_cuda or not buf.is_contiguous():
+            raise _lib.OpadpoError("adopt_grad_buffer: a contiguous fp32 CUDA tensor is required")
+        _lib.check(self.lib.opadpo_engine_adopt_grad_buffer(self._h, buf.data_ptr(), buf.numel()), "adopt_grad_buffer")
+        self._grad_owner = buf      # keeps the allocation alive as long as the engine uses it
+        self._views = None
+
     def layer_grad_range(self, layer: int) -> Tuple[int, int]:
         off, cnt = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(self.lib.opadpo_engine_layer_grad_range(self._h, layer, ctypes.byref(off), ctypes.byref(cnt)),

@@ -87,6 +87,7 @@ class B200DPOTrainer:
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
             self.overlap = make_grad_allreduce(self.model.engine, self.model.flat_param.grad, process_group)
+            self.model.flat_param.grad = self.overlap.grad   # the symmetric bucket the engine now accumulates into (or the same tensor)
 
     # ------------------------------------------------------------------ rollout (dpo_trainer.py:214-427)
     @torch.no_grad()
