@@ -7,6 +7,7 @@
 #include "attention.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -85,6 +86,50 @@ __device__ __forceinline__ bool tile_skipped(const AttnParams& p, int q0, int j)
   if (p.segR <= 0 || q0 < p.S0) return false;
   const int seg_start = p.S0 + ((q0 - p.S0) / p.segR) * p.segR;
   return j * BKV >= p.S0 && (j + 1) * BKV <= seg_start;
+}
+
+// The same rules with everything that does not depend on the key tile hoisted out of the tile loop (the segment arithmetic
+// needs an integer division: ~40 dependent instructions per tile when left inside).
+struct RowVis {   // what query row i may see, as key intervals
+  int hi;         // keys >= hi are invisible (sequence end, causal diagonal; 0 for a row beyond the sequence)
+  int ex_lo, ex_hi;  // keys in [ex_lo, ex_hi) are invisible (the other responses' segments in front of the row's own); empty if ex_hi <= ex_lo
+};
+__device__ __forceinline__ RowVis make_row_vis(const AttnParams& p, int i, bool causal) {
+  RowVis v;
+  v.hi = i < p.S ? (causal ? min(i + 1, p.S) : p.S) : 0;
+  v.ex_lo = v.ex_hi = 0;
+  if (p.segR > 0 && i >= p.S0) {
+    v.ex_lo = p.S0;
+    v.ex_hi = p.S0 + ((i - p.S0) / p.segR) * p.segR;
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t low_bits(int n) {  // n in [0, 64]
+  return n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+}
+__device__ __forceinline__ uint64_t key_bits_v(const RowVis& v, uint64_t bits, int j) {
+  const int base = j * BKV;
+  bits &= low_bits(min(max(v.hi - base, 0), 64));
+  const int lo = min(max(v.ex_lo - base, 0), 64), hi = min(max(v.ex_hi - base, 0), 64);
+  if (hi > lo) bits &= ~(low_bits(hi) & ~low_bits(lo));
+  return bits;
+}
+// Key tiles [lo, hi) are invisible to every row of the query tile at q0 (tile_skipped as an interval).
+struct TileSkip {
+  int lo, hi;
+};
+__device__ __forceinline__ TileSkip make_tile_skip(const AttnParams& p, int q0) {
+  TileSkip t{0, 0};
+  if (p.segR > 0 && q0 >= p.S0) {
+    const int seg_start = p.S0 + ((q0 - p.S0) / p.segR) * p.segR;
+    t.lo = (p.S0 + BKV - 1) / BKV;
+    t.hi = seg_start / BKV;
+  }
+  return t;
+}
+__device__ __forceinline__ int next_tile_after(const TileSkip& t, int j) {
+  ++j;
+  return (j >= t.lo && j < t.hi) ? t.hi : j;
 }
 
 // =====================================================================================================
@@ -363,6 +408,286 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 }
 
 // =====================================================================================================
+// Forward, P kept in tensor memory. Same tiling as attn_fwd_kernel (128 query rows per CTA, 64-key tiles, two CTAs per SM),
+// but (1) the softmax threads write P as bf16 pairs straight back into the S columns they just read (tcgen05.st) and
+// O += P V takes its A operand from TMEM, so there is no shared-memory P buffer, no generic->async proxy fence, and P is
+// double-buffered for free: the exponentials of tile j+1 no longer wait for P V of tile j; (2) K and V travel in separate
+// two-stage rings, a K stage being released as soon as Q K^T has read it, so the load of K(j+2) starts a whole tile earlier
+// than when it shared a stage with V. O is only touched by the softmax threads when the running maximum moves (lazy
+// rescale), which is the one place that still waits for the previous P V.
+// =====================================================================================================
+template <int HD>
+struct FwdTsSmem {
+  static constexpr int NB = HD / 64;
+  static constexpr int Q_BYTES = NB * BQ * 128;
+  static constexpr int KV_BYTES = NB * BKV * 128;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;      // [2]
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;  // [2]
+  static constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 256;  // S / P double-buffered (2 x 64) + O (HD)
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(NTHREADS, 2)
+    attn_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = FwdTsSmem<HD>;
+  constexpr int NB = L::NB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* pv_done = bars + 13;
+  uint64_t* o_full = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int row0 = n * p.S + q0;
+  const int col0 = h * HD;
+  int num_kv = (p.S + BKV - 1) / BKV;
+  if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
+  const TileSkip skip = make_tile_skip(p, q0);
+  auto next_j = [&](int j) { return next_tile_after(skip, j); };  // next processed key tile after j (>= num_kv: none)
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK);
+      ptx::prefetch_tmap(&tmV);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
+    ptx::tmem_relinquish();
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+      ptx::mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&k_full[i], 1);
+        ptx::mbar_init(&k_empty[i], 1);
+        ptx::mbar_init(&v_full[i], 1);
+        ptx::mbar_init(&v_empty[i], 1);
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&p_full[i], 128);
+      }
+      ptx::mbar_init(pv_done, 1);
+      ptx::mbar_init(o_full, 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_o = tmem + 128;  // S / P buffers at columns [0, 64) and [64, 128)
+
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
+      int it = 0;
+      for (int j = next_j(-1); j < num_kv; j = next_j(j), ++it) {
+        const int st = it & 1;
+        const uint32_t ph = ((it >> 1) & 1) ^ 1;
+        ptx::mbar_wait(&k_empty[st], ph);
+        ptx::mbar_arrive_expect_tx(&k_full[st], L::KV_BYTES);
+        load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &k_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        ptx::mbar_wait(&v_empty[st], ph);
+        ptx::mbar_arrive_expect_tx(&v_full[st], L::KV_BYTES);
+        load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &v_full[st], col0, n * p.S + j * BKV, BKV, NB);
+      }
+    }
+  } else if (warp == 5) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, false, false);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, false, true);
+      const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q);
+      ptx::mbar_wait(q_full, 0);
+      int n_tiles = 0;
+      for (int j = next_j(-1); j < num_kv; j = next_j(j)) ++n_tiles;
+      // S = Q K^T of pipeline slot `it` into S buffer it & 1; the K stage is free again as soon as these MMAs are done
+      auto issue_qk = [&](int it) {
+        const int st = it & 1;
+        const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
+        ptx::mbar_wait(&k_full[st], (it >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int blk = kk >> 2, off = (kk & 3) * 32;
+          ptx::mma_bf16_ss(t_s + st * 64, ptx::make_smem_desc(aQ + blk * (BQ * 128) + off, 16, 1024),
+                           ptx::make_smem_desc(aK + blk * (BKV * 128) + off, 16, 1024), idesc_qk, kk > 0);
+        }
+        ptx::mma_commit(&s_full[st]);
+        ptx::mma_commit(&k_empty[st]);
+      };
+      if (n_tiles > 0) issue_qk(0);
+      for (int it = 0; it < n_tiles; ++it) {
+        // S buffer (it+1)&1 still holds P of slot it-1: P V of that slot was issued one iteration ago, and the tensor pipe
+        // executes in issue order, so Q K^T of slot it+1 overwrites it only after it has been consumed
+        if (it + 1 < n_tiles) issue_qk(it + 1);
+        const int b = it & 1;
+        const uint32_t aV = ptx::smem_u32(smem + L::OFF_V + b * L::KV_BYTES);
+        ptx::mbar_wait(&v_full[b], (it >> 1) & 1);
+        ptx::mbar_wait(&p_full[b], (it >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {  // A = P from TMEM: 16 keys = 8 columns of bf16 pairs
+          ptx::mma_bf16_ts(t_o, t_s + b * 64 + kk * 8, ptx::make_smem_desc(aV + kk * 2048, BKV * 128, 1024), idesc_pv,
+                           (it > 0 || kk > 0));
+        }
+        ptx::mma_commit(&v_empty[b]);
+        ptx::mma_commit(pv_done);
+        if (it == n_tiles - 1) ptx::mma_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: thread == query row
+    const int tid = threadIdx.x;
+    const int i = q0 + tid;
+    const bool row_valid = i < p.S;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const RowVis vis = make_row_vis(p, i, CAUSAL);
+    float m_ref = -INFINITY, l = 0.f;
+    int it = 0;
+    int j = next_j(-1);
+    uint64_t kw = j < num_kv ? load_kword(p, n, j) : 0ull;
+    for (; j < num_kv; ++it) {
+      const int jn = next_j(j);
+      const uint64_t kw_next = jn < num_kv ? load_kword(p, n, jn) : 0ull;
+      const uint64_t bits = key_bits_v(vis, kw, j);
+      const bool full = __all_sync(0xffffffffu, bits == ~0ull);
+      const int b = it & 1;
+      ptx::mbar_wait(&s_full[b], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(t_s + b * 64 + lane_off, r0);
+      ptx::tmem_ld32(t_s + b * 64 + lane_off + 32, r1);
+      ptx::tmem_ld_wait();
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          cm0 = fmaxf(cm0, __uint_as_float(r0[c]));
+          cm1 = fmaxf(cm1, __uint_as_float(r1[c]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float x = ((bits >> c) & 1ull) ? __uint_as_float(r0[c]) : -INFINITY;
+          const float y = ((bits >> (32 + c)) & 1ull) ? __uint_as_float(r1[c]) : -INFINITY;
+          r0[c] = __float_as_uint(x);
+          r1[c] = __float_as_uint(y);
+          cm0 = fmaxf(cm0, x);
+          cm1 = fmaxf(cm1, y);
+        }
+      }
+      const float cm = fmaxf(cm0, cm1) * p.scale_log2;
+      const bool need = cm > m_ref + 8.f;  // lazy rescale: move the reference maximum only when it grows by more than 2^8
+      float alpha = 1.f;
+      if (need) {
+        alpha = ptx::ex2_approx(m_ref - cm);
+        m_ref = cm;
+        l *= alpha;
+      }
+      if (it > 0 && __any_sync(0xffffffffu, need)) {
+        // O may only be touched between P V of slot it-1 (complete: phase it-1 of pv_done; the barrier cannot run further
+        // ahead than that before this thread has delivered P of slot it) and P V of slot it (waits for this thread's arrive)
+        ptx::mbar_wait(pv_done, (it - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t t[32];
+          ptx::tmem_ld32(t_o + lane_off + c * 32, t);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
+          ptx::tmem_st32(t_o + lane_off + c * 32, t);
+        }
+      }
+      const float nmu = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      const float sc2 = p.scale_log2;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      uint32_t pk[32];  // column c of the P buffer = keys 2c, 2c+1 of this row as a bf16 pair
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float a0 = ptx::ex2_approx(fmaf(__uint_as_float(r0[c]), sc2, nmu));
+        const float a1 = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 1]), sc2, nmu));
+        const float a2 = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 2]), sc2, nmu));
+        const float a3 = ptx::ex2_approx(fmaf(__uint_as_float(r0[c + 3]), sc2, nmu));
+        s0 += a0;
+        s1 += a1;
+        s2 += a2;
+        s3 += a3;
+        pk[c / 2] = ptx::pack_bf16(a0, a1);
+        pk[c / 2 + 1] = ptx::pack_bf16(a2, a3);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float a0 = ptx::ex2_approx(fmaf(__uint_as_float(r1[c]), sc2, nmu));
+        const float a1 = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 1]), sc2, nmu));
+        const float a2 = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 2]), sc2, nmu));
+        const float a3 = ptx::ex2_approx(fmaf(__uint_as_float(r1[c + 3]), sc2, nmu));
+        s0 += a0;
+        s1 += a1;
+        s2 += a2;
+        s3 += a3;
+        pk[16 + c / 2] = ptx::pack_bf16(a0, a1);
+        pk[16 + c / 2 + 1] = ptx::pack_bf16(a2, a3);
+      }
+      l += (s0 + s1) + (s2 + s3);
+      ptx::tmem_st32(t_s + b * 64 + lane_off, pk);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[b]);
+      j = jn;
+      kw = kw_next;
+    }
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row0 + tid) * p.ld_o + col0;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t t[32];
+      ptx::tmem_ld32(t_o + lane_off + c * 32, t);
+      ptx::tmem_ld_wait();
+      if (row_valid) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]) * inv, __uint_as_float(t[q * 8 + 1]) * inv);
+          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]) * inv, __uint_as_float(t[q * 8 + 3]) * inv);
+          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]) * inv, __uint_as_float(t[q * 8 + 5]) * inv);
+          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]) * inv, __uint_as_float(t[q * 8 + 7]) * inv);
+          dst[q] = u;
+        }
+      }
+      __syncwarp();
+    }
+    if (row_valid && p.lse)
+      p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] = l > 0.f ? (m_ref + log2f(l)) * LN2 : INFINITY;
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, L::TMEM_COLS);
+  }
+}
+
+// =====================================================================================================
 // Backward, shared score recomputation: p = exp2(s*scale_log2 - lse2), ds' = p*(dp - delta). The softmax scale that
 // belongs on ds is applied once per output element in the dQ / dK epilogues instead of once per score.
 // =====================================================================================================
@@ -401,14 +726,14 @@ struct DqSmem {
   // One CTA per SM, pipelined inside the CTA (as the dK/dV kernel): three K/V stages keep two tile loads in flight, S/dP
   // live in two TMEM buffers and dS in two smem buffers, so S,dP of key tile j+1 are computed while the softmax warps turn
   // tile j into dS and dQ += dS_j K_j follows as soon as that is written.
-  static constexpr int KV_STAGES = 3;
+  // dS never touches shared memory: the softmax threads write it as bf16 pairs back into the S columns they read
+  // (tcgen05.st) and dQ += dS K takes its A operand from TMEM, which also leaves room for a fourth K/V stage.
+  static constexpr int KV_STAGES = 4;
   static constexpr int OFF_K = OFF_DO + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
-  static constexpr int DS_BYTES = BQ * 128;
-  static constexpr int OFF_DS = OFF_V + KV_STAGES * KV_BYTES;  // [2]
-  static constexpr int OFF_BAR = OFF_DS + 2 * DS_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 128;
-  static constexpr int TMEM_COLS = 512;  // [S0 | dP0 | S1 | dP1] (4 x 64) + dQ (HD)
+  static constexpr int OFF_BAR = OFF_V + KV_STAGES * KV_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 512;  // [S0 (dS0 aliased) | dP0 | S1 (dS1) | dP1] (4 x 64) + dQ (HD)
 };
 
 template <int HD, bool CAUSAL>
@@ -422,11 +747,10 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* sdp_full = bars + 7;   // [2]
-  uint64_t* ds_full = bars + 9;    // [2]
-  uint64_t* ds_empty = bars + 11;  // [2]
+  uint64_t* kv_full = bars + 1;    // [4]
+  uint64_t* kv_empty = bars + 5;   // [4]
+  uint64_t* sdp_full = bars + 9;   // [2]
+  uint64_t* ds_full = bars + 11;   // [2]
   uint64_t* dq_done = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
@@ -438,11 +762,8 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   const int col0 = h * HD;
   int num_kv = (p.S + BKV - 1) / BKV;
   if (CAUSAL) num_kv = min(num_kv, (q0 + BQ + BKV - 1) / BKV);
-  auto next_j = [&](int j) {  // next processed key tile after j (num_kv = none)
-    ++j;
-    while (j < num_kv && tile_skipped(p, q0, j)) ++j;
-    return j;
-  };
+  const TileSkip skip = make_tile_skip(p, q0);
+  auto next_j = [&](int j) { return next_tile_after(skip, j); };  // next processed key tile after j (>= num_kv: none)
 
   if (warp == 8) {
     ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -458,7 +779,6 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&sdp_full[i], 1);
         ptx::mbar_init(&ds_full[i], 256);
-        ptx::mbar_init(&ds_empty[i], 1);
       }
       ptx::mbar_init(dq_done, 1);
       ptx::fence_barrier_init();
@@ -517,20 +837,20 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       ptx::mbar_wait(q_full, 0);
       if (n_tiles > 0) issue_sdp(0);
       for (int it = 0; it < n_tiles; ++it) {
-        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose ds_full was awaited one iteration ago
+        // TMEM buffer (it+1)&1 holds dS of slot it-1: dQ += dS K of that slot was issued one iteration ago and the tensor
+        // pipe runs in issue order, so S, dP of slot it+1 overwrite the buffer only after it has been consumed
         if (it + 1 < n_tiles) issue_sdp(it + 1);
         const int st = it % NS, b = it & 1;
         const uint32_t aK = ptx::smem_u32(smem + L::OFF_K + st * L::KV_BYTES);
-        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + b * L::DS_BYTES);
+        const uint32_t t_ds = tmem + b * 128;  // keys 0..31 as bf16 pairs in columns [0, 16), keys 32..63 in [32, 48)
         ptx::mbar_wait(&ds_full[b], (it >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          ptx::mma_bf16_ss(t_dq, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
-                           ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024), idesc_dq, (it > 0 || kk > 0));
+          ptx::mma_bf16_ts(t_dq, t_ds + (kk >> 1) * 32 + (kk & 1) * 8, ptx::make_smem_desc(aK + kk * 2048, BKV * 128, 1024),
+                           idesc_dq, (it > 0 || kk > 0));
         }
-        ptx::mma_commit(&kv_empty[st]);  // the K/V stage and ...
-        ptx::mma_commit(&ds_empty[b]);   // ... the dS buffer may be overwritten once these MMAs are done
+        ptx::mma_commit(&kv_empty[st]);  // the K/V stage may be refilled once these MMAs are done
         if (it == n_tiles - 1) ptx::mma_commit(dq_done);
       }
     }
@@ -543,18 +863,18 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
     const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
+    const RowVis vis = make_row_vis(p, i, CAUSAL);
     int it = 0;
     int j = next_j(-1);
     uint64_t kw = j < num_kv ? load_kword(p, n, j) : 0ull;
     for (; j < num_kv; ++it) {
       const int jn = next_j(j);
       const uint64_t kw_next = jn < num_kv ? load_kword(p, n, jn) : 0ull;
-      const uint64_t bits = key_bits_w(p, kw, j, i, CAUSAL, row_valid);
+      const uint64_t bits = key_bits_v(vis, kw, j);
       const bool full = __all_sync(0xffffffffu, (half ? (bits >> 32) : (bits & 0xffffffffull)) == 0xffffffffull);
       const int b = it & 1;
       const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
-      ptx::mbar_wait(&ds_empty[b], ((it >> 1) & 1) ^ 1);  // dQ of two slots ago has consumed this dS buffer
-      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);
+      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);  // also: dQ of two slots ago has consumed this buffer's dS (issue order)
       ptx::tc_fence_after();
       {
         uint32_t s[32], dp[32];
@@ -563,9 +883,12 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
         recompute_half<false>(s, dp, bits, full, half, p.scale_log2, lse2, delta, pv, dsv);
-        store_half_row_sw128(smem + L::OFF_DS + b * L::DS_BYTES, tid, half, dsv);
+        uint32_t pk[16];  // this thread's 32 keys as bf16 pairs, over the first half of the S columns it has just read
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pk[c] = ptx::pack_bf16(dsv[2 * c], dsv[2 * c + 1]);
+        ptx::tmem_st16(t_s + lane_off + half * 32, pk);
       }
-      ptx::fence_proxy_async();
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ds_full[b]);
       j = jn;
@@ -606,10 +929,12 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
 // TRANSPOSED scores: S^T = K Q^T and dP^T = V dO^T put the KEYS on the 128 TMEM lanes and the query rows on the columns, so
 //   * the resident operand is the big one (K, V: 128 rows) and the streamed one the small one (Q, dO: 64 rows = 32 KB per
 //     pipeline slot for 4 GEMM-units; the [64 keys x 128 queries] form streamed 64 KB for the same work),
-//   * P^T / dS^T land in shared memory as K-major A operands (row = key) and dV += P^T dO, dK += dS^T Q accumulate as
-//     [128 keys x HD] tiles whose rows are contiguous in global memory (16 B epilogue stores, no transposed 2 B scatter),
-//   * three Q/dO stages fit (K,V 64 KB + 3 x 32 KB + P^T,dS^T 2 x 32 KB), so the load of slot it+2 no longer waits for the
-//     accumulate MMAs of slot it to release its stage.
+//   * P^T / dS^T have the keys on the lanes, i.e. they are K-major A operands of dV += P^T dO, dK += dS^T Q: the softmax
+//     threads write them as bf16 pairs over the S^T / dP^T columns they have just read (tcgen05.st) and the MMAs take A from
+//     TMEM — no shared-memory round trip, no proxy fence; dV, dK accumulate as [128 keys x HD] tiles whose rows are
+//     contiguous in global memory (16 B epilogue stores, no transposed 2 B scatter),
+//   * four Q/dO stages fit (K,V 64 KB + 4 x 32 KB), so the load of slot it+2 no longer waits for the accumulate MMAs of
+//     slot it to release its stage.
 // The per-query statistics (lse, delta) vary along the COLUMNS here: they are staged through shared memory once per slot
 // and read back as broadcast float4 loads.
 constexpr int BKT = 128;  // keys per CTA
@@ -620,15 +945,12 @@ struct DkvSmem {
   static constexpr int NB = HD / 64;
   static constexpr int KV_BYTES = NB * BKT * 128;
   static constexpr int Q_BYTES = NB * BQT * 128;
-  static constexpr int NS = 3;
+  static constexpr int NS = 4;
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
   static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [NS]
   static constexpr int OFF_DO = OFF_Q + NS * Q_BYTES;  // [NS]
-  static constexpr int PD_BYTES = BKT * 128;           // 128 key rows x 64 query columns, bf16
-  static constexpr int OFF_P = OFF_DO + NS * Q_BYTES;  // [2]
-  static constexpr int OFF_DS = OFF_P + 2 * PD_BYTES;  // [2]
-  static constexpr int OFF_STAT = OFF_DS + 2 * PD_BYTES;  // float [2][2][BQT]: -lse*log2(e) | delta of the slot's query rows
+  static constexpr int OFF_STAT = OFF_DO + NS * Q_BYTES;  // float [2][2][BQT]: -lse*log2(e) | delta of the slot's query rows
   static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * BQT * 4;
   static constexpr int TOTAL = OFF_BAR + 128;
   static constexpr int TMEM_COLS = 512;  // S^T,dP^T double-buffered (4 x 64) + dV + dK (2 x HD)
@@ -668,11 +990,10 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [3]
-  uint64_t* qdo_empty = bars + 4;   // [3]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* pds_full = bars + 9;    // [2]
-  uint64_t* pds_empty = bars + 11;  // [2]
+  uint64_t* qdo_full = bars + 1;    // [4]
+  uint64_t* qdo_empty = bars + 5;   // [4]
+  uint64_t* sdp_full = bars + 9;    // [2]
+  uint64_t* pds_full = bars + 11;   // [2]
   uint64_t* done = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* stat = reinterpret_cast<float*>(smem + L::OFF_STAT);
@@ -714,7 +1035,6 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&sdp_full[i], 1);
         ptx::mbar_init(&pds_full[i], 256);
-        ptx::mbar_init(&pds_empty[i], 1);
       }
       ptx::mbar_init(done, 1);
       ptx::fence_barrier_init();
@@ -772,28 +1092,28 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       ptx::mbar_wait(kv_full, 0);
       issue_sdp(0);
       for (int it = 0; it < n_slots; ++it) {
-        // the TMEM buffer of slot it+1 was last read by the softmax of slot it-1, whose pds_full was awaited one iteration ago
+        // TMEM buffer (it+1)&1 holds P^T / dS^T of slot it-1: their accumulate MMAs were issued one iteration ago and the
+        // tensor pipe runs in issue order, so S^T, dP^T of slot it+1 overwrite the buffer only after it has been consumed
         if (it + 1 < n_slots) issue_sdp(it + 1);
         const int st = it % NS, b = it & 1;
         const uint32_t aQ = ptx::smem_u32(smem + L::OFF_Q + st * L::Q_BYTES);
         const uint32_t adO = ptx::smem_u32(smem + L::OFF_DO + st * L::Q_BYTES);
-        const uint32_t aP = ptx::smem_u32(smem + L::OFF_P + b * L::PD_BYTES);
-        const uint32_t adS = ptx::smem_u32(smem + L::OFF_DS + b * L::PD_BYTES);
+        // query rows 0..31 of the slot as bf16 pairs in columns [0, 16) of the S^T (P^T) / dP^T (dS^T) buffer, rows 32..63 in [32, 48)
+        const uint32_t t_p = tmem + b * 128, t_ds = t_p + 64;
         ptx::mbar_wait(&pds_full[b], (it >> 1) & 1);
         ptx::tc_fence_after();
-        // dV[keys, hd] += P^T dO ; dK[keys, hd] += dS^T Q   (contraction over the slot's 64 query rows; B operands MN-major)
+        // dV[keys, hd] += P^T dO ; dK[keys, hd] += dS^T Q   (contraction over the slot's 64 query rows; A from TMEM, B MN-major)
 #pragma unroll
         for (int kk = 0; kk < BQT / 16; ++kk) {
-          ptx::mma_bf16_ss(t_dv, ptx::make_smem_desc(aP + kk * 32, 16, 1024),
-                           ptx::make_smem_desc(adO + kk * 2048, BQT * 128, 1024), idesc_acc, (it > 0 || kk > 0));
+          ptx::mma_bf16_ts(t_dv, t_p + (kk >> 1) * 32 + (kk & 1) * 8, ptx::make_smem_desc(adO + kk * 2048, BQT * 128, 1024),
+                           idesc_acc, (it > 0 || kk > 0));
         }
 #pragma unroll
         for (int kk = 0; kk < BQT / 16; ++kk) {
-          ptx::mma_bf16_ss(t_dk, ptx::make_smem_desc(adS + kk * 32, 16, 1024),
-                           ptx::make_smem_desc(aQ + kk * 2048, BQT * 128, 1024), idesc_acc, (it > 0 || kk > 0));
+          ptx::mma_bf16_ts(t_dk, t_ds + (kk >> 1) * 32 + (kk & 1) * 8, ptx::make_smem_desc(aQ + kk * 2048, BQT * 128, 1024),
+                           idesc_acc, (it > 0 || kk > 0));
         }
-        ptx::mma_commit(&qdo_empty[st]);  // Q/dO stage and ...
-        ptx::mma_commit(&pds_empty[b]);   // ... the P^T/dS^T buffer may be overwritten once these MMAs are done
+        ptx::mma_commit(&qdo_empty[st]);  // the Q/dO stage may be refilled once these MMAs are done
         if (it == n_slots - 1) ptx::mma_commit(done);
       }
     }
@@ -830,11 +1150,8 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       const uint32_t m32 = hi > lo ? ((hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
       const bool full = __all_sync(0xffffffffu, m32 == ~0u);
       const uint32_t t_s = tmem + b * 128, t_dp = t_s + 64;
-      uint8_t* sP = smem + L::OFF_P + b * L::PD_BYTES;
-      uint8_t* sdS = smem + L::OFF_DS + b * L::PD_BYTES;
       ptx::named_bar_sync(1, 256);  // this slot's statistics are in shared memory (two buffers: the previous slot's are still being read)
-      ptx::mbar_wait(&pds_empty[b], ((it >> 1) & 1) ^ 1);  // the MMAs that read this P^T/dS^T buffer two slots ago are done
-      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);
+      ptx::mbar_wait(&sdp_full[b], (it >> 1) & 1);  // also: the MMAs that read this buffer's P^T / dS^T two slots ago are done
       ptx::tc_fence_after();
       {
         uint32_t s[32], dp[32];
@@ -843,10 +1160,16 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::tmem_ld_wait();
         float pv[32], dsv[32];
         recompute_half_t(s, dp, m32, full, p.scale_log2, st_buf + half * 32, st_buf + BQT + half * 32, pv, dsv);
-        store_half_row_sw128(sP, tid, half, pv);
-        store_half_row_sw128(sdS, tid, half, dsv);
+        uint32_t pk[16], dk[16];  // 32 query columns as bf16 pairs, over the first half of the columns this thread has just read
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          pk[c] = ptx::pack_bf16(pv[2 * c], pv[2 * c + 1]);
+          dk[c] = ptx::pack_bf16(dsv[2 * c], dsv[2 * c + 1]);
+        }
+        ptx::tmem_st16(t_s + lane_off + half * 32, pk);
+        ptx::tmem_st16(t_dp + lane_off + half * 32, dk);
       }
-      ptx::fence_proxy_async();
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&pds_full[b]);
     }
@@ -971,14 +1294,29 @@ int launch_fwd(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap mq, mk, mv;
   if (make_maps(a, a.q, a.ld_qkv, BQ, &mq) || make_maps(a, a.k, a.ld_qkv, BKV, &mk) || make_maps(a, a.v, a.ld_qkv, BKV, &mv))
     return -6;
-  auto kern = attn_fwd_kernel<HD, CAUSAL>;
-  static bool once = false;
-  if (!once) {
-    if (int rc = set_smem(kern, FwdSmem<HD>::TOTAL)) return rc;
-    once = true;
-  }
+  // OPADPO_ATTN_FWD=ss selects the first-generation kernel (P staged through shared memory); default: P in tensor memory
+  static const bool use_ts = []() {
+    const char* e = getenv("OPADPO_ATTN_FWD");
+    return !(e && e[0] == 's' && e[1] == 's');
+  }();
   dim3 grid((a.S + BQ - 1) / BQ, a.H, a.N);
-  kern<<<grid, NTHREADS, FwdSmem<HD>::TOTAL, stream>>>(mq, mk, mv, make_params(a));
+  if (use_ts) {
+    auto kern = attn_fwd_ts_kernel<HD, CAUSAL>;
+    static bool once_ts = false;
+    if (!once_ts) {
+      if (int rc = set_smem(kern, FwdTsSmem<HD>::TOTAL)) return rc;
+      once_ts = true;
+    }
+    kern<<<grid, NTHREADS, FwdTsSmem<HD>::TOTAL, stream>>>(mq, mk, mv, make_params(a));
+  } else {
+    auto kern = attn_fwd_kernel<HD, CAUSAL>;
+    static bool once = false;
+    if (!once) {
+      if (int rc = set_smem(kern, FwdSmem<HD>::TOTAL)) return rc;
+      once = true;
+    }
+    kern<<<grid, NTHREADS, FwdSmem<HD>::TOTAL, stream>>>(mq, mk, mv, make_params(a));
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
