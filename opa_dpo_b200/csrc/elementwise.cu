@@ -560,25 +560,52 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* out)
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
-__global__ void adamw_kernel(float* __restrict__ master, const float* __restrict__ grad, float* __restrict__ m,
-                             float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr, float b1, float b2,
-                             float eps, float wd, float bc1, float bc2, float gscale, const float* sumsq, float max_norm) {
+// One element of the update; the vector and scalar paths share it so both produce the same bits.
+__device__ __forceinline__ float adamw_one(float g, float p, float& mi, float& vi, float lr, float b1, float b2, float eps,
+                                           float wd, float bc1, float bc2, float gs) {
+  g *= gs;
+  p *= 1.f - lr * wd;
+  mi = b1 * mi + (1.f - b1) * g;
+  vi = b2 * vi + (1.f - b2) * g * g;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  return p - (lr / bc1) * (mi / denom);
+}
+
+// 16 B per thread and array (4 streams read, 4 written: 30 B per element, touched once -> streaming loads / stores).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, const float* __restrict__ grad,
+                                                    float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow,
+                                                    int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                    float bc2, float gscale, const float* sumsq, float max_norm) {
   float gs = gscale;
   if (sumsq && max_norm > 0.f) {
     const float norm = sqrtf(*sumsq) * gscale;
     gs *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float g = grad[i] * gs;
-    float p = master[i];
-    p *= 1.f - lr * wd;
-    const float mi = b1 * m[i] + (1.f - b1) * g;
-    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(grad) + i);
+    float4 p = __ldcs(reinterpret_cast<const float4*>(master) + i);
+    float4 mi = __ldcs(reinterpret_cast<const float4*>(m) + i);
+    float4 vi = __ldcs(reinterpret_cast<const float4*>(v) + i);
+    p.x = adamw_one(g.x, p.x, mi.x, vi.x, lr, b1, b2, eps, wd, bc1, bc2, gs);
+    p.y = adamw_one(g.y, p.y, mi.y, vi.y, lr, b1, b2, eps, wd, bc1, bc2, gs);
+    p.z = adamw_one(g.z, p.z, mi.z, vi.z, lr, b1, b2, eps, wd, bc1, bc2, gs);
+    p.w = adamw_one(g.w, p.w, mi.w, vi.w, lr, b1, b2, eps, wd, bc1, bc2, gs);
+    __stcs(reinterpret_cast<float4*>(m) + i, mi);
+    __stcs(reinterpret_cast<float4*>(v) + i, vi);
+    __stcs(reinterpret_cast<float4*>(master) + i, p);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(shadow + 4 * i) = pk;  // the next forward reads the shadow: keep it cacheable
+  }
+  for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float mi = m[i], vi = v[i];
+    const float p = adamw_one(grad[i], master[i], mi, vi, lr, b1, b2, eps, wd, bc1, bc2, gs);
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-    p -= (lr / bc1) * (mi / denom);
     master[i] = p;
     shadow[i] = __float2bfloat16(p);
   }
@@ -1343,7 +1370,7 @@ int adamw_step(float* master, const float* grad, float* m, float* v, bf16* shado
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(b1, static_cast<float>(step));
   const float bc2 = 1.f - powf(b2, static_cast<float>(step));
-  const unsigned blocks = capped_blocks(n, 256, 148 * 16);
+  const unsigned blocks = capped_blocks((n + 3) / 4, 256, 148 * 8);
   adamw_kernel<<<blocks, 256, 0, s>>>(master, grad, m, v, shadow, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, sumsq, max_norm);
   return check_launch("adamw");
 }
