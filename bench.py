@@ -335,6 +335,9 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "rollout"],
                     help="rollout: print BASELINE configs[3] (greedy rollout, batch 32, 256 new tokens) as the line itself")
     ap.add_argument("--no-rollout", action="store_true", help="train mode: skip the rollout object")
+    ap.add_argument("--diag-no-collective", action="store_true",
+                    help="diagnostic (N > 1): skip the gradient all-reduce, every rank steps on its own shard; the line then shows "
+                         "what max-over-ranks timing alone costs against one GPU (not a valid bench value: marked in config)")
     ap.add_argument("--profile", action="store_true",
                     help="for runs UNDER ncu only: warm-up as given (may be < 3), --steps device steps, then exit; prints no bench line")
     ap.add_argument("--rollout-batch", type=int, default=32)
@@ -387,7 +390,7 @@ def main():
     tok = SimpleNamespace(pad_token_id=cfg.pad_id, eos_token_id=cfg.eos_id)
     policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_policy")
     ref_policy = AutoregressivePolicy(dargs, model, tok, adapter_name="lora_ref_policy")
-    stepper = DPOStepper(policy, ref_policy, dargs, world_size=world)
+    stepper = DPOStepper(policy, ref_policy, dargs, world_size=1 if args.diag_no_collective else world)
 
     if args.mode == "rollout":
         if rank == 0:
@@ -475,12 +478,17 @@ def main():
     ms_e2e, loss_host = timed(step_e2e, args.steps)
 
     # instrumented step: CUDA events around every tcgen05 GEMM launch (the dominant kernel family)
+    # (run on ONE stream: with the reference pass on its side stream two GEMM launches share the SMs and each launch's
+    # events would bracket the other's tiles too)
     lib = _lib.load()
     barrier()
+    concurrent = stepper.concurrent_reference
+    stepper.concurrent_reference = False
     lib.opadpo_prof_begin()
     step_device()
     gm, gf, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     lib.opadpo_prof_end(ctypes.byref(gm), ctypes.byref(gf), ctypes.byref(gl))
+    stepper.concurrent_reference = concurrent
     barrier()
 
     if rank != 0:
@@ -520,8 +528,11 @@ def main():
                    "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
                    "prefix_sharing": (not args.no_share_prefix), "merged_reference_adapter": bool(args.merge_frozen),
                    "fused_rope_epilogue": bool(args.fuse_rope), "fused_swiglu_epilogue": bool(args.fuse_swiglu),
+                   "reference_pass": ("side stream, concurrent with the policy forward" if stepper.concurrent_reference
+                                      else "same stream, before the policy forward"),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
-                   "collective": collective_note(stepper, world),
+                   "collective": ("DIAGNOSTIC RUN: gradient all-reduce skipped, ranks independent (not a bench value)"
+                                  if args.diag_no_collective and world > 1 else collective_note(stepper, world)),
                    "loss": float(loss.item()), "grad_norm": float(norm.item())},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_host},

@@ -51,6 +51,22 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// Two sums in one pass through shared memory (same reduction order per quantity as block_sum). red must hold 64 floats.
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) {
+    red[warp] = a;
+    red[32 + warp] = b;
+  }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  a = warp_sum((lane < nw) ? red[lane] : 0.f);
+  b = warp_sum((lane < nw) ? red[32 + lane] : 0.f);
+}
+
 __device__ __forceinline__ int64_t map_row(int64_t r, const int32_t* idx) { return idx ? idx[r] : r; }
 
 constexpr int NORM_THREADS = 256;
@@ -95,26 +111,37 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const bf16* _
   }
 }
 
+// NV = 16 B vectors per thread (d <= NV * 8 * NORM_THREADS): sized per width so the three row buffers stay in registers
+template <int NV>
 __global__ void __launch_bounds__(NORM_THREADS)
     rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                        const bf16* dres, bf16* dx, int d, float eps, const int32_t* __restrict__ x_idx,
                        const int32_t* __restrict__ dx_idx) {
-  __shared__ float red[32];
+  __shared__ float red[64];
   const int64_t r = blockIdx.x;
   const int64_t xrw = map_row(r, x_idx);
   const int64_t fr = map_row(r, dx_idx);
   const uint4* xr = reinterpret_cast<const uint4*>(x + xrw * d);
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * d);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + fr * d) : nullptr;
   const int nv = d >> 3;
-  uint4 xv[NORM_MAXV], gv[NORM_MAXV];  // gv = w*dy packed as bf16 is lossy; keep dy and re-multiply
+  uint4 xv[NV], gv[NV];  // gv = w*dy packed as bf16 is lossy; keep dy and re-multiply
+  uint4 rv[NV];                 // the incoming residual gradient: requested now, needed after the row reductions
   float ss = 0.f, dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
       xv[i] = xr[v];
       gv[i] = dyr[v];
+      rv[i] = drr ? drr[v] : make_uint4(0u, 0u, 0u, 0u);  // bf16 +0 bits
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nv) {
       float f[8], g[8], ww[8];
       unpack8(xv[i], f);
       unpack8(gv[i], g);
@@ -126,26 +153,19 @@ __global__ void __launch_bounds__(NORM_THREADS)
       }
     }
   }
-  ss = block_sum(ss, red);
-  dot = block_sum(dot, red);
+  block_sum2(ss, dot, red);
   const float rstd = rsqrtf(ss / d + eps);
   const float c = dot / d * rstd * rstd * rstd;
   uint4* dxr = reinterpret_cast<uint4*>(dx + fr * d);
-  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + fr * d) : nullptr;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nv) {
       float f[8], g[8], ww[8], o[8];
       unpack8(xv[i], f);
       unpack8(gv[i], g);
       unpack8(__ldg(wr + v), ww);
-      if (drr) {
-        unpack8(drr[v], o);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
-      }
+      unpack8(rv[i], o);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] += rstd * ww[e] * g[e] - f[e] * c;
       dxr[v] = pack8(o);
@@ -1267,7 +1287,16 @@ int rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const bf16* dres, 
                 const int32_t* x_idx, const int32_t* dx_idx, cudaStream_t s) {
   if (d % 8 != 0 || d > 8 * NORM_THREADS * NORM_MAXV) return -1;
   if (rows == 0) return 0;
-  rmsnorm_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
+  const int nvt = ((d >> 3) + NORM_THREADS - 1) / NORM_THREADS;
+  const unsigned grid = static_cast<unsigned>(rows);
+  if (nvt <= 1)
+    rmsnorm_bwd_kernel<1><<<grid, NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
+  else if (nvt == 2)
+    rmsnorm_bwd_kernel<2><<<grid, NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
+  else if (nvt == 3)
+    rmsnorm_bwd_kernel<3><<<grid, NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
+  else
+    rmsnorm_bwd_kernel<4><<<grid, NORM_THREADS, 0, s>>>(dy, x, w, dres, dx, d, eps, x_idx, dx_idx);
   return check_launch("rmsnorm_bwd");
 }
 int layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, int64_t rows, int d, float eps, cudaStream_t s) {

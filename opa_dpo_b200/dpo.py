@@ -7,6 +7,8 @@
 """
 from __future__ import annotations
 
+import os
+
 import ctypes
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -200,6 +202,9 @@ class DPOStepper:
         self.world_size = world_size
         self.process_group = process_group
         self.lr = args.learning_rate
+        # reference pass on a side stream next to the policy forward (step(); -1 % step time at 7B); OPADPO_CONCURRENT_REF=0: one stream
+        self.concurrent_reference = os.environ.get("OPADPO_CONCURRENT_REF", "1") != "0"
+        self._side = self._ref_ready = None
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
             self.overlap = make_grad_allreduce(self.model.engine, self.model.flat_param.grad, process_group)
@@ -212,11 +217,13 @@ class DPOStepper:
         return {"ref_base_" + k: v for k, v in out.items()}
 
     def pair_loss(self, batch: Dict[str, Tensor], ref: Dict[str, Tensor], chosen: str, rejected: str, grad_accum: int = 1,
-                  last_micro_batch: bool = True):
+                  last_micro_batch: bool = True, ref_ready: Optional[torch.cuda.Event] = None):
         self.policy.train()
         if self.overlap is not None and last_micro_batch:
             self.overlap.arm()   # this backward completes the bucket: all-reduce its slices as they become final
         out = self.policy(**batch, temperature=self.args.temperature, mode="policy")
+        if ref_ready is not None:    # the reference pass ran on a side stream next to the policy forward
+            torch.cuda.current_stream().wait_event(ref_ready)
         total, o = self.loss.pair(out[chosen + "_logprobs"], out[rejected + "_logprobs"],
                                   ref["ref_base_" + chosen + "_logprobs"], ref["ref_base_" + rejected + "_logprobs"])
         (total / grad_accum).backward()
@@ -236,7 +243,20 @@ class DPOStepper:
         return norm
 
     def step(self, batch: Dict[str, Tensor], chosen: str, rejected: str):
-        ref = self.reference_logprobs(batch)
-        loss, o = self.pair_loss(batch, ref, chosen, rejected)
+        if self.concurrent_reference and batch[chosen].is_cuda:
+            # The frozen-adapter pass and the policy forward are independent until the loss: enqueue them on two streams. Their
+            # persistent GEMM grids cannot share an SM (shared memory), so each launch's tail fills with the other's first
+            # tiles, and one pass's HBM-bound kernels (norms, SwiGLU, embeddings) run under the other's tensor-bound ones.
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side, self._ref_ready = torch.cuda.Stream(), torch.cuda.Event()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                ref = self.reference_logprobs(batch)
+                self._ref_ready.record(self._side)
+            loss, o = self.pair_loss(batch, ref, chosen, rejected, ref_ready=self._ref_ready)
+        else:
+            ref = self.reference_logprobs(batch)
+            loss, o = self.pair_loss(batch, ref, chosen, rejected)
         norm = self.optimizer_step()
         return loss, norm

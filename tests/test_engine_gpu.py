@@ -550,6 +550,51 @@ def test_checkpoint_roundtrip_peft_layout(tmp_path):
     model.engine.close(); model2.engine.close()
 
 
+def test_stepper_concurrent_reference_pass_equals_sequential_step():
+    """DPOStepper.step with the frozen-adapter pass enqueued on a side stream next to the policy forward (the default) against
+    the same step run sequentially on one stream: both passes are deterministic, so the loss is identical bit for bit; the
+    gradient norm and the updated masters agree to fp32-atomics noise (split-K wgrad partials land in any order)."""
+    from types import SimpleNamespace
+    from oracle import llava_oracle as O
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200.dpo import DPOArgs, DPOStepper
+    oc, ec = _cfgs()
+    args = DPOArgs(beta=0.1, response_len=24, learning_rate=1e-3)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, NAMES2, left_pad=2)
+    out = {}
+    for concurrent in (True, False):
+        model = B200LlavaModel(ec)
+        w = O.init_weights(oc)
+        sd = dict(w)
+        sd[O.VT + "embeddings.patch_embedding.weight"] = w[O.VT + "embeddings.patch_embedding.weight"].reshape(oc.v_d, -1)
+        model.engine.load_state_dict(sd)
+        for name, seed in (("lora_policy", 11), ("lora_ref_policy", 12)):
+            lo = O.init_lora(oc, seed)
+            model.load_adapter_state(name, {f"base_model.model.{m}.lora_{x}.weight": t for m, ab in lo.items() for x, t in zip("AB", ab)})
+        model.make_trainable("lora_policy")
+        dev = model.engine.device
+        batch = dict(images=images.to(dev), queries=q.to(dev), queries_attn_masks=qm.to(dev), **{k: v.to(dev) for k, v in resp.items()})
+        st = DPOStepper(AutoregressivePolicy(args, model, tok, "lora_policy"), AutoregressivePolicy(args, model, tok, "lora_ref_policy"), args)
+        st.concurrent_reference = concurrent
+        losses, norms = [], []
+        for _ in range(3):      # three steps: the side stream's buffers are recycled across steps
+            loss, norm = st.step(batch, NAMES2[0], NAMES2[1])
+            losses.append(float(loss)); norms.append(float(norm))
+        torch.cuda.synchronize()
+        v = model.engine.buffers()
+        out[concurrent] = (losses, norms, v["master"][: v["n_train"]].clone())
+        assert (st._side is not None) == concurrent
+        model.engine.close()
+    (l1, n1, m1), (l0, n0, m0) = out[True], out[False]
+    assert l1[0] == l0[0], (l1, l0)                      # first step: identical weights, deterministic forwards
+    for a, b in zip(l1, l0):
+        assert abs(a - b) <= 1e-5 * abs(b), (l1, l0)
+    for a, b in zip(n1, n0):
+        assert abs(a - b) <= 1e-3 * abs(b), (n1, n0)
+    assert (m1 - m0).abs().mean().item() < 1e-6
+
+
 def test_opa_sft_loss_and_grads_vs_oracle():
     """OPA stage (LoRA-SFT): token-mean NLL over the response tokens == HF causal-LM loss with prompt labels ignored
     (opa_trainer.py:58-125, entropy_loss off); loss and LoRA gradients vs the oracle's logits + F.cross_entropy."""
