@@ -346,6 +346,8 @@ def main():
                     help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
     ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "1")),
                     help="1: SwiGLU in the gate|up GEMM epilogue of the merged reference pass")
+    ap.add_argument("--wgrad-stream", type=int, default=int(os.environ.get("OPADPO_WGRAD_STREAM", "1")),
+                    help="LoRA weight-gradient GEMMs on a side stream, off the backward's critical path (engine option wgrad_stream)")
     ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "1")),
                     help="1: RoPE in the q|k|v GEMM epilogue")
     args = ap.parse_args()
@@ -383,6 +385,7 @@ def main():
         model.engine.set_option("share_prefix", 0)
     model.engine.set_option("merge_frozen", args.merge_frozen)
     model.engine.set_option("fuse_rope", int(bool(args.fuse_rope)))
+    model.engine.set_option("wgrad_stream", int(bool(args.wgrad_stream)))
     model.engine.set_option("fuse_swiglu", int(bool(args.fuse_swiglu)))
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
@@ -484,11 +487,13 @@ def main():
     barrier()
     concurrent = stepper.concurrent_reference
     stepper.concurrent_reference = False
+    model.engine.set_option("wgrad_stream", 0)
     lib.opadpo_prof_begin()
     step_device()
     gm, gf, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     lib.opadpo_prof_end(ctypes.byref(gm), ctypes.byref(gf), ctypes.byref(gl))
     stepper.concurrent_reference = concurrent
+    model.engine.set_option("wgrad_stream", args.wgrad_stream)
     barrier()
 
     if rank != 0:
@@ -503,11 +508,14 @@ def main():
     fl = flops_per_pair(cfg, Q_LEN, R)
     peaks = _peaks()
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_fwd_layer.json")
+    traffic_alg = None
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_full_gemm_dominant.json")
     if args.model == "7b" and os.path.exists(prof):
-        try:  # dram bytes of the dominant launch (fused gate|up forward GEMM) from the committed ncu --set full capture
+        try:  # dram bytes of the dominant launch (merged gate|up forward GEMM, SwiGLU epilogue) from this round's ncu --set full
+              # capture of the bench's own step (tools/gpu_r2_m.sh); ncu cannot run inside a timed bench, so it is a committed figure
             with open(prof) as f:
-                traffic = json.load(f).get("dominant_launch_dram_bytes")
+                pj = json.load(f)
+            traffic, traffic_alg = pj.get("dram_bytes_read_plus_write"), pj.get("algorithmic_bytes")
         except Exception:
             traffic = None
     gemm_tflops = gf.value / (gm.value * 1e-3) / 1e12 if gm.value > 0 else None
@@ -528,6 +536,8 @@ def main():
                    "pairs_per_gpu": b, "global_pairs": pairs_per_step, "seq_len": Q_LEN - 1 + cfg.n_patches + R,
                    "prefix_sharing": (not args.no_share_prefix), "merged_reference_adapter": bool(args.merge_frozen),
                    "fused_rope_epilogue": bool(args.fuse_rope), "fused_swiglu_epilogue": bool(args.fuse_swiglu),
+                   "lora_weight_gradients": ("side stream, under the backward's HBM-bound kernels" if args.wgrad_stream
+                                             else "main stream"),
                    "reference_pass": ("side stream, concurrent with the policy forward" if stepper.concurrent_reference
                                       else "same stream, before the policy forward"),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",
@@ -539,8 +549,10 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                      "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None, "traffic": traffic,
-                     "traffic_note": "dram read+write bytes of ONE dominant launch (gate|up forward GEMM, M=13816 N=22016 K=4096+256; "
-                                     "algorithmic 0.92 GB) from profiles/r01_ncu_full_gemm_fwd_layer.json",
+                     "traffic_algorithmic": traffic_alg,
+                     "traffic_note": "dram read+write bytes of ONE dominant launch (merged gate|up forward GEMM with the SwiGLU epilogue, "
+                                     "M=13816 N=22016 K=4096, 1.53 ms, tensor pipe 98.7 % active) against its algorithmic bytes, from "
+                                     "profiles/r02_ncu_full_gemm_dominant.json (ncu --set full of this bench's step, round 2)",
                      "kernel": "opadpo::gemm_kernel (tcgen05; CTA-pair cta_group::2 256x256x64 tiles for the large GEMMs, 128x256x64 otherwise; all epilogues)", "peak_source": peaks["source"] + " sustained",
                      "gemm_launches_per_step": int(gl.value), "gemm_ms_per_step": gm.value,
                      "gemm_share_of_step": gm.value / ms_step,

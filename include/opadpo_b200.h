@@ -249,6 +249,8 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
  * "fuse_rope" (default 1): the q|k|v projection applies RoPE in its GEMM epilogue (one bf16 rounding instead of two).
  * "fuse_swiglu" (default 1; acts with merge_frozen): the merged frozen adapter's gate|up projection
  * applies SwiGLU in its epilogue over an interleaved copy of the merged weight (bit-identical results).
+ * "wgrad_stream" (default 1): the LoRA weight-gradient GEMMs of opadpo_backward run on an engine-owned side stream and are
+ * joined before the call's last kernel, the layer callback and the projector (same results up to fp32-atomics order).
  * "merge_rollout" (default 1): rollouts merge the adapter per call. "adam_step": optimizer-state restore. */
 int opadpo_engine_set_option(opadpo_engine* e, const char* name, int64_t value);
 /* Communication overlap: `cb(layer, user)` is called on the host thread inside opadpo_backward right after the backward

@@ -72,7 +72,30 @@ Engine::~Engine() {
   for (int i = 0; i < 2; ++i) release_slot(i, nullptr);
   drop_frozen_merged();
   for (void* p : allocs) cudaFree(p);
+  if (ev_u) cudaEventDestroy(ev_u);
+  for (int k = 0; k < 4; ++k)
+    if (ev_side[k]) cudaEventDestroy(ev_side[k]);
+  if (wg_stream) cudaStreamDestroy(wg_stream);
   cudaDeviceSynchronize();
+}
+
+int Engine::ensure_wgrad_stream() {
+  if (wg_stream) return 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming);
+  for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev_side[k], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    set_error("wgrad side stream: %s", cudaGetErrorString(e));
+    return OPADPO_ECUDA;
+  }
+  return 0;
+}
+
+void Engine::wait_side(int kind, cudaStream_t s) {
+  if (kind >= 0 && side_pending[kind]) {
+    cudaStreamWaitEvent(s, ev_side[kind], 0);
+    side_pending[kind] = false;
+  }
 }
 
 template <typename T>
@@ -554,7 +577,7 @@ static int pick_splits(int Mo, int No, int64_t Ktok) {
 //   u  = s * dy B            (per group)          dB += dy^T t      (t = s x A^T saved by the forward)
 //   dA += u^T x                                   dx  = [dy | u] [W ; A]
 int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
-                       int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s) {
+                       int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind) {
   const int G = L.groups, out_g = L.out / G;
   const bool lora = L.slot >= 0 && r > 0;
   Adapter& ad = adapters[adapter];
@@ -562,6 +585,10 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
     const LoraSlot& sl = slots[L.slot];
     float* gA = ad.grad + sl.offA;
     float* gB = ad.grad + sl.offB;
+    // side_kind >= 0: the weight gradients go to the side stream. `u` then belongs to this linear kind alone, and the caller
+    // has made the main stream wait for the previous reader of it (wait_side) before getting here.
+    const bool side = side_kind >= 0 && wgrad_stream && wg_stream != nullptr;
+    cudaStream_t ws = side ? wg_stream : s;
     for (int g = 0; g < G; ++g) {
       GemmArgs a;  // u_g = s * dy_g B_g
       a.M = static_cast<int>(M);
@@ -574,6 +601,12 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
       a.C = u + static_cast<int64_t>(g) * r;
       a.ldc = static_cast<int64_t>(G) * r;
       EN_CHECK(gemm_checked(a, s));
+    }
+    if (side) {  // everything the weight gradients read (dy, t, x, u) is complete in main-stream order at this point
+      cudaEventRecord(ev_u, s);
+      cudaStreamWaitEvent(ws, ev_u, 0);
+    }
+    for (int g = 0; g < G; ++g) {
       GemmArgs w;  // dB_g += dy_g^T t_g
       w.M = out_g;
       w.N = r;
@@ -585,7 +618,7 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
       w.splits = pick_splits(out_g, r, M);
       w.C = gB + static_cast<int64_t>(g) * out_g * r;
       w.ldc = r;
-      EN_CHECK(gemm_checked(w, s));
+      EN_CHECK(gemm_checked(w, ws));
     }
     GemmArgs w;  // dA += u^T x
     w.M = G * r;
@@ -598,7 +631,11 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
     w.splits = pick_splits(G * r, L.in, M);
     w.C = gA;
     w.ldc = L.in;
-    EN_CHECK(gemm_checked(w, s));
+    EN_CHECK(gemm_checked(w, ws));
+    if (side) {
+      cudaEventRecord(ev_side[side_kind], ws);
+      side_pending[side_kind] = true;
+    }
   }
   if (dx) {
     GemmArgs a;
@@ -974,7 +1011,20 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
   EN_CHECK(pool_alloc(&dqkv, T * 3 * d, s, tmp));
   EN_CHECK(pool_alloc(&dh, T * d, s, tmp));
   EN_CHECK(pool_alloc(&dob, T * d, s, tmp));
-  EN_CHECK(pool_alloc(&u, T * 3 * rr, s, tmp));
+  EN_CHECK(pool_alloc(&u, T * 3 * rr, s, tmp));   // u of q|k|v (and, after the decoder, of the projector)
+  // one u buffer per linear kind: the side-stream dA GEMM of a layer reads it while the main stream already runs the next linear
+  bf16 *u_down, *u_gu, *u_o;
+  EN_CHECK(pool_alloc(&u_down, T * rr, s, tmp));
+  EN_CHECK(pool_alloc(&u_gu, T * 2 * rr, s, tmp));
+  EN_CHECK(pool_alloc(&u_o, T * rr, s, tmp));
+  const bool side = wgrad_stream && r > 0 && c.n_layers > 0;
+  if (side) {
+    EN_CHECK(ensure_wgrad_stream());
+    for (int k = 0; k < 4; ++k) side_pending[k] = false;
+  }
+  enum { K_DOWN = 0, K_GU = 1, K_O = 2, K_QKV = 3 };
+  const int kd = side ? K_DOWN : -1, kg = side ? K_GU : -1, ko = side ? K_O : -1, kq = side ? K_QKV : -1;
+  int pending_cb = -1;  // a layer whose slice becomes final once its side-stream weight gradients are done
   EN_CHECK(pool_alloc(&delta, T * H, s, tmp));
 
   {  // d logits = dlp/T * (onehot - softmax) [- dent/T * p (ln p + H)], recomputed tile-wise from the saved LSE (never stored
@@ -1016,12 +1066,17 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
     LlamaLayer& L = layers[l];
     const LayerActs& a = cx.layers[l];
     // MLP
-    EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u, dact, F, nullptr, 0, s));
+    // Main-stream writers wait for the side stream's readers of the buffer they are about to overwrite (wait_side): u_k and
+    // the dy of linear kind k were last read by that kind's weight gradients one layer ago — normally long done.
+    wait_side(kd, s);  // u_down (previous layer's dA)
+    EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u_down, dact, F, nullptr, 0, s, kd));
+    wait_side(kg, s);  // dgu and u_gu (previous layer's gate|up weight gradients)
     EN_CHECK(swiglu_bwd(dact, a.gu, dgu, T, F, s));
-    EN_CHECK(linear_bwd(L.gu, adapter, a.h2, d, a.tgu, dgu, 2 * F, T, u, dh, d, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.gu, adapter, a.h2, d, a.tgu, dgu, 2 * F, T, u_gu, dh, d, nullptr, 0, s, kg));
+    wait_side(ko, s);  // dx1 and u_o (previous layer's o-projection weight gradients)
     EN_CHECK(rmsnorm_bwd(dh, a.x1, L.ln2, dx, dx1, T, d, c.rms_eps, nullptr, nullptr, s));
     // attention
-    EN_CHECK(linear_bwd(L.o, adapter, a.o, d, a.to, dx1, d, T, u, dob, d, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.o, adapter, a.o, d, a.to, dx1, d, T, u_o, dob, d, nullptr, 0, s, ko));
     AttnArgs at;
     at.N = N;
     at.S = S;
@@ -1046,11 +1101,24 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
     at.dk = dqkv + d;
     at.dv = dqkv + 2 * d;
     at.ld_dqkv = 3 * d;
+    wait_side(kq, s);  // dqkv and u (previous layer's q|k|v weight gradients: the last side-stream work of that layer)
+    if (pending_cb >= 0) {  // ... so the previous layer's LoRA-grad slice is now complete in main-stream order
+      if (layer_cb) layer_cb(pending_cb, layer_cb_user);
+      pending_cb = -1;
+    }
     EN_CHECK(attn_bwd_checked(at, s));
     EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, nullptr, 2 * H, hd, rope_cs, 1, s));
-    EN_CHECK(linear_bwd(L.qkv, adapter, a.h1, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s));
+    EN_CHECK(linear_bwd(L.qkv, adapter, a.h1, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s, kq));
+    wait_side(kd, s);  // dx is this layer's down-projection dy: its weight gradients must have read it before it is rewritten
     EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, nullptr, nullptr, s));
-    if (layer_cb) layer_cb(l, layer_cb_user);  // this layer's LoRA-grad slice is complete in stream order
+    if (side)
+      pending_cb = l;  // reported once the main stream has waited for this layer's side-stream work
+    else if (layer_cb)
+      layer_cb(l, layer_cb_user);  // this layer's LoRA-grad slice is complete in stream order
+  }
+  if (side) {  // join: every weight gradient is in the bucket before anything downstream (projector, all-reduce, optimizer)
+    for (int k = 0; k < 4; ++k) wait_side(k, s);
+    if (pending_cb >= 0 && layer_cb) layer_cb(pending_cb, layer_cb_user);
   }
   // image rows -> projector (its LoRA adapters are trainable; the CLIP tower is not differentiated)
   const int64_t PR = static_cast<int64_t>(cx.b) * P;
@@ -1147,6 +1215,10 @@ int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "fuse_swiglu") == 0) {
     if (fuse_swiglu != (value != 0)) drop_frozen_merged();  // the merged copy is built with or without the interleaved weight
     fuse_swiglu = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "wgrad_stream") == 0) {
+    wgrad_stream = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_rope") == 0) {

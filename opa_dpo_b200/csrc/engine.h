@@ -130,6 +130,16 @@ class Engine {
   bool merge_frozen = false;
   // q|k|v projection with RoPE applied in the GEMM epilogue (EPI_BF16_ROPE) instead of a separate in-place pass
   bool fuse_rope = true;
+  // LoRA weight-gradient GEMMs (dB += dy^T t, dA += u^T x) are off the backward's critical path: they run on a side stream,
+  // where their tensor-bound tiles overlap the main stream's HBM-bound kernels (SwiGLU / RMSNorm backward, inverse RoPE) and
+  // the tails of its persistent dgrad launches. Option "wgrad_stream" (default 1).
+  bool wgrad_stream = true;
+  cudaStream_t wg_stream = nullptr;
+  cudaEvent_t ev_u = nullptr;         // main: this linear's u = dy B is enqueued (and, in stream order, its dy / t / x)
+  cudaEvent_t ev_side[4] = {};        // side: the weight gradients of linear kind k (0 down, 1 gate|up, 2 o, 3 q|k|v) are done
+  bool side_pending[4] = {};          // ev_side[k] carries a record nobody on the main stream has waited for since
+  int ensure_wgrad_stream();
+  void wait_side(int kind, cudaStream_t s);   // main stream waits for the side stream's readers of kind k's dy / u buffers
   // merged frozen adapter only: gate|up projection with SwiGLU in the GEMM epilogue (EPI_SWIGLU_BF16) over an interleaved
   // copy of the merged weight; bit-identical to projection + swiglu_fwd
   bool fuse_swiglu = true;
@@ -175,7 +185,7 @@ class Engine {
   int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy, int act,
                  const bf16* residual, int64_t ldr, cudaStream_t s, RopeFuse* rope = nullptr);
   int linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
-                 int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s);
+                 int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind = -1);
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);

@@ -96,6 +96,42 @@ def _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, names):
     return loss.detach(), lpg, ref, pol
 
 
+def test_side_stream_weight_gradients_equal_main_stream_weight_gradients():
+    """opadpo_backward with the LoRA weight-gradient GEMMs on the engine's side stream (default) against the same backward
+    with everything on one stream: the same gradient bucket up to the order of the fp32 split-K atomics, three backward
+    calls in a row (the side stream's u / dy buffers are recycled layer by layer and call by call), and the layer callback
+    still sees every slice exactly once, in top-down order, projector last."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs(n_layers=5)      # deep enough for every buffer to be recycled several times
+    eng, w, lp, lr = _build(oc, ec, share_prefix=1)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    grads = {}
+    seen = []
+    eng.set_backward_callback(lambda layer: seen.append(layer))
+    for side in (1, 0):
+        eng.set_option("wgrad_stream", side)
+        acc = []
+        for rep in range(3):
+            pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+            d = torch.randn(pol_lp.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(40 + rep)) * 0.1
+            eng.zero_grad()
+            seen.clear()
+            eng.backward(0, d)
+            torch.cuda.synchronize()
+            assert seen == list(range(ec.n_layers - 1, -1, -1)) + [ec.n_layers], seen
+            acc.append(eng.buffers()["grad"].clone())
+        grads[side] = acc
+    eng.set_backward_callback(None)
+    for a, b in zip(grads[1], grads[0]):
+        assert torch.isfinite(a).all()
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel <= 1e-5, rel
+    eng.close()
+
+
 @pytest.mark.parametrize("share", [0, 1])
 def test_dpo_step_loss_and_lora_grads_vs_oracle(share):
     """Four-forward DPO step (policy & frozen reference x chosen & rejected): loss within 1e-3 relative, LoRA grads.
