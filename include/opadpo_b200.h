@@ -246,7 +246,8 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
  * "merge_frozen" (default 0): inference forwards (save_slot = -1) and rollouts of a NON-trainable adapter run on decoder
  * weights merged once, W' = W + (alpha/r) B A (peft merge_adapter semantics; bf16 W'), so the reference pass of the DPO
  * step carries no LoRA GEMMs; costs one extra copy of the decoder weights, rebuilt when that adapter is reloaded.
- * "fuse_rope" (default 1): the q|k|v projection applies RoPE in its GEMM epilogue (one bf16 rounding instead of two).
+ * "fuse_rope" (default 1): the q|k|v projection applies RoPE in its GEMM epilogue (one bf16 rounding instead of two), and
+ * the attention backward applies the inverse rotation to dq / dk in its epilogues (no standalone RoPE kernel in either pass).
  * "fuse_swiglu" (default 1; acts with merge_frozen): the merged frozen adapter's gate|up projection
  * applies SwiGLU in its epilogue over an interleaved copy of the merged weight (bit-identical results).
  * "wgrad_stream" (default 1): the LoRA weight-gradient GEMMs of opadpo_backward run on an engine-owned side stream and are

@@ -35,7 +35,44 @@ struct AttnParams {
   const float* delta;
   __nv_bfloat16 *dq, *dk, *dv;
   int64_t ld_dqkv;
+  const float2* rope_cs;
+  const int32_t* rope_pos;
 };
+
+// 32 columns [c0, c0+32) and their rotary partners [c0+64, c0+96) of one row, fp32 accumulators -> bf16, with the optional
+// inverse rotation (cs = this row's (cos, sin) entries for columns c0..c0+31, or null) and a common scale.
+__device__ __forceinline__ void store_rotary_pair_runs(__nv_bfloat16* row, int c0, const uint32_t (&ta)[32], const uint32_t (&tb)[32],
+                                                       float scale, const float2* cs) {
+  float a[32], b[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const float x = __uint_as_float(ta[e]) * scale, y = __uint_as_float(tb[e]) * scale;
+    if (cs) {
+      const float2 k = __ldg(cs + e);
+      a[e] = x * k.x + y * k.y;
+      b[e] = y * k.x - x * k.y;
+    } else {
+      a[e] = x;
+      b[e] = y;
+    }
+  }
+  uint4* da = reinterpret_cast<uint4*>(row + c0);
+  uint4* db = reinterpret_cast<uint4*>(row + c0 + 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u, w;
+    u.x = ptx::pack_bf16(a[q * 8 + 0], a[q * 8 + 1]);
+    u.y = ptx::pack_bf16(a[q * 8 + 2], a[q * 8 + 3]);
+    u.z = ptx::pack_bf16(a[q * 8 + 4], a[q * 8 + 5]);
+    u.w = ptx::pack_bf16(a[q * 8 + 6], a[q * 8 + 7]);
+    w.x = ptx::pack_bf16(b[q * 8 + 0], b[q * 8 + 1]);
+    w.y = ptx::pack_bf16(b[q * 8 + 2], b[q * 8 + 3]);
+    w.z = ptx::pack_bf16(b[q * 8 + 4], b[q * 8 + 5]);
+    w.w = ptx::pack_bf16(b[q * 8 + 6], b[q * 8 + 7]);
+    da[q] = u;
+    db[q] = w;
+  }
+}
 
 // K-major tile of `rows` rows x (nblk*64) columns -> smem [blk][rows][128 B]
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int col0, int row0,
@@ -729,9 +766,11 @@ struct DqSmem {
   // dS never touches shared memory: the softmax threads write it as bf16 pairs back into the S columns they read
   // (tcgen05.st) and dQ += dS K takes its A operand from TMEM, which also leaves room for a fourth K/V stage.
   static constexpr int KV_STAGES = 4;
-  static constexpr int OFF_K = OFF_DO + Q_BYTES;
+  static constexpr int OFF_O = OFF_DO + Q_BYTES;  // the forward output tile: delta = rowsum(dO * O) is computed here, once per row
+  static constexpr int OFF_K = OFF_O + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_V + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_DELTA = OFF_V + KV_STAGES * KV_BYTES;  // float [2][BQ]: per-row partial dot products of the two column halves
+  static constexpr int OFF_BAR = OFF_DELTA + 2 * BQ * 4;
   static constexpr int TOTAL = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 512;  // [S0 (dS0 aliased) | dP0 | S1 (dS1) | dP1] (4 x 64) + dQ (HD)
 };
@@ -739,8 +778,8 @@ struct DqSmem {
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                       const AttnParams p) {
+                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const AttnParams p, float* __restrict__ delta_out) {
   using L = DqSmem<HD>;
   constexpr int NB = L::NB;
   constexpr int NS = L::KV_STAGES;
@@ -792,9 +831,10 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
 
   if (warp == 8) {
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(q_full, 2 * L::Q_BYTES);
+      ptx::mbar_arrive_expect_tx(q_full, 3 * L::Q_BYTES);
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
       load_tile(smem + L::OFF_DO, &tmdO, q_full, col0, row0, BQ, NB);
+      load_tile(smem + L::OFF_O, &tmO, q_full, col0, row0, BQ, NB);
       int it = 0;
       for (int j = next_j(-1); j < num_kv; j = next_j(j), ++it) {
         const int st = it % NS;
@@ -862,7 +902,31 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     const bool row_valid = i < p.S;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float lse2 = row_valid ? p.lse[static_cast<int64_t>(row0 + tid) * p.H + h] * LOG2E : INFINITY;
-    const float delta = row_valid ? p.delta[static_cast<int64_t>(row0 + tid) * p.H + h] : 0.f;
+    // delta[row] = sum_c dO[row, c] * O[row, c], from the tiles in shared memory: this thread takes the 64 columns of its half
+    // (one 128 B row of block `half`; dO and O share the swizzle, so chunk k of one meets chunk k of the other), the two
+    // halves meet through shared memory. Written out for the dK/dV kernel, which runs after this one.
+    float* dl_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
+    {
+      static_assert(NB == 2, "one 64-column block per thread half");
+      ptx::mbar_wait(q_full, 0);
+      const uint4* ro = reinterpret_cast<const uint4*>(smem + L::OFF_O + half * (BQ * 128) + tid * 128);
+      const uint4* rd = reinterpret_cast<const uint4*>(smem + L::OFF_DO + half * (BQ * 128) + tid * 128);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 a = ro[k], b = rd[k];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(bw[e] << 16), acc);
+          acc = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(bw[e] & 0xffff0000u), acc);
+        }
+      }
+      dl_s[half * BQ + tid] = acc;
+      ptx::named_bar_sync(1, 256);
+    }
+    const float delta = row_valid ? dl_s[tid] + dl_s[BQ + tid] : 0.f;
+    if (half == 0 && row_valid) delta_out[static_cast<int64_t>(row0 + tid) * p.H + h] = delta;
     const RowVis vis = make_row_vis(p, i, CAUSAL);
     int it = 0;
     int j = next_j(-1);
@@ -896,23 +960,21 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     }
     ptx::mbar_wait(dq_done, 0);
     ptx::tc_fence_after();
+    // this thread's 64 columns of the row as two runs: [half*32, +32) and the rotary partners [64 + half*32, +32)
+    static_assert(HD == 128, "rotary pairs are (j, j + 64)");
     __nv_bfloat16* drow = p.dq + static_cast<int64_t>(row0 + tid) * p.ld_dqkv + col0;
-#pragma unroll 1
-    for (int c = half * (HD / 64); c < (half + 1) * (HD / 64); ++c) {
-      uint32_t t[32];
-      ptx::tmem_ld32(t_dq + lane_off + c * 32, t);
+    {
+      uint32_t ta[32], tb[32];
+      ptx::tmem_ld32(t_dq + lane_off + half * 32, ta);
+      ptx::tmem_ld32(t_dq + lane_off + 64 + half * 32, tb);
       ptx::tmem_ld_wait();
       if (row_valid) {
-        uint4* dst = reinterpret_cast<uint4*>(drow + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = ptx::pack_bf16(__uint_as_float(t[q * 8 + 0]) * p.scale, __uint_as_float(t[q * 8 + 1]) * p.scale);
-          u.y = ptx::pack_bf16(__uint_as_float(t[q * 8 + 2]) * p.scale, __uint_as_float(t[q * 8 + 3]) * p.scale);
-          u.z = ptx::pack_bf16(__uint_as_float(t[q * 8 + 4]) * p.scale, __uint_as_float(t[q * 8 + 5]) * p.scale);
-          u.w = ptx::pack_bf16(__uint_as_float(t[q * 8 + 6]) * p.scale, __uint_as_float(t[q * 8 + 7]) * p.scale);
-          dst[q] = u;
+        const float2* cs = nullptr;
+        if (p.rope_cs) {
+          const int pos = p.rope_pos ? __ldg(p.rope_pos + row0 + tid) : i;
+          cs = p.rope_cs + static_cast<int64_t>(pos) * (HD / 2) + half * 32;
         }
+        store_rotary_pair_runs(drow, half * 32, ta, tb, p.scale, cs);
       }
       __syncwarp();
     }
@@ -1175,33 +1237,42 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     }
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
-    // thread == key row; this thread's half of the head dimension: 64 contiguous bf16 of dV and of dK
+    // thread == key row. dV: this thread's half of the head dimension, 64 contiguous bf16. dK: two runs of 32 columns,
+    // [half*32, +32) and the rotary partners [64 + half*32, +32), so the inverse rotation needs no second thread.
     const bool row_ok = k < p.S;
     __nv_bfloat16* vrow = p.dv + (static_cast<int64_t>(n) * p.S + k) * p.ld_dqkv + col0 + half * 64;
-    __nv_bfloat16* krow = p.dk + (static_cast<int64_t>(n) * p.S + k) * p.ld_dqkv + col0 + half * 64;
+    __nv_bfloat16* krow = p.dk + (static_cast<int64_t>(n) * p.S + k) * p.ld_dqkv + col0;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      uint32_t tv[32], tk[32];
+      uint32_t tv[32];
       ptx::tmem_ld32(t_dv + lane_off + half * 64 + c * 32, tv);
-      ptx::tmem_ld32(t_dk + lane_off + half * 64 + c * 32, tk);
       ptx::tmem_ld_wait();
       if (row_ok) {
         uint4* dv4 = reinterpret_cast<uint4*>(vrow + c * 32);
-        uint4* dk4 = reinterpret_cast<uint4*>(krow + c * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint4 u, w;
+          uint4 u;
           u.x = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 0]), __uint_as_float(tv[q * 8 + 1]));
           u.y = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 2]), __uint_as_float(tv[q * 8 + 3]));
           u.z = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 4]), __uint_as_float(tv[q * 8 + 5]));
           u.w = ptx::pack_bf16(__uint_as_float(tv[q * 8 + 6]), __uint_as_float(tv[q * 8 + 7]));
-          w.x = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 0]) * p.scale, __uint_as_float(tk[q * 8 + 1]) * p.scale);
-          w.y = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 2]) * p.scale, __uint_as_float(tk[q * 8 + 3]) * p.scale);
-          w.z = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 4]) * p.scale, __uint_as_float(tk[q * 8 + 5]) * p.scale);
-          w.w = ptx::pack_bf16(__uint_as_float(tk[q * 8 + 6]) * p.scale, __uint_as_float(tk[q * 8 + 7]) * p.scale);
           dv4[q] = u;
-          dk4[q] = w;
         }
+      }
+      __syncwarp();
+    }
+    {
+      uint32_t ta[32], tb[32];
+      ptx::tmem_ld32(t_dk + lane_off + half * 32, ta);
+      ptx::tmem_ld32(t_dk + lane_off + 64 + half * 32, tb);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+        const float2* cs = nullptr;
+        if (p.rope_cs) {
+          const int pos = p.rope_pos ? __ldg(p.rope_pos + static_cast<int64_t>(n) * p.S + k) : k;
+          cs = p.rope_cs + static_cast<int64_t>(pos) * (HD / 2) + half * 32;
+        }
+        store_rotary_pair_runs(krow, half * 32, ta, tb, p.scale, cs);
       }
       __syncwarp();
     }
@@ -1212,28 +1283,6 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, L::TMEM_COLS);
   }
-}
-
-// delta[t, h] = sum_c dO[t, h*HD + c] * O[t, h*HD + c]   (one warp per (t, h))
-template <int HD>
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int64_t ld_do, const __nv_bfloat16* __restrict__ O,
-                                  int64_t ld_o, float* __restrict__ delta, int64_t T, int H) {
-  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= T * H) return;
-  const int64_t t = w / H;
-  const int h = static_cast<int>(w % H);
-  const __nv_bfloat16* a = dO + t * ld_do + h * HD;
-  const __nv_bfloat16* b = O + t * ld_o + h * HD;
-  float s = 0.f;
-  for (int c = lane * 2; c < HD; c += 64) {
-    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + c));
-    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + c));
-    s += x.x * y.x + x.y * y.y;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) delta[w] = s;
 }
 
 __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __restrict__ bits, int N, int S, int nwords) {
@@ -1276,6 +1325,8 @@ AttnParams make_params(const AttnArgs& a) {
   p.dk = a.dk;
   p.dv = a.dv;
   p.ld_dqkv = a.ld_dqkv;
+  p.rope_cs = a.rope_cs;
+  p.rope_pos = a.rope_pos;
   return p;
 }
 
@@ -1338,13 +1389,8 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
   if (make_maps(a, a.q, a.ld_qkv, BQT, &mq64) || make_maps(a, a.dO, a.ld_do, BQT, &mdo64) ||
       make_maps(a, a.k, a.ld_qkv, BKT, &mk128) || make_maps(a, a.v, a.ld_qkv, BKT, &mv128))
     return -6;
-  const int64_t T = static_cast<int64_t>(a.N) * a.S;
-  {
-    const int64_t warps = T * a.H;
-    const int threads = 256;
-    const int64_t blocks = (warps * 32 + threads - 1) / threads;
-    attn_delta_kernel<HD><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(a.dO, a.ld_do, a.o, a.ld_o, a.delta, T, a.H);
-  }
+  CUtensorMap mo;  // the dQ kernel also computes delta = rowsum(dO * O) from the O tile (and writes it for the dK/dV kernel)
+  if (make_maps(a, a.o, a.ld_o, BQ, &mo)) return -6;
   AttnParams p = make_params(a);
   auto kdq = attn_bwd_dq_kernel<HD, CAUSAL>;
   auto kdkv = attn_bwd_dkdv_kernel<HD, CAUSAL>;
@@ -1355,10 +1401,10 @@ int launch_bwd(const AttnArgs& a, cudaStream_t stream) {
     once = true;
   }
   dim3 gq((a.S + BQ - 1) / BQ, a.H, a.N);
-  kdq<<<gq, NTHREADS_BWD, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mk, mv, p);
+  kdq<<<gq, NTHREADS_BWD, DqSmem<HD>::TOTAL, stream>>>(mq, mdo, mo, mk, mv, p, a.delta);
   dim3 gk((a.S + BKT - 1) / BKT, a.H, a.N);
   kdkv<<<gk, NTHREADS_BWD, DkvSmem<HD>::TOTAL, stream>>>(mq64, mdo64, mk128, mv128, p);
-  count_launch(3);
+  count_launch(2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "attn bwd launch: %s", cudaGetErrorString(e));

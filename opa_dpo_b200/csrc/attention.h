@@ -32,6 +32,12 @@ struct AttnArgs {
   float* delta = nullptr;  // [T, H] scratch (rowsum(dO*O))
   __nv_bfloat16 *dq = nullptr, *dk = nullptr, *dv = nullptr;
   int64_t ld_dqkv = 0;
+  // backward only, optional: q and k went through the rotary embedding before the forward (HF LLaMA: column j of a head
+  // paired with j + HD/2, angle table rope_cs [position][HD/2] = (cos, sin)); with rope_cs set, the backward returns the
+  // gradients w.r.t. the UN-rotated q and k (the inverse rotation is applied to dq / dk in the kernels' epilogues, on the fp32
+  // accumulators). rope_pos [T] = position of each token row, or null for row index modulo S.
+  const float2* rope_cs = nullptr;
+  const int32_t* rope_pos = nullptr;
 };
 
 int attn_forward(const AttnArgs& a, cudaStream_t stream);

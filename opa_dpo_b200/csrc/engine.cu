@@ -1106,8 +1106,12 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
       if (layer_cb) layer_cb(pending_cb, layer_cb_user);
       pending_cb = -1;
     }
+    if (fuse_rope && hd == 128) {  // inverse rotary embedding of dq / dk inside the attention backward's epilogues
+      at.rope_cs = rope_cs;
+      at.rope_pos = cx.lay.pos;
+    }
     EN_CHECK(attn_bwd_checked(at, s));
-    EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, nullptr, 2 * H, hd, rope_cs, 1, s));
+    if (!at.rope_cs) EN_CHECK(rope_inplace(dqkv, 3 * d, T, S, cx.lay.pos, 0, nullptr, 2 * H, hd, rope_cs, 1, s));
     EN_CHECK(linear_bwd(L.qkv, adapter, a.h1, d, a.tqkv, dqkv, 3 * d, T, u, dh, d, nullptr, 0, s, kq));
     wait_side(kd, s);  // dx is this layer's down-projection dy: its weight gradients must have read it before it is rewritten
     EN_CHECK(rmsnorm_bwd(dh, a.x, L.ln1, dx1, dx, T, d, c.rms_eps, nullptr, nullptr, s));
