@@ -346,6 +346,8 @@ def main():
                     help="1: the frozen reference adapter's forwards run on decoder weights merged once (no LoRA GEMMs)")
     ap.add_argument("--fuse-swiglu", type=int, default=int(os.environ.get("OPADPO_FUSE_SWIGLU", "1")),
                     help="1: SwiGLU in the gate|up GEMM epilogue of the merged reference pass")
+    ap.add_argument("--engine-opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="extra opadpo_engine_set_option calls (A/B runs), e.g. --engine-opt fuse_swiglu_bwd=0")
     ap.add_argument("--wgrad-stream", type=int, default=int(os.environ.get("OPADPO_WGRAD_STREAM", "1")),
                     help="LoRA weight-gradient GEMMs on a side stream, off the backward's critical path (engine option wgrad_stream)")
     ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "1")),
@@ -386,6 +388,9 @@ def main():
     model.engine.set_option("merge_frozen", args.merge_frozen)
     model.engine.set_option("fuse_rope", int(bool(args.fuse_rope)))
     model.engine.set_option("wgrad_stream", int(bool(args.wgrad_stream)))
+    for kv in args.engine_opt:
+        name, _, val = kv.partition("=")
+        model.engine.set_option(name, int(val))
     model.engine.set_option("fuse_swiglu", int(bool(args.fuse_swiglu)))
     model.engine.random_init(seed=1234)
     model.make_trainable("lora_policy")
@@ -538,6 +543,7 @@ def main():
                    "fused_rope_epilogue": bool(args.fuse_rope), "fused_swiglu_epilogue": bool(args.fuse_swiglu),
                    "lora_weight_gradients": ("side stream, under the backward's HBM-bound kernels" if args.wgrad_stream
                                              else "main stream"),
+                   "engine_options": args.engine_opt,
                    "reference_pass": ("side stream, concurrent with the policy forward" if stepper.concurrent_reference
                                       else "same stream, before the policy forward"),
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (weights 13.5 GB + activations >> 126 MB)",

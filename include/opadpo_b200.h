@@ -41,6 +41,9 @@ int opadpo_abi_version(void);
 enum { OPADPO_EPI_BF16 = 0, OPADPO_EPI_F32_ATOMIC = 1, OPADPO_EPI_LSE = 2, OPADPO_EPI_CEGRAD = 3, OPADPO_EPI_F32_PARTIAL = 4,
        OPADPO_EPI_SWIGLU_BF16 = 6, /* B rows interleaved [128 gate | 128 up] per 256 columns; C bf16 [M, N/2] = silu(gate) * up with
                                       the unfused path's bf16 roundings (bit-identical to projection + SwiGLU) */
+       OPADPO_EPI_SWIGLU_BWD = 7, /* down-projection dgrad with the SwiGLU backward in its epilogue: acc = d(act) [M, N = F]; residual =
+                                     the saved gate|up activations [M, 2F] (ldr); C = d(gate|up) [M, 2F] (ldc): C[:, j] = d gate_j,
+                                     C[:, F + j] = d up_j; same bits as the unfused pair (d(act) rounded to bf16 in between) */
        OPADPO_EPI_BF16_ROPE = 5 /* bf16 output with HF LLaMA's rotary embedding [UPSTREAM apply_rotary_pos_emb] applied to the
                                     first rope_cols columns (heads of 128 columns, column j paired with j + 64) */ };
 enum { OPADPO_ACT_NONE = 0, OPADPO_ACT_GELU = 1, OPADPO_ACT_QUICK_GELU = 2 };
@@ -250,6 +253,9 @@ int opadpo_engine_lora_offsets(opadpo_engine* e, const char* module, int64_t* of
  * the attention backward applies the inverse rotation to dq / dk in its epilogues (no standalone RoPE kernel in either pass).
  * "fuse_swiglu" (default 1; acts with merge_frozen): the merged frozen adapter's gate|up projection
  * applies SwiGLU in its epilogue over an interleaved copy of the merged weight (bit-identical results).
+ * "fuse_swiglu_bwd" (default 0): the down projection's dgrad GEMM turns its d(act) tile into d(gate), d(up) in the epilogue
+ * (OPADPO_EPI_SWIGLU_BWD; bit-identical to the separate SwiGLU-backward pass, d(act) never goes to memory; measured no
+ * faster at 7B — the GEMM becomes epilogue-bound — hence opt-in).
  * "wgrad_stream" (default 1): the LoRA weight-gradient GEMMs of opadpo_backward run on an engine-owned side stream and are
  * joined before the call's last kernel, the layer callback and the projector (same results up to fp32-atomics order).
  * "merge_rollout" (default 1): rollouts merge the adapter per call. "adam_step": optimizer-state restore. */

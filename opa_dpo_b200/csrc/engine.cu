@@ -577,7 +577,8 @@ static int pick_splits(int Mo, int No, int64_t Ktok) {
 //   u  = s * dy B            (per group)          dB += dy^T t      (t = s x A^T saved by the forward)
 //   dA += u^T x                                   dx  = [dy | u] [W ; A]
 int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
-                       int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind) {
+                       int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind,
+                       const bf16* swiglu_gu) {
   const int G = L.groups, out_g = L.out / G;
   const bool lora = L.slot >= 0 && r > 0;
   Adapter& ad = adapters[adapter];
@@ -655,6 +656,11 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
     if (dres) {
       a.residual = dres;
       a.ldr = lddres;
+    }
+    if (swiglu_gu) {  // this is the down projection: dx is d(gate|up) [M, 2 in], produced from the d(act) tile in the epilogue
+      a.epilogue = EPI_SWIGLU_BWD;
+      a.residual = swiglu_gu;
+      a.ldr = 2 * static_cast<int64_t>(L.in);
     }
     EN_CHECK(gemm_checked(a, s));
   }
@@ -1069,9 +1075,13 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
     // Main-stream writers wait for the side stream's readers of the buffer they are about to overwrite (wait_side): u_k and
     // the dy of linear kind k were last read by that kind's weight gradients one layer ago — normally long done.
     wait_side(kd, s);  // u_down (previous layer's dA)
-    EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u_down, dact, F, nullptr, 0, s, kd));
     wait_side(kg, s);  // dgu and u_gu (previous layer's gate|up weight gradients)
-    EN_CHECK(swiglu_bwd(dact, a.gu, dgu, T, F, s));
+    if (fuse_swiglu_bwd && F % 32 == 0) {
+      EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u_down, dgu, 2 * F, nullptr, 0, s, kd, a.gu));
+    } else {
+      EN_CHECK(linear_bwd(L.down, adapter, a.act, F, a.td, dx, d, T, u_down, dact, F, nullptr, 0, s, kd));
+      EN_CHECK(swiglu_bwd(dact, a.gu, dgu, T, F, s));
+    }
     EN_CHECK(linear_bwd(L.gu, adapter, a.h2, d, a.tgu, dgu, 2 * F, T, u_gu, dh, d, nullptr, 0, s, kg));
     wait_side(ko, s);  // dx1 and u_o (previous layer's o-projection weight gradients)
     EN_CHECK(rmsnorm_bwd(dh, a.x1, L.ln2, dx, dx1, T, d, c.rms_eps, nullptr, nullptr, s));
@@ -1219,6 +1229,10 @@ int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "fuse_swiglu") == 0) {
     if (fuse_swiglu != (value != 0)) drop_frozen_merged();  // the merged copy is built with or without the interleaved weight
     fuse_swiglu = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "fuse_swiglu_bwd") == 0) {
+    fuse_swiglu_bwd = value != 0;
     return 0;
   }
   if (strcmp(name, "wgrad_stream") == 0) {

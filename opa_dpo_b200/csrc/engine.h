@@ -133,6 +133,11 @@ class Engine {
   // LoRA weight-gradient GEMMs (dB += dy^T t, dA += u^T x) are off the backward's critical path: they run on a side stream,
   // where their tensor-bound tiles overlap the main stream's HBM-bound kernels (SwiGLU / RMSNorm backward, inverse RoPE) and
   // the tails of its persistent dgrad launches. Option "wgrad_stream" (default 1).
+  // SwiGLU backward inside the down-projection dgrad's epilogue (option "fuse_swiglu_bwd"). Off by default: bit-compatible and
+  // tested, but measured no faster (profiles/r02_bench_swiglu_bwd_epilogue_ab.log): 256 columns x (2 MUFU + ~20 instructions)
+  // on the 4 epilogue warps outlast the 68 k-blocks of the mainloop, so the GEMM turns epilogue-bound and gives back what
+  // the removed HBM pass saved.
+  bool fuse_swiglu_bwd = false;
   bool wgrad_stream = true;
   cudaStream_t wg_stream = nullptr;
   cudaEvent_t ev_u = nullptr;         // main: this linear's u = dy B is enqueued (and, in stream order, its dy / t / x)
@@ -185,7 +190,8 @@ class Engine {
   int linear_fwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, int64_t M, bf16* t, bf16* y, int64_t ldy, int act,
                  const bf16* residual, int64_t ldr, cudaStream_t s, RopeFuse* rope = nullptr);
   int linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx, const bf16* t, const bf16* dy, int64_t ldy,
-                 int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind = -1);
+                 int64_t M, bf16* u, bf16* dx, int64_t lddx, const bf16* dres, int64_t lddres, cudaStream_t s, int side_kind = -1,
+                 const bf16* swiglu_gu = nullptr);
   int clip_forward(int adapter, const float* images, int n, bf16* feats_out, cudaStream_t s, std::vector<void*>* tmp);
   int projector_forward(int adapter, const bf16* clip_feats, int64_t rows, bf16* pre, bf16* act, bf16* t0, bf16* t2,
                         bf16* feats, cudaStream_t s);

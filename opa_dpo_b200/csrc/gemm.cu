@@ -394,6 +394,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
           __syncwarp();
         }
+      } else if constexpr (EPI == EPI_SWIGLU_BWD) {
+        // d(act) never goes to memory: the tile is turned into d(gate), d(up) against the saved gate|up activations right here
+        // (swiglu_bwd_kernel's arithmetic on d(act) rounded to bf16 as the unfused path stores it: bit-identical results). The
+        // GEMM is tensor-bound, so the 4 F bytes per token this epilogue moves ride along for free.
+        const __nv_bfloat16* grow = p.residual + static_cast<int64_t>(row) * p.ldr;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 + 32 <= p.N) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(grow + col0);
+            const uint4* u4 = reinterpret_cast<const uint4*>(grow + p.N + col0);
+            uint4* dg4 = reinterpret_cast<uint4*>(orow + col0);
+            uint4* du4 = reinterpret_cast<uint4*>(orow + p.N + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 gv = __ldg(g4 + q), uv = __ldg(u4 + q);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
+              const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&uv);
+              float dg[8], du[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 gf = __bfloat1622float2(gh[e]), uf = __bfloat1622float2(uh[e]);
+                const float gg[2] = {gf.x, gf.y}, uu[2] = {uf.x, uf.y};
+#pragma unroll
+                for (int t2 = 0; t2 < 2; ++t2) {
+                  const float da = __bfloat162float(__float2bfloat16(__uint_as_float(r[q * 8 + e * 2 + t2]) * p.alpha));
+                  const float sg = 1.f / (1.f + __expf(-gg[t2]));
+                  const float silu = gg[t2] * sg;
+                  du[e * 2 + t2] = da * silu;
+                  dg[e * 2 + t2] = da * uu[t2] * sg * (1.f + gg[t2] * (1.f - sg));
+                }
+              }
+              uint4 a, b;
+              a.x = ptx::pack_bf16(dg[0], dg[1]);
+              a.y = ptx::pack_bf16(dg[2], dg[3]);
+              a.z = ptx::pack_bf16(dg[4], dg[5]);
+              a.w = ptx::pack_bf16(dg[6], dg[7]);
+              b.x = ptx::pack_bf16(du[0], du[1]);
+              b.y = ptx::pack_bf16(du[2], du[3]);
+              b.z = ptx::pack_bf16(du[4], du[5]);
+              b.w = ptx::pack_bf16(du[6], du[7]);
+              dg4[q] = a;
+              du4[q] = b;
+            }
+          }
+          __syncwarp();
+        }
       } else if constexpr (EPI == EPI_BF16_ROPE) {
         // q|k|v projection with the rotary embedding applied to the fp32 accumulator (one bf16 rounding instead of two and
         // no separate pass over q and k): heads are 128 columns, HF's rotate_half pairs column j with j + 64, the table
@@ -748,7 +799,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     snprintf(g_err, sizeof(g_err), "gemm: EPI_SWIGLU_BF16 needs N %% 256 == 0 (gate / up rows interleaved in blocks of 128) and no bias / act / residual");
     return -9;
   }
-  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD || a.epilogue == EPI_BF16_ROPE || a.epilogue == EPI_SWIGLU_BF16) &&
+  if (a.epilogue == EPI_SWIGLU_BWD && (a.N % 32 != 0 || !a.residual || a.ldr % 8 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15) ||
+                                        a.bias || a.act != ACT_NONE || a.splits > 1 || a.ldc < 2 * static_cast<int64_t>(a.N))) {
+    snprintf(g_err, sizeof(g_err), "gemm: EPI_SWIGLU_BWD needs N %% 32 == 0, the saved gate|up activations in `residual` (16 B-aligned, ldr %% 8 == 0), ldc >= 2 N, no bias / act / split-K");
+    return -9;
+  }
+  if ((a.epilogue == EPI_BF16 || a.epilogue == EPI_CEGRAD || a.epilogue == EPI_BF16_ROPE || a.epilogue == EPI_SWIGLU_BF16 || a.epilogue == EPI_SWIGLU_BWD) &&
       (a.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15))) {
     snprintf(g_err, sizeof(g_err), "gemm: bf16 output needs ldc %% 8 == 0 and 16B-aligned C");
     return -5;
@@ -864,6 +920,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_F32_PARTIAL: return launch_impl<AMN, BMN, EPI_F32_PARTIAL, CL>(maps, kp, grid, stream); \
     case EPI_BF16_ROPE: return launch_impl<AMN, BMN, EPI_BF16_ROPE, CL>(maps, kp, grid, stream);   \
     case EPI_SWIGLU_BF16: return launch_impl<AMN, BMN, EPI_SWIGLU_BF16, CL>(maps, kp, grid, stream); \
+    case EPI_SWIGLU_BWD: return launch_impl<AMN, BMN, EPI_SWIGLU_BWD, CL>(maps, kp, grid, stream); \
     default: break;                                                                               \
   }
 #define OPADPO_DISPATCH(AMN, BMN)          \

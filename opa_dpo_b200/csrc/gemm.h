@@ -23,6 +23,8 @@ enum GemmEpilogue : int {
   EPI_CEGRAD = 3,    // C bf16 = dlp[m]*alpha*(onehot(label[m]) - p) - dent[m]*alpha*p*(ln p + ent[m]),  p = exp(alpha*acc - lse[m])
   EPI_F32_PARTIAL = 4,  // C f32 [splits, M, ldc]: plain per-split stores (decode: weight streaming fills all SMs, fixed-order reduce)
   EPI_SWIGLU_BF16 = 6,  // C bf16 [M, N/2]: B rows interleaved [gate 128 | up 128] per 256-wide tile; C[:, t*128 + j] = silu(gate_j) * up_j
+  EPI_SWIGLU_BWD = 7,   // down-projection dgrad with the SwiGLU backward in its epilogue: acc = d(act) tile [M, N = F]; `residual` points at
+                        // the saved gate|up activations [M, 2F] (ldr), C is d(gate|up) [M, 2F] (ldc): C[:, j] = dgate_j, C[:, F + j] = dup_j
   EPI_BF16_ROPE = 5,    // C bf16 = rotary(alpha*acc) on the first rope_cols columns (heads of 128, HF rotate_half pairing), plain beyond
 };
 

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import AttnDesc, GemmDesc
 
-EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD, EPI_F32_PARTIAL, EPI_BF16_ROPE, EPI_SWIGLU_BF16 = 0, 1, 2, 3, 4, 5, 6
+EPI_BF16, EPI_F32_ATOMIC, EPI_LSE, EPI_CEGRAD, EPI_F32_PARTIAL, EPI_BF16_ROPE, EPI_SWIGLU_BF16, EPI_SWIGLU_BWD = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2
 
 

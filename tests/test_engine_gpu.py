@@ -96,6 +96,49 @@ def _oracle_grads(oc, w, lp, lr, images, q, qm, resp, lc, names):
     return loss.detach(), lpg, ref, pol
 
 
+def test_fused_swiglu_backward_and_rope_backward_equal_the_standalone_kernels():
+    """opadpo_backward with the SwiGLU backward inside the down projection's dgrad epilogue and the inverse rotary embedding
+    inside the attention backward's epilogues (the second is the default, the first opt-in) against the same backward with the standalone kernels: the LoRA
+    gradient bucket agrees to bf16-rounding noise of the intermediate dq / dk (the fused rotation works on the fp32
+    accumulator: one rounding instead of two; the option also moves the forward's rotation into its GEMM epilogue) — relative
+    L2 <= 1e-2, cosine >= 0.9999."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    oc, ec = _cfgs(n_layers=3)
+    eng, w, lp, lr = _build(oc, ec, share_prefix=1)
+    images, q, qm, resp = O.synthetic_batch(oc, 3, 16, 24, NAMES2, left_pad=3)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+    eng.set_option("wgrad_stream", 0)
+    grads = {}
+    for fused in (1, 0):
+        eng.set_option("fuse_swiglu_bwd", fused)
+        eng.set_option("fuse_rope", fused)
+        pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+        d = torch.randn(pol_lp.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(77)) * 0.1
+        eng.zero_grad()
+        eng.backward(0, d)
+        torch.cuda.synchronize()
+        grads[fused] = eng.buffers()["grad"].clone()
+    a, b = grads[1].double(), grads[0].double()
+    assert torch.isfinite(grads[1]).all()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    rel = float((a - b).norm() / b.norm())
+    assert cos >= 0.9999 and rel <= 1e-2, (cos, rel)
+    # the SwiGLU fusion alone is bit-compatible with the standalone kernel (same roundings): fp32-atomics noise only
+    eng.set_option("fuse_rope", 1)
+    for fused in (1, 0):
+        eng.set_option("fuse_swiglu_bwd", fused)
+        pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+        eng.zero_grad()
+        eng.backward(0, d)
+        torch.cuda.synchronize()
+        grads[fused] = eng.buffers()["grad"].clone()
+    rel = float((grads[1] - grads[0]).norm() / grads[0].norm())
+    assert rel <= 2e-5, rel
+    eng.close()
+
+
 def test_side_stream_weight_gradients_equal_main_stream_weight_gradients():
     """opadpo_backward with the LoRA weight-gradient GEMMs on the engine's side stream (default) against the same backward
     with everything on one stream: the same gradient bucket up to the order of the fp32 split-K atomics, three backward

@@ -266,6 +266,30 @@ def test_gemm_swiglu_epilogue_bit_identical_to_unfused(cluster):
     assert (diff > 0).float().mean().item() < 2e-3 and diff.max().item() <= 2.0 ** -7 * want.float().abs().max().item()
 
 
+@pytest.mark.parametrize("cluster", [0, 2])
+def test_gemm_swiglu_backward_epilogue_equals_unfused(cluster):
+    """EPI_SWIGLU_BWD: the down projection's dgrad (dy W, B operand MN-major, LoRA as a second K segment) with the SwiGLU
+    backward in its epilogue == the same GEMM writing d(act) as bf16 followed by the SwiGLU-backward formula on it (d gate
+    = d act * up * sig * (1 + gate (1 - sig)), d up = d act * silu(gate)); ragged M, F a multiple of 32 only."""
+    from opa_dpo_b200 import ops
+    M, F, K, r = 1100, 416, 320, 64
+    dy, W = _mk((M, K), 51, 0.5), _mk((K, F), 52, 0.2)          # W = down-projection weight [out = K, in = F]
+    u, A = _mk((M, r), 53, 0.5), _mk((r, F), 54, 0.2)           # LoRA: dx += u A
+    gu = _mk((M, 2 * F), 55, 1.5)
+    dact = torch.empty((M, F), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, W, dact, a2=u, b2=A, b_mn=True, cluster=cluster)
+    dgu = torch.full((M, 2 * F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, W, dgu, a2=u, b2=A, b_mn=True, epilogue=ops.EPI_SWIGLU_BWD, residual=gu, cluster=cluster)
+    torch.cuda.synchronize()
+    g, up, da = gu[:, :F].float(), gu[:, F:].float(), dact.float()
+    sg = 1.0 / (1.0 + torch.exp(-g))
+    want = torch.cat([da * up * sg * (1.0 + g * (1.0 - sg)), da * g * sg], 1).to(torch.bfloat16)
+    assert torch.isfinite(dgu.float()).all()
+    diff = (dgu.float() - want.float()).abs()
+    # __expf vs torch.exp: a last-bit difference in the exponential may move a result by one bf16 ulp, never more
+    assert (diff > 0).float().mean().item() < 5e-3 and diff.max().item() <= 2.0 ** -7 * want.float().abs().max().item()
+
+
 @pytest.mark.parametrize("Mb,N,K,splits", [(32, 4096, 4096, 0), (32, 12288, 4096, 0), (1, 256, 64, 1), (5, 136, 200, 2),
                                            (32, 22016, 4096, 0), (32, 4096, 11008, 0), (64, 520, 1000, 3), (100, 1000, 320, 0),
                                            (128, 32000, 4096, 2), (17, 128, 4096, 16)])
