@@ -39,22 +39,38 @@ struct AttnParams {
   const int32_t* rope_pos;
 };
 
+// The (cos, sin) rows of a tile's 128 token rows, staged through shared memory. Read straight from global memory, every lane
+// of a warp would walk its own 512 B table row 8 bytes at a time: 32 wavefronts per load instruction, ~8000 per CTA, all on
+// the exposed tail of the kernel. Staged: each warp copies 16 rows with coalesced 16 B lanes (4 wavefronts per row); rows are
+// padded to 132 floats so that the per-thread float4 reads afterwards are bank-conflict free.
+constexpr int CS_ROW_FLOATS = 132;  // 64 (cos, sin) pairs + 4 floats of padding
+constexpr int CS_STAGE_BYTES = 128 * CS_ROW_FLOATS * 4;
+// warp w of the 8 epilogue warps stages rows [16 w, 16 w + 16); pos_of(r) = rotary position of tile row r
+template <typename PosFn>
+__device__ __forceinline__ void stage_rope_rows(float* cs_s, const float2* table, int half_hd, int warp, PosFn pos_of) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(table + static_cast<int64_t>(pos_of(r)) * half_hd) + lane);
+    *reinterpret_cast<float4*>(cs_s + r * CS_ROW_FLOATS + lane * 4) = v;
+  }
+}
+
 // 32 columns [c0, c0+32) and their rotary partners [c0+64, c0+96) of one row, fp32 accumulators -> bf16, with the optional
-// inverse rotation (cs = this row's (cos, sin) entries for columns c0..c0+31, or null) and a common scale.
+// inverse rotation (cs = this row's staged (cos, sin) entries for columns c0..c0+31, or null) and a common scale.
 __device__ __forceinline__ void store_rotary_pair_runs(__nv_bfloat16* row, int c0, const uint32_t (&ta)[32], const uint32_t (&tb)[32],
-                                                       float scale, const float2* cs) {
+                                                       float scale, const float* cs) {
   float a[32], b[32];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const float x = __uint_as_float(ta[e]) * scale, y = __uint_as_float(tb[e]) * scale;
-    if (cs) {
-      const float2 k = __ldg(cs + e);
-      a[e] = x * k.x + y * k.y;
-      b[e] = y * k.x - x * k.y;
-    } else {
-      a[e] = x;
-      b[e] = y;
-    }
+  for (int e = 0; e < 32; e += 2) {
+    float4 k = make_float4(1.f, 0.f, 1.f, 0.f);  // (cos, sin) of columns e and e + 1; identity without a table
+    if (cs) k = *reinterpret_cast<const float4*>(cs + 2 * e);
+    const float x0 = __uint_as_float(ta[e]) * scale, y0 = __uint_as_float(tb[e]) * scale;
+    const float x1 = __uint_as_float(ta[e + 1]) * scale, y1 = __uint_as_float(tb[e + 1]) * scale;
+    a[e] = x0 * k.x + y0 * k.y;
+    b[e] = y0 * k.x - x0 * k.y;
+    a[e + 1] = x1 * k.z + y1 * k.w;
+    b[e + 1] = y1 * k.z - x1 * k.w;
   }
   uint4* da = reinterpret_cast<uint4*>(row + c0);
   uint4* db = reinterpret_cast<uint4*>(row + c0 + 64);
@@ -967,15 +983,19 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       uint32_t ta[32], tb[32];
       ptx::tmem_ld32(t_dq + lane_off + half * 32, ta);
       ptx::tmem_ld32(t_dq + lane_off + 64 + half * 32, tb);
-      ptx::tmem_ld_wait();
-      if (row_valid) {
-        const float2* cs = nullptr;
-        if (p.rope_cs) {
-          const int pos = p.rope_pos ? __ldg(p.rope_pos + row0 + tid) : i;
-          cs = p.rope_cs + static_cast<int64_t>(pos) * (HD / 2) + half * 32;
-        }
-        store_rotary_pair_runs(drow, half * 32, ta, tb, p.scale, cs);
+      const float* cs = nullptr;
+      if (p.rope_cs) {  // every MMA has completed (dq_done): the K/V stages are free to hold the tile's table rows
+        static_assert(L::KV_STAGES * 2 * L::KV_BYTES >= CS_STAGE_BYTES, "staging fits in the K/V ring");
+        float* cs_s = reinterpret_cast<float*>(smem + L::OFF_K);
+        stage_rope_rows(cs_s, p.rope_cs, HD / 2, warp, [&](int r) {
+          const int ri = min(q0 + r, p.S - 1);  // rows beyond the sequence are never stored: any valid table row will do
+          return p.rope_pos ? __ldg(p.rope_pos + n * p.S + ri) : ri;
+        });
+        ptx::named_bar_sync(1, 256);
+        cs = cs_s + tid * CS_ROW_FLOATS + half * 64;
       }
+      ptx::tmem_ld_wait();
+      if (row_valid) store_rotary_pair_runs(drow, half * 32, ta, tb, p.scale, cs);
       __syncwarp();
     }
   }
@@ -1265,15 +1285,19 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
       uint32_t ta[32], tb[32];
       ptx::tmem_ld32(t_dk + lane_off + half * 32, ta);
       ptx::tmem_ld32(t_dk + lane_off + 64 + half * 32, tb);
-      ptx::tmem_ld_wait();
-      if (row_ok) {
-        const float2* cs = nullptr;
-        if (p.rope_cs) {
-          const int pos = p.rope_pos ? __ldg(p.rope_pos + static_cast<int64_t>(n) * p.S + k) : k;
-          cs = p.rope_cs + static_cast<int64_t>(pos) * (HD / 2) + half * 32;
-        }
-        store_rotary_pair_runs(krow, half * 32, ta, tb, p.scale, cs);
+      const float* cs = nullptr;
+      if (p.rope_cs) {  // every MMA has completed (done): the Q/dO stages are free to hold the tile's table rows
+        static_assert(2 * L::NS * L::Q_BYTES >= CS_STAGE_BYTES, "staging fits in the Q/dO ring");
+        float* cs_s = reinterpret_cast<float*>(smem + L::OFF_Q);
+        stage_rope_rows(cs_s, p.rope_cs, HD / 2, warp, [&](int r) {
+          const int ki = min(k0 + r, p.S - 1);
+          return p.rope_pos ? __ldg(p.rope_pos + n * p.S + ki) : ki;
+        });
+        ptx::named_bar_sync(1, 256);
+        cs = cs_s + tid * CS_ROW_FLOATS + half * 64;
       }
+      ptx::tmem_ld_wait();
+      if (row_ok) store_rotary_pair_runs(krow, half * 32, ta, tb, p.scale, cs);
       __syncwarp();
     }
   }

@@ -1116,7 +1116,7 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
       if (layer_cb) layer_cb(pending_cb, layer_cb_user);
       pending_cb = -1;
     }
-    if (fuse_rope && hd == 128) {  // inverse rotary embedding of dq / dk inside the attention backward's epilogues
+    if (fuse_rope && fuse_rope_bwd && hd == 128) {  // inverse rotary embedding of dq / dk inside the attention backward's epilogues
       at.rope_cs = rope_cs;
       at.rope_pos = cx.lay.pos;
     }
@@ -1229,6 +1229,10 @@ int Engine::set_option(const char* name, int64_t value) {
   if (strcmp(name, "fuse_swiglu") == 0) {
     if (fuse_swiglu != (value != 0)) drop_frozen_merged();  // the merged copy is built with or without the interleaved weight
     fuse_swiglu = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "fuse_rope_bwd") == 0) {
+    fuse_rope_bwd = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_swiglu_bwd") == 0) {

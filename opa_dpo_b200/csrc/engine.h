@@ -130,6 +130,7 @@ class Engine {
   bool merge_frozen = false;
   // q|k|v projection with RoPE applied in the GEMM epilogue (EPI_BF16_ROPE) instead of a separate in-place pass
   bool fuse_rope = true;
+  bool fuse_rope_bwd = true;  // with fuse_rope: inverse rotation of dq / dk inside the attention backward (option "fuse_rope_bwd")
   // LoRA weight-gradient GEMMs (dB += dy^T t, dA += u^T x) are off the backward's critical path: they run on a side stream,
   // where their tensor-bound tiles overlap the main stream's HBM-bound kernels (SwiGLU / RMSNorm backward, inverse RoPE) and
   // the tails of its persistent dgrad launches. Option "wgrad_stream" (default 1).
