@@ -103,7 +103,7 @@ typedef struct opadpo_attn_desc {
   float* lse;
   const uint64_t* kbits;
   const void* dO; int64_t ld_do;   /* backward only from here */
-  float* delta;
+  float* delta;                    /* f32 [N*S, H] scratch: rowsum(dO * O), written by the backward's first kernel, read by its second */
   void *dq, *dk, *dv; int64_t ld_dqkv;
   /* shared-prefix packing (causal): rows are [prefix | resp_0 | resp_1 ...] with segments of segment_len tokens after
    * prefix_len positions; a response query sees the prefix and its own segment only. segment_len = 0: off. */

@@ -267,12 +267,28 @@ __global__ void rope_table_kernel(float2* cs, int max_pos, int half, float theta
 }
 
 // ---------------------------------------------------------------------------------------------- SwiGLU / GELU
+// (token row, 16 B vector) of a flat thread index. The 64-bit division by a runtime F/8 costs more instructions than the
+// rest of these kernels together; every real shape fits 32 bits.
+__device__ __forceinline__ bool row_and_vec(int64_t T, int fv, int64_t& t, int& v) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = T * fv;
+  if (idx >= total) return false;
+  if (total <= 0xffffffffLL) {
+    const uint32_t i = static_cast<uint32_t>(idx), q = i / static_cast<uint32_t>(fv);
+    t = q;
+    v = static_cast<int>(i - q * static_cast<uint32_t>(fv));
+  } else {
+    t = idx / fv;
+    v = static_cast<int>(idx % fv);
+  }
+  return true;
+}
+
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int64_t T, int F) {
   const int fv = F >> 3;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= T * fv) return;
-  const int64_t t = idx / fv;
-  const int v = static_cast<int>(idx % fv);
+  int64_t t;
+  int v;
+  if (!row_and_vec(T, fv, t, v)) return;
   const uint4* row = reinterpret_cast<const uint4*>(gu + t * 2 * F);
   float g[8], u[8];
   unpack8(row[v], g);
@@ -297,10 +313,9 @@ __global__ void interleave_gate_up_kernel(const bf16* __restrict__ W, bf16* __re
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
                                   int64_t T, int F) {
   const int fv = F >> 3;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= T * fv) return;
-  const int64_t t = idx / fv;
-  const int v = static_cast<int>(idx % fv);
+  int64_t t;
+  int v;
+  if (!row_and_vec(T, fv, t, v)) return;
   const uint4* row = reinterpret_cast<const uint4*>(gu + t * 2 * F);
   float g[8], u[8], da[8], dg[8], du[8];
   unpack8(row[v], g);

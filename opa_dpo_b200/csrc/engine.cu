@@ -93,7 +93,8 @@ int Engine::ensure_wgrad_stream() {
 
 void Engine::wait_side(int kind, cudaStream_t s) {
   if (kind >= 0 && side_pending[kind]) {
-    cudaStreamWaitEvent(s, ev_side[kind], 0);
+    // a failure here would surface as a wrong gradient, not as an error: remember it for the end-of-backward check
+    if (cudaStreamWaitEvent(s, ev_side[kind], 0) != cudaSuccess) side_error = true;
     side_pending[kind] = false;
   }
 }
@@ -604,8 +605,7 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
       EN_CHECK(gemm_checked(a, s));
     }
     if (side) {  // everything the weight gradients read (dy, t, x, u) is complete in main-stream order at this point
-      cudaEventRecord(ev_u, s);
-      cudaStreamWaitEvent(ws, ev_u, 0);
+      if (cudaEventRecord(ev_u, s) != cudaSuccess || cudaStreamWaitEvent(ws, ev_u, 0) != cudaSuccess) side_error = true;
     }
     for (int g = 0; g < G; ++g) {
       GemmArgs w;  // dB_g += dy_g^T t_g
@@ -634,7 +634,7 @@ int Engine::linear_bwd(const LinearW& L, int adapter, const bf16* x, int64_t ldx
     w.ldc = L.in;
     EN_CHECK(gemm_checked(w, ws));
     if (side) {
-      cudaEventRecord(ev_side[side_kind], ws);
+      if (cudaEventRecord(ev_side[side_kind], ws) != cudaSuccess) side_error = true;
       side_pending[side_kind] = true;
     }
   }
@@ -1132,6 +1132,12 @@ int Engine::backward(int save_slot, const float* dlp, const float* dent, cudaStr
   }
   if (side) {  // join: every weight gradient is in the bucket before anything downstream (projector, all-reduce, optimizer)
     for (int k = 0; k < 4; ++k) wait_side(k, s);
+    if (side_error) {
+      side_error = false;
+      cudaStreamSynchronize(wg_stream);
+      set_error("backward: ordering the weight-gradient side stream failed (%s)", cudaGetErrorString(cudaGetLastError()));
+      return OPADPO_ECUDA;
+    }
     if (pending_cb >= 0 && layer_cb) layer_cb(pending_cb, layer_cb_user);
   }
   // image rows -> projector (its LoRA adapters are trainable; the CLIP tower is not differentiated)

@@ -143,6 +143,7 @@ class Engine {
   cudaStream_t wg_stream = nullptr;
   cudaEvent_t ev_u = nullptr;         // main: this linear's u = dy B is enqueued (and, in stream order, its dy / t / x)
   cudaEvent_t ev_side[4] = {};        // side: the weight gradients of linear kind k (0 down, 1 gate|up, 2 o, 3 q|k|v) are done
+  bool side_error = false;            // an event record / wait of the side-stream plumbing failed during this backward
   bool side_pending[4] = {};          // ev_side[k] carries a record nobody on the main stream has waited for since
   int ensure_wgrad_stream();
   void wait_side(int kind, cudaStream_t s);   // main stream waits for the side stream's readers of kind k's dy / u buffers
