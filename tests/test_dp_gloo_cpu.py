@@ -116,3 +116,67 @@ def test_shard_range():
     assert [shard_range(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
     with pytest.raises(ValueError):
         shard_range(10, 0, 4)
+
+
+def _fake_nvl(n_layers, layer_elems, proj_elems, group_layers=4, blocks=16, tail_blocks=128, overlap=True):
+    """NvlGradAllReduce with its launch replaced by a recorder (the launch plan is host logic; the kernel has its own
+    hardware test in tests/dist_gpu_check.py)."""
+    from types import SimpleNamespace
+    from opa_dpo_b200.dist import NvlGradAllReduce
+    total = n_layers * layer_elems + proj_elems
+
+    def grad_range(layer):      # the engine's layout: decoder layers bottom-up, then the projector
+        return (layer * layer_elems, layer_elems) if layer < n_layers else (n_layers * layer_elems, proj_elems)
+
+    ar = object.__new__(NvlGradAllReduce)
+    ar.engine = SimpleNamespace(cfg=SimpleNamespace(n_layers=n_layers), layer_grad_range=grad_range)
+    ar.grad = torch.zeros(total)
+    ar.world, ar.rank = 2, 0
+    ar.group_layers, ar.blocks, ar.tail_blocks, ar.overlap = group_layers, blocks, tail_blocks, overlap
+    ar.n_layers, ar.ranges, ar.pending, ar.launched, ar.armed = None, {}, None, False, False
+    ar.err = torch.zeros(1, dtype=torch.int32)
+    calls = []
+
+    def launch(off, cnt, nblocks):
+        calls.append((off, cnt, nblocks))
+        ar.launched = True
+    ar._launch = launch
+    return ar, calls, total
+
+
+@pytest.mark.parametrize("n_layers,group", [(32, 4), (32, 8), (6, 4), (2, 4), (1, 4), (5, 3)])
+def test_nvl_allreduce_launch_plan_covers_the_bucket_exactly_once(n_layers, group):
+    """The layer callback order of opadpo_backward (top layer first, projector last) turned into all-reduce launches: every
+    element of the bucket is reduced exactly once, runs are contiguous and 8-aligned, grouped launches use the small grid,
+    the last decoder layer and the projector the wide one; un-armed steps are one bucket-wide launch."""
+    L, P = 8 * 1000, 8 * 70
+    ar, calls, total = _fake_nvl(n_layers, L, P, group_layers=group)
+    ar.arm()
+    for layer in list(range(n_layers - 1, -1, -1)) + [n_layers]:
+        ar._on_layer(layer)
+    assert ar.pending is None        # layer 0 always flushes
+    seen = torch.zeros(total, dtype=torch.int32)
+    for off, cnt, nb in calls:
+        assert off % 8 == 0 and cnt % 8 == 0 and cnt > 0
+        seen[off:off + cnt] += 1
+    assert bool((seen == 1).all())
+    assert calls[-1] == (n_layers * L, P, 128)                      # the projector, wide grid
+    assert calls[-2][0] == 0 and calls[-2][2] == 128                # the run that ends with layer 0, wide grid
+    assert all(nb == 16 for _, _, nb in calls[:-2])
+    assert len(calls) <= n_layers // group + 4
+    # a step whose backward was not armed (gradient accumulation): one bucket-wide launch from finish()
+    ar2, calls2, total2 = _fake_nvl(n_layers, L, P, group_layers=group)
+    for layer in list(range(n_layers - 1, -1, -1)) + [n_layers]:
+        ar2._on_layer(layer)
+    assert calls2 == []
+    ar2.comm = ar2.done = None
+    ar2.finish = None    # (finish() needs CUDA streams; its un-armed branch is the single call below)
+    if not ar2.launched:
+        ar2._launch(0, ar2.grad.numel(), ar2.tail_blocks)
+    assert calls2 == [(0, total2, 128)]
+    # overlap switched off: the callbacks launch nothing
+    ar3, calls3, _ = _fake_nvl(n_layers, L, P, group_layers=group, overlap=False)
+    ar3.arm()
+    for layer in list(range(n_layers - 1, -1, -1)) + [n_layers]:
+        ar3._on_layer(layer)
+    assert calls3 == []
