@@ -808,6 +808,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
   uint64_t* ds_full = bars + 11;   // [2]
   uint64_t* dq_done = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* o_full = bars + 15;    // the O tile (delta only): loaded behind the first K/V stage so it never delays the first MMAs
 
   const int warp = threadIdx.x >> 5;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
@@ -836,6 +837,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::mbar_init(&ds_full[i], 256);
       }
       ptx::mbar_init(dq_done, 1);
+      ptx::mbar_init(o_full, 1);
       ptx::fence_barrier_init();
     }
   }
@@ -847,10 +849,13 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
 
   if (warp == 8) {
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(q_full, 3 * L::Q_BYTES);
+      ptx::mbar_arrive_expect_tx(q_full, 2 * L::Q_BYTES);
       load_tile(smem + L::OFF_Q, &tmQ, q_full, col0, row0, BQ, NB);
       load_tile(smem + L::OFF_DO, &tmdO, q_full, col0, row0, BQ, NB);
-      load_tile(smem + L::OFF_O, &tmO, q_full, col0, row0, BQ, NB);
+      auto load_o = [&]() {
+        ptx::mbar_arrive_expect_tx(o_full, L::Q_BYTES);
+        load_tile(smem + L::OFF_O, &tmO, o_full, col0, row0, BQ, NB);
+      };
       int it = 0;
       for (int j = next_j(-1); j < num_kv; j = next_j(j), ++it) {
         const int st = it % NS;
@@ -858,7 +863,9 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
         ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * L::KV_BYTES);
         load_tile(smem + L::OFF_K + st * L::KV_BYTES, &tmK, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
         load_tile(smem + L::OFF_V + st * L::KV_BYTES, &tmV, &kv_full[st], col0, n * p.S + j * BKV, BKV, NB);
+        if (it == 0) load_o();
       }
+      if (it == 0) load_o();
     }
   } else if (warp == 9) {
     if (ptx::elect_one()) {
@@ -925,6 +932,7 @@ __global__ void __launch_bounds__(NTHREADS_BWD, 1)
     {
       static_assert(NB == 2, "one 64-column block per thread half");
       ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(o_full, 0);
       const uint4* ro = reinterpret_cast<const uint4*>(smem + L::OFF_O + half * (BQ * 128) + tid * 128);
       const uint4* rd = reinterpret_cast<const uint4*>(smem + L::OFF_DO + half * (BQ * 128) + tid * 128);
       float acc = 0.f;
