@@ -139,6 +139,54 @@ def test_fused_swiglu_backward_and_rope_backward_equal_the_standalone_kernels():
     eng.close()
 
 
+def test_adopted_gradient_buffer_receives_the_gradients():
+    """opadpo_engine_adopt_grad_buffer (what the data-parallel step uses to accumulate straight into a symmetric-memory
+    bucket): the current gradients move into the caller's buffer, the engine's views point at it, the next backward and
+    zero_grad act on it, the optimizer reads it; too small / unaligned / non-fp32 buffers are rejected."""
+    from oracle import llava_oracle as O
+    from opa_dpo_b200 import POLICY
+    from opa_dpo_b200._lib import OpadpoError
+    oc, ec = _cfgs()
+    eng, w, lp, lr = _build(oc, ec, share_prefix=1)
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, NAMES2, left_pad=2)
+    dev = eng.device
+    args = [images.to(dev), q.to(dev), qm.to(dev), [resp[n].to(dev) for n in NAMES2]]
+
+    def backward():
+        pol_lp, _ = eng.forward_logprobs(POLICY, *args, save_slot=0)
+        d = torch.randn(pol_lp.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3)) * 0.1
+        eng.backward(0, d)
+        torch.cuda.synchronize()
+
+    eng.zero_grad()
+    backward()
+    v = eng.buffers()
+    n = v["n_train"]
+    g0 = v["grad"].clone()
+    assert g0.abs().sum().item() > 0
+    with pytest.raises(OpadpoError):
+        eng.adopt_grad_buffer(torch.zeros(n - 8, device=dev))                       # too small
+    with pytest.raises(OpadpoError):
+        eng.adopt_grad_buffer(torch.zeros(n, device=dev, dtype=torch.bfloat16))     # not fp32
+    buf = torch.full((n + 64,), 7.0, device=dev)
+    eng.adopt_grad_buffer(buf)
+    v2 = eng.buffers()
+    assert v2["grad"].data_ptr() == buf.data_ptr() and v2["grad"].numel() == n
+    assert torch.equal(buf[:n], g0) and bool((buf[n:] == 7.0).all())                # gradients carried over, the tail untouched
+    eng.zero_grad()
+    torch.cuda.synchronize()
+    assert buf[:n].abs().sum().item() == 0
+    backward()
+    rel = ((buf[:n] - g0).norm() / g0.norm()).item()
+    assert rel <= 1e-5, rel                                                         # the same gradient, now in the adopted buffer
+    master0 = v2["master"][:n].clone()
+    norm = eng.optimizer_step(lr=1e-3, max_grad_norm=1.0)
+    torch.cuda.synchronize()
+    assert abs(norm.item() - g0.norm().item()) <= 1e-4 * g0.norm().item()
+    assert not torch.equal(v2["master"][:n], master0)
+    eng.close()
+
+
 def test_side_stream_weight_gradients_equal_main_stream_weight_gradients():
     """opadpo_backward with the LoRA weight-gradient GEMMs on the engine's side stream (default) against the same backward
     with everything on one stream: the same gradient bucket up to the order of the fp32 split-K atomics, three backward
