@@ -55,9 +55,13 @@ def test_struct_layouts_match_header_field_order():
 
     for struct, cls in (("opadpo_gemm_desc", _lib.GemmDesc), ("opadpo_attn_desc", _lib.AttnDesc),
                         ("opadpo_dpo_pair_desc", _lib.DpoPairDesc), ("opadpo_config", _lib.Config),
-                        ("opadpo_sampler", _lib.Sampler)):
+                        ("opadpo_sampler", _lib.Sampler), ("opadpo_allreduce_desc", _lib.AllReduceDesc)):
         assert fields(struct) == [f[0] for f in cls._fields_], struct
     assert ctypes.sizeof(_lib.Sampler) == 24 + 4 + 4 * 8 + 4      # uint64 alignment pads the tail
+    # rank, world | grad, stage_local, stage_mc | 8 + 8 peer addresses | count | epoch, blocks | err_flag | timeout_ms, fp32_in_place
+    assert ctypes.sizeof(_lib.AllReduceDesc) == 8 + 3 * 8 + 16 * 8 + 8 + 8 + 8 + 8
+    assert _lib.MAX_RANKS == 8 and _lib.AR_MAX_BLOCKS == 256 and "#define OPADPO_MAX_RANKS 8" in src and \
+        "#define OPADPO_AR_MAX_BLOCKS 256" in src
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
