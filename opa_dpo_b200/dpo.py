@@ -139,8 +139,9 @@ class FusedDPO:
 
     def compute_policy_loss(self, outputs: Dict[str, Tensor], rollouts: Dict[str, Tensor],
                             outputs_mask: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Dict[str, Tensor]]:
-        """dpo_trainer.py:582-712 + the dpo/policy stats of :776-797 (logging stats on the raw log-probs, :733-751, are
-        left to the caller). `outputs` / `outputs_mask` are AutoregressivePolicy.forward results."""
+        """dpo_trainer.py:582-712 and the flat stats dict of :714-802 with every key the reference returns: `loss/*` (5),
+        `policy/*` (12 reward means / gaps) and `logprobs/*` (15 masked mean / min / max of the raw policy log-probs).
+        `outputs` / `outputs_mask` are AutoregressivePolicy.forward results."""
         a = self.args
         dev = outputs["standard_response_logprobs"].device
         g = lambda k: rollouts[k].to(dev, torch.float32)
@@ -177,17 +178,45 @@ class FusedDPO:
             m3, m4 = (r_std != 0).float(), (r_ai != 0).float()
             rr3 = a.beta * (pm_std.detach() - (0.0 if a.reference_free else 1.0) * rm_std)
             rr4 = a.beta * (pm_ai.detach() - (0.0 if a.reference_free else 1.0) * rm_ai)
-            stats.update({"policy/stand_mask_chosen_mean": o3[2], "policy/stand_mask_reject_mean": (rr3 * m3).sum() / m3.sum(),
-                          "policy/AI_mask_chosen_mean": o4[2], "policy/AI_mask_reject_mean": (rr4 * m4).sum() / m4.sum()})
-        elif a.AncPO:
-            # without CoPO the reference adds the anchor on chosen_rewards3/4 == 0 (scalars): -logsigmoid(-a) - logsigmoid(a)
-            # resp. 2*a^2 (dpo_trainer.py:700-708); constants w.r.t. the parameters
-            av = torch.tensor(a.Anchor_value, device=dev)
-            const = (-torch.nn.functional.logsigmoid(-av) - torch.nn.functional.logsigmoid(av)) if a.mDPO_anchor else 2 * av * av
-            loss = loss + const * a.Anchor_coef
-            anc = anc + const
+            rj3, rj4 = (rr3 * m3).sum() / m3.sum(), (rr4 * m4).sum() / m4.sum()
+            stats.update({"policy/stand_mask_chosen_mean": o3[2], "policy/stand_mask_reject_mean": rj3,
+                          "policy/stand_mask_gap_mean": o3[2] - rj3, "policy/AI_mask_chosen_mean": o4[2],
+                          "policy/AI_mask_reject_mean": rj4, "policy/AI_mask_gap_mean": o4[2] - rj4})
+            lpm_std, lpm_ai = pm_std.detach(), pm_ai.detach()
+        else:
+            # the reference reports the masked pairs' rewards (scalar zeros, dpo_trainer.py:694-700) under the same keys
+            stats.update({f"policy/{p}_mask_{q}_mean": zero for p in ("stand", "AI") for q in ("chosen", "reject", "gap")})
+            lpm_std = lpm_ai = torch.zeros_like(p_std, dtype=torch.float32)
+            if a.AncPO:
+                # without CoPO the reference adds the anchor on chosen_rewards3/4 == 0 (scalars): -logsigmoid(-a) - logsigmoid(a)
+                # resp. 2*a^2 (dpo_trainer.py:700-708); constants w.r.t. the parameters
+                av = torch.tensor(a.Anchor_value, device=dev)
+                const = (-torch.nn.functional.logsigmoid(-av) - torch.nn.functional.logsigmoid(av)) if a.mDPO_anchor else 2 * av * av
+                loss = loss + const * a.Anchor_coef
+                anc = anc + const
         stats["loss/AncPO"] = anc
+        stats.update(_logprob_stats(p_org.detach(), p_std.detach(), p_ai.detach(), lpm_std, lpm_ai))
         return loss, {k: v.detach() for k, v in stats.items()}
+
+
+def _logprob_stats(lp_org: Tensor, lp_std: Tensor, lp_ai: Tensor, lpm_std: Tensor, lpm_ai: Tensor) -> Dict[str, Tensor]:
+    """The `logprobs/*` block of compute_policy_loss's stats (dpo_trainer.py:714-751): masked mean over the batch, and the
+    batch mean of every row's masked minimum / maximum, of the five raw policy log-prob arrays. A token counts when the
+    policy's own log-prob there is non-zero (pads are exactly 0); the two masked-image arrays use the unmasked arrays'
+    masks, as the reference does. All five arrays go through one batched reduction each instead of 15 separate ones."""
+    L = torch.stack([lp_org, lp_std, lp_ai, lpm_std, lpm_ai]).float()          # [5, b, R]
+    m_org, m_std, m_ai = lp_org != 0, lp_std != 0, lp_ai != 0
+    M = torch.stack([m_org, m_std, m_ai, m_std, m_ai])
+    mean = (L * M).sum((1, 2)) / M.sum((1, 2))
+    lo = torch.where(M, L, L.new_tensor(1e9)).amin(2).mean(1)
+    hi = torch.where(M, L, L.new_tensor(-1e9)).amax(2).mean(1)
+    names = ("original", "standard", "AI", "standard_mask", "AI_mask")
+    out = {}
+    for i, n in enumerate(names):
+        out[f"logprobs/{n}_logprobs"] = mean[i]
+        out[f"logprobs/{n}_logprobs_min"] = lo[i]
+        out[f"logprobs/{n}_logprobs_max"] = hi[i]
+    return out
 
 
 class DPOStepper:

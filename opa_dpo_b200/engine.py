@@ -109,6 +109,29 @@ def required_tensor_names(cfg: EngineConfig) -> List[str]:
     return names
 
 
+def check_call_shapes(cfg: EngineConfig, images, queries, qmask, responses: Sequence = (), img_mask=None, what: str = "forward_logprobs"):
+    """The C ABI takes plain pointers + sizes, so an array of the wrong extent would be read out of bounds on the device:
+    every array's shape is checked against (b, Q, R) and the configured image size before its pointer crosses the boundary.
+    (The reference fails in the first torch op that meets the mismatch; here it is an OpadpoError naming the argument.)"""
+    if queries.dim() != 2:
+        raise OpadpoError(f"{what}: queries must be [b, Q], got {tuple(queries.shape)}")
+    b, Q = queries.shape
+    if b < 1 or Q < 1:
+        raise OpadpoError(f"{what}: empty batch (queries {tuple(queries.shape)})")
+    want_img = (b, 3, cfg.v_image, cfg.v_image)
+    if tuple(images.shape) != want_img:
+        raise OpadpoError(f"{what}: images must be {want_img} (one {cfg.v_image}x{cfg.v_image} image per query), got {tuple(images.shape)}")
+    if tuple(qmask.shape) != (b, Q):
+        raise OpadpoError(f"{what}: the query attention mask must be [{b}, {Q}], got {tuple(qmask.shape)}")
+    if responses:
+        R = responses[0].shape[-1]
+        for i, r in enumerate(responses):
+            if tuple(r.shape) != (b, R):
+                raise OpadpoError(f"{what}: response {i} must be [{b}, {R}] like the first one, got {tuple(r.shape)}")
+    if img_mask is not None and tuple(img_mask.shape) != (b, cfg.n_patches):
+        raise OpadpoError(f"{what}: the image-token mask must be [{b}, {cfg.n_patches}], got {tuple(img_mask.shape)}")
+
+
 class Engine:
     def __init__(self, cfg: EngineConfig, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
@@ -244,6 +267,9 @@ class Engine:
                          responses: Sequence[torch.Tensor], temperature: float = 1.0, img_mask: Optional[torch.Tensor] = None,
                          save_slot: int = -1, want_entropy: bool = True):
         """-> (logprobs [K,b,R] f32, entropies [K,b,R] f32 or None). All inputs must already be on the device."""
+        if len(responses) < 1:
+            raise OpadpoError("forward_logprobs: at least one response array")
+        check_call_shapes(self.cfg, images, queries, qmask, responses, img_mask)
         b, Q = queries.shape
         K, R = len(responses), responses[0].shape[1]
         images = images.to(torch.float32).contiguous()
@@ -289,6 +315,7 @@ class Engine:
     def generate(self, adapter: int, images: torch.Tensor, queries: torch.Tensor, qmask: torch.Tensor, max_new_tokens: int,
                  do_sample: bool = False, top_k: int = 0, top_p: float = 1.0, temperature: float = 1.0, seed: int = 0,
                  suppress_tokens=None):
+        check_call_shapes(self.cfg, images, queries, qmask, what="generate")
         b, Q = queries.shape
         sup = [int(t) for t in (suppress_tokens or [])]
         if len(sup) > 8:

@@ -209,7 +209,17 @@ class B200LlavaModel(nn.Module):
         Greedy ids reproduce the reference exactly; sampling follows HF's warper order with a counter-based RNG seeded from
         torch.initial_seed() (same distribution, not the same random stream as torch.multinomial)."""
         if num_return_sequences != 1:
-            raise NotImplementedError("num_return_sequences > 1")
+            # [UPSTREAM transformers generate()]: every prompt row is repeated num_return_sequences times in place
+            # (row 0's copies first); greedy decoding of identical copies is rejected there as well. The copies draw from
+            # different random streams because the sampler's counter RNG is keyed by (seed, row, position).
+            if not do_sample:
+                raise ValueError("Greedy methods without beam search do not support `num_return_sequences` different than 1 "
+                                 f"(got {num_return_sequences}).")
+            n = int(num_return_sequences)
+            inputs, images, attention_mask = (t.repeat_interleave(n, dim=0) for t in (inputs, images, attention_mask))
+        if pad_token_id is not None and int(pad_token_id) != self.cfg.pad_id:
+            raise OpadpoError(f"generate(pad_token_id={pad_token_id}): the engine was built with pad_id {self.cfg.pad_id} "
+                              "(EngineConfig.pad_id; the reference pads with unk = 0, opadpo_train.py:696-698)")
         self._gen_calls = getattr(self, "_gen_calls", 0) + 1
         seed = (int(torch.initial_seed()) * 1000003 + self._gen_calls) & (2 ** 63 - 1)
         aid = ADAPTER_IDS[self.active_adapter]
@@ -278,10 +288,10 @@ class AutoregressivePolicy(Policy):
             temperature = self.args.temperature
         seq = self.base_model.generate(inputs=queries, images=images, attention_mask=query_attn_masks, do_sample=True,
                                        max_new_tokens=self.args.response_len, top_p=1.0, top_k=0, temperature=temperature,
-                                       pad_token_id=self.base_tokenizer.pad_token_id,
+                                       pad_token_id=self.base_tokenizer.pad_token_id, num_return_sequences=num_return_sequences,
                                        suppress_tokens=([self.base_tokenizer.eos_token_id]
                                                         if getattr(self.args, "suppress_eos_at_generation", False) else None))
-        return dict(responses=seq[:, queries.size(1):])
+        return dict(responses=seq[:, queries.size(1):])     # [bsz * num_return_sequences, response_len], already right-padded
 
 
 def make_policy_with_base_model(args, base_model, base_tokenizer, adapter_name: Optional[str] = "default"):

@@ -83,6 +83,8 @@ class B200DPOTrainer:
         self.device = device if device is not None else self.model.engine.device
         self.world_size, self.process_group = world_size, process_group
         self._micro_step = 0
+        self.log_fn: Optional[Callable] = None        # log_fn(stats, step=) <- accelerator.log (dpo_trainer.py:832-833)
+        self.last_train_stats: Dict[str, Tensor] = {}
         self.max_step = getattr(args, "max_step", B200DPOTrainer.max_step)
         self.overlap = None
         if world_size > 1 and self.model.flat_param is not None:
@@ -215,10 +217,38 @@ class B200DPOTrainer:
     def train(self, dataset_len: int, train_dataloader_factory: Callable[[], Iterable], resume_training_ckpt: Optional[str] = None):
         return train_loop(self, dataset_len, train_dataloader_factory, resume_training_ckpt)
 
-    def step(self, train_dataloader, step_idx: int = 0) -> Dict[str, Tensor]:
+    def step(self, train_dataloader, step_idx: int = 0) -> Dict[str, float]:
+        """RLTrainer.step (rl_trainer.py:181-195): rollout -> optimisation epochs -> scheduler -> the logged stats dict of
+        record_step_stats. The per-optimizer-step tensors of step_with_rollouts stay readable as `last_train_stats`."""
         batches = [next(train_dataloader) for _ in range(self.args.rollout_accumulation_steps)]
         rollouts = self.rollout(batches)
-        stats = self.step_with_rollouts(rollouts)
+        self.last_train_stats = self.step_with_rollouts(rollouts)
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
-        return stats
+        return self.record_step_stats(train_stats=self.last_train_stats, rollouts=rollouts, step_idx=step_idx)
+
+    def record_step_stats(self, train_stats: Dict[str, Tensor], rollouts: Dict[str, Tensor], step_idx: int, **_kwargs) -> Dict[str, float]:
+        """DPOTrainer.record_step_stats (dpo_trainer.py:804-835): `objective/lr`, `objective/<key>` = batch mean of the
+        per-row mean entropy over non-zero positions for every `*entropies*` rollout key, `dpo/<key>` (`logprobs/<key>`
+        kept as is) = mean over the optimizer steps of the outer step; python floats; any '/' behind the first one turned
+        into '-'. Rank 0 hands the dict to `log_fn(stats, step=step_idx)` (the accelerator.log stand-in) when one is set.
+        All tensor values are read back with ONE device-to-host copy instead of one `.item()` per key."""
+        stats: Dict[str, object] = {"objective/lr": self.optimizer.param_groups[0]["lr"]}
+        for key in rollouts:
+            if "entropies" in key:
+                ent = rollouts[key]
+                m = ent != 0.0
+                stats[f"objective/{key}"] = ((ent * m).sum(1, keepdim=True) / m.sum(1, keepdim=True)).mean()
+        for k, v in train_stats.items():
+            stats[k if "logprobs/" in k else f"dpo/{k}"] = v.mean(dim=0)
+        tkeys = [k for k, v in stats.items() if torch.is_tensor(v)]
+        if tkeys:
+            flat = torch.stack([stats[k].reshape(()).float() for k in tkeys]).tolist()
+            stats.update(zip(tkeys, flat))
+        renamed = {}
+        for key, value in stats.items():
+            cut = key.find("/") + 1
+            renamed[key[:cut] + key[cut:].replace("/", "-") if "/" in key else key] = value
+        if self.log_fn is not None and int(os.environ.get("RANK", 0)) == 0:
+            self.log_fn(renamed, step=step_idx)
+        return renamed

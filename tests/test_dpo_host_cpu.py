@@ -103,7 +103,7 @@ def test_compute_policy_loss_composition_vs_reference_all_switches():
                        response_image_relation=use_rel, response_len=R)
         loss, stats = FusedDPO(mine, pair_impl=torch_pair).compute_policy_loss(dict(pol), rollouts, dict(polm) if copo else None)
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+        assert set(stats) == set(stats_ref), set(stats) ^ set(stats_ref)     # loss/* 5, policy/* 12, logprobs/* 15
         for k, v in stats.items():
-            assert k in stats_ref, k
             assert abs(v.item() - stats_ref[k].item()) <= 1e-5 * max(1.0, abs(stats_ref[k].item())), (k, v.item(), stats_ref[k].item())
     check()

@@ -1000,7 +1000,8 @@ def test_trainer_mirror_outer_step_matches_manual_composition():
     model, policy, ref_policy, opt = make()
     tr = B200DPOTrainer(args, policy, ref_policy, opt)
     torch.manual_seed(7)
-    stats = tr.step(iter(batches))
+    tr.step(iter(batches))
+    stats = tr.last_train_stats
     torch.cuda.synchronize()
     assert stats["loss/grad_norm"].shape == (2,) and torch.isfinite(stats["loss/grad_norm"]).all()   # 4 micro-batches / gas 2
     got = model.engine.buffers()["master"].clone()

@@ -98,8 +98,14 @@ def test_collator_trainer_checkpoint_pipeline(tmp_path):
     trainer = B200DPOTrainer(args, policy, ref_policy, opt, sch)
     before = model.engine.buffers()["master"].clone()
     torch.manual_seed(3)
-    stats = trainer.step(iter(batches), step_idx=1)
+    logged = trainer.step(iter(batches), step_idx=1)          # what the reference's step returns: the logged floats
     torch.cuda.synchronize()
+    import math
+    assert {"objective/lr", "dpo/loss-grad_norm", "dpo/policy-stand_gen_gap_mean", "logprobs/original_logprobs",
+            "objective/ref_base_standard_response_entropies"} <= set(logged)
+    assert all(isinstance(v, float) and math.isfinite(v) for v in logged.values()), logged
+    stats = trainer.last_train_stats                           # per-optimizer-step tensors of step_with_rollouts
+    assert abs(logged["dpo/loss-grad_norm"] - stats["loss/grad_norm"].mean().item()) <= 1e-6 * abs(logged["dpo/loss-grad_norm"])
     assert opt.step_count == 2 and stats["loss/grad_norm"].shape == (2,)
     for k, v in stats.items():
         assert torch.isfinite(v).all(), k

@@ -111,3 +111,67 @@ def test_respond_arguments_match_reference_call():
     pol.train()
     with pytest.raises(AssertionError):
         pol.respond(q, q != 0)
+
+
+def test_generate_num_return_sequences_and_argument_errors():
+    """B200LlavaModel.generate (the `model.generate` surface of online_generator.py:292-310 / rl_models.py:166-188):
+    num_return_sequences repeats every prompt row in place (transformers' repeat_interleave expansion), greedy with more
+    than one return sequence is rejected as transformers rejects it, a pad id other than the engine's is refused, and every
+    call gets a new RNG seed. The engine is a recording stub here (the product's engine needs a GPU)."""
+    from opa_dpo_b200.engine import EngineConfig
+    from opa_dpo_b200.policy import AutoregressivePolicy, B200LlavaModel
+    from opa_dpo_b200._lib import OpadpoError
+    calls = []
+
+    class Eng:
+        def generate(self, aid, images, queries, qmask, max_new, **kw):
+            calls.append(dict(aid=aid, images=images, queries=queries, qmask=qmask, max_new=max_new, **kw))
+            return torch.cat([queries, torch.full((queries.size(0), max_new), 7)], 1)
+
+    model = object.__new__(B200LlavaModel)
+    torch.nn.Module.__init__(model)
+    model.cfg = EngineConfig(v_image=28, v_patch=14)
+    model.engine, model.active_adapter = Eng(), "lora_policy"
+    q = torch.tensor([[0, 5, -200, 6], [7, 8, -200, 9]])
+    img = torch.arange(2.0).view(2, 1, 1, 1).expand(2, 3, 28, 28)
+    out = model.generate(inputs=q, images=img, attention_mask=q != 0, do_sample=True, max_new_tokens=3, pad_token_id=0,
+                         top_k=30, top_p=0.95, temperature=1.2, num_return_sequences=3, synced_gpus=True)
+    assert out.shape == (6, 7)
+    c = calls[-1]
+    assert torch.equal(c["queries"], q[[0, 0, 0, 1, 1, 1]]) and torch.equal(c["qmask"], (q != 0)[[0, 0, 0, 1, 1, 1]])
+    assert torch.equal(c["images"][:, 0, 0, 0], torch.tensor([0.0, 0, 0, 1, 1, 1]))
+    assert c["do_sample"] is True and c["top_k"] == 30 and c["top_p"] == 0.95 and c["temperature"] == 1.2 and c["max_new"] == 3
+    model.generate(inputs=q, images=img, attention_mask=q != 0, do_sample=True, max_new_tokens=3)
+    assert calls[-1]["seed"] != c["seed"] and calls[-1]["queries"].shape == (2, 4)
+    with pytest.raises(ValueError, match="num_return_sequences"):
+        model.generate(inputs=q, images=img, attention_mask=q != 0, do_sample=False, max_new_tokens=3, num_return_sequences=2)
+    with pytest.raises(OpadpoError, match="pad_id"):
+        model.generate(inputs=q, images=img, attention_mask=q != 0, max_new_tokens=3, pad_token_id=32000)
+
+    # Policy._respond passes num_return_sequences through (rl_models.py:166-183) and returns [b * n, response_len]
+    pol = AutoregressivePolicy(SimpleNamespace(temperature=1.0, response_len=3, suppress_eos_at_generation=True), model,
+                               SimpleNamespace(pad_token_id=0, eos_token_id=2), "lora_policy")
+    pol.eval()
+    model.get_vision_tower = lambda: SimpleNamespace(num_patches=4)
+    model.config = SimpleNamespace(use_cache=False, cache_shape=None)
+    r = pol.respond(q, q != 0, images=img, num_return_sequences=2)["responses"]
+    assert r.shape == (4, 3) and calls[-1]["suppress_tokens"] == [2] and calls[-1]["queries"].shape == (4, 4)
+
+
+def test_call_shapes_are_checked_before_pointers_cross_the_abi():
+    from opa_dpo_b200.engine import EngineConfig, check_call_shapes
+    from opa_dpo_b200._lib import OpadpoError
+    cfg = EngineConfig(v_image=28, v_patch=14)
+    b, Q, R = 2, 5, 4
+    img, q, qm = torch.zeros(b, 3, 28, 28), torch.zeros(b, Q, dtype=torch.long), torch.ones(b, Q, dtype=torch.bool)
+    resp = [torch.zeros(b, R, dtype=torch.long)] * 2
+    check_call_shapes(cfg, img, q, qm, resp, torch.ones(b, 4))
+    check_call_shapes(cfg, img, q, qm, what="generate")
+    bad = [dict(images=torch.zeros(b, 3, 14, 14)), dict(images=torch.zeros(1, 3, 28, 28)), dict(qmask=torch.ones(b, Q + 4)),
+           dict(responses=[resp[0], torch.zeros(b, R + 1, dtype=torch.long)]), dict(responses=[torch.zeros(1, R, dtype=torch.long)]),
+           dict(img_mask=torch.ones(b, 5)), dict(queries=torch.zeros(Q, dtype=torch.long)), dict(queries=torch.zeros(0, Q, dtype=torch.long))]
+    for kw in bad:
+        args = dict(images=img, queries=q, qmask=qm, responses=resp, img_mask=None)
+        args.update(kw)
+        with pytest.raises(OpadpoError):
+            check_call_shapes(cfg, **args)

@@ -156,3 +156,83 @@ def test_oracle_warpers_equal_transformers_logits_processors(top_k, top_p, tempe
     keep = ~torch.isinf(want)
     assert torch.allclose(got[keep], want[keep], rtol=1e-6, atol=0)
     assert keep.any(-1).all()
+
+
+class LearnableStubPolicy(StubPolicy):
+    """StubPolicy whose log-probs depend on one trainable scalar, so step_with_rollouts can differentiate the loss."""
+
+    def __init__(self, salt):
+        super().__init__(salt)
+        self.theta = torch.nn.Parameter(torch.tensor(0.3))
+
+    def __call__(self, *a, **kw):
+        out = super().__call__(*a, **kw)
+        return {k: (v * (1.0 + self.theta) if k.endswith("_logprobs") else v) for k, v in out.items()}
+
+
+class StubOptimizer:
+    def __init__(self, params, lr):
+        self.param_groups, self.params, self.steps = [dict(lr=lr)], params, 0
+
+    def step(self, scale=1.0):
+        self.steps += 1
+        return torch.stack([p.grad.detach().norm() for p in self.params]).norm()
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+
+@pytest.mark.parametrize("copo", [False, True])
+def test_step_returns_reference_record_step_stats(copo):
+    """Row a6: B200DPOTrainer.step = rollout -> step_with_rollouts -> scheduler -> record_step_stats, and what it returns /
+    logs is the reference's DPOTrainer.record_step_stats (dpo_trainer.py:804-835) run VERBATIM on the same train stats and
+    rollouts: same keys ('dpo/loss-grad_norm', 'logprobs/…', 'objective/lr', 'objective/<entropies>'), python floats."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    import opadpo.dpo_models.dpo_trainer as dpo_trainer
+    from opa_dpo_b200.dpo import DPOArgs, FusedDPO
+    from opa_dpo_b200.trainer import B200DPOTrainer
+    from test_dpo_host_cpu import torch_pair
+    g = torch.Generator().manual_seed(5)
+    b, Q, R = 2, 6, 5
+    batches = []
+    for _ in range(4):
+        bt = {"images": torch.randn(b, 3, 28, 28, generator=g), "queries": torch.randint(3, 99, (b, Q), generator=g),
+              "queries_attention_mask": torch.ones(b, Q, dtype=torch.long)}
+        for n in NAMES:
+            r = torch.randint(3, 99, (b, R), generator=g)
+            r[0, 3:] = 0
+            bt[n] = r
+            bt[n + "_attention_mask"] = (r != 0).long()
+        batches.append(bt)
+    args = DPOArgs(CoPO=copo, CoPO_method="random", CoPO_mask_ratio=0.3, AncPO=True, temperature=1.0, bf16=False, response_len=R,
+                   rollout_accumulation_steps=4, step_per_device_batch_size=2, gradient_accumulation_steps=2, noptepochs=1)
+    pol, ref = LearnableStubPolicy(0.5), StubPolicy(0.25)
+    opt = StubOptimizer([pol.theta], lr=3e-6)
+    logged = []
+    tr = B200DPOTrainer(args, pol, ref, opt, mask_ops=OracleMaskOps(), loss=FusedDPO(args, pair_impl=torch_pair),
+                        device=torch.device("cpu"))
+    tr.log_fn = lambda stats, step: logged.append((step, dict(stats)))
+    torch.manual_seed(2)
+    got = tr.step(iter(batches), step_idx=7)
+    assert opt.steps == 2 and tr.last_train_stats["loss/grad_norm"].shape == (2,)     # 8 rows / 2 per micro-batch / gas 2
+    assert logged == [(7, got)]
+    assert all(isinstance(v, float) for v in got.values())
+
+    torch.manual_seed(2)
+    rollouts = tr.rollout(batches)           # the same rollouts again (the mask stream is re-seeded)
+    rt = object.__new__(dpo_trainer.DPOTrainer)
+    rt.optimizer = opt
+    ref_logged = []
+    rt.accelerator = SimpleNamespace(is_main_process=True, log=lambda stats, step: ref_logged.append((step, stats)))
+    want = rt.record_step_stats(train_stats=tr.last_train_stats, rollouts=rollouts, step_idx=7)
+    assert set(got) == set(want), sorted(set(got) ^ set(want))
+    assert {"objective/lr", "dpo/loss-grad_norm", "dpo/loss-AncPO", "dpo/policy-AI_mask_gap_mean", "logprobs/AI_mask_logprobs_max",
+            "objective/ref_base_standard_response_entropies"} <= set(got)
+    assert len(got) == 1 + (5 if copo else 3) + 33      # lr, entropy keys of the rollouts, 32 policy-loss stats + grad_norm
+    for k, v in want.items():
+        assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
+    assert ref_logged[0][0] == 7 and set(ref_logged[0][1]) == set(got)
