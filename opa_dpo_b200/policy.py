@@ -10,6 +10,7 @@ the PEFT-wrapped LlavaLlamaForCausalLM (`base_model`): `set_adapter`, `config.us
 from __future__ import annotations
 
 import json
+import math
 import os
 import weakref
 from types import SimpleNamespace
@@ -19,7 +20,7 @@ import torch
 from torch import Tensor, nn
 
 from .engine import BASE, POLICY, REF, Engine, EngineConfig, linear_modules
-from ._lib import OpadpoError
+from ._lib import OpadpoError, OpadpoUnknownName
 
 ADAPTER_IDS = {"lora_policy": POLICY, "lora_ref_policy": REF, "lora_default": POLICY, None: BASE}
 
@@ -62,9 +63,11 @@ class B200LlavaModel(nn.Module):
     qlora_model.get_accelerate_model :44-294): one shared base + adapters 'lora_policy' (trainable) and
     'lora_ref_policy' (frozen)."""
 
-    def __init__(self, cfg: EngineConfig, device=None, base_model_name_or_path: str = ""):
+    def __init__(self, cfg: EngineConfig, device=None, base_model_name_or_path: str = "", engine=None):
+        """`engine`: an already-built engine handle to wrap instead of creating one (the CPU tests pass a recorder to check
+        the host logic of make_models / adapter loading; the package itself only ever builds `Engine`, which needs a GPU)."""
         super().__init__()
-        self.engine = Engine(cfg, device)
+        self.engine = engine if engine is not None else Engine(cfg, device)
         self.cfg = cfg
         self.config = SimpleNamespace(use_cache=False, cache_shape=None, vocab_size=cfg.vocab, hidden_size=cfg.d_model)
         self.active_adapter: Optional[str] = "lora_policy"
@@ -120,6 +123,20 @@ class B200LlavaModel(nn.Module):
                 continue
             self.engine.load_lora(aid, short, ab["A"], ab["B"])
         self.peft_config.setdefault(name, self.default_peft_config())
+
+    def add_adapter(self, name: str, is_trainable: bool = False, peft_config: Optional[dict] = None, generator=None):
+        """A freshly initialised adapter on every LoRA target (qlora_model.py:84-113, the `train_from_sft=False` branch:
+        `model.add_adapter(LoraConfig(r, lora_alpha, ...), adapter_name)`), with PEFT's reset_lora_parameters init
+        [UPSTREAM peft 0.5.0 tuners/lora.py]: A ~ kaiming_uniform(a = sqrt(5)), B = 0."""
+        aid = ADAPTER_IDS[name]
+        r = self.cfg.lora_r
+        for mod, (out_f, in_f) in linear_modules(self.cfg).items():
+            A = torch.empty(r, in_f)
+            torch.nn.init.kaiming_uniform_(A, a=math.sqrt(5), generator=generator)
+            self.engine.load_lora(aid, mod, A, torch.zeros(out_f, r))
+        self.peft_config[name] = dict(peft_config) if peft_config is not None else self.default_peft_config()
+        if is_trainable:
+            self.make_trainable(name)
 
     def adapter_state_dict(self, name: str) -> Dict[str, Tensor]:
         aid = ADAPTER_IDS[name]
@@ -297,3 +314,55 @@ class AutoregressivePolicy(Policy):
 def make_policy_with_base_model(args, base_model, base_tokenizer, adapter_name: Optional[str] = "default"):
     """rl_models.py:193-204."""
     return AutoregressivePolicy(args, base_model, base_tokenizer, adapter_name=adapter_name)
+
+
+def make_models(base_model, tokenizer, args, accelerator=None, num_new_tokens: int = 0,
+                resume_from_checkpoint: Optional[str] = None, model_factory=None) -> dict:
+    """DPOTrainer's model construction (dpo_trainer.py:958-1038 over load_nbit_model_for_inference /
+    get_accelerate_model, qlora_model.py:44-127, 297-356), same signature and return dict `{policy, ref_policy}`:
+
+    * the adapter directory is `args.policy_model_name_or_path` resolved through `[adapter_model/][lora_default/]`; the
+      policy adapter of a resumed run comes from `<resume_from_checkpoint>/adapter_model/lora_policy` instead (:983-987);
+    * the base checkpoint is the one `adapter_config.json` names (`base_model_name_or_path`, qlora_model.py:327-328), the
+      LoRA rank / alpha are the ones it records; ONE base is shared by both adapters (REGISTERED_BASE_MODELS);
+    * `args.train_from_sft` (default True): both adapters start from the checkpoint's weights, `lora_policy` trainable and
+      `lora_ref_policy` frozen; False: both are freshly initialised with the recorded LoRA config (qlora_model.py:92-113);
+    * afterwards the vision tower / projector tensors are re-read from `args.base_model_name`
+      (`loading_vision_tower_parameter`, opadpo_train.py:539-557), when that is another directory than the base.
+    `base_model`: an already-loaded B200LlavaModel to reuse (None builds one on `accelerator.device`); there is no
+    `accelerator.prepare` — data parallelism is dist.py's. New tokens (smart_tokenizer_and_embedding_resize, :934-955) are
+    refused: the engine's vocabulary is the checkpoint's and its embeddings are frozen."""
+    from . import checkpoint
+    if num_new_tokens > 0:
+        raise OpadpoError("make_models: num_new_tokens > 0 needs trainable, resized embeddings; the engine trains LoRA tensors only")
+    adapter_dir = checkpoint.resolve_adapter_dir(args.policy_model_name_or_path)
+    policy_dir = adapter_dir
+    if resume_from_checkpoint:
+        policy_dir = os.path.join(resume_from_checkpoint, "adapter_model", "lora_policy")
+    with open(os.path.join(adapter_dir, "adapter_config.json")) as f:
+        lora_cfg = json.load(f)
+    base_path = lora_cfg["base_model_name_or_path"]
+    if base_model is None:
+        cfg = checkpoint.engine_config_from_hf(base_path, lora_r=int(lora_cfg["r"]), lora_alpha=float(lora_cfg["lora_alpha"]))
+        factory = model_factory if model_factory is not None else B200LlavaModel
+        base_model = factory(cfg, device=getattr(accelerator, "device", None), base_model_name_or_path=base_path)
+        checkpoint.load_llava_base(base_model.engine, base_path)
+    if getattr(args, "train_from_sft", True):
+        base_model.load_adapter(adapter_dir, "lora_ref_policy", is_trainable=False)
+        base_model.load_adapter(policy_dir, "lora_policy", is_trainable=True)
+    else:
+        base_model.add_adapter("lora_ref_policy", is_trainable=False, peft_config=lora_cfg)
+        if resume_from_checkpoint:
+            base_model.load_adapter(policy_dir, "lora_policy", is_trainable=True)
+        else:
+            base_model.add_adapter("lora_policy", is_trainable=True, peft_config=lora_cfg)
+    tower_src = getattr(args, "base_model_name", None)
+    if tower_src and os.path.abspath(tower_src.rstrip("/")) != os.path.abspath(base_path.rstrip("/")):
+        for name, t in checkpoint.iter_checkpoint_tensors(tower_src, lambda n: "vision_tower" in n or "mm_projector" in n):
+            try:
+                base_model.engine.load_tensor(name, t)
+            except OpadpoUnknownName:
+                pass          # a tensor the engine does not execute (e.g. the tower's last layer): the reference skips unknown names too
+    policy = make_policy_with_base_model(args, base_model, tokenizer, adapter_name="lora_policy")
+    ref_policy = make_policy_with_base_model(args, base_model, tokenizer, adapter_name="lora_ref_policy")
+    return dict(policy=policy, ref_policy=ref_policy)

@@ -159,3 +159,113 @@ def test_last_checkpoint_contract_vs_reference_function(tmp_path):
     assert mine(str(d)) == ref(str(d))
     (d / "completed").write_text("")
     assert mine(str(d)) == ref(str(d)) == (None, True)
+
+
+def test_make_models_mirrors_reference_construction(tmp_path):
+    """policy.make_models (dpo_trainer.py:958-1038 over qlora_model.py:44-127,297-356): which directories are read, which
+    base the adapters sit on, the two adapter names on ONE shared base, trainable / frozen, the resumed policy adapter,
+    the fresh-adapter branch (train_from_sft=False: A ~ kaiming_uniform, B = 0) and the vision-tower re-read from
+    args.base_model_name. The engine is a recorder (the product's engine needs a GPU)."""
+    import math
+    from types import SimpleNamespace
+    from opa_dpo_b200 import policy as P
+    from opa_dpo_b200.engine import EngineConfig, linear_modules
+    from opa_dpo_b200._lib import OpadpoError, OpadpoUnknownName
+    base, clip, s1, s2, cs = _fake_llava(tmp_path)
+    tiny = EngineConfig(d_model=8, n_layers=1, n_heads=1, d_ffn=16, vocab=32, v_d=4, v_layers=1, v_heads=1, v_ffn=8, v_image=28,
+                        v_patch=14, lora_r=2, lora_alpha=4.0)
+    mods = linear_modules(tiny)
+
+    class RecEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.cfg, self.tensors, self.lora, self.trainable = tiny, {}, {}, None
+
+        def load_tensor(self, name, t):
+            if "inv_freq" in name or "post_layernorm" in name:
+                raise OpadpoUnknownName("unknown tensor")
+            self.tensors[name] = t.clone()
+
+        def lora_shape(self, module):
+            if module not in mods:
+                raise OpadpoError("not a LoRA target")
+            return mods[module]
+
+        def load_lora(self, aid, module, A, B):
+            assert A.shape == (2, mods[module][1]) and B.shape == (mods[module][0], 2), module
+            self.lora[(aid, module)] = (A.clone(), B.clone())
+
+        def set_trainable(self, aid):
+            self.trainable = aid
+
+        def buffers(self):
+            return dict(master=torch.zeros(8), grad=torch.zeros(8), n_train=8)
+
+    made = []
+
+    def factory(cfg, device=None, base_model_name_or_path=""):
+        made.append((cfg, device, base_model_name_or_path))
+        return P.B200LlavaModel(tiny, base_model_name_or_path=base_model_name_or_path, engine=RecEngine())
+
+    g = torch.Generator().manual_seed(1)
+    sft = tmp_path / "sft" / "adapter_model" / "lora_default"
+    sft.mkdir(parents=True)
+    state = {}
+    for m, (o, i) in mods.items():
+        state[f"base_model.model.{m}.lora_A.weight"] = torch.randn(2, i, generator=g)
+        state[f"base_model.model.{m}.lora_B.weight"] = torch.randn(o, 2, generator=g)
+    torch.save(state, sft / "adapter_model.bin")
+    (sft / "adapter_config.json").write_text(json.dumps({"r": 2, "lora_alpha": 4.0, "lora_dropout": 0.0, "target_modules": ["q_proj"],
+                                                         "base_model_name_or_path": base, "peft_type": "LORA"}))
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    args = SimpleNamespace(policy_model_name_or_path=str(tmp_path / "sft"), base_model_name=base, temperature=1.0, response_len=4)
+    acc = SimpleNamespace(device=torch.device("cpu"))
+    out = P.make_models(None, tok, args, acc, model_factory=factory)
+    assert set(out) == {"policy", "ref_policy"} and len(made) == 1
+    cfg_seen, dev_seen, name_seen = made[0]
+    assert name_seen == base and dev_seen == acc.device
+    assert cfg_seen == EngineConfig(lora_r=2, lora_alpha=4.0)      # dims from the base's config.json, LoRA from adapter_config.json
+    pol, ref = out["policy"], out["ref_policy"]
+    assert pol.base_model is ref.base_model and pol.adapter_name == "lora_policy" and ref.adapter_name == "lora_ref_policy"
+    eng = pol.base_model.engine
+    assert eng.trainable == P.POLICY and pol.base_model.flat_param is not None
+    m0 = next(iter(mods))
+    for aid in (P.POLICY, P.REF):
+        assert set(k[1] for k in eng.lora if k[0] == aid) == set(mods)
+        assert torch.equal(eng.lora[(aid, m0)][0], state[f"base_model.model.{m0}.lora_A.weight"])
+    assert set(eng.tensors) == (set(s1) | set(s2) | {"model.vision_tower.vision_tower." + k for k in cs if k.startswith("vision_model.")}) \
+        - {"model.layers.0.self_attn.rotary_emb.inv_freq", "model.vision_tower.vision_tower.vision_model.post_layernorm.weight"}
+    assert pol.base_model.peft_config["lora_policy"]["r"] == 2
+
+    # resumed run: the policy adapter comes from <ckpt>/adapter_model/lora_policy, the reference adapter from the SFT directory
+    ck = tmp_path / "checkpoint-5"
+    state2 = {k: v + 1.0 for k, v in state.items()}
+    (ck / "adapter_model" / "lora_policy").mkdir(parents=True)
+    torch.save(state2, ck / "adapter_model" / "lora_policy" / "adapter_model.bin")
+    (ck / "adapter_model" / "lora_policy" / "adapter_config.json").write_text((sft / "adapter_config.json").read_text())
+    out2 = P.make_models(None, tok, args, acc, resume_from_checkpoint=str(ck), model_factory=factory)
+    e2 = out2["policy"].base_model.engine
+    assert torch.equal(e2.lora[(P.POLICY, m0)][1], state2[f"base_model.model.{m0}.lora_B.weight"])
+    assert torch.equal(e2.lora[(P.REF, m0)][1], state[f"base_model.model.{m0}.lora_B.weight"])
+
+    # train_from_sft=False: fresh adapters, PEFT's init (B = 0, |A| <= 1/sqrt(fan_in)); an already-built base is reused
+    args2 = SimpleNamespace(**{**vars(args), "train_from_sft": False})
+    out3 = P.make_models(out2["policy"].base_model, tok, args2, acc, model_factory=factory)
+    assert len(made) == 2 and out3["policy"].base_model is out2["policy"].base_model
+    for aid in (P.POLICY, P.REF):
+        A, B = e2.lora[(aid, m0)]
+        assert (B == 0).all() and A.abs().max() <= 1.0 / math.sqrt(A.shape[1]) + 1e-6 and A.abs().max() > 0
+    assert not torch.equal(e2.lora[(P.POLICY, m0)][0], e2.lora[(P.REF, m0)][0])
+
+    # the vision tower / projector are re-read from args.base_model_name when it is another directory
+    other = tmp_path / "other-base"
+    other.mkdir()
+    vt = "model.vision_tower.vision_tower.vision_model.pre_layrnorm.weight"
+    torch.save({vt: torch.full((4,), 7.0), "model.embed_tokens.weight": torch.zeros(32, 8)}, other / "pytorch_model.bin")
+    args3 = SimpleNamespace(**{**vars(args), "base_model_name": str(other)})
+    out4 = P.make_models(None, tok, args3, acc, model_factory=factory)
+    e4 = out4["policy"].base_model.engine
+    assert (e4.tensors[vt] == 7.0).all() and torch.equal(e4.tensors["model.embed_tokens.weight"], s1["model.embed_tokens.weight"])
+    with pytest.raises(OpadpoError):
+        P.make_models(None, tok, args, acc, num_new_tokens=1, model_factory=factory)
