@@ -147,22 +147,36 @@ def last_checkpoint_and_completion(checkpoint_dir: str):
     return best, False
 
 
-def save_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], output_dir: str, step,
-                    is_main_process: bool = True):
-    """DPOTrainer.save_model (dpo_trainer.py:837-899): rank 0 writes the policy adapter in PEFT layout plus optimizer.pt and
-    scheduler.pt, then older optimizer.pt files are removed."""
+def save_checkpoint_dir(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], ckpt: str,
+                        is_main_process: bool = True, for_best_ckpt: bool = False):
+    """DPOTrainer.save_model (dpo_trainer.py:837-899) into the directory it is given: rank 0 writes the policy adapter in
+    PEFT layout under <ckpt>/adapter_model/lora_policy, removes stray pytorch_model*.bin files there, and — unless
+    `for_best_ckpt` — writes optimizer.pt and scheduler.pt and deletes the optimizer.pt of every sibling directory."""
     if not is_main_process:
         return None
-    ckpt = os.path.join(output_dir, f"checkpoint-{step}")
+    ckpt = ckpt.rstrip("/")
+    os.makedirs(ckpt, exist_ok=True)
     model.save_adapter(os.path.join(ckpt, "adapter_model"), "lora_policy")
+    for name in os.listdir(ckpt):
+        if name.startswith("pytorch_model") and name.endswith(".bin"):
+            os.remove(os.path.join(ckpt, name))
+    if for_best_ckpt:
+        return ckpt
     torch.save(optimizer.state_dict(), os.path.join(ckpt, "optimizer.pt"))
     if scheduler is not None:
         torch.save(scheduler.state_dict(), os.path.join(ckpt, "scheduler.pt"))
-    for name in os.listdir(output_dir):
-        other = os.path.join(output_dir, name, "optimizer.pt")
-        if name.startswith("checkpoint-") and name != f"checkpoint-{step}" and os.path.exists(other):
+    parent = os.path.dirname(ckpt) or "."
+    for name in os.listdir(parent):
+        other = os.path.join(parent, name, "optimizer.pt")
+        if os.path.join(parent, name) != ckpt and os.path.isfile(other):
             os.remove(other)
     return ckpt
+
+
+def save_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], output_dir: str, step,
+                    is_main_process: bool = True):
+    """save_checkpoint_dir into <output_dir>/checkpoint-{step} (the directory RLTrainer.train names, rl_trainer.py:250-257)."""
+    return save_checkpoint_dir(model, optimizer, scheduler, os.path.join(output_dir, f"checkpoint-{step}"), is_main_process)
 
 
 def load_checkpoint(model, optimizer: B200AdamW, scheduler: Optional[cosine_schedule], ckpt: str) -> int:

@@ -199,13 +199,13 @@ class B200DPOTrainer:
             self.lr_scheduler = cosine_schedule(self.optimizer, getattr(self.args, "warmup_steps", 5), num_training_steps)
         return self.optimizer, self.lr_scheduler
 
-    def save_model(self, output_dir: str):
-        """DPOTrainer.save_model (dpo_trainer.py:837-899): <output_dir>/adapter_model/lora_policy + optimizer.pt + scheduler.pt."""
-        from .optim import save_checkpoint
-        parent, name = os.path.split(output_dir.rstrip("/"))
-        step = name[len("checkpoint-"):] if name.startswith("checkpoint-") else name
-        return save_checkpoint(self.model, self.optimizer, self.lr_scheduler, parent, step,
-                               is_main_process=int(os.environ.get("RANK", 0)) == 0)
+    def save_model(self, output_dir: Optional[str] = None, give_rw_access=True, check_corrupted=True, for_best_ckpt=False):
+        """DPOTrainer.save_model (dpo_trainer.py:837-899): <output_dir>/adapter_model/lora_policy + optimizer.pt + scheduler.pt
+        (rank 0 only; `output_dir` defaults to args.output_dir; any directory name, not only checkpoint-N)."""
+        from .optim import save_checkpoint_dir
+        output_dir = self.args.output_dir if output_dir is None else output_dir
+        return save_checkpoint_dir(self.model, self.optimizer, self.lr_scheduler, output_dir,
+                                   is_main_process=int(os.environ.get("RANK", 0)) == 0, for_best_ckpt=for_best_ckpt)
 
     def resume_training(self, checkpoint_dir: str) -> int:
         from .optim import load_checkpoint

@@ -269,3 +269,41 @@ def test_make_models_mirrors_reference_construction(tmp_path):
     assert (e4.tensors[vt] == 7.0).all() and torch.equal(e4.tensors["model.embed_tokens.weight"], s1["model.embed_tokens.weight"])
     with pytest.raises(OpadpoError):
         P.make_models(None, tok, args, acc, num_new_tokens=1, model_factory=factory)
+
+
+def test_save_model_directory_rules(tmp_path, monkeypatch):
+    """DPOTrainer.save_model's file rules (dpo_trainer.py:837-899): the directory it is given (any name), adapter under
+    adapter_model/lora_policy, stray pytorch_model*.bin removed, optimizer.pt of every sibling directory deleted, nothing but
+    the adapter for a best-checkpoint save, nothing at all off rank 0."""
+    from types import SimpleNamespace
+    from opa_dpo_b200.trainer import B200DPOTrainer
+
+    class Model:
+        flat_param = None
+        engine = SimpleNamespace(device=torch.device("cpu"))
+
+        def save_adapter(self, d, name):
+            os.makedirs(os.path.join(d, name), exist_ok=True)
+            open(os.path.join(d, name, "adapter_model.bin"), "w").write("x")
+
+    sd = SimpleNamespace(state_dict=lambda: {"k": 1})
+    tr = B200DPOTrainer(SimpleNamespace(output_dir=str(tmp_path / "run" / "final"), max_step=3), SimpleNamespace(base_model=Model()),
+                        None, optimizer=sd, lr_scheduler=sd, loss=object())
+    old = tmp_path / "run" / "checkpoint-3"
+    old.mkdir(parents=True)
+    (old / "optimizer.pt").write_text("old")
+    (old / "scheduler.pt").write_text("old")
+    out = tmp_path / "run" / "final"
+    out.mkdir()
+    (out / "pytorch_model-00001-of-00002.bin").write_text("stray")
+    monkeypatch.setenv("RANK", "1")
+    assert tr.save_model() is None and not (out / "adapter_model").exists()
+    monkeypatch.setenv("RANK", "0")
+    assert tr.save_model() == str(out)                       # output_dir defaults to args.output_dir
+    assert (out / "adapter_model" / "lora_policy" / "adapter_model.bin").exists()
+    assert (out / "optimizer.pt").exists() and (out / "scheduler.pt").exists() and not (out / "pytorch_model-00001-of-00002.bin").exists()
+    assert not (old / "optimizer.pt").exists() and (old / "scheduler.pt").exists()
+    best = tmp_path / "run" / "best"
+    assert tr.save_model(str(best), for_best_ckpt=True) == str(best)
+    assert (best / "adapter_model" / "lora_policy" / "adapter_model.bin").exists() and not (best / "optimizer.pt").exists()
+    assert (out / "optimizer.pt").exists()                   # a best-checkpoint save leaves the others' optimizer state alone
