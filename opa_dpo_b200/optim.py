@@ -32,8 +32,9 @@ class B200AdamW:
 
     def step(self, grad_scale: float = 1.0):
         g = self.param_groups[0]
+        # max_grad_norm None = no clipping (rl_trainer.py:164: `if self.args.max_grad_norm is not None`); the kernel skips the clip at 0
         self.last_grad_norm = self.model.engine.optimizer_step(g["lr"], g["betas"], g["eps"], g["weight_decay"],
-                                                               self.max_grad_norm, grad_scale)
+                                                               0.0 if self.max_grad_norm is None else self.max_grad_norm, grad_scale)
         self.step_count += 1
         return self.last_grad_norm
 
@@ -81,17 +82,30 @@ class B200AdamW:
 
 
 class cosine_schedule:
-    """HF get_cosine_schedule_with_warmup [UPSTREAM transformers.optimization]; stepped once per outer step
-    (rl_trainer.py:188-189)."""
+    """HF get_scheduler(name, optimizer, num_warmup_steps, num_training_steps) [UPSTREAM transformers.optimization] for the
+    schedules the reference's `--lr_scheduler_type` can name without extra arguments — "cosine" (the recipe's,
+    run/train_opa_dpo.sh:47-53; the default here, hence the class name), "linear", "constant", "constant_with_warmup" —
+    stepped once per outer step (rl_trainer.py:188-189)."""
 
-    def __init__(self, optimizer: B200AdamW, num_warmup_steps: int, num_training_steps: int):
-        self.opt, self.warmup, self.total = optimizer, num_warmup_steps, num_training_steps
+    KINDS = ("cosine", "linear", "constant", "constant_with_warmup")
+
+    def __init__(self, optimizer: B200AdamW, num_warmup_steps: int, num_training_steps: int, kind: str = "cosine"):
+        kind = getattr(kind, "value", kind)        # transformers.SchedulerType members compare by their string value
+        if kind not in self.KINDS:
+            raise ValueError(f"lr_scheduler_type {kind!r} is not one of {self.KINDS}")
+        self.opt, self.warmup, self.total, self.kind = optimizer, num_warmup_steps, num_training_steps, kind
         self.last_epoch = 0
         self._apply()
 
     def factor(self, step: int) -> float:
+        if self.kind == "constant":
+            return 1.0
         if step < self.warmup:
             return float(step) / float(max(1, self.warmup))
+        if self.kind == "constant_with_warmup":
+            return 1.0
+        if self.kind == "linear":
+            return max(0.0, float(self.total - step) / float(max(1, self.total - self.warmup)))
         progress = float(step - self.warmup) / float(max(1, self.total - self.warmup))
         return max(0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * progress)))
 
@@ -107,7 +121,7 @@ class cosine_schedule:
         return [g["lr"] for g in self.opt.param_groups]
 
     def state_dict(self):
-        return dict(last_epoch=self.last_epoch, warmup=self.warmup, total=self.total)
+        return dict(last_epoch=self.last_epoch, warmup=self.warmup, total=self.total, kind=self.kind)
 
     def load_state_dict(self, sd):
         """Accepts this class's own state and a torch LambdaLR state dict (what the reference's scheduler.pt holds,
@@ -116,7 +130,17 @@ class cosine_schedule:
         self.last_epoch = int(sd["last_epoch"])
         self.warmup = sd.get("warmup", self.warmup)
         self.total = sd.get("total", self.total)
+        self.kind = sd.get("kind", self.kind)
         self._apply()
+
+
+def warmup_steps_of(args, num_training_steps: int) -> int:
+    """TrainingArguments.get_warmup_steps [UPSTREAM transformers]: `warmup_steps` when positive, else
+    ceil(num_training_steps * warmup_ratio); the args object's own method is used when it has one."""
+    if callable(getattr(args, "get_warmup_steps", None)):
+        return int(args.get_warmup_steps(num_training_steps))
+    ws = int(getattr(args, "warmup_steps", 0) or 0)
+    return ws if ws > 0 else math.ceil(num_training_steps * float(getattr(args, "warmup_ratio", 0.0) or 0.0))
 
 
 def get_last_checkpoint(folder: str) -> Optional[str]:

@@ -192,11 +192,21 @@ class B200DPOTrainer:
     max_step: int = 300                       # TrainingArguments.max_step default (opadpo_train.py:152)
 
     def create_optimizer_and_scheduler(self, num_training_steps: int):
-        """create_optimizer / create_scheduler (utils/trainer_utils.py:9-49): the optimizer is the one handed in; the
-        schedule is HF's cosine with `warmup_steps` warm-up over num_training_steps, unless one was handed in."""
+        """create_optimizer / create_scheduler (utils/trainer_utils.py:9-49) unless they were handed in: AdamW over the LoRA
+        bucket with the args' learning_rate / adam_beta1,2 / adam_epsilon / weight_decay (every LoRA tensor is a "decay
+        parameter" there: no biases, no norms) and the global-norm clip of rl_trainer.py:164-168 fused into its step; HF's
+        `lr_scheduler_type` schedule (cosine in the recipe) with `args.get_warmup_steps(n)` warm-up steps."""
+        a = self.args
+        if self.optimizer is None:
+            from .optim import B200AdamW
+            self.optimizer = B200AdamW(self.model, lr=getattr(a, "learning_rate", 1e-6),
+                                       betas=(getattr(a, "adam_beta1", 0.9), getattr(a, "adam_beta2", 0.999)),
+                                       eps=getattr(a, "adam_epsilon", 1e-8), weight_decay=getattr(a, "weight_decay", 0.0),
+                                       max_grad_norm=getattr(a, "max_grad_norm", 1.0))
         if self.lr_scheduler is None:
-            from .optim import cosine_schedule
-            self.lr_scheduler = cosine_schedule(self.optimizer, getattr(self.args, "warmup_steps", 5), num_training_steps)
+            from .optim import cosine_schedule, warmup_steps_of
+            self.lr_scheduler = cosine_schedule(self.optimizer, warmup_steps_of(a, num_training_steps), num_training_steps,
+                                                kind=getattr(a, "lr_scheduler_type", "cosine"))
         return self.optimizer, self.lr_scheduler
 
     def save_model(self, output_dir: Optional[str] = None, give_rw_access=True, check_corrupted=True, for_best_ckpt=False):

@@ -132,6 +132,34 @@ def test_cosine_schedule_matches_hf_and_last_checkpoint(tmp_path):
     assert get_last_checkpoint(str(tmp_path)) is None
 
 
+def test_scheduler_types_and_warmup_match_hf_get_scheduler():
+    """create_scheduler (utils/trainer_utils.py:41-49) = transformers.get_scheduler(args.lr_scheduler_type, optimizer,
+    args.get_warmup_steps(n), n): every schedule the flag can name without extra arguments, and the warm-up rule."""
+    from types import SimpleNamespace
+    from transformers import SchedulerType
+    from transformers.optimization import get_scheduler
+    from opa_dpo_b200.optim import cosine_schedule, warmup_steps_of
+    for kind in ("cosine", "linear", "constant", "constant_with_warmup"):
+        for warm, total in ((5, 60), (0, 7), (9, 9)):
+            fake = SimpleNamespace(param_groups=[dict(lr=3e-5, initial_lr=3e-5)])
+            opt = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=3e-5)
+            hf = get_scheduler(kind, optimizer=opt, num_warmup_steps=warm, num_training_steps=total)
+            mine = cosine_schedule(fake, warm, total, kind=SchedulerType(kind))
+            for _ in range(total + 3):
+                assert abs(hf.get_last_lr()[0] - mine.get_last_lr()[0]) < 1e-18, (kind, warm, total)
+                opt.step(); hf.step(); mine.step()
+            again = cosine_schedule(SimpleNamespace(param_groups=[dict(lr=3e-5, initial_lr=3e-5)]), 1, 2)
+            again.load_state_dict(mine.state_dict())
+            assert again.get_last_lr() == mine.get_last_lr() and again.kind == kind
+    with pytest.raises(ValueError):
+        cosine_schedule(SimpleNamespace(param_groups=[dict(lr=1.0, initial_lr=1.0)]), 0, 10, kind="polynomial")
+    # TrainingArguments.get_warmup_steps: warmup_steps wins when positive, else ceil(n * warmup_ratio)
+    # (the rule of the pinned transformers 4.34.1, training_args.py get_warmup_steps; constructing TrainingArguments needs accelerate)
+    for ws, ratio, n, want in ((5, 0.0, 100, 5), (0, 0.03, 100, 3), (0, 0.03, 101, 4), (7, 0.5, 10, 7), (0, 0.0, 10, 0)):
+        assert warmup_steps_of(SimpleNamespace(warmup_steps=ws, warmup_ratio=ratio), n) == want, (ws, ratio, n)
+    assert warmup_steps_of(SimpleNamespace(get_warmup_steps=lambda n: 11), 100) == 11
+
+
 def test_importing_the_whole_package_does_not_load_the_oracle():
     """oracle/ is test infrastructure: no module of the package imports it (statically), and importing the whole package
     does not pull it in."""

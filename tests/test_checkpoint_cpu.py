@@ -307,3 +307,28 @@ def test_save_model_directory_rules(tmp_path, monkeypatch):
     assert tr.save_model(str(best), for_best_ckpt=True) == str(best)
     assert (best / "adapter_model" / "lora_policy" / "adapter_model.bin").exists() and not (best / "optimizer.pt").exists()
     assert (out / "optimizer.pt").exists()                   # a best-checkpoint save leaves the others' optimizer state alone
+
+
+def test_create_optimizer_and_scheduler_from_args():
+    """RLTrainer.create_optimizer_and_scheduler (rl_trainer.py:197-215 over utils/trainer_utils.py:9-49) when neither was
+    handed in: AdamW hyper-parameters and the schedule come from the args; max_grad_norm None = no clipping."""
+    from types import SimpleNamespace
+    from opa_dpo_b200.optim import B200AdamW, cosine_schedule
+    from opa_dpo_b200.trainer import B200DPOTrainer
+    calls = []
+    eng = SimpleNamespace(device=torch.device("cpu"),
+                          optimizer_step=lambda lr, betas, eps, wd, mg, scale: calls.append((lr, betas, eps, wd, mg, scale)) or torch.ones(1))
+    model = SimpleNamespace(flat_param=torch.nn.Parameter(torch.zeros(4)), engine=eng)
+    args = SimpleNamespace(learning_rate=2e-6, adam_beta1=0.8, adam_beta2=0.95, adam_epsilon=1e-6, weight_decay=0.1, max_grad_norm=None,
+                           lr_scheduler_type="linear", warmup_steps=0, warmup_ratio=0.2, max_step=50)
+    tr = B200DPOTrainer(args, SimpleNamespace(base_model=model), None, optimizer=None, loss=object())
+    opt, sch = tr.create_optimizer_and_scheduler(10)
+    assert isinstance(opt, B200AdamW) and isinstance(sch, cosine_schedule) and sch.kind == "linear" and sch.warmup == 2 and sch.total == 10
+    g = opt.param_groups[0]
+    assert g["initial_lr"] == 2e-6 and g["betas"] == (0.8, 0.95) and g["eps"] == 1e-6 and g["weight_decay"] == 0.1 and g["lr"] == 0.0
+    sch.step()
+    opt.step(0.5)
+    assert calls == [(1e-6, (0.8, 0.95), 1e-6, 0.1, 0.0, 0.5)]          # lr after one warm-up step; clip disabled -> 0
+    # handed-in objects are kept (create_optimizer / create_scheduler return them unchanged)
+    tr2 = B200DPOTrainer(args, SimpleNamespace(base_model=model), None, optimizer=opt, lr_scheduler=sch, loss=object())
+    assert tr2.create_optimizer_and_scheduler(99) == (opt, sch)
