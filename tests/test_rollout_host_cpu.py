@@ -236,3 +236,126 @@ def test_step_returns_reference_record_step_stats(copo):
     for k, v in want.items():
         assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
     assert ref_logged[0][0] == 7 and set(ref_logged[0][1]) == set(got)
+
+
+class _GenTok:
+    """Tokenizer stub for the generation-stage tests: ids decode to fixed pieces, 0 / 1 / 2 are special."""
+    pad_token_id, eos_token_id = 0, 2
+    PIECES = {50: "USER:  \n", 51: " ASSISTANT:"}
+
+    def encode(self, text, add_special_tokens=True):
+        return [1577] if text == "?" else [1, 29973]
+
+    def batch_decode(self, ids, skip_special_tokens=True, clean_up_tokenization_spaces=True):
+        return ["".join(self.PIECES.get(int(t), f"<{int(t)}>") for t in row if int(t) not in (0, 1, 2)) for row in ids]
+
+
+def _gen_batches(n_batches, b=2, Q=8, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n_batches):
+        q = torch.randint(3, 40, (b, Q), generator=g)
+        q[:, 0], q[:, 1], q[:, 2], q[:, -1] = 0, 50, -200, 51
+        out.append({"images": torch.randn(b, 3, 4, 4, generator=g), "images_path": [f"img{i}_{j}.jpg" for j in range(b)],
+                    "images_url": [f"http://x/{i}/{j}" for j in range(b)], "images_bytes": [bytes([i, j]) for j in range(b)],
+                    "queries": q, "query_attn_masks": q != 0, "standard_responses": torch.randint(3, 40, (b, 5), generator=g)})
+    return out
+
+
+def _stub_generate(inputs, images, max_new_tokens, **kw):
+    """A deterministic stand-in for model.generate: ids from the prompt and the (possibly bf16-rounded) image, with stop
+    tokens sprinkled in so the truncation rule matters."""
+    base = (inputs.clamp(min=0).sum(1) + (images.float().sum((1, 2, 3)) * 64).round().long()) % 17
+    new = (base[:, None] + torch.arange(max_new_tokens)[None, :] * 3) % 23 + 3
+    new[0, 3] = 2
+    new[1, 4] = 1577
+    return torch.cat([inputs, new], 1)
+
+
+def test_generation_stage_rollout_and_loop_vs_reference(tmp_path, monkeypatch):
+    """Rows a10 / f-4: B200OnlineGenerator.rollout / step / generate against the reference's Online_Generator.rollout
+    (online_generator.py:235-378) and Generator.generate / find_max_step / record_step_stats (generator.py:99-175) run
+    VERBATIM over the same stub model: generate() arguments, bf16 image cast, truncation, decoded texts, the query cut, the
+    record columns, the files written, the skipped / repeated steps of a resumed run."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    from oracle.make_golden import install_stubs
+    from oracle import llava_oracle as O
+    install_stubs()
+    import opadpo.generator_models.online_generator as OG
+    from opa_dpo_b200.generation import B200OnlineGenerator, find_max_step
+    monkeypatch.setenv("RANK", "0")
+    tok = _GenTok()
+
+    def make_args(out):
+        return SimpleNamespace(bf16=True, fp16=False, response_len=6, suppress_eos_at_generation=True, top_p=0.95, top_k=30,
+                               temperature=1.1, rollout_accumulation_steps=2, rollout_batch_size=4, total_epochs=1, sample_num=16,
+                               output_dir=str(out))
+    seen_ref, seen_mine = [], []
+
+    def revise(responses, images_url, text_queries, text_responses, text_standard_responses, *_rest):
+        return {"Pseudo_response": [r + "|p" for r in text_responses], "Pseudo_response_ids": None,
+                "Generated_response": [r + "|g" for r in text_responses], "Generated_response_ids": None,
+                "report_json": [{"url": u, "q": q} for u, q in zip(images_url, text_queries)]}
+
+    class RefPolicy:
+        def eval(self):
+            return self
+
+        def generate(self, **kw):
+            seen_ref.append({k: v for k, v in kw.items() if k not in ("inputs", "images", "attention_mask")} | {"dtype": kw["images"].dtype})
+            return _stub_generate(kw["inputs"], kw["images"], kw["max_new_tokens"])
+
+    class MyModel:
+        def generate(self, **kw):
+            seen_mine.append({k: v for k, v in kw.items() if k not in ("inputs", "images", "attention_mask")} | {"dtype": kw["images"].dtype})
+            return _stub_generate(kw["inputs"], kw["images"], kw["max_new_tokens"])
+
+    # ---- one rollout call
+    batches = _gen_batches(2)
+    ref = object.__new__(OG.Online_Generator)
+    ref.args, ref.tokenizer, ref.policy = make_args(tmp_path / "ref"), tok, RefPolicy()
+    ref.accelerator = SimpleNamespace(device=torch.device("cpu"), is_main_process=False)
+    ref.process_responses_coco_gpt4v = revise
+    want = ref.rollout([dict(b) for b in batches], 1)
+    mine = B200OnlineGenerator(make_args(tmp_path / "mine"), MyModel(), tok, revise=revise, truncate=O.truncate_after_eos_with_padding)
+    got = mine.rollout([dict(b) for b in batches], 1)
+    assert got == want and list(got) == list(want)          # same columns in the same order, same records
+    assert "USER" not in got["query"][0] and got["query"][0].startswith("<image>\n<")
+    for a, b in zip(seen_mine, seen_ref):
+        assert a["dtype"] == b["dtype"] == torch.bfloat16
+        for k in ("do_sample", "max_new_tokens", "pad_token_id", "suppress_tokens", "top_p", "top_k", "temperature", "num_return_sequences"):
+            assert a[k] == b[k], k
+        assert a["synced_gpus"] is False                     # by design: ranks decode independently
+    # without a revision service the AI_* columns are None and the rest is unchanged
+    bare = B200OnlineGenerator(make_args(tmp_path / "bare"), MyModel(), tok, truncate=O.truncate_after_eos_with_padding).rollout(batches, 1)
+    assert bare["AI_json_report"] == [None] * 4 and bare["original_generate_response"] == want["original_generate_response"]
+
+    # ---- the loop: 3 steps of 2 batches (max_step = 16 // 4 = 4 stops before step 4), then a restart that finds step 3 recorded
+    import itertools
+
+    class RefLoop(OG.Online_Generator):
+        def get_train_dataloader(self):
+            return itertools.cycle([dict(b) for b in _gen_batches(5, seed=9)])
+
+    ref2 = object.__new__(RefLoop)
+    ref2.args, ref2.tokenizer, ref2.policy = make_args(tmp_path / "ref"), tok, RefPolicy()
+    ref2.accelerator = SimpleNamespace(device=torch.device("cpu"), is_main_process=False)
+    ref2.process_responses_coco_gpt4v = revise
+    ref2.train_dataset, ref2.log_history = list(range(20)), []
+    hist_ref = ref2.generate()
+    mine2 = B200OnlineGenerator(make_args(tmp_path / "mine"), MyModel(), tok, revise=revise, truncate=O.truncate_after_eos_with_padding)
+    hist = mine2.generate(20, lambda: itertools.cycle([dict(b) for b in _gen_batches(5, seed=9)]))
+    assert hist == hist_ref == [None, None, None]
+    files = sorted(os.listdir(tmp_path / "ref" / "rollouts"))
+    assert files == sorted(os.listdir(tmp_path / "mine" / "rollouts")) == ["step1_rank0.json", "step2_rank0.json", "step3_rank0.json"]
+    for f in files:
+        assert (tmp_path / "ref" / "rollouts" / f).read_bytes() == (tmp_path / "mine" / "rollouts" / f).read_bytes(), f
+    assert find_max_step(str(tmp_path / "mine")) == ref2.find_max_step() == 3
+    # restart: steps 1-2 are skipped with their batches consumed, step 3 is generated again from the same batches -> same file
+    before = (tmp_path / "mine" / "rollouts" / "step3_rank0.json").read_bytes()
+    n_calls = len(seen_mine)
+    mine3 = B200OnlineGenerator(make_args(tmp_path / "mine"), MyModel(), tok, revise=revise, truncate=O.truncate_after_eos_with_padding)
+    assert mine3.generate(20, lambda: itertools.cycle([dict(b) for b in _gen_batches(5, seed=9)])) == [None]
+    assert len(seen_mine) == n_calls + 2 and (tmp_path / "mine" / "rollouts" / "step3_rank0.json").read_bytes() == before
+    assert find_max_step(str(tmp_path / "fresh")) == 0 and os.path.isdir(tmp_path / "fresh" / "rollouts")
