@@ -102,12 +102,72 @@ def cpu_full_depth_config0_step(threads: int, pairs: int = 2, R: int = 128):
     t0 = time.perf_counter()
     with torch.no_grad():
         ref = O.policy_forward(oc, w, lr, images, q, qm, resp)
-    pol = O.policy_forward(oc, w, lpg, images, q, qm, resp)
+    # gradient checkpointing per decoder layer, as the reference trains (opadpo_train.py:324-327): same numbers, and the
+    # step's host memory stays near the 28 GB of fp32 weights instead of ~100 GB of kept activations
+    pol = O.policy_forward(oc, w, lpg, images, q, qm, resp, checkpoint_layers=True)
     loss, _, _ = O.pair_loss(O.LossConfig(beta=0.1), pol["chosen_response_logprobs"], pol["rejected_response_logprobs"],
                              ref["chosen_response_logprobs"], ref["rejected_response_logprobs"])
     loss.backward()
     t = time.perf_counter() - t0
     return t, flops_per_pair(EngineConfig(), Q_LEN, R)["per_pair"] * pairs, t_init
+
+
+FULL_DEPTH_NEED_GB = 50.0     # measured peak RSS of the checkpointed configs[0] step (43.5 GB) + margin
+
+
+def _available_host_gb():
+    """Host memory this process may still take: MemAvailable, capped by the cgroup limit when there is one."""
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    avail = int(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    for lim_p, cur_p in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_p).read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                room = (int(lim) - int(open(cur_p).read().strip())) / 1e9
+                avail = room if avail is None else min(avail, room)
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
+def full_depth_config0_isolated(threads: int, timeout_s: float):
+    """cpu_full_depth_config0_step in a child process: a host that cannot hold the 7B fp32 model (the kernel's OOM killer ends
+    the child, not this process) or is too slow for the time box costs the reference arm its full-depth figure, never its
+    line. Returns the `full_depth_config0` object of the JSON line."""
+    avail = _available_host_gb()
+    if avail is not None and avail < FULL_DEPTH_NEED_GB:
+        return {"skipped": f"needs ~{FULL_DEPTH_NEED_GB:.0f} GB of host memory, {avail:.0f} GB available"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--full-depth-child", str(threads)]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"failed": f"no result within the {timeout_s:.0f} s time box"}
+    for ln in reversed(p.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"failed": f"child exited {p.returncode}: {(p.stderr or '').strip()[-200:]}"}
+
+
+def _full_depth_child(threads: int) -> int:
+    import resource
+    from opa_dpo_b200.flops import flops_per_pair
+    from opa_dpo_b200.engine import EngineConfig
+    full = flops_per_pair(EngineConfig(), Q_LEN, R_LEN)["per_pair"]
+    t_fd, fl_fd, t_init = cpu_full_depth_config0_step(threads)
+    print(json.dumps({"config": "BASELINE configs[0]: full-depth LLaVA-1.5-7B (32 LLaMA + 23 CLIP layers), 2 pairs, R=128, fp32, "
+                                "reference fwd x2 + policy fwd x2 + DPO loss + LoRA backward, gradient checkpointing per decoder "
+                                "layer as in the reference's recipe",
+                      "seconds_per_step": t_fd, "pairs_per_s_at_R128": 2.0 / t_fd, "cpu_tflops": fl_fd / t_fd / 1e12,
+                      "pairs_per_s_at_R512_by_flops": (fl_fd / t_fd) / full, "weight_init_seconds": t_init,
+                      "peak_rss_gb": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6}), flush=True)
+    return 0
 
 
 def cpu_rollout_sample(threads: int, batch: int = 4, new: int = 8, n_layers: int = 2, v_layers: int = 2):
@@ -151,14 +211,9 @@ def run_reference_arm(args):
               "full depth by algorithmic FLOPs (%.1f TFLOP sample vs %.1f TFLOP full pair)" % (fl / 1e12, full / 1e12))
     full_depth = None
     if not args.no_full_depth:
-        try:   # one un-truncated step: configs[0] (2 pairs x 128 tokens), every layer, forward and backward
-            t_fd, fl_fd, t_init = cpu_full_depth_config0_step(threads)
-            full_depth = {"config": "BASELINE configs[0]: full-depth LLaVA-1.5-7B (32 LLaMA + 23 CLIP layers), 2 pairs, R=128, fp32, "
-                                    "reference fwd x2 + policy fwd x2 + DPO loss + LoRA backward",
-                          "seconds_per_step": t_fd, "pairs_per_s_at_R128": 2.0 / t_fd, "cpu_tflops": fl_fd / t_fd / 1e12,
-                          "pairs_per_s_at_R512_by_flops": (fl_fd / t_fd) / full, "weight_init_seconds": t_init}
-        except Exception as ex:
-            full_depth = {"failed": f"{type(ex).__name__}: {ex}"}
+        # one un-truncated step: configs[0] (2 pairs x 128 tokens), every layer, forward and backward — in a child process
+        # behind a memory check and a time box, so that it can only ever add to the line
+        full_depth = full_depth_config0_isolated(threads, args.full_depth_timeout)
     if full_depth and "pairs_per_s_at_R512_by_flops" in full_depth:
         # the line's value is the HIGHER of the two CPU estimates (the one less flattering to the GPU arm)
         value = max(value, full_depth["pairs_per_s_at_R512_by_flops"])
@@ -331,7 +386,9 @@ def main():
     ap.add_argument("--resp-len", type=int, default=R_LEN)
     ap.add_argument("--no-share-prefix", action="store_true", help="run the reference's K stacked rows (no prefix sharing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-full-depth", action="store_true", help="reference arm: skip the full-depth configs[0] CPU step (~3 min)")
+    ap.add_argument("--no-full-depth", action="store_true", help="reference arm: skip the full-depth configs[0] CPU step (~4 min)")
+    ap.add_argument("--full-depth-timeout", type=float, default=900.0, help="reference arm: time box of the full-depth step (s)")
+    ap.add_argument("--full-depth-child", type=int, default=0, metavar="THREADS", help=argparse.SUPPRESS)
     ap.add_argument("--mode", default="train", choices=["train", "rollout"],
                     help="rollout: print BASELINE configs[3] (greedy rollout, batch 32, 256 new tokens) as the line itself")
     ap.add_argument("--no-rollout", action="store_true", help="train mode: skip the rollout object")
@@ -353,6 +410,8 @@ def main():
     ap.add_argument("--fuse-rope", type=int, default=int(os.environ.get("OPADPO_FUSE_ROPE", "1")),
                     help="1: RoPE in the q|k|v GEMM epilogue")
     args = ap.parse_args()
+    if args.full_depth_child:
+        return _full_depth_child(args.full_depth_child)
     if args.impl == "reference":
         return run_reference_arm(args)
     if not args.profile:

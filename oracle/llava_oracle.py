@@ -242,10 +242,13 @@ def _rotate_half(x):
     return torch.cat([-x[..., h:], x[..., :h]], dim=-1)
 
 
-def llama_hidden(cfg: OracleConfig, w, lora, x: torch.Tensor, mask: torch.Tensor, past=None, pos0: int = 0):
+def llama_hidden(cfg: OracleConfig, w, lora, x: torch.Tensor, mask: torch.Tensor, past=None, pos0: int = 0,
+                 checkpoint_layers: bool = False):
     """HF LlamaModel [UPSTREAM transformers 4.34.1] over inputs_embeds with a key-padding mask; position_ids are
     arange over the PADDED row (no position_ids are passed by rl_models.py:114-120). Optional KV cache for rollout:
-    `past` = list of (k, v) per layer, `mask` then covers past + new keys."""
+    `past` = list of (k, v) per layer, `mask` then covers past + new keys. `checkpoint_layers`: HF gradient checkpointing
+    per decoder layer, which the reference trains with (opadpo_train.py:324-327, qlora_model.py:204-205) — same values and
+    gradients, each layer's internals recomputed in the backward instead of kept (used by the full-depth CPU timing)."""
     scale = cfg.lora_alpha / cfg.lora_r if cfg.lora_r else 0.0
     N, S, d = x.shape
     H = cfg.n_heads
@@ -257,7 +260,8 @@ def llama_hidden(cfg: OracleConfig, w, lora, x: torch.Tensor, mask: torch.Tensor
     kj = torch.arange(Sk)[None, :]
     allowed = (kj <= qi)[None, None] & mask.bool()[:, None, None, :]           # [N,1,S,Sk]
     new_past = []
-    for i in range(cfg.n_layers):
+
+    def layer(i: int, x: torch.Tensor) -> torch.Tensor:
         p = f"model.layers.{i}."
         h = _rms(x, w[p + "input_layernorm.weight"], cfg.rms_eps)
         q = _lin(h, w, p + "self_attn.q_proj", lora, scale).view(N, S, H, hd).transpose(1, 2)
@@ -279,7 +283,15 @@ def llama_hidden(cfg: OracleConfig, w, lora, x: torch.Tensor, mask: torch.Tensor
         h = _rms(x, w[p + "post_attention_layernorm.weight"], cfg.rms_eps)
         g = _lin(h, w, p + "mlp.gate_proj", lora, scale)
         u = _lin(h, w, p + "mlp.up_proj", lora, scale)
-        x = x + _lin(F.silu(g) * u, w, p + "mlp.down_proj", lora, scale)
+        return x + _lin(F.silu(g) * u, w, p + "mlp.down_proj", lora, scale)
+
+    recompute = checkpoint_layers and past is None and torch.is_grad_enabled() and x.requires_grad
+    for i in range(cfg.n_layers):
+        if recompute:
+            from torch.utils.checkpoint import checkpoint
+            x = checkpoint(layer, i, x, use_reentrant=False)
+        else:
+            x = layer(i, x)
     x = _rms(x, w["model.norm.weight"], cfg.rms_eps)
     return (x, new_past) if past is not None else x
 
@@ -290,13 +302,14 @@ def _rms(x, weight, eps):
     return weight * (x * torch.rsqrt(var + eps))
 
 
-def llava_logits(cfg: OracleConfig, w, lora, input_ids, attention_mask, images, img_mask=None, img_of_row=None):
+def llava_logits(cfg: OracleConfig, w, lora, input_ids, attention_mask, images, img_mask=None, img_of_row=None,
+                 checkpoint_layers: bool = False):
     """LlavaLlamaForCausalLM.forward, multimodal branch (llava_modifications.patch:12127-12202)."""
     feats = projector(cfg, w, lora, clip_features(cfg, w, lora, images))
     if img_of_row is not None:
         feats = feats[img_of_row]
     x, mask = splice(cfg, w, input_ids, attention_mask, feats, img_mask)
-    h = llama_hidden(cfg, w, lora, x, mask)
+    h = llama_hidden(cfg, w, lora, x, mask, checkpoint_layers=checkpoint_layers)
     return h @ w["lm_head.weight"].t()
 
 
@@ -307,7 +320,7 @@ def compute_logprobs(logits: torch.Tensor, labels: torch.Tensor, ignore_index: i
 
 
 def policy_forward(cfg: OracleConfig, w, lora, images, queries, queries_attn_masks, responses: Dict[str, torch.Tensor],
-                   temperature: float = 1.0) -> Dict[str, torch.Tensor]:
+                   temperature: float = 1.0, checkpoint_layers: bool = False) -> Dict[str, torch.Tensor]:
     """AutoregressivePolicy.forward (opadpo/dpo_models/rl_models.py:75-144)."""
     keys = [k for k in responses if "response" in k and "_mask" not in k and "scores" not in k and "image_relations" not in k]
     Q = queries.size(1)
@@ -331,7 +344,8 @@ def policy_forward(cfg: OracleConfig, w, lora, images, queries, queries_attn_mas
     response_mask = ~input_ids[:, Q:].eq(cfg.pad_id)
     img_of_row = torch.arange(K * b) % b
     logits = llava_logits(cfg, w, lora, input_ids, attn, images,
-                          None if img_mask is None else img_mask.repeat(K, 1), img_of_row=img_of_row)
+                          None if img_mask is None else img_mask.repeat(K, 1), img_of_row=img_of_row,
+                          checkpoint_layers=checkpoint_layers)
     logits = logits[:, -R - 1:-1] / temperature
     labels = input_ids[:, -R:]
     logprobs = compute_logprobs(logits, labels, cfg.pad_id) * response_mask
