@@ -205,3 +205,38 @@ def test_collator_abi_argument_errors_without_gpu():
     ids = (ctypes.c_int64 * 8)()
     assert lib.opadpo_op_truncate_after_eos(ids, ids, 1, 8, 2, 0, None, 3, None) == -1               # n_extra > 0 without the array
     assert lib.opadpo_backward_ent(None, 0, None, None, None) == -1 and b"null engine" in lib.opadpo_last_error()
+
+
+def test_reference_arm_full_depth_step_is_isolated(monkeypatch):
+    """bench.py --impl reference: the full-depth configs[0] CPU step runs in a child process behind a host-memory check and a
+    time box, so a small or slow host loses that figure, never the reference line."""
+    import bench
+    avail = bench._available_host_gb()
+    assert avail is None or avail > 0
+    monkeypatch.setattr(bench, "_available_host_gb", lambda: 8.0)
+    out = bench.full_depth_config0_isolated(4, 5.0)
+    assert "skipped" in out and "8 GB available" in out["skipped"]
+    monkeypatch.setattr(bench, "_available_host_gb", lambda: None)
+    calls = {}
+
+    class P:
+        returncode, stdout, stderr = 0, 'noise\n{"seconds_per_step": 2.0, "pairs_per_s_at_R512_by_flops": 0.5}\n', ""
+
+    def fake_run(cmd, **kw):
+        calls["cmd"], calls["kw"] = cmd, kw
+        return P()
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    assert bench.full_depth_config0_isolated(4, 7.0)["pairs_per_s_at_R512_by_flops"] == 0.5
+    assert calls["cmd"][-2:] == ["--full-depth-child", "4"] and calls["kw"]["timeout"] == 7.0
+
+    def killed(cmd, **kw):
+        class Q:
+            returncode, stdout, stderr = -9, "", "Killed"
+        return Q()
+    monkeypatch.setattr(bench.subprocess, "run", killed)
+    assert "child exited -9" in bench.full_depth_config0_isolated(4, 7.0)["failed"]
+
+    def slow(cmd, **kw):
+        raise bench.subprocess.TimeoutExpired(cmd, kw["timeout"])
+    monkeypatch.setattr(bench.subprocess, "run", slow)
+    assert "time box" in bench.full_depth_config0_isolated(4, 7.0)["failed"]

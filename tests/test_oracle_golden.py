@@ -133,3 +133,27 @@ def test_greedy_rollout_matches_hf_generate_with_early_eos(gold, setup, eos):
     assert margin > 1e-3 and torch.equal(got, want), (got, want)
     if eos != 2:
         assert (got == cfg.pad_id).any(), "the case must make at least one row finish early"
+
+
+def test_layer_checkpointing_option_is_bit_identical():
+    """oracle.policy_forward(checkpoint_layers=True) — HF gradient checkpointing per decoder layer, which the reference
+    trains with (opadpo_train.py:324-327) and which the reference arm's full-depth CPU timing uses to stay within the host's
+    memory — gives the same loss and the same LoRA gradients, bit for bit."""
+    from oracle import llava_oracle as O
+    oc = O.OracleConfig()
+    w, lp = O.init_weights(oc), O.init_lora(oc, 11)
+    names = ["chosen_response", "rejected_response"]
+    images, q, qm, resp = O.synthetic_batch(oc, 2, 16, 24, names, left_pad=3)
+
+    def run(ck):
+        lpg = {m: (A.clone().requires_grad_(not m.startswith(O.VT)), B.clone().requires_grad_(not m.startswith(O.VT)))
+               for m, (A, B) in lp.items()}
+        out = O.policy_forward(oc, w, lpg, images, q, qm, resp, checkpoint_layers=ck)
+        loss = out["chosen_response_logprobs"].sum() - out["rejected_response_logprobs"].sum()
+        loss.backward()
+        return loss.detach(), {m: (A.grad, B.grad) for m, (A, B) in lpg.items() if A.grad is not None}
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    assert torch.equal(l0, l1) and set(g0) == set(g1) and len(g0) > 0
+    for m in g0:
+        assert torch.equal(g0[m][0], g1[m][0]) and torch.equal(g0[m][1], g1[m][1]), m
