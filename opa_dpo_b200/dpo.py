@@ -132,7 +132,7 @@ class FusedDPO:
         if a.AncPO and anchor_sign != 0.0:
             mode = 1 if a.mDPO_anchor else 2
         p = dict(beta=a.beta, label_smoothing=a.label_smoothing, reference_free=a.reference_free,
-                 divergence=_DIV[a.f_divergence_type], alpha_div=a.alpha_divergence_coef, loss_coef=float(loss_coef),
+                 divergence=_DIV[a.f_divergence_type], alpha_div=getattr(a, "alpha_divergence_coef", 1.0), loss_coef=float(loss_coef),
                  anchor_mode=mode, anchor_sign=float(anchor_sign), anchor_value=a.Anchor_value,
                  anchor_coef=a.Anchor_coef if mode else 0.0)
         return self._pair_impl(pi_c, pi_r, ref_c, ref_r, s_c, s_r, p)

@@ -184,9 +184,14 @@ class B200DPOTrainer:
             scale = allreduce_grad_bucket(self.model.flat_param.grad, self.process_group)
         else:
             scale = 1.0
-        norm = self.optimizer.step(scale)      # clip_grad_norm_ + AdamW, fused (rl_trainer.py:164-175)
+        norm = self.optimizer.step(scale).reshape(())      # clip_grad_norm_ + AdamW, fused (rl_trainer.py:164-175)
         self.optimizer.zero_grad()
-        return norm.reshape(())
+        # the reference logs `loss/grad_norm` = _compute_grad_norm() AFTER clip_grad_norm_ (rl_trainer.py:164-171), i.e. the
+        # clipped gradients' norm; the fused step returns the norm before clipping (kept as optimizer.last_grad_norm)
+        mg = getattr(self.optimizer, "max_grad_norm", None)
+        if mg is not None and mg > 0:
+            norm = norm * torch.clamp(mg / (norm + 1e-6), max=1.0)
+        return norm
 
     # ------------------------------------------------------------------ outer loop (rl_trainer.py:197-279)
     max_step: int = 300                       # TrainingArguments.max_step default (opadpo_train.py:152)
@@ -262,3 +267,57 @@ class B200DPOTrainer:
         if self.log_fn is not None and int(os.environ.get("RANK", 0)) == 0:
             self.log_fn(renamed, step=step_idx)
         return renamed
+
+
+def train_opa_dpo(args, tokenizer, dataset_len: int, train_dataloader_factory: Callable[[], Iterable], accelerator=None,
+                  model_factory=None, trainer_kwargs: Optional[dict] = None) -> "B200DPOTrainer":
+    """The model / training half of the reference's entry point `opadpo_train.train` (opadpo/opadpo_train.py:583-595,
+    727-797) — what is left of it once the hydra config, tokenizer and data module exist, which stay the reference's:
+
+    1. `get_last_checkpoint(args.output_dir)`, falling back to `args.resume_dir` (:583-595);
+    2. "building the LoRA model from scratch" when `base_model_name == policy_model_name_or_path` (:727-763): a freshly
+       initialised adapter (`lora_r`, `lora_alpha`) is written once to `<output_dir>/init_model/{adapter_model.bin,
+       adapter_config.json}` and becomes the policy checkpoint both adapters start from;
+    3. `make_models(..., resume_from_checkpoint=checkpoint if args.resume_from_training)` (:769-778);
+    4. `DPOTrainer(...).train(resume_training_ckpt=...)` (:781-793);
+    5. rank 0 saves `<output_dir>/checkpoint-final`, then a barrier (:794-797).
+    `dataset_len` / `train_dataloader_factory` stand for the data module (`len(train_dataset)` and the infinite loader of
+    collated batches). Returns the trainer."""
+    import json
+    import torch.distributed as dist
+    from . import checkpoint
+    from .optim import last_checkpoint_and_completion
+    from .policy import B200LlavaModel, make_models
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    ckpt, _completed = last_checkpoint_and_completion(args.output_dir)
+    if ckpt is None and getattr(args, "resume_dir", None) is not None:
+        ckpt, _ = last_checkpoint_and_completion(args.resume_dir)
+    base_model = None
+    if args.base_model_name == args.policy_model_name_or_path:
+        init_dir = os.path.join(args.output_dir, "init_model")
+        have = all(os.path.exists(os.path.join(init_dir, f)) for f in ("adapter_model.bin", "adapter_config.json"))
+        if not have:
+            cfg = checkpoint.engine_config_from_hf(args.base_model_name, lora_r=int(args.lora_r), lora_alpha=float(args.lora_alpha))
+            factory = model_factory if model_factory is not None else B200LlavaModel
+            base_model = factory(cfg, device=getattr(accelerator, "device", None), base_model_name_or_path=args.base_model_name)
+            checkpoint.load_llava_base(base_model.engine, args.base_model_name)
+            base_model.add_adapter("lora_policy")
+            if rank == 0:
+                os.makedirs(init_dir, exist_ok=True)
+                torch.save(base_model.adapter_state_dict("lora_policy"), os.path.join(init_dir, "adapter_model.bin"))
+                with open(os.path.join(init_dir, "adapter_config.json"), "w") as f:
+                    json.dump(dict(base_model.peft_config["lora_policy"], lora_dropout=getattr(args, "lora_dropout", 0.0),
+                                   bias=getattr(args, "lora_bias", "none")), f, indent=2, sort_keys=True)
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()
+        args.policy_model_name_or_path = init_dir
+    resume = ckpt if getattr(args, "resume_from_training", True) else None
+    models = make_models(base_model, tokenizer, args, accelerator, resume_from_checkpoint=resume, model_factory=model_factory)
+    trainer = B200DPOTrainer(args, models["policy"], models["ref_policy"], optimizer=None, world_size=world,
+                             **(trainer_kwargs or {}))
+    trainer.train(dataset_len, train_dataloader_factory, resume_training_ckpt=resume)
+    if rank == 0:
+        trainer.save_model(os.path.join(args.output_dir, "checkpoint-final"))
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    return trainer

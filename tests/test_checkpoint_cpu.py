@@ -329,6 +329,119 @@ def test_create_optimizer_and_scheduler_from_args():
     sch.step()
     opt.step(0.5)
     assert calls == [(1e-6, (0.8, 0.95), 1e-6, 0.1, 0.0, 0.5)]          # lr after one warm-up step; clip disabled -> 0
+    # `loss/grad_norm` is the norm AFTER clipping, as the reference logs it (rl_trainer.py:164-171); no clip -> the raw norm
+    eng.zero_grad = lambda: None
+    model.release_slots = lambda: None
+    eng.optimizer_step = lambda *a: torch.full((1,), 4.0)
+    assert tr._optimizer_step().item() == 4.0 and opt.last_grad_norm.item() == 4.0          # max_grad_norm None
+    opt.max_grad_norm = 1.0
+    assert abs(tr._optimizer_step().item() - 1.0) < 1e-5 and opt.last_grad_norm.item() == 4.0
+    eng.optimizer_step = lambda *a: torch.full((1,), 0.5)
+    assert tr._optimizer_step().item() == 0.5
+    opt.max_grad_norm = None
     # handed-in objects are kept (create_optimizer / create_scheduler return them unchanged)
     tr2 = B200DPOTrainer(args, SimpleNamespace(base_model=model), None, optimizer=opt, lr_scheduler=sch, loss=object())
     assert tr2.create_optimizer_and_scheduler(99) == (opt, sch)
+
+
+def test_train_opa_dpo_entry_flow(tmp_path, monkeypatch):
+    """trainer.train_opa_dpo = the model / training half of opadpo_train.train (opadpo_train.py:583-595, 727-797): LoRA from
+    scratch into <output_dir>/init_model when base == policy path, make_models on it, the training loop, checkpoint-final; a
+    second launch finds init_model and the last checkpoint and resumes. Recorder engine, stub policies' arithmetic."""
+    from types import SimpleNamespace
+    from opa_dpo_b200 import policy as P, trainer as T
+    from opa_dpo_b200.engine import EngineConfig, linear_modules
+    from opa_dpo_b200._lib import OpadpoError, OpadpoUnknownName
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    base, clip, *_ = _fake_llava(tmp_path)
+    tiny = EngineConfig(d_model=8, n_layers=1, n_heads=1, d_ffn=16, vocab=32, v_d=4, v_layers=1, v_heads=1, v_ffn=8, v_image=28,
+                        v_patch=14, lora_r=2, lora_alpha=4.0)
+    mods = linear_modules(tiny)
+    events = []
+
+    class RecEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.cfg, self.lora, self.master = tiny, {}, torch.zeros(8)
+
+        def load_tensor(self, name, t):
+            if "inv_freq" in name or "post_layernorm" in name:
+                raise OpadpoUnknownName("unknown tensor")
+
+        def lora_shape(self, module):
+            if module not in mods:
+                raise OpadpoError("not a LoRA target")
+            return mods[module]
+
+        def load_lora(self, aid, module, A, B):
+            self.lora[(aid, module)] = (A.clone(), B.clone())
+
+        def export_lora(self, aid, module):
+            return self.lora[(aid, module)]
+
+        def set_trainable(self, aid):
+            events.append(("trainable", aid))
+
+        def buffers(self):
+            return dict(master=self.master, grad=torch.zeros(8), exp_avg=torch.zeros(8), exp_avg_sq=torch.zeros(8), n_train=8, n_total=8)
+
+        def optimizer_step(self, *a):
+            events.append("opt_step")
+            return torch.ones(1)
+
+        def zero_grad(self):
+            pass
+
+        def set_option(self, *a):
+            pass
+
+        def sync_shadow(self):
+            pass
+
+    def factory(cfg, device=None, base_model_name_or_path=""):
+        events.append(("build", cfg.lora_r, cfg.lora_alpha))
+        return P.B200LlavaModel(tiny, base_model_name_or_path=base_model_name_or_path, engine=RecEngine())
+
+    class Trainer(T.B200DPOTrainer):      # the step itself is covered elsewhere: record it, advance the optimizer / scheduler
+        def step(self, loader, step_idx=0):
+            events.append(("step", step_idx))
+            for _ in range(self.args.rollout_accumulation_steps):
+                next(loader)
+            self.optimizer.step(1.0)
+            self.lr_scheduler.step()
+            return {}
+    monkeypatch.setattr(T, "B200DPOTrainer", Trainer)
+    out = tmp_path / "out"
+    args = SimpleNamespace(output_dir=str(out), resume_dir=None, base_model_name=base, policy_model_name_or_path=base, lora_r=2,
+                           lora_alpha=4.0, resume_from_training=True, total_epochs=1, rollout_batch_size=2,
+                           rollout_accumulation_steps=1, save_steps=2, save_steps_extra_list=[], eval_steps=None, max_step=10,
+                           learning_rate=1e-5, warmup_steps=1, temperature=1.0, response_len=4, loss_type="sigmoid",
+                           f_divergence_type="reverse_kl")
+    import itertools
+    tr = T.train_opa_dpo(args, SimpleNamespace(pad_token_id=0, eos_token_id=2), 8, lambda: itertools.cycle([{}]),
+                         accelerator=SimpleNamespace(device=torch.device("cpu")), model_factory=factory, trainer_kwargs=dict(loss=object()))
+    init = out / "init_model"
+    assert (init / "adapter_model.bin").exists() and args.policy_model_name_or_path == str(init)
+    cfgj = json.load(open(init / "adapter_config.json"))
+    assert cfgj["r"] == 2 and cfgj["lora_alpha"] == 4.0 and cfgj["base_model_name_or_path"] == base and cfgj["bias"] == "none"
+    sd = torch.load(init / "adapter_model.bin")
+    m0 = next(iter(mods))
+    assert (sd[f"base_model.model.{m0}.lora_B.weight"] == 0).all() and sd[f"base_model.model.{m0}.lora_A.weight"].abs().max() > 0
+    eng = tr.model.engine
+    assert torch.equal(eng.lora[(P.POLICY, m0)][0], eng.lora[(P.REF, m0)][0])           # both adapters start from init_model
+    assert [e for e in events if e[0] == "build"] == [("build", 2, 4.0)]                 # ONE base for everything
+    assert [e for e in events if isinstance(e, tuple) and e[0] == "step"] == [("step", i) for i in (1, 2, 3, 4)]   # 8 / 2 steps
+    assert sorted(os.listdir(out)) == ["checkpoint-2", "checkpoint-4", "checkpoint-final", "init_model"]
+    assert (out / "checkpoint-final" / "adapter_model" / "lora_policy" / "adapter_model.bin").exists()
+    assert (out / "checkpoint-final" / "optimizer.pt").exists() and not (out / "checkpoint-4" / "optimizer.pt").exists()
+
+    # second launch: init_model is reused (no rebuild of a fresh adapter), the run resumes from checkpoint-4: steps 1-3 skipped
+    events.clear()
+    args2 = SimpleNamespace(**{**vars(args), "policy_model_name_or_path": base})
+    (out / "checkpoint-4" / "optimizer.pt").write_bytes((out / "checkpoint-final" / "optimizer.pt").read_bytes())
+    tr2 = T.train_opa_dpo(args2, SimpleNamespace(pad_token_id=0, eos_token_id=2), 8, lambda: itertools.cycle([{}]),
+                          accelerator=SimpleNamespace(device=torch.device("cpu")), model_factory=factory, trainer_kwargs=dict(loss=object()))
+    assert [e for e in events if isinstance(e, tuple) and e[0] == "step"] == [("step", 4)]
+    assert args2.policy_model_name_or_path == str(init) and tr2.optimizer.step_count == 4 + 1
