@@ -270,3 +270,60 @@ def make_grad_allreduce(engine, flat_grad: torch.Tensor, group=None):
     fb._keep_alive = impl
     fb.fallback_reason = why or "another rank could not map the symmetric buffers"
     return fb
+
+
+# ------------------------------------------------------------------------------------------------ sharded input pipeline
+class InfiniteLoader:
+    """utils/common_utils.py:174-187: `next()` forever, restarting the wrapped loader (a new shuffled epoch) when it ends."""
+
+    def __init__(self, loader):
+        self.loader = loader
+        self.iterator = iter(loader)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        try:
+            return next(self.iterator)
+        except StopIteration:
+            self.iterator = iter(self.loader)
+            return next(self.iterator)
+
+
+class ShardedBatchSampler:
+    """What `accelerator.prepare(DataLoader(shuffle=True, drop_last=True))` does to the batch sampler (rl_trainer.py:314-321,
+    opadpo_train.py:598-603 `even_batches=True, split_batches=False`) [UPSTREAM accelerate 0.21 BatchSamplerShard]: all
+    ranks walk the SAME shuffled sequence of batches, rank r keeps batch i when i % world == r, and a batch is only yielded
+    once its whole round of `world` batches exists — so every rank sees the same number of equally sized batches and the
+    pairs of one step are disjoint across ranks. The ranks agree on the permutation without communicating because each
+    builds the sampler's generator from the same seed (accelerate broadcasts rank 0's generator state instead)."""
+
+    def __init__(self, batch_sampler, rank: int, world: int):
+        if not 0 <= rank < world:
+            raise ValueError(f"rank {rank} outside world {world}")
+        self.batch_sampler, self.rank, self.world = batch_sampler, rank, world
+
+    def __len__(self):
+        return len(self.batch_sampler) // self.world
+
+    def __iter__(self):
+        mine = None
+        for i, batch in enumerate(self.batch_sampler):
+            if i % self.world == self.rank:
+                mine = batch
+            if i % self.world == self.world - 1:
+                yield mine
+                mine = None
+
+
+def get_train_dataloader(train_dataset, data_collator, per_device_batch_size: int, rank: int = 0, world: int = 1, seed: int = 0,
+                         num_workers: int = 0) -> InfiniteLoader:
+    """RLTrainer.get_train_dataloader (rl_trainer.py:309-323): shuffled, drop_last, collated batches of
+    `rollout_per_device_batch_size` samples, sharded over the ranks as accelerate would, wrapped in an InfiniteLoader."""
+    from torch.utils.data import BatchSampler, DataLoader, RandomSampler
+    gen = torch.Generator().manual_seed(int(seed))
+    sampler = BatchSampler(RandomSampler(train_dataset, generator=gen), batch_size=per_device_batch_size, drop_last=True)
+    loader = DataLoader(train_dataset, batch_sampler=ShardedBatchSampler(sampler, rank, world), collate_fn=data_collator,
+                        num_workers=num_workers)
+    return InfiniteLoader(loader)

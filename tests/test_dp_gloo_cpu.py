@@ -180,3 +180,31 @@ def test_nvl_allreduce_launch_plan_covers_the_bucket_exactly_once(n_layers, grou
     for layer in list(range(n_layers - 1, -1, -1)) + [n_layers]:
         ar3._on_layer(layer)
     assert calls3 == []
+
+
+def test_sharded_train_dataloader_partitions_each_round():
+    """dist.get_train_dataloader: every rank walks the same shuffled batch sequence and keeps its share of each complete round
+    (accelerate's BatchSamplerShard with even_batches / drop_last, rl_trainer.py:309-323): equal batch counts, disjoint
+    samples inside a round, the un-sharded order preserved, a fresh permutation per epoch through the InfiniteLoader."""
+    from torch.utils.data import BatchSampler, RandomSampler
+    from opa_dpo_b200.dist import ShardedBatchSampler, get_train_dataloader
+    data = list(range(23))
+    collate = lambda items: torch.tensor(items)
+    world, bs = 3, 2
+    ref_gen = torch.Generator().manual_seed(5)
+    plain = BatchSampler(RandomSampler(data, generator=ref_gen), batch_size=bs, drop_last=True)
+    epoch1, epoch2 = list(plain), list(plain)             # 11 batches each -> 3 complete rounds of 3
+    loaders = [get_train_dataloader(data, collate, bs, rank=r, world=world, seed=5) for r in range(world)]
+    got = [[next(l).tolist() for _ in range(6)] for l in loaders]          # two epochs of 3 batches per rank
+    for r in range(world):
+        assert got[r][:3] == [epoch1[k * world + r] for k in range(3)]
+        assert got[r][3:] == [epoch2[k * world + r] for k in range(3)]
+    for k in range(6):
+        round_items = [x for r in range(world) for x in got[r][k]]
+        assert len(set(round_items)) == world * bs                          # one step's pairs are disjoint across ranks
+    assert epoch1 != epoch2
+    assert len(ShardedBatchSampler(plain, 0, world)) == 3
+    single = get_train_dataloader(data, collate, bs, seed=5)
+    assert [next(single).tolist() for _ in range(11)] == epoch1               # world 1 = the plain shuffled loader
+    with pytest.raises(ValueError):
+        ShardedBatchSampler(plain, 3, 3)
