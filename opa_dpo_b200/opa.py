@@ -178,3 +178,29 @@ class OPAStepper:
         norm = self.opt.step(grad_scale)
         self.opt.zero_grad()
         return loss.detach(), norm
+
+
+def save_final_checkpoint(model, output_dir: str, adapter_name: str = "lora_policy", is_main_process: bool = True) -> Optional[str]:
+    """The OPA stage's final save (opa_train.py:553-561): `<output_dir>/checkpoint-final/{adapter_model.bin,
+    adapter_config.json, non_lora_trainables.bin, config.json}` — PEFT's flat single-adapter layout, which is what the DPO
+    stage's `policy_model_name_or_path` points at (qlora_model.py:318-328; `policy.make_models` reads it back).
+    `non_lora_trainables.bin` holds the trainable tensors that are not LoRA (get_peft_state_non_lora_maybe_zero_3): none here,
+    everything but the adapters is frozen, so it is the empty dict the reference writes in the same situation. `config.json`
+    is the base model's, copied from `model.base_model_name_or_path` when that directory has one."""
+    import json
+    import os
+    import shutil
+    if not is_main_process:
+        return None
+    final = os.path.join(output_dir, "checkpoint-final")
+    os.makedirs(final, exist_ok=True)
+    torch.save(model.adapter_state_dict(adapter_name), os.path.join(final, "adapter_model.bin"))
+    cfg = dict(model.peft_config.get(adapter_name) or model.default_peft_config())
+    cfg["inference_mode"] = True
+    with open(os.path.join(final, "adapter_config.json"), "w") as f:
+        json.dump(cfg, f, indent=2, sort_keys=True)
+    torch.save({}, os.path.join(final, "non_lora_trainables.bin"))
+    src = os.path.join(getattr(model, "base_model_name_or_path", "") or "", "config.json")
+    if os.path.isfile(src):
+        shutil.copyfile(src, os.path.join(final, "config.json"))
+    return final

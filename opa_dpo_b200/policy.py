@@ -22,7 +22,9 @@ from torch import Tensor, nn
 from .engine import BASE, POLICY, REF, Engine, EngineConfig, linear_modules
 from ._lib import OpadpoError, OpadpoUnknownName
 
-ADAPTER_IDS = {"lora_policy": POLICY, "lora_ref_policy": REF, "lora_default": POLICY, None: BASE}
+# "default" is PEFT's name for the single adapter of the OPA LoRA-SFT stage (opa_train.py:466-484) and the default of
+# make_policy_with_base_model (rl_models.py:193-204); it occupies the trainable slot like lora_policy
+ADAPTER_IDS = {"lora_policy": POLICY, "lora_ref_policy": REF, "lora_default": POLICY, "default": POLICY, None: BASE}
 
 
 class _PolicyForward(torch.autograd.Function):

@@ -445,3 +445,68 @@ def test_train_opa_dpo_entry_flow(tmp_path, monkeypatch):
                           accelerator=SimpleNamespace(device=torch.device("cpu")), model_factory=factory, trainer_kwargs=dict(loss=object()))
     assert [e for e in events if isinstance(e, tuple) and e[0] == "step"] == [("step", 4)]
     assert args2.policy_model_name_or_path == str(init) and tr2.optimizer.step_count == 4 + 1
+
+
+def test_opa_stage_final_checkpoint_feeds_the_dpo_stage(tmp_path):
+    """opa.save_final_checkpoint writes the OPA stage's output layout (opa_train.py:553-561) and policy.make_models — the DPO
+    stage's loader (qlora_model.py:318-328) — reads exactly that directory back as both adapters' starting point."""
+    from types import SimpleNamespace
+    from opa_dpo_b200 import opa, policy as P
+    from opa_dpo_b200.engine import EngineConfig, linear_modules
+    from opa_dpo_b200._lib import OpadpoError, OpadpoUnknownName
+    base, clip, *_ = _fake_llava(tmp_path)
+    tiny = EngineConfig(d_model=8, n_layers=1, n_heads=1, d_ffn=16, vocab=32, v_d=4, v_layers=1, v_heads=1, v_ffn=8, v_image=28,
+                        v_patch=14, lora_r=2, lora_alpha=4.0)
+    mods = linear_modules(tiny)
+
+    class RecEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.cfg, self.lora = tiny, {}
+
+        def load_tensor(self, name, t):
+            if "inv_freq" in name or "post_layernorm" in name:
+                raise OpadpoUnknownName("unknown tensor")
+
+        def lora_shape(self, module):
+            if module not in mods:
+                raise OpadpoError("not a LoRA target")
+            return mods[module]
+
+        def load_lora(self, aid, module, A, B):
+            self.lora[(aid, module)] = (A.clone().float(), B.clone().float())
+
+        def export_lora(self, aid, module):
+            return self.lora[(aid, module)]
+
+        def set_trainable(self, aid):
+            pass
+
+        def buffers(self):
+            return dict(master=torch.zeros(8), grad=torch.zeros(8), n_train=8)
+
+    factory = lambda cfg, device=None, base_model_name_or_path="": P.B200LlavaModel(tiny, base_model_name_or_path=base_model_name_or_path,
+                                                                                   engine=RecEngine())
+    sft = factory(None, base_model_name_or_path=base)
+    sft.add_adapter("default", is_trainable=True, generator=torch.Generator().manual_seed(3))     # PEFT's single OPA adapter
+    m0 = next(iter(mods))
+    A0, _ = sft.engine.lora[(P.POLICY, m0)]
+    sft.engine.lora[(P.POLICY, m0)] = (A0, torch.full((mods[m0][0], 2), 0.25))                    # "trained"
+    final = opa.save_final_checkpoint(sft, str(tmp_path / "opa_out"), adapter_name="default")
+    assert sorted(os.listdir(final)) == ["adapter_config.json", "adapter_model.bin", "config.json", "non_lora_trainables.bin"]
+    assert torch.load(os.path.join(final, "non_lora_trainables.bin")) == {}
+    cfgj = json.load(open(os.path.join(final, "adapter_config.json")))
+    assert cfgj["base_model_name_or_path"] == base and cfgj["r"] == 2 and cfgj["inference_mode"] is True
+    assert opa.save_final_checkpoint(sft, str(tmp_path / "nope"), is_main_process=False) is None and not (tmp_path / "nope").exists()
+
+    args = SimpleNamespace(policy_model_name_or_path=final, base_model_name=base, temperature=1.0, response_len=4)
+    out = P.make_models(None, SimpleNamespace(pad_token_id=0, eos_token_id=2), args, None, model_factory=factory)
+    eng = out["policy"].base_model.engine
+    for aid in (P.POLICY, P.REF):
+        A, B = eng.lora[(aid, m0)]
+        assert torch.equal(A, A0.to(torch.bfloat16).float()) and (B == 0.25).all()                # adapter_model.bin is bf16, as PEFT's
+    # the reference's default adapter name resolves (rl_models.py:193-204 `adapter_name="default"`)
+    pol = P.make_policy_with_base_model(args, out["policy"].base_model, None)
+    assert pol.adapter_name == "default"
+    out["policy"].base_model.set_adapter("default")
