@@ -388,3 +388,16 @@ class B200DPODataset:
                 "original_generate_response": item["original_generate_response"],
                 "AI_pseudo_response": item["AI_pseudo_response"],
                 "AI_json_report": item["AI_json_report"]}
+
+
+def make_dpo_data_module(tokenizer, args, data_args, device=None, ops=None) -> Dict:
+    """make_dpo_data_module (utils/data_utils_dpo.py:353-370), same signature and keys: the HF `datasets` directory at
+    `data_args.data_path` (`load_from_disk`; columns of base_operations/make_opadpo_dataset.py:111-128), wrapped by the dataset
+    mirror, and the collator with the reference's hard-coded lengths (query 128, response 896, :363-365) and
+    `args.detailed_report`. Whether images are padded to a square follows `data_args.image_aspect_ratio == "pad"` (:320)."""
+    from datasets import load_from_disk
+    dataset = load_from_disk(data_args.data_path)
+    pad = getattr(data_args, "image_aspect_ratio", "pad") == "pad"
+    collator = B200DataCollator(tokenizer=tokenizer, query_len=128, response_len=896, detailed_report=args.detailed_report,
+                                device=device, pad_to_square=pad, ops=ops)
+    return dict(train_dataset=B200DPODataset(dataset), eval_dataset=None, data_collator=collator)

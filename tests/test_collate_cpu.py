@@ -527,3 +527,47 @@ def test_host_mirror_dataset_vs_reference_dataset(tmp_path, monkeypatch):
         assert np.array_equal(C.clip_preprocess(m["images"], 56, True), want.astype(np.float32)), i
     with pytest.raises(ValueError):
         B200DPODataset([{"queries": "q", **text}])[0]
+
+
+def test_make_dpo_data_module_vs_reference(tmp_path, monkeypatch):
+    """collate.make_dpo_data_module against the reference's make_dpo_data_module (data_utils_dpo.py:353-370) run verbatim on
+    the same on-disk HF dataset: keys, dataset length and items' text fields, the collator's hard-coded 128 / 896 lengths and
+    detailed_report flag."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference")
+    import base64
+    import io
+    from types import SimpleNamespace
+    datasets = pytest.importorskip("datasets")
+    from PIL import Image
+    from transformers.models.clip.image_processing_pil_clip import CLIPImageProcessorPil
+    from oracle.make_golden import install_stubs
+    install_stubs()
+    from utils import data_utils_dpo as D
+    from opa_dpo_b200 import collate as K
+    rs = np.random.RandomState(1)
+    rows = []
+    for i in range(3):
+        buf = io.BytesIO()
+        Image.fromarray(rs.randint(0, 256, (30 + i, 44, 3)).astype(np.uint8)).save(buf, format="PNG")
+        rows.append({"queries": f"<image>\nquestion {i}?", "image_bytes": base64.b64encode(buf.getvalue()).decode(),
+                     "standard_response": f"std {i}", "original_generate_response": f"orig {i}", "AI_pseudo_response": f"ai {i}",
+                     "AI_json_report": "{}"})
+    path = str(tmp_path / "opadpo_ds")
+    datasets.Dataset.from_list(rows).save_to_disk(path)
+    proc = CLIPImageProcessorPil(size={"shortest_edge": 56}, crop_size={"height": 56, "width": 56})
+    data_args = SimpleNamespace(data_path=path, image_processor=proc, image_aspect_ratio="pad")
+    args = SimpleNamespace(detailed_report=True)
+    tok = SimpleNamespace(pad_token_id=0, eos_token_id=2)
+    want = D.make_dpo_data_module(tok, args, data_args)
+    got = K.make_dpo_data_module(tok, args, data_args, ops=object())
+    assert list(got) == list(want) == ["train_dataset", "eval_dataset", "data_collator"] and got["eval_dataset"] is None
+    assert len(got["train_dataset"]) == len(want["train_dataset"]) == 3
+    for i in range(3):
+        r, m = want["train_dataset"][i], got["train_dataset"][i]
+        assert set(r) == set(m) and all(r[k] == m[k] for k in r if k != "images")
+        assert np.array_equal(C.clip_preprocess(m["images"], 56, True), np.asarray(r["images"], dtype=np.float32))
+    cw, cg = want["data_collator"], got["data_collator"]
+    assert (cg.query_len, cg.response_len, cg.detailed_report) == (cw.query_len, cw.response_len, cw.detailed_report) == (128, 896, True)
+    assert cg.pad_to_square is True and cg.tokenizer is tok
+    assert K.make_dpo_data_module(tok, args, SimpleNamespace(data_path=path, image_aspect_ratio="square"), ops=object())["data_collator"].pad_to_square is False
