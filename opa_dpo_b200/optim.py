@@ -32,9 +32,22 @@ class B200AdamW:
 
     def step(self, grad_scale: float = 1.0):
         g = self.param_groups[0]
+        # slices the reference keeps frozen (the projector's LoRA in the DPO stage, B200LlavaModel.freeze_projector_lora): no
+        # gradient -> outside the norm, moments stay zero, no Adam update; decoupled weight decay would still shrink them, so
+        # with a non-zero decay their weights are put back afterwards
+        frozen = [(o, c) for o, c in getattr(self.model, "frozen_grad_ranges", ())]
+        keep = []
+        for off, cnt in frozen:
+            self.model.flat_param.grad[off:off + cnt].zero_()
+            if g["weight_decay"]:
+                keep.append((off, cnt, self.model.flat_param.data[off:off + cnt].clone()))
         # max_grad_norm None = no clipping (rl_trainer.py:164: `if self.args.max_grad_norm is not None`); the kernel skips the clip at 0
         self.last_grad_norm = self.model.engine.optimizer_step(g["lr"], g["betas"], g["eps"], g["weight_decay"],
                                                                0.0 if self.max_grad_norm is None else self.max_grad_norm, grad_scale)
+        if keep:
+            for off, cnt, w in keep:
+                self.model.flat_param.data[off:off + cnt].copy_(w)
+            self.model.engine.sync_shadow()
         self.step_count += 1
         return self.last_grad_norm
 

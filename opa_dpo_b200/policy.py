@@ -79,6 +79,7 @@ class B200LlavaModel(nn.Module):
         self._slot_busy = [False, False]     # the engine keeps the activations of at most two undifferentiated forwards
         self._slot_gen = [0, 0]              # bumped at every hand-out, so a stale backward / finaliser is recognised
         self._passthrough: Dict[str, Dict[str, Tensor]] = {}   # adapter tensors the engine does not execute (CLIP layer 24)
+        self.frozen_grad_ranges = []         # (offset, count) slices of the gradient bucket that must not train
 
     # ---- adapters
     def set_adapter(self, name: Optional[str]):
@@ -97,6 +98,16 @@ class B200LlavaModel(nn.Module):
         self.flat_param = nn.Parameter(v["master"][: v["n_train"]], requires_grad=True)
         self.flat_param.grad = v["grad"]
         return self.flat_param
+
+    def freeze_projector_lora(self):
+        """The DPO stage freezes the projector — its LoRA tensors included — next to the vision tower
+        (`policy_mm_projector.requires_grad_(False)`, dpo_trainer.py:1019-1029): the optimizer never sees them and they are
+        saved unchanged. The engine differentiates the projector's LoRA like every other (the OPA stage trains it,
+        opa_train.py:496-497), so here its slice of the gradient bucket is declared frozen: B200AdamW clears it before the
+        fused clip + AdamW step, which keeps it out of the gradient norm and leaves weights and moments untouched."""
+        rng = tuple(self.engine.layer_grad_range(self.cfg.n_layers))
+        if rng[1] > 0 and rng not in self.frozen_grad_ranges:
+            self.frozen_grad_ranges.append(rng)
 
     def default_peft_config(self) -> dict:
         mods = sorted({m.split(".")[-1] for m in linear_modules(self.cfg)})
@@ -329,7 +340,8 @@ def make_models(base_model, tokenizer, args, accelerator=None, num_new_tokens: i
       LoRA rank / alpha are the ones it records; ONE base is shared by both adapters (REGISTERED_BASE_MODELS);
     * `args.train_from_sft` (default True): both adapters start from the checkpoint's weights, `lora_policy` trainable and
       `lora_ref_policy` frozen; False: both are freshly initialised with the recorded LoRA config (qlora_model.py:92-113);
-    * afterwards the vision tower / projector tensors are re-read from `args.base_model_name`
+    * the vision tower and the projector are frozen, LoRA tensors included (:1016-1029; `freeze_projector_lora`), then their
+      base tensors are re-read from `args.base_model_name`
       (`loading_vision_tower_parameter`, opadpo_train.py:539-557), when that is another directory than the base.
     `base_model`: an already-loaded B200LlavaModel to reuse (None builds one on `accelerator.device`); there is no
     `accelerator.prepare` — data parallelism is dist.py's. New tokens (smart_tokenizer_and_embedding_resize, :934-955) are
@@ -337,6 +349,8 @@ def make_models(base_model, tokenizer, args, accelerator=None, num_new_tokens: i
     from . import checkpoint
     if num_new_tokens > 0:
         raise OpadpoError("make_models: num_new_tokens > 0 needs trainable, resized embeddings; the engine trains LoRA tensors only")
+    if getattr(args, "vision_tower", "different") != "different":
+        raise NotImplementedError("make_models: only vision_tower == 'different' exists (dpo_trainer.py:1016-1031)")
     adapter_dir = checkpoint.resolve_adapter_dir(args.policy_model_name_or_path)
     policy_dir = adapter_dir
     if resume_from_checkpoint:
@@ -358,6 +372,7 @@ def make_models(base_model, tokenizer, args, accelerator=None, num_new_tokens: i
             base_model.load_adapter(policy_dir, "lora_policy", is_trainable=True)
         else:
             base_model.add_adapter("lora_policy", is_trainable=True, peft_config=lora_cfg)
+    base_model.freeze_projector_lora()       # :1019-1029; the tower itself runs without gradients in the engine
     tower_src = getattr(args, "base_model_name", None)
     if tower_src and os.path.abspath(tower_src.rstrip("/")) != os.path.abspath(base_path.rstrip("/")):
         for name, t in checkpoint.iter_checkpoint_tensors(tower_src, lambda n: "vision_tower" in n or "mm_projector" in n):

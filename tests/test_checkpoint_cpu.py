@@ -199,6 +199,10 @@ def test_make_models_mirrors_reference_construction(tmp_path):
         def set_trainable(self, aid):
             self.trainable = aid
 
+        def layer_grad_range(self, layer):
+            assert layer == tiny.n_layers            # the projector's slice
+            return 6, 2
+
         def buffers(self):
             return dict(master=torch.zeros(8), grad=torch.zeros(8), n_train=8)
 
@@ -237,6 +241,10 @@ def test_make_models_mirrors_reference_construction(tmp_path):
     assert set(eng.tensors) == (set(s1) | set(s2) | {"model.vision_tower.vision_tower." + k for k in cs if k.startswith("vision_model.")}) \
         - {"model.layers.0.self_attn.rotary_emb.inv_freq", "model.vision_tower.vision_tower.vision_model.post_layernorm.weight"}
     assert pol.base_model.peft_config["lora_policy"]["r"] == 2
+    # the DPO stage freezes the projector with its LoRA tensors (dpo_trainer.py:1016-1029): its gradient slice is declared frozen
+    assert pol.base_model.frozen_grad_ranges == [(6, 2)]
+    with pytest.raises(NotImplementedError):
+        P.make_models(None, tok, SimpleNamespace(**{**vars(args), "vision_tower": "same"}), acc, model_factory=factory)
 
     # resumed run: the policy adapter comes from <ckpt>/adapter_model/lora_policy, the reference adapter from the SFT directory
     ck = tmp_path / "checkpoint-5"
@@ -339,6 +347,27 @@ def test_create_optimizer_and_scheduler_from_args():
     eng.optimizer_step = lambda *a: torch.full((1,), 0.5)
     assert tr._optimizer_step().item() == 0.5
     opt.max_grad_norm = None
+    # frozen slices (the projector's LoRA in the DPO stage): gradient cleared before the fused step, so it is outside the norm
+    # and untouched by Adam; with weight decay the weights are put back as well
+    seen = {}
+
+    def fused(lr, betas, eps, wd, mg, scale):
+        seen["grad"] = model.flat_param.grad.clone()
+        model.flat_param.data.mul_(0.5)                       # stands for the decoupled decay touching every weight
+        return torch.ones(1)
+    eng.optimizer_step, eng.sync_shadow = fused, lambda: seen.__setitem__("synced", True)
+    model.flat_param.data.fill_(2.0)
+    model.flat_param.grad = torch.ones(4)
+    model.frozen_grad_ranges = [(1, 2)]
+    opt.step(1.0)
+    assert seen["grad"].tolist() == [1.0, 0.0, 0.0, 1.0] and model.flat_param.data.tolist() == [1.0, 2.0, 2.0, 1.0] and seen["synced"]
+    opt.param_groups[0]["weight_decay"] = 0.0                 # no decay: nothing to put back, no extra copies
+    seen.clear()
+    model.flat_param.grad = torch.ones(4)
+    opt.step(1.0)
+    assert seen["grad"].tolist() == [1.0, 0.0, 0.0, 1.0] and "synced" not in seen
+    model.frozen_grad_ranges = []
+    opt.param_groups[0]["weight_decay"] = 0.1
     # handed-in objects are kept (create_optimizer / create_scheduler return them unchanged)
     tr2 = B200DPOTrainer(args, SimpleNamespace(base_model=model), None, optimizer=opt, lr_scheduler=sch, loss=object())
     assert tr2.create_optimizer_and_scheduler(99) == (opt, sch)
@@ -383,6 +412,10 @@ def test_train_opa_dpo_entry_flow(tmp_path, monkeypatch):
 
         def set_trainable(self, aid):
             events.append(("trainable", aid))
+
+        def layer_grad_range(self, layer):
+            assert layer == tiny.n_layers            # the projector's slice
+            return 6, 2
 
         def buffers(self):
             return dict(master=self.master, grad=torch.zeros(8), exp_avg=torch.zeros(8), exp_avg_sq=torch.zeros(8), n_train=8, n_total=8)
@@ -482,6 +515,10 @@ def test_opa_stage_final_checkpoint_feeds_the_dpo_stage(tmp_path):
 
         def set_trainable(self, aid):
             pass
+
+        def layer_grad_range(self, layer):
+            assert layer == tiny.n_layers            # the projector's slice
+            return 6, 2
 
         def buffers(self):
             return dict(master=torch.zeros(8), grad=torch.zeros(8), n_train=8)
