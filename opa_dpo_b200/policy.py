@@ -176,9 +176,18 @@ class B200LlavaModel(nn.Module):
         """PeftModel.load_adapter contract used at qlora_model.py:84-88."""
         with open(os.path.join(model_id, "adapter_config.json")) as f:
             self.peft_config[adapter_name] = json.load(f)
-        r = self.peft_config[adapter_name].get("r")
+        pc = self.peft_config[adapter_name]
+        r = pc.get("r")
         if r != self.cfg.lora_r:
             raise OpadpoError(f"adapter rank {r} != engine lora_r {self.cfg.lora_r}")
+        if "lora_alpha" in pc and float(pc["lora_alpha"]) != float(self.cfg.lora_alpha):
+            raise OpadpoError(f"adapter lora_alpha {pc['lora_alpha']} != engine lora_alpha {self.cfg.lora_alpha} (the LoRA scale "
+                              "alpha / r is one engine-wide constant)")
+        if is_trainable and float(pc.get("lora_dropout") or 0.0) != 0.0:
+            raise OpadpoError(f"adapter lora_dropout {pc['lora_dropout']}: the engine trains without LoRA dropout (the recipes use "
+                              "0.0, llava_dpo.yaml:128, llava_opa.yaml:20)")
+        if pc.get("bias", "none") != "none":
+            raise OpadpoError(f"adapter bias={pc['bias']!r}: only bias='none' adapters exist in this path (qlora_model.py:244-251)")
         state = torch.load(os.path.join(model_id, "adapter_model.bin"), map_location="cpu")
         self.load_adapter_state(adapter_name, state)
         if is_trainable:

@@ -547,3 +547,29 @@ def test_opa_stage_final_checkpoint_feeds_the_dpo_stage(tmp_path):
     pol = P.make_policy_with_base_model(args, out["policy"].base_model, None)
     assert pol.adapter_name == "default"
     out["policy"].base_model.set_adapter("default")
+
+
+def test_load_adapter_refuses_configs_the_engine_cannot_honour(tmp_path):
+    """PeftModel.load_adapter's contract (qlora_model.py:84-88) for what the engine cannot express: another rank or alpha than
+    it was built with, LoRA dropout on a trainable adapter, bias terms."""
+    from opa_dpo_b200 import policy as P
+    from opa_dpo_b200.engine import EngineConfig
+    from opa_dpo_b200._lib import OpadpoError
+    from types import SimpleNamespace
+    model = P.B200LlavaModel(EngineConfig(lora_r=2, lora_alpha=4.0), engine=SimpleNamespace(device=torch.device("cpu")))
+    d = tmp_path / "ad"
+    d.mkdir()
+    torch.save({}, d / "adapter_model.bin")
+
+    def write(**kw):
+        (d / "adapter_config.json").write_text(json.dumps({"r": 2, "lora_alpha": 4.0, "lora_dropout": 0.0, "bias": "none", **kw}))
+    write()
+    model.load_adapter(str(d), "lora_ref_policy")
+    for bad in (dict(r=4), dict(lora_alpha=8.0), dict(bias="all")):
+        write(**bad)
+        with pytest.raises(OpadpoError):
+            model.load_adapter(str(d), "lora_ref_policy")
+    write(lora_dropout=0.05)
+    model.load_adapter(str(d), "lora_ref_policy")              # frozen: dropout never applies in eval mode
+    with pytest.raises(OpadpoError, match="dropout"):
+        model.load_adapter(str(d), "lora_policy", is_trainable=True)
