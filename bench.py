@@ -210,10 +210,13 @@ def run_reference_arm(args):
     sample = ("1 pair, R=512, fp32, true 7B widths, depth truncated to 2 LLaMA + 2 CLIP layers; pairs/s extrapolated to "
               "full depth by algorithmic FLOPs (%.1f TFLOP sample vs %.1f TFLOP full pair)" % (fl / 1e12, full / 1e12))
     full_depth = None
-    if not args.no_full_depth:
+    if not args.no_full_depth and args.gpus == 1:
         # one un-truncated step: configs[0] (2 pairs x 128 tokens), every layer, forward and backward — in a child process
         # behind a memory check and a time box, so that it can only ever add to the line
         full_depth = full_depth_config0_isolated(threads, args.full_depth_timeout)
+    elif not args.no_full_depth:
+        # the CPU arm does not depend on the GPU count: the N > 1 launches of a scaling run repeat the bounded sample only
+        full_depth = {"skipped": "measured by this arm's N=1 launch (bench.py --impl reference --gpus 1); the CPU path is the same at every N"}
     if full_depth and "pairs_per_s_at_R512_by_flops" in full_depth:
         # the line's value is the HIGHER of the two CPU estimates (the one less flattering to the GPU arm)
         value = max(value, full_depth["pairs_per_s_at_R512_by_flops"])
