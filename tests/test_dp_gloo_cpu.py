@@ -208,3 +208,24 @@ def test_sharded_train_dataloader_partitions_each_round():
     assert [next(single).tolist() for _ in range(11)] == epoch1               # world 1 = the plain shuffled loader
     with pytest.raises(ValueError):
         ShardedBatchSampler(plain, 3, 3)
+
+
+def test_sharded_batch_sampler_properties():
+    """For any dataset size / batch size / world: every rank gets the same number of full batches, the ranks' batches of one
+    round are the consecutive batches of the shared shuffled sequence, nothing is yielded from an incomplete round."""
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from torch.utils.data import BatchSampler, SequentialSampler
+    from opa_dpo_b200.dist import ShardedBatchSampler
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(0, 60), bs=st.integers(1, 7), world=st.integers(1, 8))
+    def check(n, bs, world):
+        base = BatchSampler(SequentialSampler(range(n)), batch_size=bs, drop_last=True)
+        full = list(base)
+        shards = [list(ShardedBatchSampler(base, r, world)) for r in range(world)]
+        rounds = len(full) // world
+        assert all(len(s) == rounds == len(ShardedBatchSampler(base, 0, world)) for s in shards)
+        for k in range(rounds):
+            assert [shards[r][k] for r in range(world)] == full[k * world:(k + 1) * world]
+    check()
